@@ -1,0 +1,224 @@
+"""ctypes binding for the CPU oracle -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.  Nothing under rminc_b200/ does.
+
+liboracle.so    : oracle/rminc_oracle.c, the plain-C restatement of
+                  src/modelling_functions.c:448-576 (voxel_lm), :1012-1175
+                  (minc2_model, "lm"), src/vertex_modelling.c:104-158 and
+                  R/minc_voxel_statistics.R:1465-1497 (mincRandomize).
+_ref/librminc_ref.so : the reference's own voxel_lm / vertex_lm_loop /
+                  minc2_model object code (built by `make ref` where
+                  /root/reference exists; see oracle/Makefile).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+_REF = os.path.join(_HERE, "_ref", "librminc_ref.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+def build(ref: bool = True) -> None:
+    """Compile liboracle.so (and _ref/ when /root/reference is present)."""
+    subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    if ref and os.path.isdir("/root/reference/src"):
+        subprocess.run(["make", "-C", _HERE, "-s", "ref"], check=True)
+
+
+def _load(path):
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    return C.CDLL(path)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build(ref=False)
+        _lib = _load(_LIB)
+        _lib.orc_voxel_lm.restype = C.c_int
+        _lib.orc_vertex_lm_loop.restype = C.c_int
+        _lib.orc_minc2_model_lm.restype = C.c_int
+        _lib.orc_randomize.restype = C.c_int
+        _lib.orc_design_probe.restype = C.c_int
+        _lib.orc_dnrm2.restype = C.c_double
+    return _lib
+
+
+def have_ref() -> bool:
+    return os.path.exists(_REF)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        _ref = _load(_REF)
+        for f in ("ref_voxel_lm", "ref_vertex_lm_loop", "ref_minc2_model_lm"):
+            getattr(_ref, f).restype = C.c_int
+    return _ref
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _F(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+class OracleError(RuntimeError):
+    """The reference raises an R error (dpotri info != 0, modelling_functions.c:551-557)."""
+
+
+def voxel_lm(y, X, use_ref=False):
+    """One voxel.  Returns dict(coef, F, t, R2, logLik, pivot, rank)."""
+    y = _f64(y)
+    X = _F(X)
+    n, p = X.shape
+    coef = np.zeros(p)
+    stats = np.zeros(p + 3)
+    pivot = np.zeros(p, dtype=np.int32)
+    if use_ref:
+        err = C.create_string_buffer(512)
+        rc = ref().ref_voxel_lm(_p(y), _p(X), C.c_int(n), C.c_int(p), _p(coef), _p(stats),
+                                pivot.ctypes.data_as(_ip), err, C.c_size_t(512))
+        if rc:
+            raise OracleError(err.value.decode())
+        rank = None
+    else:
+        rk = C.c_int(0)
+        info = lib().orc_voxel_lm(_p(y), _p(X), C.c_int(n), C.c_int(p), _p(coef), _p(stats),
+                                  pivot.ctypes.data_as(_ip), C.byref(rk))
+        if info:
+            raise OracleError(f"element ({info}, {info}) is zero, so the inverse cannot be computed")
+        rank = rk.value
+    return dict(coef=coef, F=stats[0], t=stats[1:p + 1].copy(), R2=stats[p + 1], logLik=stats[p + 2],
+                pivot=pivot, rank=rank)
+
+
+def vertex_lm_loop(Y, X, use_ref=False):
+    """Y: V x n (any layout; copied to column-major).  Returns V x (2p+3), Fortran order."""
+    Y = _F(Y)
+    X = _F(X)
+    V, n = Y.shape
+    p = X.shape[1]
+    out = np.zeros((V, 2 * p + 3), order="F")
+    if use_ref:
+        err = C.create_string_buffer(512)
+        rc = ref().ref_vertex_lm_loop(_p(Y), C.c_int64(V), C.c_int(n), _p(X), C.c_int(p), _p(out),
+                                      err, C.c_size_t(512))
+        if rc:
+            raise OracleError(err.value.decode())
+    else:
+        info = lib().orc_vertex_lm_loop(_p(Y), C.c_int64(V), C.c_int64(V), C.c_int(n), _p(X), C.c_int(p),
+                                        _p(out), C.c_int64(V))
+        if info:
+            raise OracleError(f"element ({info}, {info}) is zero, so the inverse cannot be computed")
+    return out
+
+
+def vertex_lm_loop_threads(Y, X, threads):
+    """The reference's `parallel = c("local", N)` sharding (contiguous voxel chunks,
+    R/minc_parallel.R:613-622) with N host threads (ctypes drops the GIL).  Used by
+    bench.py's cpu_baseline only.  Y must be V x n Fortran order."""
+    assert Y.flags.f_contiguous
+    X = _F(X)
+    V, n = Y.shape
+    p = X.shape[1]
+    out = np.zeros((V, 2 * p + 3), order="F")
+    L = lib()
+    bounds = np.linspace(0, V, threads + 1).astype(np.int64)
+
+    def work(g):
+        a, b = int(bounds[g]), int(bounds[g + 1])
+        if b <= a:
+            return 0
+        yoff = C.cast(C.c_void_p(Y.ctypes.data + 8 * a), _dp)
+        ooff = C.cast(C.c_void_p(out.ctypes.data + 8 * a), _dp)
+        return L.orc_vertex_lm_loop(yoff, C.c_int64(b - a), C.c_int64(V), C.c_int(n), _p(X), C.c_int(p),
+                                    ooff, C.c_int64(V))
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        rcs = list(ex.map(work, range(threads)))
+    if any(rcs):
+        raise OracleError("dpotri info != 0")
+    return out
+
+
+def minc2_model_lm(Y, sizes, X, mask=None, lo=1.0, hi=99999999.0, use_ref=False, fill=0.0):
+    """Y: V x n with V = prod(sizes) rows in file (C) order.  mask: length-V doubles or None."""
+    Y = _F(Y)
+    X = _F(X)
+    V, n = Y.shape
+    p = X.shape[1]
+    sz = (C.c_int64 * 3)(*[int(s) for s in sizes])
+    assert int(np.prod(sizes)) == V
+    out = np.zeros((V, 2 * p + 3), order="F")
+    m = None if mask is None else _f64(np.asarray(mask).reshape(-1))
+    mp = _p(m) if m is not None else None
+    if use_ref:
+        err = C.create_string_buffer(512)
+        rc = ref().ref_minc2_model_lm(_p(Y), sz, C.c_int(n), _p(X), C.c_int(p), mp, C.c_double(lo),
+                                      C.c_double(hi), _p(out), C.c_double(fill), err, C.c_size_t(512))
+        if rc:
+            raise OracleError(err.value.decode())
+    else:
+        info = lib().orc_minc2_model_lm(_p(Y), sz, C.c_int(n), _p(X), C.c_int(p), mp, C.c_double(lo),
+                                        C.c_double(hi), _p(out))
+        if info:
+            raise OracleError(f"element ({info}, {info}) is zero, so the inverse cannot be computed")
+    return out
+
+
+def randomize(Y, X, idx, cols, two_sided=True, mask=None, lo=1.0, hi=99999999.0):
+    """idx: n x R (0-based).  cols: 0-based output columns.  Returns R x len(cols)."""
+    Y = _F(Y)
+    X = _F(X)
+    V, n = Y.shape
+    p = X.shape[1]
+    idx = np.asfortranarray(idx, dtype=np.int32)
+    assert idx.shape[0] == n
+    R = idx.shape[1]
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    dist = np.zeros((R, len(cols)), order="F")
+    scratch = np.zeros(V * (2 * p + 3))
+    m = None if mask is None else _f64(np.asarray(mask).reshape(-1))
+    info = lib().orc_randomize(_p(Y), C.c_int64(V), C.c_int(n), _p(X), C.c_int(p),
+                               _p(m) if m is not None else None, C.c_double(lo), C.c_double(hi),
+                               idx.ctypes.data_as(_ip), C.c_int(R), cols.ctypes.data_as(_ip),
+                               C.c_int(len(cols)), C.c_int(1 if two_sided else 0), _p(dist), _p(scratch))
+    if info:
+        raise OracleError(f"element ({info}, {info}) is zero, so the inverse cannot be computed")
+    return dist
+
+
+def design_probe(X):
+    """pivot, rank, R (p x p upper), c = diag((R'R)^-1), dpotri info."""
+    X = _F(X)
+    n, p = X.shape
+    pivot = np.zeros(p, dtype=np.int32)
+    rank = C.c_int(0)
+    Rm = np.zeros((p, p), order="F")
+    c = np.zeros(p)
+    info = lib().orc_design_probe(_p(X), C.c_int(n), C.c_int(p), pivot.ctypes.data_as(_ip), C.byref(rank),
+                                  _p(Rm), _p(c))
+    return dict(pivot=pivot, rank=rank.value, R=Rm, c=c, info=info)
