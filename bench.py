@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Benchmark of the voxel-wise OLS hot path (BASELINE.json metric: mincLm voxels/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path (one whole mincLm fit) over one batch of synthetic
+input.  Workload at N = 1: BASELINE config 2 -- mincLm(y ~ group + age + sex) on 500 synthetic
+180x252x156 volumes (V = 7,076,160 voxels, n = 500, p = 4, FP64, no mask), Y resident in HBM
+when the timed region starts.  Under torchrun (N > 1) every rank fits its own V-voxel shard
+(weak scaling: the path shards over voxels with no data-path collective) and rank 0 prints
+the ONE JSON line.  Extra keys: roofline (HBM), cpu_baseline (the oracle port on this box's
+host cores), e2e (host buffers through the C ABI, H2D/D2H inside the timed region), clocks,
+gpu_launches, and `randomize` (mincRandomize permutations/s, voxel-sharded, strong scaling,
+one NCCL max all-reduce).
+
+`--impl reference` times the reference's own CPU implementation of the path (oracle/_ref when
+it was built from /root/reference, else the oracle port) with all host cores, forked over
+contiguous voxel chunks exactly as mincLm(parallel = c("local", N)) does.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIMS = (180, 252, 156)
+N_SUBJ = 500
+P = 4
+METRIC = "mincLm voxels/s"
+UNIT = "voxels/s"
+WORKLOAD = "mincLm(y ~ group + age + sex), 500 x 180x252x156 volumes (V=7076160, n=500, p=4, FP64, no mask)"
+
+
+def design(n=N_SUBJ, seed=1):
+    rng = np.random.default_rng(seed)
+    group = (np.arange(n) % 2).astype(float)
+    age = np.round(rng.normal(60, 10, n), 1)
+    sex = rng.integers(0, 2, n).astype(float)
+    return np.column_stack([np.ones(n), group, age, sex])
+
+
+# --------------------------------------------------------------------------- CPU reference
+def _cpu_worker(args):
+    kind, a, b = args
+    from oracle import oracle as O
+    Y, X, out = _cpu_worker.Y, _cpu_worker.X, _cpu_worker.out
+    if b <= a:
+        return 0
+    res = O.vertex_lm_loop(Y[a:b], X, use_ref=(kind == "reference"))
+    out[a:b] = res
+    return b - a
+
+
+def cpu_reference_run(sample_V, procs, steps=1, warmup=0, seed=0):
+    """Times the reference's CPU path on `sample_V` voxels of the benchmark workload with
+    `procs` forked workers over contiguous voxel chunks (R/minc_voxel_statistics.R:865-873).
+    Returns (voxels_per_s, kind, seconds_per_step)."""
+    import multiprocessing as mp
+    from oracle import oracle as O
+    O.build(ref=True)
+    kind = "reference" if O.have_ref() else "port"
+    rng = np.random.default_rng(seed)
+    X = design()
+    Y = np.asfortranarray(0.2 * rng.standard_normal((sample_V, N_SUBJ)))
+    shm = mp.RawArray("d", sample_V * (2 * P + 3))
+    out = np.frombuffer(shm, dtype=np.float64).reshape(sample_V, 2 * P + 3)
+    _cpu_worker.Y, _cpu_worker.X, _cpu_worker.out = Y, X, out
+    bounds = np.linspace(0, sample_V, procs + 1).astype(int)
+    tasks = [(kind, int(bounds[g]), int(bounds[g + 1])) for g in range(procs)]
+    ctx = mp.get_context("fork")
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        with ctx.Pool(procs) as pool:       # a fresh fork per call, as mclapply does
+            done = sum(pool.map(_cpu_worker, tasks))
+        dt = time.perf_counter() - t0
+        assert done == sample_V
+        if it >= warmup:
+            times.append(dt)
+    assert np.isfinite(out[:, 0]).all()
+    sec = float(np.mean(times))
+    return sample_V / sec, kind, sec
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample_V = int(os.environ.get("RMG_BENCH_CPU_SAMPLE", 60000 * cores))
+    vps, kind, sec = cpu_reference_run(sample_V, cores, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n": N_SUBJ, "p": P},
+        "cpu_baseline": {"value": vps, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{sample_V} contiguous voxels of the workload per step, in memory (no MINC I/O), "
+                                   f"{cores} forked workers over contiguous chunks like mincLm(parallel=c('local',{cores}))"},
+        "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[6]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def gen_Y(torch, V, n, device, seed, mean=0.0, sd=0.2):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    Yt = torch.empty((n, V), dtype=torch.float64, device=device)
+    for j0 in range(0, n, 20):
+        j1 = min(n, j0 + 20)
+        Yt[j0:j1].normal_(mean, sd, generator=g)
+    return Yt
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from rminc_b200 import build
+    build.build()
+    from rminc_b200 import core, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if core.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; rminc_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    V = int(np.prod(DIMS)) if not args.small else 64 * 1024
+    n, p = N_SUBJ, P
+    X = design()
+    Yt = gen_Y(torch, V, n, dev, seed=1 + rank)
+    out = torch.empty((2 * p + 3, V), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    # ---- timed region 1: Y resident in HBM
+    for _ in range(args.warmup):
+        core.lm_fit_torch(Yt, X, out=out)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = core.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        core.lm_fit_torch(Yt, X, out=out)
+        ev[i + 1].record(stream)
+    barrier()
+    launches = core.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * V * args.steps / (total_ms * 1e-3)
+
+    # roofline of the dominant (only) kernel: algorithmic bytes per launch / its launch duration
+    alg_bytes = V * (8 * n + 8 * (2 * p + 3))
+    kern_ms = float(np.mean(step_ms))            # one fit kernel per step; the 2 tiny H2D copies precede it
+    peak, peak_src = measured_hbm_peak()
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel": "lm_fit_tma_kernel<4,8,8,4>", "kernel_ms": kern_ms}
+
+    # ---- masked variant (ellipsoid, ~38 % inside), reported beside the headline
+    masked = None
+    if rank == 0 and not args.small and not args.skip_extras:
+        z, y, x = np.meshgrid(*[np.arange(d) for d in DIMS], indexing="ij")
+        c = [(d - 1) / 2 for d in DIMS]
+        inside = sum(((a - cc) / (0.45 * d)) ** 2 for a, cc, d in zip((z, y, x), c, DIMS)) <= 1
+        mt = torch.from_numpy(inside.reshape(-1).astype(np.float64)).to(dev)
+        core.lm_fit_torch(Yt, X, mask=mt, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            core.lm_fit_torch(Yt, X, mask=mt, out=out)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        fin = float(inside.mean())
+        mb = V * (8 + 8 * (2 * p + 3)) + int(inside.sum()) * 8 * n
+        masked = {"inside_frac": fin, "ms_per_step": ms, "voxels_per_s": V / (ms * 1e-3),
+                  "achieved_gbs": mb / (ms * 1e-3) / 1e9}
+        del mt
+
+    # ---- mincRandomize (config 4): voxel-sharded, all ranks evaluate every permutation, one all-reduce(MAX)
+    rand = None
+    if not args.skip_extras:
+        Rn = args.perms
+        a, b = parallel.my_shard(V, rank, world)
+        Ys = Yt[:, a:b]
+        rng = np.random.default_rng(4)
+        idx = np.column_stack([rng.permutation(n) for _ in range(Rn)]).astype(np.int32)
+        cols = list(range(p + 2, 2 * p + 2))
+        parallel.randomize_sharded(Ys, X, idx[:, :8], cols)       # warm-up
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        d = parallel.randomize_sharded(Ys, X, idx, cols)
+        e1.record(stream)
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+        flops = 2.0 * p * n * V * Rn
+        rand = {"metric": "mincRandomize permutations/s", "value": Rn / (ms * 1e-3), "unit": "perms/s", "R": Rn,
+                "n_gpus": world, "scaling": "strong", "ms": ms, "path": os.environ.get("RMG_PERM_PATH", "gemm"),
+                "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+                "null_95pct_t": [float(x) for x in np.quantile(d.cpu().numpy(), 0.95, axis=1)]}
+        if rank == 0:
+            # FP64 denominator: cuBLAS DGEMM measured in this very run
+            A = torch.randn((4096, 4096), dtype=torch.float64, device=dev)
+            B = torch.randn((4096, 4096), dtype=torch.float64, device=dev)
+            for _ in range(2):
+                A @ B
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(5):
+                A @ B
+            e1.record(stream)
+            torch.cuda.synchronize()
+            rand["dgemm_peak_tflops"] = 5 * 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+            rand["frac_of_dgemm"] = rand["algorithmic_tflops"] / world / rand["dgemm_peak_tflops"]
+            del A, B
+
+    # ---- timed region 2: end to end through the C ABI with HOST buffers (pinned), rank-local
+    e2e = None
+    if not args.skip_extras:
+        import psutil
+        avail = psutil.virtual_memory().available
+        need = V * n * 8
+        Ve = V if avail > need * world * 1.3 + (8 << 30) else max(1024, int((avail / world * 0.5) // (8 * n)) // 1024 * 1024)
+        Ve = min(Ve, V)
+        hY = torch.empty((n, Ve), dtype=torch.float64, pin_memory=True)
+        hY.copy_(Yt[:, :Ve])
+        hO = torch.empty((2 * p + 3, Ve), dtype=torch.float64, pin_memory=True)
+        Yh = hY.numpy().T            # V x n, Fortran order, zero-copy
+        Oh = hO.numpy().T
+        assert Yh.flags.f_contiguous and Oh.flags.f_contiguous
+        from rminc_b200 import _lib
+        lib = _lib.load()
+        err = _lib.errbuf()
+
+        def e2e_step():
+            rc = lib.rmg_lm_fit(Yh.ctypes.data, Ve, Ve, n, np.asfortranarray(X).ctypes.data, p, None, 1.0, 99999999.0,
+                                Oh.ctypes.data, Ve, local_rank, err, len(err))
+            _lib.check(rc, err)
+
+        e2e_step()
+        ksteps = max(1, min(args.steps, 3))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * Ve * ksteps / dt, "unit": UNIT, "h2d_bytes_per_step": Ve * n * 8 + n * p * 8,
+               "d2h_bytes_per_step": Ve * (2 * p + 3) * 8, "steps": ksteps, "voxels_per_step_per_gpu": Ve,
+               "api": "rmg_lm_fit (C ABI, pinned host Y -> chunked H2D -> kernel -> D2H result)",
+               "kernel_ms_inside": core.last_kernel_ms()}
+        # sanity: the end-to-end result equals the device-resident result
+        chk = torch.from_numpy(np.ascontiguousarray(Oh[:4096].T)).to(dev)
+        assert torch.equal(torch.nan_to_num(chk), torch.nan_to_num(out[:, :4096])), "e2e result differs from device result"
+        del hY, hO
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_extras and not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        sample_V = int(os.environ.get("RMG_BENCH_CPU_SAMPLE", 60000 * cores))
+        vps, kind, sec = cpu_reference_run(sample_V, cores)
+        cpu = {"value": vps, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{sample_V} voxels of the workload (n=500, p=4), in memory, {cores} forked workers "
+                         f"over contiguous chunks; {sec:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD if not args.small else "SMALL SMOKE CONFIG (not a bench line)",
+                       "voxels_per_gpu": V, "n": n, "p": p,
+                       "l2": "inputs (28.3 GB per GPU) are far larger than the 126 MB L2; no flush needed",
+                       "sharding": "contiguous voxel shards, no data-path collective"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
+            "masked_variant": masked, "randomize": rand,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--perms", type=int, default=256, help="permutations timed for the randomize line")
+    ap.add_argument("--small", action="store_true", help="tiny smoke configuration (not a bench line)")
+    ap.add_argument("--skip-extras", action="store_true", help="only the device-resident headline")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,153 @@
+/*
+ * rminc_b200.h -- C ABI of the B200-native voxel-wise OLS hot path of RMINC.
+ *
+ * Plain C, plain pointers and sizes; no R, torch or CUDA types.  Every entry
+ * point is what RMINC's own .Call boundary for this path would bind
+ * (reference: src/RMINC_init.c:57-82).  All matrices are column-major (R
+ * layout).  There is NO CPU fallback: without a CUDA device every compute
+ * entry point returns RMG_ERR_NO_DEVICE.
+ *
+ * Result matrix layout (reference: src/modelling_functions.c:1159-1174,
+ * src/vertex_modelling.c:144-157): V rows x (2p+3) columns,
+ *   col 0 = F-statistic, col 1 = R-squared, cols 2..p+1 = beta (pivoted order,
+ *   zeros after the numerical rank), cols p+2..2p+1 = t-statistics,
+ *   col 2p+2 = logLik.
+ * Rows outside the mask are +0.0 in every column (reference:
+ * R/minc_voxel_statistics.R:898-905, src/minc_anova.c:270-275).
+ *
+ * Errors: functions return RMG_OK or a code below and write a NUL-terminated
+ * message into err (if err != NULL and errlen > 0).  Nothing is thrown or
+ * longjmp'd across the boundary; all device and pinned memory allocated inside
+ * a call is released before it returns.
+ */
+#ifndef RMINC_B200_H
+#define RMINC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMG_OK 0
+#define RMG_ERR_INVALID 1    /* bad argument (NULL pointer, n <= p, p > RMG_MAX_P ...) */
+#define RMG_ERR_SINGULAR 2   /* dpotri info > 0: "element (i, i) is zero, so the inverse cannot be
+                                computed" -- the reference aborts the whole call with an R error
+                                (src/modelling_functions.c:551-557) */
+#define RMG_ERR_CUDA 3       /* a CUDA runtime/driver call failed */
+#define RMG_ERR_NO_DEVICE 4  /* no CUDA device / device index out of range */
+
+#define RMG_MAX_P 32         /* largest supported number of design columns */
+
+/* Library / environment probes (never touch the GPU beyond a device count). */
+int rmg_version(void);
+int rmg_device_count(void);
+int rmg_max_p(void);
+
+/*
+ * Host-side factorisation of the shared design X (n x p), done ONCE per call
+ * instead of once per voxel.  Replaces the per-voxel F77 dqrls (LINPACK dqrdc2,
+ * tol 1e-7, limited column pivoting) and LAPACK dpotri of
+ * src/modelling_functions.c:489-495 and :549.
+ *   pivot[p]   0-based column permutation, as voxel_lm's pivot[] after dqrls
+ *   rank       numerical rank k
+ *   Q[n*p]     first k columns: the thin orthonormal factor of X[:, pivot[:k]]
+ *   Rinv[p*p]  leading k x k block: inverse of the k x k triangle R_k
+ *   cdiag[p]   diag((R'R)^-1) of the full p x p triangle, as dpotri leaves it
+ * Returns RMG_ERR_SINGULAR (and *dpotri_info = i, 1-based) when R[i,i] == 0.
+ * Any output pointer may be NULL.
+ */
+int rmg_design_factor(const double *X, int n, int p, int32_t *pivot, int *rank,
+                      double *Q, double *Rinv, double *cdiag, int *dpotri_info,
+                      char *err, size_t errlen);
+
+/*
+ * vertexLm / anatLm.  Drop-in for
+ *   SEXP vertex_lm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix)
+ * (src/vertex_modelling.c:8; R callers R/minc_vertex_statistics.R:408-414,
+ * R/minc_anatomy.R:1144-1150) with a static design (data_right = logical NA).
+ *   Y    V x n host matrix, leading dimension ldY >= V   (data_left)
+ *   X    n x p host model matrix                          (mmatrix)
+ *   out  V x (2p+3) host matrix, leading dimension ldOut >= V
+ *   device  CUDA device ordinal
+ */
+int rmg_vertex_lm(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p,
+                  double *out, int64_t ldOut, int device, char *err, size_t errlen);
+
+/*
+ * mincLm.  Drop-in for minc2_model(..., method = "lm") (src/modelling_functions.c:743-745;
+ * R caller mincLm_c_wrapper, R/minc_voxel_statistics.R:695-712) once the R layer has staged
+ * the n volumes as the columns of Y (row order = file dimension order, :1059) and the mask
+ * volume as a double vector.
+ *   mask        NULL (have_mask = 0) or V doubles
+ *   mask_lo/hi  voxel v is fitted iff mask[v] > mask_lo - 0.5 && mask[v] < mask_hi + 0.5
+ *               (:1063-1066; R defaults 1 and 99999999, R/minc_voxel_statistics.R:781-787)
+ * Y may be pageable or pinned host memory.
+ */
+int rmg_lm_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p,
+               const double *mask, double mask_lo, double mask_hi,
+               double *out, int64_t ldOut, int device, char *err, size_t errlen);
+
+/*
+ * Same fit with every buffer already resident on `device` (dY, dmask, dout are device
+ * pointers).  The work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = the
+ * legacy default stream) and the call returns without synchronising.
+ */
+int rmg_lm_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const double *X, int p,
+                      const double *dmask, double mask_lo, double mask_hi,
+                      double *dout, int64_t ldOut, int device, void *stream,
+                      char *err, size_t errlen);
+
+/*
+ * mincRandomize.  Replaces the R loop of R/minc_voxel_statistics.R:1465-1497, which re-runs
+ * the whole mincLm call once per permutation.
+ *   idx      n x R, 0-based row indices drawn by the caller (R's sample()); permutation r
+ *            refits with X_pi = X[idx[, r], ] and the same Y and mask
+ *   cols     0-based columns of the V x (2p+3) result whose maxima are wanted (default in R:
+ *            the tvalue- columns)
+ *   two_sided  non-zero: abs() before the maximum (alternative = "two.sided")
+ *   dist     R x ncols host matrix (column-major): per permutation, the maximum over ALL V
+ *            rows of the statistic with non-finite values and masked rows counted as 0
+ * A permuted design whose R factor has an exactly-zero diagonal fails the whole call with
+ * RMG_ERR_SINGULAR, as the reference's refit would.
+ */
+int rmg_randomize(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p,
+                  const double *mask, double mask_lo, double mask_hi,
+                  const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
+                  double *dist, int device, char *err, size_t errlen);
+
+/*
+ * Device-resident variant: dY/dmask on `device`; ddist is a device R x ncols matrix that
+ * receives this device's maxima over ITS voxels (voxel shards on several GPUs are combined by
+ * the caller with an element-wise max, e.g. ncclAllReduce(ncclMax)).  Enqueued on `stream`.
+ */
+int rmg_randomize_device(const double *dY, int64_t V, int64_t ldY, int n, const double *X, int p,
+                         const double *dmask, double mask_lo, double mask_hi,
+                         const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
+                         double *ddist, int device, void *stream, char *err, size_t errlen);
+
+/*
+ * Single-process multi-GPU forms (R is one process): contiguous voxel shards over devices
+ * 0..n_gpus-1, one host thread per GPU, replacing create_parallel_mask + mclapply
+ * (R/minc_voxel_statistics.R:848-906, :1503-1509).  n_gpus <= 0 means all visible devices.
+ */
+int rmg_lm_fit_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p,
+                     const double *mask, double mask_lo, double mask_hi,
+                     double *out, int64_t ldOut, int n_gpus, char *err, size_t errlen);
+int rmg_randomize_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p,
+                        const double *mask, double mask_lo, double mask_hi,
+                        const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
+                        double *dist, int n_gpus, char *err, size_t errlen);
+
+/* Timing of the most recent rmg_*_device / host call on this thread, for bench.py:
+ * milliseconds spent in the dominant kernel(s), measured with CUDA events on the stream the
+ * kernels were launched on (host entry points only; 0 if unavailable). */
+double rmg_last_kernel_ms(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t rmg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMINC_B200_H */

@@ -1,0 +1,93 @@
+"""ctypes binding of the C ABI in include/rminc_b200.h.
+
+The shared library is the product: there is NO fallback.  If librminc_b200.so is
+missing or a compute entry point cannot reach a CUDA device, the error is raised to
+the caller (RmincGpuError), never papered over with a CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librminc_b200.so")
+
+RMG_OK, RMG_ERR_INVALID, RMG_ERR_SINGULAR, RMG_ERR_CUDA, RMG_ERR_NO_DEVICE = 0, 1, 2, 3, 4
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+# name -> (restype, argtypes); mirrors include/rminc_b200.h declaration by declaration
+_FIT_HEAD = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int]
+_MASK = [C.c_void_p, C.c_double, C.c_double]
+_ERR = [C.c_char_p, C.c_size_t]
+_PERM = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+SIGNATURES = {
+    "rmg_version": (C.c_int, []),
+    "rmg_device_count": (C.c_int, []),
+    "rmg_max_p": (C.c_int, []),
+    "rmg_design_factor": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_int)] + _ERR),
+    "rmg_vertex_lm": (C.c_int, _FIT_HEAD + [C.c_void_p, C.c_int64, C.c_int] + _ERR),
+    "rmg_lm_fit": (C.c_int, _FIT_HEAD + _MASK + [C.c_void_p, C.c_int64, C.c_int] + _ERR),
+    "rmg_lm_fit_device": (C.c_int, _FIT_HEAD + _MASK + [C.c_void_p, C.c_int64, C.c_int, C.c_void_p] + _ERR),
+    "rmg_randomize": (C.c_int, _FIT_HEAD + _MASK + _PERM + [C.c_void_p, C.c_int] + _ERR),
+    "rmg_randomize_device": (C.c_int, _FIT_HEAD + _MASK + _PERM + [C.c_void_p, C.c_int, C.c_void_p] + _ERR),
+    "rmg_lm_fit_multi": (C.c_int, _FIT_HEAD + _MASK + [C.c_void_p, C.c_int64, C.c_int] + _ERR),
+    "rmg_randomize_multi": (C.c_int, _FIT_HEAD + _MASK + _PERM + [C.c_void_p, C.c_int] + _ERR),
+    "rmg_last_kernel_ms": (C.c_double, []),
+    "rmg_launch_count": (C.c_int64, []),
+}
+
+
+class RmincGpuError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(message)
+        self.code = code
+
+
+class SingularDesignError(RmincGpuError):
+    """dpotri info > 0 -- the reference raises an R error (src/modelling_functions.c:551-557)."""
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load librminc_b200.so (built in-tree by rminc_b200/build.py).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RmincGpuError(RMG_ERR_NO_DEVICE,
+                            f"{LIB_PATH} is missing: run `python -m rminc_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == the .so does not match the header
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, err: C.Array) -> None:
+    if rc == RMG_OK:
+        return
+    msg = err.value.decode(errors="replace")
+    if rc == RMG_ERR_SINGULAR:
+        raise SingularDesignError(rc, msg)
+    raise RmincGpuError(rc, msg)
+
+
+def errbuf():
+    return C.create_string_buffer(512)
+
+
+def as_f64_fortran(a) -> np.ndarray:
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def ptr(a: np.ndarray) -> int:
+    return a.ctypes.data

@@ -1,0 +1,212 @@
+"""Thin numpy / torch front-ends over the C ABI (include/rminc_b200.h).
+
+Layout convention: every matrix is column-major as in R.  A V x n column-major
+matrix is the same memory as a C-contiguous array of shape (n, V); the torch entry
+points therefore take Y as an (n, V) float64 CUDA tensor and return the result as a
+(2p+3, V) tensor whose row c is result column c.
+
+Result columns (src/modelling_functions.c:1159-1174):
+  0 F-statistic | 1 R-squared | 2..p+1 beta | p+2..2p+1 t | 2p+2 logLik
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import RmincGpuError, SingularDesignError  # noqa: F401  (re-exported)
+
+DEFAULT_MASK_LO = 1.0          # R/minc_voxel_statistics.R:781-787
+DEFAULT_MASK_HI = 99999999.0
+
+
+def mask_range(maskval=None):
+    """mincLm's maskval handling (R/minc_voxel_statistics.R:781-787)."""
+    if maskval is None:
+        return DEFAULT_MASK_LO, DEFAULT_MASK_HI
+    return float(maskval), float(maskval)
+
+
+def device_count() -> int:
+    return _lib.load().rmg_device_count()
+
+
+def design_factor(X):
+    """Host factorisation of the design (pivot, rank, Q, Rinv, cdiag).  No GPU needed."""
+    X = _lib.as_f64_fortran(X)
+    if X.ndim != 2:
+        raise ValueError("X must be n x p")
+    n, p = X.shape
+    lib = _lib.load()
+    pivot = np.zeros(p, dtype=np.int32)
+    rank = C.c_int(0)
+    info = C.c_int(0)
+    Q = np.zeros((n, p), order="F")
+    Rinv = np.zeros((p, p), order="F")
+    cdiag = np.zeros(p)
+    err = _lib.errbuf()
+    rc = lib.rmg_design_factor(X.ctypes.data, n, p, pivot.ctypes.data, C.byref(rank), Q.ctypes.data,
+                               Rinv.ctypes.data, cdiag.ctypes.data, C.byref(info), err, len(err))
+    if rc not in (_lib.RMG_OK, _lib.RMG_ERR_SINGULAR):
+        _lib.check(rc, err)
+    return dict(pivot=pivot, rank=rank.value, Q=Q, Rinv=Rinv, cdiag=cdiag, info=info.value)
+
+
+def _prep_host(Y, X, mask):
+    X = _lib.as_f64_fortran(X)
+    if X.ndim != 2:
+        raise ValueError("X must be n x p")
+    Y = np.asarray(Y)
+    if Y.ndim != 2 or Y.shape[1] != X.shape[0]:
+        raise ValueError(f"Y must be V x n with n == nrow(X); got {Y.shape} vs {X.shape}")
+    if not (Y.dtype == np.float64 and Y.flags.f_contiguous):
+        Y = _lib.as_f64_fortran(Y)
+    m = None
+    if mask is not None:
+        m = np.ascontiguousarray(np.asarray(mask, dtype=np.float64).reshape(-1))
+        if m.shape[0] != Y.shape[0]:
+            raise ValueError("mask length must equal the number of voxels")
+    return Y, X, m
+
+
+def lm_fit(Y, X, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, device=0, n_gpus=None):
+    """mincLm's native step on host data: V x (2p+3) Fortran-ordered result."""
+    Y, X, m = _prep_host(Y, X, mask)
+    V, n = Y.shape
+    p = X.shape[1]
+    out = np.empty((V, 2 * p + 3), order="F")
+    err = _lib.errbuf()
+    lib = _lib.load()
+    mp = m.ctypes.data if m is not None else None
+    ld = max(V, 1)
+    if n_gpus is None:
+        rc = lib.rmg_lm_fit(Y.ctypes.data, V, ld, n, X.ctypes.data, p, mp, mask_lo, mask_hi,
+                            out.ctypes.data, ld, device, err, len(err))
+    else:
+        rc = lib.rmg_lm_fit_multi(Y.ctypes.data, V, ld, n, X.ctypes.data, p, mp, mask_lo, mask_hi,
+                                  out.ctypes.data, ld, int(n_gpus), err, len(err))
+    _lib.check(rc, err)
+    return out
+
+
+def vertex_lm(Y, X, device=0):
+    """vertexLm / anatLm's native step (vertex_lm_loop, src/vertex_modelling.c:8)."""
+    Y, X, _ = _prep_host(Y, X, None)
+    V, n = Y.shape
+    p = X.shape[1]
+    out = np.empty((V, 2 * p + 3), order="F")
+    err = _lib.errbuf()
+    ld = max(V, 1)
+    rc = _lib.load().rmg_vertex_lm(Y.ctypes.data, V, ld, n, X.ctypes.data, p, out.ctypes.data, ld, device,
+                                   err, len(err))
+    _lib.check(rc, err)
+    return out
+
+
+def _prep_perm(idx, n, cols):
+    idx = np.asfortranarray(idx, dtype=np.int32)
+    if idx.ndim != 2 or idx.shape[0] != n:
+        raise ValueError("idx must be n x R")
+    if idx.size and (idx.min() < 0 or idx.max() >= n):
+        raise ValueError("idx entries must be in 0..n-1")
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    return idx, cols
+
+
+def randomize(Y, X, idx, cols, two_sided=True, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI,
+              device=0, n_gpus=None):
+    """mincRandomize's loop on host data: R x len(cols) matrix of per-permutation maxima."""
+    Y, X, m = _prep_host(Y, X, mask)
+    V, n = Y.shape
+    p = X.shape[1]
+    idx, cols = _prep_perm(idx, n, cols)
+    if cols.size and (cols.min() < 0 or cols.max() >= 2 * p + 3):
+        raise ValueError("cols entries must be in 0..2p+2")
+    R = idx.shape[1]
+    dist = np.empty((R, len(cols)), order="F")
+    err = _lib.errbuf()
+    lib = _lib.load()
+    mp = m.ctypes.data if m is not None else None
+    ld = max(V, 1)
+    if n_gpus is None:
+        rc = lib.rmg_randomize(Y.ctypes.data, V, ld, n, X.ctypes.data, p, mp, mask_lo, mask_hi, idx.ctypes.data, R,
+                               cols.ctypes.data, len(cols), int(bool(two_sided)), dist.ctypes.data, device,
+                               err, len(err))
+    else:
+        rc = lib.rmg_randomize_multi(Y.ctypes.data, V, ld, n, X.ctypes.data, p, mp, mask_lo, mask_hi,
+                                     idx.ctypes.data, R, cols.ctypes.data, len(cols), int(bool(two_sided)),
+                                     dist.ctypes.data, int(n_gpus), err, len(err))
+    _lib.check(rc, err)
+    return dist
+
+
+# ------------------------------------------------------------------ device-resident (torch) forms
+def _torch_stream(t):
+    import torch
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def lm_fit_torch(Yt, X, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, out=None):
+    """Fit with Y resident in HBM.  Yt: (n, V) float64 CUDA tensor (row stride = ldY).
+    Returns a (2p+3, V) CUDA tensor.  Enqueued on torch's current stream; does not synchronise."""
+    import torch
+    if not (Yt.is_cuda and Yt.dtype == torch.float64 and Yt.dim() == 2 and Yt.stride(1) == 1):
+        raise ValueError("Yt must be a float64 CUDA tensor of shape (n, V) with unit stride along V")
+    X = _lib.as_f64_fortran(X)
+    n, V = Yt.shape
+    if X.shape[0] != n:
+        raise ValueError("nrow(X) must equal Yt.shape[0]")
+    p = X.shape[1]
+    ldY = Yt.stride(0) if n > 1 else max(V, 1)
+    if out is None:
+        out = torch.empty((2 * p + 3, V), dtype=torch.float64, device=Yt.device)
+    if not (out.is_cuda and out.dtype == torch.float64 and out.shape == (2 * p + 3, V) and out.stride(1) == 1):
+        raise ValueError("out must be a (2p+3, V) float64 CUDA tensor")
+    mp = None
+    if mask is not None:
+        if not (mask.is_cuda and mask.dtype == torch.float64 and mask.numel() == V and mask.is_contiguous()):
+            raise ValueError("mask must be a contiguous float64 CUDA tensor of V elements")
+        mp = mask.data_ptr()
+    err = _lib.errbuf()
+    rc = _lib.load().rmg_lm_fit_device(Yt.data_ptr(), V, ldY, n, X.ctypes.data, p, mp, mask_lo, mask_hi,
+                                       out.data_ptr(), out.stride(0), Yt.device.index or 0, _torch_stream(Yt),
+                                       err, len(err))
+    _lib.check(rc, err)
+    return out
+
+
+def randomize_torch(Yt, X, idx, cols, two_sided=True, mask=None, mask_lo=DEFAULT_MASK_LO,
+                    mask_hi=DEFAULT_MASK_HI, dist=None):
+    """Permutation maxima over THIS device's voxels.  Returns an (ncols, R) CUDA tensor (the
+    column-major R x ncols matrix); combine shards with an element-wise max."""
+    import torch
+    if not (Yt.is_cuda and Yt.dtype == torch.float64 and Yt.dim() == 2 and Yt.stride(1) == 1):
+        raise ValueError("Yt must be a float64 CUDA tensor of shape (n, V) with unit stride along V")
+    X = _lib.as_f64_fortran(X)
+    n, V = Yt.shape
+    p = X.shape[1]
+    idx, cols = _prep_perm(idx, n, cols)
+    R = idx.shape[1]
+    ldY = Yt.stride(0) if n > 1 else max(V, 1)
+    if dist is None:
+        dist = torch.empty((len(cols), R), dtype=torch.float64, device=Yt.device)
+    mp = None
+    if mask is not None:
+        if not (mask.is_cuda and mask.dtype == torch.float64 and mask.numel() == V and mask.is_contiguous()):
+            raise ValueError("mask must be a contiguous float64 CUDA tensor of V elements")
+        mp = mask.data_ptr()
+    err = _lib.errbuf()
+    rc = _lib.load().rmg_randomize_device(Yt.data_ptr(), V, ldY, n, X.ctypes.data, p, mp, mask_lo, mask_hi,
+                                          idx.ctypes.data, R, cols.ctypes.data, len(cols), int(bool(two_sided)),
+                                          dist.data_ptr(), Yt.device.index or 0, _torch_stream(Yt), err, len(err))
+    _lib.check(rc, err)
+    return dist
+
+
+def last_kernel_ms() -> float:
+    return _lib.load().rmg_last_kernel_ms()
+
+
+def launch_count() -> int:
+    return _lib.load().rmg_launch_count()

@@ -1,0 +1,325 @@
+// capi.cu -- C ABI (include/rminc_b200.h) of the fit path: argument checking, design
+// factorisation, host<->device staging pipeline, multi-GPU voxel sharding.
+//
+// Reference interfaces replaced: minc2_model(method="lm") src/modelling_functions.c:743-745,
+// vertex_lm_loop src/vertex_modelling.c:8, and the parallel= sharding of
+// R/minc_voxel_statistics.R:848-906.  No CPU fallback exists: every compute entry point
+// fails with RMG_ERR_NO_DEVICE when no CUDA device is usable.
+#include <algorithm>
+#include <cmath>
+#include <thread>
+
+#include "capi_common.hpp"
+
+namespace rmg {
+
+std::atomic<int64_t> g_launch_count{0};
+thread_local double g_last_kernel_ms = 0.0;
+
+int select_device(int device, char *err, size_t errlen)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(err, errlen, RMG_ERR_NO_DEVICE,
+                    "no CUDA device available (%s); rminc_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count)
+        return fail(err, errlen, RMG_ERR_NO_DEVICE, "device %d out of range (have %d)", device, count);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(err, errlen, RMG_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    return RMG_OK;
+}
+
+int device_sm_count(int device)
+{
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+        cudaGetLastError();
+        sms = 148;
+    }
+    return sms;
+}
+
+int check_fit_args(const void *Y, int64_t V, int64_t ldY, int n, const void *X, int p, const void *out,
+                   int64_t ldOut, char *err, size_t errlen)
+{
+    if (!X) return fail(err, errlen, RMG_ERR_INVALID, "X is NULL");
+    if (V < 0) return fail(err, errlen, RMG_ERR_INVALID, "V < 0");
+    if (V > 0 && (!Y || !out)) return fail(err, errlen, RMG_ERR_INVALID, "Y or out is NULL");
+    if (n < 1) return fail(err, errlen, RMG_ERR_INVALID, "n must be >= 1 (got %d)", n);
+    if (p < 1 || p > RMG_MAX_P) return fail(err, errlen, RMG_ERR_INVALID, "p must be in 1..%d (got %d)", RMG_MAX_P, p);
+    if (ldY < V || ldOut < V) return fail(err, errlen, RMG_ERR_INVALID, "leading dimension smaller than V");
+    return RMG_OK;
+}
+
+void fill_dev_design(const Design &D, DevDesign &dd)
+{
+    std::memset(&dd, 0, sizeof dd);
+    dd.n = D.n;
+    dd.p = D.p;
+    dd.k = D.k;
+    dd.shift = D.has_intercept ? 1 : 0;
+    dd.gap = D.gap;
+    dd.inv_n = 1.0 / D.n;
+    dd.rdf = (double)(D.n - D.p);
+    dd.pm1 = (double)(D.p - 1);
+    dd.loglik_c = std::log(2 * M_PI) + 1 - std::log((double)D.n);
+    dd.mhalf_n = -.5 * D.n;
+    for (int i = 0; i < D.p; ++i) {
+        dd.q1[i] = D.q1[i];
+        dd.ct[i] = D.ct[i];
+        for (int j = 0; j < D.p; ++j) dd.Rinv[i * kMaxPDev + j] = D.Rinv[i + (size_t)j * D.p];
+    }
+}
+
+std::vector<double> make_qt(const Design &D, int KP)
+{
+    std::vector<double> qt((size_t)D.n * KP, 0.0);
+    for (int c = 0; c < D.k; ++c)
+        for (int i = 0; i < D.n; ++i) qt[(size_t)i * KP + c] = D.Q[i + (size_t)c * D.n];
+    return qt;
+}
+
+int factor_or_fail(const double *X, int n, int p, Design &D, char *err, size_t errlen)
+{
+    for (size_t i = 0; i < (size_t)n * p; ++i)
+        if (!std::isfinite(X[i])) return fail(err, errlen, RMG_ERR_INVALID, "model matrix contains non-finite values");
+    const int info = factor_design(X, n, p, D);
+    if (info > 0) return fail(err, errlen, RMG_ERR_SINGULAR, "%s", singular_message(info).c_str());
+    return RMG_OK;
+}
+
+namespace {
+
+// Design constants resident on the current device for the duration of one call.
+struct DeviceDesign {
+    DevDesign *dd = nullptr;
+    double *qt = nullptr;
+    cudaError_t upload(const Design &D, cudaStream_t st)
+    {
+        DevDesign h;
+        fill_dev_design(D, h);
+        const int KP = lm_padded_p(D.p);
+        const std::vector<double> qt_h = make_qt(D, KP);
+        cudaError_t e = cudaMallocAsync(&dd, sizeof(DevDesign), st);
+        if (e != cudaSuccess) return e;
+        e = cudaMallocAsync(&qt, qt_h.size() * sizeof(double), st);
+        if (e != cudaSuccess) return e;
+        // pageable sources: the runtime stages them before returning, so the locals may die
+        e = cudaMemcpyAsync(dd, &h, sizeof h, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(qt, qt_h.data(), qt_h.size() * sizeof(double), cudaMemcpyHostToDevice, st);
+    }
+    void release(cudaStream_t st)
+    {
+        if (dd) cudaFreeAsync(dd, st);
+        if (qt) cudaFreeAsync(qt, st);
+        dd = nullptr;
+        qt = nullptr;
+    }
+};
+
+LmPlan plan_from_env(int device)
+{
+    LmPlan plan;
+    plan.sm_count = device_sm_count(device);
+    if (const char *v = std::getenv("RMG_FIT_VARIANT")) {
+        if (!std::strcmp(v, "tma")) plan.variant = LmVariant::Tma;
+        else if (!std::strcmp(v, "ldg")) plan.variant = LmVariant::Ldg;
+    }
+    if (const char *s = std::getenv("RMG_FIT_SPLIT")) plan.split = std::atoi(s);
+    return plan;
+}
+
+}  // namespace
+}  // namespace rmg
+
+using namespace rmg;
+
+extern "C" {
+
+int rmg_version(void) { return 100; }
+int rmg_max_p(void) { return RMG_MAX_P; }
+
+int rmg_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
+double rmg_last_kernel_ms(void) { return g_last_kernel_ms; }
+int64_t rmg_launch_count(void) { return g_launch_count.load(); }
+
+int rmg_design_factor(const double *X, int n, int p, int32_t *pivot, int *rank, double *Q, double *Rinv,
+                      double *cdiag, int *dpotri_info, char *err, size_t errlen)
+{
+    if (!X || n < 1 || p < 1 || p > RMG_MAX_P) return fail(err, errlen, RMG_ERR_INVALID, "bad design arguments");
+    Design D;
+    const int info = factor_design(X, n, p, D);
+    if (pivot) std::copy(D.pivot.begin(), D.pivot.end(), pivot);
+    if (rank) *rank = D.k;
+    if (Q) std::copy(D.Q.begin(), D.Q.end(), Q);
+    if (Rinv) std::copy(D.Rinv.begin(), D.Rinv.end(), Rinv);
+    if (cdiag) std::copy(D.cdiag.begin(), D.cdiag.end(), cdiag);
+    if (dpotri_info) *dpotri_info = info;
+    if (info > 0) return fail(err, errlen, RMG_ERR_SINGULAR, "%s", singular_message(info).c_str());
+    return RMG_OK;
+}
+
+int rmg_lm_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const double *X, int p,
+                      const double *dmask, double mask_lo, double mask_hi, double *dout, int64_t ldOut,
+                      int device, void *stream, char *err, size_t errlen)
+{
+    int rc = check_fit_args(dY, V, ldY, n, X, p, dout, ldOut, err, errlen);
+    if (rc) return rc;
+    Design D;
+    if ((rc = factor_or_fail(X, n, p, D, err, errlen))) return rc;
+    if ((rc = select_device(device, err, errlen))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DeviceDesign dev;
+    LmScratch scr;
+    LmLaunchInfo info;
+    {
+        RMG_CUDA(dev.upload(D, st));
+        LmArgs a{dY, V, ldY, n, p, dev.qt, dev.dd, dmask, mask_lo, mask_hi, dout, ldOut};
+        RMG_CUDA(launch_lm_fit(a, plan_from_env(device), scr, st, &info));
+        g_launch_count += info.launches;
+    }
+cleanup:
+    dev.release(st);
+    scr.release(st);
+    return rc;
+}
+
+int rmg_lm_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
+               double mask_lo, double mask_hi, double *out, int64_t ldOut, int device, char *err, size_t errlen)
+{
+    int rc = check_fit_args(Y, V, ldY, n, X, p, out, ldOut, err, errlen);
+    if (rc) return rc;
+    Design D;
+    if ((rc = factor_or_fail(X, n, p, D, err, errlen))) return rc;
+    if ((rc = select_device(device, err, errlen))) return rc;
+    g_last_kernel_ms = 0.0;
+    if (V == 0) return RMG_OK;
+
+    const int ncol = 2 * p + 3;
+    // Voxel chunks of ~256 MiB of Y, multiples of 1024 voxels so TMA tiles stay aligned.
+    int64_t CV = (int64_t)(256.0 * 1024 * 1024 / (8.0 * n));
+    CV = std::max<int64_t>(1024, (CV / 1024) * 1024);
+    if (const char *s = std::getenv("RMG_CHUNK_VOXELS")) CV = std::max<int64_t>(2, (std::atoll(s) / 2) * 2);
+    if (CV > V) CV = V;
+    const int64_t nchunks = (V + CV - 1) / CV;
+    const int NB = (int)std::min<int64_t>(3, nchunks);
+    const int64_t ldc = (CV + 1) & ~int64_t(1);  // even leading dimension -> 16-byte aligned rows
+
+    cudaStream_t st[3] = {nullptr, nullptr, nullptr};
+    double *dY[3] = {nullptr, nullptr, nullptr}, *dO[3] = {nullptr, nullptr, nullptr}, *dM[3] = {nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> ev0(nchunks, nullptr), ev1(nchunks, nullptr);
+    DeviceDesign dev;
+    LmScratch scr[3];
+    const LmPlan plan = plan_from_env(device);
+    int64_t launches = 0;
+    {
+        for (int b = 0; b < NB; ++b) {
+            RMG_CUDA(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
+            RMG_CUDA(cudaMalloc(&dY[b], (size_t)ldc * n * sizeof(double)));
+            RMG_CUDA(cudaMalloc(&dO[b], (size_t)ldc * ncol * sizeof(double)));
+            if (mask) RMG_CUDA(cudaMalloc(&dM[b], (size_t)ldc * sizeof(double)));
+        }
+        RMG_CUDA(dev.upload(D, st[0]));
+        RMG_CUDA(cudaStreamSynchronize(st[0]));
+        for (int64_t c = 0; c < nchunks; ++c) {
+            const int b = (int)(c % NB);
+            const int64_t v0 = c * CV, cv = std::min(CV, V - v0);
+            RMG_CUDA(cudaEventCreate(&ev0[c]));
+            RMG_CUDA(cudaEventCreate(&ev1[c]));
+            RMG_CUDA(cudaMemcpy2DAsync(dY[b], (size_t)ldc * 8, Y + v0, (size_t)ldY * 8, (size_t)cv * 8, (size_t)n,
+                                       cudaMemcpyHostToDevice, st[b]));
+            if (mask) RMG_CUDA(cudaMemcpyAsync(dM[b], mask + v0, (size_t)cv * 8, cudaMemcpyHostToDevice, st[b]));
+            LmArgs a{dY[b], cv, ldc, n, p, dev.qt, dev.dd, mask ? dM[b] : nullptr, mask_lo, mask_hi, dO[b], ldc};
+            LmLaunchInfo info;
+            RMG_CUDA(cudaEventRecord(ev0[c], st[b]));
+            RMG_CUDA(launch_lm_fit(a, plan, scr[b], st[b], &info));
+            RMG_CUDA(cudaEventRecord(ev1[c], st[b]));
+            launches += info.launches;
+            RMG_CUDA(cudaMemcpy2DAsync(out + v0, (size_t)ldOut * 8, dO[b], (size_t)ldc * 8, (size_t)cv * 8, (size_t)ncol,
+                                       cudaMemcpyDeviceToHost, st[b]));
+        }
+        for (int b = 0; b < NB; ++b) RMG_CUDA(cudaStreamSynchronize(st[b]));
+        double ms = 0.0;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, ev0[c], ev1[c]) == cudaSuccess) ms += t;
+        }
+        g_last_kernel_ms = ms;
+        g_launch_count += launches;
+    }
+cleanup:
+    for (int b = 0; b < 3; ++b) {
+        if (st[b]) cudaStreamSynchronize(st[b]);
+    }
+    dev.release(nullptr);
+    for (int b = 0; b < 3; ++b) {
+        scr[b].release(st[b]);
+        if (st[b]) cudaStreamSynchronize(st[b]);
+        if (dY[b]) cudaFree(dY[b]);
+        if (dO[b]) cudaFree(dO[b]);
+        if (dM[b]) cudaFree(dM[b]);
+        if (st[b]) cudaStreamDestroy(st[b]);
+    }
+    for (auto e : ev0) if (e) cudaEventDestroy(e);
+    for (auto e : ev1) if (e) cudaEventDestroy(e);
+    if (rc != RMG_OK) cudaGetLastError();
+    return rc;
+}
+
+int rmg_vertex_lm(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, double *out,
+                  int64_t ldOut, int device, char *err, size_t errlen)
+{
+    // vertex_lm_loop has no mask and no I/O (src/vertex_modelling.c:104-158)
+    return rmg_lm_fit(Y, V, ldY, n, X, p, nullptr, 0.0, 0.0, out, ldOut, device, err, errlen);
+}
+
+int rmg_lm_fit_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
+                     double mask_lo, double mask_hi, double *out, int64_t ldOut, int n_gpus, char *err,
+                     size_t errlen)
+{
+    int rc = check_fit_args(Y, V, ldY, n, X, p, out, ldOut, err, errlen);
+    if (rc) return rc;
+    const int have = rmg_device_count();
+    if (have <= 0) return fail(err, errlen, RMG_ERR_NO_DEVICE, "no CUDA device available; rminc_b200 has no CPU fallback");
+    int G = n_gpus <= 0 ? have : n_gpus;
+    if (G > have) return fail(err, errlen, RMG_ERR_NO_DEVICE, "%d GPUs requested, %d visible", G, have);
+    // contiguous voxel shards, even boundaries (keeps every shard 16-byte aligned)
+    std::vector<int64_t> b(G + 1);
+    for (int g = 0; g <= G; ++g) b[g] = std::min<int64_t>(V, ((V * g / G) + 1) & ~int64_t(1));
+    b[0] = 0;
+    b[G] = V;
+    std::vector<int> rcs(G, RMG_OK);
+    std::vector<std::string> msgs(G, std::string(256, '\0'));
+    std::vector<double> kms(G, 0.0);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) {
+        th.emplace_back([&, g]() {
+            const int64_t v0 = b[g], cv = b[g + 1] - b[g];
+            if (cv <= 0) return;
+            rcs[g] = rmg_lm_fit(Y + v0, cv, ldY, n, X, p, mask ? mask + v0 : nullptr, mask_lo, mask_hi, out + v0,
+                                ldOut, g, &msgs[g][0], msgs[g].size());
+            kms[g] = rmg_last_kernel_ms();
+        });
+    }
+    for (auto &t : th) t.join();
+    g_last_kernel_ms = *std::max_element(kms.begin(), kms.end());
+    for (int g = 0; g < G; ++g)
+        if (rcs[g] != RMG_OK) return fail(err, errlen, rcs[g], "gpu %d: %s", g, msgs[g].c_str());
+    return RMG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// capi_common.hpp -- helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rminc_b200.h"
+#include "design.hpp"
+#include "lm_common.cuh"
+#include "lm_launch.hpp"
+
+namespace rmg {
+
+extern std::atomic<int64_t> g_launch_count;
+extern thread_local double g_last_kernel_ms;
+
+inline int fail(char *err, size_t errlen, int code, const char *fmt, ...)
+{
+    if (err && errlen) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(err, errlen, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define RMG_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            rc = fail(err, errlen, RMG_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                \
+                      cudaGetErrorString(e__), __FILE__, __LINE__);                             \
+            goto cleanup;                                                                       \
+        }                                                                                       \
+    } while (0)
+
+// Validates the device ordinal and makes it current.  0 on success.
+int select_device(int device, char *err, size_t errlen);
+int device_sm_count(int device);
+
+// Common argument validation of the fit entry points.
+int check_fit_args(const void *Y, int64_t V, int64_t ldY, int n, const void *X, int p, const void *out,
+                   int64_t ldOut, char *err, size_t errlen);
+
+// Host images of the per-design device constants.
+void fill_dev_design(const Design &D, DevDesign &dd);
+// Row-major [n][KP] copy of Q (columns >= rank zero).
+std::vector<double> make_qt(const Design &D, int KP);
+
+// Factor X and translate the reference's error contract.  0 or RMG_ERR_*.
+int factor_or_fail(const double *X, int n, int p, Design &D, char *err, size_t errlen);
+
+}  // namespace rmg

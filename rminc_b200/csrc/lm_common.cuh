@@ -1,0 +1,175 @@
+// lm_common.cuh -- device-side constants and the fused per-voxel statistics epilogue
+// shared by the fit kernels (K1/K2) and the permutation kernel (K3).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace rmg {
+
+constexpr int kMaxPDev = 32;
+
+// Everything the epilogue needs that depends only on the design.  Lives in global
+// memory (one per design; the permutation kernel indexes an array of them).
+struct DevDesign {
+    int n, p, k, shift;     // shift = 1: 1 in span(X), voxels are centred on their first sample
+    double gap;             // n - |Q'1|^2  (0 when shift)
+    double inv_n;           // 1/n
+    double rdf;             // n - p         (NOT n - rank: src/modelling_functions.c:534)
+    double pm1;             // p - 1         (:542)
+    double loglik_c;        // log(2*pi) + 1 - log(n)   (:527)
+    double mhalf_n;         // -0.5 * n
+    double q1[kMaxPDev];    // Q'1
+    double ct[kMaxPDev];    // diag((R'R)^-1), un-pivoted as the reference un-pivots se (:560-564)
+    double Rinv[kMaxPDev * kMaxPDev];  // row-major: Rinv[i*kMaxPDev + j], upper triangle, k x k
+};
+
+// Per-CTA shared-memory copy of the k-dependent part, padded to the kernel's KP.
+template <int KP>
+struct SmemDesign {
+    double q1[KP];
+    double ct[KP];
+    double Rinv[KP * KP];   // row-major KP x KP
+    double gap, inv_n, rdf, pm1, loglik_c, mhalf_n;
+    int n, p, k, shift;
+};
+
+template <int KP>
+__device__ __forceinline__ void load_design_to_smem(SmemDesign<KP> &s, const DevDesign *__restrict__ d,
+                                                    int tid, int nthreads)
+{
+    for (int i = tid; i < KP; i += nthreads) {
+        s.q1[i] = d->q1[i];
+        s.ct[i] = d->ct[i];
+    }
+    for (int i = tid; i < KP * KP; i += nthreads) s.Rinv[i] = d->Rinv[(i / KP) * kMaxPDev + (i % KP)];
+    if (tid == 0) {
+        s.gap = d->gap; s.inv_n = d->inv_n; s.rdf = d->rdf; s.pm1 = d->pm1;
+        s.loglik_c = d->loglik_c; s.mhalf_n = d->mhalf_n;
+        s.n = d->n; s.p = d->p; s.k = d->k; s.shift = d->shift;
+    }
+}
+
+// One-pass sums of one voxel: e = Q'(y - y0), yy = |y - y0|^2.
+// One-pass rss = yy - |e|^2 loses digits when the model explains almost all of yy; callers
+// test needs_exact() and then recompute rss/mss from explicit residuals (exact_pass()).
+template <int KP>
+struct VoxelSums {
+    double e[KP];
+    double yy;
+    double y0;
+};
+
+template <int KP>
+__device__ __forceinline__ double sumsq_e(const VoxelSums<KP> &s)
+{
+    double ee = 0.0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) ee = fma(s.e[k], s.e[k], ee);
+    return ee;
+}
+
+// mss = sum((fitted - mean(fitted))^2)   (:529-532), from e alone:
+//   fitted = Q e, sum(fitted) = q1.e =: s, |fitted|^2 = |e|^2
+//   mss = |e - q1 s/n|^2 + (n - |q1|^2)(s/n)^2        (both terms >= 0: no cancellation)
+template <int KP>
+__device__ __forceinline__ double mss_from_e(const VoxelSums<KP> &v, const SmemDesign<KP> &d)
+{
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) s = fma(d.q1[k], v.e[k], s);
+    const double m = s * d.inv_n;
+    double mss = 0.0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const double dk = fma(-d.q1[k], m, v.e[k]);
+        mss = fma(dk, dk, mss);
+    }
+    return fma(d.gap * m, m, mss);
+}
+
+// Relative threshold below which the one-pass rss is replaced by explicit residuals.
+// One-pass error ~ n*eps*yy/rss worst case; 1e-3 keeps it under ~1e-10 for n <= 4000.
+constexpr double kExactThreshold = 1e-3;
+
+// Write one result row.  Column layout: src/modelling_functions.c:1159-1174.
+//   out[v + c*ld]: c=0 F, 1 R2, 2..p+1 beta, p+2..2p+1 t, 2p+2 logLik
+template <int KP>
+__device__ __forceinline__ void finish_voxel(const VoxelSums<KP> &v, double rss, double mss,
+                                             const SmemDesign<KP> &d, double *__restrict__ out,
+                                             int64_t ld)
+{
+    const int p = d.p;
+    const double resvar = rss / d.rdf;                       // :537
+    out[0] = (mss / d.pm1) / resvar;                         // :542
+    out[ld] = mss / (mss + rss);                             // :572
+    out[(int64_t)(2 * p + 2) * ld] = d.mhalf_n * (d.loglik_c + log(rss));  // :527
+    // un-shift: e(y) = e(y - y0) + y0 * Q'1
+    double e[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) e[k] = fma(v.y0, d.q1[k], v.e[k]);
+#pragma unroll
+    for (int i = 0; i < KP; ++i) {
+        if (i < p) {
+            double b = 0.0;
+#pragma unroll
+            for (int j = i; j < KP; ++j) b = fma(d.Rinv[i * KP + j], e[j], b);
+            out[(int64_t)(2 + i) * ld] = b;                            // beta, pivoted order
+            out[(int64_t)(2 + p + i) * ld] = b / sqrt(d.ct[i] * resvar);  // :563, :568
+        }
+    }
+}
+
+template <int KP>
+__device__ __forceinline__ void zero_row(int p, double *__restrict__ out, int64_t ld)
+{
+    for (int c = 0; c < 2 * p + 3; ++c) out[(int64_t)c * ld] = 0.0;
+}
+
+__device__ __forceinline__ bool mask_selects(double m, double lo, double hi)
+{
+    return m > lo - 0.5 && m < hi + 0.5;  // src/modelling_functions.c:1063-1066
+}
+
+// Streaming 8/16-byte loads that do not pollute L1 (Y is read exactly once).
+__device__ __forceinline__ double ldg_stream(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ldg_stream2(const double *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// Explicit-residual recomputation for one voxel (rare path).  Qt is the row-major
+// [n][KP] copy of Q in global memory; y is read again with stride ld.
+template <int KP>
+__device__ __noinline__ void exact_pass(const VoxelSums<KP> &v, const double *__restrict__ y, int64_t ld,
+                                        int n, const double *__restrict__ Qt, double &rss, double &mss)
+{
+    double r2 = 0.0, sf = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double fit = 0.0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) fit = fma(__ldg(Qt + (size_t)j * KP + k), v.e[k], fit);
+        const double r = (y[(int64_t)j * ld] - v.y0) - fit;
+        r2 = fma(r, r, r2);
+        sf += fit;
+    }
+    const double mean = sf / n;
+    double m2 = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double fit = 0.0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) fit = fma(__ldg(Qt + (size_t)j * KP + k), v.e[k], fit);
+        const double dlt = fit - mean;
+        m2 = fma(dlt, dlt, m2);
+    }
+    rss = r2;
+    mss = m2;
+}
+
+}  // namespace rmg

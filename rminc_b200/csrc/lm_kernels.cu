@@ -1,0 +1,462 @@
+// lm_kernels.cu -- the fit kernels (SURVEY.md pieces K1/K2), hand-written for sm_100a.
+//
+// Replaces, for every voxel at once, the per-voxel body of minc2_model's "lm" branch
+// (src/modelling_functions.c:1057-1175), vertex_lm_loop (src/vertex_modelling.c:104-158)
+// and voxel_lm (src/modelling_functions.c:448-576).
+//
+// Data layout in HBM: Y is V x n column-major (ld = ldY): subject j's volume is the
+// contiguous run Y[j*ldY .. j*ldY+V).  One voxel's n samples are therefore strided by
+// ldY, and consecutive voxels of one subject are contiguous -- every warp load is a
+// fully coalesced row segment.  The kernel streams Y exactly once (8n bytes/voxel),
+// accumulates e = Q_k'(y - y0) and |y - y0|^2 per voxel in registers, and a fused
+// epilogue turns them into the 2p+3 result columns.  Arithmetic intensity is
+// (2p+2) flop per 8 bytes, so the roofline that bounds it is HBM bandwidth.
+//
+// Two implementations of the same contract:
+//   lm_fit_tma_kernel : persistent CTAs; one producer thread issues 2-D TMA tile loads
+//                       (cp.async.bulk.tensor, FP64 boxes of NJ subjects x TV voxels) into
+//                       a shared-memory ring guarded by mbarriers; consumer warps reduce
+//                       out of shared memory.  Default for large V.
+//   lm_fit_ldg_kernel : thread-per-voxel(-pair) direct streaming loads with an optional
+//                       split of the subject axis across threadIdx.y (K2, "split-n") and a
+//                       shared-memory reduction, for small V / large n and for layouts
+//                       TMA cannot describe (odd ldY, unaligned base).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "async_ptx.cuh"
+#include "lm_common.cuh"
+#include "lm_launch.hpp"
+
+namespace rmg {
+
+// ------------------------------------------------------------------ mask tile flags
+// flags[t] = 1 iff any voxel of tile t (tv voxels) is selected by the mask.
+__global__ void mask_tile_flags_kernel(const double *__restrict__ mask, int64_t V, int tv, double lo, double hi,
+                                       unsigned char *__restrict__ flags, int64_t ntiles)
+{
+    const int64_t t = blockIdx.x;
+    if (t >= ntiles) return;
+    const int64_t v0 = t * tv;
+    int any = 0;
+    for (int i = threadIdx.x; i < tv; i += blockDim.x) {
+        const int64_t v = v0 + i;
+        if (v < V && mask_selects(mask[v], lo, hi)) any = 1;
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) flags[t] = (unsigned char)any;
+}
+
+// One box of NJ subject rows out of shared memory into the two voxels' running sums.
+template <int KP, int NJ, int TV, bool GUARD>
+__device__ __forceinline__ void consume_box(const double *__restrict__ tile, const double *__restrict__ q,
+                                            VoxelSums<KP> &s0, VoxelSums<KP> &s1, int nvalid)
+{
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+        const double2 y = *reinterpret_cast<const double2 *>(tile + jj * TV);
+        double ya = y.x - s0.y0, yb = y.y - s1.y0;
+        if (GUARD && jj >= nvalid) ya = yb = 0.0;
+        s0.yy = fma(ya, ya, s0.yy);
+        s1.yy = fma(yb, yb, s1.yy);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const double qk = q[jj * KP + k];
+            s0.e[k] = fma(qk, ya, s0.e[k]);
+            s1.e[k] = fma(qk, yb, s1.e[k]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ TMA kernel
+// CTA = 1 producer warp + CW consumer warps.  Tile = TV = CW*64 voxels (2 per consumer
+// thread), streamed as boxes of NJ subjects.  Shared memory:
+//   [ring: STAGES x NJ x TV doubles][Qt: n x KP doubles][SmemDesign][mbarriers]
+template <int KP, int CW, int NJ, int STAGES>
+__global__ void __launch_bounds__((CW + 1) * 32, 1)
+lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsigned char *__restrict__ flags)
+{
+    constexpr int TV = CW * 64;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *ring = reinterpret_cast<double *>(smem_raw);
+    double *sQ = ring + (size_t)STAGES * NJ * TV;
+    const int n = a.n;
+    const int nq = ((n + NJ - 1) / NJ) * NJ;  // rows of sQ incl. zero padding
+    SmemDesign<KP> &sd = *reinterpret_cast<SmemDesign<KP> *>(sQ + (size_t)nq * KP);
+    uint64_t *full = reinterpret_cast<uint64_t *>(&sd + 1);
+    uint64_t *empty = full + STAGES;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int nthreads = blockDim.x;
+
+    for (int i = tid; i < nq * KP; i += nthreads) sQ[i] = (i < n * KP) ? a.Qt[i] : 0.0;
+    load_design_to_smem<KP>(sd, a.design, tid, nthreads);
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CW);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const int64_t ntiles = (a.V + TV - 1) / TV;
+    const int nit = nq / NJ;
+    constexpr uint32_t kStageBytes = NJ * TV * sizeof(double);
+
+    if (warp == CW) {
+        // ===== producer: one elected lane walks the same tile sequence as the consumers
+        if ((tid & 31) == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                if (flags && !flags[t]) continue;
+                const int c0 = (int)(t * TV);
+                for (int it = 0; it < nit; ++it) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], kStageBytes);
+                    tma_load_2d(ring + (size_t)stage * NJ * TV, &ymap, &full[stage], c0, it * NJ);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: thread owns voxels v0 + 2*tid, +1
+    uint32_t stage = 0, phase = 0;
+    const int lane = tid & 31;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t v = t * TV + 2 * tid;
+        const bool in0 = v < a.V, in1 = v + 1 < a.V;
+        bool act0 = in0, act1 = in1;
+        if (a.mask) {
+            act0 = in0 && mask_selects(a.mask[v], a.mask_lo, a.mask_hi);
+            act1 = in1 && mask_selects(a.mask[v + 1], a.mask_lo, a.mask_hi);
+        }
+        double *o = a.out + v;
+        if (flags && !flags[t]) {
+            if (in0) zero_row<KP>(sd.p, o, a.ldOut);
+            if (in1) zero_row<KP>(sd.p, o + 1, a.ldOut);
+            continue;
+        }
+        VoxelSums<KP> s0, s1;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) s0.e[k] = s1.e[k] = 0.0;
+        s0.yy = s1.yy = 0.0;
+        s0.y0 = s1.y0 = 0.0;
+        for (int it = 0; it < nit; ++it) {
+            mbar_wait(&full[stage], phase);
+            const double *tile = ring + (size_t)stage * NJ * TV + 2 * tid;
+            if (it == 0 && sd.shift) {
+                const double2 f = *reinterpret_cast<const double2 *>(tile);
+                s0.y0 = f.x;
+                s1.y0 = f.y;
+            }
+            const double *q = sQ + (size_t)it * NJ * KP;
+            // rows >= n of the last box are TMA zero-fill: their Q rows are zero, but their
+            // (0 - y0)^2 must not enter yy, so the last box runs the guarded variant.
+            if (it + 1 < nit) consume_box<KP, NJ, TV, false>(tile, q, s0, s1, NJ);
+            else consume_box<KP, NJ, TV, true>(tile, q, s0, s1, n - it * NJ);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        // ---- fused epilogue
+        if (in0) {
+            if (act0) {
+                double rss = s0.yy - sumsq_e(s0), mss = mss_from_e(s0, sd);
+                if (rss <= kExactThreshold * s0.yy && s0.yy > 0.0) exact_pass<KP>(s0, a.Y + v, a.ldY, n, a.Qt, rss, mss);
+                finish_voxel<KP>(s0, rss, mss, sd, o, a.ldOut);
+            } else {
+                zero_row<KP>(sd.p, o, a.ldOut);
+            }
+        }
+        if (in1) {
+            if (act1) {
+                double rss = s1.yy - sumsq_e(s1), mss = mss_from_e(s1, sd);
+                if (rss <= kExactThreshold * s1.yy && s1.yy > 0.0) exact_pass<KP>(s1, a.Y + v + 1, a.ldY, n, a.Qt, rss, mss);
+                finish_voxel<KP>(s1, rss, mss, sd, o + 1, a.ldOut);
+            } else {
+                zero_row<KP>(sd.p, o + 1, a.ldOut);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ LDG kernel (+ split-n)
+// blockDim = (TX, S).  Thread (x, s) accumulates subjects [s*n/S, (s+1)*n/S) of voxels
+// (blockIdx.x*TX + x)*VPT .. +VPT-1; slices are reduced through shared memory and slice 0
+// runs the epilogue.  Shared memory: max(S x JT x KP Q rows, S x (KP+1) x VPT x TX partials).
+template <int KP, int VPT>
+__global__ void __launch_bounds__(256)
+lm_fit_ldg_kernel(LmArgs a, int JT)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SmemDesign<KP> sd;
+    double *sQ = reinterpret_cast<double *>(smem_raw);
+    const int TX = blockDim.x, S = blockDim.y;
+    const int x = threadIdx.x, s = threadIdx.y;
+    const int tid = s * TX + x, nthreads = TX * S;
+    const int n = a.n;
+
+    load_design_to_smem<KP>(sd, a.design, tid, nthreads);
+    __syncthreads();
+
+    const int64_t v = ((int64_t)blockIdx.x * TX + x) * VPT;
+    bool in[VPT], act[VPT];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        in[i] = v + i < a.V;
+        act[i] = in[i] && (!a.mask || mask_selects(a.mask[v + i], a.mask_lo, a.mask_hi));
+        any |= act[i];
+    }
+    VoxelSums<KP> sum[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) sum[i].e[k] = 0.0;
+        sum[i].yy = 0.0;
+        sum[i].y0 = (sd.shift && act[i]) ? a.Y[v + i] : 0.0;
+    }
+    const int jb = (int)(((int64_t)s * n) / S), je = (int)(((int64_t)(s + 1) * n) / S);
+    const int span = (n + S - 1) / S;  // longest slice
+    const double *yp = a.Y + v;
+
+    for (int t0 = 0; t0 < span; t0 += JT) {
+        // every slice stages rows [jb + t0, jb + t0 + JT) of Qt into its own sub-tile
+        __syncthreads();
+        for (int sl = 0; sl < S; ++sl) {
+            const int b = (int)(((int64_t)sl * n) / S) + t0;
+            const int e = (int)(((int64_t)(sl + 1) * n) / S);
+            for (int i = tid; i < JT * KP; i += nthreads) {
+                const int j = b + i / KP;
+                sQ[(size_t)sl * JT * KP + i] = (j < e) ? a.Qt[(size_t)j * KP + (i % KP)] : 0.0;
+            }
+        }
+        __syncthreads();
+        if (!any) continue;
+        const double *q = sQ + (size_t)s * JT * KP;
+        const int cnt = min(JT, je - (jb + t0));
+        int jj = 0;
+        constexpr int U = 8;
+        for (; jj + U <= cnt; jj += U) {
+            double y[U][VPT];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double *src = yp + (int64_t)(jb + t0 + jj + u) * a.ldY;
+                if constexpr (VPT == 2) {
+                    const double2 t = ldg_stream2(src);
+                    y[u][0] = t.x;
+                    y[u][1] = t.y;
+                } else {
+                    y[u][0] = ldg_stream(src);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int i = 0; i < VPT; ++i) {
+                    const double yv = y[u][i] - sum[i].y0;
+                    sum[i].yy = fma(yv, yv, sum[i].yy);
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) sum[i].e[k] = fma(q[(jj + u) * KP + k], yv, sum[i].e[k]);
+                }
+            }
+        }
+        for (; jj < cnt; ++jj) {
+            const double *src = yp + (int64_t)(jb + t0 + jj) * a.ldY;
+#pragma unroll
+            for (int i = 0; i < VPT; ++i) {
+                // VPT == 2 is only launched when every pair is fully in range and aligned
+                const double yv = src[i] - sum[i].y0;
+                sum[i].yy = fma(yv, yv, sum[i].yy);
+#pragma unroll
+                for (int k = 0; k < KP; ++k) sum[i].e[k] = fma(q[jj * KP + k], yv, sum[i].e[k]);
+            }
+        }
+    }
+
+    if (S > 1) {
+        // cross-slice reduction; partial layout [slice][component][voxel-in-block]
+        __syncthreads();
+        double *red = reinterpret_cast<double *>(smem_raw);
+        const int W = TX * VPT;
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) red[((size_t)s * (KP + 1) + k) * W + x * VPT + i] = sum[i].e[k];
+            red[((size_t)s * (KP + 1) + KP) * W + x * VPT + i] = sum[i].yy;
+        }
+        __syncthreads();
+        if (s != 0) return;
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            for (int sl = 1; sl < S; ++sl) {
+#pragma unroll
+                for (int k = 0; k < KP; ++k) sum[i].e[k] += red[((size_t)sl * (KP + 1) + k) * W + x * VPT + i];
+                sum[i].yy += red[((size_t)sl * (KP + 1) + KP) * W + x * VPT + i];
+            }
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        if (!in[i]) continue;
+        double *o = a.out + v + i;
+        if (!act[i]) {
+            zero_row<KP>(sd.p, o, a.ldOut);
+            continue;
+        }
+        double rss = sum[i].yy - sumsq_e(sum[i]), mss = mss_from_e(sum[i], sd);
+        if (rss <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0)
+            exact_pass<KP>(sum[i], a.Y + v + i, a.ldY, n, a.Qt, rss, mss);
+        finish_voxel<KP>(sum[i], rss, mss, sd, o, a.ldOut);
+    }
+}
+
+// ------------------------------------------------------------------ host-side launchers
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int round_up_kp(int p)
+{
+    if (p <= 8) return p < 1 ? 1 : p;
+    if (p <= 12) return 12;
+    if (p <= 16) return 16;
+    if (p <= 24) return 24;
+    return 32;
+}
+
+template <int KP, int CW, int NJ, int STAGES>
+cudaError_t launch_tma_cfg(const LmArgs &a, const unsigned char *flags, int sm_count, cudaStream_t st)
+{
+    constexpr int TV = CW * 64;
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return cudaErrorNotSupported;
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t)a.V, (cuuint64_t)a.n};
+    const cuuint64_t strides[1] = {(cuuint64_t)a.ldY * sizeof(double)};
+    const cuuint32_t box[2] = {TV, NJ};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(a.Y), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    const int nq = ((a.n + NJ - 1) / NJ) * NJ;
+    const size_t smem = (size_t)STAGES * NJ * TV * 8 + (size_t)nq * KP * 8 + sizeof(SmemDesign<KP>) + 2 * STAGES * 8 + 128;
+    auto kern = lm_fit_tma_kernel<KP, CW, NJ, STAGES>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t ntiles = (a.V + TV - 1) / TV;
+    const int grid = (int)(ntiles < sm_count ? ntiles : sm_count);
+    kern<<<grid, (CW + 1) * 32, smem, st>>>(map, a, flags);
+    return cudaGetLastError();
+}
+
+template <int KP>
+size_t tma_smem_need(int n, int CW, int NJ, int STAGES)
+{
+    const int nq = ((n + NJ - 1) / NJ) * NJ;
+    return (size_t)STAGES * NJ * CW * 64 * 8 + (size_t)nq * KP * 8 + sizeof(SmemDesign<KP>) + 2 * STAGES * 8 + 128;
+}
+
+template <int KP>
+cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
+{
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0) && (a.ldY % 2 == 0);
+    bool use_tma = plan.variant == LmVariant::Tma ||
+                   (plan.variant == LmVariant::Auto && aligned16 && a.V >= (int64_t)plan.sm_count * 512);
+    if (use_tma && (!aligned16 || a.n > 0x7fffffff / 2 || a.V > 0x7fffffffLL)) use_tma = false;
+    constexpr int CW = 8, NJ = 8, STAGES = 4;  // 512-voxel tiles, 32 KiB stages, 128 KiB ring
+    if (use_tma && tma_smem_need<KP>(a.n, CW, NJ, STAGES) > 227 * 1024) use_tma = false;
+    if (use_tma) {
+        const unsigned char *flags = nullptr;
+        const int TV = CW * 64;
+        if (a.mask) {
+            const int64_t ntiles = (a.V + TV - 1) / TV;
+            cudaError_t e = scr.ensure_flags((size_t)ntiles, st);
+            if (e != cudaSuccess) return e;
+            mask_tile_flags_kernel<<<(unsigned)ntiles, 128, 0, st>>>(a.mask, a.V, TV, a.mask_lo, a.mask_hi, scr.flags, ntiles);
+            if (info) info->launches++;
+            flags = scr.flags;
+        }
+        cudaError_t e = launch_tma_cfg<KP, CW, NJ, STAGES>(a, flags, plan.sm_count, st);
+        if (info) { info->launches++; info->used_tma = 1; }
+        return e;
+    }
+    // ---- LDG path: pick voxels/thread, split factor and Q tile
+    const bool vec2 = aligned16 && (a.V % 2 == 0) && (a.ldOut % 2 == 0) && KP <= 16;
+    int S = plan.split;
+    if (S <= 0) {
+        // enough threads for ~2 waves of 1024 threads/SM; split the subject axis otherwise
+        S = 1;
+        const int64_t want = (int64_t)plan.sm_count * 2048;
+        while (S < 8 && (a.V / (vec2 ? 2 : 1)) * S < want && a.n / (S * 2) >= 64) S *= 2;
+    }
+    const int TX = S >= 4 ? 32 : (S == 2 ? 64 : 128);
+    const int VPT = vec2 ? 2 : 1;
+    const int span = (a.n + S - 1) / S;
+    int JT = span;
+    const size_t budget = 64 * 1024;
+    while ((size_t)S * JT * KP * 8 > budget) JT = (JT + 1) / 2;
+    size_t smem = (size_t)S * JT * KP * 8;
+    const size_t red = (size_t)S * (KP + 1) * VPT * TX * 8;
+    if (S > 1 && red > smem) smem = red;
+    const int64_t per_block = (int64_t)TX * VPT;
+    const int64_t blocks = (a.V + per_block - 1) / per_block;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    dim3 bd(TX, S);
+    cudaError_t e;
+    if (VPT == 2) {
+        auto kern = lm_fit_ldg_kernel<KP, (KP <= 16 ? 2 : 1)>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)blocks, bd, smem, st>>>(a, JT);
+    } else {
+        auto kern = lm_fit_ldg_kernel<KP, 1>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)blocks, bd, smem, st>>>(a, JT);
+    }
+    if (info) { info->launches++; info->used_tma = 0; info->split = S; }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int lm_padded_p(int p) { return round_up_kp(p); }
+
+cudaError_t launch_lm_fit(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
+{
+    if (a.V <= 0) return cudaSuccess;
+    switch (round_up_kp(a.p)) {
+#define RMG_CASE(K) case K: return launch_kp<K>(a, plan, scr, st, info);
+        RMG_CASE(1) RMG_CASE(2) RMG_CASE(3) RMG_CASE(4) RMG_CASE(5) RMG_CASE(6) RMG_CASE(7) RMG_CASE(8)
+        RMG_CASE(12) RMG_CASE(16) RMG_CASE(24) RMG_CASE(32)
+#undef RMG_CASE
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace rmg

@@ -1,0 +1,64 @@
+// lm_launch.hpp -- host-visible launch interface of the fit kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "lm_common.cuh"
+
+namespace rmg {
+
+// Device pointers only.  Y: V x n (ld ldY), out: V x (2p+3) (ld ldOut), mask: V or null.
+struct LmArgs {
+    const double *Y;
+    int64_t V, ldY;
+    int n, p;
+    const double *Qt;          // [n][KP] row-major, KP = lm_padded_p(p), columns >= rank are zero
+    const DevDesign *design;
+    const double *mask;
+    double mask_lo, mask_hi;
+    double *out;
+    int64_t ldOut;
+};
+
+enum class LmVariant { Auto = 0, Tma = 1, Ldg = 2 };
+
+struct LmPlan {
+    LmVariant variant = LmVariant::Auto;
+    int split = 0;       // LDG path: slices of the subject axis (0 = choose)
+    int sm_count = 148;
+};
+
+struct LmLaunchInfo {
+    int launches = 0;
+    int used_tma = 0;
+    int split = 1;
+};
+
+// Reusable device scratch owned by the caller (mask tile flags).
+struct LmScratch {
+    unsigned char *flags = nullptr;
+    size_t flags_cap = 0;
+    cudaError_t ensure_flags(size_t n, cudaStream_t st)
+    {
+        if (n <= flags_cap) return cudaSuccess;
+        release(st);
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&flags), n, st);
+        if (e == cudaSuccess) flags_cap = n;
+        return e;
+    }
+    // stream-ordered: safe while kernels that read the flags are still queued on st
+    void release(cudaStream_t st)
+    {
+        if (flags) cudaFreeAsync(flags, st);
+        flags = nullptr;
+        flags_cap = 0;
+    }
+};
+
+int lm_padded_p(int p);
+
+cudaError_t launch_lm_fit(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st,
+                          LmLaunchInfo *info);
+
+}  // namespace rmg

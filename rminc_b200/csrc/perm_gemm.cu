@@ -1,0 +1,477 @@
+// perm_gemm.cu -- see perm_gemm.cuh for the design.
+#include "perm_gemm.cuh"
+
+#include "async_ptx.cuh"
+
+namespace rmg {
+namespace {
+
+constexpr int KC = kPermKC, NT = kPermNT, PITCH = kPermPitch, STAGES = kPermStages;
+constexpr int WARPS_M = 4, WARPS_N = 2, WN = 4;  // warp tile: WM m8-tiles x 4 n8-tiles (32 voxels)
+constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
+
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct PermKernelParams {
+    const double *Y;
+    int64_t V, ldY;
+    int n, p, R, ncols, two_sided, shift;
+    int tcol[kPermMaxCols];          // coefficient index of each requested t-column
+    const double *Apack;             // [n_pt][n_kc][A chunk] fragment-major
+    const PermConst *pc;             // [R]
+    const double *y0;                // [V] first sample (0 when !shift)
+    const double *yy;                // [V] |y - y0|^2, or -1 for voxels outside the mask
+    unsigned long long *keys;        // [ncols][R]
+    const double *Qt;                // [R][n][KP] plain row-major copy of every Q_r (exact path)
+    unsigned char *vflag;            // [V] set when some permutation's one-pass rss lost too many digits
+    int n_pt, n_kc;
+};
+
+// ---- K5: one pass over Y for the per-voxel quantities every permutation shares.
+__global__ void __launch_bounds__(256)
+perm_prepass_kernel(const double *__restrict__ Y, int64_t V, int64_t ldY, int n, const double *__restrict__ mask,
+                    double lo, double hi, int shift, double *__restrict__ y0, double *__restrict__ yy,
+                    unsigned char *__restrict__ vflag, int *__restrict__ any_zero_row)
+{
+    const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (v >= V) return;
+    const bool two = v + 1 < V;
+    bool a0 = true, a1 = two;
+    if (mask) {
+        a0 = mask_selects(mask[v], lo, hi);
+        a1 = two && mask_selects(mask[v + 1], lo, hi);
+    }
+    double f0 = 0.0, f1 = 0.0, s0 = 0.0, s1 = 0.0;
+    if (a0 || a1) {
+        const double *yp = Y + v;
+        if (shift) {
+            f0 = yp[0];
+            if (two) f1 = yp[1];
+        }
+        int j = 0;
+        if (two) {  // V and ldY are even on this path: 16-byte loads
+            for (; j + 4 <= n; j += 4) {
+                double2 t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) t[u] = ldg_stream2(yp + (int64_t)(j + u) * ldY);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double a = t[u].x - f0, b = t[u].y - f1;
+                    s0 = fma(a, a, s0);
+                    s1 = fma(b, b, s1);
+                }
+            }
+        }
+        for (; j < n; ++j) {
+            const double a = yp[(int64_t)j * ldY] - f0;
+            s0 = fma(a, a, s0);
+            if (two) {
+                const double b = yp[(int64_t)j * ldY + 1] - f1;
+                s1 = fma(b, b, s1);
+            }
+        }
+    }
+    y0[v] = f0;
+    yy[v] = a0 ? s0 : -1.0;
+    vflag[v] = 0;
+    if (two) {
+        y0[v + 1] = f1;
+        yy[v + 1] = a1 ? s1 : -1.0;
+        vflag[v + 1] = 0;
+    }
+    if ((!a0 || (two && !a1)) && *any_zero_row == 0) *any_zero_row = 1;  // benign race: all writers store 1
+}
+
+// masked rows are 0 in every column and take part in the maximum (R/minc_voxel_statistics.R:1488)
+__global__ void perm_floor_keys_kernel(unsigned long long *keys, int nk, const int *any_zero_row)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nk && *any_zero_row) atomicMax(&keys[i], ordered_key(0.0));
+}
+
+// final: monotone proxy m = sign(b) b^2 / rss  ->  t = sign(m) sqrt(|m| * rdf / ct)
+__global__ void perm_finalize_keys_kernel(unsigned long long *keys, const PermConst *pc, PermKernelParams P)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.R * P.ncols) return;
+    const int c = i / P.R, r = i % P.R;
+    const double m = ordered_value(keys[i]);
+    double t = m;
+    if (isfinite(m)) {
+        const double mag = sqrt(fabs(m) * pc[r].rdf / pc[r].ct[P.tcol[c]]);
+        t = m < 0.0 ? -mag : mag;
+        if (!isfinite(t)) t = 0.0;
+    }
+    keys[i] = ordered_key(t);
+}
+
+// ---- rare path: voxels for which some permutation's one-pass rss = |y'|^2 - |e'|^2 lost too
+//      many digits (the permuted model explains > 99.9 % of the voxel).  The GEMM skips those
+//      (permutation, voxel) pairs and raises vflag[v]; this kernel refits EVERY permutation of a
+//      flagged voxel with explicit residuals (max is idempotent, so re-adding pairs the GEMM did
+//      handle is harmless).  One CTA per flagged voxel, permutations across threads.
+template <int KP>
+__global__ void __launch_bounds__(128)
+perm_exact_voxels_kernel(PermKernelParams P)
+{
+    for (int64_t v = blockIdx.x; v < P.V; v += gridDim.x) {
+        if (!P.vflag[v]) continue;
+        const double *y = P.Y + v;
+        const double y0 = P.y0[v];
+        for (int r = threadIdx.x; r < P.R; r += blockDim.x) {
+            const double *Q = P.Qt + (size_t)r * P.n * KP;
+            const PermConst &pc = P.pc[r];
+            double e[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) e[k] = 0.0;
+            for (int j = 0; j < P.n; ++j) {
+                const double yv = y[(int64_t)j * P.ldY] - y0;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) e[k] = fma(__ldg(Q + (size_t)j * KP + k), yv, e[k]);
+            }
+            double rss = 0.0;
+            for (int j = 0; j < P.n; ++j) {
+                double fit = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) fit = fma(__ldg(Q + (size_t)j * KP + k), e[k], fit);
+                const double res = (y[(int64_t)j * P.ldY] - y0) - fit;
+                rss = fma(res, res, rss);
+            }
+#pragma unroll
+            for (int k = 0; k < KP; ++k) e[k] = fma(y0, pc.q1[k], e[k]);  // un-shift
+            for (int c = 0; c < P.ncols; ++c) {
+                const int ci = P.tcol[c];
+                double b = 0.0;
+#pragma unroll
+                for (int j = 0; j < KP; ++j) b = fma(pc.Rinv[ci * 8 + j], e[j], b);
+                double s = b * b / rss;
+                if (!P.two_sided && b < 0.0) s = -s;
+                if (!isfinite(s)) s = 0.0;
+                atomicMax(&P.keys[(size_t)c * P.R + r], ordered_key(s));
+            }
+        }
+    }
+}
+
+// ---- the GEMM + fused statistics
+template <int KP, int PG>
+__global__ void __launch_bounds__((CONSUMER_WARPS + 1) * 32, 1)
+perm_gemm_kernel(PermKernelParams P)
+{
+    constexpr int WM = KP * PG;                           // m8-tiles per warp
+    constexpr int A_CHUNK = WARPS_M * (KC / 4) * WM * 32; // doubles per stage
+    constexpr int B_CHUNK = KC * PITCH;
+    constexpr int PERMS_PER_CTA = WARPS_M * PG * 8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sA = reinterpret_cast<double *>(smem_raw);
+    double *sB = sA + (size_t)STAGES * A_CHUNK;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sB + (size_t)STAGES * B_CHUNK);
+    uint64_t *empty = full + STAGES;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CONSUMER_WARPS);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const int64_t n_vt = (P.V + NT - 1) / NT;
+    const int n = P.n;
+
+    if (warp == CONSUMER_WARPS) {
+        // ===== producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t vt = blockIdx.x; vt < n_vt; vt += gridDim.x) {
+                const int64_t v0 = vt * NT;
+                const int cols_here = (int)min((int64_t)NT, P.V - v0);
+                const uint32_t row_bytes = (uint32_t)cols_here * 8u;
+                for (int pt = 0; pt < P.n_pt; ++pt) {
+                    for (int kc = 0; kc < P.n_kc; ++kc) {
+                        const int j0 = kc * KC;
+                        const int rows = min(KC, n - j0);
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_expect_tx(&full[stage], (uint32_t)(A_CHUNK * 8) + rows * row_bytes);
+                        bulk_load_1d(sA + (size_t)stage * A_CHUNK,
+                                     P.Apack + ((size_t)pt * P.n_kc + kc) * A_CHUNK, A_CHUNK * 8, &full[stage]);
+                        double *bdst = sB + (size_t)stage * B_CHUNK;
+                        const double *bsrc = P.Y + v0 + (int64_t)j0 * P.ldY;
+                        for (int r = 0; r < rows; ++r)
+                            bulk_load_1d(bdst + r * PITCH, bsrc + (int64_t)r * P.ldY, row_bytes, &full[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers
+    const int warp_m = warp / WARPS_N, warp_n = warp % WARPS_N;
+    const int g = lane >> 2, q = lane & 3;
+    uint32_t stage = 0, phase = 0;
+
+    for (int64_t vt = blockIdx.x; vt < n_vt; vt += gridDim.x) {
+        const int64_t vbase = vt * NT + warp_n * 32 + 2 * q;  // + nt*8 + h
+        for (int pt = 0; pt < P.n_pt; ++pt) {
+            double acc[WM][WN][2];
+#pragma unroll
+            for (int mt = 0; mt < WM; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < WN; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+            for (int kc = 0; kc < P.n_kc; ++kc) {
+                const int j0 = kc * KC;
+                const int ksteps = min(KC / 4, (n - j0 + 3) / 4);
+                mbar_wait(&full[stage], phase);
+                const double2 *As = reinterpret_cast<const double2 *>(sA + (size_t)stage * A_CHUNK) +
+                                    (size_t)warp_m * (KC / 8) * WM * 32 + lane;
+                const double *Bs = sB + (size_t)stage * B_CHUNK + q * PITCH + warp_n * 32 + g;
+#pragma unroll
+                for (int ks2 = 0; ks2 < KC / 8; ++ks2) {
+                    if (ks2 * 2 < ksteps) {
+                        double2 a[WM];
+#pragma unroll
+                        for (int mt = 0; mt < WM; ++mt) a[mt] = As[(ks2 * WM + mt) * 32];
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const int ks = ks2 * 2 + half;
+                            if (ks < ksteps) {
+                                double b[WN];
+                                const bool real = (j0 + ks * 4 + q) < n;  // padding rows hold stale data
+#pragma unroll
+                                for (int nt = 0; nt < WN; ++nt) {
+                                    const double t = Bs[ks * 4 * PITCH + nt * 8];
+                                    b[nt] = real ? t : 0.0;
+                                }
+#pragma unroll
+                                for (int mt = 0; mt < WM; ++mt)
+#pragma unroll
+                                    for (int nt = 0; nt < WN; ++nt)
+                                        dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], half ? a[mt].y : a[mt].x, b[nt]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+
+            // ---- fused epilogue: this thread holds, for PG permutations, all KP components of
+            //      e = Q_r'y for 8 voxels (nt = 0..3, h = 0..1).
+#pragma unroll
+            for (int pg = 0; pg < PG; ++pg) {
+                const int r = pt * PERMS_PER_CTA + (warp_m * PG + pg) * 8 + g;
+                const bool rvalid = r < P.R;
+                const PermConst &pc = P.pc[rvalid ? r : 0];
+                // inv > 0: 1/rss of a regular fit; 0: non-finite statistic (counts as 0); < 0: no contribution
+                double inv[WN][2];
+                {
+                    double q1[KP];
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) q1[k] = pc.q1[k];
+#pragma unroll
+                    for (int nt = 0; nt < WN; ++nt) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int64_t v = vbase + nt * 8 + h;
+                            double w = -1.0;
+                            if (rvalid && v < P.V) {
+                                const double yy = P.yy[v];
+                                if (yy >= 0.0) {  // yy < 0 marks a voxel outside the mask (global 0 floor)
+                                    const double y0 = P.y0[v];
+                                    double ee = 0.0;
+#pragma unroll
+                                    for (int k = 0; k < KP; ++k) {
+                                        const double es = fma(-y0, q1[k], acc[pg * KP + k][nt][h]);
+                                        ee = fma(es, es, ee);
+                                    }
+                                    const double rss = yy - ee;
+                                    if (yy > 0.0 && rss <= kExactThreshold * yy) {
+                                        P.vflag[v] = 1;  // model explains ~everything: explicit residuals later
+                                    } else if (rss > 0.0 && isfinite(rss)) {
+                                        w = 1.0 / rss;
+                                    } else {
+                                        w = 0.0;
+                                    }
+                                }
+                            }
+                            inv[nt][h] = w;
+                        }
+                    }
+                }
+#pragma unroll 1
+                for (int c = 0; c < P.ncols; ++c) {
+                    const int ci = P.tcol[c];
+                    double rrow[KP];
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) rrow[j] = pc.Rinv[ci * 8 + j];
+                    double best = -INFINITY;
+#pragma unroll
+                    for (int nt = 0; nt < WN; ++nt) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const double w = inv[nt][h];
+                            if (w > 0.0) {
+                                double b = 0.0;
+#pragma unroll
+                                for (int j = 0; j < KP; ++j) b = fma(rrow[j], acc[pg * KP + j][nt][h], b);
+                                double s = b * b * w;
+                                if (!P.two_sided && b < 0.0) s = -s;
+                                if (!isfinite(s)) s = 0.0;
+                                best = fmax(best, s);
+                            } else if (w == 0.0) {
+                                best = fmax(best, 0.0);
+                            }
+                        }
+                    }
+                    // the 4 lanes of a quad hold different voxels of the same permutation
+                    best = fmax(best, __shfl_xor_sync(0xffffffffu, best, 1));
+                    best = fmax(best, __shfl_xor_sync(0xffffffffu, best, 2));
+                    if (q == 0 && rvalid && best > -INFINITY) atomicMax(&P.keys[(size_t)c * P.R + r], ordered_key(best));
+                }
+            }
+        }
+    }
+}
+
+template <int KP, int PG>
+cudaError_t launch_gemm(const PermKernelParams &P, int sm_count, cudaStream_t st)
+{
+    constexpr int WM = KP * PG;
+    constexpr int A_CHUNK = WARPS_M * (KC / 4) * WM * 32;
+    const size_t smem = (size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + 2 * STAGES * 8;
+    auto kern = perm_gemm_kernel<KP, PG>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t n_vt = (P.V + NT - 1) / NT;
+    const int grid = (int)std::min<int64_t>(n_vt, sm_count);
+    kern<<<grid, (CONSUMER_WARPS + 1) * 32, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+constexpr int pg_for(int kp) { return kp == 1 ? 8 : kp == 2 ? 4 : kp <= 4 ? 2 : 1; }
+
+}  // namespace
+
+bool perm_gemm_supported(int n, int p, int64_t V, int64_t ldY, const double *dY, const int32_t *hcols, int ncols)
+{
+    if (ncols < 1 || ncols > kPermMaxCols) return false;
+    for (int c = 0; c < ncols; ++c)
+        if (hcols[c] < p + 2 || hcols[c] > 2 * p + 1) return false;  // fused epilogue covers the tvalue- columns
+    return p >= 1 && p <= 8 && n >= 4 && V >= 2 && V % 2 == 0 && ldY % 2 == 0 && V < 0x7fffffffLL &&
+           (reinterpret_cast<uintptr_t>(dY) & 15) == 0;
+}
+
+cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &designs, bool all_intercept,
+                          int sm_count, cudaStream_t st, int *launches, void **workspace_out)
+{
+    const int R = a.R, n = a.n, p = a.p, KP = p;
+    const int PG = pg_for(KP);
+    const int WM = KP * PG;
+    const int A_CHUNK = WARPS_M * (KC / 4) * WM * 32;
+    const int perms_per_cta = WARPS_M * PG * 8;
+    const int n_pt = (R + perms_per_cta - 1) / perms_per_cta;
+    const int n_kc = (n + KC - 1) / KC;
+
+    // ---- host packing: A in fragment order, plain Qt for the redo path, per-permutation constants
+    std::vector<double> Apack((size_t)n_pt * n_kc * A_CHUNK, 0.0);
+    std::vector<double> Qt((size_t)R * n * KP, 0.0);
+    std::vector<PermConst> pc(R);
+    for (int r = 0; r < R; ++r) {
+        const Design &D = designs[r];
+        PermConst &c = pc[r];
+        std::memset(&c, 0, sizeof c);
+        for (int i = 0; i < p; ++i) {
+            c.q1[i] = D.q1[i];
+            c.ct[i] = D.ct[i];
+            for (int j = 0; j < p; ++j) c.Rinv[i * 8 + j] = D.Rinv[i + (size_t)j * p];
+        }
+        c.rdf = (double)(n - p);
+        const int pt = r / perms_per_cta, rr = r % perms_per_cta;
+        const int warp_m = rr / (PG * 8), pg = (rr / 8) % PG, g = rr % 8;
+        for (int k = 0; k < D.k; ++k) {
+            const double *qcol = D.Q.data() + (size_t)k * n;
+            const int mt = pg * KP + k;
+            for (int j = 0; j < n; ++j) {
+                Qt[((size_t)r * n + j) * KP + k] = qcol[j];
+                const int kc = j / KC, jj = j % KC, ks = jj / 4, q = jj % 4;
+                const int lane = g * 4 + q;
+                // [pt][kc] chunk, inside: [warp_m][ks/2][mt][lane][ks%2]
+                const size_t off = (((size_t)pt * n_kc + kc) * A_CHUNK) +
+                                   ((((size_t)warp_m * (KC / 8) + ks / 2) * WM + mt) * 32 + lane) * 2 + (ks % 2);
+                Apack[off] = qcol[j];
+            }
+        }
+    }
+
+    // ---- one workspace allocation
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+    const size_t oA = carve(Apack.size() * 8), oQ = carve(Qt.size() * 8), oP = carve(pc.size() * sizeof(PermConst));
+    const size_t oY0 = carve((size_t)a.V * 8), oYY = carve((size_t)a.V * 8), oFlag = carve(256), oVf = carve((size_t)a.V);
+    char *ws = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ws), off, st);
+    if (e != cudaSuccess) return e;
+    *workspace_out = ws;
+    e = cudaMemcpyAsync(ws + oA, Apack.data(), Apack.size() * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ws + oQ, Qt.data(), Qt.size() * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ws + oP, pc.data(), pc.size() * sizeof(PermConst), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws + oFlag, 0, 256, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // pageable sources must outlive the copies
+    if (e != cudaSuccess) return e;
+
+    PermKernelParams P;
+    std::memset(&P, 0, sizeof P);
+    P.Y = a.Y; P.V = a.V; P.ldY = a.ldY; P.n = n; P.p = p; P.R = R; P.ncols = a.ncols; P.two_sided = a.two_sided;
+    P.shift = all_intercept ? 1 : 0;
+    P.Apack = reinterpret_cast<double *>(ws + oA);
+    P.pc = reinterpret_cast<PermConst *>(ws + oP);
+    P.y0 = reinterpret_cast<double *>(ws + oY0);
+    P.yy = reinterpret_cast<double *>(ws + oYY);
+    P.keys = a.keys;
+    P.Qt = reinterpret_cast<double *>(ws + oQ);
+    P.vflag = reinterpret_cast<unsigned char *>(ws + oVf);
+    P.n_pt = n_pt;
+    P.n_kc = n_kc;
+    int *any_zero = reinterpret_cast<int *>(ws + oFlag);
+    for (int c = 0; c < a.ncols; ++c) P.tcol[c] = a.hcols[c] - (p + 2);
+
+    const int64_t pairs = (a.V + 1) / 2;
+    perm_prepass_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(a.Y, a.V, a.ldY, n, a.mask, a.mask_lo, a.mask_hi,
+                                                                           P.shift, reinterpret_cast<double *>(ws + oY0),
+                                                                           reinterpret_cast<double *>(ws + oYY), P.vflag, any_zero);
+    const int nk = R * a.ncols;
+    perm_floor_keys_kernel<<<(nk + 255) / 256, 256, 0, st>>>(a.keys, nk, any_zero);
+    *launches += 2;
+    switch (KP) {
+#define RMG_PG_CASE(K) case K: e = launch_gemm<K, pg_for(K)>(P, sm_count, st); break;
+        RMG_PG_CASE(1) RMG_PG_CASE(2) RMG_PG_CASE(3) RMG_PG_CASE(4) RMG_PG_CASE(5) RMG_PG_CASE(6) RMG_PG_CASE(7) RMG_PG_CASE(8)
+#undef RMG_PG_CASE
+    default: e = cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return e;
+    {
+        const int eg = (int)std::min<int64_t>(a.V, (int64_t)sm_count * 16);
+        switch (KP) {
+#define RMG_EX_CASE(K) case K: perm_exact_voxels_kernel<K><<<eg, 128, 0, st>>>(P); break;
+            RMG_EX_CASE(1) RMG_EX_CASE(2) RMG_EX_CASE(3) RMG_EX_CASE(4) RMG_EX_CASE(5) RMG_EX_CASE(6) RMG_EX_CASE(7) RMG_EX_CASE(8)
+#undef RMG_EX_CASE
+        }
+        *launches += 1;
+    }
+    perm_finalize_keys_kernel<<<(nk + 255) / 256, 256, 0, st>>>(a.keys, P.pc, P);
+    *launches += 2;
+    return cudaGetLastError();
+}
+
+}  // namespace rmg

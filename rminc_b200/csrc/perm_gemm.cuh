@@ -1,0 +1,102 @@
+// perm_gemm.cuh -- permutation test as one stacked FP64 tensor-core GEMM (piece K3).
+//
+// For permutation r the refit needs e_r(v) = Q_r' y_v for every voxel v, where Q_r is the
+// thin orthonormal factor of the permuted design X[idx_r, ].  Stacking the Q_r' of many
+// permutations gives A (rows = permutation x component, cols = subjects) and the whole test is
+//     E = A (R*KP x n)  *  Y' (n x V)                      2*KP*n*V flop per permutation
+// after which t_{r,i}(v) = (Rinv_r e_r)_i / sqrt(ct_{r,i} * rss_r(v) / (n-p)) with
+// rss_r(v) = |y_v - y0_v|^2 - |e_r - y0_v Q_r'1|^2.  Only the maximum over voxels of each
+// statistic is kept (R/minc_voxel_statistics.R:1484-1488), so nothing of size R x V is ever
+// written: the epilogue reduces straight into an R x ncols buffer.
+//
+// Kernel shape (sm_100a; tcgen05/UMMA has no FP64 kind, so the tensor-core path for FP64 is
+// mma.sync DMMA m8n8k4):
+//   CTA tile  = 4x2 consumer warps = (32*PG permutations x KP components) x 64 voxels,
+//               + 1 producer warp.  Persistent CTAs; voxel tiles outer, permutation tiles
+//               inner, so each CTA's 64 x n slab of Y is fetched from HBM once and re-read from
+//               L2 for the other permutation tiles, while A (16 MB at R=1000) lives in L2.
+//   staging   = cp.async.bulk (TMA 1-D) into a 4-stage shared-memory ring guarded by
+//               mbarriers.  A is pre-packed on the host in MMA-fragment order, so one
+//               contiguous bulk copy per stage lands it conflict-free; Y rows are copied with
+//               a pitch of 68 doubles (== 4 mod 16), which makes the B-fragment loads
+//               conflict-free without a transpose.
+//   epilogue  = per (permutation, voxel): rss, beta for the requested t-columns, the
+//               monotone proxy sign(beta) beta^2 / rss, non-finite -> 0, running max in
+//               registers, one ordered-integer atomicMax per (permutation, column) per warp.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "design.hpp"
+#include "lm_common.cuh"
+
+namespace rmg {
+
+// ---- order-preserving map double -> uint64 (so atomicMax on integers is a max on doubles)
+__host__ __device__ __forceinline__ unsigned long long ordered_key(double x)
+{
+#ifdef __CUDA_ARCH__
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+#else
+    unsigned long long b;
+    std::memcpy(&b, &x, 8);
+#endif
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double ordered_value(unsigned long long k)
+{
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    double x;
+    std::memcpy(&x, &b, 8);
+    return x;
+#endif
+}
+
+// new_mod[!is.finite(new_mod)] <- 0; abs() if two-sided  (R/minc_voxel_statistics.R:1478,1484)
+__device__ __forceinline__ double perm_stat_filter(double s, int two_sided)
+{
+    if (!isfinite(s)) s = 0.0;
+    return two_sided ? fabs(s) : s;
+}
+
+struct PermGemmArgs {
+    const double *Y;
+    int64_t V, ldY;
+    int n, p;
+    const double *mask;
+    double mask_lo, mask_hi;
+    const int32_t *hcols;  // HOST copy of the requested result columns
+    int ncols, two_sided;
+    unsigned long long *keys;  // device, [ncols][R] ordered keys, initialised to key(-inf)
+    int R;
+};
+
+constexpr int kPermKC = 16;       // subjects per pipeline stage
+constexpr int kPermNT = 64;       // voxels per CTA tile
+constexpr int kPermPitch = 68;    // doubles per staged Y row (68 == 4 mod 16: conflict-free B fragments)
+constexpr int kPermStages = 4;
+constexpr int kPermMaxCols = 8;
+
+// per-permutation constants read by the epilogue (KP <= 8)
+struct PermConst {
+    double q1[8];
+    double Rinv[64];   // row-major 8 x 8
+    double ct[8];
+    double rdf;
+    double pad[7];
+};
+
+bool perm_gemm_supported(int n, int p, int64_t V, int64_t ldY, const double *dY, const int32_t *hcols, int ncols);
+
+cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &designs, bool all_intercept,
+                          int sm_count, cudaStream_t st, int *launches, void **workspace_out);
+
+}  // namespace rmg

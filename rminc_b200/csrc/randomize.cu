@@ -1,0 +1,316 @@
+// randomize.cu -- mincRandomize on the device (SURVEY.md pieces K3/K4/K5).
+//
+// Reference: R/minc_voxel_statistics.R:1465-1497.  Each permutation r refits every voxel
+// with X_pi = X[idx[, r], ] and the same Y and mask, sets non-finite statistics to 0
+// (:1478), takes abs() when two-sided (:1484-1486) and records the column maxima over ALL
+// V rows (:1488; masked rows are 0).  The reference re-runs the whole mincLm call,
+// re-reading every file, once per permutation.
+//
+// Here every permuted design is factored on the host (microseconds each), Y stays resident
+// in HBM, and the per-permutation maxima are reduced on the device into an R x ncols
+// buffer with ordered-integer atomicMax.  Voxel shards on several GPUs are combined by the
+// caller with an element-wise max (NCCL all-reduce(max) in rminc_b200/parallel.py, a host
+// max in rmg_randomize_multi).
+//
+// Two execution paths produce the same numbers:
+//   "refit": one streaming fit (lm_kernels.cu) per permutation into a scratch result
+//            matrix + a column-max reduction.  HBM-bound: R passes over Y.
+//   "gemm":  K permutations share each pass over Y -- stacked (K*p) x n by n x V FP64
+//            tensor-core GEMM (mma.sync DMMA) with the statistics + max fused in the
+//            epilogue (see perm_gemm.cuh).
+#include <algorithm>
+#include <cmath>
+#include <thread>
+
+#include "capi_common.hpp"
+#include "perm_gemm.cuh"
+
+namespace rmg {
+namespace {
+
+__global__ void keys_init_kernel(unsigned long long *keys, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ordered_key(-INFINITY);
+}
+
+__global__ void keys_decode_kernel(const unsigned long long *keys, double *dist, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dist[i] = ordered_value(keys[i]);
+}
+
+// Column maxima of one fitted result matrix (V x ncol_total, ld) for the selected columns,
+// merged into keys[c * R + r].
+__global__ void __launch_bounds__(256)
+colmax_kernel(const double *__restrict__ out, int64_t V, int64_t ld, const int32_t *__restrict__ cols, int ncols,
+              int two_sided, unsigned long long *__restrict__ keys, int R, int r)
+{
+    __shared__ double red[8];
+    for (int c = 0; c < ncols; ++c) {
+        const double *col = out + (int64_t)cols[c] * ld;
+        double best = -INFINITY;
+        for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x)
+            best = fmax(best, perm_stat_filter(col[v], two_sided));
+        for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double b = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+            for (int o = 4; o > 0; o >>= 1) b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+            if (threadIdx.x == 0) atomicMax(&keys[(size_t)c * R + r], ordered_key(b));
+        }
+        __syncthreads();
+    }
+}
+
+struct PermDesigns {
+    std::vector<Design> designs;  // one per permutation
+    bool all_intercept = true;
+};
+
+// Factor every permuted design; translate the reference's error contract.
+int factor_permutations(const double *X, int n, int p, const int32_t *idx, int R, PermDesigns &pd, char *err,
+                        size_t errlen)
+{
+    for (size_t i = 0; i < (size_t)n * p; ++i)
+        if (!std::isfinite(X[i])) return fail(err, errlen, RMG_ERR_INVALID, "model matrix contains non-finite values");
+    pd.designs.resize(R);
+    std::vector<double> Xp((size_t)n * p);
+    for (int r = 0; r < R; ++r) {
+        for (int i = 0; i < n; ++i) {
+            const int32_t src = idx[i + (size_t)r * n];
+            if (src < 0 || src >= n) return fail(err, errlen, RMG_ERR_INVALID, "idx[%d, %d] = %d out of range", i, r, src);
+            for (int j = 0; j < p; ++j) Xp[i + (size_t)j * n] = X[src + (size_t)j * n];
+        }
+        const int info = factor_design(Xp.data(), n, p, pd.designs[r]);
+        if (info > 0)
+            return fail(err, errlen, RMG_ERR_SINGULAR, "permutation %d: %s", r + 1, singular_message(info).c_str());
+        pd.all_intercept = pd.all_intercept && pd.designs[r].has_intercept;
+    }
+    return RMG_OK;
+}
+
+enum class PermPath { Auto, Refit, Gemm };
+
+PermPath perm_path_from_env()
+{
+    if (const char *v = std::getenv("RMG_PERM_PATH")) {
+        if (!std::strcmp(v, "refit")) return PermPath::Refit;
+        if (!std::strcmp(v, "gemm")) return PermPath::Gemm;
+    }
+    return PermPath::Auto;
+}
+
+}  // namespace
+}  // namespace rmg
+
+using namespace rmg;
+
+extern "C" {
+
+int rmg_randomize_device(const double *dY, int64_t V, int64_t ldY, int n, const double *X, int p,
+                         const double *dmask, double mask_lo, double mask_hi, const int32_t *idx, int R,
+                         const int32_t *cols, int ncols, int two_sided, double *ddist, int device, void *stream,
+                         char *err, size_t errlen)
+{
+    int rc = check_fit_args(dY, V, ldY, n, X, p, dY, ldY, err, errlen);
+    if (rc) return rc;
+    if (R < 0 || ncols < 0 || (R > 0 && !idx) || (ncols > 0 && !cols) || (R > 0 && ncols > 0 && !ddist))
+        return fail(err, errlen, RMG_ERR_INVALID, "bad permutation arguments");
+    for (int c = 0; c < ncols; ++c)
+        if (cols[c] < 0 || cols[c] >= 2 * p + 3) return fail(err, errlen, RMG_ERR_INVALID, "cols[%d] out of range", c);
+    PermDesigns pd;
+    if ((rc = factor_permutations(X, n, p, idx, R, pd, err, errlen))) return rc;
+    if ((rc = select_device(device, err, errlen))) return rc;
+    if (R == 0 || ncols == 0) return RMG_OK;
+
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nk = R * ncols;
+    unsigned long long *keys = nullptr;
+    int32_t *dcols = nullptr;
+    double *scratch = nullptr;
+    void *gemm_ws = nullptr;
+    LmScratch scr;
+    LmPlan plan;
+    plan.sm_count = device_sm_count(device);
+    int64_t launches = 0;
+    const PermPath path = perm_path_from_env();
+    {
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&keys), (size_t)nk * sizeof(unsigned long long), st));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dcols), (size_t)ncols * sizeof(int32_t), st));
+        RMG_CUDA(cudaMemcpyAsync(dcols, cols, (size_t)ncols * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        keys_init_kernel<<<(nk + 255) / 256, 256, 0, st>>>(keys, nk);
+        ++launches;
+
+        bool done = false;
+        if (path != PermPath::Refit && V > 0 && perm_gemm_supported(n, p, V, ldY, dY, cols, ncols)) {
+            PermGemmArgs ga{dY, V, ldY, n, p, dmask, mask_lo, mask_hi, cols, ncols, two_sided, keys, R};
+            int gl = 0;
+            cudaError_t ge = perm_gemm_run(ga, pd.designs, pd.all_intercept, plan.sm_count, st, &gl, &gemm_ws);
+            launches += gl;
+            if (ge != cudaSuccess) {
+                rc = fail(err, errlen, RMG_ERR_CUDA, "permutation GEMM failed: %s", cudaGetErrorString(ge));
+                goto cleanup;
+            }
+            done = true;
+        } else if (path == PermPath::Gemm) {
+            rc = fail(err, errlen, RMG_ERR_INVALID, "RMG_PERM_PATH=gemm but the GEMM path does not support this shape");
+            goto cleanup;
+        }
+        if (!done) {
+            // refit path: one streaming fit per permutation + column maxima
+            const int ncol_total = 2 * p + 3;
+            const int64_t ldo = (V + 1) & ~int64_t(1);
+            RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)ldo * ncol_total * sizeof(double), st));
+            const int KP = lm_padded_p(p);
+            DevDesign *dd = nullptr;
+            double *qt = nullptr;
+            RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dd), sizeof(DevDesign) * (size_t)R, st));
+            RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&qt), sizeof(double) * (size_t)R * n * KP, st));
+            {
+                std::vector<DevDesign> hdd(R);
+                std::vector<double> hqt((size_t)R * n * KP);
+                for (int r = 0; r < R; ++r) {
+                    fill_dev_design(pd.designs[r], hdd[r]);
+                    const std::vector<double> q = make_qt(pd.designs[r], KP);
+                    std::copy(q.begin(), q.end(), hqt.begin() + (size_t)r * n * KP);
+                }
+                cudaError_t e1 = cudaMemcpyAsync(dd, hdd.data(), sizeof(DevDesign) * (size_t)R, cudaMemcpyHostToDevice, st);
+                cudaError_t e2 = cudaMemcpyAsync(qt, hqt.data(), sizeof(double) * hqt.size(), cudaMemcpyHostToDevice, st);
+                // large pageable sources are not staged: wait before the host vectors die
+                cudaError_t e3 = cudaStreamSynchronize(st);
+                if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+                    cudaFreeAsync(dd, st);
+                    cudaFreeAsync(qt, st);
+                    rc = fail(err, errlen, RMG_ERR_CUDA, "uploading permuted designs failed");
+                    goto cleanup;
+                }
+            }
+            const int cm_grid = (int)std::min<int64_t>((V + 255) / 256, (int64_t)plan.sm_count * 8);
+            cudaError_t le = cudaSuccess;
+            for (int r = 0; r < R && le == cudaSuccess; ++r) {
+                LmArgs a{dY, V, ldY, n, p, qt + (size_t)r * n * KP, dd + r, dmask, mask_lo, mask_hi, scratch, ldo};
+                LmLaunchInfo info;
+                le = launch_lm_fit(a, plan, scr, st, &info);
+                launches += info.launches;
+                if (le != cudaSuccess) break;
+                colmax_kernel<<<cm_grid, 256, 0, st>>>(scratch, V, ldo, dcols, ncols, two_sided, keys, R, r);
+                ++launches;
+                le = cudaGetLastError();
+            }
+            cudaFreeAsync(dd, st);
+            cudaFreeAsync(qt, st);
+            if (le != cudaSuccess) {
+                rc = fail(err, errlen, RMG_ERR_CUDA, "permutation refit failed: %s", cudaGetErrorString(le));
+                goto cleanup;
+            }
+        }
+        keys_decode_kernel<<<(nk + 255) / 256, 256, 0, st>>>(keys, ddist, nk);
+        ++launches;
+        RMG_CUDA(cudaGetLastError());
+    }
+cleanup:
+    g_launch_count += launches;
+    if (keys) cudaFreeAsync(keys, st);
+    if (dcols) cudaFreeAsync(dcols, st);
+    if (scratch) cudaFreeAsync(scratch, st);
+    if (gemm_ws) cudaFreeAsync(gemm_ws, st);
+    scr.release(st);
+    if (rc != RMG_OK) cudaGetLastError();
+    return rc;
+}
+
+int rmg_randomize(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
+                  double mask_lo, double mask_hi, const int32_t *idx, int R, const int32_t *cols, int ncols,
+                  int two_sided, double *dist, int device, char *err, size_t errlen)
+{
+    int rc = check_fit_args(Y, V, ldY, n, X, p, Y, ldY, err, errlen);
+    if (rc) return rc;
+    if (R < 0 || ncols < 0 || (R > 0 && ncols > 0 && !dist)) return fail(err, errlen, RMG_ERR_INVALID, "bad permutation arguments");
+    if ((rc = select_device(device, err, errlen))) return rc;
+    if (R == 0 || ncols == 0) return RMG_OK;
+    // Y is staged once and stays resident for all R permutations.
+    const int64_t ldd = std::max<int64_t>(2, (V + 1) & ~int64_t(1));
+    double *dY = nullptr, *dM = nullptr, *dD = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    g_last_kernel_ms = 0.0;
+    {
+        RMG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        RMG_CUDA(cudaEventCreate(&e0));
+        RMG_CUDA(cudaEventCreate(&e1));
+        RMG_CUDA(cudaMalloc(&dY, (size_t)ldd * n * sizeof(double)));
+        RMG_CUDA(cudaMalloc(&dD, (size_t)R * ncols * sizeof(double)));
+        if (V > 0)
+            RMG_CUDA(cudaMemcpy2DAsync(dY, (size_t)ldd * 8, Y, (size_t)ldY * 8, (size_t)V * 8, (size_t)n,
+                                       cudaMemcpyHostToDevice, st));
+        if (mask && V > 0) {
+            RMG_CUDA(cudaMalloc(&dM, (size_t)V * sizeof(double)));
+            RMG_CUDA(cudaMemcpyAsync(dM, mask, (size_t)V * 8, cudaMemcpyHostToDevice, st));
+        }
+        RMG_CUDA(cudaEventRecord(e0, st));
+        rc = rmg_randomize_device(dY, V, ldd, n, X, p, mask ? dM : nullptr, mask_lo, mask_hi, idx, R, cols, ncols,
+                                  two_sided, dD, device, st, err, errlen);
+        if (rc) goto cleanup;
+        RMG_CUDA(cudaEventRecord(e1, st));
+        RMG_CUDA(cudaMemcpyAsync(dist, dD, (size_t)R * ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
+        RMG_CUDA(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) g_last_kernel_ms = ms;
+    }
+cleanup:
+    if (st) cudaStreamSynchronize(st);
+    if (dY) cudaFree(dY);
+    if (dM) cudaFree(dM);
+    if (dD) cudaFree(dD);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    if (rc != RMG_OK) cudaGetLastError();
+    return rc;
+}
+
+int rmg_randomize_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
+                        double mask_lo, double mask_hi, const int32_t *idx, int R, const int32_t *cols, int ncols,
+                        int two_sided, double *dist, int n_gpus, char *err, size_t errlen)
+{
+    int rc = check_fit_args(Y, V, ldY, n, X, p, Y, ldY, err, errlen);
+    if (rc) return rc;
+    const int have = rmg_device_count();
+    if (have <= 0) return fail(err, errlen, RMG_ERR_NO_DEVICE, "no CUDA device available; rminc_b200 has no CPU fallback");
+    int G = n_gpus <= 0 ? have : n_gpus;
+    if (G > have) return fail(err, errlen, RMG_ERR_NO_DEVICE, "%d GPUs requested, %d visible", G, have);
+    if (R <= 0 || ncols <= 0) return RMG_OK;
+    std::vector<int64_t> b(G + 1);
+    for (int g = 0; g <= G; ++g) b[g] = std::min<int64_t>(V, ((V * g / G) + 1) & ~int64_t(1));
+    b[0] = 0;
+    b[G] = V;
+    std::vector<int> rcs(G, RMG_OK);
+    std::vector<std::string> msgs(G, std::string(256, '\0'));
+    std::vector<std::vector<double>> part(G, std::vector<double>((size_t)R * ncols, -INFINITY));
+    std::vector<double> kms(G, 0.0);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) {
+        th.emplace_back([&, g]() {
+            const int64_t v0 = b[g], cv = b[g + 1] - b[g];
+            if (cv <= 0) return;
+            rcs[g] = rmg_randomize(Y + v0, cv, ldY, n, X, p, mask ? mask + v0 : nullptr, mask_lo, mask_hi, idx, R, cols,
+                                   ncols, two_sided, part[g].data(), g, &msgs[g][0], msgs[g].size());
+            kms[g] = rmg_last_kernel_ms();
+        });
+    }
+    for (auto &t : th) t.join();
+    g_last_kernel_ms = *std::max_element(kms.begin(), kms.end());
+    for (int g = 0; g < G; ++g)
+        if (rcs[g] != RMG_OK) return fail(err, errlen, rcs[g], "gpu %d: %s", g, msgs[g].c_str());
+    // the only exchange step of the path: an element-wise max over shards (R*ncols doubles)
+    for (size_t i = 0; i < (size_t)R * ncols; ++i) {
+        double m = -INFINITY;
+        for (int g = 0; g < G; ++g) m = std::fmax(m, part[g][i]);
+        dist[i] = m;
+    }
+    return RMG_OK;
+}
+
+}  // extern "C"

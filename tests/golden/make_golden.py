@@ -1,0 +1,55 @@
+"""Regenerate tests/golden/ref_golden.npz from the REFERENCE'S OWN object code.
+
+Runs only where /root/reference exists: `python tests/golden/make_golden.py`.  It builds
+oracle/_ref/librminc_ref.so (the reference's src/modelling_functions.c, vertex_modelling.c,
+minc_anova.c, slice_loop_functions.c compiled where they lie; see oracle/Makefile) and records
+the outputs of the reference's vertex_lm_loop and minc2_model(method="lm") on small seeded
+inputs.  The inputs are stored too, so the fixture is self-contained on machines that have
+neither the reference nor a GPU.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+
+
+def main():
+    O.build(ref=True)
+    assert O.have_ref(), "needs /root/reference"
+    rng = np.random.default_rng(20261019)
+    out = {}
+    # case A: vertex_lm_loop, y ~ group + age (p = 3), V = 96, n = 24
+    n, V = 24, 96
+    X = np.column_stack([np.ones(n), np.arange(n) % 2, np.round(rng.normal(60, 10, n), 1)])
+    Y = np.asfortranarray(rng.normal(1.0, 0.2, (V, n)) + 0.1 * np.outer(rng.random(V), X[:, 1]))
+    Y[5, :] = 0.0  # degenerate all-zero vertex
+    out["A_X"], out["A_Y"] = X, Y
+    out["A_out"] = O.vertex_lm_loop(Y, X, use_ref=True)
+    # case B: minc2_model lm with an integer-labelled mask, default range and maskval = 2
+    dims = (4, 6, 5)
+    V = int(np.prod(dims))
+    n = 12
+    X = np.column_stack([np.ones(n), (np.arange(n) >= n // 2).astype(float)])
+    Y = np.asfortranarray(30000 + 50 * rng.standard_normal((V, n)) + 40 * np.outer(rng.random(V), X[:, 1]))
+    mask = rng.integers(0, 4, V).astype(float)
+    out["B_dims"], out["B_X"], out["B_Y"], out["B_mask"] = np.array(dims), X, Y, mask
+    out["B_out_default"] = O.minc2_model_lm(Y, dims, X, mask=mask, use_ref=True, fill=0.0)
+    out["B_out_maskval2"] = O.minc2_model_lm(Y, dims, X, mask=mask, lo=2, hi=2, use_ref=True, fill=0.0)
+    out["B_out_nomask"] = O.minc2_model_lm(Y, dims, X, mask=None, use_ref=True, fill=0.0)
+    # case C: rank-deficient design [1, g, 1-g, age]: pivoted betas, trailing zero
+    n, V = 16, 8
+    g = (np.arange(n) % 2).astype(float)
+    X = np.column_stack([np.ones(n), g, 1 - g, np.round(rng.normal(60, 10, n), 1)])
+    Y = np.asfortranarray(rng.normal(0, 1, (V, n)))
+    out["C_X"], out["C_Y"] = X, Y
+    out["C_out"] = O.vertex_lm_loop(Y, X, use_ref=True)
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), "ref_golden.npz"), **out)
+    print("wrote ref_golden.npz:", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,123 @@
+"""CPU-side tests of the product library: the C-ABI surface and the host design factorisation.
+
+No compute entry point can run here (no GPU): they must fail loudly with RMG_ERR_NO_DEVICE.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, have_gpu
+from helpers import design_cfg1, design_cfg2, design_cov
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "rminc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rmg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from rminc_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 13
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/rminc_b200.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == syms
+    assert lib.rmg_version() >= 100 and lib.rmg_max_p() == 32
+
+
+def test_library_is_torch_free(lib):
+    import subprocess
+    from rminc_b200 import _lib
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "libR" not in out and "python" not in out
+
+
+def test_design_factor_matches_oracle(lib, oracle):
+    from rminc_b200 import core
+    rng = np.random.default_rng(2)
+    designs = [design_cfg1(20), design_cfg2(500), design_cov(2000, 7), design_cov(12, 6), np.ones((9, 1)),
+               rng.normal(size=(30, 5)),                       # no intercept
+               design_cov(64, 12), design_cov(100, 32)]
+    for X in designs:
+        n, p = X.shape
+        d, o = core.design_factor(X), oracle.design_probe(X)
+        assert d["info"] == 0 and o["info"] == 0
+        assert list(d["pivot"]) == list(o["pivot"]) and d["rank"] == o["rank"] == p
+        assert np.array_equal(d["cdiag"], o["c"])              # same operation order -> same bits
+        Q, Rinv = d["Q"], d["Rinv"]
+        assert np.allclose(Q.T @ Q, np.eye(p), atol=1e-13)
+        assert np.allclose(Q @ np.linalg.inv(Rinv), X[:, d["pivot"]], rtol=1e-12, atol=1e-12 * np.abs(X).max())
+        assert np.allclose(Rinv @ o["R"], np.eye(p), atol=1e-10)
+
+
+def test_design_factor_rank_deficient_and_singular(lib, oracle):
+    from rminc_b200 import core
+    rng = np.random.default_rng(3)
+    n = 40
+    g = (np.arange(n) % 2).astype(float)
+    age = np.round(rng.normal(60, 10, n), 1)
+    for X in (np.column_stack([np.ones(n), g, 1 - g, age]), np.column_stack([np.ones(n), g, g, age])):
+        d, o = core.design_factor(X), oracle.design_probe(X)
+        assert list(d["pivot"]) == list(o["pivot"]) == [0, 1, 3, 2]
+        assert d["rank"] == o["rank"] == 3 and d["info"] == 0
+        assert np.array_equal(d["cdiag"], o["c"])
+        assert (d["Q"][:, 3] == 0).all() and (d["Rinv"][3] == 0).all() and (d["Rinv"][:, 3] == 0).all()
+    Xz = np.column_stack([np.ones(n), g, np.zeros(n), age])
+    d = core.design_factor(Xz)
+    assert d["info"] == 4 == oracle.design_probe(Xz)["info"]
+    # the error text is the reference's (src/modelling_functions.c:554)
+    err = C.create_string_buffer(256)
+    Xf = np.asfortranarray(Xz)
+    rc = lib.rmg_design_factor(Xf.ctypes.data, n, 4, None, None, None, None, None, None, err, 256)
+    assert rc == 2 and err.value.decode() == "element (4, 4) is zero, so the inverse cannot be computed"
+
+
+def test_argument_validation(lib):
+    from rminc_b200 import core
+    X = design_cfg1(20)
+    with pytest.raises(ValueError):
+        core.lm_fit(np.zeros((10, 19)), X)
+    with pytest.raises(ValueError):
+        core.lm_fit(np.zeros((10, 20)), X, mask=np.ones(9))
+    with pytest.raises(core.RmincGpuError) as e:
+        core.lm_fit(np.zeros((10, 20)), np.ones((20, 33)))
+    assert e.value.code == 1
+    with pytest.raises(core.RmincGpuError) as e:          # non-finite design
+        core.lm_fit(np.zeros((10, 20)), np.full((20, 2), np.nan))
+    assert e.value.code == 1
+    with pytest.raises(core.SingularDesignError):         # singular design fails before any GPU work
+        core.lm_fit(np.zeros((10, 20)), np.column_stack([np.ones(20), np.zeros(20)]))
+    with pytest.raises(ValueError):
+        core.randomize(np.zeros((10, 20)), X, np.full((20, 3), 20), [4])
+
+
+@pytest.mark.skipif(have_gpu(), reason="only meaningful on a machine without a CUDA device")
+def test_no_cpu_fallback(lib):
+    """Without a GPU every compute entry point refuses; nothing silently computes on the host."""
+    from rminc_b200 import core
+    X = design_cfg1(20)
+    Y = np.random.default_rng(0).normal(size=(64, 20))
+    assert core.device_count() == 0
+    for call in (lambda: core.lm_fit(Y, X), lambda: core.vertex_lm(Y, X), lambda: core.lm_fit(Y, X, n_gpus=1),
+                 lambda: core.randomize(Y, X, np.arange(20)[:, None], [4]),
+                 lambda: core.randomize(Y, X, np.arange(20)[:, None], [4], n_gpus=2)):
+        with pytest.raises(core.RmincGpuError) as e:
+            call()
+        assert e.value.code == 4 and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    """rminc_b200/ must never import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "rminc_b200")
+    for dp, _, files in os.walk(pkg):
+        if "build" in dp.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".c", ".R")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert not re.search(r"\boracle\b|liboracle|orc_", txt), f"{f} mentions the oracle"

@@ -1,0 +1,259 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI, on a real B200.
+
+Tolerance (BASELINE.json north_star): masked voxels and output layout bit-exact; betas, F, t,
+R-squared and logLik within 1e-9 relative in FP64; rank-deficiency behaviour identical.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_rows_match, cfg1_data, design_cfg1, design_cfg2, design_cov, ellipsoid_mask
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def core(lib):
+    from rminc_b200 import core as c
+    assert c.device_count() > 0, "GPU tests need a CUDA device"
+    return c
+
+
+@pytest.fixture(params=["tma", "ldg"])
+def variant(request, monkeypatch):
+    monkeypatch.setenv("RMG_FIT_VARIANT", request.param)
+    return request.param
+
+
+def test_golden_vectors_of_the_reference(core, variant):
+    g = np.load(os.path.join(GOLD, "ref_golden.npz"))
+    assert_rows_match(core.vertex_lm(g["A_Y"], g["A_X"]), g["A_out"], RTOL, "A")
+    for key, kw in (("B_out_default", {}), ("B_out_maskval2", dict(mask_lo=2, mask_hi=2))):
+        out = core.lm_fit(g["B_Y"], g["B_X"], mask=g["B_mask"], **kw)
+        assert_rows_match(out, g[key], RTOL, key)
+        zero = g[key][:, 0] == 0
+        assert (out[zero] == 0).all() and not np.signbit(out[zero]).any()       # masked rows: +0.0 bit-exact
+    assert_rows_match(core.lm_fit(g["B_Y"], g["B_X"]), g["B_out_nomask"], RTOL, "B nomask")
+    # rank-deficient design: same pivoted layout, trailing zero beta, t ~ 0 in the coupled slots
+    out, want = core.vertex_lm(g["C_Y"], g["C_X"]), g["C_out"]
+    assert_rows_match(out[:, [0, 1, 2, 3, 4, 10]], want[:, [0, 1, 2, 3, 4, 10]], RTOL, "C")
+    assert (out[:, 5] == 0).all() and (out[:, 9] == 0).all()
+    assert np.all(np.abs(out[:, [6, 7, 9]]) < 1e-6) and np.all(np.abs(want[:, [6, 7, 9]]) < 1e-6)
+    assert_rows_match(out[:, 8], want[:, 8], RTOL, "C t_age")
+
+
+def test_config1_full_parity(core, oracle, variant):
+    """BASELINE config 1: mincLm(y ~ group), 20 volumes of 60x80x50, masked."""
+    Y, X, mask = cfg1_data()
+    want = oracle.minc2_model_lm(Y, (60, 80, 50), X, mask=mask)
+    got = core.lm_fit(Y, X, mask=mask)
+    inside = mask > 0.5
+    assert 0.3 < inside.mean() < 0.45
+    assert (got[~inside] == 0).all() and not np.signbit(got[~inside]).any()
+    assert_rows_match(got, want, RTOL, "cfg1 masked")
+    # integer labels + maskval exercises the +-0.5 interval rule
+    labels = (np.arange(Y.shape[0]) % 4).astype(float)
+    assert_rows_match(core.lm_fit(Y, X, mask=labels, mask_lo=2, mask_hi=2),
+                      oracle.minc2_model_lm(Y, (60, 80, 50), X, mask=labels, lo=2, hi=2), RTOL, "maskval")
+
+
+def test_degenerate_voxels_match_by_class(core, oracle, variant):
+    Y, X, _ = cfg1_data(dims=(20, 20, 20))
+    Y = Y.copy(order="F")
+    Y[::7] = 0.0                                  # all-zero voxels: logLik=+Inf, F/R2/t=NaN, beta=0
+    got, want = core.lm_fit(Y, X), oracle.vertex_lm_loop(Y, X)
+    assert np.isposinf(got[::7, -1]).all() and np.isnan(got[::7, 0]).all() and (got[::7, 2:4] == 0).all()
+    assert_rows_match(got, want, RTOL, "degenerate")
+
+
+@pytest.mark.parametrize("mean,sd", [(0.0, 0.2), (100.0, 10.0), (1000.0, 1.0), (30000.0, 50.0), (-5e4, 3.0)])
+def test_large_mean_small_sd_keeps_1e9(core, oracle, variant, mean, sd):
+    """Hard part H1: one-pass rss must not cancel when |mean| >> sd (ushort-scaled intensities)."""
+    rng = np.random.default_rng(5)
+    V, n = 4096, 500
+    X = design_cfg2(n)
+    Y = np.asfortranarray(mean + sd * rng.standard_normal((V, n)) + 0.5 * sd * np.outer(rng.random(V), X[:, 1]))
+    assert_rows_match(core.lm_fit(Y, X), oracle.vertex_lm_loop(Y, X), RTOL, f"mean={mean} sd={sd}")
+
+
+def test_near_perfect_fits_take_the_exact_path(core, oracle, variant):
+    """rss/|y'|^2 < 1e-3: the kernel recomputes rss/mss from explicit residuals."""
+    rng = np.random.default_rng(6)
+    V, n = 2048, 120
+    X = design_cov(n, 4)
+    B = rng.normal(size=(V, 4)) * 50
+    for noise in (1e-1, 1e-4, 1e-7):
+        Y = np.asfortranarray(B @ X.T + noise * rng.standard_normal((V, n)))
+        assert_rows_match(core.lm_fit(Y, X), oracle.vertex_lm_loop(Y, X), 1e-8 if noise < 1e-5 else RTOL,
+                          f"noise={noise}")
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 5, 6, 7, 8, 9, 12, 13, 16, 20, 32])
+def test_every_padded_width(core, oracle, p):
+    rng = np.random.default_rng(p)
+    n, V = 64, 1026
+    X = design_cov(n, p) if p > 1 else np.ones((n, 1))
+    Y = np.asfortranarray(rng.normal(3, 1, (V, n)))
+    assert_rows_match(core.lm_fit(Y, X), oracle.vertex_lm_loop(Y, X), RTOL, f"p={p}")
+
+
+def test_no_intercept_design(core, oracle, variant):
+    rng = np.random.default_rng(8)
+    n, V = 80, 3000
+    X = rng.normal(size=(n, 3))
+    Y = np.asfortranarray(rng.normal(10, 1, (V, n)))
+    assert_rows_match(core.lm_fit(Y, X), oracle.vertex_lm_loop(Y, X), RTOL, "no intercept")
+
+
+def test_ragged_shapes_and_leading_dimensions(core, oracle):
+    rng = np.random.default_rng(9)
+    X = design_cfg2(33)
+    for V in (1, 2, 3, 31, 255, 513, 1025, 4099):
+        Y = np.asfortranarray(rng.normal(0, 1, (V, 33)))
+        m = (rng.random(V) > 0.3).astype(float)
+        assert_rows_match(core.lm_fit(Y, X, mask=m), oracle.minc2_model_lm(Y, (1, 1, V), X, mask=m), RTOL, f"V={V}")
+    assert core.lm_fit(np.zeros((0, 33), order="F"), X).shape == (0, 11)
+    # everything masked out
+    Y = np.asfortranarray(rng.normal(size=(777, 33)))
+    out = core.lm_fit(Y, X, mask=np.zeros(777))
+    assert (out == 0).all() and not np.signbit(out).any()
+
+
+def test_split_n_for_few_vertices_many_subjects(core, oracle, monkeypatch):
+    """vertexLm shape (config 3 scaled down): small V, n = 2000, p = 7 -> subject axis is split."""
+    rng = np.random.default_rng(10)
+    V, n = 1500, 2000
+    X = design_cov(n, 7)
+    Y = np.asfortranarray(rng.normal(2.5, 0.4, (V, n)))
+    want = oracle.vertex_lm_loop(Y, X)
+    for split in ("0", "1", "2", "4", "8"):
+        monkeypatch.setenv("RMG_FIT_VARIANT", "ldg")
+        monkeypatch.setenv("RMG_FIT_SPLIT", split)
+        assert_rows_match(core.vertex_lm(Y, X), want, RTOL, f"split={split}")
+
+
+def test_chunked_host_pipeline(core, oracle, monkeypatch):
+    """Host entry point with several voxel chunks in flight (ragged last chunk)."""
+    Y, X, mask = cfg1_data(dims=(30, 40, 25))
+    want = oracle.minc2_model_lm(Y, (30, 40, 25), X, mask=mask)
+    monkeypatch.setenv("RMG_CHUNK_VOXELS", "7000")
+    assert_rows_match(core.lm_fit(Y, X, mask=mask), want, RTOL, "chunked")
+    assert core.last_kernel_ms() > 0
+    assert_rows_match(core.lm_fit(Y, X, mask=mask, n_gpus=1), want, RTOL, "multi(1)")
+
+
+def test_device_resident_entry_point(core, oracle, variant):
+    import torch
+    Y, X, mask = cfg1_data(dims=(24, 32, 20))
+    want = oracle.minc2_model_lm(Y, (24, 32, 20), X, mask=mask)
+    Yt = torch.from_numpy(np.ascontiguousarray(Y.T)).cuda()        # (n, V) row-major == V x n column-major
+    mt = torch.from_numpy(mask).cuda()
+    before = core.launch_count()
+    out = core.lm_fit_torch(Yt, X, mask=mt)
+    torch.cuda.synchronize()
+    assert core.launch_count() > before
+    assert_rows_match(out.cpu().numpy().T, want, RTOL, "device")
+    out2 = core.lm_fit_torch(Yt, X)
+    torch.cuda.synchronize()
+    assert_rows_match(out2.cpu().numpy().T, oracle.vertex_lm_loop(Y, X), RTOL, "device nomask")
+
+
+def test_singular_design_error_contract(core):
+    n = 30
+    X = np.column_stack([np.ones(n), np.arange(n) % 2, np.zeros(n)])
+    with pytest.raises(core.SingularDesignError, match=r"element \(3, 3\) is zero, so the inverse cannot be computed"):
+        core.lm_fit(np.ones((10, n)), X)
+
+
+# ------------------------------------------------------------------ mincRandomize
+@pytest.fixture(params=["refit", "gemm"])
+def perm_path(request, monkeypatch):
+    monkeypatch.setenv("RMG_PERM_PATH", request.param)
+    return request.param
+
+
+def perm_indices(n, R, seed=4, replace=False):
+    rng = np.random.default_rng(seed)
+    if replace:
+        return np.column_stack([rng.integers(0, n, n) for _ in range(R)])
+    return np.column_stack([rng.permutation(n) for _ in range(R)])
+
+
+def test_randomize_matches_oracle(core, oracle, perm_path):
+    Y, X, mask = cfg1_data(dims=(16, 20, 12))
+    n = X.shape[0]
+    idx = perm_indices(n, 40)
+    tcols = [4, 5]
+    for two_sided in (True, False):
+        for m in (mask, None):
+            want = oracle.randomize(Y, X, idx, tcols, two_sided=two_sided, mask=m)
+            got = core.randomize(Y, X, idx, tcols, two_sided=two_sided, mask=m)
+            assert got.shape == (40, 2)
+            np.testing.assert_allclose(got, want, rtol=RTOL, atol=0, err_msg=f"{perm_path} two_sided={two_sided}")
+
+
+def test_randomize_p4_high_mean_and_degenerate_rows(core, oracle, perm_path):
+    rng = np.random.default_rng(12)
+    V, n = 3000, 60
+    X = design_cfg2(n)
+    Y = np.asfortranarray(30000 + 50 * rng.standard_normal((V, n)))
+    Y[::11] = 0.0            # non-finite statistics -> 0
+    Y[5::13] = 123.0         # constant non-zero voxels: rounding-noise rss in the reference (H2): masked out
+    mask = np.ones(V)
+    mask[5::13] = 0
+    idx = perm_indices(n, 70)
+    cols = [6, 7, 8, 9]
+    want = oracle.randomize(Y, X, idx, cols, two_sided=True, mask=mask)
+    got = core.randomize(Y, X, idx, cols, two_sided=True, mask=mask)
+    np.testing.assert_allclose(got, want, rtol=RTOL)
+    got1 = core.randomize(Y, X, idx, cols, two_sided=False, mask=mask)
+    np.testing.assert_allclose(got1, oracle.randomize(Y, X, idx, cols, two_sided=False, mask=mask), rtol=RTOL)
+    assert (got1 >= 0).all()
+
+
+def test_randomize_with_replacement_and_other_columns(core, oracle):
+    """replace=TRUE index vectors; non-t columns go through the refit path."""
+    Y, X, mask = cfg1_data(dims=(10, 12, 10))
+    n = X.shape[0]
+    idx = perm_indices(n, 25, replace=True)
+    keep = [r for r in range(idx.shape[1]) if len(set(X[idx[:, r], 1])) == 2][:20]
+    idx = idx[:, keep]
+    cols = [0, 1, 3, 5, 6]          # F, R2, beta, t, logLik
+    want = oracle.randomize(Y, X, idx, cols, two_sided=True, mask=mask)
+    got = core.randomize(Y, X, idx, cols, two_sided=True, mask=mask)
+    np.testing.assert_allclose(got, want, rtol=RTOL)
+    # a resample that empties a factor level makes the refit singular -> the whole call fails
+    bad = idx.copy()
+    bad[:, 3] = np.flatnonzero(X[:, 1] == 0)[0]
+    with pytest.raises(core.SingularDesignError, match="permutation 4"):
+        core.randomize(Y, X, bad, [4, 5], mask=mask)
+
+
+def test_randomize_gemm_equals_refit_on_larger_case(core, monkeypatch):
+    rng = np.random.default_rng(13)
+    V, n = 20000, 100
+    X = design_cfg2(n)
+    Y = np.asfortranarray(rng.normal(0, 0.2, (V, n)))
+    mask = ellipsoid_mask((20, 25, 40))
+    idx = perm_indices(n, 130)
+    cols = [6, 7, 8, 9]
+    monkeypatch.setenv("RMG_PERM_PATH", "refit")
+    a = core.randomize(Y, X, idx, cols, mask=mask)
+    monkeypatch.setenv("RMG_PERM_PATH", "gemm")
+    b = core.randomize(Y, X, idx, cols, mask=mask)
+    np.testing.assert_allclose(b, a, rtol=1e-10)
+
+
+def test_randomize_device_entry_point(core, oracle):
+    import torch
+    Y, X, mask = cfg1_data(dims=(12, 16, 10))
+    n = X.shape[0]
+    idx = perm_indices(n, 16)
+    Yt = torch.from_numpy(np.ascontiguousarray(Y.T)).cuda()
+    mt = torch.from_numpy(mask).cuda()
+    d = core.randomize_torch(Yt, X, idx, [4, 5], two_sided=True, mask=mt)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(d.cpu().numpy().T, oracle.randomize(Y, X, idx, [4, 5], mask=mask), rtol=RTOL)

@@ -1,0 +1,223 @@
+"""The CPU oracle is pinned before anything is compared with it.
+
+(1) the reference's own object code (oracle/_ref, built from /root/reference/src when present)
+    and the committed golden vectors it produced (tests/golden/ref_golden.npz);
+(2) published base-R lm() outputs (tests/golden/r_lm_known_answers.json) -- what the
+    reference's testthat files compare with (tests/testthat/test_mincLm.R:34-56);
+(3) an independent numpy closed-form OLS and scipy's LAPACK dpotri;
+(4) SURVEY.md Appendix D known-answer vector, A.3 rank-deficiency and A.4 degenerate voxels.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_rows_match, cfg1_data, design_cfg2
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def numpy_ols(y, X):
+    """Closed-form summary.lm identities (full-rank designs)."""
+    n, p = X.shape
+    beta, *_ = np.linalg.lstsq(X, y, rcond=None)
+    fitted = X @ beta
+    resid = y - fitted
+    rss = resid @ resid
+    mss = ((fitted - fitted.mean()) ** 2).sum()
+    resvar = rss / (n - p)
+    se = np.sqrt(np.diag(np.linalg.inv(X.T @ X)) * resvar)
+    return dict(coef=beta, t=beta / se, F=(mss / (p - 1)) / resvar, R2=mss / (mss + rss),
+                logLik=-0.5 * n * (np.log(2 * np.pi) + 1 - np.log(n) + np.log(rss)))
+
+
+APPX_D_X = np.array([[1, 0, 2], [1, 0, 3], [1, 0, 5], [1, 1, 1], [1, 1, 4], [1, 1, 6], [1, 0, 7], [1, 1, 8]], float)
+APPX_D_Y = np.array([1.0, 2.5, 2.0, 4.0, 3.5, 6.0, 3.0, 7.5])
+
+
+def test_appendix_d_known_answer(oracle):
+    r = oracle.voxel_lm(APPX_D_Y, APPX_D_X)
+    assert r["F"] == pytest.approx(17.0949875380781, rel=1e-13)
+    assert r["R2"] == pytest.approx(0.87241635162350284, rel=1e-14)
+    assert r["coef"] == pytest.approx([0.217620481927707, 2.90060240963855, 0.448795180722892], rel=1e-12)
+    assert r["t"] == pytest.approx([0.291073571681093, 4.51468309113494, 3.20108273476179], rel=1e-12)
+    assert r["logLik"] == pytest.approx(-8.6568452963150087, rel=1e-14)
+    assert list(r["pivot"]) == [0, 1, 2] and r["rank"] == 3
+    # permutation check (mincRandomize semantics: X_pi = X[idx, ], same y)
+    idx = [3, 0, 7, 1, 5, 2, 6, 4]
+    rp = oracle.voxel_lm(APPX_D_Y, APPX_D_X[idx])
+    assert rp["t"] == pytest.approx([1.68979927547816, -0.234970271257997, 0.224649658769916], rel=1e-12)
+
+
+def test_published_r_lm_outputs(oracle):
+    cases = json.load(open(os.path.join(GOLD, "r_lm_known_answers.json")))["cases"]
+    assert len(cases) >= 5
+    for c in cases:
+        y = np.array(c["y"], float)
+        X = np.column_stack([np.ones(len(y))] + [np.array(v, float) for v in c["X"].values()])
+        r = oracle.voxel_lm(y, X)
+        assert np.allclose(r["coef"], c["beta"], rtol=0, atol=c["beta_tol"]), c["name"]
+        assert np.allclose(r["t"], c["t"], rtol=0, atol=c["t_tol"]), c["name"]
+        assert abs(r["F"] - c["F"]) <= c["F_tol"], c["name"]
+        assert abs(r["R2"] - c["R2"]) <= c["R2_tol"], c["name"]
+        if "logLik" in c:
+            assert abs(r["logLik"] - c["logLik"]) <= c["logLik_tol"], c["name"]
+
+
+def test_golden_vectors_from_reference_object_code(oracle):
+    """Committed outputs of the reference's own vertex_lm_loop / minc2_model (make_golden.py)."""
+    g = np.load(os.path.join(GOLD, "ref_golden.npz"))
+    assert np.array_equal(oracle.vertex_lm_loop(g["A_Y"], g["A_X"]), g["A_out"], equal_nan=True)
+    dims = tuple(int(d) for d in g["B_dims"])
+    assert np.array_equal(oracle.minc2_model_lm(g["B_Y"], dims, g["B_X"], mask=g["B_mask"]), g["B_out_default"])
+    assert np.array_equal(oracle.minc2_model_lm(g["B_Y"], dims, g["B_X"], mask=g["B_mask"], lo=2, hi=2),
+                          g["B_out_maskval2"])
+    assert np.array_equal(oracle.minc2_model_lm(g["B_Y"], dims, g["B_X"]), g["B_out_nomask"])
+    assert np.array_equal(oracle.vertex_lm_loop(g["C_Y"], g["C_X"]), g["C_out"])
+    # the fixture itself exercises what it claims to
+    assert np.isposinf(g["A_out"][5, -1]) and np.isnan(g["A_out"][5, 0])       # all-zero vertex
+    assert (g["B_out_maskval2"][g["B_mask"] != 2] == 0).all()
+    assert (g["C_out"][:, 5] == 0).all()                                        # aliased slot is beta 0
+
+
+def test_restatement_equals_reference_object_code(oracle):
+    """Bit-for-bit against oracle/_ref (the reference's compiled voxel_lm etc.), when present."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    rng = np.random.default_rng(7)
+    for n, p, V in [(20, 2, 300), (37, 4, 200), (12, 6, 100), (9, 1, 50)]:
+        X = np.column_stack([np.ones(n)] + [rng.normal(size=n) for _ in range(p - 1)])
+        Y = rng.normal(5, 2, (V, n))
+        a = oracle.vertex_lm_loop(Y, X)
+        b = oracle.vertex_lm_loop(Y, X, use_ref=True)
+        assert np.array_equal(a, b, equal_nan=True), (n, p)
+    # slice loop + mask through the reference's minc2_model with in-memory volumes
+    dims = (5, 7, 6)
+    V = int(np.prod(dims))
+    X = design_cfg2(30)
+    Y = rng.normal(0, 0.2, (V, 30))
+    mask = rng.integers(0, 3, V).astype(float)
+    for kw in (dict(), dict(lo=2, hi=2), dict(lo=1, hi=1)):
+        a = oracle.minc2_model_lm(Y, dims, X, mask=mask, **kw)
+        b = oracle.minc2_model_lm(Y, dims, X, mask=mask, use_ref=True, fill=0.0, **kw)
+        assert np.array_equal(a, b), kw
+    # Quirk Q1: the reference writes only column 0 of masked rows; the rest is never touched
+    a = oracle.minc2_model_lm(Y, dims, X, mask=mask)
+    c = oracle.minc2_model_lm(Y, dims, X, mask=mask, use_ref=True, fill=np.nan)
+    inside = mask > 0.5
+    assert (c[~inside, 0] == 0).all() and np.isnan(c[~inside, 1:]).all()
+    assert np.array_equal(c[inside], a[inside])
+    # a single voxel through voxel_lm, and the singular-design error contract
+    r1 = oracle.voxel_lm(Y[0], X)
+    r2 = oracle.voxel_lm(Y[0], X, use_ref=True)
+    for k in ("coef", "t"):
+        assert np.array_equal(r1[k], r2[k])
+    # an all-zero column (e.g. a factor level emptied by resampling) is cycled to the back and
+    # leaves R[4,4] == 0 exactly -> dpotri info 4 -> Rf_error (src/modelling_functions.c:551-557)
+    Xz = np.column_stack([X[:, 0], X[:, 1], np.zeros(30), X[:, 2]])
+    with pytest.raises(oracle.OracleError, match=r"element \(4, 4\) is zero"):
+        oracle.voxel_lm(Y[0], Xz, use_ref=True)
+    with pytest.raises(oracle.OracleError, match=r"element \(4, 4\) is zero"):
+        oracle.voxel_lm(Y[0], Xz)
+
+
+def test_against_independent_numpy_ols(oracle):
+    rng = np.random.default_rng(11)
+    for n, p in [(20, 2), (50, 4), (200, 7), (500, 4)]:
+        X = np.column_stack([np.ones(n)] + [rng.normal(size=n) for _ in range(p - 1)])
+        for mean, sd in [(0, 1), (100, 10), (30000, 50)]:
+            y = rng.normal(mean, sd, n) + X[:, -1] * sd
+            r, w = oracle.voxel_lm(y, X), numpy_ols(y, X)
+            assert r["coef"] == pytest.approx(w["coef"], rel=1e-9, abs=1e-9 * sd)
+            assert r["t"] == pytest.approx(w["t"], rel=1e-9, abs=1e-10)
+            assert r["F"] == pytest.approx(w["F"], rel=1e-9)
+            assert r["R2"] == pytest.approx(w["R2"], rel=1e-9)
+            assert r["logLik"] == pytest.approx(w["logLik"], rel=1e-11)
+
+
+def test_dpotri_restatement_matches_lapack(oracle):
+    from scipy.linalg import lapack
+    rng = np.random.default_rng(5)
+    for n, p in [(30, 3), (100, 6), (500, 4)]:
+        X = np.column_stack([np.ones(n)] + [rng.normal(60, 10, size=n) for _ in range(p - 1)])
+        d = oracle.design_probe(X)
+        assert d["info"] == 0 and d["rank"] == p
+        inv, info = lapack.dpotri(d["R"], lower=0)
+        assert info == 0
+        assert d["c"] == pytest.approx(np.diag(inv), rel=1e-12)
+        assert d["c"] == pytest.approx(np.diag(np.linalg.inv(X.T @ X)), rel=1e-8)
+
+
+def test_rank_deficient_behaviour(oracle):
+    """pivoted-order betas with a trailing zero, rdf = n - p, near-zero t."""
+    rng = np.random.default_rng(3)
+    n = 40
+    g = (np.arange(n) % 2).astype(float)
+    age = np.round(rng.normal(60, 10, n), 1)
+    X = np.column_stack([np.ones(n), g, 1 - g, age])
+    d = oracle.design_probe(X)
+    assert list(d["pivot"]) == [0, 1, 3, 2] and d["rank"] == 3 and d["info"] == 0
+    y = rng.normal(size=n)
+    r = oracle.voxel_lm(y, X)
+    w = numpy_ols(y, X[:, [0, 1, 3]])
+    assert r["coef"][:3] == pytest.approx(w["coef"], rel=1e-9)     # [b_1, b_g, b_age] ...
+    assert r["coef"][3] == 0.0                                      # ... and the aliased slot is 0
+    assert np.all(np.abs(r["t"][[0, 1, 3]]) < 1e-6)                # huge c from the ~1e-16 diagonal
+    # an exact duplicate column behaves the same way (its residual is rounding noise, not 0) ...
+    Xd = np.column_stack([np.ones(n), g, g, age])
+    dd = oracle.design_probe(Xd)
+    assert list(dd["pivot"]) == [0, 1, 3, 2] and dd["rank"] == 3 and dd["info"] == 0
+    # ... while an all-zero column leaves R[4,4] == 0 exactly -> dpotri info 4 -> the reference raises
+    Xz = np.column_stack([np.ones(n), g, np.zeros(n), age])
+    assert oracle.design_probe(Xz)["info"] == 4
+    with pytest.raises(oracle.OracleError):
+        oracle.voxel_lm(y, Xz)
+
+
+def test_degenerate_voxels(oracle):
+    """y == 0 gives logLik=+Inf, F/R2/t = NaN, beta = 0."""
+    X = design_cfg2(30)
+    r = oracle.voxel_lm(np.zeros(30), X)
+    assert np.isposinf(r["logLik"]) and np.isnan(r["F"]) and np.isnan(r["R2"])
+    assert np.isnan(r["t"]).all() and (r["coef"] == 0).all()
+
+
+def test_layout_and_mask_rule(oracle):
+    """Columns [F, R2, beta.., t.., logLik]; mask interval rule lo-0.5 < m < hi+0.5; masked rows all 0."""
+    Y, X, mask = cfg1_data(dims=(6, 8, 5))
+    V = Y.shape[0]
+    out = oracle.minc2_model_lm(Y, (6, 8, 5), X, mask=mask)
+    inside = mask > 0.5
+    assert (out[~inside] == 0).all() and not np.signbit(out[~inside]).any()
+    v = int(np.flatnonzero(inside)[0])
+    r = oracle.voxel_lm(Y[v], X)
+    assert out[v, 0] == r["F"] and out[v, 1] == r["R2"] and out[v, 6] == r["logLik"]
+    assert np.array_equal(out[v, 2:4], r["coef"]) and np.array_equal(out[v, 4:6], r["t"])
+    labels = (np.arange(V) % 4).astype(float)
+    o2 = oracle.minc2_model_lm(Y, (6, 8, 5), X, mask=labels, lo=2, hi=2)
+    assert np.array_equal(o2[:, 0] != 0, labels == 2)
+    o3 = oracle.minc2_model_lm(Y, (6, 8, 5), X, mask=labels + 0.4, lo=2, hi=2)   # 2.4 in, 1.4/3.4 out
+    assert np.array_equal(o3[:, 0] != 0, labels == 2)
+    assert_rows_match(oracle.vertex_lm_loop(Y, X)[inside], out[inside], rtol=0)
+
+
+def test_randomize_semantics(oracle):
+    """Column max over ALL rows (masked zeros included), non-finite -> 0, abs() when two-sided."""
+    Y, X, mask = cfg1_data(dims=(4, 5, 5))
+    V, n = Y.shape
+    rng = np.random.default_rng(4)
+    idx = np.column_stack([rng.permutation(n) for _ in range(6)])
+    cols = [4, 5]
+    d2 = oracle.randomize(Y, X, idx, cols, two_sided=True, mask=mask)
+    d1 = oracle.randomize(Y, X, idx, cols, two_sided=False, mask=mask)
+    for r in range(idx.shape[1]):
+        out = oracle.minc2_model_lm(Y, (4, 5, 5), X[idx[:, r]], mask=mask)
+        out[~np.isfinite(out)] = 0
+        assert np.array_equal(d2[r], np.abs(out[:, cols]).max(axis=0))
+        assert np.array_equal(d1[r], out[:, cols].max(axis=0))
+    assert (d1 >= 0).all()   # Q6: masked zeros keep every maximum >= 0 even for "greater"
+    ident = np.arange(n)[:, None]
+    d0 = oracle.randomize(Y, X, ident, cols, two_sided=True, mask=mask)
+    base = oracle.minc2_model_lm(Y, (4, 5, 5), X, mask=mask)
+    assert np.array_equal(d0[0], np.abs(base[:, cols]).max(axis=0))
