@@ -144,6 +144,9 @@ int rmg_randomize_multi(const double *Y, int64_t V, int64_t ldY, int n, const do
  * milliseconds spent in the dominant kernel(s), measured with CUDA events on the stream the
  * kernels were launched on (host entry points only; 0 if unavailable). */
 double rmg_last_kernel_ms(void);
+/* Which fit kernel the most recent fit on this thread launched: 1 = TMA-staged ring,
+ * 2 = direct streaming loads (+ split-n), 0 = none yet. */
+int rmg_last_fit_variant(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t rmg_launch_count(void);
 

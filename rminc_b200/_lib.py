@@ -38,6 +38,7 @@ SIGNATURES = {
     "rmg_lm_fit_multi": (C.c_int, _FIT_HEAD + _MASK + [C.c_void_p, C.c_int64, C.c_int] + _ERR),
     "rmg_randomize_multi": (C.c_int, _FIT_HEAD + _MASK + _PERM + [C.c_void_p, C.c_int] + _ERR),
     "rmg_last_kernel_ms": (C.c_double, []),
+    "rmg_last_fit_variant": (C.c_int, []),
     "rmg_launch_count": (C.c_int64, []),
 }
 

@@ -210,3 +210,7 @@ def last_kernel_ms() -> float:
 
 def launch_count() -> int:
     return _lib.load().rmg_launch_count()
+
+
+def last_fit_variant() -> str:
+    return {0: "none", 1: "lm_fit_tma_kernel", 2: "lm_fit_ldg_kernel"}[_lib.load().rmg_last_fit_variant()]

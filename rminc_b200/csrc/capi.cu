@@ -15,6 +15,7 @@ namespace rmg {
 
 std::atomic<int64_t> g_launch_count{0};
 thread_local double g_last_kernel_ms = 0.0;
+thread_local int g_last_fit_variant = 0;
 
 int select_device(int device, char *err, size_t errlen)
 {
@@ -131,6 +132,7 @@ LmPlan plan_from_env(int device)
         else if (!std::strcmp(v, "ldg")) plan.variant = LmVariant::Ldg;
     }
     if (const char *s = std::getenv("RMG_FIT_SPLIT")) plan.split = std::atoi(s);
+    if (const char *s = std::getenv("RMG_TMA_CFG")) plan.tma_cfg = std::atoi(s);
     return plan;
 }
 
@@ -155,6 +157,7 @@ int rmg_device_count(void)
 }
 
 double rmg_last_kernel_ms(void) { return g_last_kernel_ms; }
+int rmg_last_fit_variant(void) { return g_last_fit_variant; }
 int64_t rmg_launch_count(void) { return g_launch_count.load(); }
 
 int rmg_design_factor(const double *X, int n, int p, int32_t *pivot, int *rank, double *Q, double *Rinv,
@@ -191,6 +194,7 @@ int rmg_lm_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const dou
         LmArgs a{dY, V, ldY, n, p, dev.qt, dev.dd, dmask, mask_lo, mask_hi, dout, ldOut};
         RMG_CUDA(launch_lm_fit(a, plan_from_env(device), scr, st, &info));
         g_launch_count += info.launches;
+        g_last_fit_variant = info.used_tma ? 1 : 2;
     }
 cleanup:
     dev.release(st);
@@ -249,6 +253,7 @@ int rmg_lm_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *X, 
             RMG_CUDA(launch_lm_fit(a, plan, scr[b], st[b], &info));
             RMG_CUDA(cudaEventRecord(ev1[c], st[b]));
             launches += info.launches;
+            g_last_fit_variant = info.used_tma ? 1 : 2;
             RMG_CUDA(cudaMemcpy2DAsync(out + v0, (size_t)ldOut * 8, dO[b], (size_t)ldc * 8, (size_t)cv * 8, (size_t)ncol,
                                        cudaMemcpyDeviceToHost, st[b]));
         }

@@ -19,6 +19,7 @@ namespace rmg {
 
 extern std::atomic<int64_t> g_launch_count;
 extern thread_local double g_last_kernel_ms;
+extern thread_local int g_last_fit_variant;
 
 inline int fail(char *err, size_t errlen, int code, const char *fmt, ...)
 {

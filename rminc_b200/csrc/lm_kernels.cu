@@ -51,13 +51,13 @@ __global__ void mask_tile_flags_kernel(const double *__restrict__ mask, int64_t 
 }
 
 // One box of NJ subject rows out of shared memory into the two voxels' running sums.
-template <int KP, int NJ, int TV, bool GUARD>
+template <int KP, int NJ, int ROWW, bool GUARD>
 __device__ __forceinline__ void consume_box(const double *__restrict__ tile, const double *__restrict__ q,
                                             VoxelSums<KP> &s0, VoxelSums<KP> &s1, int nvalid)
 {
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) {
-        const double2 y = *reinterpret_cast<const double2 *>(tile + jj * TV);
+        const double2 y = *reinterpret_cast<const double2 *>(tile + jj * ROWW);
         double ya = y.x - s0.y0, yb = y.y - s1.y0;
         if (GUARD && jj >= nvalid) ya = yb = 0.0;
         s0.yy = fma(ya, ya, s0.yy);
@@ -73,13 +73,17 @@ __device__ __forceinline__ void consume_box(const double *__restrict__ tile, con
 
 // ------------------------------------------------------------------ TMA kernel
 // CTA = 1 producer warp + CW consumer warps.  Tile = TV = CW*64 voxels (2 per consumer
-// thread), streamed as boxes of NJ subjects.  Shared memory:
-//   [ring: STAGES x NJ x TV doubles][Qt: n x KP doubles][SmemDesign][mbarriers]
-template <int KP, int CW, int NJ, int STAGES>
-__global__ void __launch_bounds__((CW + 1) * 32, 1)
+// thread), streamed as TMA boxes of NJ subjects x kBoxW voxels (a TMA box dimension is at most
+// 256 elements, so a stage is TV/kBoxW boxes).  Shared memory:
+//   [ring: STAGES x (TV/kBoxW) x NJ x kBoxW doubles][Qt: n x KP doubles][SmemDesign][mbarriers]
+constexpr int kBoxW = 256;
+template <int KP, int CW, int NJ, int STAGES, int MINB>
+__global__ void __launch_bounds__((CW + 1) * 32, MINB)
 lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsigned char *__restrict__ flags)
 {
     constexpr int TV = CW * 64;
+    constexpr int NBOX = TV / kBoxW;
+    static_assert(TV % kBoxW == 0, "tile must be a whole number of TMA boxes");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *ring = reinterpret_cast<double *>(smem_raw);
     double *sQ = ring + (size_t)STAGES * NJ * TV;
@@ -118,7 +122,10 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
                 for (int it = 0; it < nit; ++it) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], kStageBytes);
-                    tma_load_2d(ring + (size_t)stage * NJ * TV, &ymap, &full[stage], c0, it * NJ);
+#pragma unroll
+                    for (int b = 0; b < NBOX; ++b)
+                        tma_load_2d(ring + (size_t)stage * NJ * TV + (size_t)b * NJ * kBoxW, &ymap, &full[stage],
+                                    c0 + b * kBoxW, it * NJ);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -150,7 +157,7 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
         s0.y0 = s1.y0 = 0.0;
         for (int it = 0; it < nit; ++it) {
             mbar_wait(&full[stage], phase);
-            const double *tile = ring + (size_t)stage * NJ * TV + 2 * tid;
+            const double *tile = ring + (size_t)stage * NJ * TV + (size_t)((2 * tid) / kBoxW) * NJ * kBoxW + (2 * tid) % kBoxW;
             if (it == 0 && sd.shift) {
                 const double2 f = *reinterpret_cast<const double2 *>(tile);
                 s0.y0 = f.x;
@@ -159,8 +166,8 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
             const double *q = sQ + (size_t)it * NJ * KP;
             // rows >= n of the last box are TMA zero-fill: their Q rows are zero, but their
             // (0 - y0)^2 must not enter yy, so the last box runs the guarded variant.
-            if (it + 1 < nit) consume_box<KP, NJ, TV, false>(tile, q, s0, s1, NJ);
-            else consume_box<KP, NJ, TV, true>(tile, q, s0, s1, n - it * NJ);
+            if (it + 1 < nit) consume_box<KP, NJ, kBoxW, false>(tile, q, s0, s1, NJ);
+            else consume_box<KP, NJ, kBoxW, true>(tile, q, s0, s1, n - it * NJ);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -348,7 +355,7 @@ int round_up_kp(int p)
     return 32;
 }
 
-template <int KP, int CW, int NJ, int STAGES>
+template <int KP, int CW, int NJ, int STAGES, int MINB>
 cudaError_t launch_tma_cfg(const LmArgs &a, const unsigned char *flags, int sm_count, cudaStream_t st)
 {
     constexpr int TV = CW * 64;
@@ -357,7 +364,8 @@ cudaError_t launch_tma_cfg(const LmArgs &a, const unsigned char *flags, int sm_c
     CUtensorMap map;
     const cuuint64_t dims[2] = {(cuuint64_t)a.V, (cuuint64_t)a.n};
     const cuuint64_t strides[1] = {(cuuint64_t)a.ldY * sizeof(double)};
-    const cuuint32_t box[2] = {TV, NJ};
+    static_assert(TV % kBoxW == 0, "");
+    const cuuint32_t box[2] = {kBoxW, NJ};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(a.Y), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -365,11 +373,12 @@ cudaError_t launch_tma_cfg(const LmArgs &a, const unsigned char *flags, int sm_c
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     const int nq = ((a.n + NJ - 1) / NJ) * NJ;
     const size_t smem = (size_t)STAGES * NJ * TV * 8 + (size_t)nq * KP * 8 + sizeof(SmemDesign<KP>) + 2 * STAGES * 8 + 128;
-    auto kern = lm_fit_tma_kernel<KP, CW, NJ, STAGES>;
+    auto kern = lm_fit_tma_kernel<KP, CW, NJ, STAGES, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t ntiles = (a.V + TV - 1) / TV;
-    const int grid = (int)(ntiles < sm_count ? ntiles : sm_count);
+    const int64_t slots = (int64_t)sm_count * MINB;
+    const int grid = (int)(ntiles < slots ? ntiles : slots);
     kern<<<grid, (CW + 1) * 32, smem, st>>>(map, a, flags);
     return cudaGetLastError();
 }
@@ -385,11 +394,18 @@ template <int KP>
 cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
 {
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0) && (a.ldY % 2 == 0);
-    bool use_tma = plan.variant == LmVariant::Tma ||
-                   (plan.variant == LmVariant::Auto && aligned16 && a.V >= (int64_t)plan.sm_count * 512);
+    // Auto picks the direct-load kernel: measured on B200 it streams config 2 at 6.46 TB/s
+    // (4.48 ms) against 4.41 TB/s (6.57 ms) for the TMA ring (profiles/), so TMA is opt-in.
+    bool use_tma = plan.variant == LmVariant::Tma;
     if (use_tma && (!aligned16 || a.n > 0x7fffffff / 2 || a.V > 0x7fffffffLL)) use_tma = false;
-    constexpr int CW = 8, NJ = 8, STAGES = 4;  // 512-voxel tiles, 32 KiB stages, 128 KiB ring
-    if (use_tma && tma_smem_need<KP>(a.n, CW, NJ, STAGES) > 227 * 1024) use_tma = false;
+    // Tile shapes (consumer warps, subjects per box, ring depth, CTAs per SM).  cfg 0 is the
+    // general default; 1-4 are occupancy variants kept for p <= 4 (RMG_TMA_CFG selects them).
+    int cfg = plan.tma_cfg;
+    if (KP > 4 && cfg != 0) cfg = 0;
+    static const int cfgs[5][4] = {{8, 8, 4, 1}, {8, 4, 4, 2}, {8, 4, 3, 3}, {4, 8, 4, 2}, {4, 4, 4, 4}};
+    if (cfg < 0 || cfg > 4) cfg = 0;
+    const int CW = cfgs[cfg][0], NJ = cfgs[cfg][1], STAGES = cfgs[cfg][2];
+    if (use_tma && tma_smem_need<KP>(a.n, CW, NJ, STAGES) > 227 * 1024 / cfgs[cfg][3]) use_tma = false;
     if (use_tma) {
         const unsigned char *flags = nullptr;
         const int TV = CW * 64;
@@ -401,7 +417,18 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
             if (info) info->launches++;
             flags = scr.flags;
         }
-        cudaError_t e = launch_tma_cfg<KP, CW, NJ, STAGES>(a, flags, plan.sm_count, st);
+        cudaError_t e = cudaErrorInvalidValue;
+        if constexpr (KP <= 4) {
+            switch (cfg) {
+            case 1: e = launch_tma_cfg<KP, 8, 4, 4, 2>(a, flags, plan.sm_count, st); break;
+            case 2: e = launch_tma_cfg<KP, 8, 4, 3, 3>(a, flags, plan.sm_count, st); break;
+            case 3: e = launch_tma_cfg<KP, 4, 8, 4, 2>(a, flags, plan.sm_count, st); break;
+            case 4: e = launch_tma_cfg<KP, 4, 4, 4, 4>(a, flags, plan.sm_count, st); break;
+            default: e = launch_tma_cfg<KP, 8, 8, 4, 1>(a, flags, plan.sm_count, st); break;
+            }
+        } else {
+            e = launch_tma_cfg<KP, 8, 8, 4, 1>(a, flags, plan.sm_count, st);
+        }
         if (info) { info->launches++; info->used_tma = 1; }
         return e;
     }

@@ -27,6 +27,7 @@ struct LmPlan {
     LmVariant variant = LmVariant::Auto;
     int split = 0;       // LDG path: slices of the subject axis (0 = choose)
     int sm_count = 148;
+    int tma_cfg = 0;     // TMA path: tile-shape variant (see lm_kernels.cu)
 };
 
 struct LmLaunchInfo {
