@@ -26,6 +26,7 @@ struct PermKernelParams {
     const PermConst *pc;             // [R]
     const double *y0;                // [V] first sample (0 when !shift)
     const double *yy;                // [V] |y - y0|^2, or -1 for voxels outside the mask
+    const double *ys;                // [V] sum_j (y_j - y0)  (only when the intercept row is skipped)
     unsigned long long *keys;        // [ncols][R]
     const double *Qt;                // [R][n][KP] plain row-major copy of every Q_r (exact path)
     unsigned char *vflag;            // [V] set when some permutation's one-pass rss lost too many digits
@@ -36,7 +37,7 @@ struct PermKernelParams {
 __global__ void __launch_bounds__(256)
 perm_prepass_kernel(const double *__restrict__ Y, int64_t V, int64_t ldY, int n, const double *__restrict__ mask,
                     double lo, double hi, int shift, double *__restrict__ y0, double *__restrict__ yy,
-                    unsigned char *__restrict__ vflag, int *__restrict__ any_zero_row)
+                    double *__restrict__ ys, unsigned char *__restrict__ vflag, int *__restrict__ any_zero_row)
 {
     const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (v >= V) return;
@@ -46,7 +47,7 @@ perm_prepass_kernel(const double *__restrict__ Y, int64_t V, int64_t ldY, int n,
         a0 = mask_selects(mask[v], lo, hi);
         a1 = two && mask_selects(mask[v + 1], lo, hi);
     }
-    double f0 = 0.0, f1 = 0.0, s0 = 0.0, s1 = 0.0;
+    double f0 = 0.0, f1 = 0.0, s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
     if (a0 || a1) {
         const double *yp = Y + v;
         if (shift) {
@@ -64,24 +65,30 @@ perm_prepass_kernel(const double *__restrict__ Y, int64_t V, int64_t ldY, int n,
                     const double a = t[u].x - f0, b = t[u].y - f1;
                     s0 = fma(a, a, s0);
                     s1 = fma(b, b, s1);
+                    t0 += a;
+                    t1 += b;
                 }
             }
         }
         for (; j < n; ++j) {
             const double a = yp[(int64_t)j * ldY] - f0;
             s0 = fma(a, a, s0);
+            t0 += a;
             if (two) {
                 const double b = yp[(int64_t)j * ldY + 1] - f1;
                 s1 = fma(b, b, s1);
+                t1 += b;
             }
         }
     }
     y0[v] = f0;
     yy[v] = a0 ? s0 : -1.0;
+    ys[v] = t0;
     vflag[v] = 0;
     if (two) {
         y0[v + 1] = f1;
         yy[v + 1] = a1 ? s1 : -1.0;
+        ys[v + 1] = t1;
         vflag[v + 1] = 0;
     }
     if ((!a0 || (two && !a1)) && *any_zero_row == 0) *any_zero_row = 1;  // benign race: all writers store 1
@@ -159,11 +166,48 @@ perm_exact_voxels_kernel(PermKernelParams P)
 }
 
 // ---- the GEMM + fused statistics
-template <int KP, int PG>
+// One pipeline stage (KC subjects) of MMAs for this warp.  GUARD: the chunk may contain padding
+// rows (j >= n) whose shared-memory rows hold stale data and must read as 0.
+template <int WM, bool GUARD>
+__device__ __forceinline__ void consume_chunk(double (&acc)[WM][WN][2], const double2 *__restrict__ As,
+                                              const double *__restrict__ Bs, int ksteps, int j0, int q, int n)
+{
+#pragma unroll
+    for (int ks2 = 0; ks2 < KC / 8; ++ks2) {
+        if (!GUARD || ks2 * 2 < ksteps) {
+            double2 a[WM];
+#pragma unroll
+            for (int mt = 0; mt < WM; ++mt) a[mt] = As[(ks2 * WM + mt) * 32];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int ks = ks2 * 2 + half;
+                if (!GUARD || ks < ksteps) {
+                    double b[WN];
+#pragma unroll
+                    for (int nt = 0; nt < WN; ++nt) {
+                        const double t = Bs[ks * 4 * PITCH + nt * 8];
+                        b[nt] = (!GUARD || (j0 + ks * 4 + q) < n) ? t : 0.0;
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < WM; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < WN; ++nt)
+                            dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], half ? a[mt].y : a[mt].x, b[nt]);
+                }
+            }
+        }
+    }
+}
+
+// KP design columns; INV = 1 when component 0 of every permuted design is the (permutation-
+// invariant) constant column c0 * 1: its e_0 = c0 * sum_j y_j comes from the prepass and only
+// KG = KP - INV components per permutation go through the tensor cores.
+template <int KP, int PG, int INV>
 __global__ void __launch_bounds__((CONSUMER_WARPS + 1) * 32, 1)
 perm_gemm_kernel(PermKernelParams P)
 {
-    constexpr int WM = KP * PG;                           // m8-tiles per warp
+    constexpr int KG = KP - INV;
+    constexpr int WM = KG * PG;                           // m8-tiles per warp
     constexpr int A_CHUNK = WARPS_M * (KC / 4) * WM * 32; // doubles per stage
     constexpr int B_CHUNK = KC * PITCH;
     constexpr int PERMS_PER_CTA = WARPS_M * PG * 8;
@@ -218,6 +262,7 @@ perm_gemm_kernel(PermKernelParams P)
     const int warp_m = warp / WARPS_N, warp_n = warp % WARPS_N;
     const int g = lane >> 2, q = lane & 3;
     uint32_t stage = 0, phase = 0;
+    const bool tail_guard = (n % KC) != 0;
 
     for (int64_t vt = blockIdx.x; vt < n_vt; vt += gridDim.x) {
         const int64_t vbase = vt * NT + warp_n * 32 + 2 * q;  // + nt*8 + h
@@ -230,43 +275,20 @@ perm_gemm_kernel(PermKernelParams P)
 
             for (int kc = 0; kc < P.n_kc; ++kc) {
                 const int j0 = kc * KC;
-                const int ksteps = min(KC / 4, (n - j0 + 3) / 4);
                 mbar_wait(&full[stage], phase);
                 const double2 *As = reinterpret_cast<const double2 *>(sA + (size_t)stage * A_CHUNK) +
                                     (size_t)warp_m * (KC / 8) * WM * 32 + lane;
                 const double *Bs = sB + (size_t)stage * B_CHUNK + q * PITCH + warp_n * 32 + g;
-#pragma unroll
-                for (int ks2 = 0; ks2 < KC / 8; ++ks2) {
-                    if (ks2 * 2 < ksteps) {
-                        double2 a[WM];
-#pragma unroll
-                        for (int mt = 0; mt < WM; ++mt) a[mt] = As[(ks2 * WM + mt) * 32];
-#pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            const int ks = ks2 * 2 + half;
-                            if (ks < ksteps) {
-                                double b[WN];
-                                const bool real = (j0 + ks * 4 + q) < n;  // padding rows hold stale data
-#pragma unroll
-                                for (int nt = 0; nt < WN; ++nt) {
-                                    const double t = Bs[ks * 4 * PITCH + nt * 8];
-                                    b[nt] = real ? t : 0.0;
-                                }
-#pragma unroll
-                                for (int mt = 0; mt < WM; ++mt)
-#pragma unroll
-                                    for (int nt = 0; nt < WN; ++nt)
-                                        dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], half ? a[mt].y : a[mt].x, b[nt]);
-                            }
-                        }
-                    }
-                }
+                if (tail_guard && kc == P.n_kc - 1)
+                    consume_chunk<WM, true>(acc, As, Bs, (n - j0 + 3) / 4, j0, q, n);
+                else
+                    consume_chunk<WM, false>(acc, As, Bs, KC / 4, j0, q, n);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
 
-            // ---- fused epilogue: this thread holds, for PG permutations, all KP components of
+            // ---- fused epilogue: this thread holds, for PG permutations, the KG GEMM components of
             //      e = Q_r'y for 8 voxels (nt = 0..3, h = 0..1).
 #pragma unroll
             for (int pg = 0; pg < PG; ++pg) {
@@ -275,6 +297,7 @@ perm_gemm_kernel(PermKernelParams P)
                 const PermConst &pc = P.pc[rvalid ? r : 0];
                 // inv > 0: 1/rss of a regular fit; 0: non-finite statistic (counts as 0); < 0: no contribution
                 double inv[WN][2];
+                double e0[WN][2];   // INV: the un-shifted invariant component
                 {
                     double q1[KP];
 #pragma unroll
@@ -285,14 +308,20 @@ perm_gemm_kernel(PermKernelParams P)
                         for (int h = 0; h < 2; ++h) {
                             const int64_t v = vbase + nt * 8 + h;
                             double w = -1.0;
+                            e0[nt][h] = 0.0;
                             if (rvalid && v < P.V) {
                                 const double yy = P.yy[v];
                                 if (yy >= 0.0) {  // yy < 0 marks a voxel outside the mask (global 0 floor)
                                     const double y0 = P.y0[v];
                                     double ee = 0.0;
+                                    if (INV) {
+                                        const double es = pc.c0 * P.ys[v];      // c0 * sum(y - y0)
+                                        ee = es * es;
+                                        e0[nt][h] = fma(y0, q1[0], es);
+                                    }
 #pragma unroll
-                                    for (int k = 0; k < KP; ++k) {
-                                        const double es = fma(-y0, q1[k], acc[pg * KP + k][nt][h]);
+                                    for (int k = 0; k < KG; ++k) {
+                                        const double es = fma(-y0, q1[k + INV], acc[pg * KG + k][nt][h]);
                                         ee = fma(es, es, ee);
                                     }
                                     const double rss = yy - ee;
@@ -322,9 +351,9 @@ perm_gemm_kernel(PermKernelParams P)
                         for (int h = 0; h < 2; ++h) {
                             const double w = inv[nt][h];
                             if (w > 0.0) {
-                                double b = 0.0;
+                                double b = INV ? rrow[0] * e0[nt][h] : 0.0;
 #pragma unroll
-                                for (int j = 0; j < KP; ++j) b = fma(rrow[j], acc[pg * KP + j][nt][h], b);
+                                for (int j = 0; j < KG; ++j) b = fma(rrow[j + INV], acc[pg * KG + j][nt][h], b);
                                 double s = b * b * w;
                                 if (!P.two_sided && b < 0.0) s = -s;
                                 if (!isfinite(s)) s = 0.0;
@@ -344,13 +373,13 @@ perm_gemm_kernel(PermKernelParams P)
     }
 }
 
-template <int KP, int PG>
+template <int KP, int PG, int INV>
 cudaError_t launch_gemm(const PermKernelParams &P, int sm_count, cudaStream_t st)
 {
-    constexpr int WM = KP * PG;
+    constexpr int WM = (KP - INV) * PG;
     constexpr int A_CHUNK = WARPS_M * (KC / 4) * WM * 32;
     const size_t smem = (size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + 2 * STAGES * 8;
-    auto kern = perm_gemm_kernel<KP, PG>;
+    auto kern = perm_gemm_kernel<KP, PG, INV>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t n_vt = (P.V + NT - 1) / NT;
@@ -359,7 +388,8 @@ cudaError_t launch_gemm(const PermKernelParams &P, int sm_count, cudaStream_t st
     return cudaGetLastError();
 }
 
-constexpr int pg_for(int kp) { return kp == 1 ? 8 : kp == 2 ? 4 : kp <= 4 ? 2 : 1; }
+// permutation groups (of 8) per warp for KG GEMM components per permutation: KG * PG <= 8 m-tiles
+constexpr int pg_for(int kg) { return kg == 1 ? 8 : kg == 2 ? 4 : kg <= 4 ? 2 : 1; }
 
 }  // namespace
 
@@ -376,14 +406,28 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
                           int sm_count, cudaStream_t st, int *launches, void **workspace_out)
 {
     const int R = a.R, n = a.n, p = a.p, KP = p;
-    const int PG = pg_for(KP);
-    const int WM = KP * PG;
+    // Is component 0 of every permuted design the same constant column (the intercept, first in
+    // pivot order)?  Then e_0 = c0 * sum(y) is permutation-invariant and needs no tensor-core row.
+    int INV = (KP >= 2 && all_intercept && !std::getenv("RMG_PERM_NO_INV")) ? 1 : 0;
+    std::vector<double> c0(R, 0.0);
+    for (int r = 0; r < R && INV; ++r) {
+        const Design &D = designs[r];
+        if (D.k < 1) { INV = 0; break; }
+        const double *q = D.Q.data();
+        double lo = q[0], hi = q[0], sum = 0.0;
+        for (int j = 0; j < n; ++j) { lo = std::min(lo, q[j]); hi = std::max(hi, q[j]); sum += q[j]; }
+        if (!(hi - lo <= 1e-13 * std::fabs(hi)) || hi == 0.0) { INV = 0; break; }
+        c0[r] = sum / n;
+    }
+    const int KG = KP - INV;
+    const int PG = pg_for(KG);
+    const int WM = KG * PG;
     const int A_CHUNK = WARPS_M * (KC / 4) * WM * 32;
     const int perms_per_cta = WARPS_M * PG * 8;
     const int n_pt = (R + perms_per_cta - 1) / perms_per_cta;
     const int n_kc = (n + KC - 1) / KC;
 
-    // ---- host packing: A in fragment order, plain Qt for the redo path, per-permutation constants
+    // ---- host packing: A in fragment order, plain Qt for the exact path, per-permutation constants
     std::vector<double> Apack((size_t)n_pt * n_kc * A_CHUNK, 0.0);
     std::vector<double> Qt((size_t)R * n * KP, 0.0);
     std::vector<PermConst> pc(R);
@@ -397,13 +441,15 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
             for (int j = 0; j < p; ++j) c.Rinv[i * 8 + j] = D.Rinv[i + (size_t)j * p];
         }
         c.rdf = (double)(n - p);
+        c.c0 = c0[r];
         const int pt = r / perms_per_cta, rr = r % perms_per_cta;
         const int warp_m = rr / (PG * 8), pg = (rr / 8) % PG, g = rr % 8;
         for (int k = 0; k < D.k; ++k) {
             const double *qcol = D.Q.data() + (size_t)k * n;
-            const int mt = pg * KP + k;
+            for (int j = 0; j < n; ++j) Qt[((size_t)r * n + j) * KP + k] = qcol[j];
+            if (k < INV) continue;
+            const int mt = pg * KG + (k - INV);
             for (int j = 0; j < n; ++j) {
-                Qt[((size_t)r * n + j) * KP + k] = qcol[j];
                 const int kc = j / KC, jj = j % KC, ks = jj / 4, q = jj % 4;
                 const int lane = g * 4 + q;
                 // [pt][kc] chunk, inside: [warp_m][ks/2][mt][lane][ks%2]
@@ -418,7 +464,8 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
     const size_t oA = carve(Apack.size() * 8), oQ = carve(Qt.size() * 8), oP = carve(pc.size() * sizeof(PermConst));
-    const size_t oY0 = carve((size_t)a.V * 8), oYY = carve((size_t)a.V * 8), oFlag = carve(256), oVf = carve((size_t)a.V);
+    const size_t oY0 = carve((size_t)a.V * 8), oYY = carve((size_t)a.V * 8), oYS = carve((size_t)a.V * 8);
+    const size_t oFlag = carve(256), oVf = carve((size_t)a.V);
     char *ws = nullptr;
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ws), off, st);
     if (e != cudaSuccess) return e;
@@ -438,6 +485,7 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
     P.pc = reinterpret_cast<PermConst *>(ws + oP);
     P.y0 = reinterpret_cast<double *>(ws + oY0);
     P.yy = reinterpret_cast<double *>(ws + oYY);
+    P.ys = reinterpret_cast<double *>(ws + oYS);
     P.keys = a.keys;
     P.Qt = reinterpret_cast<double *>(ws + oQ);
     P.vflag = reinterpret_cast<unsigned char *>(ws + oVf);
@@ -449,14 +497,18 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
     const int64_t pairs = (a.V + 1) / 2;
     perm_prepass_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(a.Y, a.V, a.ldY, n, a.mask, a.mask_lo, a.mask_hi,
                                                                            P.shift, reinterpret_cast<double *>(ws + oY0),
-                                                                           reinterpret_cast<double *>(ws + oYY), P.vflag, any_zero);
+                                                                           reinterpret_cast<double *>(ws + oYY),
+                                                                           reinterpret_cast<double *>(ws + oYS), P.vflag, any_zero);
     const int nk = R * a.ncols;
     perm_floor_keys_kernel<<<(nk + 255) / 256, 256, 0, st>>>(a.keys, nk, any_zero);
     *launches += 2;
-    switch (KP) {
-#define RMG_PG_CASE(K) case K: e = launch_gemm<K, pg_for(K)>(P, sm_count, st); break;
+    switch (KP * 2 + INV) {
+#define RMG_PG_CASE(K) case K * 2: e = launch_gemm<K, pg_for(K), 0>(P, sm_count, st); break;
+#define RMG_PG_CASE1(K) case K * 2 + 1: e = launch_gemm<K, pg_for(K - 1), 1>(P, sm_count, st); break;
         RMG_PG_CASE(1) RMG_PG_CASE(2) RMG_PG_CASE(3) RMG_PG_CASE(4) RMG_PG_CASE(5) RMG_PG_CASE(6) RMG_PG_CASE(7) RMG_PG_CASE(8)
+        RMG_PG_CASE1(2) RMG_PG_CASE1(3) RMG_PG_CASE1(4) RMG_PG_CASE1(5) RMG_PG_CASE1(6) RMG_PG_CASE1(7) RMG_PG_CASE1(8)
 #undef RMG_PG_CASE
+#undef RMG_PG_CASE1
     default: e = cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;

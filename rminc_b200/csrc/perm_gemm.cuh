@@ -91,7 +91,8 @@ struct PermConst {
     double Rinv[64];   // row-major 8 x 8
     double ct[8];
     double rdf;
-    double pad[7];
+    double c0;         // the constant value of Q_r[:, 0] when the intercept row is skipped
+    double pad[6];
 };
 
 bool perm_gemm_supported(int n, int p, int64_t V, int64_t ldY, const double *dY, const int32_t *hcols, int ncols);
