@@ -352,8 +352,10 @@ def run_gpu_arm(args):
         lib = _lib.load()
         err = _lib.errbuf()
 
+        Xf = np.asfortranarray(X)          # keep alive: ctypes only sees the address
+
         def e2e_step():
-            rc = lib.rmg_lm_fit(Yh.ctypes.data, Ve, Ve, n, np.asfortranarray(X).ctypes.data, p, None, 1.0, 99999999.0,
+            rc = lib.rmg_lm_fit(Yh.ctypes.data, Ve, Ve, n, Xf.ctypes.data, p, None, 1.0, 99999999.0,
                                 Oh.ctypes.data, Ve, local_rank, err, len(err))
             _lib.check(rc, err)
 

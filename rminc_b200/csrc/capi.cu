@@ -78,7 +78,9 @@ void fill_dev_design(const Design &D, DevDesign &dd)
 
 std::vector<double> make_qt(const Design &D, int KP)
 {
-    std::vector<double> qt((size_t)D.n * KP, 0.0);
+    // rows padded with zeros to a multiple of 16 subjects: the TMA kernel bulk-copies whole stages
+    const size_t rows = ((size_t)D.n + 15) / 16 * 16;
+    std::vector<double> qt(rows * KP, 0.0);
     for (int c = 0; c < D.k; ++c)
         for (int i = 0; i < D.n; ++i) qt[(size_t)i * KP + c] = D.Q[i + (size_t)c * D.n];
     return qt;

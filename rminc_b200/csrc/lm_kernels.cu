@@ -14,13 +14,14 @@
 //
 // Two implementations of the same contract:
 //   lm_fit_tma_kernel : persistent CTAs; one producer thread issues 2-D TMA tile loads
-//                       (cp.async.bulk.tensor, FP64 boxes of NJ subjects x TV voxels) into
-//                       a shared-memory ring guarded by mbarriers; consumer warps reduce
-//                       out of shared memory.  Default for large V.
+//                       (cp.async.bulk.tensor, FP64 boxes of NJ subjects x up to 256 voxels)
+//                       plus the matching rows of Q' into a shared-memory ring guarded by
+//                       mbarriers; consumer warps reduce out of shared memory.  Default
+//                       whenever TMA can describe Y (16-byte aligned base and row pitch).
 //   lm_fit_ldg_kernel : thread-per-voxel(-pair) direct streaming loads with an optional
 //                       split of the subject axis across threadIdx.y (K2, "split-n") and a
-//                       shared-memory reduction, for small V / large n and for layouts
-//                       TMA cannot describe (odd ldY, unaligned base).
+//                       shared-memory reduction, for layouts TMA cannot describe (odd ldY,
+//                       unaligned base), p > 16, or on request (RMG_FIT_VARIANT=ldg).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -73,32 +74,30 @@ __device__ __forceinline__ void consume_box(const double *__restrict__ tile, con
 
 // ------------------------------------------------------------------ TMA kernel
 // CTA = 1 producer warp + CW consumer warps.  Tile = TV = CW*64 voxels (2 per consumer
-// thread), streamed as TMA boxes of NJ subjects x kBoxW voxels (a TMA box dimension is at most
-// 256 elements, so a stage is TV/kBoxW boxes).  Shared memory:
-//   [ring: STAGES x (TV/kBoxW) x NJ x kBoxW doubles][Qt: n x KP doubles][SmemDesign][mbarriers]
-constexpr int kBoxW = 256;
+// thread).  One pipeline stage holds NJ subjects: the Y box(es) -- 2-D TMA tiles of NJ x
+// min(TV,256) doubles (a TMA box dimension is at most 256 elements) -- and the matching NJ
+// rows of Q' (a 1-D bulk copy), so nothing of size n lives in shared memory and any n fits.
+// Shared memory: [ring: STAGES x (NJ x TV + NJ x KP) doubles][SmemDesign][mbarriers]
 template <int KP, int CW, int NJ, int STAGES, int MINB>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB)
 lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsigned char *__restrict__ flags)
 {
     constexpr int TV = CW * 64;
-    constexpr int NBOX = TV / kBoxW;
-    static_assert(TV % kBoxW == 0, "tile must be a whole number of TMA boxes");
+    constexpr int BOXW = TV < 256 ? TV : 256;
+    constexpr int NBOX = TV / BOXW;
+    constexpr int STAGE_D = NJ * TV + NJ * KP + ((NJ * KP) & 1);   // doubles per stage, 16-byte multiple
+    static_assert(TV % BOXW == 0 && NJ % 2 == 0, "tile must be whole TMA boxes; Q rows must copy in 16-byte units");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *ring = reinterpret_cast<double *>(smem_raw);
-    double *sQ = ring + (size_t)STAGES * NJ * TV;
-    const int n = a.n;
-    const int nq = ((n + NJ - 1) / NJ) * NJ;  // rows of sQ incl. zero padding
-    SmemDesign<KP> &sd = *reinterpret_cast<SmemDesign<KP> *>(sQ + (size_t)nq * KP);
+    SmemDesign<KP> &sd = *reinterpret_cast<SmemDesign<KP> *>(ring + (size_t)STAGES * STAGE_D);
     uint64_t *full = reinterpret_cast<uint64_t *>(&sd + 1);
     uint64_t *empty = full + STAGES;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const int nthreads = blockDim.x;
+    const int n = a.n;
 
-    for (int i = tid; i < nq * KP; i += nthreads) sQ[i] = (i < n * KP) ? a.Qt[i] : 0.0;
-    load_design_to_smem<KP>(sd, a.design, tid, nthreads);
+    load_design_to_smem<KP>(sd, a.design, tid, blockDim.x);
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
@@ -109,8 +108,8 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
     __syncthreads();
 
     const int64_t ntiles = (a.V + TV - 1) / TV;
-    const int nit = nq / NJ;
-    constexpr uint32_t kStageBytes = NJ * TV * sizeof(double);
+    const int nit = (n + NJ - 1) / NJ;
+    constexpr uint32_t kStageBytes = (NJ * TV + NJ * KP) * sizeof(double);
 
     if (warp == CW) {
         // ===== producer: one elected lane walks the same tile sequence as the consumers
@@ -120,12 +119,14 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
                 if (flags && !flags[t]) continue;
                 const int c0 = (int)(t * TV);
                 for (int it = 0; it < nit; ++it) {
+                    double *dst = ring + (size_t)stage * STAGE_D;
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], kStageBytes);
 #pragma unroll
                     for (int b = 0; b < NBOX; ++b)
-                        tma_load_2d(ring + (size_t)stage * NJ * TV + (size_t)b * NJ * kBoxW, &ymap, &full[stage],
-                                    c0 + b * kBoxW, it * NJ);
+                        tma_load_2d(dst + (size_t)b * NJ * BOXW, &ymap, &full[stage], c0 + b * BOXW, it * NJ);
+                    // Qt is padded with zero rows to a multiple of 16 subjects (capi.cu: make_qt)
+                    bulk_load_1d(dst + NJ * TV, a.Qt + (size_t)it * NJ * KP, NJ * KP * sizeof(double), &full[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -157,17 +158,18 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
         s0.y0 = s1.y0 = 0.0;
         for (int it = 0; it < nit; ++it) {
             mbar_wait(&full[stage], phase);
-            const double *tile = ring + (size_t)stage * NJ * TV + (size_t)((2 * tid) / kBoxW) * NJ * kBoxW + (2 * tid) % kBoxW;
+            const double *st = ring + (size_t)stage * STAGE_D;
+            const double *tile = st + (size_t)((2 * tid) / BOXW) * NJ * BOXW + (2 * tid) % BOXW;
             if (it == 0 && sd.shift) {
                 const double2 f = *reinterpret_cast<const double2 *>(tile);
                 s0.y0 = f.x;
                 s1.y0 = f.y;
             }
-            const double *q = sQ + (size_t)it * NJ * KP;
+            const double *q = st + NJ * TV;
             // rows >= n of the last box are TMA zero-fill: their Q rows are zero, but their
             // (0 - y0)^2 must not enter yy, so the last box runs the guarded variant.
-            if (it + 1 < nit) consume_box<KP, NJ, kBoxW, false>(tile, q, s0, s1, NJ);
-            else consume_box<KP, NJ, kBoxW, true>(tile, q, s0, s1, n - it * NJ);
+            if (it + 1 < nit) consume_box<KP, NJ, BOXW, false>(tile, q, s0, s1, NJ);
+            else consume_box<KP, NJ, BOXW, true>(tile, q, s0, s1, n - it * NJ);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -355,24 +357,30 @@ int round_up_kp(int p)
     return 32;
 }
 
+template <int KP, int CW, int NJ, int STAGES>
+constexpr size_t tma_smem_bytes()
+{
+    return (size_t)STAGES * (NJ * CW * 64 + NJ * KP + ((NJ * KP) & 1)) * 8 + sizeof(SmemDesign<KP>) + 2 * STAGES * 8 + 128;
+}
+
 template <int KP, int CW, int NJ, int STAGES, int MINB>
 cudaError_t launch_tma_cfg(const LmArgs &a, const unsigned char *flags, int sm_count, cudaStream_t st)
 {
     constexpr int TV = CW * 64;
+    constexpr int BOXW = TV < 256 ? TV : 256;
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return cudaErrorNotSupported;
     CUtensorMap map;
     const cuuint64_t dims[2] = {(cuuint64_t)a.V, (cuuint64_t)a.n};
     const cuuint64_t strides[1] = {(cuuint64_t)a.ldY * sizeof(double)};
-    static_assert(TV % kBoxW == 0, "");
-    const cuuint32_t box[2] = {kBoxW, NJ};
+    const cuuint32_t box[2] = {BOXW, NJ};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(a.Y), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    const int nq = ((a.n + NJ - 1) / NJ) * NJ;
-    const size_t smem = (size_t)STAGES * NJ * TV * 8 + (size_t)nq * KP * 8 + sizeof(SmemDesign<KP>) + 2 * STAGES * 8 + 128;
+    constexpr size_t smem = tma_smem_bytes<KP, CW, NJ, STAGES>();
+    static_assert(smem * MINB <= 227 * 1024, "tile shape does not fit the requested CTAs per SM");
     auto kern = lm_fit_tma_kernel<KP, CW, NJ, STAGES, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -384,31 +392,21 @@ cudaError_t launch_tma_cfg(const LmArgs &a, const unsigned char *flags, int sm_c
 }
 
 template <int KP>
-size_t tma_smem_need(int n, int CW, int NJ, int STAGES)
-{
-    const int nq = ((n + NJ - 1) / NJ) * NJ;
-    return (size_t)STAGES * NJ * CW * 64 * 8 + (size_t)nq * KP * 8 + sizeof(SmemDesign<KP>) + 2 * STAGES * 8 + 128;
-}
-
-template <int KP>
 cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
 {
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0) && (a.ldY % 2 == 0);
-    // Auto picks the direct-load kernel: measured on B200 it streams config 2 at 6.46 TB/s
-    // (4.48 ms) against 4.41 TB/s (6.57 ms) for the TMA ring (profiles/), so TMA is opt-in.
-    bool use_tma = plan.variant == LmVariant::Tma;
-    if (use_tma && (!aligned16 || a.n > 0x7fffffff / 2 || a.V > 0x7fffffffLL)) use_tma = false;
-    // Tile shapes (consumer warps, subjects per box, ring depth, CTAs per SM).  cfg 0 is the
-    // general default; 1-4 are occupancy variants kept for p <= 4 (RMG_TMA_CFG selects them).
-    int cfg = plan.tma_cfg;
-    if (KP > 4 && cfg != 0) cfg = 0;
-    static const int cfgs[5][4] = {{8, 8, 4, 1}, {8, 4, 4, 2}, {8, 4, 3, 3}, {4, 8, 4, 2}, {4, 4, 4, 4}};
-    if (cfg < 0 || cfg > 4) cfg = 0;
-    const int CW = cfgs[cfg][0], NJ = cfgs[cfg][1], STAGES = cfgs[cfg][2];
-    if (use_tma && tma_smem_need<KP>(a.n, CW, NJ, STAGES) > 227 * 1024 / cfgs[cfg][3]) use_tma = false;
+    // TMA needs a 16-byte aligned base and row pitch; int32 tile coordinates.
+    const bool tma_ok = aligned16 && a.V <= 0x7fffffffLL && KP <= 16;
+    bool use_tma = tma_ok && plan.variant != LmVariant::Ldg;
     if (use_tma) {
+        // Tile shapes (consumer warps, subjects per stage, ring depth, CTAs per SM):
+        //   wide   4 x 64 = 256-voxel tiles, 4 CTAs/SM   -- large V (config 2: 4.5 ms, 98 % of the copy peak)
+        //   narrow 2 x 64 = 128-voxel tiles, 8 CTAs/SM   -- small V: more, smaller tiles to balance 148 SMs
+        //   cfg 0 (one 512-voxel CTA per SM) is kept for the record: too few warps to hide latency.
+        int cfg = plan.tma_cfg;
+        if (cfg < 0) cfg = (a.V >= (int64_t)plan.sm_count * 4 * 256 * 2) ? 4 : 5;
+        const int TV = cfg == 0 ? 512 : (cfg == 5 ? 128 : 256);
         const unsigned char *flags = nullptr;
-        const int TV = CW * 64;
         if (a.mask) {
             const int64_t ntiles = (a.V + TV - 1) / TV;
             cudaError_t e = scr.ensure_flags((size_t)ntiles, st);
@@ -417,21 +415,22 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
             if (info) info->launches++;
             flags = scr.flags;
         }
-        cudaError_t e = cudaErrorInvalidValue;
-        if constexpr (KP <= 4) {
+        cudaError_t e;
+        if constexpr (KP <= 8) {
             switch (cfg) {
-            case 1: e = launch_tma_cfg<KP, 8, 4, 4, 2>(a, flags, plan.sm_count, st); break;
-            case 2: e = launch_tma_cfg<KP, 8, 4, 3, 3>(a, flags, plan.sm_count, st); break;
-            case 3: e = launch_tma_cfg<KP, 4, 8, 4, 2>(a, flags, plan.sm_count, st); break;
-            case 4: e = launch_tma_cfg<KP, 4, 4, 4, 4>(a, flags, plan.sm_count, st); break;
-            default: e = launch_tma_cfg<KP, 8, 8, 4, 1>(a, flags, plan.sm_count, st); break;
+            case 0: e = launch_tma_cfg<KP, 8, 8, 4, 1>(a, flags, plan.sm_count, st); break;
+            case 5: e = launch_tma_cfg<KP, 2, 4, 4, 8>(a, flags, plan.sm_count, st); break;
+            default: e = launch_tma_cfg<KP, 4, 4, 4, 4>(a, flags, plan.sm_count, st); break;
             }
         } else {
-            e = launch_tma_cfg<KP, 8, 8, 4, 1>(a, flags, plan.sm_count, st);
+            // wide designs: more accumulators per thread -> fewer CTAs per SM
+            e = cfg == 5 ? launch_tma_cfg<KP, 2, 4, 4, 4>(a, flags, plan.sm_count, st)
+                         : launch_tma_cfg<KP, 4, 4, 4, 2>(a, flags, plan.sm_count, st);
         }
-        if (info) { info->launches++; info->used_tma = 1; }
+        if (info) { info->launches++; info->used_tma = 1; info->tma_cfg = cfg; }
         return e;
     }
+    if (plan.variant == LmVariant::Tma) return cudaErrorInvalidValue;  // asked for TMA on a layout it cannot describe
     // ---- LDG path: pick voxels/thread, split factor and Q tile
     const bool vec2 = aligned16 && (a.V % 2 == 0) && (a.ldOut % 2 == 0) && KP <= 16;
     int S = plan.split;

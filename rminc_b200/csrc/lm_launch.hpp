@@ -27,12 +27,13 @@ struct LmPlan {
     LmVariant variant = LmVariant::Auto;
     int split = 0;       // LDG path: slices of the subject axis (0 = choose)
     int sm_count = 148;
-    int tma_cfg = 0;     // TMA path: tile-shape variant (see lm_kernels.cu)
+    int tma_cfg = -1;    // TMA path: tile-shape variant (-1 = choose by V; see lm_kernels.cu)
 };
 
 struct LmLaunchInfo {
     int launches = 0;
     int used_tma = 0;
+    int tma_cfg = -1;
     int split = 1;
 };
 

@@ -167,14 +167,15 @@ int rmg_randomize_device(const double *dY, int64_t V, int64_t ldY, int n, const 
             DevDesign *dd = nullptr;
             double *qt = nullptr;
             RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dd), sizeof(DevDesign) * (size_t)R, st));
-            RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&qt), sizeof(double) * (size_t)R * n * KP, st));
+            const size_t qstride = make_qt(pd.designs[0], KP).size();   // rows padded for the TMA kernel
+            RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&qt), sizeof(double) * (size_t)R * qstride, st));
             {
                 std::vector<DevDesign> hdd(R);
-                std::vector<double> hqt((size_t)R * n * KP);
+                std::vector<double> hqt((size_t)R * qstride);
                 for (int r = 0; r < R; ++r) {
                     fill_dev_design(pd.designs[r], hdd[r]);
                     const std::vector<double> q = make_qt(pd.designs[r], KP);
-                    std::copy(q.begin(), q.end(), hqt.begin() + (size_t)r * n * KP);
+                    std::copy(q.begin(), q.end(), hqt.begin() + (size_t)r * qstride);
                 }
                 cudaError_t e1 = cudaMemcpyAsync(dd, hdd.data(), sizeof(DevDesign) * (size_t)R, cudaMemcpyHostToDevice, st);
                 cudaError_t e2 = cudaMemcpyAsync(qt, hqt.data(), sizeof(double) * hqt.size(), cudaMemcpyHostToDevice, st);
@@ -190,7 +191,7 @@ int rmg_randomize_device(const double *dY, int64_t V, int64_t ldY, int n, const 
             const int cm_grid = (int)std::min<int64_t>((V + 255) / 256, (int64_t)plan.sm_count * 8);
             cudaError_t le = cudaSuccess;
             for (int r = 0; r < R && le == cudaSuccess; ++r) {
-                LmArgs a{dY, V, ldY, n, p, qt + (size_t)r * n * KP, dd + r, dmask, mask_lo, mask_hi, scratch, ldo};
+                LmArgs a{dY, V, ldY, n, p, qt + (size_t)r * qstride, dd + r, dmask, mask_lo, mask_hi, scratch, ldo};
                 LmLaunchInfo info;
                 le = launch_lm_fit(a, plan, scr, st, &info);
                 launches += info.launches;
