@@ -242,7 +242,8 @@ def run_gpu_arm(args):
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel": core.last_fit_variant(), "kernel_ms": kern_ms}
+                "kernel": core.last_fit_variant(), "kernel_ms": kern_ms,
+                "step_ms": [round(x, 4) for x in step_ms]}
 
     # ---- masked variant (ellipsoid, ~38 % inside), reported beside the headline
     masked = None
@@ -275,12 +276,16 @@ def run_gpu_arm(args):
         Yv = gen_Y(torch, Vv, nv, dev, seed=3, mean=2.5, sd=0.4)
         ov = torch.empty((2 * pv + 3, Vv), dtype=torch.float64, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # 1.3 GB input < 10x L2: flush between steps
-        times = []
+        times, host_us = [], []
         for i in range(3 + args.steps):
             flush.zero_()
+            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
+            torch.cuda._sleep(10_000_000)      # ~1.5 ms of GPU spin: the host-side part of the call (design
+            e0.record(stream)                 # factorisation, upload, launch) overlaps it, so e0..e1 is the
+            t0 = time.perf_counter()          # device time of the call, not the launch latency
             core.lm_fit_torch(Yv, Xv, out=ov)
+            host_us.append((time.perf_counter() - t0) * 1e6)
             e1.record(stream)
             torch.cuda.synchronize()
             if i >= 3:
@@ -290,7 +295,8 @@ def run_gpu_arm(args):
         vertex = {"workload": "vertexLm, 81,924 vertices x 2000 subjects, p = 7", "ms_per_step": ms,
                   "vertices_per_s": Vv / (ms * 1e-3), "achieved_gbs": vb / (ms * 1e-3) / 1e9,
                   "frac_of_hbm_peak": vb / (ms * 1e-3) / 1e9 / measured_hbm_peak()[0],
-                  "l2": "256 MiB write between steps flushes L2", "kernel": core.last_fit_variant()}
+                  "l2": "256 MiB write between steps flushes L2", "kernel": core.last_fit_variant(),
+                  "host_call_us": float(np.median(host_us[3:]))}
         del Yv, ov, flush
 
     # ---- mincRandomize (config 4): voxel-sharded, all ranks evaluate every permutation, one all-reduce(MAX)

@@ -7,6 +7,8 @@
 // fails with RMG_ERR_NO_DEVICE when no CUDA device is usable.
 #include <algorithm>
 #include <cmath>
+#include <memory>
+#include <mutex>
 #include <thread>
 
 #include "capi_common.hpp"
@@ -31,6 +33,18 @@ int select_device(int device, char *err, size_t errlen)
         return fail(err, errlen, RMG_ERR_NO_DEVICE, "device %d out of range (have %d)", device, count);
     e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail(err, errlen, RMG_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    // Keep stream-ordered allocations in the pool across synchronisations: with the default
+    // release threshold (0) every cudaMallocAsync after a sync goes back to the OS (~ms).
+    static std::atomic<uint64_t> pool_ready{0};
+    if (device < 64 && !(pool_ready.load() & (1ull << device))) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        pool_ready.fetch_or(1ull << device);
+    }
     return RMG_OK;
 }
 
@@ -97,33 +111,86 @@ int factor_or_fail(const double *X, int n, int p, Design &D, char *err, size_t e
 
 namespace {
 
-// Design constants resident on the current device for the duration of one call.
-struct DeviceDesign {
+// Device-resident design constants, cached per (device, X).  A mincLm call, every chunk of
+// the host pipeline and repeated calls with the same model matrix share one entry, so the
+// steady-state cost of a call is the kernel launch alone: no re-factorisation, no upload and
+// no allocation on the caller's stream.  Entries are immutable once `ready` has fired; consumers
+// make their stream wait on it.
+struct CachedDesign {
+    int device = -1;
+    std::vector<double> X;   // n x p, the key
+    Design D;
     DevDesign *dd = nullptr;
     double *qt = nullptr;
-    cudaError_t upload(const Design &D, cudaStream_t st)
+    cudaEvent_t ready = nullptr;
+    uint64_t last_use = 0;
+    ~CachedDesign()
     {
-        DevDesign h;
-        fill_dev_design(D, h);
-        const int KP = lm_padded_p(D.p);
-        const std::vector<double> qt_h = make_qt(D, KP);
-        cudaError_t e = cudaMallocAsync(&dd, sizeof(DevDesign), st);
-        if (e != cudaSuccess) return e;
-        e = cudaMallocAsync(&qt, qt_h.size() * sizeof(double), st);
-        if (e != cudaSuccess) return e;
-        // pageable sources: the runtime stages them before returning, so the locals may die
-        e = cudaMemcpyAsync(dd, &h, sizeof h, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) return e;
-        return cudaMemcpyAsync(qt, qt_h.data(), qt_h.size() * sizeof(double), cudaMemcpyHostToDevice, st);
-    }
-    void release(cudaStream_t st)
-    {
-        if (dd) cudaFreeAsync(dd, st);
-        if (qt) cudaFreeAsync(qt, st);
-        dd = nullptr;
-        qt = nullptr;
+        // cudaFree synchronises the device: no kernel can still be reading the buffers
+        int cur = 0;
+        if (device >= 0 && cudaGetDevice(&cur) == cudaSuccess) {
+            cudaSetDevice(device);
+            if (dd) cudaFree(dd);
+            if (qt) cudaFree(qt);
+            if (ready) cudaEventDestroy(ready);
+            cudaSetDevice(cur);
+        }
     }
 };
+
+std::mutex g_cache_mu;
+std::vector<std::shared_ptr<CachedDesign>> g_cache;
+uint64_t g_cache_tick = 0;
+constexpr size_t kCacheEntries = 16;
+
+// Looks up (or builds) the cached design for X on the current device.  rc != RMG_OK on error.
+std::shared_ptr<CachedDesign> design_cache_get(int device, const double *X, int n, int p, int &rc, char *err,
+                                               size_t errlen)
+{
+    const size_t cnt = (size_t)n * p;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (auto &e : g_cache)
+            if (e->device == device && e->D.n == n && e->D.p == p && std::memcmp(e->X.data(), X, cnt * 8) == 0) {
+                e->last_use = ++g_cache_tick;
+                rc = RMG_OK;
+                return e;
+            }
+    }
+    auto e = std::make_shared<CachedDesign>();
+    if ((rc = factor_or_fail(X, n, p, e->D, err, errlen))) return nullptr;
+    e->device = device;
+    e->X.assign(X, X + cnt);
+    DevDesign h;
+    fill_dev_design(e->D, h);
+    const std::vector<double> qt_h = make_qt(e->D, lm_padded_p(p));
+    cudaStream_t up = nullptr;
+    cudaError_t ce = cudaMalloc(reinterpret_cast<void **>(&e->dd), sizeof(DevDesign));
+    if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void **>(&e->qt), qt_h.size() * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming);
+    // upload on a private stream so a miss never serialises with the caller's queued work
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->dd, &h, sizeof h, cudaMemcpyHostToDevice, up);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->qt, qt_h.data(), qt_h.size() * sizeof(double), cudaMemcpyHostToDevice, up);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e->ready, up);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(up);   // pageable sources die with this scope
+    if (up) cudaStreamDestroy(up);
+    if (ce != cudaSuccess) {
+        rc = fail(err, errlen, RMG_ERR_CUDA, "uploading the design failed: %s", cudaGetErrorString(ce));
+        cudaGetLastError();
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    e->last_use = ++g_cache_tick;
+    if (g_cache.size() >= kCacheEntries) {
+        auto victim = std::min_element(g_cache.begin(), g_cache.end(),
+                                       [](const auto &a, const auto &b) { return a->last_use < b->last_use; });
+        g_cache.erase(victim);   // freed when the last user drops its reference
+    }
+    g_cache.push_back(e);
+    rc = RMG_OK;
+    return e;
+}
 
 LmPlan plan_from_env(int device)
 {
@@ -135,6 +202,7 @@ LmPlan plan_from_env(int device)
     }
     if (const char *s = std::getenv("RMG_FIT_SPLIT")) plan.split = std::atoi(s);
     if (const char *s = std::getenv("RMG_TMA_CFG")) plan.tma_cfg = std::atoi(s);
+    if (const char *s = std::getenv("RMG_TMA_QSTREAM")) plan.q_stream = std::atoi(s);
     return plan;
 }
 
@@ -184,22 +252,20 @@ int rmg_lm_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const dou
 {
     int rc = check_fit_args(dY, V, ldY, n, X, p, dout, ldOut, err, errlen);
     if (rc) return rc;
-    Design D;
-    if ((rc = factor_or_fail(X, n, p, D, err, errlen))) return rc;
     if ((rc = select_device(device, err, errlen))) return rc;
+    std::shared_ptr<CachedDesign> cd = design_cache_get(device, X, n, p, rc, err, errlen);
+    if (!cd) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    DeviceDesign dev;
     LmScratch scr;
     LmLaunchInfo info;
     {
-        RMG_CUDA(dev.upload(D, st));
-        LmArgs a{dY, V, ldY, n, p, dev.qt, dev.dd, dmask, mask_lo, mask_hi, dout, ldOut};
+        RMG_CUDA(cudaStreamWaitEvent(st, cd->ready, 0));
+        LmArgs a{dY, V, ldY, n, p, cd->qt, cd->dd, dmask, mask_lo, mask_hi, dout, ldOut};
         RMG_CUDA(launch_lm_fit(a, plan_from_env(device), scr, st, &info));
         g_launch_count += info.launches;
         g_last_fit_variant = info.used_tma ? 1 : 2;
     }
 cleanup:
-    dev.release(st);
     scr.release(st);
     return rc;
 }
@@ -209,9 +275,13 @@ int rmg_lm_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *X, 
 {
     int rc = check_fit_args(Y, V, ldY, n, X, p, out, ldOut, err, errlen);
     if (rc) return rc;
-    Design D;
-    if ((rc = factor_or_fail(X, n, p, D, err, errlen))) return rc;
+    {   // the reference fails on a singular design before it touches any voxel; so do we, GPU or not
+        Design probe;
+        if (rmg_device_count() <= 0 && (rc = factor_or_fail(X, n, p, probe, err, errlen))) return rc;
+    }
     if ((rc = select_device(device, err, errlen))) return rc;
+    std::shared_ptr<CachedDesign> cd = design_cache_get(device, X, n, p, rc, err, errlen);
+    if (!cd) return rc;
     g_last_kernel_ms = 0.0;
     if (V == 0) return RMG_OK;
 
@@ -228,7 +298,6 @@ int rmg_lm_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *X, 
     cudaStream_t st[3] = {nullptr, nullptr, nullptr};
     double *dY[3] = {nullptr, nullptr, nullptr}, *dO[3] = {nullptr, nullptr, nullptr}, *dM[3] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> ev0(nchunks, nullptr), ev1(nchunks, nullptr);
-    DeviceDesign dev;
     LmScratch scr[3];
     const LmPlan plan = plan_from_env(device);
     int64_t launches = 0;
@@ -239,8 +308,7 @@ int rmg_lm_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *X, 
             RMG_CUDA(cudaMalloc(&dO[b], (size_t)ldc * ncol * sizeof(double)));
             if (mask) RMG_CUDA(cudaMalloc(&dM[b], (size_t)ldc * sizeof(double)));
         }
-        RMG_CUDA(dev.upload(D, st[0]));
-        RMG_CUDA(cudaStreamSynchronize(st[0]));
+        for (int b = 0; b < NB; ++b) RMG_CUDA(cudaStreamWaitEvent(st[b], cd->ready, 0));
         for (int64_t c = 0; c < nchunks; ++c) {
             const int b = (int)(c % NB);
             const int64_t v0 = c * CV, cv = std::min(CV, V - v0);
@@ -249,7 +317,7 @@ int rmg_lm_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *X, 
             RMG_CUDA(cudaMemcpy2DAsync(dY[b], (size_t)ldc * 8, Y + v0, (size_t)ldY * 8, (size_t)cv * 8, (size_t)n,
                                        cudaMemcpyHostToDevice, st[b]));
             if (mask) RMG_CUDA(cudaMemcpyAsync(dM[b], mask + v0, (size_t)cv * 8, cudaMemcpyHostToDevice, st[b]));
-            LmArgs a{dY[b], cv, ldc, n, p, dev.qt, dev.dd, mask ? dM[b] : nullptr, mask_lo, mask_hi, dO[b], ldc};
+            LmArgs a{dY[b], cv, ldc, n, p, cd->qt, cd->dd, mask ? dM[b] : nullptr, mask_lo, mask_hi, dO[b], ldc};
             LmLaunchInfo info;
             RMG_CUDA(cudaEventRecord(ev0[c], st[b]));
             RMG_CUDA(launch_lm_fit(a, plan, scr[b], st[b], &info));
@@ -272,7 +340,6 @@ cleanup:
     for (int b = 0; b < 3; ++b) {
         if (st[b]) cudaStreamSynchronize(st[b]);
     }
-    dev.release(nullptr);
     for (int b = 0; b < 3; ++b) {
         scr[b].release(st[b]);
         if (st[b]) cudaStreamSynchronize(st[b]);

@@ -119,6 +119,43 @@ __device__ __forceinline__ void finish_voxel(const VoxelSums<KP> &v, double rss,
     }
 }
 
+// Two adjacent voxels (v, v+1) at once with 16-byte stores: one st.global.v2.f64 per result
+// column instead of two half-used sectors.  `ok*` false -> that row is +0.0 (outside the mask).
+// Requires out + v 16-byte aligned and ld even (checked on the host).
+template <int KP>
+__device__ __forceinline__ void finish_pair(const VoxelSums<KP> &a, double rssa, double mssa, bool oka,
+                                            const VoxelSums<KP> &b, double rssb, double mssb, bool okb,
+                                            const SmemDesign<KP> &d, double *__restrict__ out, int64_t ld)
+{
+    const int p = d.p;
+    auto put = [&](int c, double x, double y) {
+        *reinterpret_cast<double2 *>(out + (int64_t)c * ld) = make_double2(oka ? x : 0.0, okb ? y : 0.0);
+    };
+    const double rva = rssa / d.rdf, rvb = rssb / d.rdf;
+    put(0, (mssa / d.pm1) / rva, (mssb / d.pm1) / rvb);
+    put(1, mssa / (mssa + rssa), mssb / (mssb + rssb));
+    put(2 * p + 2, d.mhalf_n * (d.loglik_c + log(rssa)), d.mhalf_n * (d.loglik_c + log(rssb)));
+    double ea[KP], eb[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        ea[k] = fma(a.y0, d.q1[k], a.e[k]);
+        eb[k] = fma(b.y0, d.q1[k], b.e[k]);
+    }
+#pragma unroll
+    for (int i = 0; i < KP; ++i) {
+        if (i < p) {
+            double ba = 0.0, bb = 0.0;
+#pragma unroll
+            for (int j = i; j < KP; ++j) {
+                ba = fma(d.Rinv[i * KP + j], ea[j], ba);
+                bb = fma(d.Rinv[i * KP + j], eb[j], bb);
+            }
+            put(2 + i, ba, bb);
+            put(2 + p + i, ba / sqrt(d.ct[i] * rva), bb / sqrt(d.ct[i] * rvb));
+        }
+    }
+}
+
 template <int KP>
 __device__ __forceinline__ void zero_row(int p, double *__restrict__ out, int64_t ld)
 {

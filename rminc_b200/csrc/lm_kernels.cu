@@ -78,25 +78,31 @@ __device__ __forceinline__ void consume_box(const double *__restrict__ tile, con
 // min(TV,256) doubles (a TMA box dimension is at most 256 elements) -- and the matching NJ
 // rows of Q' (a 1-D bulk copy), so nothing of size n lives in shared memory and any n fits.
 // Shared memory: [ring: STAGES x (NJ x TV + NJ x KP) doubles][SmemDesign][mbarriers]
-template <int KP, int CW, int NJ, int STAGES, int MINB>
+// QSTREAM = false keeps the whole Q' (n x KP) resident in shared memory instead (loaded once per
+// CTA); it needs n*KP*8 bytes of shared memory but issues no per-stage Q copy.
+template <int KP, int CW, int NJ, int STAGES, int MINB, bool QSTREAM>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB)
 lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsigned char *__restrict__ flags)
 {
     constexpr int TV = CW * 64;
     constexpr int BOXW = TV < 256 ? TV : 256;
     constexpr int NBOX = TV / BOXW;
-    constexpr int STAGE_D = NJ * TV + NJ * KP + ((NJ * KP) & 1);   // doubles per stage, 16-byte multiple
+    constexpr int STAGE_D = NJ * TV + (QSTREAM ? (NJ * KP + 15) / 16 * 16 : 0);  // doubles per stage; TMA dst needs 128 B
     static_assert(TV % BOXW == 0 && NJ % 2 == 0, "tile must be whole TMA boxes; Q rows must copy in 16-byte units");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *ring = reinterpret_cast<double *>(smem_raw);
-    SmemDesign<KP> &sd = *reinterpret_cast<SmemDesign<KP> *>(ring + (size_t)STAGES * STAGE_D);
+    const int n = a.n;
+    const int nit = (n + NJ - 1) / NJ;
+    double *sQ = ring + (size_t)STAGES * STAGE_D;                    // resident Q' (only when !QSTREAM)
+    SmemDesign<KP> &sd = *reinterpret_cast<SmemDesign<KP> *>(sQ + (QSTREAM ? 0 : (size_t)nit * NJ * KP));
     uint64_t *full = reinterpret_cast<uint64_t *>(&sd + 1);
     uint64_t *empty = full + STAGES;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const int n = a.n;
 
+    if (!QSTREAM)   // Qt is zero-padded to a multiple of 16 rows (capi.cu: make_qt), nit*NJ <= that
+        for (int i = tid; i < nit * NJ * KP; i += blockDim.x) sQ[i] = a.Qt[i];
     load_design_to_smem<KP>(sd, a.design, tid, blockDim.x);
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -108,8 +114,7 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
     __syncthreads();
 
     const int64_t ntiles = (a.V + TV - 1) / TV;
-    const int nit = (n + NJ - 1) / NJ;
-    constexpr uint32_t kStageBytes = (NJ * TV + NJ * KP) * sizeof(double);
+    constexpr uint32_t kStageBytes = (NJ * TV + (QSTREAM ? NJ * KP : 0)) * sizeof(double);
 
     if (warp == CW) {
         // ===== producer: one elected lane walks the same tile sequence as the consumers
@@ -125,8 +130,8 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
 #pragma unroll
                     for (int b = 0; b < NBOX; ++b)
                         tma_load_2d(dst + (size_t)b * NJ * BOXW, &ymap, &full[stage], c0 + b * BOXW, it * NJ);
-                    // Qt is padded with zero rows to a multiple of 16 subjects (capi.cu: make_qt)
-                    bulk_load_1d(dst + NJ * TV, a.Qt + (size_t)it * NJ * KP, NJ * KP * sizeof(double), &full[stage]);
+                    if (QSTREAM)
+                        bulk_load_1d(dst + NJ * TV, a.Qt + (size_t)it * NJ * KP, NJ * KP * sizeof(double), &full[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -165,7 +170,7 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
                 s0.y0 = f.x;
                 s1.y0 = f.y;
             }
-            const double *q = st + NJ * TV;
+            const double *q = QSTREAM ? st + NJ * TV : sQ + (size_t)it * NJ * KP;
             // rows >= n of the last box are TMA zero-fill: their Q rows are zero, but their
             // (0 - y0)^2 must not enter yy, so the last box runs the guarded variant.
             if (it + 1 < nit) consume_box<KP, NJ, BOXW, false>(tile, q, s0, s1, NJ);
@@ -175,22 +180,20 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         // ---- fused epilogue
-        if (in0) {
-            if (act0) {
-                double rss = s0.yy - sumsq_e(s0), mss = mss_from_e(s0, sd);
-                if (rss <= kExactThreshold * s0.yy && s0.yy > 0.0) exact_pass<KP>(s0, a.Y + v, a.ldY, n, a.Qt, rss, mss);
-                finish_voxel<KP>(s0, rss, mss, sd, o, a.ldOut);
-            } else {
-                zero_row<KP>(sd.p, o, a.ldOut);
+        double rss0 = s0.yy - sumsq_e(s0), mss0 = mss_from_e(s0, sd);
+        double rss1 = s1.yy - sumsq_e(s1), mss1 = mss_from_e(s1, sd);
+        if (act0 && rss0 <= kExactThreshold * s0.yy && s0.yy > 0.0) exact_pass<KP>(s0, a.Y + v, a.ldY, n, a.Qt, rss0, mss0);
+        if (act1 && rss1 <= kExactThreshold * s1.yy && s1.yy > 0.0) exact_pass<KP>(s1, a.Y + v + 1, a.ldY, n, a.Qt, rss1, mss1);
+        if (in1 && a.out_vec2) {
+            finish_pair<KP>(s0, rss0, mss0, act0, s1, rss1, mss1, act1, sd, o, a.ldOut);
+        } else {
+            if (in0) {
+                if (act0) finish_voxel<KP>(s0, rss0, mss0, sd, o, a.ldOut);
+                else zero_row<KP>(sd.p, o, a.ldOut);
             }
-        }
-        if (in1) {
-            if (act1) {
-                double rss = s1.yy - sumsq_e(s1), mss = mss_from_e(s1, sd);
-                if (rss <= kExactThreshold * s1.yy && s1.yy > 0.0) exact_pass<KP>(s1, a.Y + v + 1, a.ldY, n, a.Qt, rss, mss);
-                finish_voxel<KP>(s1, rss, mss, sd, o + 1, a.ldOut);
-            } else {
-                zero_row<KP>(sd.p, o + 1, a.ldOut);
+            if (in1) {
+                if (act1) finish_voxel<KP>(s1, rss1, mss1, sd, o + 1, a.ldOut);
+                else zero_row<KP>(sd.p, o + 1, a.ldOut);
             }
         }
     }
@@ -313,18 +316,26 @@ lm_fit_ldg_kernel(LmArgs a, int JT)
         }
     }
 
+    double rss[VPT], mss[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        rss[i] = sum[i].yy - sumsq_e(sum[i]);
+        mss[i] = mss_from_e(sum[i], sd);
+        if (act[i] && rss[i] <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0)
+            exact_pass<KP>(sum[i], a.Y + v + i, a.ldY, n, a.Qt, rss[i], mss[i]);
+    }
+    if constexpr (VPT == 2) {
+        if (a.out_vec2 && in[1]) {
+            finish_pair<KP>(sum[0], rss[0], mss[0], act[0], sum[1], rss[1], mss[1], act[1], sd, a.out + v, a.ldOut);
+            return;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
         if (!in[i]) continue;
         double *o = a.out + v + i;
-        if (!act[i]) {
-            zero_row<KP>(sd.p, o, a.ldOut);
-            continue;
-        }
-        double rss = sum[i].yy - sumsq_e(sum[i]), mss = mss_from_e(sum[i], sd);
-        if (rss <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0)
-            exact_pass<KP>(sum[i], a.Y + v + i, a.ldY, n, a.Qt, rss, mss);
-        finish_voxel<KP>(sum[i], rss, mss, sd, o, a.ldOut);
+        if (act[i]) finish_voxel<KP>(sum[i], rss[i], mss[i], sd, o, a.ldOut);
+        else zero_row<KP>(sd.p, o, a.ldOut);
     }
 }
 
@@ -357,13 +368,15 @@ int round_up_kp(int p)
     return 32;
 }
 
-template <int KP, int CW, int NJ, int STAGES>
-constexpr size_t tma_smem_bytes()
+template <int KP, int CW, int NJ, int STAGES, bool QSTREAM>
+size_t tma_smem_bytes(int n)
 {
-    return (size_t)STAGES * (NJ * CW * 64 + NJ * KP + ((NJ * KP) & 1)) * 8 + sizeof(SmemDesign<KP>) + 2 * STAGES * 8 + 128;
+    const size_t stage = NJ * CW * 64 + (QSTREAM ? (NJ * KP + 15) / 16 * 16 : 0);
+    const size_t qres = QSTREAM ? 0 : (size_t)((n + NJ - 1) / NJ) * NJ * KP;
+    return (STAGES * stage + qres) * 8 + sizeof(SmemDesign<KP>) + 2 * STAGES * 8 + 128;
 }
 
-template <int KP, int CW, int NJ, int STAGES, int MINB>
+template <int KP, int CW, int NJ, int STAGES, int MINB, bool QSTREAM>
 cudaError_t launch_tma_cfg(const LmArgs &a, const unsigned char *flags, int sm_count, cudaStream_t st)
 {
     constexpr int TV = CW * 64;
@@ -379,9 +392,9 @@ cudaError_t launch_tma_cfg(const LmArgs &a, const unsigned char *flags, int sm_c
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    constexpr size_t smem = tma_smem_bytes<KP, CW, NJ, STAGES>();
-    static_assert(smem * MINB <= 227 * 1024, "tile shape does not fit the requested CTAs per SM");
-    auto kern = lm_fit_tma_kernel<KP, CW, NJ, STAGES, MINB>;
+    const size_t smem = tma_smem_bytes<KP, CW, NJ, STAGES, QSTREAM>(a.n);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    auto kern = lm_fit_tma_kernel<KP, CW, NJ, STAGES, MINB, QSTREAM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t ntiles = (a.V + TV - 1) / TV;
@@ -397,7 +410,9 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0) && (a.ldY % 2 == 0);
     // TMA needs a 16-byte aligned base and row pitch; int32 tile coordinates.
     const bool tma_ok = aligned16 && a.V <= 0x7fffffffLL && KP <= 16;
-    bool use_tma = tma_ok && plan.variant != LmVariant::Ldg;
+    // With a mask the direct-load kernel skips at warp (64-voxel) granularity where the TMA ring
+    // skips whole 256-voxel tiles: measured 2.72 ms vs 3.02 ms on config 2 with the 38 % ellipsoid.
+    bool use_tma = tma_ok && (plan.variant == LmVariant::Tma || (plan.variant == LmVariant::Auto && !a.mask));
     if (use_tma) {
         // Tile shapes (consumer warps, subjects per stage, ring depth, CTAs per SM):
         //   wide   4 x 64 = 256-voxel tiles, 4 CTAs/SM   -- large V (config 2: 4.5 ms, 98 % of the copy peak)
@@ -416,31 +431,37 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
             flags = scr.flags;
         }
         cudaError_t e;
+        // Q' resident in shared memory when 4 CTAs/SM still fit (n*KP*8 <= 24 KiB), else streamed
+        const bool qres = plan.q_stream == 0 || (plan.q_stream < 0 && (size_t)a.n * KP * 8 <= 24 * 1024);
         if constexpr (KP <= 8) {
-            switch (cfg) {
-            case 0: e = launch_tma_cfg<KP, 8, 8, 4, 1>(a, flags, plan.sm_count, st); break;
-            case 5: e = launch_tma_cfg<KP, 2, 4, 4, 8>(a, flags, plan.sm_count, st); break;
-            default: e = launch_tma_cfg<KP, 4, 4, 4, 4>(a, flags, plan.sm_count, st); break;
+            switch (cfg * 2 + (qres ? 0 : 1)) {
+            case 0: e = launch_tma_cfg<KP, 8, 8, 4, 1, false>(a, flags, plan.sm_count, st); break;
+            case 1: e = launch_tma_cfg<KP, 8, 8, 4, 1, true>(a, flags, plan.sm_count, st); break;
+            case 10: e = launch_tma_cfg<KP, 2, 4, 4, 8, false>(a, flags, plan.sm_count, st); break;
+            case 11: e = launch_tma_cfg<KP, 2, 4, 4, 8, true>(a, flags, plan.sm_count, st); break;
+            case 8: e = launch_tma_cfg<KP, 4, 4, 4, 4, false>(a, flags, plan.sm_count, st); break;
+            default: e = launch_tma_cfg<KP, 4, 4, 4, 4, true>(a, flags, plan.sm_count, st); break;
             }
         } else {
             // wide designs: more accumulators per thread -> fewer CTAs per SM
-            e = cfg == 5 ? launch_tma_cfg<KP, 2, 4, 4, 4>(a, flags, plan.sm_count, st)
-                         : launch_tma_cfg<KP, 4, 4, 4, 2>(a, flags, plan.sm_count, st);
+            e = cfg == 5 ? launch_tma_cfg<KP, 2, 4, 4, 4, true>(a, flags, plan.sm_count, st)
+                         : launch_tma_cfg<KP, 4, 4, 4, 2, true>(a, flags, plan.sm_count, st);
         }
         if (info) { info->launches++; info->used_tma = 1; info->tma_cfg = cfg; }
         return e;
     }
     if (plan.variant == LmVariant::Tma) return cudaErrorInvalidValue;  // asked for TMA on a layout it cannot describe
-    // ---- LDG path: pick voxels/thread, split factor and Q tile
+    // ---- LDG path: pick voxels/thread and the split factor
     const bool vec2 = aligned16 && (a.V % 2 == 0) && (a.ldOut % 2 == 0) && KP <= 16;
     int S = plan.split;
     if (S <= 0) {
         // enough threads for ~2 waves of 1024 threads/SM; split the subject axis otherwise
         S = 1;
         const int64_t want = (int64_t)plan.sm_count * 2048;
-        while (S < 8 && (a.V / (vec2 ? 2 : 1)) * S < want && a.n / (S * 2) >= 64) S *= 2;
+        while (S < 32 && (a.V / (vec2 ? 2 : 1)) * S < want && a.n / (S * 2) >= 32) S *= 2;
     }
-    const int TX = S >= 4 ? 32 : (S == 2 ? 64 : 128);
+    if (S > 32) S = 32;
+    const int TX = S == 1 ? 128 : (256 / S < 8 ? 8 : 256 / S);
     const int VPT = vec2 ? 2 : 1;
     const int span = (a.n + S - 1) / S;
     int JT = span;
@@ -453,29 +474,29 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
     const int64_t blocks = (a.V + per_block - 1) / per_block;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
     dim3 bd(TX, S);
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)blocks, bd, smem, st>>>(a, JT);
+        return cudaGetLastError();
+    };
     cudaError_t e;
-    if (VPT == 2) {
-        auto kern = lm_fit_ldg_kernel<KP, (KP <= 16 ? 2 : 1)>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kern<<<(unsigned)blocks, bd, smem, st>>>(a, JT);
-    } else {
-        auto kern = lm_fit_ldg_kernel<KP, 1>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kern<<<(unsigned)blocks, bd, smem, st>>>(a, JT);
-    }
+    constexpr int V2 = KP <= 16 ? 2 : 1;   // never instantiate the 2-voxel kernel for very wide designs
+    if (VPT == 2) e = go(lm_fit_ldg_kernel<KP, V2>);
+    else e = go(lm_fit_ldg_kernel<KP, 1>);
     if (info) { info->launches++; info->used_tma = 0; info->split = S; }
-    return cudaGetLastError();
+    return e;
 }
 
 }  // namespace
 
 int lm_padded_p(int p) { return round_up_kp(p); }
 
-cudaError_t launch_lm_fit(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
+cudaError_t launch_lm_fit(const LmArgs &a_in, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
 {
-    if (a.V <= 0) return cudaSuccess;
+    if (a_in.V <= 0) return cudaSuccess;
+    LmArgs a = a_in;
+    a.out_vec2 = ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && a.ldOut % 2 == 0) ? 1 : 0;
     switch (round_up_kp(a.p)) {
 #define RMG_CASE(K) case K: return launch_kp<K>(a, plan, scr, st, info);
         RMG_CASE(1) RMG_CASE(2) RMG_CASE(3) RMG_CASE(4) RMG_CASE(5) RMG_CASE(6) RMG_CASE(7) RMG_CASE(8)

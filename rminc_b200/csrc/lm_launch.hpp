@@ -19,6 +19,7 @@ struct LmArgs {
     double mask_lo, mask_hi;
     double *out;
     int64_t ldOut;
+    int out_vec2 = 0;          // set by launch_lm_fit: out is 16-byte aligned with an even ld
 };
 
 enum class LmVariant { Auto = 0, Tma = 1, Ldg = 2 };
@@ -28,6 +29,7 @@ struct LmPlan {
     int split = 0;       // LDG path: slices of the subject axis (0 = choose)
     int sm_count = 148;
     int tma_cfg = -1;    // TMA path: tile-shape variant (-1 = choose by V; see lm_kernels.cu)
+    int q_stream = -1;   // TMA path: 1 = stream Q' with Y, 0 = keep Q' resident in smem, -1 = choose
 };
 
 struct LmLaunchInfo {
