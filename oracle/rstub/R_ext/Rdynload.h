@@ -1,0 +1,10 @@
+/* oracle/rstub/R_ext/Rdynload.h -- TEST INFRASTRUCTURE (declarations only, for a syntax check of
+ * rminc_b200/csrc/rshim.c; see oracle/rstub/R.h). */
+#ifndef RSTUB_RDYNLOAD_H
+#define RSTUB_RDYNLOAD_H
+typedef void *(*DL_FUNC)(void);
+typedef struct { const char *name; DL_FUNC fun; int numArgs; } R_CallMethodDef;
+typedef struct rstub_dllinfo DllInfo;
+int R_registerRoutines(DllInfo *info, const void *c, const R_CallMethodDef *call, const void *f, const void *e);
+int R_useDynamicSymbols(DllInfo *info, int value);
+#endif

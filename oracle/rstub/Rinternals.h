@@ -32,6 +32,18 @@ int Rf_isNull(SEXP s);
 SEXP STRING_ELT(SEXP s, R_xlen_t i);
 const char *CHAR(SEXP s);
 SEXP Rf_install(const char *name);
+int Rf_isReal(SEXP s);
+int Rf_isInteger(SEXP s);
+int Rf_asInteger(SEXP s);
+int Rf_asLogical(SEXP s);
+double Rf_asReal(SEXP s);
+SEXP Rf_GetOption1(SEXP tag);
+R_xlen_t XLENGTH(SEXP s);
+char *R_alloc(size_t n, int size);
+#ifndef FALSE
+#define FALSE 0
+#define TRUE 1
+#endif
 SEXP Rf_lang2(SEXP a, SEXP b);
 SEXP Rf_eval(SEXP expr, SEXP rho);
 void Rf_defineVar(SEXP sym, SEXP val, SEXP rho);

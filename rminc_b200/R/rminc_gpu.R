@@ -1,0 +1,77 @@
+# rminc_gpu.R -- R wrappers that make the GPU path a drop-in inside RMINC.
+#
+# Source this after library(RMINC) (or add it to RMINC's R/ directory).  It re-defines the three
+# call sites of the native per-voxel OLS loop and nothing else; formula handling, attributes,
+# classes and every downstream consumer (mincFDR, AIC/BIC, mincWriteVolume, ...) are RMINC's own.
+#
+#   mincLm_c_wrapper   R/minc_voxel_statistics.R:695-712   -> .Call("rmincgpu_lm")
+#   vertex_lm_loop     call sites R/minc_vertex_statistics.R:408-414, R/minc_anatomy.R:1144-1150
+#                                                           -> .Call("rmincgpu_vertex_lm_loop")
+#   mincRandomize_core R/minc_voxel_statistics.R:1441-1531 -> .Call("rmincgpu_randomize")
+#
+# options(RMINC_GPU_N = k) shards voxels over k GPUs of the box (default 1).
+
+rmincgpu_n <- function(parallel = NULL) {
+  if (!is.null(parallel)) return(as.integer(parallel[2]))
+  as.integer(getOption("RMINC_GPU_N", 1L))
+}
+
+# Stage the n volumes as the columns of a V x n double matrix, in file dimension order -- the
+# same element order minc2_model uses for its output rows (src/modelling_functions.c:1059).
+rmincgpu_stage <- function(filenames) {
+  first <- mincGetVolume(filenames[1])
+  Y <- matrix(0, nrow = length(first), ncol = length(filenames))
+  Y[, 1] <- first
+  for (j in seq_along(filenames)[-1]) Y[, j] <- mincGetVolume(filenames[j])
+  Y
+}
+
+# Replacement for RMINC:::mincLm_c_wrapper.  `mask` may be a file name or NULL.
+mincLm_c_wrapper <- function(plm, mask, mask_min, mask_max, n_gpus = rmincgpu_n()) {
+  if (!is.logical(plm$data.matrix.right))
+    stop("voxel-wise covariates are not on the GPU path; use the CPU RMINC for this model")
+  Y <- rmincgpu_stage(as.character(plm$data.matrix.left))
+  m <- if (is.null(mask)) NULL else as.double(mincGetVolume(mask))
+  .Call("rmincgpu_lm", Y, as.matrix(plm$mmatrix), m, as.double(mask_min), as.double(mask_max),
+        as.integer(n_gpus), PACKAGE = "rmincgpu")
+}
+
+# mincLm(parallel = c("local", N)) on the GPU path means N GPUs, not N forked processes: a CUDA
+# context must never be forked.  The sequential branch of mincLm (R/minc_voxel_statistics.R:841-847)
+# is reused with n_gpus = N; the masked rows come back as 0 in every column, as the reference's
+# parallel branch produces (:898-905).
+mincLm_gpu <- function(formula, data = NULL, subset = NULL, mask = NULL, maskval = NULL, parallel = NULL) {
+  old <- options(RMINC_GPU_N = rmincgpu_n(parallel)); on.exit(options(old))
+  cl <- match.call(); cl[[1]] <- as.name("mincLm"); cl$parallel <- NULL
+  eval(cl, parent.frame())
+}
+
+# vertexLm / anatLm: only the routine name changes.
+vertex_lm_loop_gpu <- function(data.matrix.left, data.matrix.right, mmatrix)
+  .Call("rmincgpu_vertex_lm_loop", data.matrix.left, data.matrix.right, mmatrix, PACKAGE = "rmincgpu")
+
+# Replacement for RMINC:::mincRandomize_core (identity post_proc only).  The permutation indices
+# are drawn here with R's own sample(), so a seed gives the same null distribution as the
+# reference; the refits happen on the GPU with Y resident instead of update(lmod, data = shuf).
+mincRandomize_core <- function(x, R = 500, replace = FALSE, parallel = NULL,
+                               columns = grep("tvalue-", colnames(x)),
+                               alternative = c("two.sided", "greater"), post_proc = identity, ...) {
+  alternative <- match.arg(alternative)
+  if (!identical(post_proc, identity)) stop("post_proc (TFCE) is not on the GPU path yet")
+  lmod <- x
+  n <- nrow(attr(lmod, "data"))
+  idx <- vapply(seq_len(R), function(i) sample(seq_len(n), replace = replace), integer(n))
+  Y <- rmincgpu_stage(attr(lmod, "filenames"))
+  cl <- attr(lmod, "call")
+  mask <- eval(cl$mask, parent.frame()); maskval <- eval(cl$maskval, parent.frame())
+  m <- if (is.null(mask)) NULL else as.double(mincGetVolume(mask))
+  lo <- if (is.null(maskval)) 1 else maskval
+  hi <- if (is.null(maskval)) 99999999 else maskval
+  # all predictor columns move together (:1457-1474): the permuted design is the model matrix
+  # with its rows permuted; a resample that empties a factor level makes the refit singular and
+  # the call fails, as the reference's rbind of ragged rows would.
+  dist <- .Call("rmincgpu_randomize", Y, attr(lmod, "model"), m, as.double(lo), as.double(hi), idx,
+                as.integer(columns), alternative == "two.sided", rmincgpu_n(parallel), PACKAGE = "rmincgpu")
+  colnames(dist) <- colnames(lmod)[columns]
+  dist
+}

@@ -1,0 +1,281 @@
+"""Host-side mirror of RMINC's R interface for the voxel-wise OLS path.
+
+R is not available in this image, so the layer RMINC implements in R
+(R/minc_voxel_statistics.R, R/minc_vertex_statistics.R, R/minc_anatomy.R) is mirrored here in
+Python with the same names, argument meaning, result layout, attributes and error behaviour,
+so the parity tests read like the reference's own testthat files.  The R-side binding a
+maintainer would add is in rminc_b200/R/ and INTEGRATION.md.
+
+    mincLm(formula, data, subset, mask, maskval, parallel)   R/minc_voxel_statistics.R:751-950
+    vertexLm(formula, data, subset, column)                  R/minc_vertex_statistics.R:365-446
+    anatLm(formula, data, anat, subset, weights)             R/minc_anatomy.R:1048-1192
+    mincRandomize(x, R, alternative, replace, parallel, columns)   :1326-1378, :1441-1531
+    thresholds(x, probs)                                     :1577-1581
+
+Everything numerical goes through the C ABI (rminc_b200.core); there is no CPU path.
+MINC I/O (libminc) is outside the hot path: volumes are staged by a `reader` callable
+(default: numpy .npy files or in-memory arrays), exactly where mincTable / mincGetVolume sit in
+the reference (R/minc_interface.R:1031-1077).
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import core
+from .formula import FormulaError, model_matrix, split_formula
+
+
+# ----------------------------------------------------------------------------- result objects
+class MincMatrix(np.ndarray):
+    """A numeric matrix with R-style attributes: `colnames`, `rownames`, `attrs`, `r_class`.
+
+    Mirrors the objects mincLm / vertexLm / anatLm return: a V x (2p+3) matrix of class
+    c("mincLm","mincMultiDim","matrix") etc. with attributes likeVolume, filenames, model,
+    data, call, stat-type and df (R/minc_voxel_statistics.R:908-944)."""
+
+    def __new__(cls, array, colnames=None, rownames=None, attrs=None, r_class=()):
+        obj = np.asarray(array).view(cls)
+        obj.colnames = list(colnames) if colnames is not None else None
+        obj.rownames = list(rownames) if rownames is not None else None
+        obj.attrs = dict(attrs or {})
+        obj.r_class = tuple(r_class)
+        return obj
+
+    def __array_finalize__(self, obj):
+        if obj is None:
+            return
+        self.colnames = getattr(obj, "colnames", None)
+        self.rownames = getattr(obj, "rownames", None)
+        self.attrs = getattr(obj, "attrs", {})
+        self.r_class = getattr(obj, "r_class", ())
+
+    def col(self, name: str) -> np.ndarray:
+        return np.asarray(self)[:, self.colnames.index(name)]
+
+
+def _stat_type(p: int) -> List[str]:
+    return ["F", "R-squared"] + ["beta"] * p + ["t"] * p + ["logLik"]      # :921-927
+
+
+def _df_list(n: int, p: int) -> list:
+    fdf1, fdf2 = p - 1, n - p                                              # :929-935
+    return [[fdf1, fdf2]] + [fdf2] * p
+
+
+def _colnames(rows: Sequence[str]) -> List[str]:
+    return ["F-statistic", "R-squared"] + [f"beta-{r}" for r in rows] + [f"tvalue-{r}" for r in rows] + ["logLik"]
+
+
+def _subset_rows(data, subset):
+    n = len(data)
+    if subset is None:
+        return list(range(n))
+    s = np.asarray(subset)
+    if s.dtype == bool:
+        if len(s) != n:
+            raise ValueError("logical subset must have one entry per row of data")
+        return [i for i in range(n) if s[i]]
+    return [int(i) for i in s]
+
+
+def _column(data, name, rows):
+    c = data[name]
+    return [c.iloc[i] if hasattr(c, "iloc") else c[i] for i in rows]
+
+
+# ----------------------------------------------------------------------------- staging (I/O side)
+def default_reader(item) -> np.ndarray:
+    """Volume loader used where the reference calls mincGetVolume: in-memory arrays pass through,
+    '.npy' paths are np.load'ed.  Returns the voxels flattened in file (C) order."""
+    if isinstance(item, np.ndarray):
+        return np.asarray(item, dtype=np.float64).reshape(-1)
+    if isinstance(item, (str, os.PathLike)):
+        path = os.fspath(item)
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"Error opening input file: {path}.")          # minc2_model :809
+        if path.endswith(".npy"):
+            return np.load(path).astype(np.float64, copy=False).reshape(-1)
+        raise ValueError(f"no reader for '{path}': pass reader= (MINC I/O is outside this package)")
+    raise TypeError(f"cannot stage a volume from {type(item).__name__}")
+
+
+def mincTable(filenames: Sequence, mask=None, reader: Callable = default_reader) -> np.ndarray:
+    """V x n matrix, one column per file (R/minc_interface.R:1031-1077), Fortran order."""
+    first = reader(filenames[0])
+    Y = np.empty((first.shape[0], len(filenames)), order="F")
+    Y[:, 0] = first
+    for j, f in enumerate(filenames[1:], start=1):
+        v = reader(f)
+        if v.shape[0] != first.shape[0]:
+            raise ValueError("all volumes must have the same number of voxels")
+        Y[:, j] = v
+    return Y
+
+
+def vertexTable(filenames: Sequence, column: int = 1) -> np.ndarray:
+    """V x n matrix from one whitespace/comma separated text file per subject, `column` 1-based
+    (R/minc_interface.R:1134-1150)."""
+    cols = []
+    for f in filenames:
+        if isinstance(f, np.ndarray):
+            a = np.asarray(f, dtype=np.float64)
+            cols.append(a if a.ndim == 1 else a[:, column - 1])
+            continue
+        if not os.path.exists(f):
+            raise FileNotFoundError(f"Error opening input file: {f}.")
+        a = np.loadtxt(f, delimiter="," if str(f).endswith((".csv", ".csv.gz")) else None, ndmin=2)
+        cols.append(a[:, column - 1])
+    if len({len(c) for c in cols}) != 1:
+        raise ValueError("all vertex files must have the same number of vertices")
+    return np.asfortranarray(np.column_stack(cols))
+
+
+def _stage_mask(mask, V, reader):
+    if mask is None:
+        return None
+    m = reader(mask) if not isinstance(mask, np.ndarray) else np.asarray(mask, dtype=np.float64).reshape(-1)
+    if m.shape[0] != V:
+        raise ValueError("Mask Volume input volume dimension mismatch.")          # :837
+    return m
+
+
+# ----------------------------------------------------------------------------- mincLm
+def mincLm(formula: str, data, subset=None, mask=None, maskval=None, parallel=None,
+           reader: Callable = default_reader, device: int = 0) -> MincMatrix:
+    """Linear model at every voxel.  `data[lhs]` holds one volume (file name or array) per subject.
+
+    parallel: None (one GPU) or ("local", N) -> N GPUs of this box, contiguous voxel shards
+    (replaces create_parallel_mask + mclapply, R/minc_voxel_statistics.R:848-906).  Unlike the
+    reference's parallel path, maskval is honoured on both paths."""
+    lhs, rhs = split_formula(formula)
+    rows = _subset_rows(data, subset)
+    X, names, _ = model_matrix(rhs, data, rows)
+    filenames = _column(data, lhs, rows)
+    Y = mincTable(filenames, reader=reader)
+    V, n = Y.shape
+    m = _stage_mask(mask, V, reader)
+    lo, hi = core.mask_range(maskval)                                            # :781-787
+    n_gpus = None
+    if parallel is not None:
+        n_gpus = int(parallel[1])
+    out = core.lm_fit(Y, X, mask=m, mask_lo=lo, mask_hi=hi, device=device, n_gpus=n_gpus)
+    p = X.shape[1]
+    attrs = {
+        "likeVolume": filenames[0], "filenames": list(filenames), "model": X, "data": data,
+        "call": dict(fn="mincLm", formula=formula, subset=subset, mask=mask, maskval=maskval, parallel=parallel),
+        "stat-type": _stat_type(p), "df": _df_list(n, p), "model-colnames": names,
+        "_Y": Y, "_mask": m, "_mask_range": (lo, hi), "_rows": rows, "_rhs": rhs, "_lhs": lhs,
+    }
+    return MincMatrix(out, colnames=_colnames(names), attrs=attrs, r_class=("mincLm", "mincMultiDim", "matrix"))
+
+
+# ----------------------------------------------------------------------------- vertexLm / anatLm
+def vertexLm(formula: str, data, subset=None, column: int = 1, device: int = 0) -> MincMatrix:
+    lhs, rhs = split_formula(formula)
+    if "$" in rhs:
+        raise FormulaError("$ Not Permitted in Formula")                        # minc_vertex_statistics.R:380
+    rows = _subset_rows(data, subset)
+    X, names, _ = model_matrix(rhs, data, rows)
+    filenames = _column(data, lhs, rows)
+    Y = vertexTable(filenames, column=column)
+    out = core.vertex_lm(Y, X, device=device)
+    n, p = X.shape
+    attrs = {"likeVolume": filenames[0], "model": X, "filenames": list(filenames), "stat-type": _stat_type(p),
+             "data": data, "call": dict(fn="vertexLm", formula=formula, subset=subset, column=column),
+             "df": _df_list(n, p), "model-colnames": names, "_Y": Y, "_mask": None,
+             "_mask_range": (core.DEFAULT_MASK_LO, core.DEFAULT_MASK_HI), "_rows": rows, "_rhs": rhs, "_lhs": lhs}
+    return MincMatrix(out, colnames=_colnames(names), attrs=attrs, r_class=("vertexLm", "vertexMultiDim", "matrix"))
+
+
+def anatLm(formula: str, data, anat, subset=None, weights=None, device: int = 0) -> MincMatrix:
+    """`anat`: subjects x structures matrix (anatGetAll output); formula has no left-hand side
+    ("~ Sex").  Rows of the result are structures (R/minc_anatomy.R:1125-1128, :1153)."""
+    if weights is not None:
+        raise NotImplementedError("anatLm(weights=) (vertex_wlm_loop, src/weighted_least_squares.c) is a "
+                                  "'next' row of the scope table and is not on the GPU path yet")
+    lhs, rhs = split_formula(formula)
+    if "$" in rhs:
+        raise FormulaError("$ Not Permitted in Formula")
+    rows = _subset_rows(data, subset)
+    for term in rhs.replace("*", "+").replace(":", "+").split("+"):
+        t = term.strip()
+        if t and t not in ("0", "1", "-1"):
+            c = data[t]
+            if np.asarray(c.iloc[0] if hasattr(c, "iloc") else c[0]).ndim > 0:
+                raise ValueError("A term in your model is a matrix, this use of `anatLm` is deprecated, Please merge "
+                                 "the two anatomy matrices using rowbind or similar and use a group add a group "
+                                 "indicator to your `data.frame`")                # minc_anatomy.R:1115-1121
+    X, names, _ = model_matrix(rhs, data, rows)
+    A = np.asarray(anat, dtype=np.float64)
+    if A.ndim != 2 or A.shape[0] != len(data):
+        raise ValueError("anat must be a subjects x structures matrix with one row per row of data")
+    Y = np.asfortranarray(A[rows, :].T)                                          # structures x subjects
+    out = core.vertex_lm(Y, X, device=device)
+    n, p = X.shape
+    rownames = list(getattr(anat, "columns", [])) or None
+    attrs = {"atlas": getattr(anat, "atlas", None), "definitions": getattr(anat, "definitions", None), "model": X,
+             "data": data, "call": dict(fn="anatLm", formula=formula, subset=subset), "stat-type": _stat_type(p),
+             "df": _df_list(n, p), "model-colnames": names, "_Y": Y, "_mask": None,
+             "_mask_range": (core.DEFAULT_MASK_LO, core.DEFAULT_MASK_HI), "_rows": rows, "_rhs": rhs, "_lhs": lhs}
+    return MincMatrix(out, colnames=_colnames(names), rownames=rownames, attrs=attrs, r_class=("anatModel", "matrix"))
+
+
+# ----------------------------------------------------------------------------- mincRandomize
+class MincRandomization(dict):
+    """list(stats, randomization_dist, args) of class c("mincLm_randomization","minc_randomization")."""
+    r_class = ("mincLm_randomization", "minc_randomization")
+
+
+def draw_indices(n: int, R: int, replace: bool = False, seed=None) -> np.ndarray:
+    """n x R index matrix: column r is sample(seq_len(n), replace = replace) (:1472).  In R the
+    indices come from R's own RNG; numpy's generator stands in for it here."""
+    rng = np.random.default_rng(seed)
+    if replace:
+        return rng.integers(0, n, size=(n, R)).astype(np.int32)
+    return np.column_stack([rng.permutation(n) for _ in range(R)]).astype(np.int32)
+
+
+def mincRandomize(x: MincMatrix, R: int = 500, alternative: str = "two.sided", replace: bool = False,
+                  parallel=None, columns: Optional[Sequence[int]] = None, seed=None, idx=None,
+                  device: int = 0) -> MincRandomization:
+    """Permutation null of the extreme statistics of a mincLm / vertexLm / anatLm fit.
+
+    All predictor columns of the data frame move together (:1457-1474), so the permuted design is
+    the model matrix with its ROWS permuted; the whole voxel-wise refit per permutation happens on
+    the GPU with Y resident (the reference re-runs mincLm, re-reading every file, :1477).
+    `columns`: 0-based result columns (default: the tvalue- columns, :1333)."""
+    if alternative not in ("two.sided", "greater"):
+        raise ValueError("'arg' should be one of 'two.sided', 'greater'")        # match.arg
+    if not isinstance(x, MincMatrix) or "_Y" not in x.attrs:
+        raise TypeError("x must be the result of mincLm / vertexLm / anatLm")
+    X = x.attrs["model"]
+    n = X.shape[0]
+    if columns is None:
+        columns = [i for i, c in enumerate(x.colnames) if c.startswith("tvalue-")]
+    columns = [int(c) for c in columns]
+    if idx is None:
+        idx = draw_indices(n, R, replace=replace, seed=seed)
+    idx = np.asarray(idx, dtype=np.int32)
+    if idx.shape != (n, R):
+        raise ValueError("idx must be n x R")
+    lo, hi = x.attrs["_mask_range"]
+    n_gpus = int(parallel[1]) if parallel is not None else None
+    dist = core.randomize(x.attrs["_Y"], X, idx, columns, two_sided=(alternative == "two.sided"),
+                          mask=x.attrs["_mask"], mask_lo=lo, mask_hi=hi, device=device, n_gpus=n_gpus)
+    out = MincRandomization(
+        stats=MincMatrix(np.asarray(x)[:, columns], colnames=[x.colnames[c] for c in columns]),
+        randomization_dist=MincMatrix(dist, colnames=[x.colnames[c] for c in columns]),
+        args=dict(call=x.attrs.get("call"), alternative=alternative),
+    )
+    return out
+
+
+def thresholds(x: MincRandomization, probs=(0.01, 0.05, 0.1, 0.2)) -> MincMatrix:
+    """apply(dist, 2, quantile, probs = 1 - probs) with rownames "1%", "5%", ... (:1577-1581).
+    R's default quantile type 7 == numpy's default 'linear' method."""
+    d = np.asarray(x["randomization_dist"])
+    q = np.quantile(d, [1 - p for p in probs], axis=0)
+    return MincMatrix(q, colnames=x["randomization_dist"].colnames, rownames=[f"{p * 100:g}%" for p in probs])

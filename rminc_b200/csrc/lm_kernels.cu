@@ -316,26 +316,18 @@ lm_fit_ldg_kernel(LmArgs a, int JT)
         }
     }
 
-    double rss[VPT], mss[VPT];
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-        rss[i] = sum[i].yy - sumsq_e(sum[i]);
-        mss[i] = mss_from_e(sum[i], sd);
-        if (act[i] && rss[i] <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0)
-            exact_pass<KP>(sum[i], a.Y + v + i, a.ldY, n, a.Qt, rss[i], mss[i]);
-    }
-    if constexpr (VPT == 2) {
-        if (a.out_vec2 && in[1]) {
-            finish_pair<KP>(sum[0], rss[0], mss[0], act[0], sum[1], rss[1], mss[1], act[1], sd, a.out + v, a.ldOut);
-            return;
-        }
-    }
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
         if (!in[i]) continue;
         double *o = a.out + v + i;
-        if (act[i]) finish_voxel<KP>(sum[i], rss[i], mss[i], sd, o, a.ldOut);
-        else zero_row<KP>(sd.p, o, a.ldOut);
+        if (!act[i]) {
+            zero_row<KP>(sd.p, o, a.ldOut);
+            continue;
+        }
+        double rss = sum[i].yy - sumsq_e(sum[i]), mss = mss_from_e(sum[i], sd);
+        if (rss <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0)
+            exact_pass<KP>(sum[i], a.Y + v + i, a.ldY, n, a.Qt, rss, mss);
+        finish_voxel<KP>(sum[i], rss, mss, sd, o, a.ldOut);
     }
 }
 

@@ -1,0 +1,110 @@
+/*
+ * rshim.c -- the thin .Call layer between R and the C ABI of include/rminc_b200.h.
+ *
+ * NOT compiled into librminc_b200.so (R's headers are not part of the CUDA build); the RMINC
+ * maintainer adds this one file to RMINC's src/ and links -lrminc_b200.
+ * It is kept free of logic: argument unpacking, allocMatrix for the result, rc -> Rf_error.
+ * The R API is touched only on the calling thread, never after a failure inside the library
+ * has left anything allocated (the C ABI frees everything before it returns).
+ *
+ * Entry points registered exactly like the reference's (src/RMINC_init.c:57-82):
+ *   rmincgpu_vertex_lm_loop  same signature as vertex_lm_loop (src/vertex_modelling.c:8), so
+ *                            vertexLm / anatLm only change the routine name
+ *   rmincgpu_lm              minc2_model(method = "lm") with the volumes already staged
+ *   rmincgpu_randomize       the mincRandomize loop (R/minc_voxel_statistics.R:1465-1497)
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+
+#include "rminc_b200.h"
+
+static void check(int rc, const char *msg)
+{
+    if (rc != RMG_OK) Rf_error("%s", msg);   /* e.g. "element (4, 4) is zero, so the inverse cannot be computed" */
+}
+
+static const double *mask_or_null(SEXP mask, R_xlen_t V)
+{
+    if (Rf_isNull(mask)) return NULL;
+    if (!Rf_isReal(mask) || XLENGTH(mask) != V) Rf_error("Mask Volume input volume dimension mismatch.");
+    return REAL(mask);
+}
+
+SEXP rmincgpu_vertex_lm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix)
+{
+    if (!Rf_isLogical(data_right))
+        Rf_error("voxel-wise covariates (a file term on the right-hand side) are not on the GPU path");
+    if (!Rf_isReal(data_left) || !Rf_isReal(mmatrix)) Rf_error("data_left and mmatrix must be double matrices");
+    const R_xlen_t V = Rf_nrows(data_left);
+    const int n = Rf_ncols(data_left), p = Rf_ncols(mmatrix);
+    if (Rf_nrows(mmatrix) != n) Rf_error("model matrix has %d rows, data has %d subjects", Rf_nrows(mmatrix), n);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, 2 * p + 3));
+    char err[512] = "";
+    int rc = rmg_vertex_lm(REAL(data_left), V, V > 0 ? V : 1, n, REAL(mmatrix), p, REAL(out), V > 0 ? V : 1,
+                           Rf_asInteger(Rf_GetOption1(Rf_install("RMINC_GPU_DEVICE"))) > 0
+                               ? Rf_asInteger(Rf_GetOption1(Rf_install("RMINC_GPU_DEVICE"))) : 0,
+                           err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
+SEXP rmincgpu_lm(SEXP Y, SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP mask_upper, SEXP ngpu)
+{
+    if (!Rf_isReal(Y) || !Rf_isReal(mmatrix)) Rf_error("Y and mmatrix must be double matrices");
+    const R_xlen_t V = Rf_nrows(Y);
+    const int n = Rf_ncols(Y), p = Rf_ncols(mmatrix);
+    if (Rf_nrows(mmatrix) != n) Rf_error("model matrix has %d rows, data has %d subjects", Rf_nrows(mmatrix), n);
+    const double *m = mask_or_null(mask, V);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, 2 * p + 3));
+    char err[512] = "";
+    const int G = Rf_asInteger(ngpu);
+    int rc = G > 1 ? rmg_lm_fit_multi(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, m, Rf_asReal(mask_lower),
+                                      Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, G, err, sizeof err)
+                   : rmg_lm_fit(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, m, Rf_asReal(mask_lower),
+                                Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, 0, err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
+SEXP rmincgpu_randomize(SEXP Y, SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP mask_upper, SEXP idx,
+                        SEXP columns, SEXP two_sided, SEXP ngpu)
+{
+    if (!Rf_isReal(Y) || !Rf_isReal(mmatrix) || !Rf_isInteger(idx) || !Rf_isInteger(columns))
+        Rf_error("Y/mmatrix must be double, idx/columns integer");
+    const R_xlen_t V = Rf_nrows(Y);
+    const int n = Rf_ncols(Y), p = Rf_ncols(mmatrix), R = Rf_ncols(idx), nc = LENGTH(columns);
+    if (Rf_nrows(idx) != n) Rf_error("idx must have one row per subject");
+    const double *m = mask_or_null(mask, V);
+    /* R is 1-based: idx holds sample(seq_len(n)), columns are column numbers of the mincLm matrix */
+    int *idx0 = (int *)R_alloc((size_t)n * R, sizeof(int));
+    int *col0 = (int *)R_alloc((size_t)nc, sizeof(int));
+    for (R_xlen_t i = 0; i < (R_xlen_t)n * R; ++i) idx0[i] = INTEGER(idx)[i] - 1;
+    for (int i = 0; i < nc; ++i) col0[i] = INTEGER(columns)[i] - 1;
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, R, nc));
+    char err[512] = "";
+    const int G = Rf_asInteger(ngpu);
+    int rc = G > 1 ? rmg_randomize_multi(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, m, Rf_asReal(mask_lower),
+                                         Rf_asReal(mask_upper), idx0, R, col0, nc, Rf_asLogical(two_sided),
+                                         REAL(out), G, err, sizeof err)
+                   : rmg_randomize(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, m, Rf_asReal(mask_lower),
+                                   Rf_asReal(mask_upper), idx0, R, col0, nc, Rf_asLogical(two_sided), REAL(out), 0,
+                                   err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
+static const R_CallMethodDef callMethods[] = {
+    {"rmincgpu_vertex_lm_loop", (DL_FUNC)&rmincgpu_vertex_lm_loop, 3},
+    {"rmincgpu_lm", (DL_FUNC)&rmincgpu_lm, 6},
+    {"rmincgpu_randomize", (DL_FUNC)&rmincgpu_randomize, 9},
+    {NULL, NULL, 0}};
+
+void R_init_rmincgpu(DllInfo *dll)
+{
+    R_registerRoutines(dll, NULL, callMethods, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}

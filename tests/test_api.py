@@ -1,0 +1,179 @@
+"""The host-side mirror of RMINC's R interface (rminc_b200/api.py), tested the way the reference's
+testthat files test mincLm / vertexLm / anatLm / mincRandomize: one row of the result against an
+independent lm() of the same data (tests/testthat/test_mincLm.R:34-56, :135-208,
+test_vertexLm.R:66-74, test_anatLm.R:30-44, :152-157).
+
+Each test runs twice: with the numerical back end replaced by the CPU oracle (host logic only, no
+GPU needed) and, marked gpu, through the real CUDA path."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from test_oracle import numpy_ols
+
+
+@pytest.fixture(params=["oracle-backend", pytest.param("cuda", marks=pytest.mark.gpu)])
+def api(request, monkeypatch, oracle, lib):
+    from rminc_b200 import api as A
+    from rminc_b200 import core
+    if request.param == "oracle-backend":
+        def lm_fit(Y, X, mask=None, mask_lo=1.0, mask_hi=99999999.0, device=0, n_gpus=None):
+            return oracle.minc2_model_lm(Y, (1, 1, Y.shape[0]), X, mask=mask, lo=mask_lo, hi=mask_hi)
+
+        def vertex_lm(Y, X, device=0):
+            return oracle.vertex_lm_loop(Y, X)
+
+        def randomize(Y, X, idx, cols, two_sided=True, mask=None, mask_lo=1.0, mask_hi=99999999.0, device=0,
+                      n_gpus=None):
+            return oracle.randomize(Y, X, idx, cols, two_sided=two_sided, mask=mask, lo=mask_lo, hi=mask_hi)
+
+        monkeypatch.setattr(core, "lm_fit", lm_fit)
+        monkeypatch.setattr(core, "vertex_lm", vertex_lm)
+        monkeypatch.setattr(core, "randomize", randomize)
+    return A
+
+
+@pytest.fixture()
+def study(tmp_path):
+    """10 subjects of 10x10x10 volumes, as tests/testthat/test_mincLm.R:12-23."""
+    rng = np.random.default_rng(42)
+    n, dims = 10, (10, 10, 10)
+    sex = np.array(list("MFMFMFMFMF"))
+    scale = np.round(rng.normal(1.0, 0.2, n), 3)
+    coil = np.array([1, 2, 3, 1, 2, 3, 1, 2, 3, 1])
+    grp = np.array(list("abcabcabca"))
+    files = []
+    for i in range(n):
+        vol = rng.normal(0, 0.2, dims) + 0.3 * (sex[i] == "M") + 0.5 * scale[i]
+        f = tmp_path / f"subj{i:02d}.npy"
+        np.save(f, vol)
+        files.append(str(f))
+    gf = pd.DataFrame(dict(jacobians=files, Sex=sex, Scale=scale, Coil=coil, Grp=grp))
+    mask = np.zeros(dims)
+    mask[2:8, 2:8, 2:8] = 1
+    np.save(tmp_path / "mask.npy", mask)
+    return gf, str(tmp_path / "mask.npy"), np.stack([np.load(f).reshape(-1) for f in files], axis=1)
+
+
+def check_row(res, v, y, X, names):
+    w = numpy_ols(y, X)
+    p = X.shape[1]
+    row = np.asarray(res)[v]
+    assert row[0] == pytest.approx(w["F"], rel=1e-9)
+    assert row[1] == pytest.approx(w["R2"], rel=1e-9)
+    assert row[2:2 + p] == pytest.approx(w["coef"], rel=1e-8, abs=1e-10)
+    assert row[2 + p:2 + 2 * p] == pytest.approx(w["t"], rel=1e-8, abs=1e-10)
+    assert row[-1] == pytest.approx(w["logLik"], rel=1e-10)
+    assert res.colnames == (["F-statistic", "R-squared"] + [f"beta-{r}" for r in names]
+                            + [f"tvalue-{r}" for r in names] + ["logLik"])
+
+
+def test_mincLm_two_level_factor(api, study):
+    gf, _, Y = study
+    vs = api.mincLm("jacobians ~ Sex", gf)
+    X = np.column_stack([np.ones(10), gf.Sex == "M"]).astype(float)
+    assert vs.shape == (1000, 7) and vs.r_class == ("mincLm", "mincMultiDim", "matrix")
+    check_row(vs, 0, Y[0], X, ["(Intercept)", "SexM"])
+    check_row(vs, 567, Y[567], X, ["(Intercept)", "SexM"])
+    # attributes as R/minc_voxel_statistics.R:908-935
+    assert vs.attrs["likeVolume"] == gf.jacobians[0] and vs.attrs["filenames"] == list(gf.jacobians)
+    assert np.array_equal(vs.attrs["model"], X)
+    assert vs.attrs["stat-type"] == ["F", "R-squared", "beta", "beta", "t", "t", "logLik"]
+    assert vs.attrs["df"] == [[1, 8], 8, 8]
+    # AIC / BIC consumers use the logLik column and the model attribute (R/minc_model_selection.R:1-68)
+    ll, k = vs.col("logLik")[0], X.shape[1] + 1
+    w = numpy_ols(Y[0], X)
+    assert -2 * ll + 2 * k == pytest.approx(-2 * w["logLik"] + 2 * k)
+
+
+def test_mincLm_interaction_three_level_and_two_covariates(api, study):
+    gf, _, Y = study
+    m, s = (gf.Sex == "M").astype(float), gf.Scale.values
+    vs = api.mincLm("jacobians ~ Sex*Scale", gf)
+    check_row(vs, 1, Y[1], np.column_stack([np.ones(10), m, s, m * s]), ["(Intercept)", "SexM", "Scale", "SexM:Scale"])
+    vs = api.mincLm("jacobians ~ Grp", gf)
+    Xg = np.column_stack([np.ones(10), gf.Grp == "b", gf.Grp == "c"]).astype(float)
+    check_row(vs, 1, Y[1], Xg, ["(Intercept)", "Grpb", "Grpc"])
+    assert vs.attrs["df"] == [[2, 7], 7, 7, 7]
+    vs = api.mincLm("jacobians ~ Scale*Coil", gf.iloc[:10])
+    c = gf.Coil.values.astype(float)
+    check_row(vs, 999, Y[999], np.column_stack([np.ones(10), s, c, s * c]), ["(Intercept)", "Scale", "Coil", "Scale:Coil"])
+
+
+def test_mincLm_mask_maskval_subset(api, study):
+    gf, maskfile, Y = study
+    vs = api.mincLm("jacobians ~ Sex", gf, mask=maskfile)
+    inside = np.load(maskfile).reshape(-1) > 0.5
+    arr = np.asarray(vs)
+    assert (arr[~inside] == 0).all() and (arr[inside, 0] != 0).all()
+    labels = (np.arange(1000) % 3).astype(float)
+    vs2 = api.mincLm("jacobians ~ Sex", gf, mask=labels, maskval=2)
+    assert np.array_equal(np.asarray(vs2)[:, 0] != 0, labels == 2)
+    # subset: rows of the data frame, drop.unused.levels
+    keep = np.arange(10) != 3
+    vs3 = api.mincLm("jacobians ~ Sex", gf, subset=keep)
+    X = np.column_stack([np.ones(9), gf.Sex[keep] == "M"]).astype(float)
+    check_row(vs3, 5, Y[5][keep], X, ["(Intercept)", "SexM"])
+    with pytest.raises(ValueError, match="dimension mismatch"):
+        api.mincLm("jacobians ~ Sex", gf, mask=np.ones(999))
+    bad = gf.copy()
+    bad.loc[2, "jacobians"] = "/nonexistent/file.npy"
+    with pytest.raises(FileNotFoundError, match="Error opening input file"):
+        api.mincLm("jacobians ~ Sex", bad)
+
+
+def test_vertexLm_and_anatLm(api, tmp_path):
+    rng = np.random.default_rng(7)
+    n, V = 12, 40
+    dx = np.array(["AD", "CN"] * 6)
+    age = np.round(rng.normal(70, 5, n), 1)
+    files = []
+    for i in range(n):
+        f = tmp_path / f"thick{i}.txt"
+        np.savetxt(f, np.column_stack([rng.normal(3, 0.3, V) + 0.2 * (dx[i] == "CN"), rng.normal(size=V)]))
+        files.append(str(f))
+    gf = pd.DataFrame(dict(thickness=files, Dx=dx, Age=age))
+    Y = np.column_stack([np.loadtxt(f)[:, 0] for f in files])
+    res = api.vertexLm("thickness ~ Dx + Age", gf)
+    X = np.column_stack([np.ones(n), dx == "CN", age]).astype(float)
+    assert res.r_class == ("vertexLm", "vertexMultiDim", "matrix") and res.shape == (V, 9)
+    check_row(res, 0, Y[0], X, ["(Intercept)", "DxCN", "Age"])
+    res2 = api.vertexLm("thickness ~ Dx + Age", gf, column=2)
+    Y2 = np.column_stack([np.loadtxt(f)[:, 1] for f in files])
+    check_row(res2, 3, Y2[3], X, ["(Intercept)", "DxCN", "Age"])
+    # anatLm: subjects x structures matrix, rows of the result are structures
+    anat = pd.DataFrame(rng.normal(10, 1, (n, 5)) + 0.5 * (dx == "CN")[:, None], columns=list("ABCDE"))
+    ra = api.anatLm("~ Dx", gf, anat)
+    assert ra.r_class == ("anatModel", "matrix") and ra.rownames == list("ABCDE") and ra.shape == (5, 7)
+    check_row(ra, 2, anat.values[:, 2], X[:, :2], ["(Intercept)", "DxCN"])
+    with pytest.raises(NotImplementedError):
+        api.anatLm("~ Dx", gf, anat, weights=np.ones(n))
+    gm = gf.copy()
+    gm["M"] = [np.ones(3)] * n
+    with pytest.raises(ValueError, match="A term in your model is a matrix"):
+        api.anatLm("~ M", gm, anat)                                    # tests/testthat/test_anatLm.R:152-157
+
+
+def test_mincRandomize_and_thresholds(api, study):
+    gf, maskfile, Y = study
+    vs = api.mincLm("jacobians ~ Sex", gf, mask=maskfile)
+    rand = api.mincRandomize(vs, R=9, seed=3)
+    th = api.thresholds(rand)
+    assert th.shape == (4, 2)                                          # tests/testthat/test_mincLm.R:261-267
+    assert th.rownames == ["1%", "5%", "10%", "20%"] and th.colnames == ["tvalue-(Intercept)", "tvalue-SexM"]
+    assert rand.r_class == ("mincLm_randomization", "minc_randomization")
+    assert rand["args"]["alternative"] == "two.sided"
+    assert np.array_equal(np.asarray(rand["stats"]), np.asarray(vs)[:, [4, 5]])
+    # every row of the null distribution is the column max of |t| of a refit with permuted predictors
+    idx = api.draw_indices(10, 9, seed=3)
+    X = vs.attrs["model"]
+    inside = np.load(maskfile).reshape(-1) > 0.5
+    for r in (0, 8):
+        tmax = np.zeros(2)
+        for v in np.flatnonzero(inside):
+            tmax = np.maximum(tmax, np.abs(numpy_ols(Y[v], X[idx[:, r]])["t"]))
+        assert np.asarray(rand["randomization_dist"])[r] == pytest.approx(tmax, rel=1e-8)
+    one = api.mincRandomize(vs, R=5, alternative="greater", seed=3, columns=[5])
+    assert np.asarray(one["randomization_dist"]).shape == (5, 1) and (np.asarray(one["randomization_dist"]) >= 0).all()
+    with pytest.raises(ValueError):
+        api.mincRandomize(vs, R=3, alternative="less")

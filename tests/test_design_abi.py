@@ -121,3 +121,17 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".c", ".R")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert not re.search(r"\boracle\b|liboracle|orc_", txt), f"{f} mentions the oracle"
+
+
+def test_rshim_compiles_against_r_api_declarations():
+    """rminc_b200/csrc/rshim.c (the .Call layer a maintainer adds to RMINC) cannot be built here --
+    R's headers are absent -- so at least syntax-check it against the declaration-only stand-ins in
+    oracle/rstub and the real include/rminc_b200.h."""
+    import subprocess
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "oracle", "rstub"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "rminc_b200", "csrc", "rshim.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(ROOT, "rminc_b200", "csrc", "rshim.c")).read()
+    for name in ("rmincgpu_vertex_lm_loop", "rmincgpu_lm", "rmincgpu_randomize"):
+        assert name in src and name in open(os.path.join(ROOT, "rminc_b200", "R", "rminc_gpu.R")).read()
