@@ -155,6 +155,25 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_numa(index):
+    """Run this process on the CPUs NVML reports as local to GPU `index`, so that the pinned host
+    buffers of the end-to-end leg are first-touched on the GPU's NUMA node.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = ((os.cpu_count() or 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {w * 64 + i for w in range(words) for i in range(64) if (mask[w] >> i) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def measured_hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -344,6 +363,7 @@ def run_gpu_arm(args):
     e2e = None
     if "e2e" in args.parts:
         import psutil
+        numa_cpus = bind_to_gpu_numa(local_rank)
         avail = psutil.virtual_memory().available
         need = V * n * 8
         Ve = V if avail > need * world * 1.3 + (8 << 30) else max(1024, int((avail / world * 0.5) // (8 * n)) // 1024 * 1024)
@@ -359,6 +379,14 @@ def run_gpu_arm(args):
         err = _lib.errbuf()
 
         Xf = np.asfortranarray(X)          # keep alive: ctypes only sees the address
+        # plain pinned->device copy rate on this box, reported beside the number it bounds
+        probe = torch.empty((min(n, 64), Ve), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        tp = time.perf_counter()
+        probe.copy_(hY[:probe.shape[0]], non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = probe.numel() * 8 / (time.perf_counter() - tp) / 1e9
+        del probe
 
         def e2e_step():
             rc = lib.rmg_lm_fit(Yh.ctypes.data, Ve, Ve, n, Xf.ctypes.data, p, None, 1.0, 99999999.0,
@@ -380,7 +408,8 @@ def run_gpu_arm(args):
         e2e = {"value": world * Ve * ksteps / dt, "unit": UNIT, "h2d_bytes_per_step": Ve * n * 8 + n * p * 8,
                "d2h_bytes_per_step": Ve * (2 * p + 3) * 8, "steps": ksteps, "voxels_per_step_per_gpu": Ve,
                "api": "rmg_lm_fit (C ABI, pinned host Y -> chunked H2D -> kernel -> D2H result)",
-               "kernel_ms_inside": core.last_kernel_ms()}
+               "kernel_ms_inside": core.last_kernel_ms(), "pinned_h2d_gbs_probe": h2d_gbs,
+               "bound": "PCIe: Y is 4000 B/voxel over the host link", "numa_bound_cpus": len(numa_cpus) if numa_cpus else None}
         # sanity: the end-to-end result equals the device-resident result
         # (different chunk shapes pick different summation orders, so "equal" means 1e-9 of the
         #  column scale, the same criterion tests/helpers.py uses)
