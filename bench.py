@@ -453,7 +453,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--perms", type=int, default=256, help="permutations timed for the randomize line")
+    ap.add_argument("--perms", type=int, default=1000, help="permutations timed for the randomize line")
     ap.add_argument("--small", action="store_true", help="tiny smoke configuration (not a bench line)")
     ap.add_argument("--skip-extras", action="store_true", help="only the device-resident headline")
     ap.add_argument("--skip-cpu", action="store_true")

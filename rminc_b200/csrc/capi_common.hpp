@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rminc_b200.h"
@@ -54,6 +55,26 @@ int check_fit_args(const void *Y, int64_t V, int64_t ldY, int n, const void *X, 
 void fill_dev_design(const Design &D, DevDesign &dd);
 // Row-major [n][KP] copy of Q (columns >= rank zero).
 std::vector<double> make_qt(const Design &D, int KP);
+
+// Runs fn(begin, end) over [0, count) on up to hardware_concurrency host threads (host-side
+// preparation of the permutation test: factorisations and operand packing).
+template <class Fn>
+inline void parallel_for(int count, Fn fn)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)(hw ? (hw > 16 ? 16 : hw) : 1);
+    if (nt > count / 8) nt = count / 8;
+    if (nt <= 1) {
+        fn(0, count);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) {
+        const int a = (int)((int64_t)count * t / nt), b = (int)((int64_t)count * (t + 1) / nt);
+        th.emplace_back([=, &fn]() { fn(a, b); });
+    }
+    for (auto &t : th) t.join();
+}
 
 // Factor X and translate the reference's error contract.  0 or RMG_ERR_*.
 int factor_or_fail(const double *X, int n, int p, Design &D, char *err, size_t errlen);

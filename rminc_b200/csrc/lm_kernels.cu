@@ -51,6 +51,94 @@ __global__ void mask_tile_flags_kernel(const double *__restrict__ mask, int64_t 
     if (threadIdx.x == 0) flags[t] = (unsigned char)any;
 }
 
+// ------------------------------------------------------------------ mask compaction
+// With a mask only the selected voxels need their n samples streamed.  Three small kernels turn
+// the mask into an ascending list of voxel pairs (v, v+1) that contain a selected voxel; pairs
+// with none get their +0.0 result rows written here and are never visited again.
+constexpr int kCompactBlock = 1024;   // pairs per block
+
+__device__ __forceinline__ bool pair_selected(const double *__restrict__ mask, int64_t pair, int64_t V, double lo,
+                                              double hi)
+{
+    const int64_t v = pair * 2;
+    if (v >= V) return false;
+    const double2 m = *reinterpret_cast<const double2 *>(mask + v);   // V even, mask 16-byte aligned (host checks)
+    return mask_selects(m.x, lo, hi) || mask_selects(m.y, lo, hi);
+}
+
+__global__ void __launch_bounds__(kCompactBlock)
+mask_count_kernel(const double *__restrict__ mask, int64_t V, double lo, double hi, unsigned int *__restrict__ counts)
+{
+    const int64_t pair = (int64_t)blockIdx.x * kCompactBlock + threadIdx.x;
+    const int c = __syncthreads_count(pair_selected(mask, pair, V, lo, hi));
+    if (threadIdx.x == 0) counts[blockIdx.x] = (unsigned int)c;
+}
+
+// exclusive scan of the per-block counts by one block; total -> *n_pairs
+__global__ void __launch_bounds__(1024)
+mask_scan_kernel(unsigned int *__restrict__ counts, int nblocks, unsigned int *__restrict__ n_pairs)
+{
+    __shared__ unsigned int warp_sums[32];
+    __shared__ unsigned int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned int x = i < nblocks ? counts[i] : 0u;
+        unsigned int incl = x;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned int w = warp_sums[threadIdx.x], wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int y = __shfl_up_sync(0xffffffffu, wi, o);
+                if (threadIdx.x >= o) wi += y;
+            }
+            warp_sums[threadIdx.x] = wi - w;   // exclusive
+        }
+        __syncthreads();
+        const unsigned int excl = carry + warp_sums[threadIdx.x >> 5] + incl - x;
+        if (i < nblocks) counts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_pairs = carry;
+}
+
+__global__ void __launch_bounds__(kCompactBlock)
+mask_compact_kernel(const double *__restrict__ mask, int64_t V, double lo, double hi,
+                    const unsigned int *__restrict__ offsets, uint32_t *__restrict__ list, double *__restrict__ out,
+                    int64_t ldOut, int ncol)
+{
+    __shared__ unsigned int warp_sums[32];
+    const int64_t pair = (int64_t)blockIdx.x * kCompactBlock + threadIdx.x;
+    const bool sel = pair_selected(mask, pair, V, lo, hi);
+    const unsigned int ballot = __ballot_sync(0xffffffffu, sel);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_sums[warp] = __popc(ballot);
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int w = warp_sums[lane], wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    if (sel) {
+        list[offsets[blockIdx.x] + warp_sums[warp] + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)pair;
+    } else if (pair * 2 < V) {
+        double2 *o = reinterpret_cast<double2 *>(out + pair * 2);   // out 16-byte aligned, ldOut even (host checks)
+        for (int c = 0; c < ncol; ++c) o[(int64_t)c * (ldOut / 2)] = make_double2(0.0, 0.0);
+    }
+}
+
 // One box of NJ subject rows out of shared memory into the two voxels' running sums.
 template <int KP, int NJ, int ROWW, bool GUARD>
 __device__ __forceinline__ void consume_box(const double *__restrict__ tile, const double *__restrict__ q,
@@ -218,7 +306,12 @@ lm_fit_ldg_kernel(LmArgs a, int JT)
     load_design_to_smem<KP>(sd, a.design, tid, nthreads);
     __syncthreads();
 
-    const int64_t v = ((int64_t)blockIdx.x * TX + x) * VPT;
+    int64_t v = ((int64_t)blockIdx.x * TX + x) * VPT;
+    if (VPT == 2 && a.pair_list) {
+        // compacted: slot -> pair index; slots past the count have nothing to do
+        const int64_t slot = (int64_t)blockIdx.x * TX + x;
+        v = slot < (int64_t)*a.n_pairs ? (int64_t)a.pair_list[slot] * 2 : a.V;
+    }
     bool in[VPT], act[VPT];
     bool any = false;
 #pragma unroll
@@ -237,7 +330,8 @@ lm_fit_ldg_kernel(LmArgs a, int JT)
     }
     const int jb = (int)(((int64_t)s * n) / S), je = (int)(((int64_t)(s + 1) * n) / S);
     const int span = (n + S - 1) / S;  // longest slice
-    const double *yp = a.Y + v;
+    const double *yp = a.Y + (any ? v : 0);
+    if (a.pair_list && (int64_t)blockIdx.x * TX >= (int64_t)*a.n_pairs) return;   // whole block past the list
 
     for (int t0 = 0; t0 < span; t0 += JT) {
         // every slice stages rows [jb + t0, jb + t0 + JT) of Qt into its own sub-tile
@@ -466,10 +560,32 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
     const int64_t blocks = (a.V + per_block - 1) / per_block;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
     dim3 bd(TX, S);
+    // ---- mask compaction: stream only the selected voxels (falls back to in-kernel skipping when the
+    //      layout does not allow 16-byte pair accesses)
+    LmArgs ac = a;
+    const bool compact = a.mask && VPT == 2 && a.out_vec2 && (reinterpret_cast<uintptr_t>(a.mask) & 15) == 0 &&
+                         a.V / 2 < 0xffffffffLL && !plan.no_compact;
+    if (compact) {
+        const int64_t npairs = a.V / 2;
+        const int nb = (int)((npairs + kCompactBlock - 1) / kCompactBlock);
+        const size_t off_list = ((size_t)nb * 4 + 4 + 255) & ~size_t(255);
+        cudaError_t e = scr.ensure_bytes(off_list + (size_t)npairs * 4, st);
+        if (e != cudaSuccess) return e;
+        unsigned int *counts = reinterpret_cast<unsigned int *>(scr.flags);
+        unsigned int *n_pairs = counts + nb;
+        uint32_t *list = reinterpret_cast<uint32_t *>(scr.flags + off_list);
+        mask_count_kernel<<<nb, kCompactBlock, 0, st>>>(a.mask, a.V, a.mask_lo, a.mask_hi, counts);
+        mask_scan_kernel<<<1, 1024, 0, st>>>(counts, nb, n_pairs);
+        mask_compact_kernel<<<nb, kCompactBlock, 0, st>>>(a.mask, a.V, a.mask_lo, a.mask_hi, counts, list, a.out, a.ldOut,
+                                                           2 * a.p + 3);
+        if (info) info->launches += 3;
+        ac.pair_list = list;
+        ac.n_pairs = n_pairs;
+    }
     auto go = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<(unsigned)blocks, bd, smem, st>>>(a, JT);
+        kern<<<(unsigned)blocks, bd, smem, st>>>(ac, JT);
         return cudaGetLastError();
     };
     cudaError_t e;

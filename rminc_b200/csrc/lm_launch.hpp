@@ -20,6 +20,10 @@ struct LmArgs {
     double *out;
     int64_t ldOut;
     int out_vec2 = 0;          // set by launch_lm_fit: out is 16-byte aligned with an even ld
+    // mask compaction (direct-load kernel): ascending list of voxel PAIRS with at least one selected
+    // voxel and their count, both device-resident; null = process every pair
+    const uint32_t *pair_list = nullptr;
+    const unsigned int *n_pairs = nullptr;
 };
 
 enum class LmVariant { Auto = 0, Tma = 1, Ldg = 2 };
@@ -29,6 +33,7 @@ struct LmPlan {
     int split = 0;       // LDG path: slices of the subject axis (0 = choose)
     int sm_count = 148;
     int tma_cfg = -1;    // TMA path: tile-shape variant (-1 = choose by V; see lm_kernels.cu)
+    int no_compact = 0;  // direct-load path: 1 = never compact masked voxels (debug / comparison)
     int q_stream = -1;   // TMA path: 1 = stream Q' with Y, 0 = keep Q' resident in smem, -1 = choose
 };
 
@@ -39,7 +44,7 @@ struct LmLaunchInfo {
     int split = 1;
 };
 
-// Reusable device scratch owned by the caller (mask tile flags).
+// Reusable device scratch owned by the caller (mask tile flags / compacted pair list).
 struct LmScratch {
     unsigned char *flags = nullptr;
     size_t flags_cap = 0;
@@ -51,6 +56,7 @@ struct LmScratch {
         if (e == cudaSuccess) flags_cap = n;
         return e;
     }
+    cudaError_t ensure_bytes(size_t n, cudaStream_t st) { return ensure_flags(n, st); }
     // stream-ordered: safe while kernels that read the flags are still queued on st
     void release(cudaStream_t st)
     {

@@ -2,6 +2,7 @@
 #include "perm_gemm.cuh"
 
 #include "async_ptx.cuh"
+#include "capi_common.hpp"
 
 namespace rmg {
 namespace {
@@ -431,7 +432,8 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
     std::vector<double> Apack((size_t)n_pt * n_kc * A_CHUNK, 0.0);
     std::vector<double> Qt((size_t)R * n * KP, 0.0);
     std::vector<PermConst> pc(R);
-    for (int r = 0; r < R; ++r) {
+    parallel_for(R, [&](int r0, int r1) {
+      for (int r = r0; r < r1; ++r) {
         const Design &D = designs[r];
         PermConst &c = pc[r];
         std::memset(&c, 0, sizeof c);
@@ -458,7 +460,8 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
                 Apack[off] = qcol[j];
             }
         }
-    }
+      }
+    });
 
     // ---- one workspace allocation
     size_t off = 0;

@@ -76,16 +76,26 @@ int factor_permutations(const double *X, int n, int p, const int32_t *idx, int R
     for (size_t i = 0; i < (size_t)n * p; ++i)
         if (!std::isfinite(X[i])) return fail(err, errlen, RMG_ERR_INVALID, "model matrix contains non-finite values");
     pd.designs.resize(R);
-    std::vector<double> Xp((size_t)n * p);
-    for (int r = 0; r < R; ++r) {
+    for (int r = 0; r < R; ++r)
         for (int i = 0; i < n; ++i) {
             const int32_t src = idx[i + (size_t)r * n];
             if (src < 0 || src >= n) return fail(err, errlen, RMG_ERR_INVALID, "idx[%d, %d] = %d out of range", i, r, src);
-            for (int j = 0; j < p; ++j) Xp[i + (size_t)j * n] = X[src + (size_t)j * n];
         }
-        const int info = factor_design(Xp.data(), n, p, pd.designs[r]);
-        if (info > 0)
-            return fail(err, errlen, RMG_ERR_SINGULAR, "permutation %d: %s", r + 1, singular_message(info).c_str());
+    // the R factorisations are independent: spread them over the host cores
+    std::vector<int> infos(R, 0);
+    parallel_for(R, [&](int r0, int r1) {
+        std::vector<double> Xp((size_t)n * p);
+        for (int r = r0; r < r1; ++r) {
+            for (int i = 0; i < n; ++i) {
+                const int32_t src = idx[i + (size_t)r * n];
+                for (int j = 0; j < p; ++j) Xp[i + (size_t)j * n] = X[src + (size_t)j * n];
+            }
+            infos[r] = factor_design(Xp.data(), n, p, pd.designs[r]);
+        }
+    });
+    for (int r = 0; r < R; ++r) {   // report the FIRST failing permutation, as a sequential loop would
+        if (infos[r] > 0)
+            return fail(err, errlen, RMG_ERR_SINGULAR, "permutation %d: %s", r + 1, singular_message(infos[r]).c_str());
         pd.all_intercept = pd.all_intercept && pd.designs[r].has_intercept;
     }
     return RMG_OK;
