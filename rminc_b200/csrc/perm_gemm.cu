@@ -7,15 +7,30 @@
 namespace rmg {
 namespace {
 
-constexpr int KC = kPermKC, NT = kPermNT, PITCH = kPermPitch, STAGES = kPermStages;
-constexpr int WARPS_M = 4, WARPS_N = 2, WN = 4;  // warp tile: WM m8-tiles x 4 n8-tiles (32 voxels)
-constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
+constexpr int NT = kPermNT, PITCH = kPermPitch;
+// Subjects per pipeline stage and ring depth depend on the warp tile height: the A chunk of a stage is
+// 4 * (KC/4) * WM * 32 doubles, so WM <= 6 affords 32-subject stages (3 of them), WM = 7..8 keeps 16 (4).
+
+constexpr int WARPS_N = 2, WN = 4;  // warp tile: WM m8-tiles x 4 n8-tiles (32 voxels)
+// Consumer warps along M and CTAs per SM come in two shapes: 4 x 2 warps, one CTA per SM (default),
+// or 2 x 2 warps, two CTAs per SM (RMG_PERM_CTAS=2; same throughput, more L2/DRAM traffic).
 
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+}
+
+// 1/x for a positive, finite, normal x: MUFU.RCP64H seed (~20 bits) + two Newton steps = full
+// double precision for about a quarter of the instructions of an IEEE division.
+__device__ __forceinline__ double rcp_pos(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
 }
 
 struct PermKernelParams {
@@ -32,6 +47,7 @@ struct PermKernelParams {
     const double *Qt;                // [R][n][KP] plain row-major copy of every Q_r (exact path)
     unsigned char *vflag;            // [V] set when some permutation's one-pass rss lost too many digits
     int n_pt, n_kc;
+    int debug_skip;                  // diagnostics only: 1 = skip the statistics epilogue, 2 = skip the MMAs
 };
 
 // ---- K5: one pass over Y for the per-voxel quantities every permutation shares.
@@ -167,35 +183,37 @@ perm_exact_voxels_kernel(PermKernelParams P)
 }
 
 // ---- the GEMM + fused statistics
-// One pipeline stage (KC subjects) of MMAs for this warp.  GUARD: the chunk may contain padding
-// rows (j >= n) whose shared-memory rows hold stale data and must read as 0.
-template <int WM, bool GUARD>
-__device__ __forceinline__ void consume_chunk(double (&acc)[WM][WN][2], const double2 *__restrict__ As,
+// One pipeline stage (KC subjects = KC/4 k-steps) of MMAs for this warp.  The fragments of k-step
+// ks+1 are loaded into a second register set before the MMAs of k-step ks are issued, so the
+// LDS latency is hidden behind tensor-pipe work.  GUARD: the chunk may contain padding rows
+// (j >= n) whose shared-memory rows hold stale data and must read as 0.
+template <int WM, int KC, bool GUARD, bool PREFETCH>
+__device__ __forceinline__ void consume_chunk(double (&acc)[WM][WN][2], const double *__restrict__ As,
                                               const double *__restrict__ Bs, int ksteps, int j0, int q, int n)
 {
+    constexpr int KS = KC / 4;
+    double a[2][WM], b[2][WN];
+    auto load = [&](int buf, int ks) {
 #pragma unroll
-    for (int ks2 = 0; ks2 < KC / 8; ++ks2) {
-        if (!GUARD || ks2 * 2 < ksteps) {
-            double2 a[WM];
+        for (int mt = 0; mt < WM; ++mt) a[buf][mt] = As[(ks * WM + mt) * 32];
+        const bool real = !GUARD || (j0 + ks * 4 + q) < n;
 #pragma unroll
-            for (int mt = 0; mt < WM; ++mt) a[mt] = As[(ks2 * WM + mt) * 32];
+        for (int nt = 0; nt < WN; ++nt) {
+            const double t = Bs[ks * 4 * PITCH + nt * 8];
+            b[buf][nt] = real ? t : 0.0;
+        }
+    };
+    if (PREFETCH) load(0, 0);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int ks = ks2 * 2 + half;
-                if (!GUARD || ks < ksteps) {
-                    double b[WN];
+    for (int ks = 0; ks < KS; ++ks) {
+        if (!GUARD || ks < ksteps) {
+            if (!PREFETCH) load(ks & 1, ks);
+            else if (ks + 1 < KS && (!GUARD || ks + 1 < ksteps)) load((ks + 1) & 1, ks + 1);
 #pragma unroll
-                    for (int nt = 0; nt < WN; ++nt) {
-                        const double t = Bs[ks * 4 * PITCH + nt * 8];
-                        b[nt] = (!GUARD || (j0 + ks * 4 + q) < n) ? t : 0.0;
-                    }
+            for (int mt = 0; mt < WM; ++mt)
 #pragma unroll
-                    for (int mt = 0; mt < WM; ++mt)
-#pragma unroll
-                        for (int nt = 0; nt < WN; ++nt)
-                            dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], half ? a[mt].y : a[mt].x, b[nt]);
-                }
-            }
+                for (int nt = 0; nt < WN; ++nt)
+                    dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[ks & 1][mt], b[ks & 1][nt]);
         }
     }
 }
@@ -203,10 +221,11 @@ __device__ __forceinline__ void consume_chunk(double (&acc)[WM][WN][2], const do
 // KP design columns; INV = 1 when component 0 of every permuted design is the (permutation-
 // invariant) constant column c0 * 1: its e_0 = c0 * sum_j y_j comes from the prepass and only
 // KG = KP - INV components per permutation go through the tensor cores.
-template <int KP, int PG, int INV>
-__global__ void __launch_bounds__((CONSUMER_WARPS + 1) * 32, 1)
+template <int KP, int PG, int INV, int KC, int STAGES, bool PREFETCH, int WARPS_M>
+__global__ void __launch_bounds__((WARPS_M * WARPS_N + 1) * 32, WARPS_M == 4 ? 1 : 2)
 perm_gemm_kernel(PermKernelParams P)
 {
+    constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
     constexpr int KG = KP - INV;
     constexpr int WM = KG * PG;                           // m8-tiles per warp
     constexpr int A_CHUNK = WARPS_M * (KC / 4) * WM * 32; // doubles per stage
@@ -217,6 +236,9 @@ perm_gemm_kernel(PermKernelParams P)
     double *sB = sA + (size_t)STAGES * A_CHUNK;
     uint64_t *full = reinterpret_cast<uint64_t *>(sB + (size_t)STAGES * B_CHUNK);
     uint64_t *empty = full + STAGES;
+    // per-voxel constants of the current voxel tile (|y'|^2, y0, sum y'), staged once per tile so the
+    // epilogue never waits on a chain of dependent global loads
+    double *sv = reinterpret_cast<double *>(empty + STAGES);   // [3][NT]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -267,6 +289,16 @@ perm_gemm_kernel(PermKernelParams P)
 
     for (int64_t vt = blockIdx.x; vt < n_vt; vt += gridDim.x) {
         const int64_t vbase = vt * NT + warp_n * 32 + 2 * q;  // + nt*8 + h
+        const int cbase = warp_n * 32 + 2 * q;                // column of this thread inside the tile
+        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");   // previous tile's epilogues are done
+        if (tid < NT) {
+            const int64_t v = vt * NT + tid;
+            const bool ok = v < P.V;
+            sv[tid] = ok ? P.yy[v] : -1.0;
+            sv[NT + tid] = ok ? P.y0[v] : 0.0;
+            sv[2 * NT + tid] = (ok && INV) ? P.ys[v] : 0.0;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
         for (int pt = 0; pt < P.n_pt; ++pt) {
             double acc[WM][WN][2];
 #pragma unroll
@@ -277,18 +309,20 @@ perm_gemm_kernel(PermKernelParams P)
             for (int kc = 0; kc < P.n_kc; ++kc) {
                 const int j0 = kc * KC;
                 mbar_wait(&full[stage], phase);
-                const double2 *As = reinterpret_cast<const double2 *>(sA + (size_t)stage * A_CHUNK) +
-                                    (size_t)warp_m * (KC / 8) * WM * 32 + lane;
+                const double *As = sA + (size_t)stage * A_CHUNK + (size_t)warp_m * (KC / 4) * WM * 32 + lane;
                 const double *Bs = sB + (size_t)stage * B_CHUNK + q * PITCH + warp_n * 32 + g;
-                if (tail_guard && kc == P.n_kc - 1)
-                    consume_chunk<WM, true>(acc, As, Bs, (n - j0 + 3) / 4, j0, q, n);
+                if (P.debug_skip == 2) {
+                    acc[0][0][0] += As[0] * Bs[0];
+                } else if (tail_guard && kc == P.n_kc - 1)
+                    consume_chunk<WM, KC, true, PREFETCH>(acc, As, Bs, (n - j0 + 3) / 4, j0, q, n);
                 else
-                    consume_chunk<WM, false>(acc, As, Bs, KC / 4, j0, q, n);
+                    consume_chunk<WM, KC, false, PREFETCH>(acc, As, Bs, KC / 4, j0, q, n);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
 
+            if (P.debug_skip == 1) continue;
             // ---- fused epilogue: this thread holds, for PG permutations, the KG GEMM components of
             //      e = Q_r'y for 8 voxels (nt = 0..3, h = 0..1).
 #pragma unroll
@@ -308,15 +342,16 @@ perm_gemm_kernel(PermKernelParams P)
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int64_t v = vbase + nt * 8 + h;
+                            const int col = cbase + nt * 8 + h;
                             double w = -1.0;
                             e0[nt][h] = 0.0;
                             if (rvalid && v < P.V) {
-                                const double yy = P.yy[v];
+                                const double yy = sv[col];
                                 if (yy >= 0.0) {  // yy < 0 marks a voxel outside the mask (global 0 floor)
-                                    const double y0 = P.y0[v];
+                                    const double y0 = sv[NT + col];
                                     double ee = 0.0;
                                     if (INV) {
-                                        const double es = pc.c0 * P.ys[v];      // c0 * sum(y - y0)
+                                        const double es = pc.c0 * sv[2 * NT + col];   // c0 * sum(y - y0)
                                         ee = es * es;
                                         e0[nt][h] = fma(y0, q1[0], es);
                                     }
@@ -328,8 +363,8 @@ perm_gemm_kernel(PermKernelParams P)
                                     const double rss = yy - ee;
                                     if (yy > 0.0 && rss <= kExactThreshold * yy) {
                                         P.vflag[v] = 1;  // model explains ~everything: explicit residuals later
-                                    } else if (rss > 0.0 && isfinite(rss)) {
-                                        w = 1.0 / rss;
+                                    } else if (rss > 1e-290 && rss < 1e290) {
+                                        w = rcp_pos(rss);
                                     } else {
                                         w = 0.0;
                                     }
@@ -374,19 +409,28 @@ perm_gemm_kernel(PermKernelParams P)
     }
 }
 
-template <int KP, int PG, int INV>
-cudaError_t launch_gemm(const PermKernelParams &P, int sm_count, cudaStream_t st)
+template <int KP, int PG, int INV, int KC, int STAGES, bool PREFETCH, int WARPS_M>
+cudaError_t launch_gemm_cfg(const PermKernelParams &P, int sm_count, cudaStream_t st)
 {
+    constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
     constexpr int WM = (KP - INV) * PG;
     constexpr int A_CHUNK = WARPS_M * (KC / 4) * WM * 32;
-    const size_t smem = (size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + 2 * STAGES * 8;
-    auto kern = perm_gemm_kernel<KP, PG, INV>;
+    const size_t smem = (size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + 2 * STAGES * 8 + 3 * NT * 8;
+    static_assert((size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + 2 * STAGES * 8 + 3 * NT * 8 <= 227 * 1024, "ring does not fit");
+    auto kern = perm_gemm_kernel<KP, PG, INV, KC, STAGES, PREFETCH, WARPS_M>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t n_vt = (P.V + NT - 1) / NT;
-    const int grid = (int)std::min<int64_t>(n_vt, sm_count);
+    const int grid = (int)std::min<int64_t>(n_vt, (int64_t)sm_count * (WARPS_M == 4 ? 1 : 2));
     kern<<<grid, (CONSUMER_WARPS + 1) * 32, smem, st>>>(P);
     return cudaGetLastError();
+}
+
+template <int KP, int PG, int INV>
+cudaError_t launch_gemm(const PermKernelParams &P, int sm_count, cudaStream_t st, int warps_m)
+{
+    return warps_m == 4 ? launch_gemm_cfg<KP, PG, INV, 16, 4, false, 4>(P, sm_count, st)
+                        : launch_gemm_cfg<KP, PG, INV, 16, 4, false, 2>(P, sm_count, st);
 }
 
 // permutation groups (of 8) per warp for KG GEMM components per permutation: KG * PG <= 8 m-tiles
@@ -423,6 +467,11 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
     const int KG = KP - INV;
     const int PG = pg_for(KG);
     const int WM = KG * PG;
+    const int KC = 16;
+    // 4 x 2 consumer warps, one CTA per SM.  (2 x 2 warps with two CTAs per SM measured the same
+    // 1.30e3 perms/s but re-reads Y more: 35 GB vs 28.5 GB of DRAM traffic per 64 permutations.)
+    int WARPS_M = 4;
+    if (const char *e = std::getenv("RMG_PERM_CTAS")) WARPS_M = std::atoi(e) == 2 ? 2 : 4;
     const int A_CHUNK = WARPS_M * (KC / 4) * WM * 32;
     const int perms_per_cta = WARPS_M * PG * 8;
     const int n_pt = (R + perms_per_cta - 1) / perms_per_cta;
@@ -454,9 +503,9 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
             for (int j = 0; j < n; ++j) {
                 const int kc = j / KC, jj = j % KC, ks = jj / 4, q = jj % 4;
                 const int lane = g * 4 + q;
-                // [pt][kc] chunk, inside: [warp_m][ks/2][mt][lane][ks%2]
+                // [pt][kc] chunk, inside: [warp_m][ks][mt][lane]  (one MMA A-fragment = 32 consecutive doubles)
                 const size_t off = (((size_t)pt * n_kc + kc) * A_CHUNK) +
-                                   ((((size_t)warp_m * (KC / 8) + ks / 2) * WM + mt) * 32 + lane) * 2 + (ks % 2);
+                                   (((size_t)warp_m * (KC / 4) + ks) * WM + mt) * 32 + lane;
                 Apack[off] = qcol[j];
             }
         }
@@ -494,6 +543,7 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
     P.vflag = reinterpret_cast<unsigned char *>(ws + oVf);
     P.n_pt = n_pt;
     P.n_kc = n_kc;
+    if (const char *e = std::getenv("RMG_PERM_DEBUG_SKIP")) P.debug_skip = std::atoi(e);
     int *any_zero = reinterpret_cast<int *>(ws + oFlag);
     for (int c = 0; c < a.ncols; ++c) P.tcol[c] = a.hcols[c] - (p + 2);
 
@@ -506,8 +556,8 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
     perm_floor_keys_kernel<<<(nk + 255) / 256, 256, 0, st>>>(a.keys, nk, any_zero);
     *launches += 2;
     switch (KP * 2 + INV) {
-#define RMG_PG_CASE(K) case K * 2: e = launch_gemm<K, pg_for(K), 0>(P, sm_count, st); break;
-#define RMG_PG_CASE1(K) case K * 2 + 1: e = launch_gemm<K, pg_for(K - 1), 1>(P, sm_count, st); break;
+#define RMG_PG_CASE(K) case K * 2: e = launch_gemm<K, pg_for(K), 0>(P, sm_count, st, WARPS_M); break;
+#define RMG_PG_CASE1(K) case K * 2 + 1: e = launch_gemm<K, pg_for(K - 1), 1>(P, sm_count, st, WARPS_M); break;
         RMG_PG_CASE(1) RMG_PG_CASE(2) RMG_PG_CASE(3) RMG_PG_CASE(4) RMG_PG_CASE(5) RMG_PG_CASE(6) RMG_PG_CASE(7) RMG_PG_CASE(8)
         RMG_PG_CASE1(2) RMG_PG_CASE1(3) RMG_PG_CASE1(4) RMG_PG_CASE1(5) RMG_PG_CASE1(6) RMG_PG_CASE1(7) RMG_PG_CASE1(8)
 #undef RMG_PG_CASE

@@ -15,8 +15,8 @@
 //               + 1 producer warp.  Persistent CTAs; voxel tiles outer, permutation tiles
 //               inner, so each CTA's 64 x n slab of Y is fetched from HBM once and re-read from
 //               L2 for the other permutation tiles, while A (16 MB at R=1000) lives in L2.
-//   staging   = cp.async.bulk (TMA 1-D) into a 4-stage shared-memory ring guarded by
-//               mbarriers.  A is pre-packed on the host in MMA-fragment order, so one
+//   staging   = cp.async.bulk (TMA 1-D) into a 3-4 stage shared-memory ring (32 or 16 subjects per
+//               stage) guarded by mbarriers.  A is pre-packed on the host in MMA-fragment order, so one
 //               contiguous bulk copy per stage lands it conflict-free; Y rows are copied with
 //               a pitch of 68 doubles (== 4 mod 16), which makes the B-fragment loads
 //               conflict-free without a transpose.
@@ -79,10 +79,8 @@ struct PermGemmArgs {
     int R;
 };
 
-constexpr int kPermKC = 16;       // subjects per pipeline stage
 constexpr int kPermNT = 64;       // voxels per CTA tile
 constexpr int kPermPitch = 68;    // doubles per staged Y row (68 == 4 mod 16: conflict-free B fragments)
-constexpr int kPermStages = 4;
 constexpr int kPermMaxCols = 8;
 
 // per-permutation constants read by the epilogue (KP <= 8)
