@@ -100,6 +100,23 @@ int rmg_lm_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const dou
                       char *err, size_t errlen);
 
 /*
+ * mincAnova / vertexAnova / anatAnova.  Drop-in for per_voxel_anova (src/minc_anova.c:142-304;
+ * R caller R/minc_voxel_statistics.R:557-566) and vertex_anova_loop (src/vertex_modelling.c:178;
+ * R callers R/minc_vertex_statistics.R:314-320, R/minc_anatomy.R anatAnova), whose per-voxel body is
+ * voxel_anova (src/minc_anova.c:4-80): sequential F-statistics, one per model term.
+ *   asgn[p]   model.matrix's "assign" attribute (term index of every design column, 0 = intercept)
+ *   out       V x max(asgn) matrix: F_t = (sum of effects^2 over the term's columns / df_t) / (RSS / (n-p))
+ * Rows outside the mask are 0.0 (src/minc_anova.c:270-275).  The model matrix must have full
+ * column rank (RMG_ERR_INVALID otherwise).
+ */
+int rmg_anova_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *asgn,
+                  const double *mask, double mask_lo, double mask_hi,
+                  double *out, int64_t ldOut, int device, char *err, size_t errlen);
+int rmg_anova_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const double *X, int p,
+                         const int32_t *asgn, const double *dmask, double mask_lo, double mask_hi,
+                         double *dout, int64_t ldOut, int device, void *stream, char *err, size_t errlen);
+
+/*
  * mincRandomize.  Replaces the R loop of R/minc_voxel_statistics.R:1465-1497, which re-runs
  * the whole mincLm call once per permutation.
  *   idx      n x R, 0-based row indices drawn by the caller (R's sample()); permutation r

@@ -57,6 +57,7 @@ def lib():
         _lib.orc_randomize.restype = C.c_int
         _lib.orc_design_probe.restype = C.c_int
         _lib.orc_dnrm2.restype = C.c_double
+        _lib.orc_anova_loop.restype = C.c_int
     return _lib
 
 
@@ -68,7 +69,8 @@ def ref():
     global _ref
     if _ref is None:
         _ref = _load(_REF)
-        for f in ("ref_voxel_lm", "ref_vertex_lm_loop", "ref_minc2_model_lm"):
+        for f in ("ref_voxel_lm", "ref_vertex_lm_loop", "ref_minc2_model_lm", "ref_vertex_anova_loop",
+                  "ref_per_voxel_anova"):
             getattr(_ref, f).restype = C.c_int
     return _ref
 
@@ -222,3 +224,36 @@ def design_probe(X):
     info = lib().orc_design_probe(_p(X), C.c_int(n), C.c_int(p), pivot.ctypes.data_as(_ip), C.byref(rank),
                                   _p(Rm), _p(c))
     return dict(pivot=pivot, rank=rank.value, R=Rm, c=c, info=info)
+
+
+def anova(Y, X, asgn, mask=None, lo=1.0, hi=99999999.0, use_ref=False, sizes=None):
+    """mincAnova / vertexAnova / anatAnova native step: V x nterms F-statistics (voxel_anova,
+    src/minc_anova.c:4-80).  asgn = model.matrix's "assign" attribute.  use_ref: the reference's
+    vertex_anova_loop (no mask) or per_voxel_anova (mask or sizes given)."""
+    Y = _F(Y)
+    X = _F(X)
+    V, n = Y.shape
+    p = X.shape[1]
+    asgn = np.ascontiguousarray(asgn, dtype=np.int32)
+    nterms = int(asgn.max()) if len(asgn) else 0
+    out = np.zeros((V, nterms), order="F")
+    m = None if mask is None else _f64(np.asarray(mask).reshape(-1))
+    if use_ref:
+        err = C.create_string_buffer(512)
+        if m is None and sizes is None:
+            rc = ref().ref_vertex_anova_loop(_p(Y), C.c_int64(V), C.c_int(n), _p(X), C.c_int(p),
+                                             asgn.ctypes.data_as(_ip), _p(out), err, C.c_size_t(512))
+        else:
+            sz = (C.c_int64 * 3)(*[int(s) for s in (sizes or (1, 1, V))])
+            rc = ref().ref_per_voxel_anova(_p(Y), sz, C.c_int(n), _p(X), C.c_int(p), asgn.ctypes.data_as(_ip),
+                                           _p(m) if m is not None else None, C.c_double(lo), C.c_double(hi), _p(out),
+                                           err, C.c_size_t(512))
+        if rc:
+            raise OracleError(err.value.decode())
+        return out
+    info = lib().orc_anova_loop(_p(Y), C.c_int64(V), C.c_int64(V), C.c_int(n), _p(X), C.c_int(p),
+                                asgn.ctypes.data_as(_ip), _p(m) if m is not None else None, C.c_double(lo),
+                                C.c_double(hi), _p(out), C.c_int64(max(V, 1)))
+    if info:
+        raise OracleError(f"element ({info}, {info}) is zero, so the inverse cannot be computed")
+    return out

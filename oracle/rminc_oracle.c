@@ -272,12 +272,10 @@ int orc_dpotri_upper(int p, double *a, int lda)
  * Returns dpotri's info (the reference raises an R error when it is != 0,
  * :551-557).  Scratch is allocated per call, as the reference allocates per
  * voxel (:471, :476). */
-int orc_voxel_lm(const double *y, const double *X, int n, int p, double *coef,
-                 double *stats, int *pivot, int *rank)
+static int orc_voxel_lm_full(const double *y, const double *X, int n, int p, double *coef,
+                             double *stats, int *pivot, int *rank, double *resid, double *effects)
 {
     double *x = (double *)malloc((size_t)n * p * sizeof(double));
-    double *resid = (double *)malloc((size_t)n * sizeof(double));
-    double *effects = (double *)malloc((size_t)n * sizeof(double));
     double *qraux = (double *)malloc((size_t)p * sizeof(double));
     double *work = (double *)malloc((size_t)2 * p * sizeof(double));
     double *se = (double *)malloc((size_t)p * sizeof(double));
@@ -308,8 +306,74 @@ int orc_voxel_lm(const double *y, const double *X, int n, int p, double *coef,
         stats[p + 1] = mss / (mss + rss);
         stats[p + 2] = logLik;
     }
-    free(x); free(resid); free(effects); free(qraux); free(work); free(se);
+    free(x); free(qraux); free(work); free(se);
     return info;
+}
+
+int orc_voxel_lm(const double *y, const double *X, int n, int p, double *coef,
+                 double *stats, int *pivot, int *rank)
+{
+    double *resid = (double *)malloc((size_t)n * sizeof(double));
+    double *effects = (double *)malloc((size_t)n * sizeof(double));
+    int info = orc_voxel_lm_full(y, X, n, p, coef, stats, pivot, rank, resid, effects);
+    free(resid); free(effects);
+    return info;
+}
+
+/* ------------------------------------------------------------ voxel_anova */
+/* src/minc_anova.c:4-80.  asgn[p] is model.matrix's "assign" attribute (0 = intercept).
+ * f[maxasgn-1]: F per term = (sum of effects_i^2 over the term's columns / df_term) / (ssr / (n-p)).
+ * effects = the first p entries of Q'y as dqrls leaves them (indexed by PIVOTED column position
+ * while asgn is indexed by original column -- the reference does not un-pivot). */
+int orc_voxel_anova(const double *y, const double *X, int n, int p, const int32_t *asgn, double *f)
+{
+    double *resid = (double *)malloc((size_t)n * sizeof(double));
+    double *effects = (double *)malloc((size_t)n * sizeof(double));
+    double *coef = (double *)malloc((size_t)p * sizeof(double));
+    double *stats = (double *)malloc((size_t)(p + 3) * sizeof(double));
+    int *pivot = (int *)malloc((size_t)p * sizeof(int));
+    int rank, maxasgn = 0;
+    for (int i = 0; i < p; ++i) if (asgn[i] > maxasgn) maxasgn = asgn[i];
+    maxasgn++;
+    double *ss = (double *)calloc((size_t)maxasgn, sizeof(double));
+    int *df = (int *)calloc((size_t)maxasgn, sizeof(int));
+    int info = orc_voxel_lm_full(y, X, n, p, coef, stats, pivot, &rank, resid, effects);
+    if (info == 0) {
+        int dfr = n - p;
+        for (int i = 0; i < p; ++i) {
+            ss[asgn[i]] += pow(effects[i], 2);
+            df[asgn[i]]++;
+        }
+        double ssr = 0.0;
+        for (int i = 0; i < n; ++i) ssr += pow(resid[i], 2);
+        for (int i = 1; i < maxasgn; ++i) f[i - 1] = (ss[i] / df[i]) / (ssr / dfr);
+    }
+    free(resid); free(effects); free(coef); free(stats); free(pivot); free(ss); free(df);
+    return info;
+}
+
+/* vertex_anova_loop (src/vertex_modelling.c:178-282) and per_voxel_anova (src/minc_anova.c:142-304):
+ * rows outside the mask are 0.0 in every column (:270-275).  out is V x nterms, ld ldOut. */
+int orc_anova_loop(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p,
+                   const int32_t *asgn, const double *mask, double lo, double hi, double *out, int64_t ldOut)
+{
+    int maxasgn = 0, rc = 0;
+    for (int i = 0; i < p; ++i) if (asgn[i] > maxasgn) maxasgn = asgn[i];
+    const int nterms = maxasgn;
+    double *ybuf = (double *)malloc((size_t)n * sizeof(double));
+    double *f = (double *)malloc((size_t)(nterms > 0 ? nterms : 1) * sizeof(double));
+    for (int64_t i = 0; i < V && rc == 0; ++i) {
+        if (mask && !(mask[i] > lo - 0.5 && mask[i] < hi + .5)) {
+            for (int k = 0; k < nterms; ++k) out[i + k * ldOut] = 0.0;
+            continue;
+        }
+        for (int j = 0; j < n; ++j) ybuf[j] = Y[i + ldY * j];
+        rc = orc_voxel_anova(ybuf, X, n, p, asgn, f);
+        if (rc) break;
+        for (int k = 0; k < nterms; ++k) out[i + k * ldOut] = f[k];
+    }
+    free(ybuf); free(f);
+    return rc;
 }
 
 /* --------------------------------------------------------- vertex_lm_loop */

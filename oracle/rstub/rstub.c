@@ -242,6 +242,9 @@ SEXP voxel_lm(SEXP Sy, SEXP Sx, int n, int p, double *coefficients, double *resi
               double *effects, double *work, double *qraux, double *v, int *pivot,
               double *se, double *t);
 SEXP vertex_lm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix);
+SEXP vertex_anova_loop(SEXP data, SEXP Sx, SEXP asgn);
+SEXP per_voxel_anova(SEXP filenames, SEXP Sx, SEXP asgn, SEXP have_mask, SEXP mask, SEXP mask_lower_value,
+                     SEXP mask_upper_value);
 SEXP minc2_model(SEXP filenames, SEXP filenames_right, SEXP mmatrix, SEXP asgn, SEXP have_mask,
                  SEXP mask, SEXP mask_lower_value, SEXP mask_upper_value, SEXP rho,
                  SEXP nresults, SEXP method);
@@ -379,6 +382,80 @@ int ref_minc2_model_lm(const double *Y, const int64_t sizes[3], int n, const dou
     reset_after_call();
     perm_free(files); perm_free(right); perm_free(mm); perm_free(have_mask); perm_free(maskf);
     perm_free(slo); perm_free(shi); perm_free(method);
+    for (int i = 0; i < n; ++i) free(names[i]);
+    free(names);
+    rstub_clear_volumes();
+    return rc;
+}
+
+static SEXP perm_int(const int32_t *src, R_xlen_t n)
+{
+    SEXP s = alloc_obj(INTSXP, n, 1);
+    memcpy(s->data, src, (size_t)n * sizeof(int));
+    return s;
+}
+
+/* the reference's vertex_anova_loop on an in-memory V x n matrix; out is V x (max(asgn)). */
+int ref_vertex_anova_loop(const double *Y, int64_t V, int n, const double *X, int p, const int32_t *asgn,
+                          double *out, char *err, size_t errlen)
+{
+    int nterms = 0;
+    for (int i = 0; i < p; ++i) if (asgn[i] > nterms) nterms = asgn[i];
+    SEXP data = alloc_obj(REALSXP, 0, 1);
+    free(data->data);
+    data->data = (void *)Y; data->len = (R_xlen_t)V * n; data->nrow = (int)V; data->ncol = n;
+    SEXP mm = perm_real(X, (R_xlen_t)n * p, n, p);
+    SEXP as = perm_int(asgn, p);
+    int rc = 0;
+    err_armed = 1;
+    if (setjmp(err_jmp) == 0) {
+        SEXP res = vertex_anova_loop(data, mm, as);
+        memcpy(out, REAL(res), sizeof(double) * (size_t)V * nterms);
+    } else {
+        rc = 1;
+        if (err && errlen) snprintf(err, errlen, "%s", err_msg);
+    }
+    err_armed = 0;
+    reset_after_call();
+    data->data = NULL; perm_free(data); perm_free(mm); perm_free(as);
+    return rc;
+}
+
+/* the reference's per_voxel_anova (slice_loop driver) over registered in-memory volumes. */
+int ref_per_voxel_anova(const double *Y, const int64_t sizes[3], int n, const double *X, int p, const int32_t *asgn,
+                        const double *mask, double lo, double hi, double *out, char *err, size_t errlen)
+{
+    int64_t V = sizes[0] * sizes[1] * sizes[2];
+    int nterms = 0;
+    for (int i = 0; i < p; ++i) if (asgn[i] > nterms) nterms = asgn[i];
+    rstub_clear_volumes();
+    char **names = malloc(sizeof(char *) * n);
+    for (int i = 0; i < n; ++i) {
+        names[i] = malloc(32);
+        snprintf(names[i], 32, "subject_%05d.mnc", i);
+        rstub_register_volume(names[i], Y + (size_t)i * V, sizes);
+    }
+    const char *mask_name = "mask.mnc";
+    if (mask) rstub_register_volume(mask_name, mask, sizes);
+    SEXP files = perm_string((const char *const *)names, n);
+    SEXP mm = perm_real(X, (R_xlen_t)n * p, n, p);
+    SEXP as = perm_int(asgn, p);
+    double hm = mask ? 1.0 : 0.0;
+    SEXP have_mask = perm_real(&hm, 1, 0, -1);
+    SEXP maskf = perm_string(&mask_name, mask ? 1 : 0);
+    SEXP slo = perm_real(&lo, 1, 0, -1), shi = perm_real(&hi, 1, 0, -1);
+    int rc = 0;
+    err_armed = 1;
+    if (setjmp(err_jmp) == 0) {
+        SEXP res = per_voxel_anova(files, mm, as, have_mask, maskf, slo, shi);
+        memcpy(out, REAL(res), sizeof(double) * (size_t)V * nterms);
+    } else {
+        rc = 1;
+        if (err && errlen) snprintf(err, errlen, "%s", err_msg);
+    }
+    err_armed = 0;
+    reset_after_call();
+    perm_free(files); perm_free(mm); perm_free(as); perm_free(have_mask); perm_free(maskf); perm_free(slo); perm_free(shi);
     for (int i = 0; i < n; ++i) free(names[i]);
     free(names);
     rstub_clear_volumes();

@@ -75,3 +75,16 @@ mincRandomize_core <- function(x, R = 500, replace = FALSE, parallel = NULL,
   colnames(dist) <- colnames(lmod)[columns]
   dist
 }
+
+# mincAnova / vertexAnova / anatAnova: the native loops (.Call("per_voxel_anova", ...),
+# R/minc_voxel_statistics.R:557-566; .Call("vertex_anova_loop", ...), R/minc_vertex_statistics.R:314-320)
+# become one routine taking the staged matrix and model.matrix's "assign" attribute.
+per_voxel_anova_gpu <- function(filenames, mmatrix, mask = NULL, mask_min = 1, mask_max = 99999999) {
+  Y <- rmincgpu_stage(filenames)
+  m <- if (is.null(mask)) NULL else as.double(mincGetVolume(mask))
+  .Call("rmincgpu_anova", Y, mmatrix, as.integer(attr(mmatrix, "assign")), m, as.double(mask_min),
+        as.double(mask_max), PACKAGE = "rmincgpu")
+}
+vertex_anova_loop_gpu <- function(data.matrix, mmatrix)
+  .Call("rmincgpu_anova", data.matrix, mmatrix, as.integer(attr(mmatrix, "assign")), NULL, 1, 99999999,
+        PACKAGE = "rmincgpu")

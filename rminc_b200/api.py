@@ -9,6 +9,8 @@ maintainer would add is in rminc_b200/R/ and INTEGRATION.md.
     mincLm(formula, data, subset, mask, maskval, parallel)   R/minc_voxel_statistics.R:751-950
     vertexLm(formula, data, subset, column)                  R/minc_vertex_statistics.R:365-446
     anatLm(formula, data, anat, subset, weights)             R/minc_anatomy.R:1048-1192
+    mincAnova / vertexAnova / anatAnova                      R/minc_voxel_statistics.R:495-693,
+                                                             R/minc_vertex_statistics.R:301-344
     mincRandomize(x, R, alternative, replace, parallel, columns)   :1326-1378, :1441-1531
     thresholds(x, probs)                                     :1577-1581
 
@@ -221,6 +223,73 @@ def anatLm(formula: str, data, anat, subset=None, weights=None, device: int = 0)
              "df": _df_list(n, p), "model-colnames": names, "_Y": Y, "_mask": None,
              "_mask_range": (core.DEFAULT_MASK_LO, core.DEFAULT_MASK_HI), "_rows": rows, "_rhs": rhs, "_lhs": lhs}
     return MincMatrix(out, colnames=_colnames(names), rownames=rownames, attrs=attrs, r_class=("anatModel", "matrix"))
+
+
+# ----------------------------------------------------------------------------- anova
+def _anova_result(out, X, names, assign, data, call, filenames, r_class, rownames=None):
+    n, p = X.shape
+    nterms = max(assign) if assign else 0
+    labels = []
+    for t in range(1, nterms + 1):                       # term labels as attr(terms(formula), "term.labels")
+        cols = [names[i] for i in range(p) if assign[i] == t]
+        labels.append(call["_term_labels"][t - 1] if call.get("_term_labels") else cols[0])
+    dfr = n - p
+    dflist = [[sum(1 for a in assign if a == t), dfr] for t in range(1, nterms + 1)]   # :329-338
+    attrs = {"model": X, "filenames": filenames, "stat-type": ["F"] * nterms, "df": dflist, "data": data,
+             "call": {k: v for k, v in call.items() if not k.startswith("_")}, "model-colnames": names,
+             "assign": list(assign)}
+    return MincMatrix(out, colnames=labels, rownames=rownames, attrs=attrs, r_class=r_class)
+
+
+def _term_labels(rhs):
+    from .formula import parse_rhs
+    _, terms = parse_rhs(rhs)
+    return [":".join(t) for t in terms]
+
+
+def mincAnova(formula: str, data, subset=None, mask=None, maskval=None, reader: Callable = default_reader,
+              device: int = 0) -> MincMatrix:
+    """Sequential (type I) F-statistic of every model term at every voxel
+    (R/minc_voxel_statistics.R:495-693 -> per_voxel_anova, src/minc_anova.c:142-304)."""
+    lhs, rhs = split_formula(formula)
+    rows = _subset_rows(data, subset)
+    X, names, assign = model_matrix(rhs, data, rows)
+    filenames = _column(data, lhs, rows)
+    Y = mincTable(filenames, reader=reader)
+    m = _stage_mask(mask, Y.shape[0], reader)
+    lo, hi = core.mask_range(maskval)
+    out = core.anova_fit(Y, X, assign, mask=m, mask_lo=lo, mask_hi=hi, device=device)
+    call = dict(fn="mincAnova", formula=formula, subset=subset, mask=mask, maskval=maskval, _term_labels=_term_labels(rhs))
+    res = _anova_result(out, X, names, assign, data, call, list(filenames), ("mincMultiDim", "matrix"))
+    res.attrs["likeVolume"] = filenames[0]
+    return res
+
+
+def vertexAnova(formula: str, data, subset=None, column: int = 1, device: int = 0) -> MincMatrix:
+    """R/minc_vertex_statistics.R:301-344 -> vertex_anova_loop (src/vertex_modelling.c:178)."""
+    lhs, rhs = split_formula(formula)
+    rows = _subset_rows(data, subset)
+    X, names, assign = model_matrix(rhs, data, rows)
+    filenames = _column(data, lhs, rows)
+    Y = vertexTable(filenames, column=column)
+    out = core.anova_fit(Y, X, assign, device=device)
+    call = dict(fn="vertexAnova", formula=formula, subset=subset, column=column, _term_labels=_term_labels(rhs))
+    return _anova_result(out, X, names, assign, data, call, list(filenames), ("vertexMultiDim", "matrix"))
+
+
+def anatAnova(formula: str, data, anat, subset=None, device: int = 0) -> MincMatrix:
+    """anatAnova (R/minc_anatomy.R) -> vertex_anova_loop on the structures x subjects matrix."""
+    lhs, rhs = split_formula(formula)
+    rows = _subset_rows(data, subset)
+    X, names, assign = model_matrix(rhs, data, rows)
+    A = np.asarray(anat, dtype=np.float64)
+    if A.ndim != 2 or A.shape[0] != len(data):
+        raise ValueError("anat must be a subjects x structures matrix with one row per row of data")
+    Y = np.asfortranarray(A[rows, :].T)
+    out = core.anova_fit(Y, X, assign, device=device)
+    call = dict(fn="anatAnova", formula=formula, subset=subset, _term_labels=_term_labels(rhs))
+    return _anova_result(out, X, names, assign, data, call, None, ("anatModel", "matrix"),
+                         rownames=list(getattr(anat, "columns", [])) or None)
 
 
 # ----------------------------------------------------------------------------- mincRandomize

@@ -104,6 +104,45 @@ def vertex_lm(Y, X, device=0):
     return out
 
 
+def anova_fit(Y, X, asgn, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, device=0):
+    """mincAnova / vertexAnova / anatAnova native step: V x nterms sequential F-statistics."""
+    Y, X, m = _prep_host(Y, X, mask)
+    V, n = Y.shape
+    p = X.shape[1]
+    asgn = np.ascontiguousarray(asgn, dtype=np.int32)
+    if asgn.shape != (p,):
+        raise ValueError("asgn must have one entry per design column")
+    nterms = int(asgn.max()) if p else 0
+    out = np.empty((V, nterms), order="F")
+    err = _lib.errbuf()
+    ld = max(V, 1)
+    rc = _lib.load().rmg_anova_fit(Y.ctypes.data, V, ld, n, X.ctypes.data, p, asgn.ctypes.data,
+                                   m.ctypes.data if m is not None else None, mask_lo, mask_hi,
+                                   out.ctypes.data, ld, device, err, len(err))
+    _lib.check(rc, err)
+    return out
+
+
+def anova_fit_torch(Yt, X, asgn, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, out=None):
+    """Device-resident anova: Yt (n, V) CUDA tensor -> (nterms, V) CUDA tensor, current stream."""
+    import torch
+    X = _lib.as_f64_fortran(X)
+    n, V = Yt.shape
+    p = X.shape[1]
+    asgn = np.ascontiguousarray(asgn, dtype=np.int32)
+    nterms = int(asgn.max()) if p else 0
+    if out is None:
+        out = torch.empty((nterms, V), dtype=torch.float64, device=Yt.device)
+    mp = mask.data_ptr() if mask is not None else None
+    err = _lib.errbuf()
+    rc = _lib.load().rmg_anova_fit_device(Yt.data_ptr(), V, Yt.stride(0) if n > 1 else max(V, 1), n, X.ctypes.data, p,
+                                          asgn.ctypes.data, mp, mask_lo, mask_hi, out.data_ptr(),
+                                          out.stride(0) if nterms > 1 else max(V, 1), Yt.device.index or 0,
+                                          _torch_stream(Yt), err, len(err))
+    _lib.check(rc, err)
+    return out
+
+
 def _prep_perm(idx, n, cols):
     idx = np.asfortranarray(idx, dtype=np.int32)
     if idx.ndim != 2 or idx.shape[0] != n:

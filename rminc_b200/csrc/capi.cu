@@ -83,11 +83,30 @@ void fill_dev_design(const Design &D, DevDesign &dd)
     dd.pm1 = (double)(D.p - 1);
     dd.loglik_c = std::log(2 * M_PI) + 1 - std::log((double)D.n);
     dd.mhalf_n = -.5 * D.n;
+    dd.mode = 0;
+    dd.nterms = 0;
+    dd.ncol_out = 2 * D.p + 3;
     for (int i = 0; i < D.p; ++i) {
         dd.q1[i] = D.q1[i];
         dd.ct[i] = D.ct[i];
         for (int j = 0; j < D.p; ++j) dd.Rinv[i * kMaxPDev + j] = D.Rinv[i + (size_t)j * D.p];
     }
+}
+
+// voxel_anova (src/minc_anova.c:4-80): effects[i] (pivoted position i) is booked under asgn[i].
+void set_anova_mode(const Design &D, const int32_t *asgn, DevDesign &dd)
+{
+    int nterms = 0;
+    for (int i = 0; i < D.p; ++i) nterms = std::max(nterms, (int)asgn[i]);
+    dd.mode = 1;
+    dd.nterms = nterms;
+    dd.ncol_out = nterms;
+    std::vector<int> df(nterms + 1, 0);
+    for (int i = 0; i < D.p; ++i) {
+        dd.term[i] = asgn[i];
+        df[asgn[i]]++;
+    }
+    for (int t = 0; t <= nterms; ++t) dd.inv_df[t] = df[t] ? 1.0 / df[t] : 0.0;   // 0/0 -> NaN as the reference's ss/df
 }
 
 std::vector<double> make_qt(const Design &D, int KP)
@@ -118,7 +137,8 @@ namespace {
 // make their stream wait on it.
 struct CachedDesign {
     int device = -1;
-    std::vector<double> X;   // n x p, the key
+    std::vector<double> X;   // n x p, the key ...
+    std::vector<int32_t> asgn;   // ... together with the term assignment (empty = lm epilogue)
     Design D;
     DevDesign *dd = nullptr;
     double *qt = nullptr;
@@ -144,14 +164,16 @@ uint64_t g_cache_tick = 0;
 constexpr size_t kCacheEntries = 16;
 
 // Looks up (or builds) the cached design for X on the current device.  rc != RMG_OK on error.
-std::shared_ptr<CachedDesign> design_cache_get(int device, const double *X, int n, int p, int &rc, char *err,
-                                               size_t errlen)
+std::shared_ptr<CachedDesign> design_cache_get(int device, const double *X, int n, int p, const int32_t *asgn,
+                                               int &rc, char *err, size_t errlen)
 {
     const size_t cnt = (size_t)n * p;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         for (auto &e : g_cache)
-            if (e->device == device && e->D.n == n && e->D.p == p && std::memcmp(e->X.data(), X, cnt * 8) == 0) {
+            if (e->device == device && e->D.n == n && e->D.p == p && std::memcmp(e->X.data(), X, cnt * 8) == 0 &&
+                e->asgn.size() == (asgn ? (size_t)p : 0) &&
+                (!asgn || std::memcmp(e->asgn.data(), asgn, (size_t)p * sizeof(int32_t)) == 0)) {
                 e->last_use = ++g_cache_tick;
                 rc = RMG_OK;
                 return e;
@@ -163,6 +185,20 @@ std::shared_ptr<CachedDesign> design_cache_get(int device, const double *X, int 
     e->X.assign(X, X + cnt);
     DevDesign h;
     fill_dev_design(e->D, h);
+    if (asgn) {
+        for (int i = 0; i < p; ++i)
+            if (asgn[i] < 0 || asgn[i] > p) {
+                rc = fail(err, errlen, RMG_ERR_INVALID, "asgn[%d] = %d out of range", i, asgn[i]);
+                return nullptr;
+            }
+        if (e->D.k < p) {
+            rc = fail(err, errlen, RMG_ERR_INVALID,
+                      "rank-deficient design (rank %d < %d columns): the anova path needs a full-rank model matrix", e->D.k, p);
+            return nullptr;
+        }
+        e->asgn.assign(asgn, asgn + p);
+        set_anova_mode(e->D, asgn, h);
+    }
     const std::vector<double> qt_h = make_qt(e->D, lm_padded_p(p));
     cudaStream_t up = nullptr;
     cudaError_t ce = cudaMalloc(reinterpret_cast<void **>(&e->dd), sizeof(DevDesign));
@@ -247,14 +283,14 @@ int rmg_design_factor(const double *X, int n, int p, int32_t *pivot, int *rank, 
     return RMG_OK;
 }
 
-int rmg_lm_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const double *X, int p,
-                      const double *dmask, double mask_lo, double mask_hi, double *dout, int64_t ldOut,
-                      int device, void *stream, char *err, size_t errlen)
+static int fit_device_impl(const double *dY, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *asgn,
+                           const double *dmask, double mask_lo, double mask_hi, double *dout, int64_t ldOut,
+                           int device, void *stream, char *err, size_t errlen)
 {
     int rc = check_fit_args(dY, V, ldY, n, X, p, dout, ldOut, err, errlen);
     if (rc) return rc;
     if ((rc = select_device(device, err, errlen))) return rc;
-    std::shared_ptr<CachedDesign> cd = design_cache_get(device, X, n, p, rc, err, errlen);
+    std::shared_ptr<CachedDesign> cd = design_cache_get(device, X, n, p, asgn, rc, err, errlen);
     if (!cd) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LmScratch scr;
@@ -262,6 +298,8 @@ int rmg_lm_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const dou
     {
         RMG_CUDA(cudaStreamWaitEvent(st, cd->ready, 0));
         LmArgs a{dY, V, ldY, n, p, cd->qt, cd->dd, dmask, mask_lo, mask_hi, dout, ldOut};
+        a.ncol_out = asgn ? (int)*std::max_element(cd->asgn.begin(), cd->asgn.end()) : 2 * p + 3;
+        if (a.ncol_out == 0) goto cleanup;   // intercept-only anova: no terms, nothing to write
         RMG_CUDA(launch_lm_fit(a, plan_from_env(device), scr, st, &info));
         g_launch_count += info.launches;
         g_last_fit_variant = info.used_tma ? 1 : 2;
@@ -271,8 +309,24 @@ cleanup:
     return rc;
 }
 
-int rmg_lm_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
-               double mask_lo, double mask_hi, double *out, int64_t ldOut, int device, char *err, size_t errlen)
+int rmg_lm_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const double *X, int p,
+                      const double *dmask, double mask_lo, double mask_hi, double *dout, int64_t ldOut,
+                      int device, void *stream, char *err, size_t errlen)
+{
+    return fit_device_impl(dY, V, ldY, n, X, p, nullptr, dmask, mask_lo, mask_hi, dout, ldOut, device, stream, err, errlen);
+}
+
+int rmg_anova_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *asgn,
+                         const double *dmask, double mask_lo, double mask_hi, double *dout, int64_t ldOut,
+                         int device, void *stream, char *err, size_t errlen)
+{
+    if (!asgn) return fail(err, errlen, RMG_ERR_INVALID, "asgn is NULL");
+    return fit_device_impl(dY, V, ldY, n, X, p, asgn, dmask, mask_lo, mask_hi, dout, ldOut, device, stream, err, errlen);
+}
+
+static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *asgn,
+                         const double *mask, double mask_lo, double mask_hi, double *out, int64_t ldOut, int device,
+                         char *err, size_t errlen)
 {
     int rc = check_fit_args(Y, V, ldY, n, X, p, out, ldOut, err, errlen);
     if (rc) return rc;
@@ -281,12 +335,12 @@ int rmg_lm_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *X, 
         if (rmg_device_count() <= 0 && (rc = factor_or_fail(X, n, p, probe, err, errlen))) return rc;
     }
     if ((rc = select_device(device, err, errlen))) return rc;
-    std::shared_ptr<CachedDesign> cd = design_cache_get(device, X, n, p, rc, err, errlen);
+    std::shared_ptr<CachedDesign> cd = design_cache_get(device, X, n, p, asgn, rc, err, errlen);
     if (!cd) return rc;
     g_last_kernel_ms = 0.0;
-    if (V == 0) return RMG_OK;
+    const int ncol = asgn ? (int)*std::max_element(cd->asgn.begin(), cd->asgn.end()) : 2 * p + 3;
+    if (V == 0 || ncol == 0) return RMG_OK;
 
-    const int ncol = 2 * p + 3;
     // Voxel chunks of ~1 GiB of Y (measured on B200/PCIe5: 256 MiB chunks reach 61 % of the pinned
     // copy rate, 1 GiB chunks 98 %), multiples of 1024 voxels so TMA tiles stay aligned.
     int64_t CV = (int64_t)(1024.0 * 1024 * 1024 / (8.0 * n));
@@ -320,6 +374,7 @@ int rmg_lm_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *X, 
                                        cudaMemcpyHostToDevice, st[b]));
             if (mask) RMG_CUDA(cudaMemcpyAsync(dM[b], mask + v0, (size_t)cv * 8, cudaMemcpyHostToDevice, st[b]));
             LmArgs a{dY[b], cv, ldc, n, p, cd->qt, cd->dd, mask ? dM[b] : nullptr, mask_lo, mask_hi, dO[b], ldc};
+            a.ncol_out = ncol;
             LmLaunchInfo info;
             RMG_CUDA(cudaEventRecord(ev0[c], st[b]));
             RMG_CUDA(launch_lm_fit(a, plan, scr[b], st[b], &info));
@@ -354,6 +409,20 @@ cleanup:
     for (auto e : ev1) if (e) cudaEventDestroy(e);
     if (rc != RMG_OK) cudaGetLastError();
     return rc;
+}
+
+int rmg_lm_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
+               double mask_lo, double mask_hi, double *out, int64_t ldOut, int device, char *err, size_t errlen)
+{
+    return fit_host_impl(Y, V, ldY, n, X, p, nullptr, mask, mask_lo, mask_hi, out, ldOut, device, err, errlen);
+}
+
+int rmg_anova_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *asgn,
+                  const double *mask, double mask_lo, double mask_hi, double *out, int64_t ldOut, int device,
+                  char *err, size_t errlen)
+{
+    if (!asgn) return fail(err, errlen, RMG_ERR_INVALID, "asgn is NULL");
+    return fit_host_impl(Y, V, ldY, n, X, p, asgn, mask, mask_lo, mask_hi, out, ldOut, device, err, errlen);
 }
 
 int rmg_vertex_lm(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, double *out,

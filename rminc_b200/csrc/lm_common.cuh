@@ -21,6 +21,10 @@ struct DevDesign {
     double q1[kMaxPDev];    // Q'1
     double ct[kMaxPDev];    // diag((R'R)^-1), un-pivoted as the reference un-pivots se (:560-564)
     double Rinv[kMaxPDev * kMaxPDev];  // row-major: Rinv[i*kMaxPDev + j], upper triangle, k x k
+    // anova epilogue (voxel_anova, src/minc_anova.c:4-80): mode 1 writes nterms F-statistics
+    int mode, nterms, ncol_out, pad_;   // ncol_out = 2p+3 (lm) or nterms (anova)
+    int term[kMaxPDev];     // asgn[i]: term of the effect at (pivoted) position i; 0 = intercept
+    double inv_df[kMaxPDev + 1];  // 1 / (number of columns of term t)
 };
 
 // Per-CTA shared-memory copy of the k-dependent part, padded to the kernel's KP.
@@ -31,6 +35,9 @@ struct SmemDesign {
     double Rinv[KP * KP];   // row-major KP x KP
     double gap, inv_n, rdf, pm1, loglik_c, mhalf_n;
     int n, p, k, shift;
+    int mode, nterms, ncol_out, pad_;
+    int term[KP];
+    double inv_df[KP + 1];
 };
 
 template <int KP>
@@ -40,12 +47,15 @@ __device__ __forceinline__ void load_design_to_smem(SmemDesign<KP> &s, const Dev
     for (int i = tid; i < KP; i += nthreads) {
         s.q1[i] = d->q1[i];
         s.ct[i] = d->ct[i];
+        s.term[i] = d->term[i];
     }
+    for (int i = tid; i < KP + 1; i += nthreads) s.inv_df[i] = d->inv_df[i];
     for (int i = tid; i < KP * KP; i += nthreads) s.Rinv[i] = d->Rinv[(i / KP) * kMaxPDev + (i % KP)];
     if (tid == 0) {
         s.gap = d->gap; s.inv_n = d->inv_n; s.rdf = d->rdf; s.pm1 = d->pm1;
         s.loglik_c = d->loglik_c; s.mhalf_n = d->mhalf_n;
         s.n = d->n; s.p = d->p; s.k = d->k; s.shift = d->shift;
+        s.mode = d->mode; s.nterms = d->nterms; s.ncol_out = d->ncol_out;
     }
 }
 
@@ -100,6 +110,22 @@ __device__ __forceinline__ void finish_voxel(const VoxelSums<KP> &v, double rss,
 {
     const int p = d.p;
     const double resvar = rss / d.rdf;                       // :537
+    if (d.mode == 1) {
+        // voxel_anova: F_t = (sum of effects^2 over the term's columns / df_t) / (ssr / (n-p))
+        double e2[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const double ek = fma(v.y0, d.q1[k], v.e[k]);
+            e2[k] = ek * ek;
+        }
+        for (int t = 1; t <= d.nterms; ++t) {
+            double ss = 0.0;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) ss += (d.term[k] == t) ? e2[k] : 0.0;
+            out[(int64_t)(t - 1) * ld] = (ss * d.inv_df[t]) / resvar;
+        }
+        return;
+    }
     out[0] = (mss / d.pm1) / resvar;                         // :542
     out[ld] = mss / (mss + rss);                             // :572
     out[(int64_t)(2 * p + 2) * ld] = d.mhalf_n * (d.loglik_c + log(rss));  // :527
@@ -132,6 +158,25 @@ __device__ __forceinline__ void finish_pair(const VoxelSums<KP> &a, double rssa,
         *reinterpret_cast<double2 *>(out + (int64_t)c * ld) = make_double2(oka ? x : 0.0, okb ? y : 0.0);
     };
     const double rva = rssa / d.rdf, rvb = rssb / d.rdf;
+    if (d.mode == 1) {
+        double ea2[KP], eb2[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const double x = fma(a.y0, d.q1[k], a.e[k]), y = fma(b.y0, d.q1[k], b.e[k]);
+            ea2[k] = x * x;
+            eb2[k] = y * y;
+        }
+        for (int t = 1; t <= d.nterms; ++t) {
+            double sa = 0.0, sb = 0.0;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                sa += (d.term[k] == t) ? ea2[k] : 0.0;
+                sb += (d.term[k] == t) ? eb2[k] : 0.0;
+            }
+            put(t - 1, (sa * d.inv_df[t]) / rva, (sb * d.inv_df[t]) / rvb);
+        }
+        return;
+    }
     put(0, (mssa / d.pm1) / rva, (mssb / d.pm1) / rvb);
     put(1, mssa / (mssa + rssa), mssb / (mssb + rssb));
     put(2 * p + 2, d.mhalf_n * (d.loglik_c + log(rssa)), d.mhalf_n * (d.loglik_c + log(rssb)));
@@ -157,9 +202,9 @@ __device__ __forceinline__ void finish_pair(const VoxelSums<KP> &a, double rssa,
 }
 
 template <int KP>
-__device__ __forceinline__ void zero_row(int p, double *__restrict__ out, int64_t ld)
+__device__ __forceinline__ void zero_row(int ncol, double *__restrict__ out, int64_t ld)
 {
-    for (int c = 0; c < 2 * p + 3; ++c) out[(int64_t)c * ld] = 0.0;
+    for (int c = 0; c < ncol; ++c) out[(int64_t)c * ld] = 0.0;
 }
 
 __device__ __forceinline__ bool mask_selects(double m, double lo, double hi)

@@ -240,8 +240,8 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
         }
         double *o = a.out + v;
         if (flags && !flags[t]) {
-            if (in0) zero_row<KP>(sd.p, o, a.ldOut);
-            if (in1) zero_row<KP>(sd.p, o + 1, a.ldOut);
+            if (in0) zero_row<KP>(sd.ncol_out, o, a.ldOut);
+            if (in1) zero_row<KP>(sd.ncol_out, o + 1, a.ldOut);
             continue;
         }
         VoxelSums<KP> s0, s1;
@@ -277,11 +277,11 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
         } else {
             if (in0) {
                 if (act0) finish_voxel<KP>(s0, rss0, mss0, sd, o, a.ldOut);
-                else zero_row<KP>(sd.p, o, a.ldOut);
+                else zero_row<KP>(sd.ncol_out, o, a.ldOut);
             }
             if (in1) {
                 if (act1) finish_voxel<KP>(s1, rss1, mss1, sd, o + 1, a.ldOut);
-                else zero_row<KP>(sd.p, o + 1, a.ldOut);
+                else zero_row<KP>(sd.ncol_out, o + 1, a.ldOut);
             }
         }
     }
@@ -415,7 +415,7 @@ lm_fit_ldg_kernel(LmArgs a, int JT)
         if (!in[i]) continue;
         double *o = a.out + v + i;
         if (!act[i]) {
-            zero_row<KP>(sd.p, o, a.ldOut);
+            zero_row<KP>(sd.ncol_out, o, a.ldOut);
             continue;
         }
         double rss = sum[i].yy - sumsq_e(sum[i]), mss = mss_from_e(sum[i], sd);
@@ -577,7 +577,7 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
         mask_count_kernel<<<nb, kCompactBlock, 0, st>>>(a.mask, a.V, a.mask_lo, a.mask_hi, counts);
         mask_scan_kernel<<<1, 1024, 0, st>>>(counts, nb, n_pairs);
         mask_compact_kernel<<<nb, kCompactBlock, 0, st>>>(a.mask, a.V, a.mask_lo, a.mask_hi, counts, list, a.out, a.ldOut,
-                                                           2 * a.p + 3);
+                                                           a.ncol_out);
         if (info) info->launches += 3;
         ac.pair_list = list;
         ac.n_pairs = n_pairs;
@@ -605,6 +605,7 @@ cudaError_t launch_lm_fit(const LmArgs &a_in, const LmPlan &plan, LmScratch &scr
     if (a_in.V <= 0) return cudaSuccess;
     LmArgs a = a_in;
     a.out_vec2 = ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && a.ldOut % 2 == 0) ? 1 : 0;
+    if (a.ncol_out <= 0) a.ncol_out = 2 * a.p + 3;
     switch (round_up_kp(a.p)) {
 #define RMG_CASE(K) case K: return launch_kp<K>(a, plan, scr, st, info);
         RMG_CASE(1) RMG_CASE(2) RMG_CASE(3) RMG_CASE(4) RMG_CASE(5) RMG_CASE(6) RMG_CASE(7) RMG_CASE(8)

@@ -12,6 +12,7 @@
  *                            vertexLm / anatLm only change the routine name
  *   rmincgpu_lm              minc2_model(method = "lm") with the volumes already staged
  *   rmincgpu_randomize       the mincRandomize loop (R/minc_voxel_statistics.R:1465-1497)
+ *   rmincgpu_anova           per_voxel_anova / vertex_anova_loop (src/minc_anova.c:142, src/vertex_modelling.c:178)
  */
 #include <R.h>
 #include <Rinternals.h>
@@ -97,10 +98,30 @@ SEXP rmincgpu_randomize(SEXP Y, SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP m
     return out;
 }
 
+/* per_voxel_anova / vertex_anova_loop replacement: V x max(asgn) F-statistics. */
+SEXP rmincgpu_anova(SEXP Y, SEXP mmatrix, SEXP asgn, SEXP mask, SEXP mask_lower, SEXP mask_upper)
+{
+    if (!Rf_isReal(Y) || !Rf_isReal(mmatrix) || !Rf_isInteger(asgn)) Rf_error("Y/mmatrix must be double, asgn integer");
+    const R_xlen_t V = Rf_nrows(Y);
+    const int n = Rf_ncols(Y), p = Rf_ncols(mmatrix);
+    if (Rf_nrows(mmatrix) != n || LENGTH(asgn) != p) Rf_error("model matrix / assign do not match the data");
+    int nterms = 0;
+    for (int i = 0; i < p; ++i) if (INTEGER(asgn)[i] > nterms) nterms = INTEGER(asgn)[i];
+    const double *m = mask_or_null(mask, V);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, nterms));
+    char err[512] = "";
+    int rc = rmg_anova_fit(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, INTEGER(asgn), m, Rf_asReal(mask_lower),
+                           Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, 0, err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
 static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_vertex_lm_loop", (DL_FUNC)&rmincgpu_vertex_lm_loop, 3},
     {"rmincgpu_lm", (DL_FUNC)&rmincgpu_lm, 6},
     {"rmincgpu_randomize", (DL_FUNC)&rmincgpu_randomize, 9},
+    {"rmincgpu_anova", (DL_FUNC)&rmincgpu_anova, 6},
     {NULL, NULL, 0}};
 
 void R_init_rmincgpu(DllInfo *dll)

@@ -47,6 +47,17 @@ def main():
     Y = np.asfortranarray(rng.normal(0, 1, (V, n)))
     out["C_X"], out["C_Y"] = X, Y
     out["C_out"] = O.vertex_lm_loop(Y, X, use_ref=True)
+    # case D: per_voxel_anova (slice loop + mask), 3-level factor * covariate
+    n, dims = 18, (3, 4, 5)
+    V = int(np.prod(dims))
+    g3 = np.array(list("abc" * 6))
+    age = np.round(rng.normal(60, 10, n), 1)
+    X = np.column_stack([np.ones(n), g3 == "b", g3 == "c", age, (g3 == "b") * age, (g3 == "c") * age]).astype(float)
+    asgn = np.array([0, 1, 1, 2, 3, 3], dtype=np.int32)
+    Y = np.asfortranarray(rng.normal(1.0, 0.3, (V, n)))
+    mask = (rng.random(V) > 0.3).astype(float)
+    out["D_X"], out["D_Y"], out["D_asgn"], out["D_mask"] = X, Y, asgn, mask
+    out["D_out"] = O.anova(Y, X, asgn, mask=mask, use_ref=True, sizes=dims)
     np.savez_compressed(os.path.join(os.path.dirname(__file__), "ref_golden.npz"), **out)
     print("wrote ref_golden.npz:", {k: v.shape for k, v in out.items()})
 

@@ -27,6 +27,10 @@ def api(request, monkeypatch, oracle, lib):
                       n_gpus=None):
             return oracle.randomize(Y, X, idx, cols, two_sided=two_sided, mask=mask, lo=mask_lo, hi=mask_hi)
 
+        def anova_fit(Y, X, asgn, mask=None, mask_lo=1.0, mask_hi=99999999.0, device=0):
+            return oracle.anova(Y, X, asgn, mask=mask, lo=mask_lo, hi=mask_hi)
+
+        monkeypatch.setattr(core, "anova_fit", anova_fit)
         monkeypatch.setattr(core, "lm_fit", lm_fit)
         monkeypatch.setattr(core, "vertex_lm", vertex_lm)
         monkeypatch.setattr(core, "randomize", randomize)
@@ -177,3 +181,46 @@ def test_mincRandomize_and_thresholds(api, study):
     assert np.asarray(one["randomization_dist"]).shape == (5, 1) and (np.asarray(one["randomization_dist"]) >= 0).all()
     with pytest.raises(ValueError):
         api.mincRandomize(vs, R=3, alternative="less")
+
+
+def test_mincAnova_vertexAnova_anatAnova(api, study, tmp_path):
+    """tests/testthat/test_mincAnova.R:22-109 pattern: F per term at one voxel == anova(lm(...))."""
+    gf, maskfile, Y = study
+    res = api.mincAnova("jacobians ~ Sex*Scale", gf, mask=maskfile)
+    assert res.colnames == ["Sex", "Scale", "Sex:Scale"] and res.shape == (1000, 3)
+    assert res.attrs["stat-type"] == ["F", "F", "F"] and res.attrs["df"] == [[1, 6], [1, 6], [1, 6]]
+    m, s = (gf.Sex == "M").astype(float).values, gf.Scale.values
+    X = np.column_stack([np.ones(10), m, s, m * s])
+
+    def rss(Xs, y):
+        b = np.linalg.lstsq(Xs, y, rcond=None)[0]
+        r = y - Xs @ b
+        return r @ r
+
+    inside = np.load(maskfile).reshape(-1) > 0.5
+    v = int(np.flatnonzero(inside)[7])
+    r = [rss(X[:, :c], Y[v]) for c in (1, 2, 3, 4)]
+    want = [(r[i] - r[i + 1]) / (r[3] / 6) for i in range(3)]
+    assert np.asarray(res)[v] == pytest.approx(want, rel=1e-8)
+    assert (np.asarray(res)[~inside] == 0).all()
+    res3 = api.mincAnova("jacobians ~ Grp", gf)
+    assert res3.colnames == ["Grp"] and res3.attrs["df"] == [[2, 7]]
+    Xg = np.column_stack([np.ones(10), gf.Grp == "b", gf.Grp == "c"]).astype(float)
+    assert np.asarray(res3)[3, 0] == pytest.approx(((rss(Xg[:, :1], Y[3]) - rss(Xg, Y[3])) / 2) / (rss(Xg, Y[3]) / 7), rel=1e-8)
+    # vertexAnova / anatAnova share the native loop
+    rng = np.random.default_rng(9)
+    anat = pd.DataFrame(rng.normal(10, 1, (10, 4)) + 0.5 * m[:, None], columns=list("ABCD"))
+    ra = api.anatAnova("~ Sex + Scale", gf, anat)
+    assert ra.rownames == list("ABCD") and ra.colnames == ["Sex", "Scale"] and ra.r_class == ("anatModel", "matrix")
+    X2 = np.column_stack([np.ones(10), m, s])
+    y = anat.values[:, 1]
+    assert np.asarray(ra)[1] == pytest.approx([(rss(X2[:, :1], y) - rss(X2[:, :2], y)) / (rss(X2, y) / 7),
+                                               (rss(X2[:, :2], y) - rss(X2, y)) / (rss(X2, y) / 7)], rel=1e-8)
+    files = []
+    for i in range(10):
+        f = tmp_path / f"v{i}.txt"
+        np.savetxt(f, anat.values[i])
+        files.append(str(f))
+    gv = gf.assign(thick=files)
+    rv = api.vertexAnova("thick ~ Sex + Scale", gv)
+    assert np.array_equal(np.asarray(rv), np.asarray(ra)) and rv.r_class == ("vertexMultiDim", "matrix")

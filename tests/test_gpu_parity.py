@@ -264,3 +264,41 @@ def test_randomize_device_entry_point(core, oracle):
     d = core.randomize_torch(Yt, X, idx, [4, 5], two_sided=True, mask=mt)
     torch.cuda.synchronize()
     np.testing.assert_allclose(d.cpu().numpy().T, oracle.randomize(Y, X, idx, [4, 5], mask=mask), rtol=RTOL)
+
+
+# ------------------------------------------------------------------ anova epilogue (scope row f-1)
+def test_anova_matches_oracle(core, oracle, variant):
+    g = np.load(os.path.join(GOLD, "ref_golden.npz"))
+    out = core.anova_fit(g["D_Y"], g["D_X"], g["D_asgn"], mask=g["D_mask"])
+    assert_rows_match(out, g["D_out"], RTOL, "anova golden")
+    assert (out[g["D_mask"] < 0.5] == 0).all()
+    rng = np.random.default_rng(31)
+    n, V = 60, 5000
+    grp = np.arange(n) % 3
+    age = np.round(rng.normal(60, 10, n), 1)
+    X = np.column_stack([np.ones(n), grp == 1, grp == 2, age, (grp == 1) * age, (grp == 2) * age]).astype(float)
+    asgn = [0, 1, 1, 2, 3, 3]
+    Y = np.asfortranarray(30000 + 50 * rng.standard_normal((V, n)) + 30 * np.outer(rng.random(V), X[:, 1]))
+    mask = (rng.random(V) > 0.3).astype(float)
+    assert_rows_match(core.anova_fit(Y, X, asgn, mask=mask), oracle.anova(Y, X, asgn, mask=mask), RTOL, "anova")
+    assert_rows_match(core.anova_fit(Y, X, asgn), oracle.anova(Y, X, asgn), RTOL, "anova nomask")
+    # single-term and intercept-free designs; one term spanning all columns
+    X2 = np.column_stack([np.ones(n), age])
+    assert_rows_match(core.anova_fit(Y, X2, [0, 1]), oracle.anova(Y, X2, [0, 1]), RTOL, "anova p=2")
+    X3 = np.column_stack([grp == 0, grp == 1, grp == 2]).astype(float)
+    assert_rows_match(core.anova_fit(Y, X3, [1, 1, 1]), oracle.anova(Y, X3, [1, 1, 1]), RTOL, "anova no intercept")
+    with pytest.raises(core.RmincGpuError, match="full-rank"):
+        core.anova_fit(Y, np.column_stack([np.ones(n), grp == 1, grp != 1, age]).astype(float), [0, 1, 1, 2])
+
+
+def test_anova_device_entry_point(core, oracle):
+    import torch
+    rng = np.random.default_rng(32)
+    n, V = 40, 4096
+    X = design_cov(n, 5)
+    asgn = [0, 1, 2, 2, 3]
+    Y = rng.normal(1, 0.5, (V, n))
+    Yt = torch.from_numpy(np.ascontiguousarray(Y.T)).cuda()
+    out = core.anova_fit_torch(Yt, X, asgn)
+    torch.cuda.synchronize()
+    assert_rows_match(out.cpu().numpy().T, oracle.anova(Y, X, asgn), RTOL, "anova device")

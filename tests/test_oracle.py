@@ -221,3 +221,35 @@ def test_randomize_semantics(oracle):
     d0 = oracle.randomize(Y, X, ident, cols, two_sided=True, mask=mask)
     base = oracle.minc2_model_lm(Y, (4, 5, 5), X, mask=mask)
     assert np.array_equal(d0[0], np.abs(base[:, cols]).max(axis=0))
+
+
+def test_anova_restatement(oracle):
+    """voxel_anova (src/minc_anova.c:4-80): sequential F per term; equals the reference's object
+    code bit for bit and the nested-model (type I) identity F_t = ((RSS_{t-1}-RSS_t)/df_t)/(RSS/(n-p))."""
+    rng = np.random.default_rng(21)
+    n, V = 30, 60
+    g = np.array(list("abc" * 10))
+    age = np.round(rng.normal(60, 10, n), 1)
+    X = np.column_stack([np.ones(n), g == "b", g == "c", age, (g == "b") * age, (g == "c") * age]).astype(float)
+    asgn = [0, 1, 1, 2, 3, 3]
+    Y = rng.normal(2, 1, (V, n))
+    f = oracle.anova(Y, X, asgn)
+    assert f.shape == (V, 3)
+
+    def rss(Xs, y):
+        b = np.linalg.lstsq(Xs, y, rcond=None)[0]
+        r = y - Xs @ b
+        return r @ r
+
+    for v in (0, 17, 59):
+        r = [rss(X[:, :c], Y[v]) for c in (1, 3, 4, 6)]
+        want = [((r[i] - r[i + 1]) / d) / (r[3] / (n - 6)) for i, d in enumerate((2, 1, 2))]
+        assert f[v] == pytest.approx(want, rel=1e-9)
+    mask = (rng.random(V) > 0.4) * rng.integers(1, 3, V).astype(float)
+    fm = oracle.anova(Y, X, asgn, mask=mask, lo=2, hi=2)
+    assert np.array_equal(fm[mask == 2], f[mask == 2]) and (fm[mask != 2] == 0).all()
+    if oracle.have_ref():
+        assert np.array_equal(oracle.anova(Y, X, asgn, use_ref=True), f)                          # vertex_anova_loop
+        assert np.array_equal(oracle.anova(Y, X, asgn, mask=mask, lo=2, hi=2, use_ref=True, sizes=(3, 4, 5)), fm)  # per_voxel_anova
+    g = np.load(os.path.join(GOLD, "ref_golden.npz"))
+    assert np.array_equal(oracle.anova(g["D_Y"], g["D_X"], g["D_asgn"], mask=g["D_mask"]), g["D_out"])
