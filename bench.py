@@ -259,8 +259,15 @@ def run_gpu_arm(args):
     kern_ms = float(np.mean(step_ms))            # one fit kernel per step; the 2 tiny H2D copies precede it
     peak, peak_src = measured_hbm_peak()
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(core.last_fit_variant())
+        if tj and not args.small:
+            traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel": core.last_fit_variant(), "kernel_ms": kern_ms,
                 "step_ms": [round(x, 4) for x in step_ms]}
 

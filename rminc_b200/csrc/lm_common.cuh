@@ -226,18 +226,29 @@ __device__ __forceinline__ double2 ldg_stream2(const double *p)
     return v;
 }
 
-// Explicit-residual recomputation for one voxel (rare path).  Qt is the row-major
-// [n][KP] copy of Q in global memory; y is read again with stride ld.
+// Explicit-residual recomputation for one voxel (rare path).  Qt is the row-major [n][KP] copy
+// of Q in global memory; y is read again with stride ld.  Deliberately takes only scalars and
+// pointers and recomputes e itself: passing the caller's accumulator struct by reference to a
+// non-inlined function forces it onto the local-memory stack for EVERY voxel (measured: 0.46 GB of
+// extra DRAM writes per config-2 launch).  Returns (rss, mss).
 template <int KP>
-__device__ __noinline__ void exact_pass(const VoxelSums<KP> &v, const double *__restrict__ y, int64_t ld,
-                                        int n, const double *__restrict__ Qt, double &rss, double &mss)
+__device__ __noinline__ double2 exact_pass(const double *__restrict__ y, int64_t ld, int n,
+                                           const double *__restrict__ Qt, double y0)
 {
+    double e[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) e[k] = 0.0;
+    for (int j = 0; j < n; ++j) {
+        const double yv = y[(int64_t)j * ld] - y0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = fma(__ldg(Qt + (size_t)j * KP + k), yv, e[k]);
+    }
     double r2 = 0.0, sf = 0.0;
     for (int j = 0; j < n; ++j) {
         double fit = 0.0;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) fit = fma(__ldg(Qt + (size_t)j * KP + k), v.e[k], fit);
-        const double r = (y[(int64_t)j * ld] - v.y0) - fit;
+        for (int k = 0; k < KP; ++k) fit = fma(__ldg(Qt + (size_t)j * KP + k), e[k], fit);
+        const double r = (y[(int64_t)j * ld] - y0) - fit;
         r2 = fma(r, r, r2);
         sf += fit;
     }
@@ -246,12 +257,11 @@ __device__ __noinline__ void exact_pass(const VoxelSums<KP> &v, const double *__
     for (int j = 0; j < n; ++j) {
         double fit = 0.0;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) fit = fma(__ldg(Qt + (size_t)j * KP + k), v.e[k], fit);
+        for (int k = 0; k < KP; ++k) fit = fma(__ldg(Qt + (size_t)j * KP + k), e[k], fit);
         const double dlt = fit - mean;
         m2 = fma(dlt, dlt, m2);
     }
-    rss = r2;
-    mss = m2;
+    return make_double2(r2, m2);
 }
 
 }  // namespace rmg

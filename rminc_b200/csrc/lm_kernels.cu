@@ -270,8 +270,16 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
         // ---- fused epilogue
         double rss0 = s0.yy - sumsq_e(s0), mss0 = mss_from_e(s0, sd);
         double rss1 = s1.yy - sumsq_e(s1), mss1 = mss_from_e(s1, sd);
-        if (act0 && rss0 <= kExactThreshold * s0.yy && s0.yy > 0.0) exact_pass<KP>(s0, a.Y + v, a.ldY, n, a.Qt, rss0, mss0);
-        if (act1 && rss1 <= kExactThreshold * s1.yy && s1.yy > 0.0) exact_pass<KP>(s1, a.Y + v + 1, a.ldY, n, a.Qt, rss1, mss1);
+        if (act0 && rss0 <= kExactThreshold * s0.yy && s0.yy > 0.0) {
+            const double2 ex = exact_pass<KP>(a.Y + v, a.ldY, n, a.Qt, s0.y0);
+            rss0 = ex.x;
+            mss0 = ex.y;
+        }
+        if (act1 && rss1 <= kExactThreshold * s1.yy && s1.yy > 0.0) {
+            const double2 ex = exact_pass<KP>(a.Y + v + 1, a.ldY, n, a.Qt, s1.y0);
+            rss1 = ex.x;
+            mss1 = ex.y;
+        }
         if (in1 && a.out_vec2) {
             finish_pair<KP>(s0, rss0, mss0, act0, s1, rss1, mss1, act1, sd, o, a.ldOut);
         } else {
@@ -419,8 +427,11 @@ lm_fit_ldg_kernel(LmArgs a, int JT)
             continue;
         }
         double rss = sum[i].yy - sumsq_e(sum[i]), mss = mss_from_e(sum[i], sd);
-        if (rss <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0)
-            exact_pass<KP>(sum[i], a.Y + v + i, a.ldY, n, a.Qt, rss, mss);
+        if (rss <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0) {
+            const double2 ex = exact_pass<KP>(a.Y + v + i, a.ldY, n, a.Qt, sum[i].y0);
+            rss = ex.x;
+            mss = ex.y;
+        }
         finish_voxel<KP>(sum[i], rss, mss, sd, o, a.ldOut);
     }
 }

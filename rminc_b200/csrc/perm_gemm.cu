@@ -143,8 +143,18 @@ template <int KP>
 __global__ void __launch_bounds__(128)
 perm_exact_voxels_kernel(PermKernelParams P)
 {
-    for (int64_t v = blockIdx.x; v < P.V; v += gridDim.x) {
-        if (!P.vflag[v]) continue;
+    __shared__ int hits[128];
+    __shared__ int nhits;
+    // scan 128 flags per block iteration; flagged voxels (normally none) are refitted one at a time
+    for (int64_t base = (int64_t)blockIdx.x * 128; base < P.V; base += (int64_t)gridDim.x * 128) {
+        if (threadIdx.x == 0) nhits = 0;
+        __syncthreads();
+        const int64_t mine = base + threadIdx.x;
+        if (mine < P.V && P.vflag[mine]) hits[atomicAdd(&nhits, 1)] = threadIdx.x;
+        __syncthreads();
+        const int cnt = nhits;
+      for (int hidx = 0; hidx < cnt; ++hidx) {
+        const int64_t v = base + hits[hidx];
         const double *y = P.Y + v;
         const double y0 = P.y0[v];
         for (int r = threadIdx.x; r < P.R; r += blockDim.x) {
@@ -179,6 +189,8 @@ perm_exact_voxels_kernel(PermKernelParams P)
                 atomicMax(&P.keys[(size_t)c * P.R + r], ordered_key(s));
             }
         }
+      }
+        __syncthreads();
     }
 }
 

@@ -18,3 +18,10 @@ timeout -k 10 1500 python bench.py --steps 10 --warmup 3 | tee gpurun_out/bench_
 echo "=== reference arm"
 timeout -k 10 900 python bench.py --impl reference --steps 2 --warmup 1 | tee gpurun_out/bench_reference.json
 echo "=== done"
+echo "=== ncu: traffic of the fit kernels after the local-memory fix"
+export RMG_BENCH_SPIN_S=0
+CMD="python bench.py --steps 2 --warmup 3 --parts masked"
+$CMD > gpurun_out/plain_fit.log 2>&1 &&
+ncu --set full --clock-control none -k regex:"lm_fit" -s 3 -c 4 -o /tmp/prof_fit_fix -f $CMD > gpurun_out/ncu_fit.log 2>&1
+echo "ncu rc=$?"
+ncu -i /tmp/prof_fit_fix.ncu-rep --page raw --csv > gpurun_out/prof_fit_fix_raw.csv 2>/dev/null
