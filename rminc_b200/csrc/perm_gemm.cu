@@ -1,6 +1,9 @@
 // perm_gemm.cu -- see perm_gemm.cuh for the design.
 #include "perm_gemm.cuh"
 
+#include <chrono>
+#include <cstdio>
+
 #include "async_ptx.cuh"
 #include "capi_common.hpp"
 
@@ -36,7 +39,8 @@ __device__ __forceinline__ double rcp_pos(double x)
 struct PermKernelParams {
     const double *Y;
     int64_t V, ldY;
-    int n, p, R, ncols, two_sided, shift;
+    int n, p, R, ncols, two_sided, shift;   // R: permutations of THIS launch (a batch)
+    int Rstride;                             // permutations of the whole call (row stride of keys)
     int tcol[kPermMaxCols];          // coefficient index of each requested t-column
     const double *Apack;             // [n_pt][n_kc][A chunk] fragment-major
     const PermConst *pc;             // [R]
@@ -44,7 +48,8 @@ struct PermKernelParams {
     const double *yy;                // [V] |y - y0|^2, or -1 for voxels outside the mask
     const double *ys;                // [V] sum_j (y_j - y0)  (only when the intercept row is skipped)
     unsigned long long *keys;        // [ncols][R]
-    const double *Qt;                // [R][n][KP] plain row-major copy of every Q_r (exact path)
+    // geometry of Apack, so the (rare) exact path can read Q_r[j][k] back out of the packed operand
+    int inv, kg, pg, wm, warps_m, a_chunk, perms_per_cta;
     unsigned char *vflag;            // [V] set when some permutation's one-pass rss lost too many digits
     int n_pt, n_kc;
     int debug_skip;                  // diagnostics only: 1 = skip the statistics epilogue, 2 = skip the MMAs
@@ -134,6 +139,17 @@ __global__ void perm_finalize_keys_kernel(unsigned long long *keys, const PermCo
     keys[i] = ordered_key(t);
 }
 
+// Q_r[j][k] read back from the fragment-packed A operand (see the host packing in perm_gemm_run).
+__device__ __forceinline__ double perm_q(const PermKernelParams &P, const PermConst &pc, int r, int k, int j)
+{
+    if (k < P.inv) return pc.c0;
+    const int pt = r / P.perms_per_cta, rr = r % P.perms_per_cta;
+    const int warp_m = rr / (P.pg * 8), pg = (rr / 8) % P.pg, g = rr % 8;
+    const int mt = pg * P.kg + (k - P.inv);
+    const int kc = j / 16, jj = j % 16, ks = jj / 4, q = jj % 4;
+    return P.Apack[((size_t)pt * P.n_kc + kc) * P.a_chunk + (((size_t)warp_m * 4 + ks) * P.wm + mt) * 32 + g * 4 + q];
+}
+
 // ---- rare path: voxels for which some permutation's one-pass rss = |y'|^2 - |e'|^2 lost too
 //      many digits (the permuted model explains > 99.9 % of the voxel).  The GEMM skips those
 //      (permutation, voxel) pairs and raises vflag[v]; this kernel refits EVERY permutation of a
@@ -158,7 +174,6 @@ perm_exact_voxels_kernel(PermKernelParams P)
         const double *y = P.Y + v;
         const double y0 = P.y0[v];
         for (int r = threadIdx.x; r < P.R; r += blockDim.x) {
-            const double *Q = P.Qt + (size_t)r * P.n * KP;
             const PermConst &pc = P.pc[r];
             double e[KP];
 #pragma unroll
@@ -166,13 +181,13 @@ perm_exact_voxels_kernel(PermKernelParams P)
             for (int j = 0; j < P.n; ++j) {
                 const double yv = y[(int64_t)j * P.ldY] - y0;
 #pragma unroll
-                for (int k = 0; k < KP; ++k) e[k] = fma(__ldg(Q + (size_t)j * KP + k), yv, e[k]);
+                for (int k = 0; k < KP; ++k) e[k] = fma(perm_q(P, pc, r, k, j), yv, e[k]);
             }
             double rss = 0.0;
             for (int j = 0; j < P.n; ++j) {
                 double fit = 0.0;
 #pragma unroll
-                for (int k = 0; k < KP; ++k) fit = fma(__ldg(Q + (size_t)j * KP + k), e[k], fit);
+                for (int k = 0; k < KP; ++k) fit = fma(perm_q(P, pc, r, k, j), e[k], fit);
                 const double res = (y[(int64_t)j * P.ldY] - y0) - fit;
                 rss = fma(res, res, rss);
             }
@@ -186,7 +201,7 @@ perm_exact_voxels_kernel(PermKernelParams P)
                 double s = b * b / rss;
                 if (!P.two_sided && b < 0.0) s = -s;
                 if (!isfinite(s)) s = 0.0;
-                atomicMax(&P.keys[(size_t)c * P.R + r], ordered_key(s));
+                atomicMax(&P.keys[(size_t)c * P.Rstride + r], ordered_key(s));
             }
         }
       }
@@ -414,7 +429,7 @@ perm_gemm_kernel(PermKernelParams P)
                     // the 4 lanes of a quad hold different voxels of the same permutation
                     best = fmax(best, __shfl_xor_sync(0xffffffffu, best, 1));
                     best = fmax(best, __shfl_xor_sync(0xffffffffu, best, 2));
-                    if (q == 0 && rvalid && best > -INFINITY) atomicMax(&P.keys[(size_t)c * P.R + r], ordered_key(best));
+                    if (q == 0 && rvalid && best > -INFINITY) atomicMax(&P.keys[(size_t)c * P.Rstride + r], ordered_key(best));
                 }
             }
         }
@@ -463,6 +478,16 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
                           int sm_count, cudaStream_t st, int *launches, void **workspace_out)
 {
     const int R = a.R, n = a.n, p = a.p, KP = p;
+    const bool timing = std::getenv("RMG_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
+    double t_mark = t_start;
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        const double t = now();
+        std::fprintf(stderr, "[rmg perm] %-28s %8.3f ms\n", what, t - t_mark);
+        t_mark = t;
+    };
     // Is component 0 of every permuted design the same constant column (the intercept, first in
     // pivot order)?  Then e_0 = c0 * sum(y) is permutation-invariant and needs no tensor-core row.
     int INV = (KP >= 2 && all_intercept && !std::getenv("RMG_PERM_NO_INV")) ? 1 : 0;
@@ -489,61 +514,24 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
     const int n_pt = (R + perms_per_cta - 1) / perms_per_cta;
     const int n_kc = (n + KC - 1) / KC;
 
-    // ---- host packing: A in fragment order, plain Qt for the exact path, per-permutation constants
-    std::vector<double> Apack((size_t)n_pt * n_kc * A_CHUNK, 0.0);
-    std::vector<double> Qt((size_t)R * n * KP, 0.0);
-    std::vector<PermConst> pc(R);
-    parallel_for(R, [&](int r0, int r1) {
-      for (int r = r0; r < r1; ++r) {
-        const Design &D = designs[r];
-        PermConst &c = pc[r];
-        std::memset(&c, 0, sizeof c);
-        for (int i = 0; i < p; ++i) {
-            c.q1[i] = D.q1[i];
-            c.ct[i] = D.ct[i];
-            for (int j = 0; j < p; ++j) c.Rinv[i * 8 + j] = D.Rinv[i + (size_t)j * p];
-        }
-        c.rdf = (double)(n - p);
-        c.c0 = c0[r];
-        const int pt = r / perms_per_cta, rr = r % perms_per_cta;
-        const int warp_m = rr / (PG * 8), pg = (rr / 8) % PG, g = rr % 8;
-        for (int k = 0; k < D.k; ++k) {
-            const double *qcol = D.Q.data() + (size_t)k * n;
-            for (int j = 0; j < n; ++j) Qt[((size_t)r * n + j) * KP + k] = qcol[j];
-            if (k < INV) continue;
-            const int mt = pg * KG + (k - INV);
-            for (int j = 0; j < n; ++j) {
-                const int kc = j / KC, jj = j % KC, ks = jj / 4, q = jj % 4;
-                const int lane = g * 4 + q;
-                // [pt][kc] chunk, inside: [warp_m][ks][mt][lane]  (one MMA A-fragment = 32 consecutive doubles)
-                const size_t off = (((size_t)pt * n_kc + kc) * A_CHUNK) +
-                                   (((size_t)warp_m * (KC / 4) + ks) * WM + mt) * 32 + lane;
-                Apack[off] = qcol[j];
-            }
-        }
-      }
-    });
-
-    // ---- one workspace allocation
+    // ---- device workspace; the prepass (which needs only Y) starts before any host packing
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
-    const size_t oA = carve(Apack.size() * 8), oQ = carve(Qt.size() * 8), oP = carve(pc.size() * sizeof(PermConst));
+    const size_t apack_doubles = (size_t)n_pt * n_kc * A_CHUNK;
+    const size_t oA = carve(apack_doubles * 8), oP = carve((size_t)R * sizeof(PermConst));
     const size_t oY0 = carve((size_t)a.V * 8), oYY = carve((size_t)a.V * 8), oYS = carve((size_t)a.V * 8);
     const size_t oFlag = carve(256), oVf = carve((size_t)a.V);
     char *ws = nullptr;
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ws), off, st);
     if (e != cudaSuccess) return e;
     *workspace_out = ws;
-    e = cudaMemcpyAsync(ws + oA, Apack.data(), Apack.size() * 8, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ws + oQ, Qt.data(), Qt.size() * 8, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ws + oP, pc.data(), pc.size() * sizeof(PermConst), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ws + oFlag, 0, 256, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // pageable sources must outlive the copies
+    e = cudaMemsetAsync(ws + oFlag, 0, 256, st);
     if (e != cudaSuccess) return e;
 
     PermKernelParams P;
     std::memset(&P, 0, sizeof P);
-    P.Y = a.Y; P.V = a.V; P.ldY = a.ldY; P.n = n; P.p = p; P.R = R; P.ncols = a.ncols; P.two_sided = a.two_sided;
+    P.Y = a.Y; P.V = a.V; P.ldY = a.ldY; P.n = n; P.p = p; P.R = R; P.Rstride = R; P.ncols = a.ncols;
+    P.two_sided = a.two_sided;
     P.shift = all_intercept ? 1 : 0;
     P.Apack = reinterpret_cast<double *>(ws + oA);
     P.pc = reinterpret_cast<PermConst *>(ws + oP);
@@ -551,11 +539,11 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
     P.yy = reinterpret_cast<double *>(ws + oYY);
     P.ys = reinterpret_cast<double *>(ws + oYS);
     P.keys = a.keys;
-    P.Qt = reinterpret_cast<double *>(ws + oQ);
+    P.inv = INV; P.kg = KG; P.pg = PG; P.wm = WM; P.warps_m = WARPS_M; P.a_chunk = A_CHUNK; P.perms_per_cta = perms_per_cta;
     P.vflag = reinterpret_cast<unsigned char *>(ws + oVf);
     P.n_pt = n_pt;
     P.n_kc = n_kc;
-    if (const char *e = std::getenv("RMG_PERM_DEBUG_SKIP")) P.debug_skip = std::atoi(e);
+    if (const char *dbg = std::getenv("RMG_PERM_DEBUG_SKIP")) P.debug_skip = std::atoi(dbg);
     int *any_zero = reinterpret_cast<int *>(ws + oFlag);
     for (int c = 0; c < a.ncols; ++c) P.tcol[c] = a.hcols[c] - (p + 2);
 
@@ -567,28 +555,108 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
     const int nk = R * a.ncols;
     perm_floor_keys_kernel<<<(nk + 255) / 256, 256, 0, st>>>(a.keys, nk, any_zero);
     *launches += 2;
-    switch (KP * 2 + INV) {
-#define RMG_PG_CASE(K) case K * 2: e = launch_gemm<K, pg_for(K), 0>(P, sm_count, st, WARPS_M); break;
-#define RMG_PG_CASE1(K) case K * 2 + 1: e = launch_gemm<K, pg_for(K - 1), 1>(P, sm_count, st, WARPS_M); break;
-        RMG_PG_CASE(1) RMG_PG_CASE(2) RMG_PG_CASE(3) RMG_PG_CASE(4) RMG_PG_CASE(5) RMG_PG_CASE(6) RMG_PG_CASE(7) RMG_PG_CASE(8)
-        RMG_PG_CASE1(2) RMG_PG_CASE1(3) RMG_PG_CASE1(4) RMG_PG_CASE1(5) RMG_PG_CASE1(6) RMG_PG_CASE1(7) RMG_PG_CASE1(8)
+    lap("alloc + prepass launch");
+
+    // ---- batches of permutations: pack on the host (all cores), upload on a side stream, launch the
+    //      GEMM of the batch; the host packs batch b+1 while the GPU multiplies batch b.
+    //      Host staging persists across calls (first-touch page faults of fresh 10+ MB vectors cost more
+    //      than the packing itself).
+    static thread_local std::vector<double> tl_apack;
+    static thread_local std::vector<PermConst> tl_pc;
+    // bind the calling thread's instances: a thread_local named inside a worker lambda would resolve
+    // to the WORKER's (empty) instance
+    std::vector<double> &Apack = tl_apack;
+    std::vector<PermConst> &pc = tl_pc;
+    Apack.resize(apack_doubles);
+    pc.resize(R);
+    const int tiles_per_batch = std::max(1, 256 / perms_per_cta);
+    const int nbatch = (n_pt + tiles_per_batch - 1) / tiles_per_batch;
+    cudaStream_t cs = nullptr;
+    std::vector<cudaEvent_t> ev(nbatch, nullptr);
+    e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+    for (int b = 0; b < nbatch && e == cudaSuccess; ++b) {
+        const int pt0 = b * tiles_per_batch, pt1 = std::min(n_pt, pt0 + tiles_per_batch);
+        const int r0 = pt0 * perms_per_cta, r1 = std::min(R, pt1 * perms_per_cta);
+        double *hA = Apack.data() + (size_t)pt0 * n_kc * A_CHUNK;
+        const size_t nA = (size_t)(pt1 - pt0) * n_kc * A_CHUNK;
+        std::memset(hA, 0, nA * sizeof(double));   // padding: permutations past R, subjects past n
+        parallel_for(r1 - r0, [&](int i0, int i1) {
+            for (int r = r0 + i0; r < r0 + i1; ++r) {
+                const Design &D = designs[r];
+                PermConst &c = pc[r];
+                std::memset(&c, 0, sizeof c);
+                for (int i = 0; i < p; ++i) {
+                    c.q1[i] = D.q1[i];
+                    c.ct[i] = D.ct[i];
+                    for (int j = 0; j < p; ++j) c.Rinv[i * 8 + j] = D.Rinv[i + (size_t)j * p];
+                }
+                c.rdf = (double)(n - p);
+                c.c0 = c0[r];
+                const int pt = r / perms_per_cta, rr = r % perms_per_cta;
+                const int warp_m = rr / (PG * 8), pg = (rr / 8) % PG, g = rr % 8;
+                for (int k = INV; k < D.k; ++k) {
+                    const double *qcol = D.Q.data() + (size_t)k * n;
+                    const int mt = pg * KG + (k - INV);
+                    for (int j = 0; j < n; ++j) {
+                        const int kc = j / KC, jj = j % KC, ks = jj / 4, q = jj % 4;
+                        const int lane = g * 4 + q;
+                        // [pt][kc] chunk, inside: [warp_m][ks][mt][lane]  (one MMA A-fragment = 32 consecutive doubles)
+                        Apack[(((size_t)pt * n_kc + kc) * A_CHUNK) + (((size_t)warp_m * (KC / 4) + ks) * WM + mt) * 32 + lane] =
+                            qcol[j];
+                    }
+                }
+            }
+        });
+        e = cudaMemcpyAsync(ws + oA + (size_t)pt0 * n_kc * A_CHUNK * 8, hA, nA * 8, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(ws + oP + (size_t)r0 * sizeof(PermConst), pc.data() + r0, (size_t)(r1 - r0) * sizeof(PermConst),
+                                cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[b], cs);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev[b], 0);
+        if (e != cudaSuccess) break;
+        PermKernelParams Pb = P;
+        Pb.Apack = P.Apack + (size_t)pt0 * n_kc * A_CHUNK;
+        Pb.pc = P.pc + r0;
+        Pb.keys = P.keys + r0;
+        Pb.R = r1 - r0;
+        Pb.n_pt = pt1 - pt0;
+        switch (KP * 2 + INV) {
+#define RMG_PG_CASE(K) case K * 2: e = launch_gemm<K, pg_for(K), 0>(Pb, sm_count, st, WARPS_M); break;
+#define RMG_PG_CASE1(K) case K * 2 + 1: e = launch_gemm<K, pg_for(K - 1), 1>(Pb, sm_count, st, WARPS_M); break;
+            RMG_PG_CASE(1) RMG_PG_CASE(2) RMG_PG_CASE(3) RMG_PG_CASE(4) RMG_PG_CASE(5) RMG_PG_CASE(6) RMG_PG_CASE(7) RMG_PG_CASE(8)
+            RMG_PG_CASE1(2) RMG_PG_CASE1(3) RMG_PG_CASE1(4) RMG_PG_CASE1(5) RMG_PG_CASE1(6) RMG_PG_CASE1(7) RMG_PG_CASE1(8)
 #undef RMG_PG_CASE
 #undef RMG_PG_CASE1
-    default: e = cudaErrorInvalidValue;
+        default: e = cudaErrorInvalidValue;
+        }
+        *launches += 1;
     }
-    if (e != cudaSuccess) return e;
-    {
-        const int eg = (int)std::min<int64_t>(a.V, (int64_t)sm_count * 16);
+    lap("pack + upload + GEMM launches");
+    if (e == cudaSuccess) {
+        const int eg = (int)std::min<int64_t>((a.V + 127) / 128, (int64_t)sm_count * 16);
         switch (KP) {
 #define RMG_EX_CASE(K) case K: perm_exact_voxels_kernel<K><<<eg, 128, 0, st>>>(P); break;
             RMG_EX_CASE(1) RMG_EX_CASE(2) RMG_EX_CASE(3) RMG_EX_CASE(4) RMG_EX_CASE(5) RMG_EX_CASE(6) RMG_EX_CASE(7) RMG_EX_CASE(8)
 #undef RMG_EX_CASE
         }
-        *launches += 1;
+        perm_finalize_keys_kernel<<<(nk + 255) / 256, 256, 0, st>>>(a.keys, P.pc, P);
+        *launches += 2;
+        e = cudaGetLastError();
     }
-    perm_finalize_keys_kernel<<<(nk + 255) / 256, 256, 0, st>>>(a.keys, P.pc, P);
-    *launches += 2;
-    return cudaGetLastError();
+    // the staging buffers are reused by the next call: wait for the (long finished) uploads
+    if (cs) {
+        cudaError_t e2 = cudaStreamSynchronize(cs);
+        if (e == cudaSuccess) e = e2;
+        cudaStreamDestroy(cs);
+    }
+    for (auto evb : ev)
+        if (evb) cudaEventDestroy(evb);
+    if (timing) {
+        cudaStreamSynchronize(st);
+        lap("GPU work (sync, timing only)");
+    }
+    return e;
 }
 
 }  // namespace rmg

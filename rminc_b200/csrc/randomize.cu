@@ -19,7 +19,9 @@
 //            tensor-core GEMM (mma.sync DMMA) with the statistics + max fused in the
 //            epilogue (see perm_gemm.cuh).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <thread>
 
 #include "capi_common.hpp"
@@ -131,7 +133,11 @@ int rmg_randomize_device(const double *dY, int64_t V, int64_t ldY, int n, const 
     for (int c = 0; c < ncols; ++c)
         if (cols[c] < 0 || cols[c] >= 2 * p + 3) return fail(err, errlen, RMG_ERR_INVALID, "cols[%d] out of range", c);
     PermDesigns pd;
+    const auto t_f0 = std::chrono::steady_clock::now();
     if ((rc = factor_permutations(X, n, p, idx, R, pd, err, errlen))) return rc;
+    if (std::getenv("RMG_TIMING"))
+        std::fprintf(stderr, "[rmg perm] %-28s %8.3f ms\n", "factor R designs",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_f0).count());
     if ((rc = select_device(device, err, errlen))) return rc;
     if (R == 0 || ncols == 0) return RMG_OK;
 
