@@ -48,6 +48,22 @@ int select_device(int device, char *err, size_t errlen)
     return RMG_OK;
 }
 
+int host_threads()
+{
+    static int cached = 0;
+    if (cached) return cached;
+    int nt = 0;
+    if (const char *e = std::getenv("RMG_HOST_THREADS")) nt = std::atoi(e);
+    if (nt <= 0) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        int gpus = 0;
+        if (cudaGetDeviceCount(&gpus) != cudaSuccess) { cudaGetLastError(); gpus = 1; }
+        nt = (int)(hw ? hw : 1) / std::max(1, gpus);
+    }
+    cached = std::max(1, std::min(nt, 16));
+    return cached;
+}
+
 int device_sm_count(int device)
 {
     int sms = 148;

@@ -58,11 +58,14 @@ std::vector<double> make_qt(const Design &D, int KP);
 
 // Runs fn(begin, end) over [0, count) on up to hardware_concurrency host threads (host-side
 // preparation of the permutation test: factorisations and operand packing).
+// Host worker threads for this process: the cores are shared with the other ranks of the box (one
+// process per GPU), so take hardware_concurrency / visible GPUs, at most 16 (RMG_HOST_THREADS overrides).
+int host_threads();
+
 template <class Fn>
 inline void parallel_for(int count, Fn fn)
 {
-    unsigned hw = std::thread::hardware_concurrency();
-    int nt = (int)(hw ? (hw > 16 ? 16 : hw) : 1);
+    int nt = host_threads();
     if (nt > count / 8) nt = count / 8;
     if (nt <= 1) {
         fn(0, count);

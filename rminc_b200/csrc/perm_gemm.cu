@@ -474,9 +474,10 @@ bool perm_gemm_supported(int n, int p, int64_t V, int64_t ldY, const double *dY,
            (reinterpret_cast<uintptr_t>(dY) & 15) == 0;
 }
 
-cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &designs, bool all_intercept,
-                          int sm_count, cudaStream_t st, int *launches, void **workspace_out)
+cudaError_t perm_gemm_run(const PermGemmArgs &a, const PermSet &ps, int sm_count, cudaStream_t st, int *launches,
+                          void **workspace_out)
 {
+    const bool all_intercept = ps.all_intercept;
     const int R = a.R, n = a.n, p = a.p, KP = p;
     const bool timing = std::getenv("RMG_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -492,14 +493,23 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
     // pivot order)?  Then e_0 = c0 * sum(y) is permutation-invariant and needs no tensor-core row.
     int INV = (KP >= 2 && all_intercept && !std::getenv("RMG_PERM_NO_INV")) ? 1 : 0;
     std::vector<double> c0(R, 0.0);
-    for (int r = 0; r < R && INV; ++r) {
-        const Design &D = designs[r];
-        if (D.k < 1) { INV = 0; break; }
+    auto constant_column = [&](const Design &D, double &value) {
+        if (D.k < 1) return false;
         const double *q = D.Q.data();
         double lo = q[0], hi = q[0], sum = 0.0;
         for (int j = 0; j < n; ++j) { lo = std::min(lo, q[j]); hi = std::max(hi, q[j]); sum += q[j]; }
-        if (!(hi - lo <= 1e-13 * std::fabs(hi)) || hi == 0.0) { INV = 0; break; }
-        c0[r] = sum / n;
+        value = sum / n;
+        return (hi - lo <= 1e-13 * std::fabs(hi)) && hi != 0.0;
+    };
+    double base_c0 = 0.0;
+    const bool base_const = constant_column(ps.base, base_c0);   // a row gather keeps a constant column constant
+    for (int r = 0; r < R && INV; ++r) {
+        if (ps.is_perm(r)) {
+            if (!base_const) INV = 0;
+            c0[r] = base_c0;
+        } else if (!constant_column(ps.own[r], c0[r])) {
+            INV = 0;
+        }
     }
     const int KG = KP - INV;
     const int PG = pg_for(KG);
@@ -582,7 +592,9 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
         std::memset(hA, 0, nA * sizeof(double));   // padding: permutations past R, subjects past n
         parallel_for(r1 - r0, [&](int i0, int i1) {
             for (int r = r0 + i0; r < r0 + i1; ++r) {
-                const Design &D = designs[r];
+                const Design &D = ps.design(r);
+                const bool gather = ps.is_perm(r);
+                const int32_t *ix = ps.idx + (size_t)r * n;
                 PermConst &c = pc[r];
                 std::memset(&c, 0, sizeof c);
                 for (int i = 0; i < p; ++i) {
@@ -602,7 +614,7 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &desi
                         const int lane = g * 4 + q;
                         // [pt][kc] chunk, inside: [warp_m][ks][mt][lane]  (one MMA A-fragment = 32 consecutive doubles)
                         Apack[(((size_t)pt * n_kc + kc) * A_CHUNK) + (((size_t)warp_m * (KC / 4) + ks) * WM + mt) * 32 + lane] =
-                            qcol[j];
+                            gather ? qcol[ix[j]] : qcol[j];
                     }
                 }
             }

@@ -93,9 +93,34 @@ struct PermConst {
     double pad[6];
 };
 
+// The R permuted designs of one call.  A column of idx that is a true permutation only re-orders the
+// rows of X (X_pi = P X => Q_pi = P Q, same R / pivoting / rank / (R'R)^-1), so it is represented by
+// the base factorisation plus the index column; only columns with repeated indices (replace = TRUE)
+// carry a factorisation of their own.
+struct PermSet {
+    Design base;
+    std::vector<Design> own;        // own[r].n == 0  <=>  idx[, r] is a true permutation
+    const int32_t *idx = nullptr;   // n x R, 0-based
+    int R = 0;
+    bool all_intercept = true;
+    bool is_perm(int r) const { return own[r].n == 0; }
+    const Design &design(int r) const { return is_perm(r) ? base : own[r]; }
+    const double *qcol_own(int r, int k) const { return own[r].Q.data() + (size_t)k * own[r].n; }
+    // materialise permutation r as a stand-alone Design (refit path only)
+    Design materialise(int r) const
+    {
+        if (!is_perm(r)) return own[r];
+        Design D = base;
+        const int n = base.n;
+        for (int c = 0; c < base.p; ++c)
+            for (int i = 0; i < n; ++i) D.Q[i + (size_t)c * n] = base.Q[idx[i + (size_t)r * n] + (size_t)c * n];
+        return D;
+    }
+};
+
 bool perm_gemm_supported(int n, int p, int64_t V, int64_t ldY, const double *dY, const int32_t *hcols, int ncols);
 
-cudaError_t perm_gemm_run(const PermGemmArgs &a, const std::vector<Design> &designs, bool all_intercept,
-                          int sm_count, cudaStream_t st, int *launches, void **workspace_out);
+cudaError_t perm_gemm_run(const PermGemmArgs &a, const PermSet &ps, int sm_count, cudaStream_t st, int *launches,
+                          void **workspace_out);
 
 }  // namespace rmg

@@ -66,39 +66,47 @@ colmax_kernel(const double *__restrict__ out, int64_t V, int64_t ld, const int32
     }
 }
 
-struct PermDesigns {
-    std::vector<Design> designs;  // one per permutation
-    bool all_intercept = true;
-};
-
 // Factor every permuted design; translate the reference's error contract.
-int factor_permutations(const double *X, int n, int p, const int32_t *idx, int R, PermDesigns &pd, char *err,
+int factor_permutations(const double *X, int n, int p, const int32_t *idx, int R, PermSet &pd, char *err,
                         size_t errlen)
 {
     for (size_t i = 0; i < (size_t)n * p; ++i)
         if (!std::isfinite(X[i])) return fail(err, errlen, RMG_ERR_INVALID, "model matrix contains non-finite values");
-    pd.designs.resize(R);
+    pd.own.assign(R, Design{});
+    pd.idx = idx;
+    pd.R = R;
     for (int r = 0; r < R; ++r)
         for (int i = 0; i < n; ++i) {
             const int32_t src = idx[i + (size_t)r * n];
             if (src < 0 || src >= n) return fail(err, errlen, RMG_ERR_INVALID, "idx[%d, %d] = %d out of range", i, r, src);
         }
-    // the R factorisations are independent: spread them over the host cores
+    // A column of idx that is a true permutation (replace = FALSE) only re-orders the rows of X:
+    // X_pi = P X  =>  Q_pi = P Q with the same R, pivoting, rank and (R'R)^-1, so its factorisation is a
+    // row gather of the base one.  Columns with repeated indices (replace = TRUE) change the column
+    // space and are factored from scratch.  The work is independent per permutation: host threads.
+    const int base_info = factor_design(X, n, p, pd.base);
     std::vector<int> infos(R, 0);
     parallel_for(R, [&](int r0, int r1) {
         std::vector<double> Xp((size_t)n * p);
+        std::vector<unsigned char> seen(n);
         for (int r = r0; r < r1; ++r) {
-            for (int i = 0; i < n; ++i) {
-                const int32_t src = idx[i + (size_t)r * n];
-                for (int j = 0; j < p; ++j) Xp[i + (size_t)j * n] = X[src + (size_t)j * n];
+            const int32_t *ix = idx + (size_t)r * n;
+            std::fill(seen.begin(), seen.end(), 0);
+            bool is_perm = base_info == 0;
+            for (int i = 0; i < n && is_perm; ++i) {
+                if (seen[ix[i]]) is_perm = false;
+                seen[ix[i]] = 1;
             }
-            infos[r] = factor_design(Xp.data(), n, p, pd.designs[r]);
+            if (is_perm) continue;   // own[r] stays empty: represented by the base factorisation + idx[, r]
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < p; ++j) Xp[i + (size_t)j * n] = X[ix[i] + (size_t)j * n];
+            infos[r] = factor_design(Xp.data(), n, p, pd.own[r]);
         }
     });
     for (int r = 0; r < R; ++r) {   // report the FIRST failing permutation, as a sequential loop would
         if (infos[r] > 0)
             return fail(err, errlen, RMG_ERR_SINGULAR, "permutation %d: %s", r + 1, singular_message(infos[r]).c_str());
-        pd.all_intercept = pd.all_intercept && pd.designs[r].has_intercept;
+        pd.all_intercept = pd.all_intercept && pd.design(r).has_intercept;
     }
     return RMG_OK;
 }
@@ -132,7 +140,7 @@ int rmg_randomize_device(const double *dY, int64_t V, int64_t ldY, int n, const 
         return fail(err, errlen, RMG_ERR_INVALID, "bad permutation arguments");
     for (int c = 0; c < ncols; ++c)
         if (cols[c] < 0 || cols[c] >= 2 * p + 3) return fail(err, errlen, RMG_ERR_INVALID, "cols[%d] out of range", c);
-    PermDesigns pd;
+    PermSet pd;
     const auto t_f0 = std::chrono::steady_clock::now();
     if ((rc = factor_permutations(X, n, p, idx, R, pd, err, errlen))) return rc;
     if (std::getenv("RMG_TIMING"))
@@ -163,7 +171,7 @@ int rmg_randomize_device(const double *dY, int64_t V, int64_t ldY, int n, const 
         if (path != PermPath::Refit && V > 0 && perm_gemm_supported(n, p, V, ldY, dY, cols, ncols)) {
             PermGemmArgs ga{dY, V, ldY, n, p, dmask, mask_lo, mask_hi, cols, ncols, two_sided, keys, R};
             int gl = 0;
-            cudaError_t ge = perm_gemm_run(ga, pd.designs, pd.all_intercept, plan.sm_count, st, &gl, &gemm_ws);
+            cudaError_t ge = perm_gemm_run(ga, pd, plan.sm_count, st, &gl, &gemm_ws);
             launches += gl;
             if (ge != cudaSuccess) {
                 rc = fail(err, errlen, RMG_ERR_CUDA, "permutation GEMM failed: %s", cudaGetErrorString(ge));
@@ -183,14 +191,15 @@ int rmg_randomize_device(const double *dY, int64_t V, int64_t ldY, int n, const 
             DevDesign *dd = nullptr;
             double *qt = nullptr;
             RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dd), sizeof(DevDesign) * (size_t)R, st));
-            const size_t qstride = make_qt(pd.designs[0], KP).size();   // rows padded for the TMA kernel
+            const size_t qstride = make_qt(pd.base, KP).size();   // rows padded for the TMA kernel
             RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&qt), sizeof(double) * (size_t)R * qstride, st));
             {
                 std::vector<DevDesign> hdd(R);
                 std::vector<double> hqt((size_t)R * qstride);
                 for (int r = 0; r < R; ++r) {
-                    fill_dev_design(pd.designs[r], hdd[r]);
-                    const std::vector<double> q = make_qt(pd.designs[r], KP);
+                    const Design Dr = pd.materialise(r);
+                    fill_dev_design(Dr, hdd[r]);
+                    const std::vector<double> q = make_qt(Dr, KP);
                     std::copy(q.begin(), q.end(), hqt.begin() + (size_t)r * qstride);
                 }
                 cudaError_t e1 = cudaMemcpyAsync(dd, hdd.data(), sizeof(DevDesign) * (size_t)R, cudaMemcpyHostToDevice, st);
