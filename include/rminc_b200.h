@@ -76,6 +76,15 @@ int rmg_vertex_lm(const double *Y, int64_t V, int64_t ldY, int n, const double *
                   double *out, int64_t ldOut, int device, char *err, size_t errlen);
 
 /*
+ * anatLm(weights = w).  Drop-in for
+ *   SEXP vertex_wlm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix, SEXP ws)
+ * (src/weighted_least_squares.c:168; R caller R/minc_anatomy.R:1135-1142): weighted least squares,
+ * per-voxel body voxel_wlm (:14-166).  weights: n values, finite and > 0.  Same result layout.
+ */
+int rmg_vertex_wlm(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p,
+                   const double *weights, double *out, int64_t ldOut, int device, char *err, size_t errlen);
+
+/*
  * mincLm.  Drop-in for minc2_model(..., method = "lm") (src/modelling_functions.c:743-745;
  * R caller mincLm_c_wrapper, R/minc_voxel_statistics.R:695-712) once the R layer has staged
  * the n volumes as the columns of Y (row order = file dimension order, :1059) and the mask

@@ -58,6 +58,7 @@ def lib():
         _lib.orc_design_probe.restype = C.c_int
         _lib.orc_dnrm2.restype = C.c_double
         _lib.orc_anova_loop.restype = C.c_int
+        _lib.orc_vertex_wlm_loop.restype = C.c_int
     return _lib
 
 
@@ -70,7 +71,7 @@ def ref():
     if _ref is None:
         _ref = _load(_REF)
         for f in ("ref_voxel_lm", "ref_vertex_lm_loop", "ref_minc2_model_lm", "ref_vertex_anova_loop",
-                  "ref_per_voxel_anova"):
+                  "ref_per_voxel_anova", "ref_vertex_wlm_loop"):
             getattr(_ref, f).restype = C.c_int
     return _ref
 
@@ -254,6 +255,28 @@ def anova(Y, X, asgn, mask=None, lo=1.0, hi=99999999.0, use_ref=False, sizes=Non
     info = lib().orc_anova_loop(_p(Y), C.c_int64(V), C.c_int64(V), C.c_int(n), _p(X), C.c_int(p),
                                 asgn.ctypes.data_as(_ip), _p(m) if m is not None else None, C.c_double(lo),
                                 C.c_double(hi), _p(out), C.c_int64(max(V, 1)))
+    if info:
+        raise OracleError(f"element ({info}, {info}) is zero, so the inverse cannot be computed")
+    return out
+
+
+def vertex_wlm_loop(Y, X, w, use_ref=False):
+    """anatLm(weights=): vertex_wlm_loop / voxel_wlm (src/weighted_least_squares.c).  V x (2p+3)."""
+    Y = _F(Y)
+    X = _F(X)
+    w = _f64(w)
+    V, n = Y.shape
+    p = X.shape[1]
+    out = np.zeros((V, 2 * p + 3), order="F")
+    if use_ref:
+        err = C.create_string_buffer(512)
+        rc = ref().ref_vertex_wlm_loop(_p(Y), C.c_int64(V), C.c_int(n), _p(X), C.c_int(p), _p(w), _p(out), err,
+                                       C.c_size_t(512))
+        if rc:
+            raise OracleError(err.value.decode())
+        return out
+    info = lib().orc_vertex_wlm_loop(_p(Y), C.c_int64(V), C.c_int64(V), C.c_int(n), _p(X), C.c_int(p), _p(w), _p(out),
+                                     C.c_int64(max(V, 1)))
     if info:
         raise OracleError(f"element ({info}, {info}) is zero, so the inverse cannot be computed")
     return out

@@ -376,6 +376,83 @@ int orc_anova_loop(const double *Y, int64_t V, int64_t ldY, int n, const double 
     return rc;
 }
 
+/* ------------------------------------------------------------- voxel_wlm */
+/* src/weighted_least_squares.c:14-166.  Rows of X and y are scaled by sqrt(w); residuals are
+ * un-scaled again; wrss = sum w res^2; mss about the WEIGHTED mean of the fitted values; logLik
+ * gains 0.5 * sum(log w).  stats = [F, t.., R2, logLik]. */
+int orc_voxel_wlm(const double *y, const double *X, const double *w, int n, int p, double *coef,
+                  double *stats, int *pivot, int *rank)
+{
+    double *x = (double *)malloc((size_t)n * p * sizeof(double));
+    double *yw = (double *)malloc((size_t)n * sizeof(double));
+    double *xws = (double *)malloc((size_t)n * sizeof(double));
+    double *resid = (double *)malloc((size_t)n * sizeof(double));
+    double *effects = (double *)malloc((size_t)n * sizeof(double));
+    double *fitted = (double *)malloc((size_t)n * sizeof(double));
+    double *qraux = (double *)malloc((size_t)p * sizeof(double));
+    double *work = (double *)malloc((size_t)2 * p * sizeof(double));
+    double *se = (double *)malloc((size_t)p * sizeof(double));
+    double total_log_weight = 0;
+    for (int i = 0; i < n; ++i) {
+        total_log_weight += log(w[i]);
+        xws[i] = sqrt(w[i]);
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < p; ++j) x[i + (size_t)j * n] = X[i + (size_t)j * n] * xws[i];
+    for (int i = 0; i < n; ++i) yw[i] = y[i] * xws[i];
+    for (int j = 0; j < p; ++j) pivot[j] = j;
+    orc_dqrls(x, n, p, yw, 1, 1e-07, coef, resid, effects, rank, pivot, qraux, work);
+    double rss = 0, wrss = 0, sumw = 0, mss = 0;
+    for (int i = 0; i < n; ++i) {
+        sumw += w[i];
+        resid[i] /= xws[i];
+        double res2 = pow(resid[i], 2);
+        rss += res2;
+        wrss += w[i] * res2;
+        fitted[i] = y[i] - resid[i];
+    }
+    double logLik = .5 * (total_log_weight - n * (log(2 * M_PI) + 1 - log(n) + log(wrss)));
+    double m = 0;
+    for (int i = 0; i < n; ++i) m += (w[i] * fitted[i]) / sumw;
+    for (int i = 0; i < n; ++i) mss += w[i] * pow(fitted[i] - m, 2);
+    int rdf = n - p;
+    double resvar = wrss / rdf;
+    stats[0] = (mss / (p - 1)) / resvar;
+    int info = orc_dpotri_upper(p, x, n);
+    if (info == 0) {
+        for (int i = 0; i < p; ++i) se[pivot[i]] = sqrt(x[(size_t)i * n + i] * resvar);
+        for (int i = 0; i < p; ++i) stats[i + 1] = coef[i] / se[i];
+        stats[p + 1] = mss / (mss + wrss);
+        stats[p + 2] = logLik;
+    }
+    free(x); free(yw); free(xws); free(resid); free(effects); free(fitted); free(qraux); free(work); free(se);
+    (void)rss;
+    return info;
+}
+
+/* vertex_wlm_loop (src/weighted_least_squares.c:168-335), static design. */
+int orc_vertex_wlm_loop(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *w,
+                        double *out, int64_t ldOut)
+{
+    double *ybuf = (double *)malloc((size_t)n * sizeof(double));
+    double *coef = (double *)malloc((size_t)p * sizeof(double));
+    double *stats = (double *)malloc((size_t)(p + 3) * sizeof(double));
+    int *pivot = (int *)malloc((size_t)p * sizeof(int));
+    int rank, rc = 0;
+    for (int64_t i = 0; i < V && rc == 0; ++i) {
+        for (int j = 0; j < n; ++j) ybuf[j] = Y[i + ldY * j];
+        rc = orc_voxel_wlm(ybuf, X, w, n, p, coef, stats, pivot, &rank);
+        if (rc) break;
+        out[i] = stats[0];
+        out[i + 1 * ldOut] = stats[p + 1];
+        for (int k = 2; k < p + 2; ++k) out[i + k * ldOut] = coef[k - 2];
+        for (int k = 1; k < p + 1; ++k) out[i + (k + p + 1) * ldOut] = stats[k];
+        out[i + (2 * p + 2) * ldOut] = stats[p + 2];
+    }
+    free(ybuf); free(coef); free(stats); free(pivot);
+    return rc;
+}
+
 /* --------------------------------------------------------- vertex_lm_loop */
 /* src/vertex_modelling.c:104-158.  Y is V x n column-major with leading
  * dimension ldY (the reference has ldY == V); out is V x (2p+3) with leading

@@ -243,6 +243,7 @@ SEXP voxel_lm(SEXP Sy, SEXP Sx, int n, int p, double *coefficients, double *resi
               double *se, double *t);
 SEXP vertex_lm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix);
 SEXP vertex_anova_loop(SEXP data, SEXP Sx, SEXP asgn);
+SEXP vertex_wlm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix, SEXP ws);
 SEXP per_voxel_anova(SEXP filenames, SEXP Sx, SEXP asgn, SEXP have_mask, SEXP mask, SEXP mask_lower_value,
                      SEXP mask_upper_value);
 SEXP minc2_model(SEXP filenames, SEXP filenames_right, SEXP mmatrix, SEXP asgn, SEXP have_mask,
@@ -459,5 +460,30 @@ int ref_per_voxel_anova(const double *Y, const int64_t sizes[3], int n, const do
     for (int i = 0; i < n; ++i) free(names[i]);
     free(names);
     rstub_clear_volumes();
+    return rc;
+}
+
+/* the reference's vertex_wlm_loop (anatLm(weights=)) on an in-memory V x n matrix. */
+int ref_vertex_wlm_loop(const double *Y, int64_t V, int n, const double *X, int p, const double *w, double *out,
+                        char *err, size_t errlen)
+{
+    SEXP left = alloc_obj(REALSXP, 0, 1);
+    free(left->data);
+    left->data = (void *)Y; left->len = (R_xlen_t)V * n; left->nrow = (int)V; left->ncol = n;
+    SEXP right = perm_logical_na_matrix();
+    SEXP mm = perm_real(X, (R_xlen_t)n * p, n, p);
+    SEXP ws = perm_real(w, n, 0, -1);
+    int rc = 0;
+    err_armed = 1;
+    if (setjmp(err_jmp) == 0) {
+        SEXP res = vertex_wlm_loop(left, right, mm, ws);
+        memcpy(out, REAL(res), sizeof(double) * (size_t)V * (2 * p + 3));
+    } else {
+        rc = 1;
+        if (err && errlen) snprintf(err, errlen, "%s", err_msg);
+    }
+    err_armed = 0;
+    reset_after_call();
+    left->data = NULL; perm_free(left); perm_free(right); perm_free(mm); perm_free(ws);
     return rc;
 }

@@ -50,6 +50,11 @@ mincLm_gpu <- function(formula, data = NULL, subset = NULL, mask = NULL, maskval
 vertex_lm_loop_gpu <- function(data.matrix.left, data.matrix.right, mmatrix)
   .Call("rmincgpu_vertex_lm_loop", data.matrix.left, data.matrix.right, mmatrix, PACKAGE = "rmincgpu")
 
+# anatLm(weights = w): .Call("vertex_wlm_loop", ...) at R/minc_anatomy.R:1135-1142
+vertex_wlm_loop_gpu <- function(data.matrix.left, data.matrix.right, mmatrix, weights)
+  .Call("rmincgpu_vertex_wlm_loop", data.matrix.left, data.matrix.right, mmatrix, as.double(weights),
+        PACKAGE = "rmincgpu")
+
 # Replacement for RMINC:::mincRandomize_core (identity post_proc only).  The permutation indices
 # are drawn here with R's own sample(), so a seed gives the same null distribution as the
 # reference; the refits happen on the GPU with Y resident instead of update(lmod, data = shuf).

@@ -31,6 +31,7 @@ SIGNATURES = {
     "rmg_design_factor": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.POINTER(C.c_int)] + _ERR),
     "rmg_vertex_lm": (C.c_int, _FIT_HEAD + [C.c_void_p, C.c_int64, C.c_int] + _ERR),
+    "rmg_vertex_wlm": (C.c_int, _FIT_HEAD + [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + _ERR),
     "rmg_lm_fit": (C.c_int, _FIT_HEAD + _MASK + [C.c_void_p, C.c_int64, C.c_int] + _ERR),
     "rmg_lm_fit_device": (C.c_int, _FIT_HEAD + _MASK + [C.c_void_p, C.c_int64, C.c_int, C.c_void_p] + _ERR),
     "rmg_anova_fit": (C.c_int, _FIT_HEAD + [C.c_void_p] + _MASK + [C.c_void_p, C.c_int64, C.c_int] + _ERR),

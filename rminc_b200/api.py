@@ -195,9 +195,6 @@ def vertexLm(formula: str, data, subset=None, column: int = 1, device: int = 0) 
 def anatLm(formula: str, data, anat, subset=None, weights=None, device: int = 0) -> MincMatrix:
     """`anat`: subjects x structures matrix (anatGetAll output); formula has no left-hand side
     ("~ Sex").  Rows of the result are structures (R/minc_anatomy.R:1125-1128, :1153)."""
-    if weights is not None:
-        raise NotImplementedError("anatLm(weights=) (vertex_wlm_loop, src/weighted_least_squares.c) is a "
-                                  "'next' row of the scope table and is not on the GPU path yet")
     lhs, rhs = split_formula(formula)
     if "$" in rhs:
         raise FormulaError("$ Not Permitted in Formula")
@@ -215,7 +212,12 @@ def anatLm(formula: str, data, anat, subset=None, weights=None, device: int = 0)
     if A.ndim != 2 or A.shape[0] != len(data):
         raise ValueError("anat must be a subjects x structures matrix with one row per row of data")
     Y = np.asfortranarray(A[rows, :].T)                                          # structures x subjects
-    out = core.vertex_lm(Y, X, device=device)
+    if weights is not None:
+        if len(weights) != X.shape[0]:
+            raise ValueError("Incorrect number of weights supplied, need one per observation")   # :1132-1134
+        out = core.vertex_wlm(Y, X, weights, device=device)                      # vertex_wlm_loop, :1135-1142
+    else:
+        out = core.vertex_lm(Y, X, device=device)
     n, p = X.shape
     rownames = list(getattr(anat, "columns", [])) or None
     attrs = {"atlas": getattr(anat, "atlas", None), "definitions": getattr(anat, "definitions", None), "model": X,

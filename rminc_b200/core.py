@@ -104,6 +104,23 @@ def vertex_lm(Y, X, device=0):
     return out
 
 
+def vertex_wlm(Y, X, weights, device=0):
+    """anatLm(weights=)'s native step (vertex_wlm_loop, src/weighted_least_squares.c:168)."""
+    Y, X, _ = _prep_host(Y, X, None)
+    V, n = Y.shape
+    p = X.shape[1]
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    if w.shape != (n,):
+        raise ValueError("Incorrect number of weights supplied, need one per observation")   # minc_anatomy.R:1133
+    out = np.empty((V, 2 * p + 3), order="F")
+    err = _lib.errbuf()
+    ld = max(V, 1)
+    rc = _lib.load().rmg_vertex_wlm(Y.ctypes.data, V, ld, n, X.ctypes.data, p, w.ctypes.data, out.ctypes.data, ld,
+                                    device, err, len(err))
+    _lib.check(rc, err)
+    return out
+
+
 def anova_fit(Y, X, asgn, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, device=0):
     """mincAnova / vertexAnova / anatAnova native step: V x nterms sequential F-statistics."""
     Y, X, m = _prep_host(Y, X, mask)

@@ -99,6 +99,8 @@ void fill_dev_design(const Design &D, DevDesign &dd)
     dd.pm1 = (double)(D.p - 1);
     dd.loglik_c = std::log(2 * M_PI) + 1 - std::log((double)D.n);
     dd.mhalf_n = -.5 * D.n;
+    dd.loglik_add = D.loglik_add;
+    if (!D.rowscale.empty()) dd.inv_n = 1.0 / D.sumw;   // weighted mean of the fitted values
     dd.mode = 0;
     dd.nterms = 0;
     dd.ncol_out = 2 * D.p + 3;
@@ -135,11 +137,15 @@ std::vector<double> make_qt(const Design &D, int KP)
     return qt;
 }
 
-int factor_or_fail(const double *X, int n, int p, Design &D, char *err, size_t errlen)
+int factor_or_fail(const double *X, int n, int p, Design &D, char *err, size_t errlen, const double *w)
 {
     for (size_t i = 0; i < (size_t)n * p; ++i)
         if (!std::isfinite(X[i])) return fail(err, errlen, RMG_ERR_INVALID, "model matrix contains non-finite values");
-    const int info = factor_design(X, n, p, D);
+    if (w)
+        for (int i = 0; i < n; ++i)
+            if (!(w[i] > 0.0) || !std::isfinite(w[i]))
+                return fail(err, errlen, RMG_ERR_INVALID, "weights must be finite and > 0 (weights[%d] = %g)", i, w[i]);
+    const int info = factor_design(X, n, p, D, w);
     if (info > 0) return fail(err, errlen, RMG_ERR_SINGULAR, "%s", singular_message(info).c_str());
     return RMG_OK;
 }
@@ -155,9 +161,11 @@ struct CachedDesign {
     int device = -1;
     std::vector<double> X;   // n x p, the key ...
     std::vector<int32_t> asgn;   // ... together with the term assignment (empty = lm epilogue)
+    std::vector<double> w;       // ... and the observation weights (empty = unweighted)
     Design D;
     DevDesign *dd = nullptr;
     double *qt = nullptr;
+    double *rowscale = nullptr;  // device copy of sqrt(w) (weighted fits)
     cudaEvent_t ready = nullptr;
     uint64_t last_use = 0;
     ~CachedDesign()
@@ -168,6 +176,7 @@ struct CachedDesign {
             cudaSetDevice(device);
             if (dd) cudaFree(dd);
             if (qt) cudaFree(qt);
+            if (rowscale) cudaFree(rowscale);
             if (ready) cudaEventDestroy(ready);
             cudaSetDevice(cur);
         }
@@ -181,7 +190,7 @@ constexpr size_t kCacheEntries = 16;
 
 // Looks up (or builds) the cached design for X on the current device.  rc != RMG_OK on error.
 std::shared_ptr<CachedDesign> design_cache_get(int device, const double *X, int n, int p, const int32_t *asgn,
-                                               int &rc, char *err, size_t errlen)
+                                               int &rc, char *err, size_t errlen, const double *w = nullptr)
 {
     const size_t cnt = (size_t)n * p;
     {
@@ -189,14 +198,16 @@ std::shared_ptr<CachedDesign> design_cache_get(int device, const double *X, int 
         for (auto &e : g_cache)
             if (e->device == device && e->D.n == n && e->D.p == p && std::memcmp(e->X.data(), X, cnt * 8) == 0 &&
                 e->asgn.size() == (asgn ? (size_t)p : 0) &&
-                (!asgn || std::memcmp(e->asgn.data(), asgn, (size_t)p * sizeof(int32_t)) == 0)) {
+                (!asgn || std::memcmp(e->asgn.data(), asgn, (size_t)p * sizeof(int32_t)) == 0) &&
+                e->w.size() == (w ? (size_t)n : 0) && (!w || std::memcmp(e->w.data(), w, (size_t)n * 8) == 0)) {
                 e->last_use = ++g_cache_tick;
                 rc = RMG_OK;
                 return e;
             }
     }
     auto e = std::make_shared<CachedDesign>();
-    if ((rc = factor_or_fail(X, n, p, e->D, err, errlen))) return nullptr;
+    if ((rc = factor_or_fail(X, n, p, e->D, err, errlen, w))) return nullptr;
+    if (w) e->w.assign(w, w + n);
     e->device = device;
     e->X.assign(X, X + cnt);
     DevDesign h;
@@ -219,11 +230,14 @@ std::shared_ptr<CachedDesign> design_cache_get(int device, const double *X, int 
     cudaStream_t up = nullptr;
     cudaError_t ce = cudaMalloc(reinterpret_cast<void **>(&e->dd), sizeof(DevDesign));
     if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void **>(&e->qt), qt_h.size() * sizeof(double));
+    if (ce == cudaSuccess && w) ce = cudaMalloc(reinterpret_cast<void **>(&e->rowscale), (size_t)n * sizeof(double));
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming);
     // upload on a private stream so a miss never serialises with the caller's queued work
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->dd, &h, sizeof h, cudaMemcpyHostToDevice, up);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->qt, qt_h.data(), qt_h.size() * sizeof(double), cudaMemcpyHostToDevice, up);
+    if (ce == cudaSuccess && w)
+        ce = cudaMemcpyAsync(e->rowscale, e->D.rowscale.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, up);
     if (ce == cudaSuccess) ce = cudaEventRecord(e->ready, up);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(up);   // pageable sources die with this scope
     if (up) cudaStreamDestroy(up);
@@ -342,16 +356,16 @@ int rmg_anova_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const 
 
 static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *asgn,
                          const double *mask, double mask_lo, double mask_hi, double *out, int64_t ldOut, int device,
-                         char *err, size_t errlen)
+                         char *err, size_t errlen, const double *w = nullptr)
 {
     int rc = check_fit_args(Y, V, ldY, n, X, p, out, ldOut, err, errlen);
     if (rc) return rc;
     {   // the reference fails on a singular design before it touches any voxel; so do we, GPU or not
         Design probe;
-        if (rmg_device_count() <= 0 && (rc = factor_or_fail(X, n, p, probe, err, errlen))) return rc;
+        if (rmg_device_count() <= 0 && (rc = factor_or_fail(X, n, p, probe, err, errlen, w))) return rc;
     }
     if ((rc = select_device(device, err, errlen))) return rc;
-    std::shared_ptr<CachedDesign> cd = design_cache_get(device, X, n, p, asgn, rc, err, errlen);
+    std::shared_ptr<CachedDesign> cd = design_cache_get(device, X, n, p, asgn, rc, err, errlen, w);
     if (!cd) return rc;
     g_last_kernel_ms = 0.0;
     const int ncol = asgn ? (int)*std::max_element(cd->asgn.begin(), cd->asgn.end()) : 2 * p + 3;
@@ -391,6 +405,7 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
             if (mask) RMG_CUDA(cudaMemcpyAsync(dM[b], mask + v0, (size_t)cv * 8, cudaMemcpyHostToDevice, st[b]));
             LmArgs a{dY[b], cv, ldc, n, p, cd->qt, cd->dd, mask ? dM[b] : nullptr, mask_lo, mask_hi, dO[b], ldc};
             a.ncol_out = ncol;
+            a.rowscale = cd->rowscale;
             LmLaunchInfo info;
             RMG_CUDA(cudaEventRecord(ev0[c], st[b]));
             RMG_CUDA(launch_lm_fit(a, plan, scr[b], st[b], &info));
@@ -439,6 +454,13 @@ int rmg_anova_fit(const double *Y, int64_t V, int64_t ldY, int n, const double *
 {
     if (!asgn) return fail(err, errlen, RMG_ERR_INVALID, "asgn is NULL");
     return fit_host_impl(Y, V, ldY, n, X, p, asgn, mask, mask_lo, mask_hi, out, ldOut, device, err, errlen);
+}
+
+int rmg_vertex_wlm(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *weights,
+                   double *out, int64_t ldOut, int device, char *err, size_t errlen)
+{
+    if (!weights) return fail(err, errlen, RMG_ERR_INVALID, "weights is NULL");
+    return fit_host_impl(Y, V, ldY, n, X, p, nullptr, nullptr, 0.0, 0.0, out, ldOut, device, err, errlen, weights);
 }
 
 int rmg_vertex_lm(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, double *out,

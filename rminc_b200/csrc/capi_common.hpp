@@ -80,6 +80,6 @@ inline void parallel_for(int count, Fn fn)
 }
 
 // Factor X and translate the reference's error contract.  0 or RMG_ERR_*.
-int factor_or_fail(const double *X, int n, int p, Design &D, char *err, size_t errlen);
+int factor_or_fail(const double *X, int n, int p, Design &D, char *err, size_t errlen, const double *w = nullptr);
 
 }  // namespace rmg

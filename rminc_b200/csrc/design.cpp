@@ -145,11 +145,29 @@ std::string singular_message(int info)
     return buf;
 }
 
-int factor_design(const double *X, int n, int p, Design &D)
+int factor_design(const double *X_in, int n, int p, Design &D, const double *w)
 {
     D = Design{};
     D.n = n;
     D.p = p;
+    D.sumw = n;
+    std::vector<double> Xw;
+    const double *X = X_in;
+    if (w) {   // :41-53: xws = sqrt(w); new_x = X * xws (row-wise)
+        D.rowscale.resize(n);
+        D.sumw = 0.0;
+        double tlw = 0.0;
+        for (int i = 0; i < n; ++i) {
+            tlw += std::log(w[i]);
+            D.rowscale[i] = std::sqrt(w[i]);
+            D.sumw += w[i];
+        }
+        D.loglik_add = 0.5 * tlw;
+        Xw.resize(static_cast<size_t>(n) * p);
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < p; ++j) Xw[i + static_cast<size_t>(j) * n] = X_in[i + static_cast<size_t>(j) * n] * D.rowscale[i];
+        X = Xw.data();
+    }
     const Householder H = reduce(X, n, p, 1e-7);
     const int k = H.rank;
     D.k = k;
@@ -169,21 +187,22 @@ int factor_design(const double *X, int n, int p, Design &D)
         for (int l = nref - 1; l >= 0; --l) apply_reflector(H, n, l, q);
     }
 
-    // q1 = Q'1 and the part of the constant vector outside span(Q).
+    // q1 = Q'u and the part of u outside span(Q), u = 1 (or sqrt(w) for weighted fits: the image of
+    // the constant vector in the scaled problem).
     D.q1.assign(p, 0.0);
     for (int c = 0; c < k; ++c) {
         const double *q = D.Q.data() + static_cast<size_t>(c) * n;
         double s = 0.0;
-        for (int i = 0; i < n; ++i) s += q[i];
+        for (int i = 0; i < n; ++i) s += q[i] * (w ? D.rowscale[i] : 1.0);
         D.q1[c] = s;
     }
     double gap = 0.0;
     for (int i = 0; i < n; ++i) {
-        double r = 1.0;
+        double r = w ? D.rowscale[i] : 1.0;
         for (int c = 0; c < k; ++c) r -= D.Q[i + static_cast<size_t>(c) * n] * D.q1[c];
         gap += r * r;
     }
-    D.has_intercept = gap < 1e-26 * n;
+    D.has_intercept = gap < 1e-26 * D.sumw;
     D.gap = D.has_intercept ? 0.0 : gap;
 
     // Inverse of the leading k x k triangle (used for beta = R_k^-1 Q_k'y).

@@ -28,10 +28,16 @@ struct Design {
     double gap = 0.0;                 // n - |q1|^2 = |1 - Q Q'1|^2; exactly 0 when 1 is in span(X)
     bool has_intercept = false;       // 1 in span(X): per-voxel shift by the first sample is exact
     int dpotri_info = 0;              // > 0: R[info,info] == 0 -> the reference raises an R error
+    // weighted least squares (voxel_wlm, src/weighted_least_squares.c:14-166); empty = unweighted
+    std::vector<double> rowscale;     // n: sqrt(w_j); every sample is multiplied by it before accumulation
+    double sumw = 0.0;                // sum of the weights (n when unweighted)
+    double loglik_add = 0.0;          // 0.5 * sum(log w_j)
 };
 
 // Returns 0, or dpotri_info (> 0) when the inverse cannot be formed.  Throws nothing.
-int factor_design(const double *X, int n, int p, Design &D);
+// w == nullptr: ordinary least squares.  Otherwise rows of X are scaled by sqrt(w) first and the
+// "constant vector" of the mean/intercept logic becomes sqrt(w) itself.
+int factor_design(const double *X, int n, int p, Design &D, const double *w = nullptr);
 
 // The reference's message for dpotri info > 0 (src/modelling_functions.c:554).
 std::string singular_message(int info);

@@ -13,11 +13,12 @@ constexpr int kMaxPDev = 32;
 struct DevDesign {
     int n, p, k, shift;     // shift = 1: 1 in span(X), voxels are centred on their first sample
     double gap;             // n - |Q'1|^2  (0 when shift)
-    double inv_n;           // 1/n
+    double inv_n;           // 1/n  (1/sum(w) for weighted fits)
     double rdf;             // n - p         (NOT n - rank: src/modelling_functions.c:534)
     double pm1;             // p - 1         (:542)
     double loglik_c;        // log(2*pi) + 1 - log(n)   (:527)
     double mhalf_n;         // -0.5 * n
+    double loglik_add;      // 0.5 * sum(log w) for weighted fits (src/weighted_least_squares.c:112), else 0
     double q1[kMaxPDev];    // Q'1
     double ct[kMaxPDev];    // diag((R'R)^-1), un-pivoted as the reference un-pivots se (:560-564)
     double Rinv[kMaxPDev * kMaxPDev];  // row-major: Rinv[i*kMaxPDev + j], upper triangle, k x k
@@ -33,7 +34,7 @@ struct SmemDesign {
     double q1[KP];
     double ct[KP];
     double Rinv[KP * KP];   // row-major KP x KP
-    double gap, inv_n, rdf, pm1, loglik_c, mhalf_n;
+    double gap, inv_n, rdf, pm1, loglik_c, mhalf_n, loglik_add;
     int n, p, k, shift;
     int mode, nterms, ncol_out, pad_;
     int term[KP];
@@ -53,7 +54,7 @@ __device__ __forceinline__ void load_design_to_smem(SmemDesign<KP> &s, const Dev
     for (int i = tid; i < KP * KP; i += nthreads) s.Rinv[i] = d->Rinv[(i / KP) * kMaxPDev + (i % KP)];
     if (tid == 0) {
         s.gap = d->gap; s.inv_n = d->inv_n; s.rdf = d->rdf; s.pm1 = d->pm1;
-        s.loglik_c = d->loglik_c; s.mhalf_n = d->mhalf_n;
+        s.loglik_c = d->loglik_c; s.mhalf_n = d->mhalf_n; s.loglik_add = d->loglik_add;
         s.n = d->n; s.p = d->p; s.k = d->k; s.shift = d->shift;
         s.mode = d->mode; s.nterms = d->nterms; s.ncol_out = d->ncol_out;
     }
@@ -128,7 +129,7 @@ __device__ __forceinline__ void finish_voxel(const VoxelSums<KP> &v, double rss,
     }
     out[0] = (mss / d.pm1) / resvar;                         // :542
     out[ld] = mss / (mss + rss);                             // :572
-    out[(int64_t)(2 * p + 2) * ld] = d.mhalf_n * (d.loglik_c + log(rss));  // :527
+    out[(int64_t)(2 * p + 2) * ld] = d.mhalf_n * (d.loglik_c + log(rss)) + d.loglik_add;  // :527
     // un-shift: e(y) = e(y - y0) + y0 * Q'1
     double e[KP];
 #pragma unroll
@@ -179,7 +180,7 @@ __device__ __forceinline__ void finish_pair(const VoxelSums<KP> &a, double rssa,
     }
     put(0, (mssa / d.pm1) / rva, (mssb / d.pm1) / rvb);
     put(1, mssa / (mssa + rssa), mssb / (mssb + rssb));
-    put(2 * p + 2, d.mhalf_n * (d.loglik_c + log(rssa)), d.mhalf_n * (d.loglik_c + log(rssb)));
+    put(2 * p + 2, d.mhalf_n * (d.loglik_c + log(rssa)) + d.loglik_add, d.mhalf_n * (d.loglik_c + log(rssb)) + d.loglik_add);
     double ea[KP], eb[KP];
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
@@ -231,34 +232,41 @@ __device__ __forceinline__ double2 ldg_stream2(const double *p)
 // pointers and recomputes e itself: passing the caller's accumulator struct by reference to a
 // non-inlined function forces it onto the local-memory stack for EVERY voxel (measured: 0.46 GB of
 // extra DRAM writes per config-2 launch).  Returns (rss, mss).
+// rowscale (sqrt of the weights) may be null.
 template <int KP>
 __device__ __noinline__ double2 exact_pass(const double *__restrict__ y, int64_t ld, int n,
-                                           const double *__restrict__ Qt, double y0)
+                                           const double *__restrict__ Qt, double y0,
+                                           const double *__restrict__ rowscale = nullptr)
 {
     double e[KP];
 #pragma unroll
     for (int k = 0; k < KP; ++k) e[k] = 0.0;
     for (int j = 0; j < n; ++j) {
-        const double yv = y[(int64_t)j * ld] - y0;
+        const double yv = (y[(int64_t)j * ld] - y0) * (rowscale ? rowscale[j] : 1.0);
 #pragma unroll
         for (int k = 0; k < KP; ++k) e[k] = fma(__ldg(Qt + (size_t)j * KP + k), yv, e[k]);
     }
-    double r2 = 0.0, sf = 0.0;
+    // in the scaled problem fit_j = sqrt(w_j) * fitted_j: weighted mean m = sum(s_j fit_j) / sum(s_j^2),
+    // mss = sum (fit_j - s_j m)^2   (s_j = 1: the ordinary mean / mss)
+    double r2 = 0.0, sf = 0.0, sw = 0.0;
     for (int j = 0; j < n; ++j) {
+        const double sj = rowscale ? rowscale[j] : 1.0;
         double fit = 0.0;
 #pragma unroll
         for (int k = 0; k < KP; ++k) fit = fma(__ldg(Qt + (size_t)j * KP + k), e[k], fit);
-        const double r = (y[(int64_t)j * ld] - y0) - fit;
+        const double r = (y[(int64_t)j * ld] - y0) * sj - fit;
         r2 = fma(r, r, r2);
-        sf += fit;
+        sf = fma(sj, fit, sf);
+        sw = fma(sj, sj, sw);
     }
-    const double mean = sf / n;
+    const double mean = sf / sw;
     double m2 = 0.0;
     for (int j = 0; j < n; ++j) {
+        const double sj = rowscale ? rowscale[j] : 1.0;
         double fit = 0.0;
 #pragma unroll
         for (int k = 0; k < KP; ++k) fit = fma(__ldg(Qt + (size_t)j * KP + k), e[k], fit);
-        const double dlt = fit - mean;
+        const double dlt = fma(-sj, mean, fit);
         m2 = fma(dlt, dlt, m2);
     }
     return make_double2(r2, m2);

@@ -299,12 +299,15 @@ lm_fit_tma_kernel(const __grid_constant__ CUtensorMap ymap, LmArgs a, const unsi
 // blockDim = (TX, S).  Thread (x, s) accumulates subjects [s*n/S, (s+1)*n/S) of voxels
 // (blockIdx.x*TX + x)*VPT .. +VPT-1; slices are reduced through shared memory and slice 0
 // runs the epilogue.  Shared memory: max(S x JT x KP Q rows, S x (KP+1) x VPT x TX partials).
-template <int KP, int VPT>
+// WGT: weighted least squares (voxel_wlm): every sample is multiplied by sqrt(w_j) (a.rowscale) after
+// the shift; the staged tile row carries that factor as an extra KP-th value.
+template <int KP, int VPT, bool WGT>
 __global__ void __launch_bounds__(256)
 lm_fit_ldg_kernel(LmArgs a, int JT)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SmemDesign<KP> sd;
+    constexpr int QW = KP + (WGT ? 1 : 0);   // doubles per staged row
     double *sQ = reinterpret_cast<double *>(smem_raw);
     const int TX = blockDim.x, S = blockDim.y;
     const int x = threadIdx.x, s = threadIdx.y;
@@ -347,14 +350,16 @@ lm_fit_ldg_kernel(LmArgs a, int JT)
         for (int sl = 0; sl < S; ++sl) {
             const int b = (int)(((int64_t)sl * n) / S) + t0;
             const int e = (int)(((int64_t)(sl + 1) * n) / S);
-            for (int i = tid; i < JT * KP; i += nthreads) {
-                const int j = b + i / KP;
-                sQ[(size_t)sl * JT * KP + i] = (j < e) ? a.Qt[(size_t)j * KP + (i % KP)] : 0.0;
+            for (int i = tid; i < JT * QW; i += nthreads) {
+                const int j = b + i / QW, c = i % QW;
+                double val = 0.0;
+                if (j < e) val = (c < KP) ? a.Qt[(size_t)j * KP + c] : a.rowscale[j];
+                sQ[(size_t)sl * JT * QW + i] = val;
             }
         }
         __syncthreads();
         if (!any) continue;
-        const double *q = sQ + (size_t)s * JT * KP;
+        const double *q = sQ + (size_t)s * JT * QW;
         const int cnt = min(JT, je - (jb + t0));
         int jj = 0;
         constexpr int U = 8;
@@ -375,10 +380,11 @@ lm_fit_ldg_kernel(LmArgs a, int JT)
             for (int u = 0; u < U; ++u) {
 #pragma unroll
                 for (int i = 0; i < VPT; ++i) {
-                    const double yv = y[u][i] - sum[i].y0;
+                    double yv = y[u][i] - sum[i].y0;
+                    if (WGT) yv *= q[(jj + u) * QW + KP];
                     sum[i].yy = fma(yv, yv, sum[i].yy);
 #pragma unroll
-                    for (int k = 0; k < KP; ++k) sum[i].e[k] = fma(q[(jj + u) * KP + k], yv, sum[i].e[k]);
+                    for (int k = 0; k < KP; ++k) sum[i].e[k] = fma(q[(jj + u) * QW + k], yv, sum[i].e[k]);
                 }
             }
         }
@@ -387,10 +393,11 @@ lm_fit_ldg_kernel(LmArgs a, int JT)
 #pragma unroll
             for (int i = 0; i < VPT; ++i) {
                 // VPT == 2 is only launched when every pair is fully in range and aligned
-                const double yv = src[i] - sum[i].y0;
+                double yv = src[i] - sum[i].y0;
+                if (WGT) yv *= q[jj * QW + KP];
                 sum[i].yy = fma(yv, yv, sum[i].yy);
 #pragma unroll
-                for (int k = 0; k < KP; ++k) sum[i].e[k] = fma(q[jj * KP + k], yv, sum[i].e[k]);
+                for (int k = 0; k < KP; ++k) sum[i].e[k] = fma(q[jj * QW + k], yv, sum[i].e[k]);
             }
         }
     }
@@ -428,7 +435,7 @@ lm_fit_ldg_kernel(LmArgs a, int JT)
         }
         double rss = sum[i].yy - sumsq_e(sum[i]), mss = mss_from_e(sum[i], sd);
         if (rss <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0) {
-            const double2 ex = exact_pass<KP>(a.Y + v + i, a.ldY, n, a.Qt, sum[i].y0);
+            const double2 ex = exact_pass<KP>(a.Y + v + i, a.ldY, n, a.Qt, sum[i].y0, WGT ? a.rowscale : nullptr);
             rss = ex.x;
             mss = ex.y;
         }
@@ -509,7 +516,7 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
     const bool tma_ok = aligned16 && a.V <= 0x7fffffffLL && KP <= 16;
     // With a mask the direct-load kernel skips at warp (64-voxel) granularity where the TMA ring
     // skips whole 256-voxel tiles: measured 2.72 ms vs 3.02 ms on config 2 with the 38 % ellipsoid.
-    bool use_tma = tma_ok && (plan.variant == LmVariant::Tma || (plan.variant == LmVariant::Auto && !a.mask));
+    bool use_tma = tma_ok && !a.rowscale && (plan.variant == LmVariant::Tma || (plan.variant == LmVariant::Auto && !a.mask));
     if (use_tma) {
         // Tile shapes (consumer warps, subjects per stage, ring depth, CTAs per SM):
         //   wide   4 x 64 = 256-voxel tiles, 4 CTAs/SM   -- large V (config 2: 4.5 ms, 98 % of the copy peak)
@@ -547,9 +554,9 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
         if (info) { info->launches++; info->used_tma = 1; info->tma_cfg = cfg; }
         return e;
     }
-    if (plan.variant == LmVariant::Tma) return cudaErrorInvalidValue;  // asked for TMA on a layout it cannot describe
+    if (plan.variant == LmVariant::Tma && !a.rowscale) return cudaErrorInvalidValue;  // asked for TMA on a layout it cannot describe
     // ---- LDG path: pick voxels/thread and the split factor
-    const bool vec2 = aligned16 && (a.V % 2 == 0) && (a.ldOut % 2 == 0) && KP <= 16;
+    const bool vec2 = aligned16 && (a.V % 2 == 0) && (a.ldOut % 2 == 0) && KP <= 16 && !a.rowscale;
     int S = plan.split;
     if (S <= 0) {
         // enough threads for ~2 waves of 1024 threads/SM; split the subject axis otherwise
@@ -563,8 +570,9 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
     const int span = (a.n + S - 1) / S;
     int JT = span;
     const size_t budget = 64 * 1024;
-    while ((size_t)S * JT * KP * 8 > budget) JT = (JT + 1) / 2;
-    size_t smem = (size_t)S * JT * KP * 8;
+    const int QW = KP + (a.rowscale ? 1 : 0);
+    while ((size_t)S * JT * QW * 8 > budget) JT = (JT + 1) / 2;
+    size_t smem = (size_t)S * JT * QW * 8;
     const size_t red = (size_t)S * (KP + 1) * VPT * TX * 8;
     if (S > 1 && red > smem) smem = red;
     const int64_t per_block = (int64_t)TX * VPT;
@@ -601,8 +609,9 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
     };
     cudaError_t e;
     constexpr int V2 = KP <= 16 ? 2 : 1;   // never instantiate the 2-voxel kernel for very wide designs
-    if (VPT == 2) e = go(lm_fit_ldg_kernel<KP, V2>);
-    else e = go(lm_fit_ldg_kernel<KP, 1>);
+    if (a.rowscale) e = go(lm_fit_ldg_kernel<KP, 1, true>);       // weighted fits: anatLm-sized problems
+    else if (VPT == 2) e = go(lm_fit_ldg_kernel<KP, V2, false>);
+    else e = go(lm_fit_ldg_kernel<KP, 1, false>);
     if (info) { info->launches++; info->used_tma = 0; info->split = S; }
     return e;
 }

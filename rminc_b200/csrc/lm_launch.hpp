@@ -21,6 +21,7 @@ struct LmArgs {
     int64_t ldOut;
     int out_vec2 = 0;          // set by launch_lm_fit: out is 16-byte aligned with an even ld
     int ncol_out = 0;          // result columns: 0 -> 2p+3 (lm); nterms for the anova epilogue
+    const double *rowscale = nullptr;  // n doubles sqrt(w_j) for weighted fits (direct-load kernel only), else null
     // mask compaction (direct-load kernel): ascending list of voxel PAIRS with at least one selected
     // voxel and their count, both device-resident; null = process every pair
     const uint32_t *pair_list = nullptr;

@@ -51,6 +51,24 @@ SEXP rmincgpu_vertex_lm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix)
     return out;
 }
 
+/* vertex_wlm_loop (src/weighted_least_squares.c:168): same arity as the reference routine. */
+SEXP rmincgpu_vertex_wlm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix, SEXP ws)
+{
+    if (!Rf_isLogical(data_right))
+        Rf_error("voxel-wise covariates (a file term on the right-hand side) are not on the GPU path");
+    if (!Rf_isReal(data_left) || !Rf_isReal(mmatrix) || !Rf_isReal(ws)) Rf_error("data_left, mmatrix and ws must be double");
+    const R_xlen_t V = Rf_nrows(data_left);
+    const int n = Rf_ncols(data_left), p = Rf_ncols(mmatrix);
+    if (Rf_nrows(mmatrix) != n || LENGTH(ws) != n) Rf_error("Incorrect number of weights supplied, need one per observation");
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, 2 * p + 3));
+    char err[512] = "";
+    int rc = rmg_vertex_wlm(REAL(data_left), V, V > 0 ? V : 1, n, REAL(mmatrix), p, REAL(ws), REAL(out), V > 0 ? V : 1, 0,
+                            err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
 SEXP rmincgpu_lm(SEXP Y, SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP mask_upper, SEXP ngpu)
 {
     if (!Rf_isReal(Y) || !Rf_isReal(mmatrix)) Rf_error("Y and mmatrix must be double matrices");
@@ -119,6 +137,7 @@ SEXP rmincgpu_anova(SEXP Y, SEXP mmatrix, SEXP asgn, SEXP mask, SEXP mask_lower,
 
 static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_vertex_lm_loop", (DL_FUNC)&rmincgpu_vertex_lm_loop, 3},
+    {"rmincgpu_vertex_wlm_loop", (DL_FUNC)&rmincgpu_vertex_wlm_loop, 4},
     {"rmincgpu_lm", (DL_FUNC)&rmincgpu_lm, 6},
     {"rmincgpu_randomize", (DL_FUNC)&rmincgpu_randomize, 9},
     {"rmincgpu_anova", (DL_FUNC)&rmincgpu_anova, 6},

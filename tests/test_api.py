@@ -30,6 +30,10 @@ def api(request, monkeypatch, oracle, lib):
         def anova_fit(Y, X, asgn, mask=None, mask_lo=1.0, mask_hi=99999999.0, device=0):
             return oracle.anova(Y, X, asgn, mask=mask, lo=mask_lo, hi=mask_hi)
 
+        def vertex_wlm(Y, X, weights, device=0):
+            return oracle.vertex_wlm_loop(Y, X, weights)
+
+        monkeypatch.setattr(core, "vertex_wlm", vertex_wlm)
         monkeypatch.setattr(core, "anova_fit", anova_fit)
         monkeypatch.setattr(core, "lm_fit", lm_fit)
         monkeypatch.setattr(core, "vertex_lm", vertex_lm)
@@ -150,8 +154,20 @@ def test_vertexLm_and_anatLm(api, tmp_path):
     ra = api.anatLm("~ Dx", gf, anat)
     assert ra.r_class == ("anatModel", "matrix") and ra.rownames == list("ABCDE") and ra.shape == (5, 7)
     check_row(ra, 2, anat.values[:, 2], X[:, :2], ["(Intercept)", "DxCN"])
-    with pytest.raises(NotImplementedError):
-        api.anatLm("~ Dx", gf, anat, weights=np.ones(n))
+    # weighted anatLm vs an independent WLS (tests/testthat/test_anatLm.R:121-148)
+    w = rng.uniform(0.5, 2.0, n)
+    rw = api.anatLm("~ Dx", gf, anat, weights=w)
+    Xw, yv = X[:, :2], anat.values[:, 3]
+    W = np.diag(w)
+    beta = np.linalg.solve(Xw.T @ W @ Xw, Xw.T @ W @ yv)
+    res = yv - Xw @ beta
+    wrss = (w * res ** 2).sum()
+    se = np.sqrt(np.diag(np.linalg.inv(Xw.T @ W @ Xw)) * wrss / (n - 2))
+    assert np.asarray(rw)[3, 2:4] == pytest.approx(beta, rel=1e-9)
+    assert np.asarray(rw)[3, 4:6] == pytest.approx(beta / se, rel=1e-9)
+    assert np.asarray(rw)[3, 6] == pytest.approx(0.5 * (np.log(w).sum() - n * (np.log(2 * np.pi) + 1 - np.log(n) + np.log(wrss))), rel=1e-10)
+    with pytest.raises(ValueError, match="Incorrect number of weights"):
+        api.anatLm("~ Dx", gf, anat, weights=np.ones(n - 1))
     gm = gf.copy()
     gm["M"] = [np.ones(3)] * n
     with pytest.raises(ValueError, match="A term in your model is a matrix"):

@@ -302,3 +302,22 @@ def test_anova_device_entry_point(core, oracle):
     out = core.anova_fit_torch(Yt, X, asgn)
     torch.cuda.synchronize()
     assert_rows_match(out.cpu().numpy().T, oracle.anova(Y, X, asgn), RTOL, "anova device")
+
+
+# ------------------------------------------------------------------ weighted least squares (scope row f-2)
+def test_weighted_fit_matches_oracle(core, oracle):
+    rng = np.random.default_rng(51)
+    for n, p, V in [(25, 3, 40), (120, 5, 3001), (500, 4, 2048)]:
+        X = design_cov(n, p, seed=p)
+        w = rng.uniform(0.2, 3.0, n)
+        Y = np.asfortranarray(rng.normal(1000, 5, (V, n)) + 3 * np.outer(rng.random(V), X[:, 1]))
+        Y[V // 2] = 0.0
+        assert_rows_match(core.vertex_wlm(Y, X, w), oracle.vertex_wlm_loop(Y, X, w), RTOL, f"wlm n={n}")
+    # unit weights reproduce the unweighted fit; no-intercept weighted design
+    assert_rows_match(core.vertex_wlm(Y, X, np.ones(n)), oracle.vertex_lm_loop(Y, X), RTOL, "unit weights")
+    Xn = rng.normal(size=(n, 3))
+    assert_rows_match(core.vertex_wlm(Y, Xn, w), oracle.vertex_wlm_loop(Y, Xn, w), RTOL, "wlm no intercept")
+    with pytest.raises(core.RmincGpuError, match="weights must be finite and > 0"):
+        core.vertex_wlm(Y, X, np.r_[0.0, np.ones(n - 1)])
+    with pytest.raises(ValueError, match="Incorrect number of weights"):
+        core.vertex_wlm(Y, X, np.ones(n - 1))

@@ -253,3 +253,31 @@ def test_anova_restatement(oracle):
         assert np.array_equal(oracle.anova(Y, X, asgn, mask=mask, lo=2, hi=2, use_ref=True, sizes=(3, 4, 5)), fm)  # per_voxel_anova
     g = np.load(os.path.join(GOLD, "ref_golden.npz"))
     assert np.array_equal(oracle.anova(g["D_Y"], g["D_X"], g["D_asgn"], mask=g["D_mask"]), g["D_out"])
+
+
+def test_weighted_least_squares_restatement(oracle):
+    """voxel_wlm (src/weighted_least_squares.c:14-166): equals the reference's object code bit for bit,
+    an independent WLS (tests/testthat/test_anatLm.R:121-148 compares with lm(weights=)), and reduces
+    to voxel_lm for unit weights."""
+    rng = np.random.default_rng(41)
+    n, V = 25, 40
+    X = np.column_stack([np.ones(n), np.arange(n) % 2, np.round(rng.normal(60, 10, n), 1)])
+    w = rng.uniform(0.5, 2.0, n)
+    Y = rng.normal(5, 1, (V, n))
+    out = oracle.vertex_wlm_loop(Y, X, w)
+    if oracle.have_ref():
+        assert np.array_equal(out, oracle.vertex_wlm_loop(Y, X, w, use_ref=True))
+    W = np.diag(w)
+    for v in (0, 13, 39):
+        y = Y[v]
+        beta = np.linalg.solve(X.T @ W @ X, X.T @ W @ y)
+        fitted = X @ beta
+        res = y - fitted
+        wrss = (w * res ** 2).sum()
+        m = (w * fitted).sum() / w.sum()
+        mss = (w * (fitted - m) ** 2).sum()
+        se = np.sqrt(np.diag(np.linalg.inv(X.T @ W @ X)) * wrss / (n - 3))
+        ll = 0.5 * (np.log(w).sum() - n * (np.log(2 * np.pi) + 1 - np.log(n) + np.log(wrss)))
+        want = np.r_[(mss / 2) / (wrss / (n - 3)), mss / (mss + wrss), beta, beta / se, ll]
+        assert out[v] == pytest.approx(want, rel=1e-9)
+    assert np.allclose(oracle.vertex_wlm_loop(Y, X, np.ones(n)), oracle.vertex_lm_loop(Y, X), rtol=1e-12, atol=0)
