@@ -427,6 +427,27 @@ def run_gpu_arm(args):
         assert bool(((chk - ref).abs() <= 1e-9 * scale).all()), "e2e result differs from device result"
         del hY, hO
 
+    # ---- the same call with PAGEABLE host memory (what R's heap is): informational
+    if rank == 0 and "e2e_pageable" in args.parts:
+        from rminc_b200 import _lib
+        lib = _lib.load()
+        err = _lib.errbuf()
+        Vp = min(V, 1769040)                       # a quarter of the volume: 7 GB of pageable host memory
+        Yp = np.empty((Vp, n), order="F")
+        Yp[:] = Yt[:, :Vp].T.cpu().numpy()
+        Op = np.empty((Vp, 2 * p + 3), order="F")
+        Xf2 = np.asfortranarray(X)
+        for it in range(2):
+            t0 = time.perf_counter()
+            rc = lib.rmg_lm_fit(Yp.ctypes.data, Vp, Vp, n, Xf2.ctypes.data, p, None, 1.0, 99999999.0,
+                                Op.ctypes.data, Vp, local_rank, err, len(err))
+            _lib.check(rc, err)
+            dtp = time.perf_counter() - t0
+        if e2e is None:
+            e2e = {}
+        e2e["pageable_host"] = {"value": Vp / dtp, "unit": UNIT, "voxels": Vp, "gbs": Vp * n * 8 / dtp / 1e9}
+        del Yp, Op
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and "cpu" in args.parts:

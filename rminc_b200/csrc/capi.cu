@@ -354,6 +354,61 @@ int rmg_anova_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const 
     return fit_device_impl(dY, V, ldY, n, X, p, asgn, dmask, mask_lo, mask_hi, dout, ldOut, device, stream, err, errlen);
 }
 
+// Pageable host memory (R's heap, plain numpy) reaches only ~9.5 GB/s through cudaMemcpy2DAsync
+// (the driver stages it single-threaded); pinned memory reaches the PCIe rate (55 GB/s).  For
+// pageable Y the rows of a chunk are therefore copied by all host threads into a small ring of
+// pinned staging buffers, and the DMA engine drains the ring while the next buffer is being filled.
+struct PinnedRing {
+    static constexpr int kSlots = 4;
+    double *buf[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    bool busy[kSlots] = {false, false, false, false};
+    size_t slot_doubles = 0;
+    int next = 0;
+    cudaError_t init(size_t doubles)
+    {
+        slot_doubles = doubles;
+        for (int s = 0; s < kSlots; ++s) {
+            cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&buf[s]), doubles * sizeof(double), cudaHostAllocDefault);
+            if (e != cudaSuccess) return e;
+            e = cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    // next free slot (waits for the DMA that last read it)
+    cudaError_t acquire(int &slot)
+    {
+        slot = next;
+        next = (next + 1) % kSlots;
+        if (busy[slot]) {
+            cudaError_t e = cudaEventSynchronize(done[slot]);
+            if (e != cudaSuccess) return e;
+            busy[slot] = false;
+        }
+        return cudaSuccess;
+    }
+    void release_all()
+    {
+        for (int s = 0; s < kSlots; ++s) {
+            if (done[s]) cudaEventDestroy(done[s]);
+            if (buf[s]) cudaFreeHost(buf[s]);
+            buf[s] = nullptr;
+            done[s] = nullptr;
+        }
+    }
+};
+
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
 static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *asgn,
                          const double *mask, double mask_lo, double mask_hi, double *out, int64_t ldOut, int device,
                          char *err, size_t errlen, const double *w = nullptr)
@@ -387,7 +442,13 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
     LmScratch scr[3];
     const LmPlan plan = plan_from_env(device);
     int64_t launches = 0;
+    PinnedRing ring;
+    // (small transfers are not worth four cudaHostAlloc calls)
+    const bool staged = !is_pinned_host(Y) && (double)V * n * 8.0 >= 256.0 * 1024 * 1024 && !std::getenv("RMG_NO_STAGING");
+    // rows (subjects) per staging slot: ~128 MiB
+    const int rows_per_slot = (int)std::max<int64_t>(1, std::min<int64_t>(n, (128ll << 20) / (8 * std::max<int64_t>(CV, 1))));
     {
+        if (staged) RMG_CUDA(ring.init((size_t)rows_per_slot * (size_t)std::min(CV, V)));
         for (int b = 0; b < NB; ++b) {
             RMG_CUDA(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
             RMG_CUDA(cudaMalloc(&dY[b], (size_t)ldc * n * sizeof(double)));
@@ -400,8 +461,30 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
             const int64_t v0 = c * CV, cv = std::min(CV, V - v0);
             RMG_CUDA(cudaEventCreate(&ev0[c]));
             RMG_CUDA(cudaEventCreate(&ev1[c]));
-            RMG_CUDA(cudaMemcpy2DAsync(dY[b], (size_t)ldc * 8, Y + v0, (size_t)ldY * 8, (size_t)cv * 8, (size_t)n,
-                                       cudaMemcpyHostToDevice, st[b]));
+            if (!staged) {
+                RMG_CUDA(cudaMemcpy2DAsync(dY[b], (size_t)ldc * 8, Y + v0, (size_t)ldY * 8, (size_t)cv * 8, (size_t)n,
+                                           cudaMemcpyHostToDevice, st[b]));
+            } else {
+                for (int r0 = 0; r0 < n; r0 += rows_per_slot) {
+                    const int rows = std::min(rows_per_slot, n - r0);
+                    int slot = 0;
+                    RMG_CUDA(ring.acquire(slot));
+                    double *dst = ring.buf[slot];
+                    // all host threads copy the strided rows of this group into the pinned slot
+                    const int64_t pieces = (int64_t)rows * 8;   // 8 column pieces per row keep every thread busy
+                    parallel_for((int)pieces, [&](int i0, int i1) {
+                        for (int i = i0; i < i1; ++i) {
+                            const int r = i / 8, part = i % 8;
+                            const int64_t a0 = cv * part / 8, a1 = cv * (part + 1) / 8;
+                            std::memcpy(dst + (size_t)r * cv + a0, Y + v0 + (int64_t)(r0 + r) * ldY + a0, (size_t)(a1 - a0) * 8);
+                        }
+                    });
+                    RMG_CUDA(cudaMemcpy2DAsync(dY[b] + (size_t)r0 * ldc, (size_t)ldc * 8, dst, (size_t)cv * 8, (size_t)cv * 8,
+                                               (size_t)rows, cudaMemcpyHostToDevice, st[b]));
+                    RMG_CUDA(cudaEventRecord(ring.done[slot], st[b]));
+                    ring.busy[slot] = true;
+                }
+            }
             if (mask) RMG_CUDA(cudaMemcpyAsync(dM[b], mask + v0, (size_t)cv * 8, cudaMemcpyHostToDevice, st[b]));
             LmArgs a{dY[b], cv, ldc, n, p, cd->qt, cd->dd, mask ? dM[b] : nullptr, mask_lo, mask_hi, dO[b], ldc};
             a.ncol_out = ncol;
@@ -438,6 +521,7 @@ cleanup:
     }
     for (auto e : ev0) if (e) cudaEventDestroy(e);
     for (auto e : ev1) if (e) cudaEventDestroy(e);
+    ring.release_all();
     if (rc != RMG_OK) cudaGetLastError();
     return rc;
 }
