@@ -59,6 +59,7 @@ def lib():
         _lib.orc_dnrm2.restype = C.c_double
         _lib.orc_anova_loop.restype = C.c_int
         _lib.orc_vertex_wlm_loop.restype = C.c_int
+        _lib.orc_lm_loop_cov.restype = C.c_int
     return _lib
 
 
@@ -71,7 +72,7 @@ def ref():
     if _ref is None:
         _ref = _load(_REF)
         for f in ("ref_voxel_lm", "ref_vertex_lm_loop", "ref_minc2_model_lm", "ref_vertex_anova_loop",
-                  "ref_per_voxel_anova", "ref_vertex_wlm_loop"):
+                  "ref_per_voxel_anova", "ref_vertex_wlm_loop", "ref_vertex_lm_loop_cov"):
             getattr(_ref, f).restype = C.c_int
     return _ref
 
@@ -277,6 +278,34 @@ def vertex_wlm_loop(Y, X, w, use_ref=False):
         return out
     info = lib().orc_vertex_wlm_loop(_p(Y), C.c_int64(V), C.c_int64(V), C.c_int(n), _p(X), C.c_int(p), _p(w), _p(out),
                                      C.c_int64(max(V, 1)))
+    if info:
+        raise OracleError(f"element ({info}, {info}) is zero, so the inverse cannot be computed")
+    return out
+
+
+def lm_loop_cov(Y, Z, Xs=None, mask=None, lo=1.0, hi=99999999.0, use_ref=False):
+    """Voxel-wise covariate design [Xs | z_v] (or [1 | z_v] when Xs is None): a file term on the
+    right-hand side of the formula (src/vertex_modelling.c:112-140).  V x (2p+3), p = ncol(Xs)+1."""
+    Y = _F(Y)
+    Z = _F(Z)
+    V, n = Y.shape
+    assert Z.shape == (V, n)
+    Xs_ = None if Xs is None else _F(Xs)
+    ps = 0 if Xs_ is None else Xs_.shape[1]
+    p = ps + 1 if Xs_ is not None else 2
+    out = np.zeros((V, 2 * p + 3), order="F")
+    m = None if mask is None else _f64(np.asarray(mask).reshape(-1))
+    if use_ref:
+        assert m is None
+        err = C.create_string_buffer(512)
+        rc = ref().ref_vertex_lm_loop_cov(_p(Y), _p(Z), C.c_int64(V), C.c_int(n), _p(Xs_) if Xs_ is not None else None,
+                                          C.c_int(ps), _p(out), err, C.c_size_t(512))
+        if rc:
+            raise OracleError(err.value.decode())
+        return out
+    info = lib().orc_lm_loop_cov(_p(Y), _p(Z), C.c_int64(V), C.c_int64(V), C.c_int(n),
+                                 _p(Xs_) if Xs_ is not None else None, C.c_int(ps), _p(m) if m is not None else None,
+                                 C.c_double(lo), C.c_double(hi), _p(out), C.c_int64(max(V, 1)))
     if info:
         raise OracleError(f"element ({info}, {info}) is zero, so the inverse cannot be computed")
     return out

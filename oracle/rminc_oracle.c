@@ -482,6 +482,45 @@ int orc_vertex_lm_loop(const double *Y, int64_t V, int64_t ldY, int n,
     return rc;
 }
 
+/* ----------------------------------- vertex_lm_loop / minc2_model with a voxel-wise covariate */
+/* src/vertex_modelling.c:112-140, src/modelling_functions.c:1118-1144: with a file term on the right-hand
+ * side the design of voxel i is [Xs | z_i] (p = ps + 1), or [1 | z_i] (p = 2) when there is no static part
+ * (Xs == NULL, ps == 0).  Z is V x n like Y.  mask may be NULL; masked rows are 0. */
+int orc_lm_loop_cov(const double *Y, const double *Z, int64_t V, int64_t ldY, int n, const double *Xs, int ps,
+                    const double *mask, double lo, double hi, double *out, int64_t ldOut)
+{
+    const int p = Xs ? ps + 1 : 2;
+    double *ybuf = (double *)malloc((size_t)n * sizeof(double));
+    double *xbuf = (double *)malloc((size_t)n * p * sizeof(double));
+    double *coef = (double *)malloc((size_t)p * sizeof(double));
+    double *stats = (double *)malloc((size_t)(p + 3) * sizeof(double));
+    int *pivot = (int *)malloc((size_t)p * sizeof(int));
+    int rank, rc = 0;
+    for (int64_t i = 0; i < V && rc == 0; ++i) {
+        if (mask && !(mask[i] > lo - 0.5 && mask[i] < hi + 0.5)) {
+            for (int k = 0; k < 2 * p + 3; ++k) out[i + k * ldOut] = 0.0;
+            continue;
+        }
+        for (int j = 0; j < n; ++j) ybuf[j] = Y[i + ldY * j];
+        if (!Xs) {
+            for (int j = 0; j < n; ++j) xbuf[j] = 1.0;
+            for (int j = 0; j < n; ++j) xbuf[j + n] = Z[i + ldY * j];
+        } else {
+            for (int j = 0; j < n * ps; ++j) xbuf[j] = Xs[j];
+            for (int j = 0; j < n; ++j) xbuf[j + (size_t)n * ps] = Z[i + ldY * j];
+        }
+        rc = orc_voxel_lm(ybuf, xbuf, n, p, coef, stats, pivot, &rank);
+        if (rc) break;
+        out[i] = stats[0];
+        out[i + 1 * ldOut] = stats[p + 1];
+        for (int k = 2; k < p + 2; ++k) out[i + k * ldOut] = coef[k - 2];
+        for (int k = 1; k < p + 1; ++k) out[i + (k + p + 1) * ldOut] = stats[k];
+        out[i + (2 * p + 2) * ldOut] = stats[p + 2];
+    }
+    free(ybuf); free(xbuf); free(coef); free(stats); free(pivot);
+    return rc;
+}
+
 /* ------------------------------------------------------- minc2_model, "lm" */
 /* src/modelling_functions.c:1012-1175 with the files already read: vol[i] is
  * subject i's volume (sizes[0]*sizes[1]*sizes[2] doubles in file dimension

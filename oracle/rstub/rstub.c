@@ -487,3 +487,30 @@ int ref_vertex_wlm_loop(const double *Y, int64_t V, int n, const double *X, int 
     left->data = NULL; perm_free(left); perm_free(right); perm_free(mm); perm_free(ws);
     return rc;
 }
+
+/* the reference's vertex_lm_loop with a voxel-wise covariate: data_right = Z (V x n); Xs may be NULL
+ * (mmatrix = logical NA -> design [1 | z]). */
+int ref_vertex_lm_loop_cov(const double *Y, const double *Z, int64_t V, int n, const double *Xs, int ps, double *out,
+                           char *err, size_t errlen)
+{
+    const int p = Xs ? ps + 1 : 2;
+    SEXP left = alloc_obj(REALSXP, 0, 1), right = alloc_obj(REALSXP, 0, 1);
+    free(left->data); free(right->data);
+    left->data = (void *)Y; left->len = (R_xlen_t)V * n; left->nrow = (int)V; left->ncol = n;
+    right->data = (void *)Z; right->len = (R_xlen_t)V * n; right->nrow = (int)V; right->ncol = n;
+    SEXP mm = Xs ? perm_real(Xs, (R_xlen_t)n * ps, n, ps) : perm_logical_na_matrix();
+    int rc = 0;
+    err_armed = 1;
+    if (setjmp(err_jmp) == 0) {
+        SEXP res = vertex_lm_loop(left, right, mm);
+        memcpy(out, REAL(res), sizeof(double) * (size_t)V * (2 * p + 3));
+    } else {
+        rc = 1;
+        if (err && errlen) snprintf(err, errlen, "%s", err_msg);
+    }
+    err_armed = 0;
+    reset_after_call();
+    left->data = NULL; right->data = NULL;
+    perm_free(left); perm_free(right); perm_free(mm);
+    return rc;
+}

@@ -58,6 +58,16 @@ def main():
     mask = (rng.random(V) > 0.3).astype(float)
     out["D_X"], out["D_Y"], out["D_asgn"], out["D_mask"] = X, Y, asgn, mask
     out["D_out"] = O.anova(Y, X, asgn, mask=mask, use_ref=True, sizes=dims)
+    # case E: voxel-wise covariate (a file term on the right-hand side): vertex_lm_loop with data_right,
+    # static part [1, group] and no static part ([1 | z]); one vertex with a constant covariate (rank p-1)
+    n, V = 20, 40
+    Xs = np.column_stack([np.ones(n), np.arange(n) % 2]).astype(float)
+    Y = np.asfortranarray(rng.normal(2.0, 0.5, (V, n)))
+    Z = np.asfortranarray(rng.normal(100.0, 3.0, (V, n)))
+    Z[7, :] = 42.0
+    out["E_Xs"], out["E_Y"], out["E_Z"] = Xs, Y, Z
+    out["E_out_static"] = O.lm_loop_cov(Y, Z, Xs, use_ref=True)
+    out["E_out_nostatic"] = O.lm_loop_cov(Y, Z, None, use_ref=True)
     np.savez_compressed(os.path.join(os.path.dirname(__file__), "ref_golden.npz"), **out)
     print("wrote ref_golden.npz:", {k: v.shape for k, v in out.items()})
 

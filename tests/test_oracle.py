@@ -281,3 +281,38 @@ def test_weighted_least_squares_restatement(oracle):
         want = np.r_[(mss / 2) / (wrss / (n - 3)), mss / (mss + wrss), beta, beta / se, ll]
         assert out[v] == pytest.approx(want, rel=1e-9)
     assert np.allclose(oracle.vertex_wlm_loop(Y, X, np.ones(n)), oracle.vertex_lm_loop(Y, X), rtol=1e-12, atol=0)
+
+
+def test_voxelwise_covariate_restatement(oracle):
+    """A file term on the right-hand side (src/vertex_modelling.c:112-140, src/modelling_functions.c:1118-1144):
+    the design of voxel v is [Xs | z_v], or [1 | z_v] without a static part.  Equals the reference's object
+    code bit for bit, the committed golden vectors, and an independent per-voxel OLS."""
+    g = np.load(os.path.join(GOLD, "ref_golden.npz"))
+    Y, Z, Xs = g["E_Y"], g["E_Z"], g["E_Xs"]
+    a = oracle.lm_loop_cov(Y, Z, Xs)
+    b = oracle.lm_loop_cov(Y, Z, None)
+    assert np.array_equal(a, g["E_out_static"]) and np.array_equal(b, g["E_out_nostatic"])
+    if oracle.have_ref():
+        assert np.array_equal(a, oracle.lm_loop_cov(Y, Z, Xs, use_ref=True))
+        assert np.array_equal(b, oracle.lm_loop_cov(Y, Z, None, use_ref=True))
+    n = Y.shape[1]
+    for v in (0, 11, 39):
+        for out, X in ((a, np.column_stack([Xs, Z[v]])), (b, np.column_stack([np.ones(n), Z[v]]))):
+            w = numpy_ols(Y[v], X)
+            p = X.shape[1]
+            want = np.r_[w["F"], w["R2"], w["coef"], w["t"], w["logLik"]]
+            assert out[v] == pytest.approx(want, rel=1e-8), (v, p)
+    # vertex 7 has a constant covariate: negligible column -> rank p-1, beta = 0 and t = 0 in its slot, the other
+    # betas are the fit without it (dqrdc2's limited pivoting, SURVEY A.3)
+    assert a[7, 4] == 0.0 and a[7, 7] == 0.0
+    w = numpy_ols(Y[7], Xs)
+    assert a[7, 2:4] == pytest.approx(w["coef"], rel=1e-9)
+    # masked rows are 0 in every column
+    mask = (np.arange(Y.shape[0]) % 3 != 0).astype(float)
+    am = oracle.lm_loop_cov(Y, Z, Xs, mask=mask)
+    assert np.array_equal(am[mask > 0.5], a[mask > 0.5]) and (am[mask < 0.5] == 0).all()
+    # an all-zero covariate at an unmasked voxel is the reference's dpotri error (exact zero on R's diagonal)
+    Z0 = Z.copy()
+    Z0[3, :] = 0.0
+    with pytest.raises(oracle.OracleError, match="is zero, so the inverse cannot be computed"):
+        oracle.lm_loop_cov(Y, Z0, Xs)
