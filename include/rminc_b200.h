@@ -109,6 +109,33 @@ int rmg_lm_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const dou
                       char *err, size_t errlen);
 
 /*
+ * Voxel-wise covariate: a MINC file (or vertex file) term on the right-hand side of the formula, e.g.
+ * mincLm(jacobians ~ group + otherVolume).  The design of voxel v is [Xs | z_v] (p = ps + 1 columns), or
+ * [1 | z_v] (p = 2) when there is no static part.  Drop-in for minc2_model(filenames, filenames_right, mmatrix, ...)
+ * with filenames_right a file list (src/modelling_functions.c:848-854, :1118-1144; R caller
+ * R/minc_voxel_statistics.R:695-712 with parseLmFormula's data.matrix.right, R/minc_interface.R:1266-1300) and for
+ *   SEXP vertex_lm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix)
+ * with data_right a V x n matrix (src/vertex_modelling.c:33-55, :112-140).
+ *   Z     V x n host matrix, same leading dimension as Y          (data_right / filenames_right staged like Y)
+ *   Xs    n x ps static model matrix; NULL or ps = 0 means "no static part" (mmatrix = logical NA)
+ *   out   V x (2p+3), p = ps + 1 (2 without a static part); the covariate's beta / t are the LAST of each block
+ * Per-voxel pivoting as dqrdc2 decides it for the last column: a covariate that is (numerically) in the span of
+ * Xs at some voxel gives rank p-1 there: beta = 0 and t = 0 in its slot, the rest is the fit on Xs alone.  A
+ * covariate that is exactly zero for every subject at a fitted voxel fails the whole call with RMG_ERR_SINGULAR,
+ * as the reference's dpotri check does.  Xs must have full column rank (RMG_ERR_INVALID otherwise), ps <= 16.
+ */
+int rmg_lm_fit_cov(const double *Y, const double *Z, int64_t V, int64_t ldY, int n, const double *Xs, int ps,
+                   const double *mask, double mask_lo, double mask_hi,
+                   double *out, int64_t ldOut, int device, char *err, size_t errlen);
+int rmg_vertex_lm_cov(const double *Y, const double *Z, int64_t V, int64_t ldY, int n, const double *Xs, int ps,
+                      double *out, int64_t ldOut, int device, char *err, size_t errlen);
+/* Device-resident form, enqueued on `stream` without synchronising.  dstatus (nullable) is a device int32 the
+ * caller zeroes beforehand: it is raised to p when a fitted voxel's covariate is all zero (those rows are NaN). */
+int rmg_lm_fit_cov_device(const double *dY, const double *dZ, int64_t V, int64_t ldY, int n, const double *Xs, int ps,
+                          const double *dmask, double mask_lo, double mask_hi, double *dout, int64_t ldOut,
+                          int32_t *dstatus, int device, void *stream, char *err, size_t errlen);
+
+/*
  * mincAnova / vertexAnova / anatAnova.  Drop-in for per_voxel_anova (src/minc_anova.c:142-304;
  * R caller R/minc_voxel_statistics.R:557-566) and vertex_anova_loop (src/vertex_modelling.c:178;
  * R callers R/minc_vertex_statistics.R:314-320, R/minc_anatomy.R anatAnova), whose per-voxel body is
@@ -171,7 +198,7 @@ int rmg_randomize_multi(const double *Y, int64_t V, int64_t ldY, int n, const do
  * kernels were launched on (host entry points only; 0 if unavailable). */
 double rmg_last_kernel_ms(void);
 /* Which fit kernel the most recent fit on this thread launched: 1 = TMA-staged ring,
- * 2 = direct streaming loads (+ split-n), 0 = none yet. */
+ * 2 = direct streaming loads (+ split-n), 3 = voxel-wise covariate kernel, 0 = none yet. */
 int rmg_last_fit_variant(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t rmg_launch_count(void);

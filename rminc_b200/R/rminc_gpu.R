@@ -28,10 +28,14 @@ rmincgpu_stage <- function(filenames) {
 
 # Replacement for RMINC:::mincLm_c_wrapper.  `mask` may be a file name or NULL.
 mincLm_c_wrapper <- function(plm, mask, mask_min, mask_max, n_gpus = rmincgpu_n()) {
-  if (!is.logical(plm$data.matrix.right))
-    stop("voxel-wise covariates are not on the GPU path; use the CPU RMINC for this model")
   Y <- rmincgpu_stage(as.character(plm$data.matrix.left))
   m <- if (is.null(mask)) NULL else as.double(mincGetVolume(mask))
+  if (!is.logical(plm$data.matrix.right)) {
+    # a file term on the right-hand side: per-voxel design [mmatrix | z_v] (one GPU)
+    Z <- rmincgpu_stage(as.character(plm$data.matrix.right))
+    mm <- if (is.logical(plm$mmatrix)) plm$mmatrix else as.matrix(plm$mmatrix)
+    return(.Call("rmincgpu_lm_cov", Y, Z, mm, m, as.double(mask_min), as.double(mask_max), PACKAGE = "rmincgpu"))
+  }
   .Call("rmincgpu_lm", Y, as.matrix(plm$mmatrix), m, as.double(mask_min), as.double(mask_max),
         as.integer(n_gpus), PACKAGE = "rmincgpu")
 }

@@ -27,7 +27,7 @@ from typing import Callable, Dict, List, Optional, Sequence
 import numpy as np
 
 from . import core
-from .formula import FormulaError, model_matrix, split_formula
+from .formula import FormulaError, model_matrix, parse_rhs, split_formula
 
 
 # ----------------------------------------------------------------------------- result objects
@@ -144,6 +144,57 @@ def _stage_mask(mask, V, reader):
     return m
 
 
+# ----------------------------------------------------------------------------- parseLmFormula
+def _is_file_term(data, name, rows) -> bool:
+    """A right-hand-side term whose entries are volumes (file names or arrays) rather than numbers:
+    parseLmFormula's `file.info(term[1])` / '\\.mnc$' test (R/minc_interface.R:1266, :1295-1296)."""
+    try:
+        c = data[name]
+    except Exception:  # noqa: BLE001
+        return False
+    first = c.iloc[rows[0]] if hasattr(c, "iloc") else c[rows[0]]
+    if isinstance(first, np.ndarray):
+        return first.ndim >= 1
+    if isinstance(first, (str, os.PathLike)):
+        path = os.fspath(first)
+        return path.endswith(".mnc") or os.path.exists(path)
+    return False
+
+
+def parseLmFormula(rhs: str, data, rows):
+    """Mirror of parseLmFormula (R/minc_interface.R:1234-1324): finds a voxel-wise (file) term on the right-hand
+    side.  Returns dict(matrixFound, mmatrix (static part or None), rows (coefficient names), right (the file
+    column's entries))."""
+    intercept, terms = parse_rhs(rhs)
+    file_terms = [t[0] for t in terms if len(t) == 1 and _is_file_term(data, t[0], rows)]
+    if not file_terms:
+        return dict(matrixFound=False, mmatrix=None, rows=None, right=None)
+    name = file_terms[0]
+    if len(terms) == 1:
+        # one term: design [1 | z]; the reference labels the intercept 'Intercept' here (:1270)
+        return dict(matrixFound=True, mmatrix=None, rows=["Intercept", name], right=_column(data, name, rows))
+    if "*" in rhs or ":" in rhs:
+        raise FormulaError("Only + sign allowed when using filenames")           # :1298
+    if len(terms) > 2 or len(file_terms) > 1:
+        raise FormulaError("Only 2 terms allowed when using filenames on the RHS")   # :1301
+    other = [t[0] for t in terms if t[0] != name][0]
+    X, names, _ = model_matrix(other if intercept else other + " - 1", data, rows)   # :1304-1311
+    return dict(matrixFound=True, mmatrix=X, rows=names + [name], right=_column(data, name, rows))
+
+
+def _cov_attrs(n, plm):
+    """model / df attributes in the file-covariate case: the reference derives them from the STATIC model
+    matrix alone (R/minc_voxel_statistics.R:908, :929-935), so Fdf1 = ncol(mmatrix) - 1, Fdf2 = n - ncol(mmatrix)
+    (0, 0 for the 1 x 1 NA matrix of the no-static case); mirrored as is."""
+    X = plm["mmatrix"]
+    p = len(plm["rows"])
+    if X is None:
+        model, f1, f2 = np.array([[np.nan]]), 0, 0
+    else:
+        model, f1, f2 = X, X.shape[1] - 1, n - X.shape[1]
+    return model, [[f1, f2]] + [f2] * p
+
+
 # ----------------------------------------------------------------------------- mincLm
 def mincLm(formula: str, data, subset=None, mask=None, maskval=None, parallel=None,
            reader: Callable = default_reader, device: int = 0) -> MincMatrix:
@@ -154,12 +205,27 @@ def mincLm(formula: str, data, subset=None, mask=None, maskval=None, parallel=No
     reference's parallel path, maskval is honoured on both paths."""
     lhs, rhs = split_formula(formula)
     rows = _subset_rows(data, subset)
-    X, names, _ = model_matrix(rhs, data, rows)
+    plm = parseLmFormula(rhs, data, rows)                                        # :796
     filenames = _column(data, lhs, rows)
     Y = mincTable(filenames, reader=reader)
     V, n = Y.shape
     m = _stage_mask(mask, V, reader)
     lo, hi = core.mask_range(maskval)                                            # :781-787
+    if plm["matrixFound"]:
+        # a volume on the right-hand side: per-voxel design [mmatrix | z_v] (minc2_model with filenames_right)
+        Z = mincTable(plm["right"], reader=reader)
+        if Z.shape != Y.shape:
+            raise ValueError("the right-hand-side volumes must match the left-hand-side volumes")
+        out = core.lm_fit_cov(Y, Z, plm["mmatrix"], mask=m, mask_lo=lo, mask_hi=hi, device=device)
+        model, dflist = _cov_attrs(n, plm)
+        p = len(plm["rows"])
+        attrs = {
+            "likeVolume": filenames[0], "filenames": list(filenames), "model": model, "data": data,
+            "call": dict(fn="mincLm", formula=formula, subset=subset, mask=mask, maskval=maskval, parallel=parallel),
+            "stat-type": _stat_type(p), "df": dflist, "model-colnames": plm["rows"],
+        }
+        return MincMatrix(out, colnames=_colnames(plm["rows"]), attrs=attrs, r_class=("mincLm", "mincMultiDim", "matrix"))
+    X, names, _ = model_matrix(rhs, data, rows)
     n_gpus = None
     if parallel is not None:
         n_gpus = int(parallel[1])
@@ -180,9 +246,22 @@ def vertexLm(formula: str, data, subset=None, column: int = 1, device: int = 0) 
     if "$" in rhs:
         raise FormulaError("$ Not Permitted in Formula")                        # minc_vertex_statistics.R:380
     rows = _subset_rows(data, subset)
-    X, names, _ = model_matrix(rhs, data, rows)
+    plm = parseLmFormula(rhs, data, rows)                                        # minc_vertex_statistics.R:391
     filenames = _column(data, lhs, rows)
     Y = vertexTable(filenames, column=column)
+    if plm["matrixFound"]:
+        Z = vertexTable(plm["right"], column=column)                             # :398-401
+        if Z.shape != Y.shape:
+            raise ValueError("the right-hand-side vertex files must match the left-hand-side files")
+        out = core.lm_fit_cov(Y, Z, plm["mmatrix"], device=device)               # vertex_lm_loop with data_right
+        model, dflist = _cov_attrs(Y.shape[1], plm)
+        p = len(plm["rows"])
+        attrs = {"likeVolume": filenames[0], "model": model, "filenames": list(filenames), "stat-type": _stat_type(p),
+                 "data": data, "call": dict(fn="vertexLm", formula=formula, subset=subset, column=column),
+                 "df": dflist, "model-colnames": plm["rows"]}
+        return MincMatrix(out, colnames=_colnames(plm["rows"]), attrs=attrs,
+                          r_class=("vertexLm", "vertexMultiDim", "matrix"))
+    X, names, _ = model_matrix(rhs, data, rows)
     out = core.vertex_lm(Y, X, device=device)
     n, p = X.shape
     attrs = {"likeVolume": filenames[0], "model": X, "filenames": list(filenames), "stat-type": _stat_type(p),

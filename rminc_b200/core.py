@@ -104,6 +104,66 @@ def vertex_lm(Y, X, device=0):
     return out
 
 
+def lm_fit_cov(Y, Z, Xs=None, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, device=0):
+    """Voxel-wise covariate design [Xs | z_v] ([1 | z_v] when Xs is None): a file term on the right-hand side
+    (src/vertex_modelling.c:112-140, src/modelling_functions.c:1118-1144).  V x (2p+3), p = ncol(Xs) + 1."""
+    Y = np.asarray(Y)
+    if Y.ndim != 2:
+        raise ValueError("Y must be V x n")
+    V, n = Y.shape
+    Xs_ = None if Xs is None else _lib.as_f64_fortran(Xs)
+    if Xs_ is not None and (Xs_.ndim != 2 or Xs_.shape[0] != n):
+        raise ValueError(f"Xs must be n x ps with n == ncol(Y); got {Xs_.shape} vs {Y.shape}")
+    if not (Y.dtype == np.float64 and Y.flags.f_contiguous):
+        Y = _lib.as_f64_fortran(Y)
+    Z = np.asarray(Z)
+    if Z.shape != Y.shape:
+        raise ValueError("the voxel-wise covariate must have the shape of Y")
+    if not (Z.dtype == np.float64 and Z.flags.f_contiguous):
+        Z = _lib.as_f64_fortran(Z)
+    m = None
+    if mask is not None:
+        m = np.ascontiguousarray(np.asarray(mask, dtype=np.float64).reshape(-1))
+        if m.shape[0] != V:
+            raise ValueError("mask length must equal the number of voxels")
+    ps = 0 if Xs_ is None else Xs_.shape[1]
+    p = ps + 1 if ps else 2
+    out = np.empty((V, 2 * p + 3), order="F")
+    err = _lib.errbuf()
+    ld = max(V, 1)
+    rc = _lib.load().rmg_lm_fit_cov(Y.ctypes.data, Z.ctypes.data, V, ld, n, Xs_.ctypes.data if ps else None, ps,
+                                    m.ctypes.data if m is not None else None, mask_lo, mask_hi, out.ctypes.data, ld,
+                                    device, err, len(err))
+    _lib.check(rc, err)
+    return out
+
+
+def lm_fit_cov_torch(Yt, Zt, Xs=None, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, out=None,
+                     status=None):
+    """Device-resident form: Yt, Zt (n, V) float64 CUDA tensors with the same row stride -> (2p+3, V) tensor.
+    `status`: optional zeroed int32 CUDA tensor of one element, raised when a fitted covariate row is all zero."""
+    import torch
+    for t in (Yt, Zt):
+        if not (t.is_cuda and t.dtype == torch.float64 and t.dim() == 2 and t.stride(1) == 1):
+            raise ValueError("Yt / Zt must be float64 CUDA tensors of shape (n, V) with unit stride along V")
+    n, V = Yt.shape
+    if Zt.shape != Yt.shape or (n > 1 and Zt.stride(0) != Yt.stride(0)):
+        raise ValueError("Zt must have Yt's shape and row stride")
+    Xs_ = None if Xs is None else _lib.as_f64_fortran(Xs)
+    ps = 0 if Xs_ is None else Xs_.shape[1]
+    p = ps + 1 if ps else 2
+    if out is None:
+        out = torch.empty((2 * p + 3, V), dtype=torch.float64, device=Yt.device)
+    mp = mask.data_ptr() if mask is not None else None
+    err = _lib.errbuf()
+    rc = _lib.load().rmg_lm_fit_cov_device(Yt.data_ptr(), Zt.data_ptr(), V, Yt.stride(0) if n > 1 else max(V, 1), n,
+                                           Xs_.ctypes.data if ps else None, ps, mp, mask_lo, mask_hi, out.data_ptr(),
+                                           out.stride(0), status.data_ptr() if status is not None else None,
+                                           Yt.device.index or 0, _torch_stream(Yt), err, len(err))
+    _lib.check(rc, err)
+    return out
+
+
 def vertex_wlm(Y, X, weights, device=0):
     """anatLm(weights=)'s native step (vertex_wlm_loop, src/weighted_least_squares.c:168)."""
     Y, X, _ = _prep_host(Y, X, None)
@@ -269,4 +329,4 @@ def launch_count() -> int:
 
 
 def last_fit_variant() -> str:
-    return {0: "none", 1: "lm_fit_tma_kernel", 2: "lm_fit_ldg_kernel"}[_lib.load().rmg_last_fit_variant()]
+    return {0: "none", 1: "lm_fit_tma_kernel", 2: "lm_fit_ldg_kernel", 3: "lm_cov_kernel"}[_lib.load().rmg_last_fit_variant()]

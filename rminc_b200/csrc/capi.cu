@@ -411,10 +411,12 @@ static bool is_pinned_host(const void *p)
 
 static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *asgn,
                          const double *mask, double mask_lo, double mask_hi, double *out, int64_t ldOut, int device,
-                         char *err, size_t errlen, const double *w = nullptr)
+                         char *err, size_t errlen, const double *w = nullptr, const double *Z = nullptr)
 {
+    // Z != nullptr: voxel-wise covariate design [X | z_v]; X is the static part (lm_cov.cu)
     int rc = check_fit_args(Y, V, ldY, n, X, p, out, ldOut, err, errlen);
     if (rc) return rc;
+    if (Z && p + 1 > 17) return fail(err, errlen, RMG_ERR_INVALID, "voxel-wise covariate designs support at most 16 static columns (got %d)", p);
     {   // the reference fails on a singular design before it touches any voxel; so do we, GPU or not
         Design probe;
         if (rmg_device_count() <= 0 && (rc = factor_or_fail(X, n, p, probe, err, errlen, w))) return rc;
@@ -422,8 +424,11 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
     if ((rc = select_device(device, err, errlen))) return rc;
     std::shared_ptr<CachedDesign> cd = design_cache_get(device, X, n, p, asgn, rc, err, errlen, w);
     if (!cd) return rc;
+    if (Z && cd->D.k < p)
+        return fail(err, errlen, RMG_ERR_INVALID,
+                    "rank-deficient static design (rank %d < %d columns) with a voxel-wise covariate is not supported", cd->D.k, p);
     g_last_kernel_ms = 0.0;
-    const int ncol = asgn ? (int)*std::max_element(cd->asgn.begin(), cd->asgn.end()) : 2 * p + 3;
+    const int ncol = Z ? 2 * (p + 1) + 3 : asgn ? (int)*std::max_element(cd->asgn.begin(), cd->asgn.end()) : 2 * p + 3;
     if (V == 0 || ncol == 0) return RMG_OK;
 
     // Voxel chunks of ~1 GiB of Y (measured on B200/PCIe5: 256 MiB chunks reach 61 % of the pinned
@@ -438,6 +443,8 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
 
     cudaStream_t st[3] = {nullptr, nullptr, nullptr};
     double *dY[3] = {nullptr, nullptr, nullptr}, *dO[3] = {nullptr, nullptr, nullptr}, *dM[3] = {nullptr, nullptr, nullptr};
+    double *dZ[3] = {nullptr, nullptr, nullptr};
+    int *dstatus = nullptr;
     std::vector<cudaEvent_t> ev0(nchunks, nullptr), ev1(nchunks, nullptr);
     LmScratch scr[3];
     const LmPlan plan = plan_from_env(device);
@@ -454,6 +461,11 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
             RMG_CUDA(cudaMalloc(&dY[b], (size_t)ldc * n * sizeof(double)));
             RMG_CUDA(cudaMalloc(&dO[b], (size_t)ldc * ncol * sizeof(double)));
             if (mask) RMG_CUDA(cudaMalloc(&dM[b], (size_t)ldc * sizeof(double)));
+            if (Z) RMG_CUDA(cudaMalloc(&dZ[b], (size_t)ldc * n * sizeof(double)));
+        }
+        if (Z) {
+            RMG_CUDA(cudaMalloc(&dstatus, sizeof(int)));
+            RMG_CUDA(cudaMemset(dstatus, 0, sizeof(int)));
         }
         for (int b = 0; b < NB; ++b) RMG_CUDA(cudaStreamWaitEvent(st[b], cd->ready, 0));
         for (int64_t c = 0; c < nchunks; ++c) {
@@ -461,10 +473,14 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
             const int64_t v0 = c * CV, cv = std::min(CV, V - v0);
             RMG_CUDA(cudaEventCreate(&ev0[c]));
             RMG_CUDA(cudaEventCreate(&ev1[c]));
-            if (!staged) {
-                RMG_CUDA(cudaMemcpy2DAsync(dY[b], (size_t)ldc * 8, Y + v0, (size_t)ldY * 8, (size_t)cv * 8, (size_t)n,
-                                           cudaMemcpyHostToDevice, st[b]));
-            } else {
+            for (int operand = 0; operand < (Z ? 2 : 1); ++operand) {
+                const double *src = operand ? Z : Y;
+                double *dstdev = operand ? dZ[b] : dY[b];
+                if (!staged) {
+                    RMG_CUDA(cudaMemcpy2DAsync(dstdev, (size_t)ldc * 8, src + v0, (size_t)ldY * 8, (size_t)cv * 8, (size_t)n,
+                                               cudaMemcpyHostToDevice, st[b]));
+                    continue;
+                }
                 for (int r0 = 0; r0 < n; r0 += rows_per_slot) {
                     const int rows = std::min(rows_per_slot, n - r0);
                     int slot = 0;
@@ -476,10 +492,10 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
                         for (int i = i0; i < i1; ++i) {
                             const int r = i / 8, part = i % 8;
                             const int64_t a0 = cv * part / 8, a1 = cv * (part + 1) / 8;
-                            std::memcpy(dst + (size_t)r * cv + a0, Y + v0 + (int64_t)(r0 + r) * ldY + a0, (size_t)(a1 - a0) * 8);
+                            std::memcpy(dst + (size_t)r * cv + a0, src + v0 + (int64_t)(r0 + r) * ldY + a0, (size_t)(a1 - a0) * 8);
                         }
                     });
-                    RMG_CUDA(cudaMemcpy2DAsync(dY[b] + (size_t)r0 * ldc, (size_t)ldc * 8, dst, (size_t)cv * 8, (size_t)cv * 8,
+                    RMG_CUDA(cudaMemcpy2DAsync(dstdev + (size_t)r0 * ldc, (size_t)ldc * 8, dst, (size_t)cv * 8, (size_t)cv * 8,
                                                (size_t)rows, cudaMemcpyHostToDevice, st[b]));
                     RMG_CUDA(cudaEventRecord(ring.done[slot], st[b]));
                     ring.busy[slot] = true;
@@ -491,10 +507,15 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
             a.rowscale = cd->rowscale;
             LmLaunchInfo info;
             RMG_CUDA(cudaEventRecord(ev0[c], st[b]));
-            RMG_CUDA(launch_lm_fit(a, plan, scr[b], st[b], &info));
+            if (Z) {
+                CovArgs ca{dY[b], dZ[b], cv, ldc, n, p, cd->qt, cd->dd, mask ? dM[b] : nullptr, mask_lo, mask_hi, dO[b], ldc, dstatus};
+                RMG_CUDA(launch_lm_cov(ca, plan, st[b], &info));
+            } else {
+                RMG_CUDA(launch_lm_fit(a, plan, scr[b], st[b], &info));
+            }
             RMG_CUDA(cudaEventRecord(ev1[c], st[b]));
             launches += info.launches;
-            g_last_fit_variant = info.used_tma ? 1 : 2;
+            g_last_fit_variant = Z ? 3 : info.used_tma ? 1 : 2;
             RMG_CUDA(cudaMemcpy2DAsync(out + v0, (size_t)ldOut * 8, dO[b], (size_t)ldc * 8, (size_t)cv * 8, (size_t)ncol,
                                        cudaMemcpyDeviceToHost, st[b]));
         }
@@ -506,6 +527,12 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
         }
         g_last_kernel_ms = ms;
         g_launch_count += launches;
+        if (Z) {
+            int status = 0;
+            RMG_CUDA(cudaMemcpy(&status, dstatus, sizeof(int), cudaMemcpyDeviceToHost));
+            // an all-zero covariate at a fitted voxel: exact zero on R's diagonal, the reference's dpotri error
+            if (status > 0) rc = fail(err, errlen, RMG_ERR_SINGULAR, "%s", singular_message(status).c_str());
+        }
     }
 cleanup:
     for (int b = 0; b < 3; ++b) {
@@ -517,8 +544,10 @@ cleanup:
         if (dY[b]) cudaFree(dY[b]);
         if (dO[b]) cudaFree(dO[b]);
         if (dM[b]) cudaFree(dM[b]);
+        if (dZ[b]) cudaFree(dZ[b]);
         if (st[b]) cudaStreamDestroy(st[b]);
     }
+    if (dstatus) cudaFree(dstatus);
     for (auto e : ev0) if (e) cudaEventDestroy(e);
     for (auto e : ev1) if (e) cudaEventDestroy(e);
     ring.release_all();
@@ -552,6 +581,64 @@ int rmg_vertex_lm(const double *Y, int64_t V, int64_t ldY, int n, const double *
 {
     // vertex_lm_loop has no mask and no I/O (src/vertex_modelling.c:104-158)
     return rmg_lm_fit(Y, V, ldY, n, X, p, nullptr, 0.0, 0.0, out, ldOut, device, err, errlen);
+}
+
+// Voxel-wise covariate: the static part defaults to the intercept column (src/vertex_modelling.c:36-39)
+static const double *static_part_or_ones(const double *Xs, int &ps, int n, std::vector<double> &ones)
+{
+    if (Xs && ps > 0) return Xs;
+    ones.assign((size_t)std::max(n, 1), 1.0);
+    ps = 1;
+    return ones.data();
+}
+
+int rmg_lm_fit_cov(const double *Y, const double *Z, int64_t V, int64_t ldY, int n, const double *Xs, int ps,
+                   const double *mask, double mask_lo, double mask_hi, double *out, int64_t ldOut, int device,
+                   char *err, size_t errlen)
+{
+    if (V > 0 && !Z) return fail(err, errlen, RMG_ERR_INVALID, "Z is NULL");
+    if (n < 1) return fail(err, errlen, RMG_ERR_INVALID, "n must be >= 1 (got %d)", n);
+    std::vector<double> ones;
+    const double *X = static_part_or_ones(Xs, ps, n, ones);
+    static const double dummy = 0.0;
+    return fit_host_impl(Y, V, ldY, n, X, ps, nullptr, mask, mask_lo, mask_hi, out, ldOut, device, err, errlen, nullptr,
+                         Z ? Z : &dummy);
+}
+
+int rmg_vertex_lm_cov(const double *Y, const double *Z, int64_t V, int64_t ldY, int n, const double *Xs, int ps,
+                      double *out, int64_t ldOut, int device, char *err, size_t errlen)
+{
+    return rmg_lm_fit_cov(Y, Z, V, ldY, n, Xs, ps, nullptr, 0.0, 0.0, out, ldOut, device, err, errlen);
+}
+
+int rmg_lm_fit_cov_device(const double *dY, const double *dZ, int64_t V, int64_t ldY, int n, const double *Xs, int ps,
+                          const double *dmask, double mask_lo, double mask_hi, double *dout, int64_t ldOut,
+                          int32_t *dstatus, int device, void *stream, char *err, size_t errlen)
+{
+    if (V > 0 && !dZ) return fail(err, errlen, RMG_ERR_INVALID, "Z is NULL");
+    if (n < 1) return fail(err, errlen, RMG_ERR_INVALID, "n must be >= 1 (got %d)", n);
+    std::vector<double> ones;
+    const double *X = static_part_or_ones(Xs, ps, n, ones);
+    int rc = check_fit_args(dY, V, ldY, n, X, ps, dout, ldOut, err, errlen);
+    if (rc) return rc;
+    if (ps > 16) return fail(err, errlen, RMG_ERR_INVALID, "voxel-wise covariate designs support at most 16 static columns (got %d)", ps);
+    if ((rc = select_device(device, err, errlen))) return rc;
+    std::shared_ptr<CachedDesign> cd = design_cache_get(device, X, n, ps, nullptr, rc, err, errlen);
+    if (!cd) return rc;
+    if (cd->D.k < ps)
+        return fail(err, errlen, RMG_ERR_INVALID,
+                    "rank-deficient static design (rank %d < %d columns) with a voxel-wise covariate is not supported", cd->D.k, ps);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LmLaunchInfo info;
+    {
+        RMG_CUDA(cudaStreamWaitEvent(st, cd->ready, 0));
+        CovArgs ca{dY, dZ, V, ldY, n, ps, cd->qt, cd->dd, dmask, mask_lo, mask_hi, dout, ldOut, dstatus};
+        RMG_CUDA(launch_lm_cov(ca, plan_from_env(device), st, &info));
+        g_launch_count += info.launches;
+        g_last_fit_variant = 3;
+    }
+cleanup:
+    return rc;
 }
 
 int rmg_lm_fit_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,

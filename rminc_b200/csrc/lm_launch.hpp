@@ -70,6 +70,23 @@ struct LmScratch {
 
 int lm_padded_p(int p);
 
+// Voxel-wise covariate designs [Xs | z_v] (lm_cov.cu).  Z has Y's shape and leading dimension; Qt / design
+// describe the static part Xs (n x ps, full column rank); out is V x (2(ps+1)+3).
+struct CovArgs {
+    const double *Y, *Z;
+    int64_t V, ldY;
+    int n, ps;
+    const double *Qt;          // [n][lm_padded_p(ps)] row-major
+    const DevDesign *design;
+    const double *mask;
+    double mask_lo, mask_hi;
+    double *out;
+    int64_t ldOut;
+    int *status;               // device int (nullable): set to p when an unmasked voxel's covariate is all zero
+};
+
+cudaError_t launch_lm_cov(const CovArgs &a, const LmPlan &plan, cudaStream_t st, LmLaunchInfo *info);
+
 cudaError_t launch_lm_fit(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st,
                           LmLaunchInfo *info);
 

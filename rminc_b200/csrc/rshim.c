@@ -11,6 +11,7 @@
  *   rmincgpu_vertex_lm_loop  same signature as vertex_lm_loop (src/vertex_modelling.c:8), so
  *                            vertexLm / anatLm only change the routine name
  *   rmincgpu_lm              minc2_model(method = "lm") with the volumes already staged
+ *   rmincgpu_lm_cov          the same with filenames_right (a voxel-wise covariate) staged as a second matrix
  *   rmincgpu_randomize       the mincRandomize loop (R/minc_voxel_statistics.R:1465-1497)
  *   rmincgpu_anova           per_voxel_anova / vertex_anova_loop (src/minc_anova.c:142, src/vertex_modelling.c:178)
  */
@@ -32,10 +33,29 @@ static const double *mask_or_null(SEXP mask, R_xlen_t V)
     return REAL(mask);
 }
 
+/* vertex_lm_loop with data_right a V x n matrix: the design of vertex v is [mmatrix | data_right[v, ]], or
+ * [1 | data_right[v, ]] when mmatrix is the logical NA matrix (src/vertex_modelling.c:33-55, :112-140). */
+static SEXP vertex_lm_loop_cov(SEXP data_left, SEXP data_right, SEXP mmatrix)
+{
+    if (!Rf_isReal(data_left) || !Rf_isReal(data_right)) Rf_error("data_left and data_right must be double matrices");
+    const R_xlen_t V = Rf_nrows(data_left);
+    const int n = Rf_ncols(data_left);
+    if (Rf_nrows(data_right) != V || Rf_ncols(data_right) != n) Rf_error("data_right must have the shape of data_left");
+    const int has_static = !Rf_isLogical(mmatrix);
+    if (has_static && (!Rf_isReal(mmatrix) || Rf_nrows(mmatrix) != n)) Rf_error("model matrix does not match the data");
+    const int ps = has_static ? Rf_ncols(mmatrix) : 0, p = has_static ? ps + 1 : 2;
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, 2 * p + 3));
+    char err[512] = "";
+    int rc = rmg_vertex_lm_cov(REAL(data_left), REAL(data_right), V, V > 0 ? V : 1, n, has_static ? REAL(mmatrix) : NULL, ps,
+                               REAL(out), V > 0 ? V : 1, 0, err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
 SEXP rmincgpu_vertex_lm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix)
 {
-    if (!Rf_isLogical(data_right))
-        Rf_error("voxel-wise covariates (a file term on the right-hand side) are not on the GPU path");
+    if (!Rf_isLogical(data_right)) return vertex_lm_loop_cov(data_left, data_right, mmatrix);
     if (!Rf_isReal(data_left) || !Rf_isReal(mmatrix)) Rf_error("data_left and mmatrix must be double matrices");
     const R_xlen_t V = Rf_nrows(data_left);
     const int n = Rf_ncols(data_left), p = Rf_ncols(mmatrix);
@@ -83,6 +103,26 @@ SEXP rmincgpu_lm(SEXP Y, SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP mask_upp
                                       Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, G, err, sizeof err)
                    : rmg_lm_fit(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, m, Rf_asReal(mask_lower),
                                 Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, 0, err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
+/* minc2_model(method = "lm") with filenames_right: Z staged like Y; mmatrix may be the logical NA matrix. */
+SEXP rmincgpu_lm_cov(SEXP Y, SEXP Z, SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP mask_upper)
+{
+    if (!Rf_isReal(Y) || !Rf_isReal(Z)) Rf_error("Y and Z must be double matrices");
+    const R_xlen_t V = Rf_nrows(Y);
+    const int n = Rf_ncols(Y);
+    if (Rf_nrows(Z) != V || Rf_ncols(Z) != n) Rf_error("the right-hand-side volumes must match the left-hand-side volumes");
+    const int has_static = !Rf_isLogical(mmatrix);
+    if (has_static && (!Rf_isReal(mmatrix) || Rf_nrows(mmatrix) != n)) Rf_error("model matrix does not match the data");
+    const int ps = has_static ? Rf_ncols(mmatrix) : 0, p = has_static ? ps + 1 : 2;
+    const double *m = mask_or_null(mask, V);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, 2 * p + 3));
+    char err[512] = "";
+    int rc = rmg_lm_fit_cov(REAL(Y), REAL(Z), V, V > 0 ? V : 1, n, has_static ? REAL(mmatrix) : NULL, ps, m,
+                            Rf_asReal(mask_lower), Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, 0, err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
     return out;
@@ -139,6 +179,7 @@ static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_vertex_lm_loop", (DL_FUNC)&rmincgpu_vertex_lm_loop, 3},
     {"rmincgpu_vertex_wlm_loop", (DL_FUNC)&rmincgpu_vertex_wlm_loop, 4},
     {"rmincgpu_lm", (DL_FUNC)&rmincgpu_lm, 6},
+    {"rmincgpu_lm_cov", (DL_FUNC)&rmincgpu_lm_cov, 6},
     {"rmincgpu_randomize", (DL_FUNC)&rmincgpu_randomize, 9},
     {"rmincgpu_anova", (DL_FUNC)&rmincgpu_anova, 6},
     {NULL, NULL, 0}};

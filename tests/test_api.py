@@ -33,6 +33,10 @@ def api(request, monkeypatch, oracle, lib):
         def vertex_wlm(Y, X, weights, device=0):
             return oracle.vertex_wlm_loop(Y, X, weights)
 
+        def lm_fit_cov(Y, Z, Xs=None, mask=None, mask_lo=1.0, mask_hi=99999999.0, device=0):
+            return oracle.lm_loop_cov(Y, Z, Xs, mask=mask, lo=mask_lo, hi=mask_hi)
+
+        monkeypatch.setattr(core, "lm_fit_cov", lm_fit_cov)
         monkeypatch.setattr(core, "vertex_wlm", vertex_wlm)
         monkeypatch.setattr(core, "anova_fit", anova_fit)
         monkeypatch.setattr(core, "lm_fit", lm_fit)
@@ -240,3 +244,55 @@ def test_mincAnova_vertexAnova_anatAnova(api, study, tmp_path):
     gv = gf.assign(thick=files)
     rv = api.vertexAnova("thick ~ Sex + Scale", gv)
     assert np.array_equal(np.asarray(rv), np.asarray(ra)) and rv.r_class == ("vertexMultiDim", "matrix")
+
+
+def test_file_covariate_on_the_right_hand_side(api, study, tmp_path):
+    """mincLm(jacobians ~ Sex + otherVolume): parseLmFormula finds the file term (R/minc_interface.R:1266-1324) and
+    the per-voxel design is [model.matrix(~ Sex) | z_v]; with the file as the only term it is [1 | z_v]."""
+    gf, maskfile, Y = study
+    rng = np.random.default_rng(11)
+    n = len(gf)
+    zfiles = []
+    for i in range(n):
+        f = tmp_path / f"cov{i:02d}.npy"
+        np.save(f, rng.normal(50, 4, (10, 10, 10)))
+        zfiles.append(str(f))
+    gf = gf.assign(other=zfiles)
+    Z = np.stack([np.load(f).reshape(-1) for f in zfiles], axis=1)
+    sexm = (gf.Sex == "M").astype(float).values
+    vs = api.mincLm("jacobians ~ Sex + other", gf)
+    assert vs.shape == (1000, 9) and vs.r_class == ("mincLm", "mincMultiDim", "matrix")
+    for v in (0, 431, 999):
+        check_row(vs, v, Y[v], np.column_stack([np.ones(n), sexm, Z[v]]), ["(Intercept)", "SexM", "other"])
+    # the reference derives model / df from the static part alone (R/minc_voxel_statistics.R:908, :929-935)
+    assert np.array_equal(vs.attrs["model"], np.column_stack([np.ones(n), sexm]))
+    assert vs.attrs["df"] == [[1, 8], 8, 8, 8]
+    assert vs.attrs["stat-type"] == ["F", "R-squared"] + ["beta"] * 3 + ["t"] * 3 + ["logLik"]
+    # term order does not matter; mask honoured
+    vm = api.mincLm("jacobians ~ other + Sex", gf, mask=maskfile)
+    inside = np.load(maskfile).reshape(-1) > 0.5
+    assert np.allclose(np.asarray(vm)[inside], np.asarray(vs)[inside], rtol=1e-12) and (np.asarray(vm)[~inside] == 0).all()
+    # the file as the only term: [1 | z], coefficient names 'Intercept' and the term (:1270)
+    v1 = api.mincLm("jacobians ~ other", gf)
+    assert v1.shape == (1000, 7)
+    check_row(v1, 77, Y[77], np.column_stack([np.ones(n), Z[77]]), ["Intercept", "other"])
+    assert v1.attrs["df"] == [[0, 0], 0, 0]
+    with pytest.raises(api.FormulaError, match="Only \\+ sign allowed"):
+        api.mincLm("jacobians ~ Sex * other", gf)
+    with pytest.raises(api.FormulaError, match="Only 2 terms allowed"):
+        api.mincLm("jacobians ~ Sex + Scale + other", gf)
+    # vertexLm with a vertex-file covariate (R/minc_vertex_statistics.R:393-401)
+    V = 30
+    yf, zf = [], []
+    for i in range(n):
+        a, b = tmp_path / f"y{i}.txt", tmp_path / f"z{i}.txt"
+        np.savetxt(a, rng.normal(3, 0.3, V))
+        np.savetxt(b, rng.normal(1, 0.1, V))
+        yf.append(str(a))
+        zf.append(str(b))
+    vf = pd.DataFrame(dict(thick=yf, Sex=gf.Sex.values, curv=zf))
+    rv = api.vertexLm("thick ~ Sex + curv", vf)
+    Yv = np.column_stack([np.loadtxt(f) for f in yf])
+    Zv = np.column_stack([np.loadtxt(f) for f in zf])
+    assert rv.r_class == ("vertexLm", "vertexMultiDim", "matrix") and rv.shape == (V, 9)
+    check_row(rv, 5, Yv[5], np.column_stack([np.ones(n), sexm, Zv[5]]), ["(Intercept)", "SexM", "curv"])

@@ -321,3 +321,125 @@ def test_weighted_fit_matches_oracle(core, oracle):
         core.vertex_wlm(Y, X, np.r_[0.0, np.ones(n - 1)])
     with pytest.raises(ValueError, match="Incorrect number of weights"):
         core.vertex_wlm(Y, X, np.ones(n - 1))
+
+
+# ------------------------------------------------------------------ voxel-wise covariate designs
+def _cov_case(V, n, ps, seed, zmean=100.0, zsd=3.0):
+    rng = np.random.default_rng(seed)
+    Xs = design_cov(n, ps, seed=seed + 1000) if ps else None     # (a different stream than the data's)
+    Y = np.asfortranarray(rng.normal(2.0, 0.5, (V, n)))
+    Z = np.asfortranarray(rng.normal(zmean, zsd, (V, n)))
+    Y += 0.02 * (Z - zmean) * rng.random((V, 1))
+    return Y, Z, Xs
+
+
+def test_covariate_golden_vectors(core):
+    g = np.load(os.path.join(GOLD, "ref_golden.npz"))
+    for key, Xs in (("E_out_static", g["E_Xs"]), ("E_out_nostatic", None)):
+        got, want = core.lm_fit_cov(g["E_Y"], g["E_Z"], Xs), g[key]
+        keep = np.ones(len(want), bool)
+        keep[7] = False                      # vertex 7: constant covariate, checked by class below
+        assert_rows_match(got[keep], want[keep], RTOL, key)
+        p = (want.shape[1] - 3) // 2
+        # rank p-1 at vertex 7: F, R2, betas (0 in the covariate's slot), logLik match; t = 0 in its slot
+        cols = [0, 1] + list(range(2, 2 + p)) + [2 * p + 2]
+        assert_rows_match(got[7, cols], want[7, cols], RTOL, key + " v7")
+        assert got[7, 1 + p] == 0.0 and got[7, 1 + 2 * p] == 0.0 and want[7, 1 + 2 * p] == 0.0
+
+
+@pytest.mark.parametrize("ps", [0, 1, 2, 3, 4, 6, 8, 11, 16])
+def test_covariate_matches_oracle_every_width(core, oracle, ps):
+    n = 64 if ps <= 8 else 96
+    Y, Z, Xs = _cov_case(1538, n, ps, seed=100 + ps)
+    assert_rows_match(core.lm_fit_cov(Y, Z, Xs), oracle.lm_loop_cov(Y, Z, Xs), RTOL, f"ps={ps}")
+
+
+@pytest.mark.parametrize("zmean,zsd", [(0.0, 1.0), (1000.0, 1.0), (30000.0, 50.0), (-5e4, 3.0)])
+def test_covariate_large_mean_small_sd(core, oracle, zmean, zsd):
+    """Both streamed operands carry ushort-like offsets: the first-sample shift keeps d^2 and rss at 1e-9."""
+    rng = np.random.default_rng(9)
+    V, n = 2048, 500
+    Xs = design_cfg2(n)
+    Y = np.asfortranarray(30000 + 50 * rng.standard_normal((V, n)) + 20 * np.outer(rng.random(V), Xs[:, 1]))
+    Z = np.asfortranarray(zmean + zsd * rng.standard_normal((V, n)))
+    assert_rows_match(core.lm_fit_cov(Y, Z, Xs), oracle.lm_loop_cov(Y, Z, Xs), RTOL, f"z {zmean} {zsd}")
+
+
+def test_covariate_near_perfect_fits_and_near_collinear_covariates(core, oracle):
+    """d^2/|z'|^2 or rss/|y'|^2 below 1e-3: the kernel recomputes them from explicit residuals (exact_cov)."""
+    rng = np.random.default_rng(16)
+    V, n = 1024, 120
+    Xs = design_cov(n, 3, seed=77)
+    B = rng.normal(size=(V, 3)) * 20
+    for noise, tol in ((1e-1, RTOL), (1e-4, RTOL), (1e-6, 1e-6)):
+        Z = np.asfortranarray(rng.normal(5.0, 1.0, (V, n)))
+        Y = np.asfortranarray(B @ Xs.T + 3.0 * Z + noise * rng.standard_normal((V, n)))
+        assert_rows_match(core.lm_fit_cov(Y, Z, Xs), oracle.lm_loop_cov(Y, Z, Xs), tol, f"y noise={noise}")
+    # covariate almost inside span(Xs), but above dqrdc2's 1e-7 cut (|z_perp|/|z| ~ noise/35): d^2 << |z|^2
+    for noise, tol in ((1e-1, RTOL), (1e-3, RTOL), (1e-4, 1e-8)):
+        Zc = np.asfortranarray(B @ Xs.T + noise * rng.standard_normal((V, n)))
+        Yc = np.asfortranarray(rng.normal(2.0, 0.5, (V, n)))
+        assert_rows_match(core.lm_fit_cov(Yc, Zc, Xs), oracle.lm_loop_cov(Yc, Zc, Xs), tol, f"z noise={noise}")
+
+
+def test_covariate_mask_odd_shapes_and_chunks(core, oracle, monkeypatch):
+    Y, Z, Xs = _cov_case(1001, 37, 3, seed=5)           # odd V -> one voxel per thread, unaligned rows
+    mask = (np.arange(1001) % 5).astype(float)
+    assert_rows_match(core.lm_fit_cov(Y, Z, Xs, mask=mask, mask_lo=2, mask_hi=3),
+                      oracle.lm_loop_cov(Y, Z, Xs, mask=mask, lo=2, hi=3), RTOL, "mask")
+    got = core.lm_fit_cov(Y, Z, Xs, mask=mask)
+    assert (got[mask < 0.5] == 0).all() and not np.signbit(got[mask < 0.5]).any()
+    monkeypatch.setenv("RMG_CHUNK_VOXELS", "300")      # several chunks through the host pipeline
+    assert_rows_match(core.lm_fit_cov(Y, Z, Xs), oracle.lm_loop_cov(Y, Z, Xs), RTOL, "chunked")
+    monkeypatch.delenv("RMG_CHUNK_VOXELS")
+    Y, Z, Xs = _cov_case(64, 2000, 6, seed=6)           # few vertices, many subjects -> split-n
+    assert_rows_match(core.lm_fit_cov(Y, Z, Xs), oracle.lm_loop_cov(Y, Z, Xs), RTOL, "split-n")
+    Xn = design_cov(40, 3, seed=2)[:, 1:]               # no intercept in the static part: no shift
+    Y, Z, _ = _cov_case(500, 40, 0, seed=7, zmean=1.0, zsd=1.0)
+    assert_rows_match(core.lm_fit_cov(Y, Z, Xn), oracle.lm_loop_cov(Y, Z, Xn), RTOL, "no intercept")
+
+
+def test_covariate_rank_and_error_contract(core, oracle):
+    Y, Z, Xs = _cov_case(400, 30, 2, seed=8)
+    Z[10, :] = 7.5                                      # constant: in span(Xs) -> rank p-1 at that voxel
+    Z[20, :] = 3.0 + 2.0 * Xs[:, 1]                     # exactly a combination of the static columns
+    Y[30, :] = 1.0 + 0.5 * Xs[:, 1] + 2.0 * Z[30, :]    # perfect fit through the covariate: rss is rounding noise
+    got, want = core.lm_fit_cov(Y, Z, Xs), oracle.lm_loop_cov(Y, Z, Xs)
+    keep = np.ones(400, bool)
+    keep[[10, 20, 30]] = False
+    assert_rows_match(got[keep], want[keep], RTOL, "regular voxels")
+    for v in (10, 20):
+        cols = [0, 1, 2, 3, 4, 8]                       # F, R2, betas, logLik are independent of R's noise diagonal
+        assert_rows_match(got[v, cols], want[v, cols], RTOL, f"rank-deficient voxel {v}")
+        assert got[v, 4] == 0.0 and got[v, 7] == 0.0 and want[v, 4] == 0.0 and want[v, 7] == 0.0
+    assert got[30, 2:5] == pytest.approx([1.0, 0.5, 2.0], rel=1e-9) and got[30, 1] == pytest.approx(1.0, rel=1e-12)
+    # all-zero covariate at a fitted voxel: the reference's dpotri error aborts the call ...
+    Z0 = Z.copy(order="F")
+    Z0[5, :] = 0.0
+    with pytest.raises(core.SingularDesignError, match="element \\(3, 3\\) is zero, so the inverse cannot be computed"):
+        core.lm_fit_cov(Y, Z0, Xs)
+    with pytest.raises(oracle.OracleError):
+        oracle.lm_loop_cov(Y, Z0, Xs)
+    # ... but not when the mask excludes it
+    mask = np.ones(400)
+    mask[5] = 0
+    assert_rows_match(core.lm_fit_cov(Y, Z0, Xs, mask=mask)[keep], oracle.lm_loop_cov(Y, Z0, Xs, mask=mask)[keep], RTOL, "masked zero")
+    # rank-deficient static part is refused, not guessed
+    with pytest.raises(core.RmincGpuError, match="rank-deficient static design"):
+        core.lm_fit_cov(Y, Z, np.column_stack([Xs, Xs[:, 1]]))
+
+
+def test_covariate_device_entry_point(core, oracle):
+    import torch
+    Y, Z, Xs = _cov_case(3000, 50, 3, seed=12)
+    Yt = torch.from_numpy(np.ascontiguousarray(Y.T)).cuda()
+    Zt = torch.from_numpy(np.ascontiguousarray(Z.T)).cuda()
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = core.lm_fit_cov_torch(Yt, Zt, Xs, status=status)
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    assert_rows_match(out.cpu().numpy().T, oracle.lm_loop_cov(Y, Z, Xs), RTOL, "device")
+    Zt[:, 17] = 0.0
+    core.lm_fit_cov_torch(Yt, Zt, Xs, out=out, status=status)
+    torch.cuda.synchronize()
+    assert int(status.item()) == 4 and torch.isnan(out[:, 17]).all()
