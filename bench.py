@@ -325,6 +325,74 @@ def run_gpu_arm(args):
                   "host_call_us": float(np.median(host_us[3:]))}
         del Yv, ov, flush
 
+    # ---- voxel-wise covariate: mincLm(y ~ group + age + otherVolume), two streamed operands
+    cov = None
+    if rank == 0 and not args.small and "cov" in args.parts:
+        Zt = gen_Y(torch, V, n, dev, seed=77, mean=100.0, sd=3.0)
+        oc = torch.empty((2 * p + 3, V), dtype=torch.float64, device=dev)
+        Xs = X[:, :p - 1]
+        core.lm_fit_cov_torch(Yt, Zt, Xs, out=oc)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            core.lm_fit_cov_torch(Yt, Zt, Xs, out=oc)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        cb = V * (16 * n + 8 * (2 * p + 3))
+        cov = {"workload": "mincLm(y ~ group + age + volume): per-voxel design [Xs | z_v], p = 4", "ms_per_step": ms,
+               "voxels_per_s": V / (ms * 1e-3), "achieved_gbs": cb / (ms * 1e-3) / 1e9,
+               "frac_of_hbm_peak": cb / (ms * 1e-3) / 1e9 / measured_hbm_peak()[0], "kernel": core.last_fit_variant()}
+        del Zt, oc
+
+    # ---- volumes in their stored type: uint16 voxels + per-slice real ranges, expanded in registers
+    stored = None
+    Ut = sc_t = of_t = None
+    if not args.small and ("stored" in args.parts or "e2e_u16" in args.parts):
+        g = torch.Generator(device=dev)
+        g.manual_seed(100 + rank)
+        Ut = torch.empty((n, V), dtype=torch.uint16, device=dev)
+        for j0 in range(0, n, 20):
+            j1 = min(n, j0 + 20)
+            blk = torch.empty((j1 - j0, V), dtype=torch.float32, device=dev).normal_(30000.0, 400.0, generator=g)
+            Ut[j0:j1] = blk.round_().clamp_(0, 32767).to(torch.int16).view(torch.uint16)
+        del blk
+        nsl, slice_len = DIMS[0], DIMS[1] * DIMS[2]
+        rs = np.random.default_rng(5)
+        smin = rs.normal(-0.8, 0.05, (n, nsl))
+        smax = smin + rs.uniform(1.5, 2.5, (n, nsl))
+        sc_h, of_h = np.ascontiguousarray((smax - smin) / 65535.0), np.ascontiguousarray(smin)   # (n, nslices) == [nslices x n] col-major
+        sc_t, of_t = torch.from_numpy(sc_h).to(dev), torch.from_numpy(of_h).to(dev)
+    if Ut is not None and "stored" in args.parts:
+        os_ = torch.empty((2 * p + 3, V), dtype=torch.float64, device=dev)
+        for _ in range(3):
+            core.lm_fit_stored_torch(Ut, X, sc_t, of_t, slice_len=slice_len, out=os_)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            core.lm_fit_stored_torch(Ut, X, sc_t, of_t, slice_len=slice_len, out=os_)
+        e1.record(stream)
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+        sb = V * (2 * n + 8 * (2 * p + 3))
+        stored = {"workload": "the same fit on uint16 voxels + per-slice real ranges (180 slices x 500 files)",
+                  "ms_per_step": ms, "voxels_per_s": world * V / (ms * 1e-3), "achieved_gbs": sb / (ms * 1e-3) / 1e9,
+                  "frac_of_hbm_peak": sb / (ms * 1e-3) / 1e9 / measured_hbm_peak()[0],
+                  "fp64_ops_per_s": V * n * (5.0 + p) / (ms * 1e-3), "kernel": core.last_fit_variant(),
+                  "bound": "FP64 pipe co-limits: (5+p) FP64 operations per 2-byte sample"}
+        # the stored-type fit equals the double fit of the expanded samples
+        Ye = ((Ut[:, :4096].to(torch.float64) - 0.0) * sc_t[:, :1]) + of_t[:, :1]
+        ref = core.lm_fit_torch(Ye, X)
+        torch.cuda.synchronize()
+        scl = torch.maximum(ref.abs(), ref.square().mean(dim=1, keepdim=True).sqrt())
+        assert bool(((os_[:, :4096] - ref).abs() <= 1e-9 * scl).all()), "stored-type result differs from the double fit"
+        del os_, Ye
+
     # ---- mincRandomize (config 4): voxel-sharded, all ranks evaluate every permutation, one all-reduce(MAX)
     rand = None
     if "randomize" in args.parts:
@@ -427,6 +495,51 @@ def run_gpu_arm(args):
         assert bool(((chk - ref).abs() <= 1e-9 * scale).all()), "e2e result differs from device result"
         del hY, hO
 
+    # ---- end to end with the volumes in their stored type: 2 bytes per sample over the host link
+    if Ut is not None and "e2e_u16" in args.parts:
+        from rminc_b200 import _lib
+        lib = _lib.load()
+        err = _lib.errbuf()
+        bind_to_gpu_numa(local_rank)
+        hU = torch.empty((n, V), dtype=torch.uint16, pin_memory=True)
+        hU.copy_(Ut)
+        hO = torch.empty((2 * p + 3, V), dtype=torch.float64, pin_memory=True)
+        Uh, Oh = hU.numpy().T, hO.numpy().T
+        Xf3 = np.asfortranarray(X)
+
+        def u16_step():
+            rc = lib.rmg_lm_fit_stored(Uh.ctypes.data, core.STORED_U16, V, V, n, sc_h.ctypes.data, of_h.ctypes.data, 0.0,
+                                       slice_len, Xf3.ctypes.data, p, None, 1.0, 99999999.0, Oh.ctypes.data, V,
+                                       local_rank, err, len(err))
+            _lib.check(rc, err)
+
+        u16_step()
+        ksteps = max(1, min(args.steps, 3))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            u16_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        if e2e is None:
+            e2e = {}
+        e2e["stored_u16"] = {"value": world * V * ksteps / dt, "unit": UNIT, "h2d_bytes_per_step": V * n * 2 + 2 * sc_h.size * 8,
+                             "d2h_bytes_per_step": V * (2 * p + 3) * 8, "steps": ksteps,
+                             "api": "rmg_lm_fit_stored (C ABI, pinned host uint16 voxels + real-range tables -> chunked "
+                                    "H2D -> expand + fit in one kernel -> D2H result)",
+                             "kernel_ms_inside": core.last_kernel_ms()}
+        chk = torch.from_numpy(np.ascontiguousarray(Oh[:4096].T)).to(dev)
+        ref = core.lm_fit_stored_torch(Ut[:, :4096], X, sc_t[:, :1].contiguous(), of_t[:, :1].contiguous(), slice_len=4096)
+        torch.cuda.synchronize()
+        scl = torch.maximum(ref.abs(), ref.square().mean(dim=1, keepdim=True).sqrt())
+        assert bool(((chk - ref).abs() <= 1e-9 * scl).all()), "stored e2e result differs from device result"
+        del hU, hO
+    Ut = None
+
     # ---- the same call with PAGEABLE host memory (what R's heap is): informational
     if rank == 0 and "e2e_pageable" in args.parts:
         from rminc_b200 import _lib
@@ -468,7 +581,7 @@ def run_gpu_arm(args):
                        "l2": "inputs (28.3 GB per GPU) are far larger than the 126 MB L2; no flush needed",
                        "sharding": "contiguous voxel shards, no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
-            "masked_variant": masked, "vertexLm": vertex, "randomize": rand,
+            "masked_variant": masked, "vertexLm": vertex, "covariate": cov, "stored_u16": stored, "randomize": rand,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -485,7 +598,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny smoke configuration (not a bench line)")
     ap.add_argument("--skip-extras", action="store_true", help="only the device-resident headline")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--parts", default="masked,vertex,randomize,e2e,cpu",
+    ap.add_argument("--parts", default="masked,vertex,cov,stored,randomize,e2e,e2e_u16,cpu",
                     help="which extra measurements to run beside the headline (comma list)")
     args = ap.parse_args()
     args.parts = set() if args.skip_extras else set(args.parts.split(","))

@@ -136,6 +136,37 @@ int rmg_lm_fit_cov_device(const double *dY, const double *dZ, int64_t V, int64_t
                           int32_t *dstatus, int device, void *stream, char *err, size_t errlen);
 
 /*
+ * mincLm on volumes kept in their STORED type.  minc2_model reads every slab with
+ * miget_real_value_hyperslab(..., MI_TYPE_DOUBLE, ...) (src/modelling_functions.c:1037-1055; mincGetVolume:
+ * src/minc_reader.c:294-331): libminc (BIC-MNI/libminc, pinned at b01ba22 by inst/tools/ch_minc_depends.m4:85)
+ * expands the stored voxels to doubles on the CPU.  Here the R layer hands over the stored samples themselves
+ * (miget_voxel_value_hyperslab with the file's own type) plus the real-range tables, 2 or 4 bytes per sample
+ * over PCIe and HBM instead of 8, and the kernel forms
+ *     y = ((double)u - voxel_min) * scale[slice, subject] + offset[slice, subject]
+ * in registers with three correctly rounded FP64 operations (no fused multiply-add), i.e. the same doubles the
+ * CPU expansion yields; the fit is then rmg_lm_fit's.
+ *   U          V x n samples, leading dimension ldU (in samples); dtype RMG_STORED_U16 or RMG_STORED_F32
+ *   scale, offset   [nslices x n] doubles, slice fastest, nslices = ceil(V / slice_len); from MINC's per-slice
+ *              image-min / image-max and the file's valid range:
+ *              scale = (image_max - image_min) / (valid_max - valid_min), offset = image_min.
+ *              Global scaling: slice_len = V (one row).  Ignored (may be NULL) for RMG_STORED_F32, which
+ *              converts exactly.
+ *   voxel_min  valid_min of the stored type; must be integral
+ *   slice_len  voxels per slice of the slowest file dimension (sizes[1] * sizes[2])
+ */
+#define RMG_STORED_U16 1
+#define RMG_STORED_F32 2
+int rmg_lm_fit_stored(const void *U, int dtype, int64_t V, int64_t ldU, int n,
+                      const double *scale, const double *offset, double voxel_min, int64_t slice_len,
+                      const double *X, int p, const double *mask, double mask_lo, double mask_hi,
+                      double *out, int64_t ldOut, int device, char *err, size_t errlen);
+/* Device-resident form (dU, dscale, doffset, dmask, dout on `device`), enqueued on `stream`. */
+int rmg_lm_fit_stored_device(const void *dU, int dtype, int64_t V, int64_t ldU, int n,
+                             const double *dscale, const double *doffset, double voxel_min, int64_t slice_len,
+                             const double *X, int p, const double *dmask, double mask_lo, double mask_hi,
+                             double *dout, int64_t ldOut, int device, void *stream, char *err, size_t errlen);
+
+/*
  * mincAnova / vertexAnova / anatAnova.  Drop-in for per_voxel_anova (src/minc_anova.c:142-304;
  * R caller R/minc_voxel_statistics.R:557-566) and vertex_anova_loop (src/vertex_modelling.c:178;
  * R callers R/minc_vertex_statistics.R:314-320, R/minc_anatomy.R anatAnova), whose per-voxel body is
@@ -198,7 +229,8 @@ int rmg_randomize_multi(const double *Y, int64_t V, int64_t ldY, int n, const do
  * kernels were launched on (host entry points only; 0 if unavailable). */
 double rmg_last_kernel_ms(void);
 /* Which fit kernel the most recent fit on this thread launched: 1 = TMA-staged ring,
- * 2 = direct streaming loads (+ split-n), 3 = voxel-wise covariate kernel, 0 = none yet. */
+ * 2 = direct streaming loads (+ split-n), 3 = voxel-wise covariate kernel,
+ * 4 = stored-type kernel (direct loads), 5 = stored-type kernel (TMA ring), 0 = none yet. */
 int rmg_last_fit_variant(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t rmg_launch_count(void);

@@ -309,3 +309,23 @@ def lm_loop_cov(Y, Z, Xs=None, mask=None, lo=1.0, hi=99999999.0, use_ref=False):
     if info:
         raise OracleError(f"element ({info}, {info}) is zero, so the inverse cannot be computed")
     return out
+
+
+def expand_stored(U, scale=None, offset=None, voxel_min=0.0, slice_len=None):
+    """The doubles libminc's miget_real_value_hyperslab(MI_TYPE_DOUBLE) hands to voxel_lm for stored voxels U
+    (V x n, uint16 with [nslices x n] scale / offset tables, or float32): see orc_expand_u16."""
+    U = np.asfortranarray(U)
+    V, n = U.shape
+    out = np.empty((V, n), order="F")
+    if U.dtype == np.float32:
+        lib().orc_expand_f32(U.ctypes.data_as(C.c_void_p), C.c_int64(V), C.c_int64(max(V, 1)), C.c_int(n), _p(out),
+                             C.c_int64(max(V, 1)))
+        return out
+    assert U.dtype == np.uint16
+    slice_len = V if slice_len is None else int(slice_len)
+    nsl = (V + slice_len - 1) // slice_len
+    sc = _F(np.asarray(scale, dtype=np.float64).reshape(nsl, n))
+    of = _F(np.asarray(offset, dtype=np.float64).reshape(nsl, n))
+    lib().orc_expand_u16(U.ctypes.data_as(C.c_void_p), C.c_int64(V), C.c_int64(max(V, 1)), C.c_int(n), _p(sc), _p(of),
+                         C.c_double(voxel_min), C.c_int64(slice_len), _p(out), C.c_int64(max(V, 1)))
+    return out

@@ -638,3 +638,32 @@ int orc_design_probe(const double *X, int n, int p, int *pivot, int *rank,
     free(x); free(y); free(b); free(rsd); free(qty); free(qraux); free(work);
     return info;
 }
+
+/* ------------------------------------------------------------------ stored type -> doubles */
+/* What the reference's read loop hands to voxel_lm (src/modelling_functions.c:1037-1055): libminc's
+ * miget_real_value_hyperslab(MI_TYPE_DOUBLE) expands the stored voxels with the file's valid range and the
+ * per-slice real range (image-min / image-max).  libminc (BIC-MNI/libminc @ b01ba22,
+ * inst/tools/ch_minc_depends.m4:85) is absent from the image, so its published conversion is restated:
+ *     real = (voxel - valid_min) * (slice_max - slice_min) / (valid_max - valid_min) + slice_min
+ * with scale[slice + nslices*j] = (slice_max - slice_min) / (valid_max - valid_min) and
+ * offset[slice + nslices*j] = slice_min precomputed per (slice, subject).  Plain C doubles: one subtraction, one
+ * multiplication, one addition, each rounded (this file is compiled without FMA contraction).
+ * U is V x n column-major (ld ldU); out V x n (ld ldOut); slice = v / slice_len. */
+void orc_expand_u16(const uint16_t *U, int64_t V, int64_t ldU, int n, const double *scale, const double *offset,
+                    double voxel_min, int64_t slice_len, double *out, int64_t ldOut)
+{
+    const int64_t nslices = (V + slice_len - 1) / slice_len;
+    for (int j = 0; j < n; ++j)
+        for (int64_t v = 0; v < V; ++v) {
+            const int64_t s = v / slice_len;
+            volatile double t = (double)U[v + ldU * j] - voxel_min;
+            volatile double m = t * scale[s + nslices * j];
+            out[v + ldOut * j] = m + offset[s + nslices * j];
+        }
+}
+
+void orc_expand_f32(const float *U, int64_t V, int64_t ldU, int n, double *out, int64_t ldOut)
+{
+    for (int j = 0; j < n; ++j)
+        for (int64_t v = 0; v < V; ++v) out[v + ldOut * j] = (double)U[v + ldU * j];
+}

@@ -164,6 +164,80 @@ def lm_fit_cov_torch(Yt, Zt, Xs=None, mask=None, mask_lo=DEFAULT_MASK_LO, mask_h
     return out
 
 
+STORED_U16, STORED_F32 = 1, 2          # RMG_STORED_U16 / RMG_STORED_F32
+
+
+def _stored_tables(U_dtype, V, n, scale, offset, slice_len):
+    if U_dtype == np.float32:
+        return STORED_F32, None, None, max(V, 1)
+    if U_dtype != np.uint16:
+        raise ValueError("stored volumes must be uint16 or float32")
+    slice_len = max(V, 1) if slice_len is None else int(slice_len)
+    nsl = (V + slice_len - 1) // slice_len if V else 0
+    sc = np.asfortranarray(np.asarray(scale, dtype=np.float64).reshape(nsl, n))
+    of = np.asfortranarray(np.asarray(offset, dtype=np.float64).reshape(nsl, n))
+    return STORED_U16, sc, of, slice_len
+
+
+def lm_fit_stored(U, X, scale=None, offset=None, voxel_min=0.0, slice_len=None, mask=None,
+                  mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, device=0):
+    """mincLm's native step on volumes in their stored type: U is V x n uint16 (with [nslices x n] scale / offset
+    tables from the files' real ranges) or float32.  The doubles ((u - voxel_min) * scale + offset) are formed on
+    the device; the result equals lm_fit on the expanded matrix."""
+    X = _lib.as_f64_fortran(X)
+    U = np.asarray(U)
+    if U.ndim != 2 or U.shape[1] != X.shape[0]:
+        raise ValueError(f"U must be V x n with n == nrow(X); got {U.shape} vs {X.shape}")
+    if not U.flags.f_contiguous:
+        U = np.asfortranarray(U)
+    V, n = U.shape
+    p = X.shape[1]
+    dtype, sc, of, slice_len = _stored_tables(U.dtype, V, n, scale, offset, slice_len)
+    m = None
+    if mask is not None:
+        m = np.ascontiguousarray(np.asarray(mask, dtype=np.float64).reshape(-1))
+        if m.shape[0] != V:
+            raise ValueError("mask length must equal the number of voxels")
+    out = np.empty((V, 2 * p + 3), order="F")
+    err = _lib.errbuf()
+    ld = max(V, 1)
+    rc = _lib.load().rmg_lm_fit_stored(U.ctypes.data, dtype, V, ld, n, sc.ctypes.data if sc is not None else None,
+                                       of.ctypes.data if of is not None else None, float(voxel_min), slice_len,
+                                       X.ctypes.data, p, m.ctypes.data if m is not None else None, mask_lo, mask_hi,
+                                       out.ctypes.data, ld, device, err, len(err))
+    _lib.check(rc, err)
+    return out
+
+
+def lm_fit_stored_torch(Ut, X, scale=None, offset=None, voxel_min=0.0, slice_len=None, mask=None,
+                        mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, out=None):
+    """Device-resident form: Ut (n, V) uint16 / float32 CUDA tensor; scale / offset (n, nslices) float64 CUDA
+    tensors (the column-major [nslices x n] tables).  Returns a (2p+3, V) CUDA tensor; current stream."""
+    import torch
+    if not (Ut.is_cuda and Ut.dim() == 2 and Ut.stride(1) == 1 and Ut.dtype in (torch.uint16, torch.float32)):
+        raise ValueError("Ut must be a uint16 / float32 CUDA tensor of shape (n, V) with unit stride along V")
+    X = _lib.as_f64_fortran(X)
+    n, V = Ut.shape
+    p = X.shape[1]
+    dtype = STORED_U16 if Ut.dtype == torch.uint16 else STORED_F32
+    slice_len = max(V, 1) if slice_len is None else int(slice_len)
+    if dtype == STORED_U16:
+        nsl = (V + slice_len - 1) // slice_len
+        for t in (scale, offset):
+            if not (t is not None and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == nsl * n):
+                raise ValueError("scale / offset must be contiguous float64 CUDA tensors of n x nslices elements")
+    if out is None:
+        out = torch.empty((2 * p + 3, V), dtype=torch.float64, device=Ut.device)
+    err = _lib.errbuf()
+    rc = _lib.load().rmg_lm_fit_stored_device(
+        Ut.data_ptr(), dtype, V, Ut.stride(0) if n > 1 else max(V, 1), n,
+        scale.data_ptr() if dtype == STORED_U16 else None, offset.data_ptr() if dtype == STORED_U16 else None,
+        float(voxel_min), slice_len, X.ctypes.data, p, mask.data_ptr() if mask is not None else None, mask_lo, mask_hi,
+        out.data_ptr(), out.stride(0), Ut.device.index or 0, _torch_stream(Ut), err, len(err))
+    _lib.check(rc, err)
+    return out
+
+
 def vertex_wlm(Y, X, weights, device=0):
     """anatLm(weights=)'s native step (vertex_wlm_loop, src/weighted_least_squares.c:168)."""
     Y, X, _ = _prep_host(Y, X, None)
@@ -329,4 +403,5 @@ def launch_count() -> int:
 
 
 def last_fit_variant() -> str:
-    return {0: "none", 1: "lm_fit_tma_kernel", 2: "lm_fit_ldg_kernel", 3: "lm_cov_kernel"}[_lib.load().rmg_last_fit_variant()]
+    return {0: "none", 1: "lm_fit_tma_kernel", 2: "lm_fit_ldg_kernel", 3: "lm_cov_kernel", 4: "lm_fit_packed_kernel",
+            5: "lm_fit_packed_tma_kernel"}[_lib.load().rmg_last_fit_variant()]

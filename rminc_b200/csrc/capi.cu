@@ -360,16 +360,16 @@ int rmg_anova_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const 
 // pinned staging buffers, and the DMA engine drains the ring while the next buffer is being filled.
 struct PinnedRing {
     static constexpr int kSlots = 4;
-    double *buf[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    char *buf[kSlots] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
     bool busy[kSlots] = {false, false, false, false};
-    size_t slot_doubles = 0;
+    size_t slot_bytes = 0;
     int next = 0;
-    cudaError_t init(size_t doubles)
+    cudaError_t init(size_t bytes)
     {
-        slot_doubles = doubles;
+        slot_bytes = bytes;
         for (int s = 0; s < kSlots; ++s) {
-            cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&buf[s]), doubles * sizeof(double), cudaHostAllocDefault);
+            cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&buf[s]), bytes, cudaHostAllocDefault);
             if (e != cudaSuccess) return e;
             e = cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming);
             if (e != cudaSuccess) return e;
@@ -409,10 +409,21 @@ static bool is_pinned_host(const void *p)
     return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
 
+// Volumes in their stored type (rmg_lm_fit_stored): Y is then V x n samples of `dtype`, not doubles.
+struct StoredSpec {
+    int dtype;
+    const double *scale, *offset;   // host, [nslices x n], slice fastest (u16 only)
+    double voxel_min;
+    int64_t slice_len;
+};
+
 static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *asgn,
                          const double *mask, double mask_lo, double mask_hi, double *out, int64_t ldOut, int device,
-                         char *err, size_t errlen, const double *w = nullptr, const double *Z = nullptr)
+                         char *err, size_t errlen, const double *w = nullptr, const double *Z = nullptr,
+                         const StoredSpec *pk = nullptr)
 {
+    const size_t es = !pk ? sizeof(double) : pk->dtype == kStoredU16 ? 2 : 4;   // bytes per sample of Y
+    const char *Yb = reinterpret_cast<const char *>(Y);
     // Z != nullptr: voxel-wise covariate design [X | z_v]; X is the static part (lm_cov.cu)
     int rc = check_fit_args(Y, V, ldY, n, X, p, out, ldOut, err, errlen);
     if (rc) return rc;
@@ -433,13 +444,16 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
 
     // Voxel chunks of ~1 GiB of Y (measured on B200/PCIe5: 256 MiB chunks reach 61 % of the pinned
     // copy rate, 1 GiB chunks 98 %), multiples of 1024 voxels so TMA tiles stay aligned.
-    int64_t CV = (int64_t)(1024.0 * 1024 * 1024 / (8.0 * n));
+    int64_t CV = (int64_t)(1024.0 * 1024 * 1024 / ((double)es * n));
     CV = std::max<int64_t>(1024, (CV / 1024) * 1024);
     if (const char *s = std::getenv("RMG_CHUNK_VOXELS")) CV = std::max<int64_t>(2, (std::atoll(s) / 2) * 2);
     if (CV > V) CV = V;
     const int64_t nchunks = (V + CV - 1) / CV;
     const int NB = (int)std::min<int64_t>(3, nchunks);
-    const int64_t ldc = (CV + 1) & ~int64_t(1);  // even leading dimension -> 16-byte aligned rows
+    const int64_t ldc = (CV + 7) & ~int64_t(7);  // rows stay 16-byte aligned for every sample type
+    const int64_t slice_len = pk ? std::max<int64_t>(1, pk->slice_len) : 1;
+    const int64_t nslices = pk ? (V + slice_len - 1) / slice_len : 0;
+    double *dScale = nullptr, *dOffset = nullptr;
 
     cudaStream_t st[3] = {nullptr, nullptr, nullptr};
     double *dY[3] = {nullptr, nullptr, nullptr}, *dO[3] = {nullptr, nullptr, nullptr}, *dM[3] = {nullptr, nullptr, nullptr};
@@ -451,14 +465,21 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
     int64_t launches = 0;
     PinnedRing ring;
     // (small transfers are not worth four cudaHostAlloc calls)
-    const bool staged = !is_pinned_host(Y) && (double)V * n * 8.0 >= 256.0 * 1024 * 1024 && !std::getenv("RMG_NO_STAGING");
+    const bool staged = !is_pinned_host(Y) && (double)V * n * (double)es >= 256.0 * 1024 * 1024 && !std::getenv("RMG_NO_STAGING");
     // rows (subjects) per staging slot: ~128 MiB
-    const int rows_per_slot = (int)std::max<int64_t>(1, std::min<int64_t>(n, (128ll << 20) / (8 * std::max<int64_t>(CV, 1))));
+    const int rows_per_slot = (int)std::max<int64_t>(1, std::min<int64_t>(n, (128ll << 20) / ((int64_t)es * std::max<int64_t>(CV, 1))));
     {
-        if (staged) RMG_CUDA(ring.init((size_t)rows_per_slot * (size_t)std::min(CV, V)));
+        if (staged) RMG_CUDA(ring.init((size_t)rows_per_slot * (size_t)std::min(CV, V) * es));
+        if (pk && pk->dtype == kStoredU16) {
+            const size_t cnt = (size_t)nslices * n * sizeof(double);
+            RMG_CUDA(cudaMalloc(&dScale, cnt));
+            RMG_CUDA(cudaMalloc(&dOffset, cnt));
+            RMG_CUDA(cudaMemcpy(dScale, pk->scale, cnt, cudaMemcpyHostToDevice));
+            RMG_CUDA(cudaMemcpy(dOffset, pk->offset, cnt, cudaMemcpyHostToDevice));
+        }
         for (int b = 0; b < NB; ++b) {
             RMG_CUDA(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
-            RMG_CUDA(cudaMalloc(&dY[b], (size_t)ldc * n * sizeof(double)));
+            RMG_CUDA(cudaMalloc(&dY[b], (size_t)ldc * n * es));
             RMG_CUDA(cudaMalloc(&dO[b], (size_t)ldc * ncol * sizeof(double)));
             if (mask) RMG_CUDA(cudaMalloc(&dM[b], (size_t)ldc * sizeof(double)));
             if (Z) RMG_CUDA(cudaMalloc(&dZ[b], (size_t)ldc * n * sizeof(double)));
@@ -474,28 +495,29 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
             RMG_CUDA(cudaEventCreate(&ev0[c]));
             RMG_CUDA(cudaEventCreate(&ev1[c]));
             for (int operand = 0; operand < (Z ? 2 : 1); ++operand) {
-                const double *src = operand ? Z : Y;
-                double *dstdev = operand ? dZ[b] : dY[b];
+                const char *src = operand ? reinterpret_cast<const char *>(Z) : Yb;
+                char *dstdev = reinterpret_cast<char *>(operand ? dZ[b] : dY[b]);
                 if (!staged) {
-                    RMG_CUDA(cudaMemcpy2DAsync(dstdev, (size_t)ldc * 8, src + v0, (size_t)ldY * 8, (size_t)cv * 8, (size_t)n,
-                                               cudaMemcpyHostToDevice, st[b]));
+                    RMG_CUDA(cudaMemcpy2DAsync(dstdev, (size_t)ldc * es, src + (size_t)v0 * es, (size_t)ldY * es, (size_t)cv * es,
+                                               (size_t)n, cudaMemcpyHostToDevice, st[b]));
                     continue;
                 }
                 for (int r0 = 0; r0 < n; r0 += rows_per_slot) {
                     const int rows = std::min(rows_per_slot, n - r0);
                     int slot = 0;
                     RMG_CUDA(ring.acquire(slot));
-                    double *dst = ring.buf[slot];
+                    char *dst = ring.buf[slot];
                     // all host threads copy the strided rows of this group into the pinned slot
                     const int64_t pieces = (int64_t)rows * 8;   // 8 column pieces per row keep every thread busy
                     parallel_for((int)pieces, [&](int i0, int i1) {
                         for (int i = i0; i < i1; ++i) {
                             const int r = i / 8, part = i % 8;
                             const int64_t a0 = cv * part / 8, a1 = cv * (part + 1) / 8;
-                            std::memcpy(dst + (size_t)r * cv + a0, src + v0 + (int64_t)(r0 + r) * ldY + a0, (size_t)(a1 - a0) * 8);
+                            std::memcpy(dst + ((size_t)r * cv + a0) * es, src + ((size_t)v0 + (size_t)(r0 + r) * ldY + a0) * es,
+                                        (size_t)(a1 - a0) * es);
                         }
                     });
-                    RMG_CUDA(cudaMemcpy2DAsync(dstdev + (size_t)r0 * ldc, (size_t)ldc * 8, dst, (size_t)cv * 8, (size_t)cv * 8,
+                    RMG_CUDA(cudaMemcpy2DAsync(dstdev + (size_t)r0 * ldc * es, (size_t)ldc * es, dst, (size_t)cv * es, (size_t)cv * es,
                                                (size_t)rows, cudaMemcpyHostToDevice, st[b]));
                     RMG_CUDA(cudaEventRecord(ring.done[slot], st[b]));
                     ring.busy[slot] = true;
@@ -510,12 +532,16 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
             if (Z) {
                 CovArgs ca{dY[b], dZ[b], cv, ldc, n, p, cd->qt, cd->dd, mask ? dM[b] : nullptr, mask_lo, mask_hi, dO[b], ldc, dstatus};
                 RMG_CUDA(launch_lm_cov(ca, plan, st[b], &info));
+            } else if (pk) {
+                PackedArgs pa{dY[b], pk->dtype, cv, ldc, n, p, cd->qt, cd->dd, mask ? dM[b] : nullptr, mask_lo, mask_hi, dO[b], ldc,
+                              dScale, dOffset, 4503599627370496.0 + pk->voxel_min, slice_len, nslices, v0};
+                RMG_CUDA(launch_lm_packed(pa, plan, scr[b], st[b], &info));
             } else {
                 RMG_CUDA(launch_lm_fit(a, plan, scr[b], st[b], &info));
             }
             RMG_CUDA(cudaEventRecord(ev1[c], st[b]));
             launches += info.launches;
-            g_last_fit_variant = Z ? 3 : info.used_tma ? 1 : 2;
+            g_last_fit_variant = Z ? 3 : pk ? (info.used_tma ? 5 : 4) : info.used_tma ? 1 : 2;
             RMG_CUDA(cudaMemcpy2DAsync(out + v0, (size_t)ldOut * 8, dO[b], (size_t)ldc * 8, (size_t)cv * 8, (size_t)ncol,
                                        cudaMemcpyDeviceToHost, st[b]));
         }
@@ -548,6 +574,8 @@ cleanup:
         if (st[b]) cudaStreamDestroy(st[b]);
     }
     if (dstatus) cudaFree(dstatus);
+    if (dScale) cudaFree(dScale);
+    if (dOffset) cudaFree(dOffset);
     for (auto e : ev0) if (e) cudaEventDestroy(e);
     for (auto e : ev1) if (e) cudaEventDestroy(e);
     ring.release_all();
@@ -581,6 +609,60 @@ int rmg_vertex_lm(const double *Y, int64_t V, int64_t ldY, int n, const double *
 {
     // vertex_lm_loop has no mask and no I/O (src/vertex_modelling.c:104-158)
     return rmg_lm_fit(Y, V, ldY, n, X, p, nullptr, 0.0, 0.0, out, ldOut, device, err, errlen);
+}
+
+static int check_stored_args(int dtype, const double *scale, const double *offset, double voxel_min, int64_t slice_len,
+                             int p, char *err, size_t errlen)
+{
+    if (dtype != RMG_STORED_U16 && dtype != RMG_STORED_F32)
+        return fail(err, errlen, RMG_ERR_INVALID, "dtype must be RMG_STORED_U16 or RMG_STORED_F32 (got %d)", dtype);
+    if (p > 16) return fail(err, errlen, RMG_ERR_INVALID, "stored-type fits support at most 16 design columns (got %d)", p);
+    if (dtype == RMG_STORED_U16) {
+        if (!scale || !offset) return fail(err, errlen, RMG_ERR_INVALID, "scale / offset are NULL");
+        if (slice_len < 1) return fail(err, errlen, RMG_ERR_INVALID, "slice_len must be >= 1");
+        if (!(std::fabs(voxel_min) <= 2147483648.0) || voxel_min != std::floor(voxel_min))
+            return fail(err, errlen, RMG_ERR_INVALID, "voxel_min must be an integer (got %g)", voxel_min);
+    }
+    return RMG_OK;
+}
+
+int rmg_lm_fit_stored(const void *U, int dtype, int64_t V, int64_t ldU, int n, const double *scale, const double *offset,
+                      double voxel_min, int64_t slice_len, const double *X, int p, const double *mask, double mask_lo,
+                      double mask_hi, double *out, int64_t ldOut, int device, char *err, size_t errlen)
+{
+    int rc = check_stored_args(dtype, scale, offset, voxel_min, slice_len, p, err, errlen);
+    if (rc) return rc;
+    const StoredSpec pk{dtype, scale, offset, voxel_min, slice_len};
+    return fit_host_impl(static_cast<const double *>(U), V, ldU, n, X, p, nullptr, mask, mask_lo, mask_hi, out, ldOut, device,
+                         err, errlen, nullptr, nullptr, &pk);
+}
+
+int rmg_lm_fit_stored_device(const void *dU, int dtype, int64_t V, int64_t ldU, int n, const double *dscale,
+                             const double *doffset, double voxel_min, int64_t slice_len, const double *X, int p,
+                             const double *dmask, double mask_lo, double mask_hi, double *dout, int64_t ldOut, int device,
+                             void *stream, char *err, size_t errlen)
+{
+    int rc = check_fit_args(dU, V, ldU, n, X, p, dout, ldOut, err, errlen);
+    if (rc) return rc;
+    if ((rc = check_stored_args(dtype, dscale, doffset, voxel_min, slice_len, p, err, errlen))) return rc;
+    if ((rc = select_device(device, err, errlen))) return rc;
+    std::shared_ptr<CachedDesign> cd = design_cache_get(device, X, n, p, nullptr, rc, err, errlen);
+    if (!cd) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LmLaunchInfo info;
+    LmScratch scr;
+    {
+        RMG_CUDA(cudaStreamWaitEvent(st, cd->ready, 0));
+        const int64_t sl = dtype == RMG_STORED_U16 ? slice_len : std::max<int64_t>(V, 1);
+        PackedArgs pa{dU, dtype, V, ldU, n, p, cd->qt, cd->dd, dmask, mask_lo, mask_hi, dout, ldOut,
+                      dscale, doffset, 4503599627370496.0 + voxel_min, sl, (V + sl - 1) / sl, 0};
+        RMG_CUDA(launch_lm_packed(pa, plan_from_env(device), scr, st, &info));
+        g_launch_count += info.launches;
+        g_last_fit_variant = info.used_tma ? 5 : 4;
+    }
+cleanup:
+    scr.release(st);
+    return rc;
 }
 
 // Voxel-wise covariate: the static part defaults to the intercept column (src/vertex_modelling.c:36-39)

@@ -87,6 +87,29 @@ struct CovArgs {
 
 cudaError_t launch_lm_cov(const CovArgs &a, const LmPlan &plan, cudaStream_t st, LmLaunchInfo *info);
 
+// The fit on volumes in their stored type (lm_packed.cu).  U: V x n samples of `dtype`, leading dimension ldU
+// (in samples).  A sample's double is ((double)u - voxel_min) * scale[slice, j] + offset[slice, j] with
+// slice = (v_base + v) / slice_len; scale / offset are device arrays [nslices x n], slice fastest (null for f32).
+constexpr int kStoredU16 = 1, kStoredF32 = 2;   // == RMG_STORED_U16 / RMG_STORED_F32
+struct PackedArgs {
+    const void *U;
+    int dtype;
+    int64_t V, ldU;
+    int n, p;
+    const double *Qt;
+    const DevDesign *design;
+    const double *mask;
+    double mask_lo, mask_hi;
+    double *out;
+    int64_t ldOut;
+    const double *scale, *offset;
+    double cmagic;             // 2^52 + voxel_min (u16)
+    int64_t slice_len, nslices, v_base;
+    int out_vec2 = 0;
+};
+
+cudaError_t launch_lm_packed(const PackedArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info);
+
 cudaError_t launch_lm_fit(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st,
                           LmLaunchInfo *info);
 

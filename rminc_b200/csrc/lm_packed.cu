@@ -1,0 +1,587 @@
+// lm_packed.cu -- the fit on volumes kept in their STORED type, sm_100a.
+//
+// Reference: minc2_model reads every slab with miget_real_value_hyperslab(..., MI_TYPE_DOUBLE, ...)
+// (src/modelling_functions.c:1037-1055; src/minc_reader.c:294-331): libminc converts the stored voxels
+// (usually unsigned 16-bit with a per-slice real range, or 32-bit float) to doubles on the CPU, and the
+// doubles are what voxel_lm sees.  Shipping those doubles costs 8 bytes per sample over PCIe and HBM.
+//
+// Here the stored values travel as they are (2 or 4 bytes per sample) and the conversion
+//     y = ((double)u - voxel_min) * scale[slice, subject] + offset[slice, subject]
+// (three correctly rounded FP64 operations, no fused multiply-add: the doubles a C compiler produces from
+// libminc's expression on a target without FMA contraction) happens in registers inside the fit kernel.  The
+// accumulation and the epilogue are those of lm_fit_ldg_kernel, so the result equals the fit on the expanded
+// doubles.  float32 volumes convert exactly and carry no scale.
+//
+// Roofline: HBM at 2n (u16) / 4n (f32) + 8(2p+3) bytes per voxel; at 2 bytes per sample the FP64 pipe
+// ((5 + p) n operations per voxel) is the co-limiter.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <type_traits>
+
+#include "async_ptx.cuh"
+#include "lm_common.cuh"
+#include "lm_launch.hpp"
+
+namespace rmg {
+
+namespace {
+
+// Four consecutive stored samples -> doubles.  u16: 2^52 + u is exact, so (2^52 + u) - (2^52 + voxel_min) is the
+// exactly rounded (double)u - voxel_min for integral voxel_min (checked on the host) in ONE FP64 add.
+template <typename T>
+struct Stored;
+
+template <>
+struct Stored<uint16_t> {
+    static constexpr bool kScaled = true;
+    using Raw = uint2;
+    __device__ static __forceinline__ Raw load_raw(const uint16_t *p)
+    {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        return r;
+    }
+    __device__ static __forceinline__ void convert(const Raw &r, double (&y)[4], double cmagic)
+    {
+        y[0] = __hiloint2double(0x43300000, (int)(r.x & 0xffffu)) - cmagic;
+        y[1] = __hiloint2double(0x43300000, (int)(r.x >> 16)) - cmagic;
+        y[2] = __hiloint2double(0x43300000, (int)(r.y & 0xffffu)) - cmagic;
+        y[3] = __hiloint2double(0x43300000, (int)(r.y >> 16)) - cmagic;
+    }
+    __device__ static __forceinline__ double load1(const uint16_t *p, double cmagic)
+    {
+        return __hiloint2double(0x43300000, (int)__ldg(p)) - cmagic;
+    }
+};
+
+template <>
+struct Stored<float> {
+    static constexpr bool kScaled = false;
+    using Raw = float4;
+    __device__ static __forceinline__ Raw load_raw(const float *p)
+    {
+        float4 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+        return r;
+    }
+    __device__ static __forceinline__ void convert(const Raw &r, double (&y)[4], double)
+    {
+        y[0] = (double)r.x; y[1] = (double)r.y; y[2] = (double)r.z; y[3] = (double)r.w;
+    }
+    __device__ static __forceinline__ double load1(const float *p, double) { return (double)__ldg(p); }
+};
+
+// value of one sample as the reference's doubles: separate multiply and add (never an FMA)
+__device__ __forceinline__ double descale(double t, double sc, double of) { return __dadd_rn(__dmul_rn(t, sc), of); }
+
+template <int KP, typename T>
+__device__ __noinline__ double2 exact_pass_packed(const T *__restrict__ u, int64_t ld, int n, const double *__restrict__ Qt,
+                                                  double y0, double cmagic, const double *__restrict__ sc,
+                                                  const double *__restrict__ of, int64_t sstride)
+{
+    auto sample = [&](int j) {
+        double t = Stored<T>::load1(u + (int64_t)j * ld, cmagic);
+        if (Stored<T>::kScaled) t = descale(t, __ldg(sc + (int64_t)j * sstride), __ldg(of + (int64_t)j * sstride));
+        return t - y0;
+    };
+    double e[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) e[k] = 0.0;
+    for (int j = 0; j < n; ++j) {
+        const double yv = sample(j);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = fma(__ldg(Qt + (size_t)j * KP + k), yv, e[k]);
+    }
+    double r2 = 0.0, sf = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double fit = 0.0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) fit = fma(__ldg(Qt + (size_t)j * KP + k), e[k], fit);
+        const double r = sample(j) - fit;
+        r2 = fma(r, r, r2);
+        sf += fit;
+    }
+    const double mean = sf / n;
+    double m2 = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double fit = 0.0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) fit = fma(__ldg(Qt + (size_t)j * KP + k), e[k], fit);
+        const double dlt = fit - mean;
+        m2 = fma(dlt, dlt, m2);
+    }
+    return make_double2(r2, m2);
+}
+
+}  // namespace
+
+// One thread = VPT (4 or 1) adjacent voxels, all n subjects.  Shared memory holds, JT subjects at a time, one row
+// [Q'(j, 0..KP) | scale_a(j) offset_a(j) | scale_b(j) offset_b(j)] per subject, where a / b are the (at most two)
+// slices the block's voxels lie in: no global load besides the samples themselves remains in the inner loop.  The
+// next UNR subjects' raw samples are prefetched into registers while the current ones are converted and accumulated.
+template <int KP, typename T, int VPT>
+__global__ void __launch_bounds__(128, VPT == 1 ? 6 : (KP <= 4 ? 4 : (KP <= 6 ? 3 : (KP <= 8 ? 2 : 1))))
+lm_fit_packed_kernel(PackedArgs a, int JT)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SmemDesign<KP> sd;
+    constexpr bool SC = Stored<T>::kScaled;
+    constexpr int TS = (KP + 1) & ~1;                   // first table column (even: 16-byte aligned pairs)
+    constexpr int QW = TS + (SC ? 4 : 0);               // doubles per staged row
+    double *sQ = reinterpret_cast<double *>(smem_raw);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int n = a.n;
+    const T *U = static_cast<const T *>(a.U);
+
+    load_design_to_smem<KP>(sd, a.design, tid, nthreads);
+    __syncthreads();
+
+    const int64_t vb = (int64_t)blockIdx.x * nthreads * VPT;     // first voxel of the block
+    const int64_t v = vb + (int64_t)tid * VPT;
+    bool in[VPT], act[VPT];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        in[i] = v + i < a.V;
+        act[i] = in[i] && (!a.mask || mask_selects(a.mask[v + i], a.mask_lo, a.mask_hi));
+        any |= act[i];
+    }
+    // slices: the block's first slice is table a, the next one table b; a block reaching a third slice (tiny slices)
+    // or a thread whose voxels straddle a boundary reads the tables from global memory instead
+    const int64_t sl_a = SC ? min((a.v_base + vb) / a.slice_len, a.nslices - 1) : 0;
+    const int64_t sl_b = min(sl_a + 1, a.nslices - 1);
+    int64_t sl[VPT];
+    bool same = true;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        sl[i] = SC ? min((a.v_base + v + i) / a.slice_len, a.nslices - 1) : 0;
+        same &= sl[i] == sl[0];
+    }
+    const bool fast = !SC || (same && sl[0] <= sl_b);
+    const int tsel = TS + ((SC && sl[0] != sl_a) ? 2 : 0);       // column of this thread's (scale, offset) pair
+    const double cm = a.cmagic;
+    VoxelSums<KP> sum[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) sum[i].e[k] = 0.0;
+        sum[i].yy = 0.0;
+        sum[i].y0 = 0.0;
+        if (sd.shift && act[i]) {
+            double t = Stored<T>::load1(U + v + i, cm);
+            if (SC) t = descale(t, __ldg(a.scale + sl[i]), __ldg(a.offset + sl[i]));
+            sum[i].y0 = t;
+        }
+    }
+    const T *up = U + (any ? v : 0);
+    constexpr int UNR = 8;
+
+    for (int t0 = 0; t0 < n; t0 += JT) {
+        __syncthreads();
+        const int cnt = min(JT, n - t0);
+        for (int i = tid; i < cnt * QW; i += nthreads) {
+            const int j = t0 + i / QW, c = i % QW;
+            double val = 0.0;
+            if (c < KP) val = a.Qt[(size_t)j * KP + c];
+            else if (SC && c >= TS) {
+                const int64_t s_ = (c - TS) < 2 ? sl_a : sl_b;
+                val = ((c - TS) & 1) ? a.offset[s_ + (int64_t)j * a.nslices] : a.scale[s_ + (int64_t)j * a.nslices];
+            }
+            sQ[i] = val;
+        }
+        __syncthreads();
+        if (!any) continue;
+
+        // FAST: this thread's (scale, offset) pair comes from the staged row; otherwise (a thread straddling a slice
+        // boundary, or tiny slices) from global memory.  Two separately compiled loops keep the common one lean.
+        auto run = [&](auto fast_tag) {
+            constexpr bool FAST = decltype(fast_tag)::value;
+            auto accumulate = [&](int jj, int i, double t) {
+                const double *row = sQ + jj * QW;
+                if (SC) {
+                    double sc, of;
+                    if (FAST) {
+                        const double2 so = *reinterpret_cast<const double2 *>(row + tsel);
+                        sc = so.x;
+                        of = so.y;
+                    } else {
+                        sc = __ldg(a.scale + sl[i] + (int64_t)(t0 + jj) * a.nslices);
+                        of = __ldg(a.offset + sl[i] + (int64_t)(t0 + jj) * a.nslices);
+                    }
+                    t = descale(t, sc, of);
+                }
+                const double yv = t - sum[i].y0;
+                sum[i].yy = fma(yv, yv, sum[i].yy);
+#pragma unroll
+                for (int k = 0; k < KP; ++k) sum[i].e[k] = fma(row[k], yv, sum[i].e[k]);
+            };
+            int jj = 0;
+            if constexpr (VPT == 4) {
+                typename Stored<T>::Raw cur[UNR], nxt[UNR];
+                if (cnt >= UNR) {
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) nxt[u] = Stored<T>::load_raw(up + (int64_t)(t0 + u) * a.ldU);
+                }
+                for (; jj + UNR <= cnt; jj += UNR) {
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) cur[u] = nxt[u];
+                    if (jj + 2 * UNR <= cnt) {
+#pragma unroll
+                        for (int u = 0; u < UNR; ++u)
+                            nxt[u] = Stored<T>::load_raw(up + (int64_t)(t0 + jj + UNR + u) * a.ldU);
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        double y[4];
+                        Stored<T>::convert(cur[u], y, cm);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) accumulate(jj + u, i, y[i]);
+                    }
+                }
+            } else {
+                for (; jj + UNR <= cnt; jj += UNR) {
+                    double y1[UNR];
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) y1[u] = Stored<T>::load1(up + (int64_t)(t0 + jj + u) * a.ldU, cm);
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) accumulate(jj + u, 0, y1[u]);
+                }
+            }
+            for (; jj < cnt; ++jj) {
+                const T *src = up + (int64_t)(t0 + jj) * a.ldU;
+#pragma unroll
+                for (int i = 0; i < VPT; ++i) accumulate(jj, i, Stored<T>::load1(src + i, cm));
+            }
+        };
+        if (fast) run(std::true_type{});
+        else run(std::false_type{});
+    }
+
+    // ---- fused epilogue (as lm_fit_ldg_kernel)
+    double rss[VPT], mss[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        rss[i] = sum[i].yy - sumsq_e(sum[i]);
+        mss[i] = mss_from_e(sum[i], sd);
+        if (act[i] && rss[i] <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0) {
+            const double2 ex = exact_pass_packed<KP, T>(U + v + i, a.ldU, n, a.Qt, sum[i].y0, cm, a.scale + sl[i],
+                                                        a.offset + sl[i], a.nslices);
+            rss[i] = ex.x;
+            mss[i] = ex.y;
+        }
+    }
+    if (VPT == 4 && a.out_vec2 && in[VPT - 1]) {
+#pragma unroll
+        for (int i = 0; i + 1 < VPT; i += 2)
+            finish_pair<KP>(sum[i], rss[i], mss[i], act[i], sum[i + 1], rss[i + 1], mss[i + 1], act[i + 1], sd,
+                            a.out + v + i, a.ldOut);
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        if (!in[i]) continue;
+        double *o = a.out + v + i;
+        if (act[i]) finish_voxel<KP>(sum[i], rss[i], mss[i], sd, o, a.ldOut);
+        else zero_row<KP>(sd.ncol_out, o, a.ldOut);
+    }
+}
+
+
+// ------------------------------------------------------------------ TMA-staged variant (default when TMA can describe U)
+// Same contract, K1's structure (lm_kernels.cu): persistent CTAs, one producer lane issues 2-D TMA boxes of the
+// STORED samples (NJ subjects x up to 256 voxels, uint16 or float32 tensor map) plus, for scaled types, the NJ
+// (scale, offset) pairs of the tile's two possible slices (1-D bulk copies out of `tab`, the tables re-packed as
+// [slice][subject][2]) into a STAGES-deep ring guarded by full / empty mbarriers.  CW consumer warps own 4 adjacent
+// voxels per thread, expand them in registers and accumulate; Q' stays resident in shared memory.  Bytes in flight
+// are set by the ring (32 KB per CTA), not by registers, so the FP64 pipe rather than load latency limits it.
+__global__ void pack_tables_kernel(const double *__restrict__ scale, const double *__restrict__ offset, int64_t nslices,
+                                   int n, int n_pad, double2 *__restrict__ tab)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslices * n_pad) return;
+    const int64_t s_ = i / n_pad;
+    const int j = (int)(i % n_pad);
+    tab[i] = j < n ? make_double2(scale[s_ + (int64_t)j * nslices], offset[s_ + (int64_t)j * nslices]) : make_double2(0.0, 0.0);
+}
+
+template <int KP, typename T, int CW, int NJ, int STAGES, int MINB>
+__global__ void __launch_bounds__((CW + 1) * 32, MINB)
+lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a, const double2 *__restrict__ tab, int n_pad)
+{
+    constexpr bool SC = Stored<T>::kScaled;
+    constexpr int VPT = 4;
+    constexpr int TV = CW * 32 * VPT;
+    constexpr int BOXW = TV < 256 ? TV : 256;
+    constexpr int NBOX = TV / BOXW;
+    constexpr int DATA_B = NJ * TV * (int)sizeof(T);
+    constexpr int TAB_B = SC ? 2 * NJ * 16 : 0;
+    constexpr int STAGE_B = (DATA_B + TAB_B + 127) & ~127;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *ring = smem_raw;
+    const int n = a.n;
+    const int nit = (n + NJ - 1) / NJ;
+    double *sQ = reinterpret_cast<double *>(ring + (size_t)STAGES * STAGE_B);
+    SmemDesign<KP> &sd = *reinterpret_cast<SmemDesign<KP> *>(sQ + (size_t)nit * NJ * KP);
+    uint64_t *full = reinterpret_cast<uint64_t *>(&sd + 1);
+    uint64_t *empty = full + STAGES;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    for (int i = tid; i < nit * NJ * KP; i += blockDim.x) sQ[i] = a.Qt[i];   // Qt rows are zero-padded to 16 (make_qt)
+    load_design_to_smem<KP>(sd, a.design, tid, blockDim.x);
+    if (tid == 0) {
+        for (int s_ = 0; s_ < STAGES; ++s_) {
+            mbar_init(&full[s_], 1);
+            mbar_init(&empty[s_], CW);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const int64_t ntiles = (a.V + TV - 1) / TV;
+
+    if (warp == CW) {
+        if ((tid & 31) == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int c0 = (int)(t * TV);
+                const int64_t sl_a = SC ? min((a.v_base + t * TV) / a.slice_len, a.nslices - 1) : 0;
+                const int64_t sl_b = SC ? min(sl_a + 1, a.nslices - 1) : 0;
+                for (int it = 0; it < nit; ++it) {
+                    unsigned char *dst = ring + (size_t)stage * STAGE_B;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], DATA_B + TAB_B);
+#pragma unroll
+                    for (int b = 0; b < NBOX; ++b)
+                        tma_load_2d(dst + (size_t)b * NJ * BOXW * sizeof(T), &umap, &full[stage], c0 + b * BOXW, it * NJ);
+                    if (SC) {
+                        bulk_load_1d(dst + DATA_B, tab + sl_a * n_pad + it * NJ, NJ * 16, &full[stage]);
+                        bulk_load_1d(dst + DATA_B + NJ * 16, tab + sl_b * n_pad + it * NJ, NJ * 16, &full[stage]);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    uint32_t stage = 0, phase = 0;
+    const int lane = tid & 31;
+    const double cm = a.cmagic;
+    const int boff = ((VPT * tid) / BOXW) * NJ * BOXW + (VPT * tid) % BOXW;     // this thread's samples inside a stage
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t v = t * TV + (int64_t)VPT * tid;
+        bool in[VPT];
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) in[i] = v + i < a.V;
+        // which of the tile's two slices each voxel lies in
+        const int64_t sl_a = SC ? min((a.v_base + t * TV) / a.slice_len, a.nslices - 1) : 0;
+        int sel[VPT];
+        bool same = true;
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            sel[i] = (SC && min((a.v_base + v + i) / a.slice_len, a.nslices - 1) != sl_a) ? 1 : 0;
+            same &= sel[i] == sel[0];
+        }
+        VoxelSums<KP> sum[VPT];
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) sum[i].e[k] = 0.0;
+            sum[i].yy = 0.0;
+            sum[i].y0 = 0.0;
+        }
+        for (int it = 0; it < nit; ++it) {
+            mbar_wait(&full[stage], phase);
+            const unsigned char *st = ring + (size_t)stage * STAGE_B;
+            const T *mine = reinterpret_cast<const T *>(st) + boff;
+            const double2 *tabs = reinterpret_cast<const double2 *>(st + DATA_B);
+            const double *q = sQ + (size_t)it * NJ * KP;
+            const int nvalid = min(NJ, n - it * NJ);      // rows >= n of the last box are TMA zero-fill: skipped
+            auto run = [&](auto same_tag) {
+                constexpr bool SAME = decltype(same_tag)::value;
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) {
+                    if (jj < nvalid) {
+                        double y[4];
+                        Stored<T>::convert(*reinterpret_cast<const typename Stored<T>::Raw *>(mine + jj * BOXW), y, cm);
+                        double2 so0 = make_double2(1.0, 0.0), so1 = so0;
+                        if (SC) {
+                            so0 = tabs[(SAME ? sel[0] : 0) * NJ + jj];
+                            if (!SAME) so1 = tabs[NJ + jj];
+                        }
+#pragma unroll
+                        for (int i = 0; i < VPT; ++i) {
+                            double tv = y[i];
+                            if (SC) {
+                                const double2 so = (SAME || sel[i] == 0) ? so0 : so1;
+                                tv = descale(tv, so.x, so.y);
+                            }
+                            if (it == 0 && jj == 0 && sd.shift) sum[i].y0 = tv;
+                            const double yv = tv - sum[i].y0;
+                            sum[i].yy = fma(yv, yv, sum[i].yy);
+#pragma unroll
+                            for (int k = 0; k < KP; ++k) sum[i].e[k] = fma(q[jj * KP + k], yv, sum[i].e[k]);
+                        }
+                    }
+                }
+            };
+            if (same) run(std::true_type{});
+            else run(std::false_type{});
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        // ---- fused epilogue
+        double rss[VPT], mss[VPT];
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            rss[i] = sum[i].yy - sumsq_e(sum[i]);
+            mss[i] = mss_from_e(sum[i], sd);
+            if (in[i] && rss[i] <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0) {
+                const int64_t sli = SC ? min((a.v_base + v + i) / a.slice_len, a.nslices - 1) : 0;
+                const double2 ex = exact_pass_packed<KP, T>(static_cast<const T *>(a.U) + v + i, a.ldU, n, a.Qt, sum[i].y0, cm,
+                                                            a.scale + sli, a.offset + sli, a.nslices);
+                rss[i] = ex.x;
+                mss[i] = ex.y;
+            }
+        }
+        if (a.out_vec2 && in[VPT - 1]) {
+#pragma unroll
+            for (int i = 0; i + 1 < VPT; i += 2)
+                finish_pair<KP>(sum[i], rss[i], mss[i], true, sum[i + 1], rss[i + 1], mss[i + 1], true, sd, a.out + v + i, a.ldOut);
+        } else {
+#pragma unroll
+            for (int i = 0; i < VPT; ++i)
+                if (in[i]) finish_voxel<KP>(sum[i], rss[i], mss[i], sd, a.out + v + i, a.ldOut);
+        }
+    }
+}
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn packed_encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// returns cudaErrorNotSupported when this layout / size is not for the TMA variant (caller falls back)
+template <int KP, typename T, int MINB>
+cudaError_t launch_packed_tma(const PackedArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
+{
+    constexpr bool SC = Stored<T>::kScaled;
+    constexpr int CW = 4, NJ = 8, STAGES = 4;
+    constexpr int TV = CW * 128, BOXW = 256;
+    constexpr int STAGE_B = (NJ * TV * (int)sizeof(T) + (SC ? 2 * NJ * 16 : 0) + 127) & ~127;
+    if (a.mask || KP > 8) return cudaErrorNotSupported;
+    if ((reinterpret_cast<uintptr_t>(a.U) & 15) || (a.ldU * sizeof(T)) % 16 || a.V > 0x7fffffffLL) return cudaErrorNotSupported;
+    if (SC && a.slice_len < TV) return cudaErrorNotSupported;          // a tile may then touch more than two slices
+    if (a.V < (int64_t)plan.sm_count * TV) return cudaErrorNotSupported;   // too few tiles to fill the GPU
+    const int nit = (a.n + NJ - 1) / NJ;
+    const size_t smem = (size_t)STAGES * STAGE_B + (size_t)nit * NJ * KP * 8 + sizeof(SmemDesign<KP>) + 2 * STAGES * 8 + 128;
+    if (smem > 56 * 1024) return cudaErrorNotSupported;
+    EncodeTiledFn enc = packed_encode_tiled();
+    if (!enc) return cudaErrorNotSupported;
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t)a.V, (cuuint64_t)a.n};
+    const cuuint64_t strides[1] = {(cuuint64_t)a.ldU * sizeof(T)};
+    const cuuint32_t box[2] = {BOXW, NJ};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    if (enc(&map, dt, 2, const_cast<void *>(a.U), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorNotSupported;
+    const int n_pad = nit * NJ;
+    const double2 *tab = nullptr;
+    if (SC) {
+        cudaError_t e = scr.ensure_bytes((size_t)a.nslices * n_pad * sizeof(double2), st);
+        if (e != cudaSuccess) return e;
+        const int64_t cnt = a.nslices * n_pad;
+        pack_tables_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(a.scale, a.offset, a.nslices, a.n, n_pad,
+                                                                        reinterpret_cast<double2 *>(scr.flags));
+        if (info) info->launches++;
+        tab = reinterpret_cast<const double2 *>(scr.flags);
+    }
+    auto kern = lm_fit_packed_tma_kernel<KP, T, CW, NJ, STAGES, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t ntiles = (a.V + TV - 1) / TV;
+    const int64_t slots = (int64_t)plan.sm_count * MINB;
+    kern<<<(int)(ntiles < slots ? ntiles : slots), (CW + 1) * 32, smem, st>>>(map, a, tab, n_pad);
+    if (info) { info->launches++; info->used_tma = 1; }
+    return cudaGetLastError();
+}
+
+template <int KP, typename T>
+cudaError_t launch_packed_t(const PackedArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
+{
+    if (plan.variant != LmVariant::Ldg) {
+        if constexpr (KP <= 8) {
+            // CTAs per SM: as many as the accumulators leave registers for (RMG_TMA_CFG=1 forces one more, with spills)
+            constexpr int MINB = KP <= 2 ? 4 : (KP <= 4 ? 3 : 2);
+            const cudaError_t e = plan.tma_cfg == 1 ? launch_packed_tma<KP, T, MINB + 1>(a, plan, scr, st, info)
+                                                    : launch_packed_tma<KP, T, MINB>(a, plan, scr, st, info);
+            if (e != cudaErrorNotSupported) return e;
+        }
+    }
+    // vector path: 4 samples per load need an 8-byte (u16) / 16-byte (f32) aligned base and row pitch
+    const bool vec = (reinterpret_cast<uintptr_t>(a.U) % (4 * sizeof(T)) == 0) && (a.ldU % 4 == 0);
+    constexpr int QW = ((KP + 1) & ~1) + (Stored<T>::kScaled ? 4 : 0);
+    int JT = a.n;
+    while ((size_t)JT * QW * 8 > 40 * 1024) JT = ((JT + 1) / 2 + 7) & ~7;   // multiple of the unroll depth
+    const size_t smem = (size_t)JT * QW * 8;
+    const int VPT = vec ? 4 : 1;
+    const int64_t per_block = (int64_t)128 * VPT;
+    const int64_t blocks = (a.V + per_block - 1) / per_block;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)blocks, 128, smem, st>>>(a, JT);
+        return cudaGetLastError();
+    };
+    const cudaError_t e = vec ? go(lm_fit_packed_kernel<KP, T, 4>) : go(lm_fit_packed_kernel<KP, T, 1>);
+    if (info) { info->launches++; info->used_tma = 0; info->split = 1; }
+    return e;
+}
+
+template <int KP>
+cudaError_t launch_packed_kp(const PackedArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
+{
+    if (a.dtype == kStoredU16) return launch_packed_t<KP, uint16_t>(a, plan, scr, st, info);
+    if (a.dtype == kStoredF32) return launch_packed_t<KP, float>(a, plan, scr, st, info);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+cudaError_t launch_lm_packed(const PackedArgs &a_in, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
+{
+    if (a_in.V <= 0) return cudaSuccess;
+    PackedArgs a = a_in;
+    a.out_vec2 = ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && a.ldOut % 2 == 0) ? 1 : 0;
+    switch (lm_padded_p(a.p)) {
+#define RMG_CASE(K) case K: return launch_packed_kp<K>(a, plan, scr, st, info);
+        RMG_CASE(1) RMG_CASE(2) RMG_CASE(3) RMG_CASE(4) RMG_CASE(5) RMG_CASE(6) RMG_CASE(7) RMG_CASE(8)
+        RMG_CASE(12) RMG_CASE(16)
+#undef RMG_CASE
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace rmg

@@ -443,3 +443,111 @@ def test_covariate_device_entry_point(core, oracle):
     core.lm_fit_cov_torch(Yt, Zt, Xs, out=out, status=status)
     torch.cuda.synchronize()
     assert int(status.item()) == 4 and torch.isnan(out[:, 17]).all()
+
+
+# ------------------------------------------------------------------ volumes in their stored type
+def _stored_case(V, n, slice_len, seed, p=4, effect=300.0):
+    rng = np.random.default_rng(seed)
+    X = design_cfg2(n)[:, :p] if p <= 4 else design_cov(n, p, seed=seed + 1000)
+    nsl = -(-V // slice_len)
+    U = np.clip(rng.normal(30000, 400, (V, n)) + effect * np.outer(rng.random(V), X[:, min(1, p - 1)]), 0, 65535)
+    U = np.asfortranarray(np.round(U).astype(np.uint16))
+    smin = rng.normal(-0.8, 0.05, (nsl, n))
+    smax = smin + rng.uniform(1.5, 2.5, (nsl, n))
+    return U, X, (smax - smin) / 65535.0, smin
+
+
+@pytest.mark.parametrize("V,slice_len", [(4096, 512), (4100, 410), (3001, 333), (2048, 2048)])
+def test_stored_u16_matches_oracle_on_expanded_doubles(core, oracle, V, slice_len):
+    """uint16 voxels + per-slice real ranges: the device forms the same doubles libminc would and fits them."""
+    U, X, scale, offset = _stored_case(V, 60, slice_len, seed=V)
+    Y = oracle.expand_stored(U, scale, offset, slice_len=slice_len)
+    got = core.lm_fit_stored(U, X, scale, offset, slice_len=slice_len)
+    assert_rows_match(got, oracle.vertex_lm_loop(Y, X), RTOL, "stored u16")
+    # and it is the same fit as the double path on the expanded matrix, far inside the tolerance
+    assert_rows_match(got, core.lm_fit(Y, X), 1e-11, "stored vs expanded on device")
+
+
+def test_stored_variants(core, oracle, monkeypatch):
+    U, X, scale, offset = _stored_case(5000, 48, 1000, seed=3)
+    V = U.shape[0]
+    # non-zero valid_min, mask with maskval, masked rows +0.0
+    Y = oracle.expand_stored(U, scale, offset, voxel_min=100.0, slice_len=1000)
+    mask = (np.arange(V) % 4).astype(float)
+    got = core.lm_fit_stored(U, X, scale, offset, voxel_min=100.0, slice_len=1000, mask=mask, mask_lo=2, mask_hi=2)
+    assert_rows_match(got, oracle.minc2_model_lm(Y, (5, 10, 100), X, mask=mask, lo=2, hi=2), RTOL, "mask")
+    assert (got[mask != 2] == 0).all() and not np.signbit(got[mask != 2]).any()
+    # several chunks through the host pipeline: slices keep their global index
+    monkeypatch.setenv("RMG_CHUNK_VOXELS", "1400")
+    assert_rows_match(core.lm_fit_stored(U, X, scale, offset, voxel_min=100.0, slice_len=1000),
+                      oracle.vertex_lm_loop(Y, X), RTOL, "chunked")
+    monkeypatch.delenv("RMG_CHUNK_VOXELS")
+    # float32 volumes convert exactly
+    F = np.asfortranarray(np.random.default_rng(4).normal(0, 0.2, (3000, 48)).astype(np.float32))
+    assert_rows_match(core.lm_fit_stored(F, X), oracle.vertex_lm_loop(F.astype(np.float64), X), RTOL, "f32")
+    F1 = np.asfortranarray(F[:2999])                                         # odd V: scalar path
+    assert_rows_match(core.lm_fit_stored(F1, X), oracle.vertex_lm_loop(F1.astype(np.float64), X), RTOL, "f32 odd")
+    # every padded design width
+    for p in (1, 2, 3, 5, 7, 8, 11, 16):
+        Up, Xp, sc, of = _stored_case(1024, 64, 256, seed=50 + p, p=p)
+        Yp = oracle.expand_stored(Up, sc, of, slice_len=256)
+        c0 = 2 if p == 1 else 0          # intercept only: F and R2 are 0/0 noise in the reference (see test_every_padded_width)
+        assert_rows_match(core.lm_fit_stored(Up, Xp, sc, of, slice_len=256)[:, c0:], oracle.vertex_lm_loop(Yp, Xp)[:, c0:],
+                          RTOL, f"p={p}")
+    # argument contract
+    with pytest.raises(core.RmincGpuError, match="voxel_min must be an integer"):
+        core.lm_fit_stored(U, X, scale, offset, voxel_min=0.5, slice_len=1000)
+    with pytest.raises(ValueError):
+        core.lm_fit_stored(U.astype(np.int32), X, scale, offset)
+
+
+def test_stored_degenerate_and_near_perfect_voxels(core, oracle):
+    """Quantised data: constant voxels (background) and voxels the design explains almost entirely."""
+    rng = np.random.default_rng(8)
+    V, n = 2048, 40
+    X = design_cfg1(n)
+    U = np.round(rng.normal(20000, 300, (V, n))).astype(np.uint16)
+    U[::9] = 0                                                              # background: all subjects zero
+    U[1::9] = (1000 + 20000 * X[:, 1] + rng.integers(0, 3, (len(U[1::9]), n))).astype(np.uint16)   # near-perfect fit
+    U = np.asfortranarray(U)
+    scale = np.full((1, n), 2.0 / 65535.0)
+    offset = np.full((1, n), -1.0)
+    Y = oracle.expand_stored(U, scale, offset)
+    got, want = core.lm_fit_stored(U, X, scale, offset), oracle.vertex_lm_loop(Y, X)
+    const = np.zeros(V, bool)
+    const[::9] = True
+    # constant voxels: rss is exactly 0 here (classes as SURVEY A.4: the reference's rounding noise is unmatchable)
+    assert np.isposinf(got[const, -1]).all() and np.isnan(got[const, 0]).all()
+    assert_rows_match(got[~const], want[~const], RTOL, "quantised")
+
+
+def test_stored_device_entry_point(core, oracle):
+    import torch
+    U, X, scale, offset = _stored_case(8192, 50, 1024, seed=21)
+    Y = oracle.expand_stored(U, scale, offset, slice_len=1024)
+    Ut = torch.from_numpy(np.ascontiguousarray(U.T).view(np.int16)).cuda().view(torch.uint16)
+    sc = torch.from_numpy(np.ascontiguousarray(scale.T)).cuda()
+    of = torch.from_numpy(np.ascontiguousarray(offset.T)).cuda()
+    out = core.lm_fit_stored_torch(Ut, X, sc, of, slice_len=1024)
+    torch.cuda.synchronize()
+    assert_rows_match(out.cpu().numpy().T, oracle.vertex_lm_loop(Y, X), RTOL, "device u16")
+    assert core.last_fit_variant() == "lm_fit_packed_kernel"
+
+
+@pytest.mark.parametrize("slice_len", [1001, 4096, 80128])
+def test_stored_tma_ring_variant(core, oracle, slice_len):
+    """Large V takes the TMA-staged kernel: stored samples + the tile's (scale, offset) rows through the shared-memory
+    ring.  slice_len = 1001 puts slice boundaries inside tiles and inside a thread's four voxels."""
+    V, n = 80128, 24
+    U, X, scale, offset = _stored_case(V, n, slice_len, seed=slice_len)
+    Y = oracle.expand_stored(U, scale, offset, voxel_min=3.0, slice_len=slice_len)
+    got = core.lm_fit_stored(U, X, scale, offset, voxel_min=3.0, slice_len=slice_len)
+    assert core.last_fit_variant() == "lm_fit_packed_tma_kernel"
+    assert_rows_match(got, oracle.vertex_lm_loop(Y, X), RTOL, "tma u16")
+    if slice_len == 4096:
+        F = np.asfortranarray(Y.astype(np.float32))
+        got = core.lm_fit_stored(F, X[:, :3])
+        assert core.last_fit_variant() == "lm_fit_packed_tma_kernel"
+        assert_rows_match(got, oracle.vertex_lm_loop(F.astype(np.float64), X[:, :3]), RTOL, "tma f32")
+        Fr = np.asfortranarray(F[:79999])                                     # ragged tail: TMA zero-fill, scalar stores
+        assert_rows_match(core.lm_fit_stored(Fr, X), oracle.vertex_lm_loop(Fr.astype(np.float64), X), RTOL, "tma f32 ragged")

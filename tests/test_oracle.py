@@ -316,3 +316,25 @@ def test_voxelwise_covariate_restatement(oracle):
     Z0[3, :] = 0.0
     with pytest.raises(oracle.OracleError, match="is zero, so the inverse cannot be computed"):
         oracle.lm_loop_cov(Y, Z0, Xs)
+
+
+def test_stored_type_expansion(oracle):
+    """The doubles the reference's read loop produces from stored voxels (libminc's real-range conversion,
+    restated: orc_expand_u16): (u - valid_min) * scale[slice, subject] + offset[slice, subject], each operation
+    rounded once; float32 converts exactly."""
+    rng = np.random.default_rng(31)
+    V, n, slice_len = 210, 7, 40                        # 6 slices, the last one short
+    U = rng.integers(0, 65536, (V, n)).astype(np.uint16)
+    nsl = -(-V // slice_len)
+    smin = rng.normal(-1, 0.1, (nsl, n))
+    smax = smin + rng.uniform(1, 3, (nsl, n))
+    scale, offset = (smax - smin) / 65535.0, smin
+    got = oracle.expand_stored(U, scale, offset, voxel_min=0.0, slice_len=slice_len)
+    sl = np.arange(V) // slice_len
+    want = (U.astype(np.float64) - 0.0) * scale[sl, :] + offset[sl, :]
+    assert np.array_equal(got, want)
+    assert got.min() >= smin.min() - 1e-12 and got.max() <= smax.max() + 1e-12
+    got5 = oracle.expand_stored(U, scale, offset, voxel_min=5.0, slice_len=slice_len)
+    assert np.array_equal(got5, (U.astype(np.float64) - 5.0) * scale[sl, :] + offset[sl, :])
+    F = rng.normal(size=(V, n)).astype(np.float32)
+    assert np.array_equal(oracle.expand_stored(F), F.astype(np.float64))
