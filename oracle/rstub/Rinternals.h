@@ -13,6 +13,7 @@ typedef unsigned int SEXPTYPE;
 #define REALSXP 14
 #define STRSXP 16
 #define CHARSXP 9
+#define RAWSXP 24
 typedef ptrdiff_t R_xlen_t;
 extern SEXP R_NilValue;
 SEXP Rf_allocVector(SEXPTYPE type, R_xlen_t n);
@@ -39,6 +40,8 @@ int Rf_asLogical(SEXP s);
 double Rf_asReal(SEXP s);
 SEXP Rf_GetOption1(SEXP tag);
 R_xlen_t XLENGTH(SEXP s);
+int TYPEOF(SEXP s);               /* declaration only: used by rminc_b200/csrc/rshim.c's syntax check */
+unsigned char *RAW(SEXP s);
 char *R_alloc(size_t n, int size);
 #ifndef FALSE
 #define FALSE 0

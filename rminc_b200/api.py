@@ -104,6 +104,62 @@ def default_reader(item) -> np.ndarray:
     raise TypeError(f"cannot stage a volume from {type(item).__name__}")
 
 
+class StoredVolume:
+    """A volume as the file stores it: `voxels` (uint16 or float32, any shape, file order) plus, for uint16, the
+    per-slice real range of the slowest dimension as MINC keeps it (image-min / image-max) and the valid range.
+    A reader that returns StoredVolume objects instead of double arrays makes mincLm ship 2 (or 4) bytes per
+    sample to the GPU, where the doubles libminc's miget_real_value_hyperslab would produce are formed in
+    registers (src/modelling_functions.c:1037-1055; rmg_lm_fit_stored)."""
+
+    def __init__(self, voxels, image_min=None, image_max=None, valid_range=(0.0, 65535.0)):
+        v = np.asarray(voxels)
+        if v.dtype not in (np.uint16, np.float32):
+            raise TypeError("StoredVolume voxels must be uint16 or float32")
+        self.voxels = v
+        self.nslices = 1
+        self.scale = self.offset = None
+        self.valid_min = float(valid_range[0])
+        if v.dtype == np.uint16:
+            lo = np.atleast_1d(np.asarray(image_min, dtype=np.float64))
+            hi = np.atleast_1d(np.asarray(image_max, dtype=np.float64))
+            if lo.shape != hi.shape or lo.ndim != 1 or (lo.size != 1 and lo.size != v.shape[0]):
+                raise ValueError("image_min / image_max: one value, or one per slice of the slowest dimension")
+            self.nslices = lo.size
+            self.scale = (hi - lo) / (float(valid_range[1]) - float(valid_range[0]))
+            self.offset = lo
+
+    def real(self) -> np.ndarray:
+        """The doubles the CPU reader would return (what mincGetVolume yields)."""
+        v = self.voxels
+        if v.dtype == np.float32:
+            return v.astype(np.float64).reshape(-1)
+        shape = (self.nslices,) + (1,) * (v.ndim - 1) if self.nslices > 1 else (1,) * v.ndim
+        return ((v.astype(np.float64) - self.valid_min) * self.scale.reshape(shape) + self.offset.reshape(shape)).reshape(-1)
+
+
+def mincTableStored(vols: Sequence["StoredVolume"]):
+    """U (V x n, stored type), scale / offset ([nslices x n]), voxel_min, slice_len for rmg_lm_fit_stored."""
+    first = vols[0]
+    V, n = first.voxels.size, len(vols)
+    U = np.empty((V, n), dtype=first.voxels.dtype, order="F")
+    nsl = max(v.nslices for v in vols)
+    scale = offset = None
+    if first.voxels.dtype == np.uint16:
+        scale, offset = np.empty((nsl, n)), np.empty((nsl, n))
+    for j, v in enumerate(vols):
+        if v.voxels.size != V or v.voxels.dtype != U.dtype:
+            raise ValueError("all volumes must have the same number of voxels and the same stored type")
+        if v.valid_min != first.valid_min:
+            raise ValueError("all volumes must share one valid range")
+        U[:, j] = v.voxels.reshape(-1)
+        if scale is not None:
+            scale[:, j] = np.broadcast_to(v.scale, (nsl,)) if v.nslices in (1, nsl) else np.nan
+            offset[:, j] = np.broadcast_to(v.offset, (nsl,)) if v.nslices in (1, nsl) else np.nan
+            if v.nslices not in (1, nsl):
+                raise ValueError("volumes disagree on the number of slices")
+    return U, scale, offset, first.valid_min, (V // nsl if nsl > 1 else max(V, 1))
+
+
 def mincTable(filenames: Sequence, mask=None, reader: Callable = default_reader) -> np.ndarray:
     """V x n matrix, one column per file (R/minc_interface.R:1031-1077), Fortran order."""
     first = reader(filenames[0])
@@ -207,10 +263,28 @@ def mincLm(formula: str, data, subset=None, mask=None, maskval=None, parallel=No
     rows = _subset_rows(data, subset)
     plm = parseLmFormula(rhs, data, rows)                                        # :796
     filenames = _column(data, lhs, rows)
+    lo, hi = core.mask_range(maskval)                                            # :781-787
+    first = reader(filenames[0])
+    if isinstance(first, StoredVolume) and not plm["matrixFound"]:
+        # the volumes travel in their stored type; the device forms the doubles (one GPU)
+        vols = [first] + [reader(f) for f in filenames[1:]]
+        U, scale, offset, vmin, slice_len = mincTableStored(vols)
+        X, names, _ = model_matrix(rhs, data, rows)
+        m = _stage_mask(mask, U.shape[0], reader)
+        out = core.lm_fit_stored(U, X, scale, offset, voxel_min=vmin, slice_len=slice_len, mask=m, mask_lo=lo, mask_hi=hi,
+                                 device=device)
+        n, p = X.shape
+        attrs = {
+            "likeVolume": filenames[0], "filenames": list(filenames), "model": X, "data": data,
+            "call": dict(fn="mincLm", formula=formula, subset=subset, mask=mask, maskval=maskval, parallel=parallel),
+            "stat-type": _stat_type(p), "df": _df_list(n, p), "model-colnames": names,
+        }
+        return MincMatrix(out, colnames=_colnames(names), attrs=attrs, r_class=("mincLm", "mincMultiDim", "matrix"))
+    if isinstance(first, StoredVolume):
+        reader = (lambda rd: lambda item: (lambda v: v.real() if isinstance(v, StoredVolume) else v)(rd(item)))(reader)
     Y = mincTable(filenames, reader=reader)
     V, n = Y.shape
     m = _stage_mask(mask, V, reader)
-    lo, hi = core.mask_range(maskval)                                            # :781-787
     if plm["matrixFound"]:
         # a volume on the right-hand side: per-voxel design [mmatrix | z_v] (minc2_model with filenames_right)
         Z = mincTable(plm["right"], reader=reader)

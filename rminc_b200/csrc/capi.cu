@@ -479,10 +479,12 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
         }
         for (int b = 0; b < NB; ++b) {
             RMG_CUDA(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
-            RMG_CUDA(cudaMalloc(&dY[b], (size_t)ldc * n * es));
-            RMG_CUDA(cudaMalloc(&dO[b], (size_t)ldc * ncol * sizeof(double)));
-            if (mask) RMG_CUDA(cudaMalloc(&dM[b], (size_t)ldc * sizeof(double)));
-            if (Z) RMG_CUDA(cudaMalloc(&dZ[b], (size_t)ldc * n * sizeof(double)));
+            // stream-ordered allocations: the pool keeps the chunk buffers across calls (release threshold set in
+            // select_device), so a repeated call pays no cudaMalloc / cudaFree of gigabyte buffers
+            RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dY[b]), (size_t)ldc * n * es, st[b]));
+            RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dO[b]), (size_t)ldc * ncol * sizeof(double), st[b]));
+            if (mask) RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dM[b]), (size_t)ldc * sizeof(double), st[b]));
+            if (Z) RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dZ[b]), (size_t)ldc * n * sizeof(double), st[b]));
         }
         if (Z) {
             RMG_CUDA(cudaMalloc(&dstatus, sizeof(int)));
@@ -567,10 +569,11 @@ cleanup:
     for (int b = 0; b < 3; ++b) {
         scr[b].release(st[b]);
         if (st[b]) cudaStreamSynchronize(st[b]);
-        if (dY[b]) cudaFree(dY[b]);
-        if (dO[b]) cudaFree(dO[b]);
-        if (dM[b]) cudaFree(dM[b]);
-        if (dZ[b]) cudaFree(dZ[b]);
+        if (dY[b]) cudaFreeAsync(dY[b], st[b]);
+        if (dO[b]) cudaFreeAsync(dO[b], st[b]);
+        if (dM[b]) cudaFreeAsync(dM[b], st[b]);
+        if (dZ[b]) cudaFreeAsync(dZ[b], st[b]);
+        if (st[b]) cudaStreamSynchronize(st[b]);
         if (st[b]) cudaStreamDestroy(st[b]);
     }
     if (dstatus) cudaFree(dstatus);

@@ -494,7 +494,7 @@ cudaError_t launch_packed_tma(const PackedArgs &a, const LmPlan &plan, LmScratch
     if (a.V < (int64_t)plan.sm_count * TV) return cudaErrorNotSupported;   // too few tiles to fill the GPU
     const int nit = (a.n + NJ - 1) / NJ;
     const size_t smem = (size_t)STAGES * STAGE_B + (size_t)nit * NJ * KP * 8 + sizeof(SmemDesign<KP>) + 2 * STAGES * 8 + 128;
-    if (smem > 56 * 1024) return cudaErrorNotSupported;
+    if (smem > (size_t)(227 * 1024) / MINB - 1024) return cudaErrorNotSupported;   // MINB CTAs must fit an SM (1 KB reserved each)
     EncodeTiledFn enc = packed_encode_tiled();
     if (!enc) return cudaErrorNotSupported;
     CUtensorMap map;

@@ -12,6 +12,7 @@
  *                            vertexLm / anatLm only change the routine name
  *   rmincgpu_lm              minc2_model(method = "lm") with the volumes already staged
  *   rmincgpu_lm_cov          the same with filenames_right (a voxel-wise covariate) staged as a second matrix
+ *   rmincgpu_lm_stored       the same on volumes in their stored type (uint16 + real ranges, float32)
  *   rmincgpu_randomize       the mincRandomize loop (R/minc_voxel_statistics.R:1465-1497)
  *   rmincgpu_anova           per_voxel_anova / vertex_anova_loop (src/minc_anova.c:142, src/vertex_modelling.c:178)
  */
@@ -128,6 +129,32 @@ SEXP rmincgpu_lm_cov(SEXP Y, SEXP Z, SEXP mmatrix, SEXP mask, SEXP mask_lower, S
     return out;
 }
 
+/* mincLm on volumes in their stored type.  U is a RAWSXP holding V x n samples (uint16 or float32, column-major,
+ * filled by a staging routine that calls miget_voxel_value_hyperslab with the file's own type -- INTEGRATION.md);
+ * scale / offset are nslices x n double matrices from image-min / image-max and the valid range. */
+SEXP rmincgpu_lm_stored(SEXP U, SEXP dtype, SEXP nvoxels, SEXP scale, SEXP offset, SEXP voxel_min, SEXP slice_len,
+                        SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP mask_upper)
+{
+    if (TYPEOF(U) != RAWSXP || !Rf_isReal(mmatrix)) Rf_error("U must be a raw vector and mmatrix a double matrix");
+    const int dt = Rf_asInteger(dtype);
+    const size_t es = dt == RMG_STORED_U16 ? 2 : 4;
+    const R_xlen_t V = (R_xlen_t)Rf_asReal(nvoxels);
+    const int n = Rf_nrows(mmatrix), p = Rf_ncols(mmatrix);
+    if ((R_xlen_t)(XLENGTH(U) / es) != V * n) Rf_error("U holds %.0f samples, expected %.0f", (double)(XLENGTH(U) / es), (double)V * n);
+    const int scaled = dt == RMG_STORED_U16;
+    if (scaled && (!Rf_isReal(scale) || !Rf_isReal(offset) || Rf_ncols(scale) != n || Rf_ncols(offset) != n))
+        Rf_error("scale and offset must be nslices x n double matrices");
+    const double *m = mask_or_null(mask, V);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, 2 * p + 3));
+    char err[512] = "";
+    int rc = rmg_lm_fit_stored(RAW(U), dt, V, V > 0 ? V : 1, n, scaled ? REAL(scale) : NULL, scaled ? REAL(offset) : NULL,
+                               Rf_asReal(voxel_min), (int64_t)Rf_asReal(slice_len), REAL(mmatrix), p, m,
+                               Rf_asReal(mask_lower), Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, 0, err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
 SEXP rmincgpu_randomize(SEXP Y, SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP mask_upper, SEXP idx,
                         SEXP columns, SEXP two_sided, SEXP ngpu)
 {
@@ -180,6 +207,7 @@ static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_vertex_wlm_loop", (DL_FUNC)&rmincgpu_vertex_wlm_loop, 4},
     {"rmincgpu_lm", (DL_FUNC)&rmincgpu_lm, 6},
     {"rmincgpu_lm_cov", (DL_FUNC)&rmincgpu_lm_cov, 6},
+    {"rmincgpu_lm_stored", (DL_FUNC)&rmincgpu_lm_stored, 11},
     {"rmincgpu_randomize", (DL_FUNC)&rmincgpu_randomize, 9},
     {"rmincgpu_anova", (DL_FUNC)&rmincgpu_anova, 6},
     {NULL, NULL, 0}};

@@ -36,6 +36,12 @@ def api(request, monkeypatch, oracle, lib):
         def lm_fit_cov(Y, Z, Xs=None, mask=None, mask_lo=1.0, mask_hi=99999999.0, device=0):
             return oracle.lm_loop_cov(Y, Z, Xs, mask=mask, lo=mask_lo, hi=mask_hi)
 
+        def lm_fit_stored(U, X, scale=None, offset=None, voxel_min=0.0, slice_len=None, mask=None, mask_lo=1.0,
+                          mask_hi=99999999.0, device=0):
+            Y = oracle.expand_stored(U, scale, offset, voxel_min=voxel_min, slice_len=slice_len)
+            return oracle.minc2_model_lm(Y, (1, 1, Y.shape[0]), X, mask=mask, lo=mask_lo, hi=mask_hi)
+
+        monkeypatch.setattr(core, "lm_fit_stored", lm_fit_stored)
         monkeypatch.setattr(core, "lm_fit_cov", lm_fit_cov)
         monkeypatch.setattr(core, "vertex_wlm", vertex_wlm)
         monkeypatch.setattr(core, "anova_fit", anova_fit)
@@ -296,3 +302,34 @@ def test_file_covariate_on_the_right_hand_side(api, study, tmp_path):
     Zv = np.column_stack([np.loadtxt(f) for f in zf])
     assert rv.r_class == ("vertexLm", "vertexMultiDim", "matrix") and rv.shape == (V, 9)
     check_row(rv, 5, Yv[5], np.column_stack([np.ones(n), sexm, Zv[5]]), ["(Intercept)", "SexM", "curv"])
+
+
+def test_mincLm_on_stored_volumes(api, study):
+    """A reader that hands over the stored voxels (uint16 + per-slice real range, as MINC keeps them) instead of
+    doubles: same result as the fit on the doubles the CPU reader would have produced."""
+    gf, maskfile, _ = study
+    rng = np.random.default_rng(2)
+    store = {}
+    for f in gf.jacobians:
+        real = np.load(f)
+        lo, hi = real.min(axis=(1, 2)) - 0.01, real.max(axis=(1, 2)) + 0.01          # per-slice image-min / image-max
+        vox = np.round((real - lo[:, None, None]) / (hi - lo)[:, None, None] * 65535.0).astype(np.uint16)
+        store[f] = api.StoredVolume(vox, image_min=lo, image_max=hi)
+
+    def stored_reader(item):
+        return store[item] if item in store else api.default_reader(item)
+
+    vs = api.mincLm("jacobians ~ Sex + Scale", gf, mask=maskfile, reader=stored_reader)
+    Yq = np.stack([store[f].real() for f in gf.jacobians], axis=1)                   # the quantised doubles
+    X = np.column_stack([np.ones(10), gf.Sex == "M", gf.Scale.values]).astype(float)
+    inside = np.load(maskfile).reshape(-1) > 0.5
+    v = int(np.flatnonzero(inside)[17])
+    check_row(vs, v, Yq[v], X, ["(Intercept)", "SexM", "Scale"])
+    assert (np.asarray(vs)[~inside] == 0).all()
+    # float32 volumes need no range tables
+    f32 = {f: api.StoredVolume(np.load(f).astype(np.float32)) for f in gf.jacobians}
+    v32 = api.mincLm("jacobians ~ Sex", gf, reader=lambda item: f32[item])
+    Y32 = np.stack([np.load(f).astype(np.float32).astype(np.float64).reshape(-1) for f in gf.jacobians], axis=1)
+    check_row(v32, 3, Y32[3], X[:, :2], ["(Intercept)", "SexM"])
+    with pytest.raises(TypeError):
+        api.StoredVolume(np.zeros(4, dtype=np.int32))
