@@ -184,6 +184,30 @@ int rmg_anova_fit_device(const double *dY, int64_t V, int64_t ldY, int n, const 
                          double *dout, int64_t ldOut, int device, void *stream, char *err, size_t errlen);
 
 /*
+ * mincFDR / vertexFDR / anatFDR for one result column (mincFDR.mincMultiDim, R/minc_FDR.R:254-520).
+ *   stat        V statistics (a tvalue- or F-statistic column of the fit)
+ *   stat_type   RMG_STAT_T: p = pt2(t, df1) = 2 pt(-|t|, df1) (two-sided, :392-397)
+ *               RMG_STAT_F: p = pf(F, df1, df2, lower.tail = FALSE) (:398-412)
+ *   mask        NULL or V doubles; voxels with mask > 0.5 take part (:394)
+ *   qvalues     V doubles: p.adjust(p, "fdr") (Benjamini-Hochberg) over the participating voxels, NaN where the
+ *               statistic is NaN (such voxels do not count), 1 outside the mask (:369, :505)
+ *   thresholds  5 doubles (nullable): the statistic at q <= 0.01, 0.05, 0.10, 0.15, 0.20, i.e.
+ *               qt(max p / 2, df1, lower.tail = FALSE) or qf(max p, df1, df2, lower.tail = FALSE) of the largest
+ *               accepted p-value; NaN when no voxel passes (:444-475)
+ * pt / pf live in libR (nmath), not in the reference tree: restated through the regularised incomplete beta function.
+ */
+#define RMG_STAT_T 1
+#define RMG_STAT_F 2
+int rmg_fdr(const double *stat, int64_t V, int stat_type, double df1, double df2, const double *mask,
+            double *qvalues, double *thresholds, int device, char *err, size_t errlen);
+/* dstat / dmask / dq on `device`, work enqueued on `stream`; synchronises the stream before it returns (the
+ * thresholds are host values). */
+int rmg_fdr_device(const double *dstat, int64_t V, int stat_type, double df1, double df2, const double *dmask,
+                   double *dq, double *thresholds, int device, void *stream, char *err, size_t errlen);
+/* p-value of one statistic, evaluated on the host by the same code the device runs. */
+double rmg_pvalue(double stat, int stat_type, double df1, double df2);
+
+/*
  * mincRandomize.  Replaces the R loop of R/minc_voxel_statistics.R:1465-1497, which re-runs
  * the whole mincLm call once per permutation.
  *   idx      n x R, 0-based row indices drawn by the caller (R's sample()); permutation r

@@ -329,3 +329,50 @@ def expand_stored(U, scale=None, offset=None, voxel_min=0.0, slice_len=None):
     lib().orc_expand_u16(U.ctypes.data_as(C.c_void_p), C.c_int64(V), C.c_int64(max(V, 1)), C.c_int(n), _p(sc), _p(of),
                          C.c_double(voxel_min), C.c_int64(slice_len), _p(out), C.c_int64(max(V, 1)))
     return out
+
+
+# ------------------------------------------------------------------ mincFDR (R/minc_FDR.R:254-520)
+FDR_LEVELS = (0.01, 0.05, 0.10, 0.15, 0.20)
+
+
+def p_adjust_bh(p):
+    """R's p.adjust(p, "fdr") (stats::p.adjust, method "BH"): NA p-values are dropped, n is the number of the
+    remaining ones (the default n = length(p) is a promise evaluated after the NAs were removed), and
+    q = pmin(1, cummin(n / i * p[o]))[ro] with o = order(p, decreasing = TRUE)."""
+    p = np.asarray(p, dtype=np.float64)
+    q = np.full(p.shape, np.nan)
+    ok = ~np.isnan(p)
+    pp = p[ok]
+    n = pp.size
+    if n == 0:
+        return q
+    o = np.argsort(-pp, kind="stable")
+    i = np.arange(n, 0, -1)
+    adj = np.minimum(1.0, np.minimum.accumulate(n / i * pp[o]))
+    out = np.empty(n)
+    out[o] = adj
+    q[ok] = out
+    return q
+
+
+def fdr(stat, stat_type, df1, df2=None, mask=None):
+    """mincFDR.mincMultiDim for one column (R/minc_FDR.R:385-505): p-values (pt2 = 2 pt(-|t|, df) for "t",
+    pf(F, df1, df2, lower.tail = FALSE) for "F"; scipy's t / f distributions stand in for R's nmath), BH q-values
+    over mask > 0.5, output 1 outside the mask, thresholds qt(max p / 2, df, lower = FALSE) / qf(max p, ...)."""
+    from scipy import stats as S
+    s = np.asarray(stat, dtype=np.float64).reshape(-1)
+    sel = np.ones(s.shape, bool) if mask is None else (np.asarray(mask).reshape(-1) > 0.5)
+    if stat_type == "t":
+        p = 2.0 * S.t.sf(np.abs(s[sel]), df1)
+    else:
+        p = S.f.sf(s[sel], df1, df2)
+    p = np.where(np.isnan(s[sel]), np.nan, p)
+    q = p_adjust_bh(p)
+    out = np.ones(s.shape)
+    out[sel] = q
+    th = np.full(len(FDR_LEVELS), np.nan)
+    for j, lev in enumerate(FDR_LEVELS):
+        acc = p[(q <= lev) & ~np.isnan(p)]
+        if acc.size:
+            th[j] = S.t.isf(acc.max() / 2.0, df1) if stat_type == "t" else S.f.isf(acc.max(), df1, df2)
+    return out, th, p

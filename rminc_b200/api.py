@@ -13,6 +13,7 @@ maintainer would add is in rminc_b200/R/ and INTEGRATION.md.
                                                              R/minc_vertex_statistics.R:301-344
     mincRandomize(x, R, alternative, replace, parallel, columns)   :1326-1378, :1441-1531
     thresholds(x, probs)                                     :1577-1581
+    mincFDR / vertexFDR / anatFDR                            R/minc_FDR.R:254-573
 
 Everything numerical goes through the C ABI (rminc_b200.core); there is no CPU path.
 MINC I/O (libminc) is outside the hot path: volumes are staged by a `reader` callable
@@ -445,6 +446,76 @@ def anatAnova(formula: str, data, anat, subset=None, device: int = 0) -> MincMat
     call = dict(fn="anatAnova", formula=formula, subset=subset, _term_labels=_term_labels(rhs))
     return _anova_result(out, X, names, assign, data, call, None, ("anatModel", "matrix"),
                          rownames=list(getattr(anat, "columns", [])) or None)
+
+
+# ----------------------------------------------------------------------------- mincFDR
+def mincFDR(buffer: MincMatrix, columns: Optional[Sequence[str]] = None, mask=None, df=None, method: str = "FDR",
+            statType=None, reader: Callable = default_reader, device: int = 0) -> MincMatrix:
+    """False discovery rate q-values of a mincLm / mincAnova / vertexLm / anatLm result
+    (mincFDR.mincMultiDim, R/minc_FDR.R:254-520).
+
+    The beta, R-squared and logLik columns are dropped (:267-292); every remaining t / F column is converted to
+    p-values (pt2 / pf) and Benjamini-Hochberg adjusted over the voxels with mask > 0.5 on the GPU.  Returns a
+    V x ncols matrix of class c("mincQvals","mincMultiDim","matrix") with colnames "qvalue-<column>", 1 outside the
+    mask, and attributes `thresholds` (5 x ncols, rows 0.01 .. 0.2), `likeVolume`, `DF`."""
+    if method not in ("FDR", "p.adjust"):
+        raise ValueError("only method = 'FDR' / 'p.adjust' (Benjamini-Hochberg) is on the GPU path")
+    if not isinstance(buffer, MincMatrix):
+        raise TypeError("buffer must be the result of mincLm / mincAnova / vertexLm / anatLm")
+    stattype = list(statType) if statType is not None else buffer.attrs.get("stat-type")
+    if stattype is None:
+        raise ValueError("Error: need to specify the type of statistic.")                       # :301
+    dfl = df if df is not None else buffer.attrs.get("df")
+    A = np.asarray(buffer)
+    names = list(buffer.colnames)
+    if len(stattype) == 1 and A.shape[1] != 1:
+        stattype = stattype * A.shape[1]
+    keep = [i for i, st in enumerate(stattype) if st not in ("beta", "R-squared", "logLik")]
+    stattype = [stattype[i] for i in keep]
+    names = [names[i] for i in keep]
+    A = A[:, keep]
+    if any(st not in ("t", "F") for st in stattype):
+        raise ValueError("Error: not all the stat types are recognized. Currently allowed are: t F")   # :318-323 (GPU: t, F)
+    if dfl is None:
+        raise ValueError("Error: need to specify the degrees of freedom")                       # :344
+    dfl = list(dfl)
+    if len(dfl) == 1 and A.shape[1] != 1:
+        dfl = dfl * A.shape[1]
+    if len(dfl) != A.shape[1]:
+        raise ValueError("Error: df needs to be of either length 1 or the same length as number of columns in the buffer")
+    if columns is None:
+        columns = names
+    m = None
+    if mask is not None:
+        m = _stage_mask(mask, A.shape[0], reader)
+    out = np.ones((A.shape[0], len(columns)), order="F")
+    thresholds = np.full((5, len(columns)), np.nan)
+    new_dfs = []
+    for i, cname in enumerate(columns):
+        c = names.index(cname)
+        d = dfl[c]
+        new_dfs.append(d)
+        if stattype[c] == "t":
+            d1 = float(d[0] if isinstance(d, (list, tuple, np.ndarray)) else d)
+            q, th = core.fdr(A[:, c], core.STAT_T, d1, 0.0, mask=m, device=device)
+        else:
+            q, th = core.fdr(A[:, c], core.STAT_F, float(d[0]), float(d[1]), mask=m, device=device)
+        out[:, i] = q
+        thresholds[:, i] = th
+    th = MincMatrix(thresholds, colnames=list(columns), rownames=[f"{x:g}" for x in core.FDR_LEVELS])
+    return MincMatrix(out, colnames=[f"qvalue-{c}" for c in columns], rownames=buffer.rownames,
+                      attrs={"thresholds": th, "likeVolume": buffer.attrs.get("likeVolume"), "DF": new_dfs},
+                      r_class=("mincQvals", "mincMultiDim", "matrix"))
+
+
+def vertexFDR(buffer: MincMatrix, **kw) -> MincMatrix:
+    """vertexFDR.vertexMultiDim -> mincFDR.mincMultiDim (R/minc_FDR.R:528-536)."""
+    return mincFDR(buffer, **kw)
+
+
+def anatFDR(buffer: MincMatrix, **kw) -> MincMatrix:
+    """anatFDR.anatModel -> vertexFDR.vertexMultiDim (R/minc_FDR.R:571-573)."""
+    return mincFDR(buffer, **kw)
 
 
 # ----------------------------------------------------------------------------- mincRandomize

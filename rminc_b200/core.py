@@ -238,6 +238,51 @@ def lm_fit_stored_torch(Ut, X, scale=None, offset=None, voxel_min=0.0, slice_len
     return out
 
 
+STAT_T, STAT_F = 1, 2                  # RMG_STAT_T / RMG_STAT_F
+FDR_LEVELS = (0.01, 0.05, 0.10, 0.15, 0.20)      # R/minc_FDR.R:370
+
+
+def pvalue(stat, stat_type, df1, df2=0.0) -> float:
+    """pt2(t, df1) or pf(F, df1, df2, lower.tail = FALSE) of one statistic (host; no GPU needed)."""
+    return _lib.load().rmg_pvalue(float(stat), int(stat_type), float(df1), float(df2))
+
+
+def fdr(stat, stat_type, df1, df2=0.0, mask=None, device=0):
+    """mincFDR's native step for one column: (q-values [V], thresholds [5]) -- Benjamini-Hochberg over the voxels
+    with mask > 0.5 (R/minc_FDR.R:254-520)."""
+    s = np.ascontiguousarray(stat, dtype=np.float64).reshape(-1)
+    V = s.shape[0]
+    m = None
+    if mask is not None:
+        m = np.ascontiguousarray(mask, dtype=np.float64).reshape(-1)
+        if m.shape[0] != V:
+            raise ValueError("mask length must equal the number of voxels")
+    q = np.empty(V)
+    th = np.empty(5)
+    err = _lib.errbuf()
+    rc = _lib.load().rmg_fdr(s.ctypes.data, V, int(stat_type), float(df1), float(df2), m.ctypes.data if m is not None else None,
+                             q.ctypes.data, th.ctypes.data, device, err, len(err))
+    _lib.check(rc, err)
+    return q, th
+
+
+def fdr_torch(stat_t, stat_type, df1, df2=0.0, mask=None, out=None):
+    """Device-resident form: stat_t a contiguous float64 CUDA vector -> (q CUDA vector, thresholds numpy[5])."""
+    import torch
+    if not (stat_t.is_cuda and stat_t.dtype == torch.float64 and stat_t.is_contiguous()):
+        raise ValueError("stat_t must be a contiguous float64 CUDA tensor")
+    V = stat_t.numel()
+    if out is None:
+        out = torch.empty(V, dtype=torch.float64, device=stat_t.device)
+    th = np.empty(5)
+    err = _lib.errbuf()
+    rc = _lib.load().rmg_fdr_device(stat_t.data_ptr(), V, int(stat_type), float(df1), float(df2),
+                                    mask.data_ptr() if mask is not None else None, out.data_ptr(), th.ctypes.data,
+                                    stat_t.device.index or 0, _torch_stream(stat_t), err, len(err))
+    _lib.check(rc, err)
+    return out, th
+
+
 def vertex_wlm(Y, X, weights, device=0):
     """anatLm(weights=)'s native step (vertex_wlm_loop, src/weighted_least_squares.c:168)."""
     Y, X, _ = _prep_host(Y, X, None)

@@ -41,6 +41,11 @@ def api(request, monkeypatch, oracle, lib):
             Y = oracle.expand_stored(U, scale, offset, voxel_min=voxel_min, slice_len=slice_len)
             return oracle.minc2_model_lm(Y, (1, 1, Y.shape[0]), X, mask=mask, lo=mask_lo, hi=mask_hi)
 
+        def fdr(stat, stat_type, df1, df2=0.0, mask=None, device=0):
+            q, th, _ = oracle.fdr(stat, "t" if stat_type == core.STAT_T else "F", df1, df2, mask=mask)
+            return q, th
+
+        monkeypatch.setattr(core, "fdr", fdr)
         monkeypatch.setattr(core, "lm_fit_stored", lm_fit_stored)
         monkeypatch.setattr(core, "lm_fit_cov", lm_fit_cov)
         monkeypatch.setattr(core, "vertex_wlm", vertex_wlm)
@@ -333,3 +338,39 @@ def test_mincLm_on_stored_volumes(api, study):
     check_row(v32, 3, Y32[3], X[:, :2], ["(Intercept)", "SexM"])
     with pytest.raises(TypeError):
         api.StoredVolume(np.zeros(4, dtype=np.int32))
+
+
+def test_mincFDR(api, study):
+    """mincFDR on a mincLm result (tests/testthat/test_mincFDR.R style): q-values of the F and t columns, 1 outside
+    the mask, thresholds attribute 5 x ncols."""
+    from scipy import stats as S
+    gf, maskfile, Y = study
+    vs = api.mincLm("jacobians ~ Sex", gf, mask=maskfile)
+    qv = api.mincFDR(vs, mask=maskfile)
+    assert qv.r_class == ("mincQvals", "mincMultiDim", "matrix")
+    assert qv.colnames == ["qvalue-F-statistic", "qvalue-tvalue-(Intercept)", "qvalue-tvalue-SexM"]
+    assert qv.attrs["thresholds"].shape == (5, 3) and qv.attrs["thresholds"].rownames == ["0.01", "0.05", "0.1", "0.15", "0.2"]
+    assert qv.attrs["DF"] == [[1, 8], 8, 8]
+    inside = np.load(maskfile).reshape(-1) > 0.5
+    assert (np.asarray(qv)[~inside] == 1).all()
+    # independent BH on the SexM column
+    t = vs.col("tvalue-SexM")[inside]
+    p = 2 * S.t.sf(np.abs(t), 8)
+    o = np.argsort(p)
+    bh = np.minimum.accumulate((p[o] * len(p) / np.arange(1, len(p) + 1))[::-1])[::-1]
+    want = np.empty_like(p)
+    want[o] = np.minimum(bh, 1)
+    assert np.asarray(qv)[inside, 2] == pytest.approx(want, rel=1e-9)
+    # for one numerator degree of freedom F = t^2, so both columns carry the same q-values
+    assert np.asarray(qv)[inside, 0] == pytest.approx(np.asarray(qv)[inside, 2], rel=1e-8)
+    th = np.asarray(qv.attrs["thresholds"])[:, 2]
+    acc = np.abs(t)[want <= 0.2]
+    if acc.size:
+        assert th[4] == pytest.approx(acc.min(), rel=1e-8)
+    else:
+        assert np.isnan(th[4])
+    sub = api.mincFDR(vs, columns=["tvalue-SexM"], mask=maskfile)
+    assert sub.shape == (1000, 1) and np.array_equal(np.asarray(sub)[:, 0], np.asarray(qv)[:, 2])
+    with pytest.raises(ValueError, match="need to specify the degrees of freedom"):
+        bad = api.MincMatrix(np.asarray(vs), colnames=vs.colnames, attrs={"stat-type": vs.attrs["stat-type"]})
+        api.mincFDR(bad)

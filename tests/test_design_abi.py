@@ -111,6 +111,24 @@ def test_no_cpu_fallback(lib):
         assert e.value.code == 4 and "no CPU fallback" in str(e.value)
 
 
+def test_pvalue_function_matches_textbook_and_scipy(lib):
+    """rmg_pvalue (the host build of the code the FDR kernel runs): pt2 / pf through the incomplete beta function."""
+    from scipy import stats as S
+    from rminc_b200 import core
+    assert core.pvalue(2.228139, core.STAT_T, 10) == pytest.approx(0.05, rel=2e-6)       # t_.975(10)
+    assert core.pvalue(4.964603, core.STAT_F, 1, 10) == pytest.approx(0.05, rel=2e-6)     # F_.95(1, 10)
+    assert core.pvalue(1.0, core.STAT_T, 1) == pytest.approx(0.5, rel=1e-14)              # Cauchy
+    for df in (1, 3, 8, 50, 496, 1993):
+        for t in (1e-3, 0.5, 1, 2, 5, 12, 40, 1e3):
+            assert core.pvalue(t, core.STAT_T, df) == pytest.approx(2 * S.t.sf(t, df), rel=1e-11)
+            assert core.pvalue(-t, core.STAT_T, df) == core.pvalue(t, core.STAT_T, df)
+    for d1, d2 in ((1, 8), (3, 496), (6, 1993), (10, 3)):
+        for f in (1e-6, 0.5, 2, 10, 100, 1e5):
+            assert core.pvalue(f, core.STAT_F, d1, d2) == pytest.approx(S.f.sf(f, d1, d2), rel=1e-11)
+    assert np.isnan(core.pvalue(float("nan"), core.STAT_T, 5)) and core.pvalue(float("inf"), core.STAT_T, 5) == 0.0
+    assert core.pvalue(0.0, core.STAT_F, 2, 9) == 1.0 and core.pvalue(-1.0, core.STAT_F, 2, 9) == 1.0
+
+
 def test_product_does_not_reference_the_oracle():
     """rminc_b200/ must never import, link or execute anything under oracle/."""
     pkg = os.path.join(ROOT, "rminc_b200")

@@ -551,3 +551,53 @@ def test_stored_tma_ring_variant(core, oracle, slice_len):
         assert_rows_match(got, oracle.vertex_lm_loop(F.astype(np.float64), X[:, :3]), RTOL, "tma f32")
         Fr = np.asfortranarray(F[:79999])                                     # ragged tail: TMA zero-fill, scalar stores
         assert_rows_match(core.lm_fit_stored(Fr, X), oracle.vertex_lm_loop(Fr.astype(np.float64), X), RTOL, "tma f32 ragged")
+
+
+# ------------------------------------------------------------------ mincFDR
+@pytest.mark.parametrize("stat_type,df1,df2", [("t", 496, 0), ("t", 8, 0), ("F", 3, 496), ("F", 1, 18)])
+def test_fdr_matches_oracle(core, oracle, stat_type, df1, df2):
+    """p-values (incomplete beta on the device), Benjamini-Hochberg q-values and thresholds against p.adjust's
+    algorithm with scipy's distributions; NaN statistics stay NaN and do not count; 1 outside the mask."""
+    rng = np.random.default_rng(df1)
+    V = 200_003
+    if stat_type == "t":
+        s = rng.standard_t(df1, V)
+        s[: V // 20] += rng.normal(5, 1, V // 20)
+    else:
+        s = rng.f(df1, df2, V)
+        s[: V // 20] *= 8
+    s[::97] = np.nan
+    s[5] = np.inf
+    s[6] = 0.0
+    mask = (rng.random(V) > 0.3).astype(float)
+    code = core.STAT_T if stat_type == "t" else core.STAT_F
+    for m in (None, mask):
+        q, th = core.fdr(s, code, df1, df2, mask=m)
+        wq, wth, wp = oracle.fdr(s, stat_type, df1, df2, mask=m)
+        assert np.array_equal(np.isnan(q), np.isnan(wq))
+        ok = ~np.isnan(wq)
+        assert q[ok] == pytest.approx(wq[ok], rel=1e-9, abs=1e-300)
+        if m is not None:
+            assert (q[m < 0.5] == 1).all()
+        assert np.array_equal(np.isnan(th), np.isnan(wth))
+        assert th[~np.isnan(wth)] == pytest.approx(wth[~np.isnan(wth)], rel=1e-8)
+
+
+def test_fdr_edge_cases_and_device_form(core, oracle):
+    import torch
+    # nothing significant: every threshold NA; everything masked: all ones
+    s = np.random.default_rng(1).standard_t(30, 5000)
+    q, th = core.fdr(s, core.STAT_T, 30)
+    wq, wth, _ = oracle.fdr(s, "t", 30)
+    assert q == pytest.approx(wq, rel=1e-9) and np.isnan(th).all() and np.isnan(wth).all()
+    q, th = core.fdr(s, core.STAT_T, 30, mask=np.zeros(5000))
+    assert (q == 1).all() and np.isnan(th).all()
+    q, th = core.fdr(np.zeros(0), core.STAT_T, 30)
+    assert q.shape == (0,)
+    with pytest.raises(core.RmincGpuError, match="degrees of freedom"):
+        core.fdr(s, core.STAT_F, 3, 0)
+    st = torch.from_numpy(np.r_[s, 9.0, -11.0]).cuda()
+    qd, thd = core.fdr_torch(st, core.STAT_T, 30)
+    wq, wth, _ = oracle.fdr(np.r_[s, 9.0, -11.0], "t", 30)
+    assert qd.cpu().numpy() == pytest.approx(wq, rel=1e-9)
+    assert thd[~np.isnan(wth)] == pytest.approx(wth[~np.isnan(wth)], rel=1e-8)

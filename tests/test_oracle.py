@@ -338,3 +338,30 @@ def test_stored_type_expansion(oracle):
     assert np.array_equal(got5, (U.astype(np.float64) - 5.0) * scale[sl, :] + offset[sl, :])
     F = rng.normal(size=(V, n)).astype(np.float32)
     assert np.array_equal(oracle.expand_stored(F), F.astype(np.float64))
+
+
+def test_fdr_restatement(oracle):
+    """p.adjust(p, "fdr") and mincFDR's p-values / thresholds (R/minc_FDR.R:385-505).  Known answers: the BH example
+    worked by hand, and textbook critical values of the t and F distributions."""
+    # BH by hand: p = (0.01, 0.04, 0.03, 0.005) -> sorted 0.005, 0.01, 0.03, 0.04 -> 4/1*.005, 4/2*.01, 4/3*.03, 4/4*.04
+    q = oracle.p_adjust_bh([0.01, 0.04, 0.03, 0.005])
+    assert q == pytest.approx([0.02, 0.04, 0.04, 0.02], rel=1e-14)
+    # NA p-values stay NA and do not count in n
+    q = oracle.p_adjust_bh([0.01, np.nan, 0.04, 0.03, 0.005, np.nan])
+    assert np.isnan(q[[1, 5]]).all() and q[[0, 2, 3, 4]] == pytest.approx([0.02, 0.04, 0.04, 0.02], rel=1e-14)
+    assert oracle.p_adjust_bh([0.9, 0.95]) == pytest.approx([0.95, 0.95])
+    # critical values: t_{.975}(10) = 2.228139, t_{.995}(10) = 3.169273, F_{.95}(1,10) = 4.964603, F_{.95}(3,20) = 3.098391
+    _, _, p = oracle.fdr([2.228139, -3.169273], "t", 10)
+    assert p == pytest.approx([0.05, 0.01], rel=2e-6)
+    _, _, p = oracle.fdr([4.964603], "F", 1, 10)
+    assert p == pytest.approx([0.05], rel=2e-6)
+    _, _, p = oracle.fdr([3.098391], "F", 3, 20)
+    assert p == pytest.approx([0.05], rel=2e-6)
+    # thresholds: the statistic of the largest accepted p-value; outside the mask q = 1
+    rng = np.random.default_rng(3)
+    t = np.r_[rng.standard_t(20, 900), rng.normal(6, 1, 100)]
+    mask = (np.arange(1000) % 10 != 0).astype(float)
+    q, th, p = oracle.fdr(t, "t", 20, mask=mask)
+    assert (q[mask < 0.5] == 1).all() and np.all(np.diff(th[~np.isnan(th)]) <= 0)
+    acc = np.abs(t[mask > 0.5])[q[mask > 0.5] <= 0.05]
+    assert th[1] == pytest.approx(acc.min(), rel=1e-9)       # the weakest accepted |t| is the threshold
