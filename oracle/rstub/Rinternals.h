@@ -14,6 +14,7 @@ typedef unsigned int SEXPTYPE;
 #define STRSXP 16
 #define CHARSXP 9
 #define RAWSXP 24
+#define VECSXP 19
 typedef ptrdiff_t R_xlen_t;
 extern SEXP R_NilValue;
 SEXP Rf_allocVector(SEXPTYPE type, R_xlen_t n);
@@ -42,6 +43,7 @@ SEXP Rf_GetOption1(SEXP tag);
 R_xlen_t XLENGTH(SEXP s);
 int TYPEOF(SEXP s);               /* declaration only: used by rminc_b200/csrc/rshim.c's syntax check */
 unsigned char *RAW(SEXP s);
+SEXP SET_VECTOR_ELT(SEXP x, R_xlen_t i, SEXP v);
 char *R_alloc(size_t n, int size);
 #ifndef FALSE
 #define FALSE 0

@@ -97,3 +97,12 @@ per_voxel_anova_gpu <- function(filenames, mmatrix, mask = NULL, mask_min = 1, m
 vertex_anova_loop_gpu <- function(data.matrix, mmatrix)
   .Call("rmincgpu_anova", data.matrix, mmatrix, as.integer(attr(mmatrix, "assign")), NULL, 1, 99999999,
         PACKAGE = "rmincgpu")
+
+
+# mincFDR's inner loop body on the GPU (R/minc_FDR.R:385-505): p-values, p.adjust(., "fdr") and the thresholds of one
+# column.  stat_type "t" / "F"; df as in attr(buffer, "df")[[column]]; mask a numeric vector or NULL.
+rmincgpu_fdr_column <- function(stat, stat_type, df, mask = NULL) {
+  res <- .Call("rmincgpu_fdr", as.double(stat), if (stat_type == "F") 2L else 1L, as.double(df),
+               if (is.null(mask)) NULL else as.double(mask), PACKAGE = "rmincgpu")
+  list(qvalue = res[[1]], thresholds = res[[2]])
+}

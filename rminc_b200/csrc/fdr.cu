@@ -252,6 +252,12 @@ int fdr_device_impl(const double *dstat, int64_t V, int stat_type, double df1, d
     FdrWorkspace ws;
     ws.st = st;
     if (V > 0xfffffff0LL) return fail(err, errlen, RMG_ERR_INVALID, "FDR supports at most 2^32 voxels per call");
+    if (V == 0) {
+        if (thresholds)
+            for (int l = 0; l < kLevels; ++l) thresholds[l] = std::nan("");
+        return RMG_OK;
+    }
+    cudaGetLastError();   // CUB reports any stale (non-sticky) runtime error as its own: start clean
     const int nblocks = (int)((V + kBlock - 1) / kBlock);
     unsigned int m = 0;
     double pmax_h[kLevels];

@@ -14,6 +14,7 @@
  *   rmincgpu_lm_cov          the same with filenames_right (a voxel-wise covariate) staged as a second matrix
  *   rmincgpu_lm_stored       the same on volumes in their stored type (uint16 + real ranges, float32)
  *   rmincgpu_randomize       the mincRandomize loop (R/minc_voxel_statistics.R:1465-1497)
+ *   rmincgpu_fdr             mincFDR's p-value + p.adjust(., "fdr") + threshold step for one column (R/minc_FDR.R:385-505)
  *   rmincgpu_anova           per_voxel_anova / vertex_anova_loop (src/minc_anova.c:142, src/vertex_modelling.c:178)
  */
 #include <R.h>
@@ -202,6 +203,29 @@ SEXP rmincgpu_anova(SEXP Y, SEXP mmatrix, SEXP asgn, SEXP mask, SEXP mask_lower,
     return out;
 }
 
+/* mincFDR's inner step for one column (R/minc_FDR.R:385-505): list(qvalue = <V doubles>, thresholds = <5 doubles>).
+ * stat_type: 1 = t (two-sided, pt2), 2 = F (upper tail); df = c(df1) or c(df1, df2); mask NULL or V doubles (> 0.5). */
+SEXP rmincgpu_fdr(SEXP stat, SEXP stat_type, SEXP df, SEXP mask)
+{
+    if (!Rf_isReal(stat) || !Rf_isReal(df)) Rf_error("stat and df must be double vectors");
+    const R_xlen_t V = XLENGTH(stat);
+    const double *m = mask_or_null(mask, V);
+    SEXP q = PROTECT(Rf_allocVector(REALSXP, V));
+    SEXP th = PROTECT(Rf_allocVector(REALSXP, 5));
+    char err[512] = "";
+    int rc = rmg_fdr(REAL(stat), V, Rf_asInteger(stat_type), REAL(df)[0], LENGTH(df) > 1 ? REAL(df)[1] : 0.0, m, REAL(q),
+                     REAL(th), 0, err, sizeof err);
+    if (rc != RMG_OK) {
+        UNPROTECT(2);
+        check(rc, err);
+    }
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, q);
+    SET_VECTOR_ELT(out, 1, th);
+    UNPROTECT(3);
+    return out;
+}
+
 static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_vertex_lm_loop", (DL_FUNC)&rmincgpu_vertex_lm_loop, 3},
     {"rmincgpu_vertex_wlm_loop", (DL_FUNC)&rmincgpu_vertex_wlm_loop, 4},
@@ -210,6 +234,7 @@ static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_lm_stored", (DL_FUNC)&rmincgpu_lm_stored, 11},
     {"rmincgpu_randomize", (DL_FUNC)&rmincgpu_randomize, 9},
     {"rmincgpu_anova", (DL_FUNC)&rmincgpu_anova, 6},
+    {"rmincgpu_fdr", (DL_FUNC)&rmincgpu_fdr, 4},
     {NULL, NULL, 0}};
 
 void R_init_rmincgpu(DllInfo *dll)
