@@ -243,6 +243,13 @@ int rmg_randomize_device(const double *dY, int64_t V, int64_t ldY, int n, const 
 int rmg_lm_fit_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p,
                      const double *mask, double mask_lo, double mask_hi,
                      double *out, int64_t ldOut, int n_gpus, char *err, size_t errlen);
+int rmg_lm_fit_cov_multi(const double *Y, const double *Z, int64_t V, int64_t ldY, int n, const double *Xs, int ps,
+                         const double *mask, double mask_lo, double mask_hi,
+                         double *out, int64_t ldOut, int n_gpus, char *err, size_t errlen);
+int rmg_lm_fit_stored_multi(const void *U, int dtype, int64_t V, int64_t ldU, int n,
+                            const double *scale, const double *offset, double voxel_min, int64_t slice_len,
+                            const double *X, int p, const double *mask, double mask_lo, double mask_hi,
+                            double *out, int64_t ldOut, int n_gpus, char *err, size_t errlen);
 int rmg_randomize_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p,
                         const double *mask, double mask_lo, double mask_hi,
                         const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,

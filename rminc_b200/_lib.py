@@ -46,6 +46,9 @@ SIGNATURES = {
     "rmg_fdr_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int, C.c_void_p] + _ERR),
     "rmg_pvalue": (C.c_double, [C.c_double, C.c_int, C.c_double, C.c_double]),
+    "rmg_lm_fit_cov_multi": (C.c_int, [C.c_void_p] + _FIT_HEAD + _MASK + [C.c_void_p, C.c_int64, C.c_int] + _ERR),
+    "rmg_lm_fit_stored_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
+                                          C.c_int64, C.c_void_p, C.c_int] + _MASK + [C.c_void_p, C.c_int64, C.c_int] + _ERR),
     "rmg_anova_fit": (C.c_int, _FIT_HEAD + [C.c_void_p] + _MASK + [C.c_void_p, C.c_int64, C.c_int] + _ERR),
     "rmg_anova_fit_device": (C.c_int, _FIT_HEAD + [C.c_void_p] + _MASK + [C.c_void_p, C.c_int64, C.c_int, C.c_void_p] + _ERR),
     "rmg_randomize": (C.c_int, _FIT_HEAD + _MASK + _PERM + [C.c_void_p, C.c_int] + _ERR),

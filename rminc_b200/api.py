@@ -273,7 +273,7 @@ def mincLm(formula: str, data, subset=None, mask=None, maskval=None, parallel=No
         X, names, _ = model_matrix(rhs, data, rows)
         m = _stage_mask(mask, U.shape[0], reader)
         out = core.lm_fit_stored(U, X, scale, offset, voxel_min=vmin, slice_len=slice_len, mask=m, mask_lo=lo, mask_hi=hi,
-                                 device=device)
+                                 device=device, n_gpus=int(parallel[1]) if parallel is not None else None)
         n, p = X.shape
         attrs = {
             "likeVolume": filenames[0], "filenames": list(filenames), "model": X, "data": data,
@@ -291,7 +291,8 @@ def mincLm(formula: str, data, subset=None, mask=None, maskval=None, parallel=No
         Z = mincTable(plm["right"], reader=reader)
         if Z.shape != Y.shape:
             raise ValueError("the right-hand-side volumes must match the left-hand-side volumes")
-        out = core.lm_fit_cov(Y, Z, plm["mmatrix"], mask=m, mask_lo=lo, mask_hi=hi, device=device)
+        out = core.lm_fit_cov(Y, Z, plm["mmatrix"], mask=m, mask_lo=lo, mask_hi=hi, device=device,
+                              n_gpus=int(parallel[1]) if parallel is not None else None)
         model, dflist = _cov_attrs(n, plm)
         p = len(plm["rows"])
         attrs = {

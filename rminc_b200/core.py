@@ -104,7 +104,7 @@ def vertex_lm(Y, X, device=0):
     return out
 
 
-def lm_fit_cov(Y, Z, Xs=None, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, device=0):
+def lm_fit_cov(Y, Z, Xs=None, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, device=0, n_gpus=None):
     """Voxel-wise covariate design [Xs | z_v] ([1 | z_v] when Xs is None): a file term on the right-hand side
     (src/vertex_modelling.c:112-140, src/modelling_functions.c:1118-1144).  V x (2p+3), p = ncol(Xs) + 1."""
     Y = np.asarray(Y)
@@ -131,9 +131,10 @@ def lm_fit_cov(Y, Z, Xs=None, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAUL
     out = np.empty((V, 2 * p + 3), order="F")
     err = _lib.errbuf()
     ld = max(V, 1)
-    rc = _lib.load().rmg_lm_fit_cov(Y.ctypes.data, Z.ctypes.data, V, ld, n, Xs_.ctypes.data if ps else None, ps,
-                                    m.ctypes.data if m is not None else None, mask_lo, mask_hi, out.ctypes.data, ld,
-                                    device, err, len(err))
+    lib = _lib.load()
+    fn, where = (lib.rmg_lm_fit_cov, device) if n_gpus is None else (lib.rmg_lm_fit_cov_multi, int(n_gpus))
+    rc = fn(Y.ctypes.data, Z.ctypes.data, V, ld, n, Xs_.ctypes.data if ps else None, ps,
+            m.ctypes.data if m is not None else None, mask_lo, mask_hi, out.ctypes.data, ld, where, err, len(err))
     _lib.check(rc, err)
     return out
 
@@ -180,7 +181,7 @@ def _stored_tables(U_dtype, V, n, scale, offset, slice_len):
 
 
 def lm_fit_stored(U, X, scale=None, offset=None, voxel_min=0.0, slice_len=None, mask=None,
-                  mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, device=0):
+                  mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, device=0, n_gpus=None):
     """mincLm's native step on volumes in their stored type: U is V x n uint16 (with [nslices x n] scale / offset
     tables from the files' real ranges) or float32.  The doubles ((u - voxel_min) * scale + offset) are formed on
     the device; the result equals lm_fit on the expanded matrix."""
@@ -201,10 +202,12 @@ def lm_fit_stored(U, X, scale=None, offset=None, voxel_min=0.0, slice_len=None, 
     out = np.empty((V, 2 * p + 3), order="F")
     err = _lib.errbuf()
     ld = max(V, 1)
-    rc = _lib.load().rmg_lm_fit_stored(U.ctypes.data, dtype, V, ld, n, sc.ctypes.data if sc is not None else None,
-                                       of.ctypes.data if of is not None else None, float(voxel_min), slice_len,
-                                       X.ctypes.data, p, m.ctypes.data if m is not None else None, mask_lo, mask_hi,
-                                       out.ctypes.data, ld, device, err, len(err))
+    lib = _lib.load()
+    fn, where = (lib.rmg_lm_fit_stored, device) if n_gpus is None else (lib.rmg_lm_fit_stored_multi, int(n_gpus))
+    rc = fn(U.ctypes.data, dtype, V, ld, n, sc.ctypes.data if sc is not None else None,
+            of.ctypes.data if of is not None else None, float(voxel_min), slice_len,
+            X.ctypes.data, p, m.ctypes.data if m is not None else None, mask_lo, mask_hi,
+            out.ctypes.data, ld, where, err, len(err))
     _lib.check(rc, err)
     return out
 

@@ -415,6 +415,8 @@ struct StoredSpec {
     const double *scale, *offset;   // host, [nslices x n], slice fastest (u16 only)
     double voxel_min;
     int64_t slice_len;
+    int64_t v_offset = 0;        // global index of this call's first voxel (a shard of a larger volume)
+    int64_t nslices_total = 0;   // rows of scale / offset (0: derive from this call's V)
 };
 
 static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *asgn,
@@ -452,7 +454,7 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
     const int NB = (int)std::min<int64_t>(3, nchunks);
     const int64_t ldc = (CV + 7) & ~int64_t(7);  // rows stay 16-byte aligned for every sample type
     const int64_t slice_len = pk ? std::max<int64_t>(1, pk->slice_len) : 1;
-    const int64_t nslices = pk ? (V + slice_len - 1) / slice_len : 0;
+    const int64_t nslices = !pk ? 0 : pk->nslices_total > 0 ? pk->nslices_total : (V + slice_len - 1) / slice_len;
     double *dScale = nullptr, *dOffset = nullptr;
 
     cudaStream_t st[3] = {nullptr, nullptr, nullptr};
@@ -536,7 +538,7 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
                 RMG_CUDA(launch_lm_cov(ca, plan, st[b], &info));
             } else if (pk) {
                 PackedArgs pa{dY[b], pk->dtype, cv, ldc, n, p, cd->qt, cd->dd, mask ? dM[b] : nullptr, mask_lo, mask_hi, dO[b], ldc,
-                              dScale, dOffset, 4503599627370496.0 + pk->voxel_min, slice_len, nslices, v0};
+                              dScale, dOffset, 4503599627370496.0 + pk->voxel_min, slice_len, nslices, pk->v_offset + v0};
                 RMG_CUDA(launch_lm_packed(pa, plan, scr[b], st[b], &info));
             } else {
                 RMG_CUDA(launch_lm_fit(a, plan, scr[b], st[b], &info));
@@ -726,17 +728,18 @@ cleanup:
     return rc;
 }
 
-int rmg_lm_fit_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
-                     double mask_lo, double mask_hi, double *out, int64_t ldOut, int n_gpus, char *err,
-                     size_t errlen)
+}  // extern "C"
+
+// Contiguous voxel shards over devices 0..G-1, one host thread per GPU (R is one process and must never fork a CUDA
+// context).  fn(g, v0, cv, err, errlen) fits voxels [v0, v0 + cv) on device g.
+template <class Fn>
+static int run_sharded(int64_t V, int n_gpus, char *err, size_t errlen, Fn fn)
 {
-    int rc = check_fit_args(Y, V, ldY, n, X, p, out, ldOut, err, errlen);
-    if (rc) return rc;
     const int have = rmg_device_count();
     if (have <= 0) return fail(err, errlen, RMG_ERR_NO_DEVICE, "no CUDA device available; rminc_b200 has no CPU fallback");
-    int G = n_gpus <= 0 ? have : n_gpus;
+    const int G = n_gpus <= 0 ? have : n_gpus;
     if (G > have) return fail(err, errlen, RMG_ERR_NO_DEVICE, "%d GPUs requested, %d visible", G, have);
-    // contiguous voxel shards, even boundaries (keeps every shard 16-byte aligned)
+    // even boundaries keep every shard 16-byte aligned
     std::vector<int64_t> b(G + 1);
     for (int g = 0; g <= G; ++g) b[g] = std::min<int64_t>(V, ((V * g / G) + 1) & ~int64_t(1));
     b[0] = 0;
@@ -749,8 +752,7 @@ int rmg_lm_fit_multi(const double *Y, int64_t V, int64_t ldY, int n, const doubl
         th.emplace_back([&, g]() {
             const int64_t v0 = b[g], cv = b[g + 1] - b[g];
             if (cv <= 0) return;
-            rcs[g] = rmg_lm_fit(Y + v0, cv, ldY, n, X, p, mask ? mask + v0 : nullptr, mask_lo, mask_hi, out + v0,
-                                ldOut, g, &msgs[g][0], msgs[g].size());
+            rcs[g] = fn(g, v0, cv, &msgs[g][0], msgs[g].size());
             kms[g] = rmg_last_kernel_ms();
         });
     }
@@ -759,6 +761,51 @@ int rmg_lm_fit_multi(const double *Y, int64_t V, int64_t ldY, int n, const doubl
     for (int g = 0; g < G; ++g)
         if (rcs[g] != RMG_OK) return fail(err, errlen, rcs[g], "gpu %d: %s", g, msgs[g].c_str());
     return RMG_OK;
+}
+
+extern "C" {
+
+int rmg_lm_fit_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
+                     double mask_lo, double mask_hi, double *out, int64_t ldOut, int n_gpus, char *err,
+                     size_t errlen)
+{
+    int rc = check_fit_args(Y, V, ldY, n, X, p, out, ldOut, err, errlen);
+    if (rc) return rc;
+    return run_sharded(V, n_gpus, err, errlen, [&](int g, int64_t v0, int64_t cv, char *e, size_t el) {
+        return rmg_lm_fit(Y + v0, cv, ldY, n, X, p, mask ? mask + v0 : nullptr, mask_lo, mask_hi, out + v0, ldOut, g, e, el);
+    });
+}
+
+int rmg_lm_fit_cov_multi(const double *Y, const double *Z, int64_t V, int64_t ldY, int n, const double *Xs, int ps,
+                         const double *mask, double mask_lo, double mask_hi, double *out, int64_t ldOut, int n_gpus,
+                         char *err, size_t errlen)
+{
+    if (V > 0 && (!Y || !Z || !out)) return fail(err, errlen, RMG_ERR_INVALID, "Y, Z or out is NULL");
+    if (ldY < V || ldOut < V) return fail(err, errlen, RMG_ERR_INVALID, "leading dimension smaller than V");
+    return run_sharded(V, n_gpus, err, errlen, [&](int g, int64_t v0, int64_t cv, char *e, size_t el) {
+        return rmg_lm_fit_cov(Y + v0, Z + v0, cv, ldY, n, Xs, ps, mask ? mask + v0 : nullptr, mask_lo, mask_hi, out + v0,
+                              ldOut, g, e, el);
+    });
+}
+
+int rmg_lm_fit_stored_multi(const void *U, int dtype, int64_t V, int64_t ldU, int n, const double *scale,
+                            const double *offset, double voxel_min, int64_t slice_len, const double *X, int p,
+                            const double *mask, double mask_lo, double mask_hi, double *out, int64_t ldOut, int n_gpus,
+                            char *err, size_t errlen)
+{
+    int rc = check_stored_args(dtype, scale, offset, voxel_min, slice_len, p, err, errlen);
+    if (rc) return rc;
+    if ((rc = check_fit_args(U, V, ldU, n, X, p, out, ldOut, err, errlen))) return rc;
+    const size_t es = dtype == RMG_STORED_U16 ? 2 : 4;
+    const int64_t sl = dtype == RMG_STORED_U16 ? slice_len : std::max<int64_t>(V, 1);
+    const int64_t nslices_total = (V + sl - 1) / sl;
+    return run_sharded(V, n_gpus, err, errlen, [&](int g, int64_t v0, int64_t cv, char *e, size_t el) {
+        StoredSpec pk{dtype, scale, offset, voxel_min, sl};
+        pk.v_offset = v0;                    // slices keep their global index
+        pk.nslices_total = nslices_total;
+        return fit_host_impl(reinterpret_cast<const double *>(static_cast<const char *>(U) + (size_t)v0 * es), cv, ldU, n, X, p,
+                             nullptr, mask ? mask + v0 : nullptr, mask_lo, mask_hi, out + v0, ldOut, g, e, el, nullptr, nullptr, &pk);
+    });
 }
 
 }  // extern "C"

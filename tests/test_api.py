@@ -33,11 +33,11 @@ def api(request, monkeypatch, oracle, lib):
         def vertex_wlm(Y, X, weights, device=0):
             return oracle.vertex_wlm_loop(Y, X, weights)
 
-        def lm_fit_cov(Y, Z, Xs=None, mask=None, mask_lo=1.0, mask_hi=99999999.0, device=0):
+        def lm_fit_cov(Y, Z, Xs=None, mask=None, mask_lo=1.0, mask_hi=99999999.0, device=0, n_gpus=None):
             return oracle.lm_loop_cov(Y, Z, Xs, mask=mask, lo=mask_lo, hi=mask_hi)
 
         def lm_fit_stored(U, X, scale=None, offset=None, voxel_min=0.0, slice_len=None, mask=None, mask_lo=1.0,
-                          mask_hi=99999999.0, device=0):
+                          mask_hi=99999999.0, device=0, n_gpus=None):
             Y = oracle.expand_stored(U, scale, offset, voxel_min=voxel_min, slice_len=slice_len)
             return oracle.minc2_model_lm(Y, (1, 1, Y.shape[0]), X, mask=mask, lo=mask_lo, hi=mask_hi)
 

@@ -601,3 +601,18 @@ def test_fdr_edge_cases_and_device_form(core, oracle):
     wq, wth, _ = oracle.fdr(np.r_[s, 9.0, -11.0], "t", 30)
     assert qd.cpu().numpy() == pytest.approx(wq, rel=1e-9)
     assert thd[~np.isnan(wth)] == pytest.approx(wth[~np.isnan(wth)], rel=1e-8)
+
+
+def test_sharded_forms_of_the_next_row_paths(core, oracle):
+    """rmg_lm_fit_cov_multi / rmg_lm_fit_stored_multi: contiguous voxel shards over the visible GPUs (1 or more),
+    slices keep their global index across shards."""
+    G = min(2, core.device_count())
+    Y, Z, Xs = _cov_case(3001, 40, 3, seed=31)
+    mask = (np.arange(3001) % 3 != 0).astype(float)
+    assert_rows_match(core.lm_fit_cov(Y, Z, Xs, mask=mask, n_gpus=G), oracle.lm_loop_cov(Y, Z, Xs, mask=mask), RTOL, "cov multi")
+    U, X, scale, offset = _stored_case(6002, 36, 700, seed=32)
+    Yx = oracle.expand_stored(U, scale, offset, voxel_min=1.0, slice_len=700)
+    assert_rows_match(core.lm_fit_stored(U, X, scale, offset, voxel_min=1.0, slice_len=700, n_gpus=G),
+                      oracle.vertex_lm_loop(Yx, X), RTOL, "stored multi")
+    with pytest.raises(core.RmincGpuError, match="GPUs requested"):
+        core.lm_fit_stored(U, X, scale, offset, slice_len=700, n_gpus=core.device_count() + 1)
