@@ -160,3 +160,84 @@ def test_config4_randomize_full_size(torch_mod, oracle, monkeypatch):
     monkeypatch.setenv("RMG_PERM_PATH", "gemm")
     got = core.randomize_torch(Yt[:, sl], X, idx[:, :4], cols, two_sided=True, mask=mt[sl].contiguous()).cpu().numpy().T
     np.testing.assert_allclose(got, want, rtol=RTOL)
+
+
+def test_config2_full_size_stored_and_covariate(torch_mod, oracle):
+    """Config 2 through the next-row kernels at full size: uint16 voxels with per-slice real ranges (TMA ring) and a
+    voxel-wise covariate.  Checked against the oracle on a voxel sample, and over ALL voxels through properties: the
+    stored-type fit equals the double fit of the expanded samples; a covariate that does not enter y leaves the
+    static coefficients' estimates those of a model that projects it out (Frisch-Waugh: beta_z of y := y + c z moves
+    by exactly c)."""
+    torch, core, free = torch_mod
+    dims, n = (180, 252, 156), 500
+    V = int(np.prod(dims))
+    if free < 2.4 * V * n * 8:
+        pytest.skip("not enough free HBM")
+    X = design_cfg2(n)
+    p = X.shape[1]
+    nsl, slice_len = dims[0], dims[1] * dims[2]
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    Ut = torch.empty((n, V), dtype=torch.uint16, device="cuda")
+    for j0 in range(0, n, 25):
+        blk = torch.empty((25, V), dtype=torch.float32, device="cuda").normal_(30000.0, 400.0, generator=g)
+        Ut[j0:j0 + 25] = blk.round_().clamp_(0, 32767).to(torch.int16).view(torch.uint16)
+    del blk
+    rs = np.random.default_rng(5)
+    smin = rs.normal(-0.8, 0.05, (n, nsl))
+    smax = smin + rs.uniform(1.5, 2.5, (n, nsl))
+    sc_h, of_h = np.ascontiguousarray((smax - smin) / 65535.0), np.ascontiguousarray(smin)
+    sc_t, of_t = torch.from_numpy(sc_h).cuda(), torch.from_numpy(of_h).cuda()
+    out = core.lm_fit_stored_torch(Ut, X, sc_t, of_t, slice_len=slice_len)
+    torch.cuda.synchronize()
+    assert core.last_fit_variant() == "lm_fit_packed_tma_kernel"
+    # (a) oracle on a sample of voxels (expanded by the oracle's own restatement of the conversion)
+    rng = np.random.default_rng(0)
+    sel = np.sort(rng.choice(V, size=1200, replace=False))
+    sel[0], sel[-1] = 0, V - 1
+    sel[1:40] = np.arange(slice_len - 20, slice_len + 19)                 # across the first slice boundary
+    sel = np.unique(sel)
+    st = torch.from_numpy(sel).cuda()
+    Us = Ut.view(torch.int16)[:, st].cpu().numpy().view(np.uint16).T      # k x n
+    sl = sel // slice_len
+    Ys = (Us.astype(np.float64) - 0.0) * sc_h.T[sl, :] + of_h.T[sl, :]
+    assert_rows_match(out[:, st].cpu().numpy().T, oracle.vertex_lm_loop(Ys, X), RTOL, "stored sample")
+    # (b) ALL voxels: equal to the double kernel on the expanded samples, slab by slab (a slab = 12 slices)
+    for s0 in range(0, nsl, 12):
+        v0, v1 = s0 * slice_len, min(V, (s0 + 12) * slice_len)
+        scv = sc_t[:, s0:s0 + 12].repeat_interleave(slice_len, dim=1)[:, :v1 - v0]
+        ofv = of_t[:, s0:s0 + 12].repeat_interleave(slice_len, dim=1)[:, :v1 - v0]
+        Ye = Ut.view(torch.int16)[:, v0:v1].to(torch.float64) * scv + ofv
+        ref = core.lm_fit_torch(Ye, X)
+        torch.cuda.synchronize()
+        scale = torch.maximum(ref.abs(), ref.square().mean(dim=1, keepdim=True).sqrt())
+        assert bool(((out[:, v0:v1] - ref).abs() <= 1e-9 * scale).all()), f"slab {s0}"
+        del Ye, ref, scv, ofv, scale
+    del Ut, out
+    # ---- covariate: [X[:, :3] | z_v]
+    Yt = gen(torch, V, n, seed=1, mean=30000.0, sd=50.0)
+    Zt = gen(torch, V, n, seed=2, mean=100.0, sd=3.0)
+    Xs = X[:, :3]
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    oc = core.lm_fit_cov_torch(Yt, Zt, Xs, status=status)
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    sel = np.sort(rng.choice(V, size=800, replace=False))
+    sel[0], sel[-1] = 0, V - 1
+    st = torch.from_numpy(sel).cuda()
+    want = oracle.lm_loop_cov(Yt[:, st].cpu().numpy().T, Zt[:, st].cpu().numpy().T, Xs)
+    assert_rows_match(oc[:, st].cpu().numpy().T, want, RTOL, "covariate sample")
+    # ALL voxels: y + c z has the covariate's beta shifted by exactly c, the static betas and rss-derived columns unchanged
+    c = 7.25
+    Yt.add_(Zt, alpha=c)
+    o2 = core.lm_fit_cov_torch(Yt, Zt, Xs)
+    torch.cuda.synchronize()
+
+    def close(u, v, tol=1e-7):
+        scale = torch.maximum(v.abs(), v.square().mean().sqrt())
+        return bool(((u - v).abs() <= tol * scale).all())
+
+    assert close(o2[2 + 3], oc[2 + 3] + c)
+    for i in range(3):
+        assert close(o2[2 + i], oc[2 + i], 1e-6), i                       # static betas (intercept ~3e4: looser scale)
+    assert close(o2[2 * p + 2], oc[2 * p + 2], 1e-9)                      # logLik: same residuals
