@@ -10,6 +10,10 @@ liboracle.so    : oracle/rminc_oracle.c, the plain-C restatement of
 _ref/librminc_ref.so : the reference's own voxel_lm / vertex_lm_loop /
                   minc2_model object code (built by `make ref` where
                   /root/reference exists; see oracle/Makefile).
+
+Parity unpinned (third-party code absent from the image, restated from published algorithms):
+expand_stored (libminc's stored-voxel -> real conversion) and fdr / p_adjust_bh (R's nmath pt / pf,
+stats::p.adjust); see the header of rminc_oracle.c and DESIGN.md section 3.
 """
 from __future__ import annotations
 

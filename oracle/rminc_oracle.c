@@ -25,6 +25,15 @@
  *   LAPACK 3.x dpotri = dtrtri (dtrti2) + dlauum (dlauu2), unblocked because
  *   p <= 64.  Call sites: src/modelling_functions.c:494-495, :549.
  *
+ * Next-row restatements in this file and their pins:
+ *   orc_anova_loop / orc_vertex_wlm_loop / orc_lm_loop_cov: bit for bit against the reference's object code
+ *       (vertex_anova_loop, per_voxel_anova, vertex_wlm_loop, vertex_lm_loop with data_right) and golden vectors.
+ *   orc_expand_u16 / orc_expand_f32 (stored voxels -> doubles): libminc (BIC-MNI/libminc @ b01ba22,
+ *       inst/tools/ch_minc_depends.m4:85) is a third-party dependency absent from the image; its published
+ *       real-range conversion is restated -- PARITY UNPINNED against libminc's object code.
+ *   mincFDR (oracle.py: p_adjust_bh, fdr): R's p.adjust restated from its published source; pt / pf come from
+ *       scipy -- PARITY UNPINNED against R's nmath beyond textbook critical values.
+ *
  * All matrices are column-major, as in R.
  */
 #include <math.h>
