@@ -282,7 +282,13 @@ def mincLm(formula: str, data, subset=None, mask=None, maskval=None, parallel=No
         }
         return MincMatrix(out, colnames=_colnames(names), attrs=attrs, r_class=("mincLm", "mincMultiDim", "matrix"))
     if isinstance(first, StoredVolume):
-        reader = (lambda rd: lambda item: (lambda v: v.real() if isinstance(v, StoredVolume) else v)(rd(item)))(reader)
+        # stored volumes combined with a voxel-wise covariate: expand on the host like the CPU reader would
+        stored_reader = reader
+
+        def reader(item):
+            v = stored_reader(item)
+            return v.real() if isinstance(v, StoredVolume) else v
+
     Y = mincTable(filenames, reader=reader)
     V, n = Y.shape
     m = _stage_mask(mask, V, reader)

@@ -467,9 +467,13 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
     int64_t launches = 0;
     PinnedRing ring;
     // (small transfers are not worth four cudaHostAlloc calls)
-    const bool staged = !is_pinned_host(Y) && (double)V * n * (double)es >= 256.0 * 1024 * 1024 && !std::getenv("RMG_NO_STAGING");
+    // RMG_STAGING_ROWS=k forces the staging ring with k subjects per slot at any size (tests)
+    const int forced_rows = std::getenv("RMG_STAGING_ROWS") ? std::atoi(std::getenv("RMG_STAGING_ROWS")) : 0;
+    const bool staged = !is_pinned_host(Y) && !std::getenv("RMG_NO_STAGING") &&
+                        (forced_rows > 0 || (double)V * n * (double)es >= 256.0 * 1024 * 1024);
     // rows (subjects) per staging slot: ~128 MiB
-    const int rows_per_slot = (int)std::max<int64_t>(1, std::min<int64_t>(n, (128ll << 20) / ((int64_t)es * std::max<int64_t>(CV, 1))));
+    const int rows_per_slot = forced_rows > 0 ? std::min(forced_rows, n)
+        : (int)std::max<int64_t>(1, std::min<int64_t>(n, (128ll << 20) / ((int64_t)es * std::max<int64_t>(CV, 1))));
     {
         if (staged) RMG_CUDA(ring.init((size_t)rows_per_slot * (size_t)std::min(CV, V) * es));
         if (pk && pk->dtype == kStoredU16) {

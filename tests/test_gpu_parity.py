@@ -616,3 +616,20 @@ def test_sharded_forms_of_the_next_row_paths(core, oracle):
                       oracle.vertex_lm_loop(Yx, X), RTOL, "stored multi")
     with pytest.raises(core.RmincGpuError, match="GPUs requested"):
         core.lm_fit_stored(U, X, scale, offset, slice_len=700, n_gpus=core.device_count() + 1)
+
+
+def test_pageable_input_through_the_pinned_staging_ring(core, oracle, monkeypatch):
+    """Pageable host input (R's heap, plain numpy) is copied by the host threads into a ring of pinned slots that the
+    DMA engine drains.  RMG_STAGING_ROWS forces that path at test sizes: doubles, a second operand (covariate) and
+    2-byte samples, several chunks, more subject groups than ring slots."""
+    monkeypatch.setenv("RMG_STAGING_ROWS", "3")
+    monkeypatch.setenv("RMG_CHUNK_VOXELS", "2000")
+    Y, X, mask = cfg1_data(dims=(11, 23, 29))
+    assert_rows_match(core.lm_fit(Y, X, mask=mask), oracle.minc2_model_lm(Y, (11, 23, 29), X, mask=mask), RTOL, "staged f64")
+    Yc, Zc, Xs = _cov_case(5001, 31, 3, seed=41)
+    assert_rows_match(core.lm_fit_cov(Yc, Zc, Xs), oracle.lm_loop_cov(Yc, Zc, Xs), RTOL, "staged covariate")
+    U, Xu, scale, offset = _stored_case(7003, 29, 500, seed=42)
+    Yu = oracle.expand_stored(U, scale, offset, slice_len=500)
+    assert_rows_match(core.lm_fit_stored(U, Xu, scale, offset, slice_len=500), oracle.vertex_lm_loop(Yu, Xu), RTOL, "staged u16")
+    F = np.asfortranarray(Yu.astype(np.float32))
+    assert_rows_match(core.lm_fit_stored(F, Xu), oracle.vertex_lm_loop(F.astype(np.float64), Xu), RTOL, "staged f32")
