@@ -74,6 +74,41 @@ struct Stored<float> {
     __device__ static __forceinline__ double load1(const float *p, double) { return (double)__ldg(p); }
 };
 
+// VPT (2 or 4) adjacent samples out of shared memory -> doubles (after the voxel_min subtraction for uint16)
+template <typename T, int VPT>
+__device__ __forceinline__ void load_convert_smem(const T *p, double (&y)[VPT], double cmagic)
+{
+    if constexpr (sizeof(T) == 2) {
+        uint32_t w[VPT / 2];
+        if constexpr (VPT == 8) {
+            const uint4 r = *reinterpret_cast<const uint4 *>(p);
+            w[0] = r.x; w[1] = r.y; w[2] = r.z; w[3] = r.w;
+        } else if constexpr (VPT == 4) {
+            const uint2 r = *reinterpret_cast<const uint2 *>(p);
+            w[0] = r.x; w[1] = r.y;
+        } else {
+            w[0] = *reinterpret_cast<const uint32_t *>(p);
+        }
+#pragma unroll
+        for (int i = 0; i < VPT / 2; ++i) {
+            y[2 * i] = __hiloint2double(0x43300000, (int)(w[i] & 0xffffu)) - cmagic;
+            y[2 * i + 1] = __hiloint2double(0x43300000, (int)(w[i] >> 16)) - cmagic;
+        }
+    } else {
+        if constexpr (VPT == 8) {
+            const float4 r = *reinterpret_cast<const float4 *>(p), q = *reinterpret_cast<const float4 *>(p + 4);
+            y[0] = (double)r.x; y[1] = (double)r.y; y[2] = (double)r.z; y[3] = (double)r.w;
+            y[4] = (double)q.x; y[5] = (double)q.y; y[6] = (double)q.z; y[7] = (double)q.w;
+        } else if constexpr (VPT == 4) {
+            const float4 r = *reinterpret_cast<const float4 *>(p);
+            y[0] = (double)r.x; y[1] = (double)r.y; y[2] = (double)r.z; y[3] = (double)r.w;
+        } else {
+            const float2 r = *reinterpret_cast<const float2 *>(p);
+            y[0] = (double)r.x; y[1] = (double)r.y;
+        }
+    }
+}
+
 // value of one sample as the reference's doubles: separate multiply and add (never an FMA)
 __device__ __forceinline__ double descale(double t, double sc, double of) { return __dadd_rn(__dmul_rn(t, sc), of); }
 
@@ -307,12 +342,11 @@ __global__ void pack_tables_kernel(const double *__restrict__ scale, const doubl
     tab[i] = j < n ? make_double2(scale[s_ + (int64_t)j * nslices], offset[s_ + (int64_t)j * nslices]) : make_double2(0.0, 0.0);
 }
 
-template <int KP, typename T, int CW, int NJ, int STAGES, int MINB>
+template <int KP, typename T, int CW, int NJ, int STAGES, int MINB, int VPT>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB)
 lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a, const double2 *__restrict__ tab, int n_pad)
 {
     constexpr bool SC = Stored<T>::kScaled;
-    constexpr int VPT = 4;
     constexpr int TV = CW * 32 * VPT;
     constexpr int BOXW = TV < 256 ? TV : 256;
     constexpr int NBOX = TV / BOXW;
@@ -406,8 +440,8 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
 #pragma unroll
                 for (int jj = 0; jj < NJ; ++jj) {
                     if (jj < nvalid) {
-                        double y[4];
-                        Stored<T>::convert(*reinterpret_cast<const typename Stored<T>::Raw *>(mine + jj * BOXW), y, cm);
+                        double y[VPT];
+                        load_convert_smem<T, VPT>(mine + jj * BOXW, y, cm);
                         double2 so0 = make_double2(1.0, 0.0), so1 = so0;
                         if (SC) {
                             so0 = tabs[(SAME ? sel[0] : 0) * NJ + jj];
@@ -481,12 +515,12 @@ EncodeTiledFn packed_encode_tiled()
 }
 
 // returns cudaErrorNotSupported when this layout / size is not for the TMA variant (caller falls back)
-template <int KP, typename T, int MINB>
+template <int KP, typename T, int MINB, int CW = 4, int VPT = 4>
 cudaError_t launch_packed_tma(const PackedArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
 {
     constexpr bool SC = Stored<T>::kScaled;
-    constexpr int CW = 4, NJ = 8, STAGES = 4;
-    constexpr int TV = CW * 128, BOXW = 256;
+    constexpr int NJ = 8, STAGES = 4;
+    constexpr int TV = CW * 32 * VPT, BOXW = TV < 256 ? TV : 256;
     constexpr int STAGE_B = (NJ * TV * (int)sizeof(T) + (SC ? 2 * NJ * 16 : 0) + 127) & ~127;
     if (a.mask || KP > 8) return cudaErrorNotSupported;
     if ((reinterpret_cast<uintptr_t>(a.U) & 15) || (a.ldU * sizeof(T)) % 16 || a.V > 0x7fffffffLL) return cudaErrorNotSupported;
@@ -517,7 +551,7 @@ cudaError_t launch_packed_tma(const PackedArgs &a, const LmPlan &plan, LmScratch
         if (info) info->launches++;
         tab = reinterpret_cast<const double2 *>(scr.flags);
     }
-    auto kern = lm_fit_packed_tma_kernel<KP, T, CW, NJ, STAGES, MINB>;
+    auto kern = lm_fit_packed_tma_kernel<KP, T, CW, NJ, STAGES, MINB, VPT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t ntiles = (a.V + TV - 1) / TV;
@@ -534,8 +568,10 @@ cudaError_t launch_packed_t(const PackedArgs &a, const LmPlan &plan, LmScratch &
         if constexpr (KP <= 8) {
             // CTAs per SM: as many as the accumulators leave registers for (RMG_TMA_CFG=1 forces one more, with spills)
             constexpr int MINB = KP <= 2 ? 4 : (KP <= 4 ? 3 : 2);
-            const cudaError_t e = plan.tma_cfg == 1 ? launch_packed_tma<KP, T, MINB + 1>(a, plan, scr, st, info)
-                                                    : launch_packed_tma<KP, T, MINB>(a, plan, scr, st, info);
+            // Shape measured best on config 2 as uint16 (2.96 ms): 4 consumer warps x 4 voxels per thread, MINB CTAs/SM.
+            // Alternatives tried (profiles/README.md): 2 voxels/thread with 4-6 CTAs/SM 3.2-3.6 ms, 8 voxels/thread
+            // 3.2 ms, one more CTA per SM at 96 registers (spills) 3.17 ms.
+            const cudaError_t e = launch_packed_tma<KP, T, MINB>(a, plan, scr, st, info);
             if (e != cudaErrorNotSupported) return e;
         }
     }
