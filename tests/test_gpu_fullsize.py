@@ -241,3 +241,36 @@ def test_config2_full_size_stored_and_covariate(torch_mod, oracle):
     for i in range(3):
         assert close(o2[2 + i], oc[2 + i], 1e-6), i                       # static betas (intercept ~3e4: looser scale)
     assert close(o2[2 * p + 2], oc[2 * p + 2], 1e-9)                      # logLik: same residuals
+
+
+def test_config5_whole_volume_as_uint16_on_one_gpu(torch_mod, oracle):
+    """Config 5 (40 um, 400x560x340 x 200 subjects) is 121.9 GB as doubles and needs 8 GPUs; in its stored type the
+    whole volume is 30.5 GB and fits one B200.  V = 76,160,000 exercises the int32 TMA coordinates and 64-bit offsets."""
+    torch, core, free = torch_mod
+    dims, n = (400, 560, 340), 200
+    V = int(np.prod(dims))
+    if free < V * (2 * n + 8 * 11) * 1.25:
+        pytest.skip("not enough free HBM")
+    X = design_cfg2(n)
+    nsl, slice_len = dims[0], dims[1] * dims[2]
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    Ut = torch.empty((n, V), dtype=torch.uint16, device="cuda")
+    for j in range(n):
+        blk = torch.empty(V, dtype=torch.float32, device="cuda").normal_(20000.0, 300.0, generator=g)
+        Ut[j] = blk.round_().clamp_(0, 32767).to(torch.int16).view(torch.uint16)
+    del blk
+    rs = np.random.default_rng(6)
+    smin = rs.normal(-0.5, 0.02, (n, nsl))
+    sc_h, of_h = np.ascontiguousarray(rs.uniform(1.0, 1.2, (n, nsl)) / 65535.0), np.ascontiguousarray(smin)
+    out = core.lm_fit_stored_torch(Ut, X, torch.from_numpy(sc_h).cuda(), torch.from_numpy(of_h).cuda(), slice_len=slice_len)
+    torch.cuda.synchronize()
+    assert core.last_fit_variant() == "lm_fit_packed_tma_kernel"
+    sel = np.sort(np.random.default_rng(0).choice(V, size=1500, replace=False))
+    sel[0], sel[-1] = 0, V - 1
+    st = torch.from_numpy(sel).cuda()
+    Us = Ut.view(torch.int16)[:, st].cpu().numpy().view(np.uint16).T
+    sl = sel // slice_len
+    Ys = (Us.astype(np.float64) - 0.0) * sc_h.T[sl, :] + of_h.T[sl, :]
+    assert_rows_match(out[:, st].cpu().numpy().T, oracle.vertex_lm_loop(Ys, X), RTOL, "cfg5 uint16 sample")
+    assert bool(torch.isfinite(out).all())
