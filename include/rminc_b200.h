@@ -160,10 +160,12 @@ int rmg_lm_fit_stored(const void *U, int dtype, int64_t V, int64_t ldU, int n,
                       const double *scale, const double *offset, double voxel_min, int64_t slice_len,
                       const double *X, int p, const double *mask, double mask_lo, double mask_hi,
                       double *out, int64_t ldOut, int device, char *err, size_t errlen);
-/* Device-resident form (dU, dscale, doffset, dmask, dout on `device`), enqueued on `stream`. */
+/* Device-resident form (dU, dscale, doffset, dmask, dout on `device`), enqueued on `stream`.  dU may be a voxel
+ * shard of a larger volume: v_offset is the global index of its first voxel (slice = (v_offset + v) / slice_len) and
+ * nslices the number of rows of dscale / doffset (<= 0: ceil((v_offset + V) / slice_len)). */
 int rmg_lm_fit_stored_device(const void *dU, int dtype, int64_t V, int64_t ldU, int n,
                              const double *dscale, const double *doffset, double voxel_min, int64_t slice_len,
-                             const double *X, int p, const double *dmask, double mask_lo, double mask_hi,
+                             int64_t nslices, int64_t v_offset, const double *X, int p, const double *dmask, double mask_lo, double mask_hi,
                              double *dout, int64_t ldOut, int device, void *stream, char *err, size_t errlen);
 
 /*

@@ -40,7 +40,7 @@ SIGNATURES = {
     "rmg_lm_fit_stored": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
                                     C.c_int64, C.c_void_p, C.c_int] + _MASK + [C.c_void_p, C.c_int64, C.c_int] + _ERR),
     "rmg_lm_fit_stored_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
-                                           C.c_double, C.c_int64, C.c_void_p, C.c_int] + _MASK
+                                           C.c_double, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int] + _MASK
                                  + [C.c_void_p, C.c_int64, C.c_int, C.c_void_p] + _ERR),
     "rmg_fdr": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + _ERR),
     "rmg_fdr_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -213,9 +213,11 @@ def lm_fit_stored(U, X, scale=None, offset=None, voxel_min=0.0, slice_len=None, 
 
 
 def lm_fit_stored_torch(Ut, X, scale=None, offset=None, voxel_min=0.0, slice_len=None, mask=None,
-                        mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, out=None):
+                        mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, out=None, v_offset=0):
     """Device-resident form: Ut (n, V) uint16 / float32 CUDA tensor; scale / offset (n, nslices) float64 CUDA
-    tensors (the column-major [nslices x n] tables).  Returns a (2p+3, V) CUDA tensor; current stream."""
+    tensors (the column-major [nslices x n] tables).  Returns a (2p+3, V) CUDA tensor; current stream.
+    v_offset: global index of Ut's first voxel when Ut is a voxel shard of a larger volume (the tables then cover
+    the whole volume)."""
     import torch
     if not (Ut.is_cuda and Ut.dim() == 2 and Ut.stride(1) == 1 and Ut.dtype in (torch.uint16, torch.float32)):
         raise ValueError("Ut must be a uint16 / float32 CUDA tensor of shape (n, V) with unit stride along V")
@@ -224,19 +226,23 @@ def lm_fit_stored_torch(Ut, X, scale=None, offset=None, voxel_min=0.0, slice_len
     p = X.shape[1]
     dtype = STORED_U16 if Ut.dtype == torch.uint16 else STORED_F32
     slice_len = max(V, 1) if slice_len is None else int(slice_len)
+    nsl = 0
     if dtype == STORED_U16:
-        nsl = (V + slice_len - 1) // slice_len
         for t in (scale, offset):
-            if not (t is not None and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == nsl * n):
-                raise ValueError("scale / offset must be contiguous float64 CUDA tensors of n x nslices elements")
+            if not (t is not None and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.dim() == 2
+                    and t.shape[0] == n):
+                raise ValueError("scale / offset must be contiguous float64 CUDA tensors of shape (n, nslices)")
+        nsl = scale.shape[1]
+        if offset.shape[1] != nsl or nsl * slice_len < v_offset + V:
+            raise ValueError("scale / offset do not cover the voxels [v_offset, v_offset + V)")
     if out is None:
         out = torch.empty((2 * p + 3, V), dtype=torch.float64, device=Ut.device)
     err = _lib.errbuf()
     rc = _lib.load().rmg_lm_fit_stored_device(
         Ut.data_ptr(), dtype, V, Ut.stride(0) if n > 1 else max(V, 1), n,
         scale.data_ptr() if dtype == STORED_U16 else None, offset.data_ptr() if dtype == STORED_U16 else None,
-        float(voxel_min), slice_len, X.ctypes.data, p, mask.data_ptr() if mask is not None else None, mask_lo, mask_hi,
-        out.data_ptr(), out.stride(0), Ut.device.index or 0, _torch_stream(Ut), err, len(err))
+        float(voxel_min), slice_len, nsl, int(v_offset), X.ctypes.data, p, mask.data_ptr() if mask is not None else None,
+        mask_lo, mask_hi, out.data_ptr(), out.stride(0), Ut.device.index or 0, _torch_stream(Ut), err, len(err))
     _lib.check(rc, err)
     return out
 

@@ -647,7 +647,8 @@ int rmg_lm_fit_stored(const void *U, int dtype, int64_t V, int64_t ldU, int n, c
 }
 
 int rmg_lm_fit_stored_device(const void *dU, int dtype, int64_t V, int64_t ldU, int n, const double *dscale,
-                             const double *doffset, double voxel_min, int64_t slice_len, const double *X, int p,
+                             const double *doffset, double voxel_min, int64_t slice_len, int64_t nslices,
+                             int64_t v_offset, const double *X, int p,
                              const double *dmask, double mask_lo, double mask_hi, double *dout, int64_t ldOut, int device,
                              void *stream, char *err, size_t errlen)
 {
@@ -663,8 +664,10 @@ int rmg_lm_fit_stored_device(const void *dU, int dtype, int64_t V, int64_t ldU, 
     {
         RMG_CUDA(cudaStreamWaitEvent(st, cd->ready, 0));
         const int64_t sl = dtype == RMG_STORED_U16 ? slice_len : std::max<int64_t>(V, 1);
+        if (v_offset < 0) { rc = fail(err, errlen, RMG_ERR_INVALID, "v_offset < 0"); goto cleanup; }
         PackedArgs pa{dU, dtype, V, ldU, n, p, cd->qt, cd->dd, dmask, mask_lo, mask_hi, dout, ldOut,
-                      dscale, doffset, 4503599627370496.0 + voxel_min, sl, (V + sl - 1) / sl, 0};
+                      dscale, doffset, 4503599627370496.0 + voxel_min, sl, nslices > 0 ? nslices : (v_offset + V + sl - 1) / sl,
+                      v_offset};
         RMG_CUDA(launch_lm_packed(pa, plan_from_env(device), scr, st, &info));
         g_launch_count += info.launches;
         g_last_fit_variant = info.used_tma ? 5 : 4;

@@ -63,6 +63,27 @@ def lm_fit_sharded(Yt_local, X, mask_local=None, mask_lo=1.0, mask_hi=99999999.0
     return fit(Yt_local, X, mask=mask_local, mask_lo=mask_lo, mask_hi=mask_hi)
 
 
+def lm_fit_cov_sharded(Yt_local, Zt_local, Xs=None, mask_local=None, mask_lo=1.0, mask_hi=99999999.0,
+                       fit: Optional[Callable] = None):
+    """Voxel-wise covariate design [Xs | z_v] on this rank's shard of both operands.  No collective."""
+    if fit is None:
+        from . import core
+        fit = core.lm_fit_cov_torch
+    return fit(Yt_local, Zt_local, Xs, mask=mask_local, mask_lo=mask_lo, mask_hi=mask_hi)
+
+
+def lm_fit_stored_sharded(Ut_local, X, scale, offset, voxel_min: float, slice_len: int, v_offset: int, mask_local=None,
+                          mask_lo=1.0, mask_hi=99999999.0, fit: Optional[Callable] = None):
+    """The fit on this rank's shard of volumes in their stored type.  `scale` / `offset` are the WHOLE volume's
+    (n, nslices) tables (replicated, a few hundred KB); v_offset = first voxel of the shard, so every voxel looks up
+    the slice it has in the file.  No collective."""
+    if fit is None:
+        from . import core
+        fit = core.lm_fit_stored_torch
+    return fit(Ut_local, X, scale, offset, voxel_min=voxel_min, slice_len=slice_len, mask=mask_local, mask_lo=mask_lo,
+               mask_hi=mask_hi, v_offset=v_offset)
+
+
 def gather_rows(out_local, V: int, group=None, dst: int = 0):
     """Stitch the per-rank (ncol, V_local) blocks back into (ncol, V) on rank `dst` (what
     Reduce(rbind) + result_fleshed_out do in R/minc_voxel_statistics.R:873,898-905)."""

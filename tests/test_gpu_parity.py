@@ -633,3 +633,22 @@ def test_pageable_input_through_the_pinned_staging_ring(core, oracle, monkeypatc
     assert_rows_match(core.lm_fit_stored(U, Xu, scale, offset, slice_len=500), oracle.vertex_lm_loop(Yu, Xu), RTOL, "staged u16")
     F = np.asfortranarray(Yu.astype(np.float32))
     assert_rows_match(core.lm_fit_stored(F, Xu), oracle.vertex_lm_loop(F.astype(np.float64), Xu), RTOL, "staged f32")
+
+
+def test_stored_device_shards_keep_global_slices(core, oracle):
+    """Two voxel shards of one volume through the device entry point with v_offset: the rows equal the unsharded fit."""
+    import torch
+    V, n, slice_len = 90_000, 20, 7001
+    U, X, scale, offset = _stored_case(V, n, slice_len, seed=77)
+    Ut = torch.from_numpy(np.ascontiguousarray(U.T).view(np.int16)).cuda().view(torch.uint16)
+    sc = torch.from_numpy(np.ascontiguousarray(scale.T)).cuda()
+    of = torch.from_numpy(np.ascontiguousarray(offset.T)).cuda()
+    whole = core.lm_fit_stored_torch(Ut, X, sc, of, slice_len=slice_len)
+    a = 44_000                                                       # 8-voxel aligned cut inside slice 6
+    lo = core.lm_fit_stored_torch(Ut[:, :a], X, sc, of, slice_len=slice_len)
+    hi = core.lm_fit_stored_torch(Ut[:, a:], X, sc, of, slice_len=slice_len, v_offset=a)
+    torch.cuda.synchronize()
+    # (the shards are small enough for the direct-load kernel, the whole volume takes the TMA ring)
+    assert_rows_match(torch.cat([lo, hi], dim=1).cpu().numpy().T, whole.cpu().numpy().T, 1e-12, "shards vs whole")
+    Y = oracle.expand_stored(U, scale, offset, slice_len=slice_len)
+    assert_rows_match(whole.cpu().numpy().T, oracle.vertex_lm_loop(Y, X), RTOL, "whole")
