@@ -228,6 +228,29 @@ int rmg_randomize(const double *Y, int64_t V, int64_t ldY, int n, const double *
                   double *dist, int device, char *err, size_t errlen);
 
 /*
+ * vertexTFCE: threshold-free cluster enhancement on an adjacency graph.  Drop-in for graph_tfce_wqu / graph_tfce
+ * (src/vertex_tfce.cpp:92-157; R callers vertexTFCE.numeric / vertexTFCE.matrix, R/minc_vertex_statistics.R:738-887),
+ * batched over maps.
+ *   maps      V x nmaps (column-major: one map per column), out likewise
+ *   adj_ptr / adj_idx   CSR form of the 0-based adjacency list vertexTFCE takes (adj_ptr[V+1], adj_idx[adj_ptr[V]])
+ *   weights   V vertex areas, NULL = ones (R/minc_vertex_statistics.R:752-758)
+ *   E, H, nsteps   extent / height exponents and number of threshold steps (defaults 0.5, 2, 100); nsteps <= 253
+ *   side      0 "both" (tfce(x) - tfce(-x)), 1 "positive", 2 "negative" (-tfce(-x))   (:788-796)
+ */
+int rmg_graph_tfce(const double *maps, int64_t V, int nmaps, const int32_t *adj_ptr, const int32_t *adj_idx,
+                   const double *weights, double E, double H, int nsteps, int side, double *out, int device,
+                   char *err, size_t errlen);
+/*
+ * vertexTFCE.vertexLm's permutation test (R/minc_vertex_statistics.R:892-948 -> mincRandomize_core with
+ * post_proc = vertexTFCE.matrix): per permutation refit, non-finite -> 0, graph TFCE of every column in `cols`,
+ * abs when two_sided, column maximum.  dist: R x ncols.  No mask (vertexLm has none).
+ */
+int rmg_randomize_tfce(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p,
+                       const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
+                       const int32_t *adj_ptr, const int32_t *adj_idx, const double *weights,
+                       double E, double H, int nsteps, int side, double *dist, int device, char *err, size_t errlen);
+
+/*
  * Device-resident variant: dY/dmask on `device`; ddist is a device R x ncols matrix that
  * receives this device's maxima over ITS voxels (voxel shards on several GPUs are combined by
  * the caller with an element-wise max, e.g. ncclAllReduce(ncclMax)).  Enqueued on `stream`.

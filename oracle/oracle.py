@@ -380,3 +380,44 @@ def fdr(stat, stat_type, df1, df2=None, mask=None):
         if acc.size:
             th[j] = S.t.isf(acc.max() / 2.0, df1) if stat_type == "t" else S.f.isf(acc.max(), df1, df2)
     return out, th, p
+
+
+# ------------------------------------------------------------------ graph TFCE (src/vertex_tfce.cpp:92-157)
+_REF_TFCE = os.path.join(_HERE, "_ref", "librminc_ref_tfce.so")
+_ref_tfce = None
+TFCE_SIDES = {"both": 0, "positive": 1, "negative": 2}
+
+
+def have_ref_tfce() -> bool:
+    return os.path.exists(_REF_TFCE)
+
+
+def adjacency_csr(adjacencies):
+    """0-based adjacency list (list of neighbour arrays, as vertexTFCE takes it) -> CSR (ptr int32[V+1], idx int32)."""
+    ptr = np.zeros(len(adjacencies) + 1, dtype=np.int32)
+    ptr[1:] = np.cumsum([len(a) for a in adjacencies])
+    idx = np.concatenate([np.asarray(a, dtype=np.int32) for a in adjacencies]) if len(adjacencies) else np.zeros(0, np.int32)
+    return ptr, np.ascontiguousarray(idx, dtype=np.int32)
+
+
+def graph_tfce(x, adj_ptr, adj_idx, E=0.5, H=2.0, nsteps=100, side="both", weights=None, use_ref=False):
+    """vertexTFCE.numeric's native step: graph_tfce_wqu / graph_tfce on one map (R/minc_vertex_statistics.R:788-796)."""
+    global _ref_tfce
+    x = _f64(np.asarray(x).reshape(-1))
+    V = x.shape[0]
+    w = np.ones(V) if weights is None else _f64(np.broadcast_to(np.asarray(weights, dtype=np.float64), (V,)).copy())
+    ptr = np.ascontiguousarray(adj_ptr, dtype=np.int32)
+    idx = np.ascontiguousarray(adj_idx, dtype=np.int32)
+    out = np.zeros(V)
+    args = (_p(x), C.c_int64(V), ptr.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p), _p(w), C.c_double(E),
+            C.c_double(H), C.c_int(nsteps), C.c_int(TFCE_SIDES[side]), _p(out))
+    if use_ref:
+        if _ref_tfce is None:
+            _ref_tfce = _load(_REF_TFCE)
+            _ref_tfce.ref_graph_tfce.restype = C.c_int
+        err = C.create_string_buffer(256)
+        if _ref_tfce.ref_graph_tfce(*args, err, C.c_size_t(256)):
+            raise OracleError(err.value.decode())
+        return out
+    lib().orc_graph_tfce(*args)
+    return out

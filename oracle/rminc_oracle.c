@@ -676,3 +676,96 @@ void orc_expand_f32(const float *U, int64_t V, int64_t ldU, int n, double *out, 
     for (int j = 0; j < n; ++j)
         for (int64_t v = 0; v < V; ++v) out[v + ldOut * j] = (double)U[v + ldU * j];
 }
+
+/* ------------------------------------------------------------------ graph TFCE */
+/* graph_tfce_wqu / graph_tfce (src/vertex_tfce.cpp:92-157): threshold-free cluster enhancement on an arbitrary
+ * adjacency graph.  Vertices are visited in descending order of the map; for thresholds t = hmax, hmax - dh, ...
+ * while t >= 0 (dh = hmax / nsteps, t decremented in floating point exactly like the reference's loop) the vertices
+ * with map >= t are united with their neighbours in [t, map[v]] by weighted quick union (smaller tree under larger,
+ * path halving, cluster mass carried at the root), and every such vertex receives t^H * mass(cluster)^E * dh.
+ * side: 0 both (tfce(map) - tfce(-map)), 1 positive, 2 negative (-tfce(-map)); R/minc_vertex_statistics.R:788-796.
+ * adj_ptr / adj_idx: CSR adjacency, 0-based. */
+typedef struct { const double *v; } orc_sortctx;
+static const double *orc_sort_vals;
+static int orc_cmp_desc(const void *a, const void *b)
+{
+    const double x = orc_sort_vals[*(const int32_t *)a], y = orc_sort_vals[*(const int32_t *)b];
+    if (x > y) return -1;
+    if (x < y) return 1;
+    return (*(const int32_t *)a > *(const int32_t *)b) - (*(const int32_t *)a < *(const int32_t *)b);
+}
+
+static int32_t orc_wqu_root(int32_t *id, int32_t i)
+{
+    while (i != id[i]) {
+        id[i] = id[id[i]];
+        i = id[i];
+    }
+    return i;
+}
+
+static void orc_tfce_one_side(const double *map, int64_t V, const int32_t *adj_ptr, const int32_t *adj_idx,
+                              const double *weights, double E, double H, int nsteps, double *tfce)
+{
+    int32_t *order = (int32_t *)malloc((size_t)V * sizeof(int32_t));
+    int32_t *id = (int32_t *)malloc((size_t)V * sizeof(int32_t));
+    int32_t *sz = (int32_t *)malloc((size_t)V * sizeof(int32_t));
+    double *mass = (double *)malloc((size_t)V * sizeof(double));
+    for (int64_t v = 0; v < V; ++v) {
+        order[v] = (int32_t)v;
+        id[v] = (int32_t)v;
+        sz[v] = 1;
+        mass[v] = weights[v];
+        tfce[v] = 0.0;
+    }
+    orc_sort_vals = map;
+    qsort(order, (size_t)V, sizeof(int32_t), orc_cmp_desc);
+    const double hmin = 0.0, hmax = V > 0 ? map[order[0]] : 0.0;
+    const double dh = (hmax - hmin) / (double)nsteps;
+    if (hmax > hmin) {
+        for (double t = hmax; t >= hmin; t -= dh) {
+            int64_t nvisited = 0;
+            for (int64_t s = 0; s < V && map[order[s]] >= t; ++s) {
+                const int32_t ind = order[s];
+                ++nvisited;
+                for (int32_t e = adj_ptr[ind]; e < adj_ptr[ind + 1]; ++e) {
+                    const int32_t nb = adj_idx[e];
+                    if (map[nb] >= t && map[nb] <= map[ind]) {
+                        const int32_t i = orc_wqu_root(id, nb), j = orc_wqu_root(id, ind);
+                        if (i != j) {
+                            if (sz[i] < sz[j]) { id[i] = j; sz[j] += sz[i]; mass[j] += mass[i]; }
+                            else { id[j] = i; sz[i] += sz[j]; mass[i] += mass[j]; }
+                        }
+                    }
+                }
+            }
+            const double height_mul = pow(t, H);
+            for (int64_t s = 0; s < nvisited; ++s) {
+                int32_t r = order[s];
+                while (r != id[r]) r = id[r];
+                tfce[order[s]] += height_mul * pow(mass[r], E) * dh;
+            }
+        }
+    }
+    free(order); free(id); free(sz); free(mass);
+}
+
+void orc_graph_tfce(const double *map, int64_t V, const int32_t *adj_ptr, const int32_t *adj_idx, const double *weights,
+                    double E, double H, int nsteps, int side, double *out)
+{
+    if (side == 1) {
+        orc_tfce_one_side(map, V, adj_ptr, adj_idx, weights, E, H, nsteps, out);
+        return;
+    }
+    double *neg = (double *)malloc((size_t)(V > 0 ? V : 1) * sizeof(double));
+    double *tmp = (double *)malloc((size_t)(V > 0 ? V : 1) * sizeof(double));
+    for (int64_t v = 0; v < V; ++v) neg[v] = -map[v];
+    orc_tfce_one_side(neg, V, adj_ptr, adj_idx, weights, E, H, nsteps, tmp);
+    if (side == 2) {
+        for (int64_t v = 0; v < V; ++v) out[v] = -tmp[v];
+    } else {
+        orc_tfce_one_side(map, V, adj_ptr, adj_idx, weights, E, H, nsteps, out);
+        for (int64_t v = 0; v < V; ++v) out[v] -= tmp[v];
+    }
+    free(neg); free(tmp);
+}

@@ -1,0 +1,38 @@
+// oracle/rstub/tfce_wrap.cpp -- TEST INFRASTRUCTURE.  C entry point around the reference's own graph_tfce /
+// graph_tfce_wqu (src/vertex_tfce.cpp:92-157), compiled from /root/reference by `make ref` (oracle/Makefile).
+#include <Rcpp.h>
+
+#include <cstdint>
+#include <cstdio>
+
+std::vector<double> graph_tfce_wqu(std::vector<double> map, std::vector<std::vector<int> > adjacencies, double E, double H,
+                                   int nsteps, std::vector<double> weights);
+std::vector<double> graph_tfce(std::vector<double> map, std::vector<std::vector<int> > adjacencies, double E, double H,
+                               int nsteps, std::vector<double> weights);
+
+// side: 0 both, 1 positive, 2 negative  (vertexTFCE.numeric, R/minc_vertex_statistics.R:788-796)
+extern "C" int ref_graph_tfce(const double *map, int64_t V, const int32_t *adj_ptr, const int32_t *adj_idx,
+                              const double *weights, double E, double H, int nsteps, int side, double *out, char *err,
+                              size_t errlen)
+{
+    try {
+        std::vector<double> m(map, map + V), w(weights, weights + V);
+        std::vector<std::vector<int> > adj(V);
+        for (int64_t v = 0; v < V; ++v) adj[v].assign(adj_idx + adj_ptr[v], adj_idx + adj_ptr[v + 1]);
+        std::vector<double> r;
+        if (side == 1) {
+            r = graph_tfce_wqu(m, adj, E, H, nsteps, w);
+        } else if (side == 2) {
+            for (auto &x : m) x = -x;
+            r = graph_tfce_wqu(m, adj, E, H, nsteps, w);
+            for (auto &x : r) x = -x;
+        } else {
+            r = graph_tfce(m, adj, E, H, nsteps, w);
+        }
+        for (int64_t v = 0; v < V; ++v) out[v] = r[v];
+        return 0;
+    } catch (const std::exception &e) {
+        if (err && errlen) snprintf(err, errlen, "%s", e.what());
+        return 1;
+    }
+}

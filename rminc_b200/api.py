@@ -14,6 +14,7 @@ maintainer would add is in rminc_b200/R/ and INTEGRATION.md.
     mincRandomize(x, R, alternative, replace, parallel, columns)   :1326-1378, :1441-1531
     thresholds(x, probs)                                     :1577-1581
     mincFDR / vertexFDR / anatFDR                            R/minc_FDR.R:254-573
+    vertexTFCE (numeric / matrix / vertexLm randomisation)   R/minc_vertex_statistics.R:731-948
 
 Everything numerical goes through the C ABI (rminc_b200.core); there is no CPU path.
 MINC I/O (libminc) is outside the hot path: volumes are staged by a `reader` callable
@@ -523,6 +524,49 @@ def vertexFDR(buffer: MincMatrix, **kw) -> MincMatrix:
 def anatFDR(buffer: MincMatrix, **kw) -> MincMatrix:
     """anatFDR.anatModel -> vertexFDR.vertexMultiDim (R/minc_FDR.R:571-573)."""
     return mincFDR(buffer, **kw)
+
+
+# ----------------------------------------------------------------------------- vertexTFCE
+def vertexTFCE(x, surface, R: int = 500, alternative: str = "two.sided", E: float = 0.5, H: float = 2.0, nsteps: int = 100,
+               weights=None, side: str = "both", replace: bool = False, seed=None, idx=None, device: int = 0):
+    """Threshold-free cluster enhancement on a surface graph (R/minc_vertex_statistics.R:731-948).
+
+    `surface`: the 0-based adjacency list form vertexTFCE accepts (one neighbour array per vertex), or a CSR pair
+    (ptr, idx); mesh objects / igraph are outside this package.  Dispatch as in the reference:
+      * numeric vector -> enhanced vector (vertexTFCE.numeric)
+      * plain matrix   -> every column enhanced (vertexTFCE.matrix)
+      * vertexLm result -> permutation test on every tvalue- column: list(tfce, randomization_dist, args) of class
+        c("vertexTFCE_randomization","vertex_randomization") (vertexTFCE.vertexLm)."""
+    if side not in core.TFCE_SIDES:
+        raise ValueError("'arg' should be one of 'both', 'positive', 'negative'")
+    if isinstance(x, MincMatrix) and "vertexLm" in x.r_class:
+        if alternative not in ("two.sided", "greater"):
+            raise ValueError("'arg' should be one of 'two.sided', 'greater'")
+        if "_Y" not in x.attrs:
+            raise TypeError("x must be the result of vertexLm")
+        columns = [i for i, c in enumerate(x.colnames) if c.startswith("tvalue-")]
+        names = [x.colnames[c] for c in columns]
+        X = x.attrs["model"]
+        n = X.shape[0]
+        original = core.graph_tfce(np.asarray(x)[:, columns], surface, E=E, H=H, nsteps=nsteps, side=side, weights=weights,
+                                   device=device)
+        if idx is None:
+            idx = draw_indices(n, R, replace=replace, seed=seed)
+        idx = np.asarray(idx, dtype=np.int32)
+        if idx.shape != (n, R):
+            raise ValueError("idx must be n x R")
+        dist = core.randomize_tfce(x.attrs["_Y"], X, idx, columns, surface, two_sided=(alternative == "two.sided"), E=E,
+                                   H=H, nsteps=nsteps, side=side, weights=weights, device=device)
+        out = MincRandomization(tfce=MincMatrix(original, colnames=names),
+                                randomization_dist=MincMatrix(dist, colnames=names),
+                                args=dict(call=x.attrs.get("call"), side=side, alternative=alternative))
+        out.r_class = ("vertexTFCE_randomization", "vertex_randomization")
+        return out
+    A = np.asarray(x, dtype=np.float64)
+    res = core.graph_tfce(A, surface, E=E, H=H, nsteps=nsteps, side=side, weights=weights, device=device)
+    if A.ndim == 2:
+        return MincMatrix(res, colnames=getattr(x, "colnames", None))
+    return res
 
 
 # ----------------------------------------------------------------------------- mincRandomize

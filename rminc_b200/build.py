@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librminc_b200.so")
 
-SOURCES = ["capi.cu", "lm_kernels.cu", "lm_cov.cu", "lm_packed.cu", "fdr.cu", "randomize.cu", "perm_gemm.cu", "design.cpp"]
+SOURCES = ["capi.cu", "lm_kernels.cu", "lm_cov.cu", "lm_packed.cu", "fdr.cu", "tfce.cu", "randomize.cu", "perm_gemm.cu", "design.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -292,6 +292,74 @@ def fdr_torch(stat_t, stat_type, df1, df2=0.0, mask=None, out=None):
     return out, th
 
 
+TFCE_SIDES = {"both": 0, "positive": 1, "negative": 2}
+
+
+def adjacency_csr(adjacencies):
+    """The 0-based adjacency list vertexTFCE takes (one neighbour array per vertex) -> CSR (ptr int32[V+1], idx int32)."""
+    if isinstance(adjacencies, tuple) and len(adjacencies) == 2:
+        return (np.ascontiguousarray(adjacencies[0], dtype=np.int32), np.ascontiguousarray(adjacencies[1], dtype=np.int32))
+    ptr = np.zeros(len(adjacencies) + 1, dtype=np.int32)
+    ptr[1:] = np.cumsum([len(a) for a in adjacencies])
+    idx = (np.concatenate([np.asarray(a, dtype=np.int32).reshape(-1) for a in adjacencies])
+           if len(adjacencies) and ptr[-1] else np.zeros(0, np.int32))
+    return ptr, np.ascontiguousarray(idx, dtype=np.int32)
+
+
+def _tfce_weights(weights, V):
+    if weights is None:
+        return None
+    w = np.asarray(weights, dtype=np.float64).reshape(-1)
+    if w.size == 1:
+        w = np.full(V, float(w[0]))
+    if w.size != V:
+        raise ValueError("Please supply 1 or enough weights for each element of x")      # minc_vertex_statistics.R:763
+    return np.ascontiguousarray(w)
+
+
+def graph_tfce(maps, adjacency, E=0.5, H=2.0, nsteps=100, side="both", weights=None, device=0):
+    """vertexTFCE.numeric / .matrix native step: maps is V or V x nmaps; returns the same shape (graph_tfce,
+    src/vertex_tfce.cpp:92-157)."""
+    M = np.asarray(maps, dtype=np.float64)
+    one = M.ndim == 1
+    M = np.asfortranarray(M.reshape(-1, 1) if one else M)
+    V, nmaps = M.shape
+    ptr, idx = adjacency_csr(adjacency)
+    if ptr.shape[0] != V + 1:
+        raise ValueError("Mismatch between adjacency list and data")                        # src/vertex_tfce.cpp:97
+    w = _tfce_weights(weights, V)
+    out = np.empty((V, nmaps), order="F")
+    err = _lib.errbuf()
+    rc = _lib.load().rmg_graph_tfce(M.ctypes.data, V, nmaps, ptr.ctypes.data, idx.ctypes.data if idx.size else None,
+                                    w.ctypes.data if w is not None else None, float(E), float(H), int(nsteps),
+                                    TFCE_SIDES[side], out.ctypes.data, device, err, len(err))
+    _lib.check(rc, err)
+    return out[:, 0] if one else out
+
+
+def randomize_tfce(Y, X, idx, cols, adjacency, two_sided=True, E=0.5, H=2.0, nsteps=100, side="both", weights=None,
+                   device=0):
+    """vertexTFCE.vertexLm's permutation loop: R x len(cols) maxima of the enhanced statistic maps."""
+    Y, X, _ = _prep_host(Y, X, None)
+    V, n = Y.shape
+    p = X.shape[1]
+    idx, cols = _prep_perm(idx, n, cols)
+    ptr, aidx = adjacency_csr(adjacency)
+    if ptr.shape[0] != V + 1:
+        raise ValueError("Mismatch between adjacency list and data")
+    w = _tfce_weights(weights, V)
+    R = idx.shape[1]
+    dist = np.empty((R, len(cols)), order="F")
+    err = _lib.errbuf()
+    rc = _lib.load().rmg_randomize_tfce(Y.ctypes.data, V, max(V, 1), n, X.ctypes.data, p, idx.ctypes.data, R,
+                                        cols.ctypes.data, len(cols), int(bool(two_sided)), ptr.ctypes.data,
+                                        aidx.ctypes.data if aidx.size else None, w.ctypes.data if w is not None else None,
+                                        float(E), float(H), int(nsteps), TFCE_SIDES[side], dist.ctypes.data, device,
+                                        err, len(err))
+    _lib.check(rc, err)
+    return dist
+
+
 def vertex_wlm(Y, X, weights, device=0):
     """anatLm(weights=)'s native step (vertex_wlm_loop, src/weighted_least_squares.c:168)."""
     Y, X, _ = _prep_host(Y, X, None)

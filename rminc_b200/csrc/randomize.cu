@@ -26,6 +26,7 @@
 
 #include "capi_common.hpp"
 #include "perm_gemm.cuh"
+#include "tfce.hpp"
 
 namespace rmg {
 namespace {
@@ -109,6 +110,40 @@ int factor_permutations(const double *X, int n, int p, const int32_t *idx, int R
         pd.all_intercept = pd.all_intercept && pd.design(r).has_intercept;
     }
     return RMG_OK;
+}
+
+// t columns of one fitted result matrix -> maps[(slot * ncols + c) * V + v], non-finite -> 0
+// (new_mod[!is.finite(new_mod)] <- 0, R/minc_voxel_statistics.R:1478)
+__global__ void __launch_bounds__(256)
+extract_maps_kernel(const double *__restrict__ out, int64_t V, int64_t ld, const int32_t *__restrict__ cols, int ncols,
+                    int slot, double *__restrict__ maps)
+{
+    const int c = blockIdx.y;
+    const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (v >= V) return;
+    const double x = out[(int64_t)cols[c] * ld + v];
+    maps[((size_t)slot * ncols + c) * V + v] = isfinite(x) ? x : 0.0;
+}
+
+// per-map maximum of the enhanced maps (abs first when two-sided, :1484-1488) -> keys[c * R + r]
+__global__ void __launch_bounds__(256)
+tfce_colmax_kernel(const double *__restrict__ tf, int64_t V, int ncols, int two_sided, unsigned long long *__restrict__ keys,
+                   int R, int r0)
+{
+    __shared__ double red[8];
+    const int j = blockIdx.y;                   // map index inside the batch: (r - r0) * ncols + c
+    double best = -INFINITY;
+    for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < V; v += (int64_t)gridDim.x * 256) {
+        const double x = tf[(size_t)j * V + v];
+        best = fmax(best, two_sided ? fabs(x) : x);
+    }
+    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) best = fmax(best, red[w]);
+        atomicMax(&keys[(size_t)(j % ncols) * R + (r0 + j / ncols)], ordered_key(best));
+    }
 }
 
 enum class PermPath { Auto, Refit, Gemm };
@@ -243,6 +278,120 @@ cleanup:
     if (scratch) cudaFreeAsync(scratch, st);
     if (gemm_ws) cudaFreeAsync(gemm_ws, st);
     scr.release(st);
+    if (rc != RMG_OK) cudaGetLastError();
+    return rc;
+}
+
+// vertexTFCE.vertexLm's randomisation (R/minc_vertex_statistics.R:892-948): mincRandomize_core with
+// post_proc = vertexTFCE.matrix -- per permutation refit, non-finite -> 0, graph TFCE of every requested column, abs when
+// two-sided, column maximum.  Batches of permutations are fitted into a map stack and enhanced together.
+int rmg_randomize_tfce(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *idx, int R,
+                       const int32_t *cols, int ncols, int two_sided, const int32_t *adj_ptr, const int32_t *adj_idx,
+                       const double *weights, double E, double H, int nsteps, int side, double *dist, int device, char *err,
+                       size_t errlen)
+{
+    int rc = check_fit_args(Y, V, ldY, n, X, p, Y, ldY, err, errlen);
+    if (rc) return rc;
+    if (R < 0 || ncols < 0 || (R > 0 && !idx) || (ncols > 0 && !cols) || (R > 0 && ncols > 0 && !dist))
+        return fail(err, errlen, RMG_ERR_INVALID, "bad permutation arguments");
+    for (int c = 0; c < ncols; ++c)
+        if (cols[c] < 0 || cols[c] >= 2 * p + 3) return fail(err, errlen, RMG_ERR_INVALID, "cols[%d] out of range", c);
+    if (V > 0x7fffffffLL || (V > 0 && !adj_ptr)) return fail(err, errlen, RMG_ERR_INVALID, "bad graph arguments");
+    if (side < 0 || side > 2 || nsteps < 1 || nsteps > 253) return fail(err, errlen, RMG_ERR_INVALID, "bad TFCE arguments");
+    const int64_t nnz = V > 0 ? adj_ptr[V] : 0;
+    for (int64_t e = 0; e < nnz; ++e)
+        if (adj_idx[e] < 0 || adj_idx[e] >= V) return fail(err, errlen, RMG_ERR_INVALID, "Mismatch between adjacency list and data");
+    PermSet pd;
+    if ((rc = factor_permutations(X, n, p, idx, R, pd, err, errlen))) return rc;
+    if ((rc = select_device(device, err, errlen))) return rc;
+    if (R == 0 || ncols == 0 || V == 0) return RMG_OK;
+
+    cudaStream_t st = nullptr;
+    const int64_t ldd = std::max<int64_t>(2, (V + 1) & ~int64_t(1));
+    const int ncol_total = 2 * p + 3, KP = lm_padded_p(p);
+    double *dY = nullptr, *scratch = nullptr, *maps = nullptr, *tf = nullptr, *dw = nullptr, *qt = nullptr, *dD = nullptr;
+    int *dptr = nullptr, *didx = nullptr;
+    int32_t *dcols = nullptr;
+    DevDesign *dd = nullptr;
+    unsigned long long *keys = nullptr;
+    void *ws = nullptr;
+    LmScratch scr;
+    LmPlan plan;
+    plan.sm_count = device_sm_count(device);
+    int launches = 0;
+    {
+        // permutations per batch: keep the TFCE scratch under ~4 GiB
+        const size_t per_map = tfce_workspace_bytes(V, 1, nsteps, side) + 2 * (size_t)V * 8;
+        const int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)R, (size_t(4) << 30) / (per_map * ncols)));
+        const size_t qstride = make_qt(pd.base, KP).size();
+        std::vector<double> ones;
+        if (!weights) ones.assign((size_t)V, 1.0);
+        RMG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dY), (size_t)ldd * n * 8, st));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)ldd * ncol_total * 8, st));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&maps), (size_t)B * ncols * V * 8, st));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&tf), (size_t)B * ncols * V * 8, st));
+        RMG_CUDA(cudaMallocAsync(&ws, tfce_workspace_bytes(V, B * ncols, nsteps, side), st));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dptr), (size_t)(V + 1) * 4, st));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&didx), (size_t)std::max<int64_t>(nnz, 1) * 4, st));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dw), (size_t)V * 8, st));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dcols), (size_t)ncols * 4, st));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&keys), (size_t)R * ncols * 8, st));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dD), (size_t)R * ncols * 8, st));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dd), sizeof(DevDesign) * (size_t)B, st));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&qt), sizeof(double) * (size_t)B * qstride, st));
+        RMG_CUDA(cudaMemcpy2DAsync(dY, (size_t)ldd * 8, Y, (size_t)ldY * 8, (size_t)V * 8, (size_t)n, cudaMemcpyHostToDevice, st));
+        RMG_CUDA(cudaMemcpyAsync(dptr, adj_ptr, (size_t)(V + 1) * 4, cudaMemcpyHostToDevice, st));
+        RMG_CUDA(cudaMemcpyAsync(didx, adj_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+        RMG_CUDA(cudaMemcpyAsync(dw, weights ? weights : ones.data(), (size_t)V * 8, cudaMemcpyHostToDevice, st));
+        RMG_CUDA(cudaMemcpyAsync(dcols, cols, (size_t)ncols * 4, cudaMemcpyHostToDevice, st));
+        keys_init_kernel<<<(R * ncols + 255) / 256, 256, 0, st>>>(keys, R * ncols);
+        ++launches;
+        const TfceGraph g{dptr, didx, dw};
+        std::vector<DevDesign> hdd(B);
+        std::vector<double> hqt((size_t)B * qstride);
+        const unsigned vb = (unsigned)((V + 255) / 256);
+        for (int r0 = 0; r0 < R; r0 += B) {
+            const int rb = std::min(B, R - r0);
+            for (int i = 0; i < rb; ++i) {
+                const Design Dr = pd.materialise(r0 + i);
+                fill_dev_design(Dr, hdd[i]);
+                const std::vector<double> q = make_qt(Dr, KP);
+                std::copy(q.begin(), q.end(), hqt.begin() + (size_t)i * qstride);
+            }
+            RMG_CUDA(cudaMemcpyAsync(dd, hdd.data(), sizeof(DevDesign) * (size_t)rb, cudaMemcpyHostToDevice, st));
+            RMG_CUDA(cudaMemcpyAsync(qt, hqt.data(), sizeof(double) * (size_t)rb * qstride, cudaMemcpyHostToDevice, st));
+            RMG_CUDA(cudaStreamSynchronize(st));          // the host images are reused by the next batch
+            for (int i = 0; i < rb; ++i) {
+                LmArgs a{dY, V, ldd, n, p, qt + (size_t)i * qstride, dd + i, nullptr, 0.0, 0.0, scratch, ldd};
+                LmLaunchInfo info;
+                RMG_CUDA(launch_lm_fit(a, plan, scr, st, &info));
+                launches += info.launches;
+                extract_maps_kernel<<<dim3(vb, (unsigned)ncols), 256, 0, st>>>(scratch, V, ldd, dcols, ncols, i, maps);
+                ++launches;
+            }
+            RMG_CUDA(tfce_batch(maps, V, V, rb * ncols, g, E, H, nsteps, side, tf, V, ws, st, &launches));
+            tfce_colmax_kernel<<<dim3(std::min<unsigned>(vb, 32u), (unsigned)(rb * ncols)), 256, 0, st>>>(tf, V, ncols, two_sided, keys, R, r0);
+            ++launches;
+            RMG_CUDA(cudaGetLastError());
+        }
+        keys_decode_kernel<<<(R * ncols + 255) / 256, 256, 0, st>>>(keys, dD, R * ncols);
+        ++launches;
+        RMG_CUDA(cudaMemcpyAsync(dist, dD, (size_t)R * ncols * 8, cudaMemcpyDeviceToHost, st));
+        RMG_CUDA(cudaStreamSynchronize(st));
+    }
+cleanup:
+    g_launch_count += launches;
+    {
+        void *all[] = {dY, scratch, maps, tf, ws, dptr, didx, dw, dcols, keys, dD, dd, qt};
+        for (void *x : all)
+            if (x) cudaFreeAsync(x, st);
+    }
+    scr.release(st);
+    if (st) {
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+    }
     if (rc != RMG_OK) cudaGetLastError();
     return rc;
 }

@@ -65,3 +65,37 @@ def assert_rows_match(got, want, rtol=1e-9, what=""):
     bad = err > rtol * scale
     assert not bad.any(), (f"{what}: {bad.sum()} entries differ; worst err/scale "
                            f"{(err[bad] / np.maximum(scale[bad], 1e-300)).max():.3e} at {np.argwhere(bad)[:3].tolist()}")
+
+
+def grid_adjacency(a, b):
+    """0-based adjacency list of an a x b grid graph (4-neighbourhood), the list form vertexTFCE accepts."""
+    adj = []
+    for i in range(a):
+        for j in range(b):
+            nb = []
+            if i > 0:
+                nb.append((i - 1) * b + j)
+            if i < a - 1:
+                nb.append((i + 1) * b + j)
+            if j > 0:
+                nb.append(i * b + j - 1)
+            if j < b - 1:
+                nb.append(i * b + j + 1)
+            adj.append(nb)
+    return adj
+
+
+def tfce_randomize_oracle(oracle, Y, X, idx, cols, adjacency, two_sided=True, E=0.5, H=2.0, nsteps=100, side="both",
+                          weights=None):
+    """mincRandomize_core with post_proc = vertexTFCE.matrix, literally (R/minc_voxel_statistics.R:1465-1497):
+    refit with permuted design rows, non-finite -> 0, enhance every column, abs, column maxima."""
+    ptr, aidx = oracle.adjacency_csr(adjacency)
+    R = idx.shape[1]
+    dist = np.empty((R, len(cols)))
+    for r in range(R):
+        res = oracle.vertex_lm_loop(Y, X[idx[:, r]])
+        res[~np.isfinite(res)] = 0.0
+        for j, c in enumerate(cols):
+            tf = oracle.graph_tfce(res[:, c], ptr, aidx, E=E, H=H, nsteps=nsteps, side=side, weights=weights)
+            dist[r, j] = np.max(np.abs(tf) if two_sided else tf)
+    return dist

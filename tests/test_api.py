@@ -45,6 +45,22 @@ def api(request, monkeypatch, oracle, lib):
             q, th, _ = oracle.fdr(stat, "t" if stat_type == core.STAT_T else "F", df1, df2, mask=mask)
             return q, th
 
+        def graph_tfce(maps, adjacency, E=0.5, H=2.0, nsteps=100, side="both", weights=None, device=0):
+            ptr, aidx = core.adjacency_csr(adjacency)
+            M = np.asarray(maps, dtype=np.float64)
+            if M.ndim == 1:
+                return oracle.graph_tfce(M, ptr, aidx, E=E, H=H, nsteps=nsteps, side=side, weights=weights)
+            return np.column_stack([oracle.graph_tfce(M[:, j], ptr, aidx, E=E, H=H, nsteps=nsteps, side=side, weights=weights)
+                                    for j in range(M.shape[1])])
+
+        def randomize_tfce(Y, X, idx, cols, adjacency, two_sided=True, E=0.5, H=2.0, nsteps=100, side="both", weights=None,
+                           device=0):
+            from helpers import tfce_randomize_oracle
+            return tfce_randomize_oracle(oracle, np.asfortranarray(Y), X, np.asarray(idx), list(cols), adjacency,
+                                         two_sided=two_sided, E=E, H=H, nsteps=nsteps, side=side, weights=weights)
+
+        monkeypatch.setattr(core, "graph_tfce", graph_tfce)
+        monkeypatch.setattr(core, "randomize_tfce", randomize_tfce)
         monkeypatch.setattr(core, "fdr", fdr)
         monkeypatch.setattr(core, "lm_fit_stored", lm_fit_stored)
         monkeypatch.setattr(core, "lm_fit_cov", lm_fit_cov)
@@ -374,3 +390,42 @@ def test_mincFDR(api, study):
     with pytest.raises(ValueError, match="need to specify the degrees of freedom"):
         bad = api.MincMatrix(np.asarray(vs), colnames=vs.colnames, attrs={"stat-type": vs.attrs["stat-type"]})
         api.mincFDR(bad)
+
+
+def test_vertexTFCE(api, tmp_path, oracle):
+    """vertexTFCE on a vector, a matrix and a vertexLm result (R/minc_vertex_statistics.R:731-948); the surface is
+    given as the 0-based adjacency list the reference accepts."""
+    from helpers import grid_adjacency, tfce_randomize_oracle
+    rng = np.random.default_rng(17)
+    a, b, n = 12, 15, 12
+    V = a * b
+    adj = grid_adjacency(a, b)
+    ptr, aidx = oracle.adjacency_csr(adj)
+    dx = np.array(["AD", "CN"] * 6)
+    files = []
+    for i in range(n):
+        f = tmp_path / f"t{i}.txt"
+        y = rng.normal(3, 0.3, V)
+        y[40:70] += 0.6 * (dx[i] == "CN")
+        np.savetxt(f, y)
+        files.append(str(f))
+    gf = pd.DataFrame(dict(thickness=files, Dx=dx))
+    vs = api.vertexLm("thickness ~ Dx", gf)
+    t = vs.col("tvalue-DxCN")
+    one = api.vertexTFCE(t, adj)
+    assert one.shape == (V,) and np.allclose(one, oracle.graph_tfce(t, ptr, aidx), rtol=1e-9, atol=1e-12)
+    pos = api.vertexTFCE(t, adj, side="positive", E=1.0, H=1.0, nsteps=20)
+    assert np.allclose(pos, oracle.graph_tfce(t, ptr, aidx, E=1.0, H=1.0, nsteps=20, side="positive"), rtol=1e-9, atol=1e-12)
+    mat = api.vertexTFCE(np.column_stack([t, -t]), adj)
+    assert mat.shape == (V, 2) and np.allclose(np.asarray(mat)[:, 1], -np.asarray(mat)[:, 0], rtol=1e-9, atol=1e-12)
+    res = api.vertexTFCE(vs, adj, R=7, seed=4, nsteps=40)
+    assert res.r_class == ("vertexTFCE_randomization", "vertex_randomization")
+    assert res["tfce"].colnames == ["tvalue-(Intercept)", "tvalue-DxCN"] and res["tfce"].shape == (V, 2)
+    assert res["randomization_dist"].shape == (7, 2) and res["args"]["side"] == "both"
+    idx = api.draw_indices(n, 7, seed=4)
+    want = tfce_randomize_oracle(oracle, vs.attrs["_Y"], vs.attrs["model"], idx, [4, 5], adj, nsteps=40)
+    assert np.asarray(res["randomization_dist"]) == pytest.approx(want, rel=1e-8)
+    th = api.thresholds(res)
+    assert th.shape == (4, 2)
+    with pytest.raises(ValueError, match="should be one of"):
+        api.vertexTFCE(t, adj, side="sideways")

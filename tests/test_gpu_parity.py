@@ -652,3 +652,57 @@ def test_stored_device_shards_keep_global_slices(core, oracle):
     assert_rows_match(torch.cat([lo, hi], dim=1).cpu().numpy().T, whole.cpu().numpy().T, 1e-12, "shards vs whole")
     Y = oracle.expand_stored(U, scale, offset, slice_len=slice_len)
     assert_rows_match(whole.cpu().numpy().T, oracle.vertex_lm_loop(Y, X), RTOL, "whole")
+
+
+# ------------------------------------------------------------------ vertexTFCE
+def test_graph_tfce_matches_oracle(core, oracle):
+    """Batched graph TFCE against the restated (and reference-pinned) weighted-quick-union sweep: sides, weights,
+    exponents, step counts; maps with ties, zeros and an all-negative map."""
+    from helpers import grid_adjacency
+    rng = np.random.default_rng(5)
+    a, b = 60, 70
+    adj = grid_adjacency(a, b)
+    ptr, idx = oracle.adjacency_csr(adj)
+    V = a * b
+    M = rng.standard_normal((V, 7))
+    M[1000:1200, 0] += 3.0
+    M[:, 1] = np.round(M[:, 1], 1)                # many exact ties
+    M[::5, 2] = 0.0
+    M[:, 3] = -np.abs(M[:, 3]) - 0.5              # nothing positive
+    M[:, 4] = np.abs(M[:, 4])                     # nothing negative
+    w = rng.uniform(0.5, 2.0, V)
+    for side in ("both", "positive", "negative"):
+        for weights in (None, w):
+            for E, H, ns in ((0.5, 2.0, 100), (1.0, 1.0, 37), (0.66, 2.0, 253)):
+                got = core.graph_tfce(M, adj, E=E, H=H, nsteps=ns, side=side, weights=weights)
+                want = np.column_stack([oracle.graph_tfce(M[:, j], ptr, idx, E=E, H=H, nsteps=ns, side=side, weights=weights)
+                                        for j in range(M.shape[1])])
+                scale = np.abs(want).max(axis=0, keepdims=True) + 1e-300
+                assert np.abs(got - want).max() <= 1e-10 * scale.max(), (side, weights is None, E, H, ns)
+                assert np.array_equal(got == 0, want == 0)
+    # a single vector, CSR input, argument contract
+    v = core.graph_tfce(M[:, 0], (ptr, idx))
+    assert v.shape == (V,) and np.allclose(v, oracle.graph_tfce(M[:, 0], ptr, idx), rtol=1e-10, atol=0)
+    with pytest.raises(ValueError, match="Mismatch between adjacency list and data"):
+        core.graph_tfce(M[:-1, 0], adj)
+    with pytest.raises(core.RmincGpuError, match="nsteps"):
+        core.graph_tfce(M[:, 0], adj, nsteps=1000)
+
+
+def test_randomize_tfce_matches_literal_loop(core, oracle):
+    """vertexTFCE.vertexLm's permutation test: per permutation refit -> non-finite to 0 -> enhance -> abs -> maximum."""
+    from helpers import grid_adjacency, tfce_randomize_oracle
+    rng = np.random.default_rng(9)
+    a, b, n = 24, 31, 16
+    adj = grid_adjacency(a, b)
+    V = a * b
+    X = np.column_stack([np.ones(n), np.arange(n) % 2, rng.normal(size=n)])
+    Y = np.asfortranarray(rng.normal(3, 0.4, (V, n)))
+    Y[200:260] += 0.8 * X[:, 1]
+    Y[7] = 0.0                                        # a degenerate vertex: NaN statistics -> 0
+    idx = np.column_stack([rng.permutation(n) for _ in range(11)]).astype(np.int32)
+    cols = [5, 6, 7]
+    for two_sided, side in ((True, "both"), (False, "positive")):
+        got = core.randomize_tfce(Y, X, idx, cols, adj, two_sided=two_sided, side=side, nsteps=50)
+        want = tfce_randomize_oracle(oracle, Y, X, idx, cols, adj, two_sided=two_sided, side=side, nsteps=50)
+        np.testing.assert_allclose(got, want, rtol=1e-8)

@@ -365,3 +365,34 @@ def test_fdr_restatement(oracle):
     assert (q[mask < 0.5] == 1).all() and np.all(np.diff(th[~np.isnan(th)]) <= 0)
     acc = np.abs(t[mask > 0.5])[q[mask > 0.5] <= 0.05]
     assert th[1] == pytest.approx(acc.min(), rel=1e-9)       # the weakest accepted |t| is the threshold
+
+
+def test_graph_tfce_restatement(oracle):
+    """graph_tfce_wqu / graph_tfce (src/vertex_tfce.cpp:92-157): equals the reference's own object code bit for bit,
+    and a case small enough to enhance by hand."""
+    from helpers import grid_adjacency
+    # path graph 0-1-2-3, map (2, 1, 0, 1), nsteps = 2, E = 1, H = 1, unit weights: thresholds 2, 1, 0 (dh = 1)
+    #   t = 2: {0}                 -> v0 += 2 * 1 * 1
+    #   t = 1: {0,1} and {3}       -> v0, v1 += 1 * 2 * 1 ; v3 += 1 * 1 * 1
+    #   t = 0: everything          -> += 0
+    ptr, idx = oracle.adjacency_csr([[1], [0, 2], [1, 3], [2]])
+    got = oracle.graph_tfce([2.0, 1.0, 0.0, 1.0], ptr, idx, E=1.0, H=1.0, nsteps=2, side="positive")
+    assert got == pytest.approx([4.0, 2.0, 0.0, 1.0], abs=1e-15)
+    both = oracle.graph_tfce([2.0, 1.0, 0.0, -1.0], ptr, idx, E=1.0, H=1.0, nsteps=2, side="both")
+    assert both == pytest.approx([4.0, 2.0, 0.0, -0.5 * 1 * 0.5 - 1.0 * 1 * 0.5], abs=1e-15)   # -(t=1: 1*1*.5 + t=.5: .5*1*.5)
+    rng = np.random.default_rng(12)
+    adj = grid_adjacency(25, 30)
+    ptr, idx = oracle.adjacency_csr(adj)
+    x = rng.standard_normal(750)
+    x[100:130] += 3.0
+    x[400] = 0.0
+    w = rng.uniform(0.5, 2.0, 750)
+    for side in ("both", "positive", "negative"):
+        for weights in (None, w):
+            for E, H, ns in ((0.5, 2.0, 100), (1.0, 1.0, 37)):
+                a = oracle.graph_tfce(x, ptr, idx, E=E, H=H, nsteps=ns, side=side, weights=weights)
+                if oracle.have_ref_tfce():
+                    assert np.array_equal(a, oracle.graph_tfce(x, ptr, idx, E=E, H=H, nsteps=ns, side=side, weights=weights,
+                                                               use_ref=True))
+                assert (a >= 0).all() if side == "positive" else True
+    assert (oracle.graph_tfce(-np.abs(x) - 1, ptr, idx, side="positive") == 0).all()        # hmax <= 0: all zero
