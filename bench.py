@@ -393,6 +393,40 @@ def run_gpu_arm(args):
         assert bool(((os_[:, :4096] - ref).abs() <= 1e-9 * scl).all()), "stored-type result differs from the double fit"
         del os_, Ye
 
+    # ---- vertexTFCE randomisation: config-3-sized surface (grid graph stand-in for the mesh), all t columns
+    tfce = None
+    if rank == 0 and "tfce" in args.parts:
+        side_len, nv, pv, Rt = 286, 400, 4, args.tfce_perms
+        Vt = side_len * side_len
+        ii, jj = np.divmod(np.arange(Vt), side_len)
+        nbrs = [np.where(ii > 0, np.arange(Vt) - side_len, -1), np.where(ii < side_len - 1, np.arange(Vt) + side_len, -1),
+                np.where(jj > 0, np.arange(Vt) - 1, -1), np.where(jj < side_len - 1, np.arange(Vt) + 1, -1)]
+        nb = np.stack(nbrs, axis=1)
+        keep = nb >= 0
+        aptr = np.zeros(Vt + 1, dtype=np.int32)
+        aptr[1:] = np.cumsum(keep.sum(axis=1))
+        aidx = nb[keep].astype(np.int32)
+        rt = np.random.default_rng(8)
+        Xt = np.column_stack([np.ones(nv)] + [rt.normal(size=nv) for _ in range(pv - 1)])
+        Yt_h = np.asfortranarray(rt.normal(3.0, 0.4, (Vt, nv)))
+        idx_t = np.column_stack([rt.permutation(nv) for _ in range(Rt)]).astype(np.int32)
+        cols_t = list(range(pv + 2, 2 * pv + 2))
+        core.randomize_tfce(Yt_h, Xt, idx_t[:, :4], cols_t, (aptr, aidx))          # warm-up
+        t0 = time.perf_counter()
+        dt_ = core.randomize_tfce(Yt_h, Xt, idx_t, cols_t, (aptr, aidx))
+        sec = time.perf_counter() - t0
+        from oracle import oracle as O
+        O.build(ref=False)
+        tmap = core.lm_fit(Yt_h[:, :nv], Xt)[:, cols_t[1]]
+        c0 = time.perf_counter()
+        O.graph_tfce(tmap, aptr, aidx)
+        cpu_ms = (time.perf_counter() - c0) * 1e3
+        tfce = {"workload": f"vertexTFCE.vertexLm randomisation: {Vt} vertices x {nv} subjects, {pv} t columns, nsteps 100, both sides",
+                "R": Rt, "seconds": sec, "perms_per_s": Rt / sec, "maps_per_s": Rt * pv / sec,
+                "cpu_restatement_ms_per_map": cpu_ms, "speedup_vs_one_core": (cpu_ms * 1e-3 * Rt * pv) / sec,
+                "timing": "wall clock around the host-buffer C-ABI call (upload, refits, enhancement, maxima, download)"}
+        del Yt_h
+
     # ---- mincRandomize (config 4): voxel-sharded, all ranks evaluate every permutation, one all-reduce(MAX)
     rand = None
     if "randomize" in args.parts:
@@ -581,7 +615,7 @@ def run_gpu_arm(args):
                        "l2": "inputs (28.3 GB per GPU) are far larger than the 126 MB L2; no flush needed",
                        "sharding": "contiguous voxel shards, no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
-            "masked_variant": masked, "vertexLm": vertex, "covariate": cov, "stored_u16": stored, "randomize": rand,
+            "masked_variant": masked, "vertexLm": vertex, "covariate": cov, "stored_u16": stored, "vertexTFCE": tfce, "randomize": rand,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -598,7 +632,8 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny smoke configuration (not a bench line)")
     ap.add_argument("--skip-extras", action="store_true", help="only the device-resident headline")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--parts", default="masked,vertex,cov,stored,randomize,e2e,e2e_u16,cpu",
+    ap.add_argument("--tfce-perms", type=int, default=64, help="permutations timed for the vertexTFCE line")
+    ap.add_argument("--parts", default="masked,vertex,cov,stored,tfce,randomize,e2e,e2e_u16,cpu",
                     help="which extra measurements to run beside the headline (comma list)")
     args = ap.parse_args()
     args.parts = set() if args.skip_extras else set(args.parts.split(","))

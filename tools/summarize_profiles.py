@@ -29,7 +29,7 @@ UNIT = {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9, "ms": 1.0, "us
 
 
 def short(name):
-    name = re.sub(r"\(.*", "", name).replace("void ", "").replace("rmg::", "")
+    name = re.sub(r"\(.*", "", name).replace("void ", "").replace("rmg::", "").replace("<unnamed>::", "")
     return name.strip()
 
 
@@ -96,7 +96,7 @@ def cmd_launches(path, title):
         a[0] += 1
         a[1] += ms
     total = sum(a[1] for a in agg.values())
-    MINE = r"^(lm_|mask_|perm_|pack_|fdr_)"
+    MINE = r"^(lm_|mask_|perm_|pack_|fdr_|tfce_|extract_maps|keys_|colmax)"
     ours = sum(a[1] for k, a in agg.items() if re.search(MINE, k))
     print(f"# ncu launch list: {title}\n")
     print("`ncu --metrics gpu__time_duration.sum --clock-control none --csv`; per-launch times are cold-cache and serialised, "
