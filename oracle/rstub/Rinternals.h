@@ -44,6 +44,7 @@ R_xlen_t XLENGTH(SEXP s);
 int TYPEOF(SEXP s);               /* declaration only: used by rminc_b200/csrc/rshim.c's syntax check */
 unsigned char *RAW(SEXP s);
 SEXP SET_VECTOR_ELT(SEXP x, R_xlen_t i, SEXP v);
+SEXP VECTOR_ELT(SEXP x, R_xlen_t i);
 char *R_alloc(size_t n, int size);
 #ifndef FALSE
 #define FALSE 0

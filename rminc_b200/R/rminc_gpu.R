@@ -106,3 +106,31 @@ rmincgpu_fdr_column <- function(stat, stat_type, df, mask = NULL) {
                if (is.null(mask)) NULL else as.double(mask), PACKAGE = "rmincgpu")
   list(qvalue = res[[1]], thresholds = res[[2]])
 }
+
+
+# vertexTFCE: the Rcpp exports graph_tfce_wqu / graph_tfce (R/RcppExports.R:32-38) and the randomisation of
+# vertexTFCE.vertexLm (R/minc_vertex_statistics.R:892-948) on the GPU.  `adjacencies`: the 0-based adjacency list
+# vertexTFCE.numeric builds (lapply(igraph::as_adj_list(surface), `-`, 1)).
+graph_tfce_gpu <- function(map, adjacencies, E = .5, H = 2, nsteps = 100, weights = rep(1, NROW(map)),
+                           side = c("both", "positive", "negative")) {
+  side <- match(match.arg(side), c("both", "positive", "negative")) - 1L
+  .Call("rmincgpu_graph_tfce", map, lapply(adjacencies, as.integer), as.double(E), as.double(H), as.integer(nsteps),
+        as.double(weights), side, PACKAGE = "rmincgpu")
+}
+
+vertexTFCE_randomize_gpu <- function(lmod, adjacencies, R = 500, alternative = c("two.sided", "greater"), E = .5, H = 2,
+                                     nsteps = 100, weights = NULL, side = c("both", "positive", "negative"),
+                                     replace = FALSE, column = 1) {
+  alternative <- match.arg(alternative)
+  side <- match(match.arg(side), c("both", "positive", "negative")) - 1L
+  columns <- grep("tvalue-", colnames(lmod))
+  n <- nrow(attr(lmod, "data"))
+  idx <- vapply(seq_len(R), function(i) sample(seq_len(n), replace = replace), integer(n))
+  Y <- vertexTable(attr(lmod, "filenames"), column = column)
+  w <- if (is.null(weights)) rep(1, nrow(Y)) else as.double(weights)
+  dist <- .Call("rmincgpu_randomize_tfce", Y, attr(lmod, "model"), idx, as.integer(columns), alternative == "two.sided",
+                lapply(adjacencies, as.integer), w, as.double(E), as.double(H), as.integer(nsteps), side,
+                PACKAGE = "rmincgpu")
+  colnames(dist) <- colnames(lmod)[columns]
+  dist
+}

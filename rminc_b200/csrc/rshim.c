@@ -14,6 +14,8 @@
  *   rmincgpu_lm_cov          the same with filenames_right (a voxel-wise covariate) staged as a second matrix
  *   rmincgpu_lm_stored       the same on volumes in their stored type (uint16 + real ranges, float32)
  *   rmincgpu_randomize       the mincRandomize loop (R/minc_voxel_statistics.R:1465-1497)
+ *   rmincgpu_graph_tfce      graph_tfce_wqu / graph_tfce (src/vertex_tfce.cpp:92-157), every column of a matrix at once
+ *   rmincgpu_randomize_tfce  vertexTFCE.vertexLm's permutation loop (R/minc_vertex_statistics.R:892-948)
  *   rmincgpu_fdr             mincFDR's p-value + p.adjust(., "fdr") + threshold step for one column (R/minc_FDR.R:385-505)
  *   rmincgpu_anova           per_voxel_anova / vertex_anova_loop (src/minc_anova.c:142, src/vertex_modelling.c:178)
  */
@@ -226,6 +228,68 @@ SEXP rmincgpu_fdr(SEXP stat, SEXP stat_type, SEXP df, SEXP mask)
     return out;
 }
 
+/* Adjacency list (R list of integer vectors, 0-based as vertexTFCE documents) -> CSR in R_alloc'd memory. */
+static void adjacency_to_csr(SEXP adjacencies, int **ptr_out, int **idx_out)
+{
+    const R_xlen_t V = XLENGTH(adjacencies);
+    int *ptr = (int *)R_alloc((size_t)V + 1, sizeof(int));
+    ptr[0] = 0;
+    for (R_xlen_t v = 0; v < V; ++v) ptr[v + 1] = ptr[v] + LENGTH(VECTOR_ELT(adjacencies, v));
+    int *idx = (int *)R_alloc((size_t)(ptr[V] > 0 ? ptr[V] : 1), sizeof(int));
+    for (R_xlen_t v = 0; v < V; ++v) {
+        SEXP a = VECTOR_ELT(adjacencies, v);
+        for (int e = 0; e < LENGTH(a); ++e)
+            idx[ptr[v] + e] = Rf_isInteger(a) ? INTEGER(a)[e] : (int)REAL(a)[e];
+    }
+    *ptr_out = ptr;
+    *idx_out = idx;
+}
+
+/* graph_tfce_wqu / graph_tfce (src/vertex_tfce.cpp:92-157) for every column of `map`: same arguments as the Rcpp
+ * exports plus side (0 both, 1 positive, 2 negative) so that one routine serves vertexTFCE.numeric's three branches. */
+SEXP rmincgpu_graph_tfce(SEXP map, SEXP adjacencies, SEXP E, SEXP H, SEXP nsteps, SEXP weights, SEXP side)
+{
+    if (!Rf_isReal(map) || !Rf_isReal(weights)) Rf_error("map and weights must be double");
+    const int ismat = Rf_ncols(map) > 1 || Rf_nrows(map) != LENGTH(map);
+    const R_xlen_t V = ismat ? Rf_nrows(map) : XLENGTH(map);
+    const int nmaps = ismat ? Rf_ncols(map) : 1;
+    if (XLENGTH(adjacencies) != V) Rf_error("Mismatch between adjacency list and data");
+    int *ptr, *idx;
+    adjacency_to_csr(adjacencies, &ptr, &idx);
+    SEXP out = PROTECT(ismat ? Rf_allocMatrix(REALSXP, (int)V, nmaps) : Rf_allocVector(REALSXP, V));
+    char err[512] = "";
+    int rc = rmg_graph_tfce(REAL(map), V, nmaps, ptr, idx, XLENGTH(weights) == V ? REAL(weights) : NULL, Rf_asReal(E),
+                            Rf_asReal(H), Rf_asInteger(nsteps), Rf_asInteger(side), REAL(out), 0, err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
+/* vertexTFCE.vertexLm's mincRandomize_core(post_proc = vertexTFCE.matrix) loop in one call. */
+SEXP rmincgpu_randomize_tfce(SEXP Y, SEXP mmatrix, SEXP idx, SEXP columns, SEXP two_sided, SEXP adjacencies, SEXP weights,
+                             SEXP E, SEXP H, SEXP nsteps, SEXP side)
+{
+    if (!Rf_isReal(Y) || !Rf_isReal(mmatrix) || !Rf_isInteger(idx) || !Rf_isInteger(columns))
+        Rf_error("Y/mmatrix must be double, idx/columns integer");
+    const R_xlen_t V = Rf_nrows(Y);
+    const int n = Rf_ncols(Y), p = Rf_ncols(mmatrix), R = Rf_ncols(idx), nc = LENGTH(columns);
+    if (Rf_nrows(idx) != n || XLENGTH(adjacencies) != V) Rf_error("idx / adjacency list do not match the data");
+    int *idx0 = (int *)R_alloc((size_t)n * R, sizeof(int));
+    int *col0 = (int *)R_alloc((size_t)nc, sizeof(int));
+    for (R_xlen_t i = 0; i < (R_xlen_t)n * R; ++i) idx0[i] = INTEGER(idx)[i] - 1;
+    for (int i = 0; i < nc; ++i) col0[i] = INTEGER(columns)[i] - 1;
+    int *ptr, *aidx;
+    adjacency_to_csr(adjacencies, &ptr, &aidx);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, R, nc));
+    char err[512] = "";
+    int rc = rmg_randomize_tfce(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, idx0, R, col0, nc, Rf_asLogical(two_sided), ptr,
+                                aidx, Rf_isReal(weights) && XLENGTH(weights) == V ? REAL(weights) : NULL, Rf_asReal(E),
+                                Rf_asReal(H), Rf_asInteger(nsteps), Rf_asInteger(side), REAL(out), 0, err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
 static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_vertex_lm_loop", (DL_FUNC)&rmincgpu_vertex_lm_loop, 3},
     {"rmincgpu_vertex_wlm_loop", (DL_FUNC)&rmincgpu_vertex_wlm_loop, 4},
@@ -235,6 +299,8 @@ static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_randomize", (DL_FUNC)&rmincgpu_randomize, 9},
     {"rmincgpu_anova", (DL_FUNC)&rmincgpu_anova, 6},
     {"rmincgpu_fdr", (DL_FUNC)&rmincgpu_fdr, 4},
+    {"rmincgpu_graph_tfce", (DL_FUNC)&rmincgpu_graph_tfce, 7},
+    {"rmincgpu_randomize_tfce", (DL_FUNC)&rmincgpu_randomize_tfce, 11},
     {NULL, NULL, 0}};
 
 void R_init_rmincgpu(DllInfo *dll)
