@@ -249,6 +249,12 @@ int rmg_randomize_tfce(const double *Y, int64_t V, int64_t ldY, int n, const dou
                        const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
                        const int32_t *adj_ptr, const int32_t *adj_idx, const double *weights,
                        double E, double H, int nsteps, int side, double *dist, int device, char *err, size_t errlen);
+/* The same over n_gpus devices of the box: the R permutations are split into contiguous blocks, one host thread per GPU,
+ * no exchange (replaces mincRandomize_core's groupingVector(R, n_groups) + mclapply, R/minc_voxel_statistics.R:1503-1509). */
+int rmg_randomize_tfce_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p,
+                             const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
+                             const int32_t *adj_ptr, const int32_t *adj_idx, const double *weights,
+                             double E, double H, int nsteps, int side, double *dist, int n_gpus, char *err, size_t errlen);
 
 /*
  * Device-resident variant: dY/dmask on `device`; ddist is a device R x ncols matrix that

@@ -528,7 +528,8 @@ def anatFDR(buffer: MincMatrix, **kw) -> MincMatrix:
 
 # ----------------------------------------------------------------------------- vertexTFCE
 def vertexTFCE(x, surface, R: int = 500, alternative: str = "two.sided", E: float = 0.5, H: float = 2.0, nsteps: int = 100,
-               weights=None, side: str = "both", replace: bool = False, seed=None, idx=None, device: int = 0):
+               weights=None, side: str = "both", replace: bool = False, parallel=None, seed=None, idx=None,
+               device: int = 0):
     """Threshold-free cluster enhancement on a surface graph (R/minc_vertex_statistics.R:731-948).
 
     `surface`: the 0-based adjacency list form vertexTFCE accepts (one neighbour array per vertex), or a CSR pair
@@ -556,7 +557,8 @@ def vertexTFCE(x, surface, R: int = 500, alternative: str = "two.sided", E: floa
         if idx.shape != (n, R):
             raise ValueError("idx must be n x R")
         dist = core.randomize_tfce(x.attrs["_Y"], X, idx, columns, surface, two_sided=(alternative == "two.sided"), E=E,
-                                   H=H, nsteps=nsteps, side=side, weights=weights, device=device)
+                                   H=H, nsteps=nsteps, side=side, weights=weights, device=device,
+                                   n_gpus=int(parallel[1]) if parallel is not None else None)
         out = MincRandomization(tfce=MincMatrix(original, colnames=names),
                                 randomization_dist=MincMatrix(dist, colnames=names),
                                 args=dict(call=x.attrs.get("call"), side=side, alternative=alternative))

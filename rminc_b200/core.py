@@ -338,7 +338,7 @@ def graph_tfce(maps, adjacency, E=0.5, H=2.0, nsteps=100, side="both", weights=N
 
 
 def randomize_tfce(Y, X, idx, cols, adjacency, two_sided=True, E=0.5, H=2.0, nsteps=100, side="both", weights=None,
-                   device=0):
+                   device=0, n_gpus=None):
     """vertexTFCE.vertexLm's permutation loop: R x len(cols) maxima of the enhanced statistic maps."""
     Y, X, _ = _prep_host(Y, X, None)
     V, n = Y.shape
@@ -351,11 +351,12 @@ def randomize_tfce(Y, X, idx, cols, adjacency, two_sided=True, E=0.5, H=2.0, nst
     R = idx.shape[1]
     dist = np.empty((R, len(cols)), order="F")
     err = _lib.errbuf()
-    rc = _lib.load().rmg_randomize_tfce(Y.ctypes.data, V, max(V, 1), n, X.ctypes.data, p, idx.ctypes.data, R,
-                                        cols.ctypes.data, len(cols), int(bool(two_sided)), ptr.ctypes.data,
-                                        aidx.ctypes.data if aidx.size else None, w.ctypes.data if w is not None else None,
-                                        float(E), float(H), int(nsteps), TFCE_SIDES[side], dist.ctypes.data, device,
-                                        err, len(err))
+    lib = _lib.load()
+    fn, where = (lib.rmg_randomize_tfce, device) if n_gpus is None else (lib.rmg_randomize_tfce_multi, int(n_gpus))
+    rc = fn(Y.ctypes.data, V, max(V, 1), n, X.ctypes.data, p, idx.ctypes.data, R, cols.ctypes.data, len(cols),
+            int(bool(two_sided)), ptr.ctypes.data, aidx.ctypes.data if aidx.size else None,
+            w.ctypes.data if w is not None else None, float(E), float(H), int(nsteps), TFCE_SIDES[side],
+            dist.ctypes.data, where, err, len(err))
     _lib.check(rc, err)
     return dist
 

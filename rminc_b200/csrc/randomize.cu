@@ -396,6 +396,42 @@ cleanup:
     return rc;
 }
 
+// The TFCE permutation test shards over PERMUTATIONS (every permutation needs the whole surface): GPU g takes a
+// contiguous block of the R index vectors, one host thread per GPU, no exchange -- the rows of dist are independent.
+int rmg_randomize_tfce_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *idx, int R,
+                             const int32_t *cols, int ncols, int two_sided, const int32_t *adj_ptr, const int32_t *adj_idx,
+                             const double *weights, double E, double H, int nsteps, int side, double *dist, int n_gpus,
+                             char *err, size_t errlen)
+{
+    const int have = rmg_device_count();
+    if (have <= 0) return fail(err, errlen, RMG_ERR_NO_DEVICE, "no CUDA device available; rminc_b200 has no CPU fallback");
+    const int G = n_gpus <= 0 ? have : n_gpus;
+    if (G > have) return fail(err, errlen, RMG_ERR_NO_DEVICE, "%d GPUs requested, %d visible", G, have);
+    if (R < 0 || ncols < 0 || (R > 0 && (!idx || (ncols > 0 && !dist)))) return fail(err, errlen, RMG_ERR_INVALID, "bad permutation arguments");
+    std::vector<int> rcs(G, RMG_OK);
+    std::vector<std::string> msgs(G, std::string(256, '\0'));
+    std::vector<std::vector<double>> part(G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) {
+        th.emplace_back([&, g]() {
+            const int r0 = (int)((int64_t)R * g / G), r1 = (int)((int64_t)R * (g + 1) / G);
+            if (r1 <= r0) return;
+            part[g].assign((size_t)(r1 - r0) * std::max(ncols, 1), 0.0);
+            rcs[g] = rmg_randomize_tfce(Y, V, ldY, n, X, p, idx + (size_t)r0 * n, r1 - r0, cols, ncols, two_sided, adj_ptr, adj_idx,
+                                        weights, E, H, nsteps, side, part[g].data(), g, &msgs[g][0], msgs[g].size());
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int g = 0; g < G; ++g)
+        if (rcs[g] != RMG_OK) return fail(err, errlen, rcs[g], "gpu %d: %s", g, msgs[g].c_str());
+    for (int g = 0; g < G; ++g) {
+        const int r0 = (int)((int64_t)R * g / G), r1 = (int)((int64_t)R * (g + 1) / G);
+        for (int c = 0; c < ncols; ++c)
+            for (int r = r0; r < r1; ++r) dist[(size_t)c * R + r] = part[g][(size_t)c * (r1 - r0) + (r - r0)];
+    }
+    return RMG_OK;
+}
+
 int rmg_randomize(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
                   double mask_lo, double mask_hi, const int32_t *idx, int R, const int32_t *cols, int ncols,
                   int two_sided, double *dist, int device, char *err, size_t errlen)

@@ -54,7 +54,7 @@ def api(request, monkeypatch, oracle, lib):
                                     for j in range(M.shape[1])])
 
         def randomize_tfce(Y, X, idx, cols, adjacency, two_sided=True, E=0.5, H=2.0, nsteps=100, side="both", weights=None,
-                           device=0):
+                           device=0, n_gpus=None):
             from helpers import tfce_randomize_oracle
             return tfce_randomize_oracle(oracle, np.asfortranarray(Y), X, np.asarray(idx), list(cols), adjacency,
                                          two_sided=two_sided, E=E, H=H, nsteps=nsteps, side=side, weights=weights)

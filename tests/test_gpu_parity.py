@@ -706,3 +706,7 @@ def test_randomize_tfce_matches_literal_loop(core, oracle):
         got = core.randomize_tfce(Y, X, idx, cols, adj, two_sided=two_sided, side=side, nsteps=50)
         want = tfce_randomize_oracle(oracle, Y, X, idx, cols, adj, two_sided=two_sided, side=side, nsteps=50)
         np.testing.assert_allclose(got, want, rtol=1e-8)
+    # permutations sharded over the visible GPUs: same rows
+    G = min(2, core.device_count())
+    np.testing.assert_allclose(core.randomize_tfce(Y, X, idx, cols, adj, two_sided=False, side="positive", nsteps=50, n_gpus=G),
+                               want, rtol=1e-8)
