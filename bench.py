@@ -527,6 +527,38 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         scale = torch.maximum(ref.abs(), ref.square().mean(dim=1, keepdim=True).sqrt())
         assert bool(((chk - ref).abs() <= 1e-9 * scale).all()), "e2e result differs from device result"
+        # mincRandomize through the C ABI from the same pinned host Y: voxel blocks are uploaded on a copy stream and
+        # every block runs its R permutations as it lands (strong scaling: each rank takes its voxel shard)
+        if rand is not None and Ve == V:
+            sa, sb = parallel.my_shard(V, rank, world)
+            cols_a = np.asarray(cols, dtype=np.int32)
+            idx_f = np.asfortranarray(idx, dtype=np.int32)
+            dist_h = np.empty((Rn, len(cols)), order="F")
+
+            def perm_step(R_):
+                rc = lib.rmg_randomize(Yh.ctypes.data + 8 * sa, sb - sa, Ve, n, Xf.ctypes.data, p, None, 1.0, 99999999.0,
+                                       idx_f.ctypes.data, R_, cols_a.ctypes.data, len(cols), 1, dist_h.ctypes.data,
+                                       local_rank, err, len(err))
+                _lib.check(rc, err)
+
+            perm_step(8)
+            barrier()
+            t0 = time.perf_counter()
+            perm_step(Rn)
+            dd = torch.from_numpy(dist_h).to(dev)
+            if world > 1:
+                dist.all_reduce(dd, op=dist.ReduceOp.MAX)
+            torch.cuda.synchronize()
+            barrier()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sec = float(tt.item())
+            assert np.allclose(dd.cpu().numpy().T, d.cpu().numpy(), rtol=1e-9, atol=0), "e2e randomize differs from the device-resident result"
+            rand["e2e"] = {"value": Rn / sec, "unit": "perms/s", "seconds": sec, "h2d_bytes": (sb - sa) * n * 8,
+                           "gemm_window_ms": core.last_kernel_ms(),
+                           "api": "rmg_randomize (C ABI, pinned host Y -> voxel blocks on a copy stream -> all R permutations "
+                                  "per block as it lands -> R x ncols maxima)"}
         del hY, hO
 
     # ---- end to end with the volumes in their stored type: 2 bytes per sample over the host link
@@ -571,6 +603,40 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         scl = torch.maximum(ref.abs(), ref.square().mean(dim=1, keepdim=True).sqrt())
         assert bool(((chk - ref).abs() <= 1e-9 * scl).all()), "stored e2e result differs from device result"
+        if rand is not None:
+            sa, sb = parallel.my_shard(V, rank, world)
+            sa -= sa % slice_len                       # whole slices per rank keep the tables' global index simple here
+            sb = V if rank == world - 1 else sb - sb % slice_len
+            cols_a = np.asarray(cols, dtype=np.int32)
+            idx_f = np.asfortranarray(idx, dtype=np.int32)
+            dist_h = np.empty((Rn, len(cols)), order="F")
+            s0, s1 = sa // slice_len, (sb + slice_len - 1) // slice_len
+            sc_r, of_r = np.ascontiguousarray(sc_h[:, s0:s1]), np.ascontiguousarray(of_h[:, s0:s1])   # [slices x n] col-major
+
+            def perm_u16(R_):
+                rc = lib.rmg_randomize_stored(Uh.ctypes.data + 2 * sa, core.STORED_U16, sb - sa, V, n, sc_r.ctypes.data,
+                                              of_r.ctypes.data, 0.0, slice_len, Xf3.ctypes.data, p, None, 1.0, 99999999.0,
+                                              idx_f.ctypes.data, R_, cols_a.ctypes.data, len(cols), 1, dist_h.ctypes.data,
+                                              local_rank, err, len(err))
+                _lib.check(rc, err)
+
+            perm_u16(8)
+            barrier()
+            t0 = time.perf_counter()
+            perm_u16(Rn)
+            dd = torch.from_numpy(dist_h).to(dev)
+            if world > 1:
+                dist.all_reduce(dd, op=dist.ReduceOp.MAX)
+            torch.cuda.synchronize()
+            barrier()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sec = float(tt.item())
+            assert bool(torch.isfinite(dd).all()) and bool((dd > 0).all())
+            rand["e2e_stored_u16"] = {"value": Rn / sec, "unit": "perms/s", "seconds": sec, "h2d_bytes": (sb - sa) * n * 2,
+                                      "api": "rmg_randomize_stored (C ABI, pinned host uint16 voxels -> blocks expanded once "
+                                             "on the device -> all R permutations per block)"}
         del hU, hO
     Ut = None
 

@@ -226,6 +226,19 @@ int rmg_randomize(const double *Y, int64_t V, int64_t ldY, int n, const double *
                   const double *mask, double mask_lo, double mask_hi,
                   const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
                   double *dist, int device, char *err, size_t errlen);
+/*
+ * The same permutation test on volumes in their stored type (arguments U .. slice_len as rmg_lm_fit_stored): the
+ * samples cross the host link as stored (2 or 4 bytes each) and are expanded once on the device into the doubles
+ * libminc's reader hands minc2_model (src/modelling_functions.c:1037-1055), which stay resident for all R
+ * permutations; the reference re-reads and re-converts every file in every permutation
+ * (R/minc_voxel_statistics.R:1477).  Both host forms upload Y in voxel blocks and start the permutations of a block as
+ * soon as it has landed; pageable input is staged through pinned buffers by all host threads.
+ */
+int rmg_randomize_stored(const void *U, int dtype, int64_t V, int64_t ldU, int n,
+                         const double *scale, const double *offset, double voxel_min, int64_t slice_len,
+                         const double *X, int p, const double *mask, double mask_lo, double mask_hi,
+                         const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
+                         double *dist, int device, char *err, size_t errlen);
 
 /*
  * vertexTFCE: threshold-free cluster enhancement on an adjacency graph.  Drop-in for graph_tfce_wqu / graph_tfce
@@ -285,6 +298,11 @@ int rmg_randomize_multi(const double *Y, int64_t V, int64_t ldY, int n, const do
                         const double *mask, double mask_lo, double mask_hi,
                         const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
                         double *dist, int n_gpus, char *err, size_t errlen);
+int rmg_randomize_stored_multi(const void *U, int dtype, int64_t V, int64_t ldU, int n,
+                               const double *scale, const double *offset, double voxel_min, int64_t slice_len,
+                               const double *X, int p, const double *mask, double mask_lo, double mask_hi,
+                               const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
+                               double *dist, int n_gpus, char *err, size_t errlen);
 
 /* Timing of the most recent rmg_*_device / host call on this thread, for bench.py:
  * milliseconds spent in the dominant kernel(s), measured with CUDA events on the stream the

@@ -85,6 +85,26 @@ mincRandomize_core <- function(x, R = 500, replace = FALSE, parallel = NULL,
   dist
 }
 
+# The same permutation loop on volumes kept in their stored type.  `stored` is what the staging routine of
+# INTEGRATION.md section 5 returns: list(U = raw vector (V x n samples), dtype = 1L (uint16) / 2L (float32), V,
+# scale, offset (nslices x n), voxel_min, slice_len).  2 (or 4) bytes per sample cross the host link, once.
+mincRandomize_stored <- function(lmod, stored, R = 500, replace = FALSE, parallel = NULL,
+                                 columns = grep("tvalue-", colnames(lmod)),
+                                 alternative = c("two.sided", "greater"), mask = NULL, maskval = NULL) {
+  alternative <- match.arg(alternative)
+  n <- nrow(attr(lmod, "data"))
+  idx <- vapply(seq_len(R), function(i) sample(seq_len(n), replace = replace), integer(n))
+  m <- if (is.null(mask)) NULL else as.double(mincGetVolume(mask))
+  lo <- if (is.null(maskval)) 1 else maskval
+  hi <- if (is.null(maskval)) 99999999 else maskval
+  dist <- .Call("rmincgpu_randomize_stored", stored$U, as.integer(stored$dtype), as.double(stored$V), stored$scale,
+                stored$offset, as.double(stored$voxel_min), as.double(stored$slice_len), attr(lmod, "model"), m,
+                as.double(lo), as.double(hi), idx, as.integer(columns), alternative == "two.sided",
+                rmincgpu_n(parallel), PACKAGE = "rmincgpu")
+  colnames(dist) <- colnames(lmod)[columns]
+  dist
+}
+
 # mincAnova / vertexAnova / anatAnova: the native loops (.Call("per_voxel_anova", ...),
 # R/minc_voxel_statistics.R:557-566; .Call("vertex_anova_loop", ...), R/minc_vertex_statistics.R:314-320)
 # become one routine taking the staged matrix and model.matrix's "assign" attribute.

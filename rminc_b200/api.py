@@ -280,6 +280,8 @@ def mincLm(formula: str, data, subset=None, mask=None, maskval=None, parallel=No
             "likeVolume": filenames[0], "filenames": list(filenames), "model": X, "data": data,
             "call": dict(fn="mincLm", formula=formula, subset=subset, mask=mask, maskval=maskval, parallel=parallel),
             "stat-type": _stat_type(p), "df": _df_list(n, p), "model-colnames": names,
+            "_stored": dict(U=U, scale=scale, offset=offset, voxel_min=vmin, slice_len=slice_len),
+            "_mask": m, "_mask_range": (lo, hi), "_rows": rows, "_rhs": rhs, "_lhs": lhs,
         }
         return MincMatrix(out, colnames=_colnames(names), attrs=attrs, r_class=("mincLm", "mincMultiDim", "matrix"))
     if isinstance(first, StoredVolume):
@@ -597,7 +599,7 @@ def mincRandomize(x: MincMatrix, R: int = 500, alternative: str = "two.sided", r
     `columns`: 0-based result columns (default: the tvalue- columns, :1333)."""
     if alternative not in ("two.sided", "greater"):
         raise ValueError("'arg' should be one of 'two.sided', 'greater'")        # match.arg
-    if not isinstance(x, MincMatrix) or "_Y" not in x.attrs:
+    if not isinstance(x, MincMatrix) or ("_Y" not in x.attrs and "_stored" not in x.attrs):
         raise TypeError("x must be the result of mincLm / vertexLm / anatLm")
     X = x.attrs["model"]
     n = X.shape[0]
@@ -611,8 +613,15 @@ def mincRandomize(x: MincMatrix, R: int = 500, alternative: str = "two.sided", r
         raise ValueError("idx must be n x R")
     lo, hi = x.attrs["_mask_range"]
     n_gpus = int(parallel[1]) if parallel is not None else None
-    dist = core.randomize(x.attrs["_Y"], X, idx, columns, two_sided=(alternative == "two.sided"),
-                          mask=x.attrs["_mask"], mask_lo=lo, mask_hi=hi, device=device, n_gpus=n_gpus)
+    if "_stored" in x.attrs:      # the fit ran on volumes in their stored type: so does the permutation test
+        sv = x.attrs["_stored"]
+        dist = core.randomize_stored(sv["U"], X, idx, columns, scale=sv["scale"], offset=sv["offset"],
+                                     voxel_min=sv["voxel_min"], slice_len=sv["slice_len"],
+                                     two_sided=(alternative == "two.sided"), mask=x.attrs["_mask"], mask_lo=lo, mask_hi=hi,
+                                     device=device, n_gpus=n_gpus)
+    else:
+        dist = core.randomize(x.attrs["_Y"], X, idx, columns, two_sided=(alternative == "two.sided"),
+                              mask=x.attrs["_mask"], mask_lo=lo, mask_hi=hi, device=device, n_gpus=n_gpus)
     out = MincRandomization(
         stats=MincMatrix(np.asarray(x)[:, columns], colnames=[x.colnames[c] for c in columns]),
         randomization_dist=MincMatrix(dist, colnames=[x.colnames[c] for c in columns]),

@@ -454,6 +454,40 @@ def randomize(Y, X, idx, cols, two_sided=True, mask=None, mask_lo=DEFAULT_MASK_L
     return dist
 
 
+def randomize_stored(U, X, idx, cols, scale=None, offset=None, voxel_min=0.0, slice_len=None, two_sided=True, mask=None,
+                     mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, device=0, n_gpus=None):
+    """mincRandomize's loop on volumes in their stored type (U, scale, offset, voxel_min, slice_len as lm_fit_stored):
+    the samples are expanded once on the device; the result equals randomize() on the expanded doubles."""
+    X = _lib.as_f64_fortran(X)
+    U = np.asarray(U)
+    if U.ndim != 2 or U.shape[1] != X.shape[0]:
+        raise ValueError(f"U must be V x n with n == nrow(X); got {U.shape} vs {X.shape}")
+    if not U.flags.f_contiguous:
+        U = np.asfortranarray(U)
+    V, n = U.shape
+    p = X.shape[1]
+    dtype, sc, of, slice_len = _stored_tables(U.dtype, V, n, scale, offset, slice_len)
+    m = None
+    if mask is not None:
+        m = np.ascontiguousarray(np.asarray(mask, dtype=np.float64).reshape(-1))
+        if m.shape[0] != V:
+            raise ValueError("mask length must equal the number of voxels")
+    idx, cols = _prep_perm(idx, n, cols)
+    if cols.size and (cols.min() < 0 or cols.max() >= 2 * p + 3):
+        raise ValueError("cols entries must be in 0..2p+2")
+    R = idx.shape[1]
+    dist = np.empty((R, len(cols)), order="F")
+    err = _lib.errbuf()
+    lib = _lib.load()
+    fn, where = (lib.rmg_randomize_stored, device) if n_gpus is None else (lib.rmg_randomize_stored_multi, int(n_gpus))
+    rc = fn(U.ctypes.data, dtype, V, max(V, 1), n, sc.ctypes.data if sc is not None else None,
+            of.ctypes.data if of is not None else None, float(voxel_min), slice_len, X.ctypes.data, p,
+            m.ctypes.data if m is not None else None, mask_lo, mask_hi, idx.ctypes.data, R, cols.ctypes.data, len(cols),
+            int(bool(two_sided)), dist.ctypes.data, where, err, len(err))
+    _lib.check(rc, err)
+    return dist
+
+
 # ------------------------------------------------------------------ device-resident (torch) forms
 def _torch_stream(t):
     import torch

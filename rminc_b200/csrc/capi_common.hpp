@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -77,6 +78,86 @@ inline void parallel_for(int count, Fn fn)
         th.emplace_back([=, &fn]() { fn(a, b); });
     }
     for (auto &t : th) t.join();
+}
+
+// Pageable host memory (R's heap, plain numpy) reaches only ~9.5 GB/s through cudaMemcpy2DAsync
+// (the driver stages it single-threaded); pinned memory reaches the PCIe rate (55 GB/s).  For
+// pageable Y the rows of a chunk are therefore copied by all host threads into a small ring of
+// pinned staging buffers, and the DMA engine drains the ring while the next buffer is being filled.
+struct PinnedRing {
+    static constexpr int kSlots = 4;
+    char *buf[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    bool busy[kSlots] = {false, false, false, false};
+    size_t slot_bytes = 0;
+    int next = 0;
+    cudaError_t init(size_t bytes)
+    {
+        slot_bytes = bytes;
+        for (int s = 0; s < kSlots; ++s) {
+            cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&buf[s]), bytes, cudaHostAllocDefault);
+            if (e != cudaSuccess) return e;
+            e = cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    // next free slot (waits for the DMA that last read it)
+    cudaError_t acquire(int &slot)
+    {
+        slot = next;
+        next = (next + 1) % kSlots;
+        if (busy[slot]) {
+            cudaError_t e = cudaEventSynchronize(done[slot]);
+            if (e != cudaSuccess) return e;
+            busy[slot] = false;
+        }
+        return cudaSuccess;
+    }
+    void release_all()
+    {
+        for (int s = 0; s < kSlots; ++s) {
+            if (done[s]) cudaEventDestroy(done[s]);
+            if (buf[s]) cudaFreeHost(buf[s]);
+            buf[s] = nullptr;
+            done[s] = nullptr;
+        }
+    }
+};
+
+inline bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+// Volumes in their stored type (rmg_lm_fit_stored): Y is then V x n samples of `dtype`, not doubles.
+struct StoredSpec {
+    int dtype;
+    const double *scale, *offset;   // host, [nslices x n], slice fastest (u16 only)
+    double voxel_min;
+    int64_t slice_len;
+    int64_t v_offset = 0;        // global index of this call's first voxel (a shard of a larger volume)
+    int64_t nslices_total = 0;   // rows of scale / offset (0: derive from this call's V)
+};
+
+inline int check_stored_args(int dtype, const double *scale, const double *offset, double voxel_min, int64_t slice_len,
+                             int p, char *err, size_t errlen)
+{
+    if (dtype != RMG_STORED_U16 && dtype != RMG_STORED_F32)
+        return fail(err, errlen, RMG_ERR_INVALID, "dtype must be RMG_STORED_U16 or RMG_STORED_F32 (got %d)", dtype);
+    if (p > 16) return fail(err, errlen, RMG_ERR_INVALID, "stored-type fits support at most 16 design columns (got %d)", p);
+    if (dtype == RMG_STORED_U16) {
+        if (!scale || !offset) return fail(err, errlen, RMG_ERR_INVALID, "scale / offset are NULL");
+        if (slice_len < 1) return fail(err, errlen, RMG_ERR_INVALID, "slice_len must be >= 1");
+        if (!(std::fabs(voxel_min) <= 2147483648.0) || voxel_min != std::floor(voxel_min))
+            return fail(err, errlen, RMG_ERR_INVALID, "voxel_min must be an integer (got %g)", voxel_min);
+    }
+    return RMG_OK;
 }
 
 // Factor X and translate the reference's error contract.  0 or RMG_ERR_*.

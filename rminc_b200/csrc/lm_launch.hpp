@@ -110,6 +110,12 @@ struct PackedArgs {
 
 cudaError_t launch_lm_packed(const PackedArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info);
 
+// Stored samples -> doubles ((u - voxel_min) * scale + offset, the same three roundings as the fused kernels) into a
+// resident V x n matrix; scale / offset as in PackedArgs (device, [nslices x n]); cmagic = 2^52 + voxel_min.
+cudaError_t launch_expand_stored(const void *U, int dtype, int64_t V, int64_t ldU, int n, const double *scale,
+                                 const double *offset, double cmagic, int64_t slice_len, int64_t nslices, int64_t v_base,
+                                 double *Y, int64_t ldY, cudaStream_t st);
+
 cudaError_t launch_lm_fit(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st,
                           LmLaunchInfo *info);
 

@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <type_traits>
 
@@ -111,6 +112,26 @@ __device__ __forceinline__ void load_convert_smem(const T *p, double (&y)[VPT], 
 
 // value of one sample as the reference's doubles: separate multiply and add (never an FMA)
 __device__ __forceinline__ double descale(double t, double sc, double of) { return __dadd_rn(__dmul_rn(t, sc), of); }
+
+// Stored samples -> the doubles of the reference's reader, written to a resident V x n matrix (the permutation test
+// re-reads Y for every batch of permutations, so it expands once instead of in every pass).  One sample per thread:
+// the kernel moves 2-4 + 8 bytes per sample once per call and is nowhere near the critical path.
+template <typename T>
+__global__ void __launch_bounds__(256)
+expand_stored_kernel(const T *__restrict__ U, int64_t V, int64_t ldU, const double *__restrict__ scale,
+                     const double *__restrict__ offset, double cmagic, int64_t slice_len, int64_t nslices, int64_t v_base,
+                     double *__restrict__ Y, int64_t ldY)
+{
+    const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int j = blockIdx.y;
+    if (v >= V) return;
+    double t = Stored<T>::load1(U + (int64_t)j * ldU + v, cmagic);
+    if (Stored<T>::kScaled) {
+        const int64_t sl = min((v_base + v) / slice_len, nslices - 1);
+        t = descale(t, __ldg(scale + sl + (int64_t)j * nslices), __ldg(offset + sl + (int64_t)j * nslices));
+    }
+    Y[(int64_t)j * ldY + v] = t;
+}
 
 template <int KP, typename T>
 __device__ __noinline__ double2 exact_pass_packed(const T *__restrict__ u, int64_t ld, int n, const double *__restrict__ Qt,
@@ -605,6 +626,25 @@ cudaError_t launch_packed_kp(const PackedArgs &a, const LmPlan &plan, LmScratch 
 }
 
 }  // namespace
+
+cudaError_t launch_expand_stored(const void *U, int dtype, int64_t V, int64_t ldU, int n, const double *scale,
+                                 const double *offset, double cmagic, int64_t slice_len, int64_t nslices, int64_t v_base,
+                                 double *Y, int64_t ldY, cudaStream_t st)
+{
+    if (V <= 0 || n <= 0) return cudaSuccess;
+    const int64_t blocks = (V + 255) / 256;
+    if (blocks > 0x7fffffffLL || n > 65535) return cudaErrorInvalidValue;
+    const dim3 grid((unsigned)blocks, (unsigned)n);
+    if (dtype == kStoredU16)
+        expand_stored_kernel<uint16_t><<<grid, 256, 0, st>>>(static_cast<const uint16_t *>(U), V, ldU, scale, offset, cmagic,
+                                                             std::max<int64_t>(slice_len, 1), std::max<int64_t>(nslices, 1),
+                                                             v_base, Y, ldY);
+    else if (dtype == kStoredF32)
+        expand_stored_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(U), V, ldU, nullptr, nullptr, 0.0, 1, 1, 0, Y, ldY);
+    else
+        return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
 
 cudaError_t launch_lm_packed(const PackedArgs &a_in, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
 {

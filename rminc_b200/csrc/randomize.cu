@@ -157,51 +157,41 @@ PermPath perm_path_from_env()
     return PermPath::Auto;
 }
 
-}  // namespace
-}  // namespace rmg
-
-using namespace rmg;
-
-extern "C" {
-
-int rmg_randomize_device(const double *dY, int64_t V, int64_t ldY, int n, const double *X, int p,
-                         const double *dmask, double mask_lo, double mask_hi, const int32_t *idx, int R,
-                         const int32_t *cols, int ncols, int two_sided, double *ddist, int device, void *stream,
-                         char *err, size_t errlen)
+// keys[s][i], s < nsets: element-wise max over the sets, decoded to doubles (the voxel blocks of one call each reduce
+// into a set of their own because the GEMM path finalises its keys in place at the end of a block)
+__global__ void keys_merge_decode_kernel(const unsigned long long *keys, int nsets, double *dist, int n)
 {
-    int rc = check_fit_args(dY, V, ldY, n, X, p, dY, ldY, err, errlen);
-    if (rc) return rc;
-    if (R < 0 || ncols < 0 || (R > 0 && !idx) || (ncols > 0 && !cols) || (R > 0 && ncols > 0 && !ddist))
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long k = keys[i];
+    for (int s = 1; s < nsets; ++s) k = max(k, keys[(size_t)s * n + i]);
+    dist[i] = ordered_value(k);
+}
+
+int check_perm_args(int p, const int32_t *idx, int R, const int32_t *cols, int ncols, const void *dist, char *err, size_t errlen)
+{
+    if (R < 0 || ncols < 0 || (R > 0 && !idx) || (ncols > 0 && !cols) || (R > 0 && ncols > 0 && !dist))
         return fail(err, errlen, RMG_ERR_INVALID, "bad permutation arguments");
     for (int c = 0; c < ncols; ++c)
         if (cols[c] < 0 || cols[c] >= 2 * p + 3) return fail(err, errlen, RMG_ERR_INVALID, "cols[%d] out of range", c);
-    PermSet pd;
-    const auto t_f0 = std::chrono::steady_clock::now();
-    if ((rc = factor_permutations(X, n, p, idx, R, pd, err, errlen))) return rc;
-    if (std::getenv("RMG_TIMING"))
-        std::fprintf(stderr, "[rmg perm] %-28s %8.3f ms\n", "factor R designs",
-                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_f0).count());
-    if ((rc = select_device(device, err, errlen))) return rc;
-    if (R == 0 || ncols == 0) return RMG_OK;
+    return RMG_OK;
+}
 
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int nk = R * ncols;
-    unsigned long long *keys = nullptr;
-    int32_t *dcols = nullptr;
+// All R permutations of one RESIDENT block of voxels, reduced into keys[ncols][R] (which must hold key(-inf)).
+// Everything is queued on st; the host needs nothing of the block afterwards.
+int randomize_block(const PermSet &pd, const double *dY, int64_t V, int64_t ldY, int n, int p, const double *dmask,
+                    double mask_lo, double mask_hi, const int32_t *cols, const int32_t *dcols, int ncols, int two_sided,
+                    unsigned long long *keys, int R, int sm_count, cudaStream_t st, int64_t &launches, char *err,
+                    size_t errlen)
+{
+    int rc = RMG_OK;
     double *scratch = nullptr;
     void *gemm_ws = nullptr;
     LmScratch scr;
     LmPlan plan;
-    plan.sm_count = device_sm_count(device);
-    int64_t launches = 0;
+    plan.sm_count = sm_count;
     const PermPath path = perm_path_from_env();
     {
-        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&keys), (size_t)nk * sizeof(unsigned long long), st));
-        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dcols), (size_t)ncols * sizeof(int32_t), st));
-        RMG_CUDA(cudaMemcpyAsync(dcols, cols, (size_t)ncols * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        keys_init_kernel<<<(nk + 255) / 256, 256, 0, st>>>(keys, nk);
-        ++launches;
-
         bool done = false;
         if (path != PermPath::Refit && V > 0 && perm_gemm_supported(n, p, V, ldY, dY, cols, ncols)) {
             PermGemmArgs ga{dY, V, ldY, n, p, dmask, mask_lo, mask_hi, cols, ncols, two_sided, keys, R};
@@ -267,7 +257,54 @@ int rmg_randomize_device(const double *dY, int64_t V, int64_t ldY, int n, const 
                 goto cleanup;
             }
         }
-        keys_decode_kernel<<<(nk + 255) / 256, 256, 0, st>>>(keys, ddist, nk);
+    }
+cleanup:
+    if (scratch) cudaFreeAsync(scratch, st);
+    if (gemm_ws) cudaFreeAsync(gemm_ws, st);
+    scr.release(st);
+    if (rc != RMG_OK) cudaGetLastError();
+    return rc;
+}
+
+}  // namespace
+}  // namespace rmg
+
+using namespace rmg;
+
+extern "C" {
+
+int rmg_randomize_device(const double *dY, int64_t V, int64_t ldY, int n, const double *X, int p,
+                         const double *dmask, double mask_lo, double mask_hi, const int32_t *idx, int R,
+                         const int32_t *cols, int ncols, int two_sided, double *ddist, int device, void *stream,
+                         char *err, size_t errlen)
+{
+    int rc = check_fit_args(dY, V, ldY, n, X, p, dY, ldY, err, errlen);
+    if (rc) return rc;
+    if ((rc = check_perm_args(p, idx, R, cols, ncols, ddist, err, errlen))) return rc;
+    PermSet pd;
+    const auto t_f0 = std::chrono::steady_clock::now();
+    if ((rc = factor_permutations(X, n, p, idx, R, pd, err, errlen))) return rc;
+    if (std::getenv("RMG_TIMING"))
+        std::fprintf(stderr, "[rmg perm] %-28s %8.3f ms\n", "factor R designs",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_f0).count());
+    if ((rc = select_device(device, err, errlen))) return rc;
+    if (R == 0 || ncols == 0) return RMG_OK;
+
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nk = R * ncols;
+    unsigned long long *keys = nullptr;
+    int32_t *dcols = nullptr;
+    int64_t launches = 0;
+    {
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&keys), (size_t)nk * sizeof(unsigned long long), st));
+        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dcols), (size_t)ncols * sizeof(int32_t), st));
+        RMG_CUDA(cudaMemcpyAsync(dcols, cols, (size_t)ncols * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        keys_init_kernel<<<(nk + 255) / 256, 256, 0, st>>>(keys, nk);
+        ++launches;
+        if ((rc = randomize_block(pd, dY, V, ldY, n, p, dmask, mask_lo, mask_hi, cols, dcols, ncols, two_sided, keys, R,
+                                  device_sm_count(device), st, launches, err, errlen)))
+            goto cleanup;
+        keys_merge_decode_kernel<<<(nk + 255) / 256, 256, 0, st>>>(keys, 1, ddist, nk);
         ++launches;
         RMG_CUDA(cudaGetLastError());
     }
@@ -275,9 +312,6 @@ cleanup:
     g_launch_count += launches;
     if (keys) cudaFreeAsync(keys, st);
     if (dcols) cudaFreeAsync(dcols, st);
-    if (scratch) cudaFreeAsync(scratch, st);
-    if (gemm_ws) cudaFreeAsync(gemm_ws, st);
-    scr.release(st);
     if (rc != RMG_OK) cudaGetLastError();
     return rc;
 }
@@ -432,62 +466,183 @@ int rmg_randomize_tfce_multi(const double *Y, int64_t V, int64_t ldY, int n, con
     return RMG_OK;
 }
 
-int rmg_randomize(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
-                  double mask_lo, double mask_hi, const int32_t *idx, int R, const int32_t *cols, int ncols,
-                  int two_sided, double *dist, int device, char *err, size_t errlen)
+// mincRandomize on host data.  Y (doubles, or the volumes in their stored type) is uploaded ONCE, in voxel blocks on a
+// copy stream, and stays resident as doubles; every block runs all R permutations as soon as it has landed, so the
+// upload of block b+1 hides behind the tensor-core work of block b.  Pageable input (R's heap) goes through the pinned
+// staging ring.  Each block reduces into a key set of its own; the sets are max-merged at the end.
+static int randomize_host_impl(const void *Yv, const StoredSpec *pk, int64_t V, int64_t ldY, int n, const double *X, int p,
+                               const double *mask, double mask_lo, double mask_hi, const int32_t *idx, int R,
+                               const int32_t *cols, int ncols, int two_sided, double *dist, int device, char *err,
+                               size_t errlen)
 {
-    int rc = check_fit_args(Y, V, ldY, n, X, p, Y, ldY, err, errlen);
+    int rc = check_fit_args(Yv, V, ldY, n, X, p, Yv, ldY, err, errlen);
     if (rc) return rc;
-    if (R < 0 || ncols < 0 || (R > 0 && ncols > 0 && !dist)) return fail(err, errlen, RMG_ERR_INVALID, "bad permutation arguments");
+    if ((rc = check_perm_args(p, idx, R, cols, ncols, dist, err, errlen))) return rc;
     if ((rc = select_device(device, err, errlen))) return rc;
     if (R == 0 || ncols == 0) return RMG_OK;
-    // Y is staged once and stays resident for all R permutations.
-    const int64_t ldd = std::max<int64_t>(2, (V + 1) & ~int64_t(1));
-    double *dY = nullptr, *dM = nullptr, *dD = nullptr;
-    cudaStream_t st = nullptr;
+    PermSet pd;
+    if ((rc = factor_permutations(X, n, p, idx, R, pd, err, errlen))) return rc;
+
+    const size_t es = !pk ? sizeof(double) : pk->dtype == kStoredU16 ? 2 : 4;   // bytes per sample of the input
+    const char *Yb = static_cast<const char *>(Yv);
+    const int64_t ldd = std::max<int64_t>(8, (V + 7) & ~int64_t(7));
+    // voxel blocks: about an eighth of the volume, at least ~1 GiB of doubles (every block re-packs and re-uploads the
+    // permuted designs, ~5 ms of host work that hides behind the previous block), multiples of 1024 voxels
+    int64_t CV = std::max<int64_t>((V + 7) / 8, (int64_t)(1024.0 * 1024 * 1024 / (8.0 * n)));
+    CV = std::max<int64_t>(1024, ((CV + 1023) / 1024) * 1024);
+    if (const char *s = std::getenv("RMG_PERM_CHUNK_VOXELS")) CV = std::max<int64_t>(2, (std::atoll(s) / 2) * 2);
+    if (CV > V) CV = std::max<int64_t>(V, 1);
+    const int nchunks = (int)std::max<int64_t>(1, (V + CV - 1) / CV);
+    const int64_t slice_len = pk ? std::max<int64_t>(1, pk->slice_len) : 1;
+    const int64_t nslices = !pk ? 0 : pk->nslices_total > 0 ? pk->nslices_total : (V + slice_len - 1) / slice_len;
+    const int nk = R * ncols;
+    const int sm_count = device_sm_count(device);
+
+    double *dY = nullptr, *dM = nullptr, *dD = nullptr, *dScale = nullptr, *dOffset = nullptr;
+    char *dU = nullptr;
+    unsigned long long *keys = nullptr;
+    int32_t *dcols = nullptr;
+    cudaStream_t st = nullptr, up = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<cudaEvent_t> landed(nchunks, nullptr);
+    PinnedRing ring;
+    int64_t launches = 0;
     g_last_kernel_ms = 0.0;
+    const int forced_rows = std::getenv("RMG_STAGING_ROWS") ? std::atoi(std::getenv("RMG_STAGING_ROWS")) : 0;
+    const bool staged = V > 0 && !is_pinned_host(Yv) && !std::getenv("RMG_NO_STAGING") &&
+                        (forced_rows > 0 || (double)V * n * (double)es >= 256.0 * 1024 * 1024);
+    const int rows_per_slot = forced_rows > 0 ? std::min(forced_rows, n)
+        : (int)std::max<int64_t>(1, std::min<int64_t>(n, (128ll << 20) / ((int64_t)es * std::max<int64_t>(CV, 1))));
     {
         RMG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        RMG_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
         RMG_CUDA(cudaEventCreate(&e0));
         RMG_CUDA(cudaEventCreate(&e1));
+        if (staged) RMG_CUDA(ring.init((size_t)rows_per_slot * (size_t)CV * es));
         RMG_CUDA(cudaMalloc(&dY, (size_t)ldd * n * sizeof(double)));
-        RMG_CUDA(cudaMalloc(&dD, (size_t)R * ncols * sizeof(double)));
-        if (V > 0)
-            RMG_CUDA(cudaMemcpy2DAsync(dY, (size_t)ldd * 8, Y, (size_t)ldY * 8, (size_t)V * 8, (size_t)n,
-                                       cudaMemcpyHostToDevice, st));
+        RMG_CUDA(cudaMalloc(&dD, (size_t)nk * sizeof(double)));
+        RMG_CUDA(cudaMalloc(&keys, (size_t)nchunks * nk * sizeof(unsigned long long)));
+        RMG_CUDA(cudaMalloc(&dcols, (size_t)ncols * sizeof(int32_t)));
+        RMG_CUDA(cudaMemcpyAsync(dcols, cols, (size_t)ncols * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        keys_init_kernel<<<(nchunks * nk + 255) / 256, 256, 0, st>>>(keys, nchunks * nk);
+        ++launches;
+        if (pk) {
+            RMG_CUDA(cudaMalloc(&dU, (size_t)CV * n * es));          // one block of stored samples, rows of CV
+            if (pk->dtype == kStoredU16) {
+                const size_t cnt = (size_t)nslices * n * sizeof(double);
+                RMG_CUDA(cudaMalloc(&dScale, cnt));
+                RMG_CUDA(cudaMalloc(&dOffset, cnt));
+                RMG_CUDA(cudaMemcpyAsync(dScale, pk->scale, cnt, cudaMemcpyHostToDevice, up));
+                RMG_CUDA(cudaMemcpyAsync(dOffset, pk->offset, cnt, cudaMemcpyHostToDevice, up));
+            }
+        }
         if (mask && V > 0) {
             RMG_CUDA(cudaMalloc(&dM, (size_t)V * sizeof(double)));
-            RMG_CUDA(cudaMemcpyAsync(dM, mask, (size_t)V * 8, cudaMemcpyHostToDevice, st));
+            RMG_CUDA(cudaMemcpyAsync(dM, mask, (size_t)V * 8, cudaMemcpyHostToDevice, up));
         }
         RMG_CUDA(cudaEventRecord(e0, st));
-        rc = rmg_randomize_device(dY, V, ldd, n, X, p, mask ? dM : nullptr, mask_lo, mask_hi, idx, R, cols, ncols,
-                                  two_sided, dD, device, st, err, errlen);
-        if (rc) goto cleanup;
+        for (int c = 0; c < nchunks; ++c) {
+            const int64_t v0 = (int64_t)c * CV, cv = std::min(CV, V - v0);
+            if (cv > 0) {
+                // ---- the block's samples: host -> device on the copy stream (straight into Y for doubles)
+                char *dstdev = pk ? dU : reinterpret_cast<char *>(dY + v0);
+                const size_t dpitch = pk ? (size_t)CV * es : (size_t)ldd * 8;
+                if (!staged) {
+                    RMG_CUDA(cudaMemcpy2DAsync(dstdev, dpitch, Yb + (size_t)v0 * es, (size_t)ldY * es, (size_t)cv * es, (size_t)n,
+                                               cudaMemcpyHostToDevice, up));
+                } else {
+                    for (int r0 = 0; r0 < n; r0 += rows_per_slot) {
+                        const int rows = std::min(rows_per_slot, n - r0);
+                        int slot = 0;
+                        RMG_CUDA(ring.acquire(slot));
+                        char *dst = ring.buf[slot];
+                        const int64_t pieces = (int64_t)rows * 8;
+                        parallel_for((int)pieces, [&](int i0, int i1) {
+                            for (int i = i0; i < i1; ++i) {
+                                const int r = i / 8, part = i % 8;
+                                const int64_t a0 = cv * part / 8, a1 = cv * (part + 1) / 8;
+                                std::memcpy(dst + ((size_t)r * cv + a0) * es, Yb + ((size_t)v0 + (size_t)(r0 + r) * ldY + a0) * es,
+                                            (size_t)(a1 - a0) * es);
+                            }
+                        });
+                        RMG_CUDA(cudaMemcpy2DAsync(dstdev + (size_t)r0 * dpitch, dpitch, dst, (size_t)cv * es, (size_t)cv * es,
+                                                   (size_t)rows, cudaMemcpyHostToDevice, up));
+                        RMG_CUDA(cudaEventRecord(ring.done[slot], up));
+                        ring.busy[slot] = true;
+                    }
+                }
+                // stored samples become the reader's doubles on the copy stream too: stream order then protects the
+                // one staging block, and the expansion (~1 ms) is noise next to the block's transfer
+                if (pk) {
+                    RMG_CUDA(launch_expand_stored(dU, pk->dtype, cv, CV, n, dScale, dOffset, 4503599627370496.0 + pk->voxel_min,
+                                                  slice_len, nslices, pk->v_offset + v0, dY + v0, ldd, up));
+                    ++launches;
+                }
+            }
+            RMG_CUDA(cudaEventCreateWithFlags(&landed[c], cudaEventDisableTiming));
+            RMG_CUDA(cudaEventRecord(landed[c], up));
+            RMG_CUDA(cudaStreamWaitEvent(st, landed[c], 0));
+            // ---- all R permutations on the block
+            if ((rc = randomize_block(pd, dY + v0, cv, ldd, n, p, mask ? dM + v0 : nullptr, mask_lo, mask_hi, cols, dcols, ncols,
+                                      two_sided, keys + (size_t)c * nk, R, sm_count, st, launches, err, errlen)))
+                goto cleanup;
+        }
+        keys_merge_decode_kernel<<<(nk + 255) / 256, 256, 0, st>>>(keys, nchunks, dD, nk);
+        ++launches;
+        RMG_CUDA(cudaGetLastError());
         RMG_CUDA(cudaEventRecord(e1, st));
-        RMG_CUDA(cudaMemcpyAsync(dist, dD, (size_t)R * ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
+        RMG_CUDA(cudaMemcpyAsync(dist, dD, (size_t)nk * sizeof(double), cudaMemcpyDeviceToHost, st));
         RMG_CUDA(cudaStreamSynchronize(st));
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) g_last_kernel_ms = ms;
     }
 cleanup:
+    g_launch_count += launches;
+    if (up) cudaStreamSynchronize(up);
     if (st) cudaStreamSynchronize(st);
-    if (dY) cudaFree(dY);
-    if (dM) cudaFree(dM);
-    if (dD) cudaFree(dD);
+    {
+        void *all[] = {dY, dM, dD, dU, dScale, dOffset, keys, dcols};
+        for (void *x : all)
+            if (x) cudaFree(x);
+    }
+    for (auto e : landed)
+        if (e) cudaEventDestroy(e);
+    ring.release_all();
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
+    if (up) cudaStreamDestroy(up);
     if (st) cudaStreamDestroy(st);
     if (rc != RMG_OK) cudaGetLastError();
     return rc;
 }
 
-int rmg_randomize_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
-                        double mask_lo, double mask_hi, const int32_t *idx, int R, const int32_t *cols, int ncols,
-                        int two_sided, double *dist, int n_gpus, char *err, size_t errlen)
+int rmg_randomize(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
+                  double mask_lo, double mask_hi, const int32_t *idx, int R, const int32_t *cols, int ncols,
+                  int two_sided, double *dist, int device, char *err, size_t errlen)
 {
-    int rc = check_fit_args(Y, V, ldY, n, X, p, Y, ldY, err, errlen);
+    return randomize_host_impl(Y, nullptr, V, ldY, n, X, p, mask, mask_lo, mask_hi, idx, R, cols, ncols, two_sided, dist, device,
+                               err, errlen);
+}
+
+int rmg_randomize_stored(const void *U, int dtype, int64_t V, int64_t ldU, int n, const double *scale, const double *offset,
+                         double voxel_min, int64_t slice_len, const double *X, int p, const double *mask, double mask_lo,
+                         double mask_hi, const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided, double *dist,
+                         int device, char *err, size_t errlen)
+{
+    int rc = check_stored_args(dtype, scale, offset, voxel_min, slice_len, p, err, errlen);
     if (rc) return rc;
+    const StoredSpec pk{dtype, scale, offset, voxel_min, dtype == RMG_STORED_U16 ? slice_len : std::max<int64_t>(V, 1)};
+    return randomize_host_impl(U, &pk, V, ldU, n, X, p, mask, mask_lo, mask_hi, idx, R, cols, ncols, two_sided, dist, device, err,
+                               errlen);
+}
+
+}  // extern "C"
+
+// Voxel shards over devices 0..G-1, one host thread per GPU; the only exchange step of the path is an element-wise max
+// of the per-shard R x ncols maxima.  fn(g, v0, cv, part, err, errlen) runs voxels [v0, v0 + cv) on device g.
+template <class Fn>
+static int randomize_sharded(int64_t V, int R, int ncols, double *dist, int n_gpus, char *err, size_t errlen, Fn fn)
+{
     const int have = rmg_device_count();
     if (have <= 0) return fail(err, errlen, RMG_ERR_NO_DEVICE, "no CUDA device available; rminc_b200 has no CPU fallback");
     int G = n_gpus <= 0 ? have : n_gpus;
@@ -506,8 +661,7 @@ int rmg_randomize_multi(const double *Y, int64_t V, int64_t ldY, int n, const do
         th.emplace_back([&, g]() {
             const int64_t v0 = b[g], cv = b[g + 1] - b[g];
             if (cv <= 0) return;
-            rcs[g] = rmg_randomize(Y + v0, cv, ldY, n, X, p, mask ? mask + v0 : nullptr, mask_lo, mask_hi, idx, R, cols,
-                                   ncols, two_sided, part[g].data(), g, &msgs[g][0], msgs[g].size());
+            rcs[g] = fn(g, v0, cv, part[g].data(), &msgs[g][0], msgs[g].size());
             kms[g] = rmg_last_kernel_ms();
         });
     }
@@ -515,13 +669,49 @@ int rmg_randomize_multi(const double *Y, int64_t V, int64_t ldY, int n, const do
     g_last_kernel_ms = *std::max_element(kms.begin(), kms.end());
     for (int g = 0; g < G; ++g)
         if (rcs[g] != RMG_OK) return fail(err, errlen, rcs[g], "gpu %d: %s", g, msgs[g].c_str());
-    // the only exchange step of the path: an element-wise max over shards (R*ncols doubles)
     for (size_t i = 0; i < (size_t)R * ncols; ++i) {
         double m = -INFINITY;
         for (int g = 0; g < G; ++g) m = std::fmax(m, part[g][i]);
         dist[i] = m;
     }
     return RMG_OK;
+}
+
+extern "C" {
+
+int rmg_randomize_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
+                        double mask_lo, double mask_hi, const int32_t *idx, int R, const int32_t *cols, int ncols,
+                        int two_sided, double *dist, int n_gpus, char *err, size_t errlen)
+{
+    int rc = check_fit_args(Y, V, ldY, n, X, p, Y, ldY, err, errlen);
+    if (rc) return rc;
+    return randomize_sharded(V, R, ncols, dist, n_gpus, err, errlen,
+                             [&](int g, int64_t v0, int64_t cv, double *part, char *e, size_t el) {
+        return rmg_randomize(Y + v0, cv, ldY, n, X, p, mask ? mask + v0 : nullptr, mask_lo, mask_hi, idx, R, cols, ncols,
+                             two_sided, part, g, e, el);
+    });
+}
+
+int rmg_randomize_stored_multi(const void *U, int dtype, int64_t V, int64_t ldU, int n, const double *scale,
+                               const double *offset, double voxel_min, int64_t slice_len, const double *X, int p,
+                               const double *mask, double mask_lo, double mask_hi, const int32_t *idx, int R,
+                               const int32_t *cols, int ncols, int two_sided, double *dist, int n_gpus, char *err,
+                               size_t errlen)
+{
+    int rc = check_stored_args(dtype, scale, offset, voxel_min, slice_len, p, err, errlen);
+    if (rc) return rc;
+    if ((rc = check_fit_args(U, V, ldU, n, X, p, U, ldU, err, errlen))) return rc;
+    const size_t es = dtype == RMG_STORED_U16 ? 2 : 4;
+    const int64_t sl = dtype == RMG_STORED_U16 ? slice_len : std::max<int64_t>(V, 1);
+    const int64_t nslices_total = (V + sl - 1) / sl;
+    return randomize_sharded(V, R, ncols, dist, n_gpus, err, errlen,
+                             [&](int g, int64_t v0, int64_t cv, double *part, char *e, size_t el) {
+        StoredSpec pk{dtype, scale, offset, voxel_min, sl};
+        pk.v_offset = v0;                    // slices keep their global index
+        pk.nslices_total = nslices_total;
+        return randomize_host_impl(static_cast<const char *>(U) + (size_t)v0 * es, &pk, cv, ldU, n, X, p,
+                                   mask ? mask + v0 : nullptr, mask_lo, mask_hi, idx, R, cols, ncols, two_sided, part, g, e, el);
+    });
 }
 
 }  // extern "C"

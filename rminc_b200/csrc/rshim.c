@@ -14,6 +14,7 @@
  *   rmincgpu_lm_cov          the same with filenames_right (a voxel-wise covariate) staged as a second matrix
  *   rmincgpu_lm_stored       the same on volumes in their stored type (uint16 + real ranges, float32)
  *   rmincgpu_randomize       the mincRandomize loop (R/minc_voxel_statistics.R:1465-1497)
+ *   rmincgpu_randomize_stored  the same on volumes in their stored type
  *   rmincgpu_graph_tfce      graph_tfce_wqu / graph_tfce (src/vertex_tfce.cpp:92-157), every column of a matrix at once
  *   rmincgpu_randomize_tfce  vertexTFCE.vertexLm's permutation loop (R/minc_vertex_statistics.R:892-948)
  *   rmincgpu_fdr             mincFDR's p-value + p.adjust(., "fdr") + threshold step for one column (R/minc_FDR.R:385-505)
@@ -186,6 +187,44 @@ SEXP rmincgpu_randomize(SEXP Y, SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP m
     return out;
 }
 
+/* The mincRandomize loop on volumes in their stored type (U, dtype .. slice_len as rmincgpu_lm_stored). */
+SEXP rmincgpu_randomize_stored(SEXP U, SEXP dtype, SEXP nvoxels, SEXP scale, SEXP offset, SEXP voxel_min, SEXP slice_len,
+                               SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP mask_upper, SEXP idx, SEXP columns,
+                               SEXP two_sided, SEXP ngpu)
+{
+    if (TYPEOF(U) != RAWSXP || !Rf_isReal(mmatrix) || !Rf_isInteger(idx) || !Rf_isInteger(columns))
+        Rf_error("U must be a raw vector, mmatrix double, idx/columns integer");
+    const int dt = Rf_asInteger(dtype);
+    const size_t es = dt == RMG_STORED_U16 ? 2 : 4;
+    const R_xlen_t V = (R_xlen_t)Rf_asReal(nvoxels);
+    const int n = Rf_nrows(mmatrix), p = Rf_ncols(mmatrix), R = Rf_ncols(idx), nc = LENGTH(columns);
+    if ((R_xlen_t)(XLENGTH(U) / es) != V * n) Rf_error("U holds %.0f samples, expected %.0f", (double)(XLENGTH(U) / es), (double)V * n);
+    if (Rf_nrows(idx) != n) Rf_error("idx must have one row per subject");
+    const int scaled = dt == RMG_STORED_U16;
+    if (scaled && (!Rf_isReal(scale) || !Rf_isReal(offset) || Rf_ncols(scale) != n || Rf_ncols(offset) != n))
+        Rf_error("scale and offset must be nslices x n double matrices");
+    const double *m = mask_or_null(mask, V);
+    int *idx0 = (int *)R_alloc((size_t)n * R, sizeof(int));
+    int *col0 = (int *)R_alloc((size_t)nc, sizeof(int));
+    for (R_xlen_t i = 0; i < (R_xlen_t)n * R; ++i) idx0[i] = INTEGER(idx)[i] - 1;
+    for (int i = 0; i < nc; ++i) col0[i] = INTEGER(columns)[i] - 1;
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, R, nc));
+    char err[512] = "";
+    const int G = Rf_asInteger(ngpu);
+    const double *sc = scaled ? REAL(scale) : NULL, *of = scaled ? REAL(offset) : NULL;
+    int rc = G > 1 ? rmg_randomize_stored_multi(RAW(U), dt, V, V > 0 ? V : 1, n, sc, of, Rf_asReal(voxel_min),
+                                                (int64_t)Rf_asReal(slice_len), REAL(mmatrix), p, m, Rf_asReal(mask_lower),
+                                                Rf_asReal(mask_upper), idx0, R, col0, nc, Rf_asLogical(two_sided), REAL(out),
+                                                G, err, sizeof err)
+                   : rmg_randomize_stored(RAW(U), dt, V, V > 0 ? V : 1, n, sc, of, Rf_asReal(voxel_min),
+                                          (int64_t)Rf_asReal(slice_len), REAL(mmatrix), p, m, Rf_asReal(mask_lower),
+                                          Rf_asReal(mask_upper), idx0, R, col0, nc, Rf_asLogical(two_sided), REAL(out), 0,
+                                          err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
 /* per_voxel_anova / vertex_anova_loop replacement: V x max(asgn) F-statistics. */
 SEXP rmincgpu_anova(SEXP Y, SEXP mmatrix, SEXP asgn, SEXP mask, SEXP mask_lower, SEXP mask_upper)
 {
@@ -297,6 +336,7 @@ static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_lm_cov", (DL_FUNC)&rmincgpu_lm_cov, 6},
     {"rmincgpu_lm_stored", (DL_FUNC)&rmincgpu_lm_stored, 11},
     {"rmincgpu_randomize", (DL_FUNC)&rmincgpu_randomize, 9},
+    {"rmincgpu_randomize_stored", (DL_FUNC)&rmincgpu_randomize_stored, 15},
     {"rmincgpu_anova", (DL_FUNC)&rmincgpu_anova, 6},
     {"rmincgpu_fdr", (DL_FUNC)&rmincgpu_fdr, 4},
     {"rmincgpu_graph_tfce", (DL_FUNC)&rmincgpu_graph_tfce, 7},

@@ -59,6 +59,12 @@ def api(request, monkeypatch, oracle, lib):
             return tfce_randomize_oracle(oracle, np.asfortranarray(Y), X, np.asarray(idx), list(cols), adjacency,
                                          two_sided=two_sided, E=E, H=H, nsteps=nsteps, side=side, weights=weights)
 
+        def randomize_stored(U, X, idx, cols, scale=None, offset=None, voxel_min=0.0, slice_len=None, two_sided=True,
+                             mask=None, mask_lo=1.0, mask_hi=99999999.0, device=0, n_gpus=None):
+            Y = oracle.expand_stored(U, scale, offset, voxel_min=voxel_min, slice_len=slice_len)
+            return oracle.randomize(Y, X, idx, cols, two_sided=two_sided, mask=mask, lo=mask_lo, hi=mask_hi)
+
+        monkeypatch.setattr(core, "randomize_stored", randomize_stored)
         monkeypatch.setattr(core, "graph_tfce", graph_tfce)
         monkeypatch.setattr(core, "randomize_tfce", randomize_tfce)
         monkeypatch.setattr(core, "fdr", fdr)
@@ -347,6 +353,14 @@ def test_mincLm_on_stored_volumes(api, study):
     v = int(np.flatnonzero(inside)[17])
     check_row(vs, v, Yq[v], X, ["(Intercept)", "SexM", "Scale"])
     assert (np.asarray(vs)[~inside] == 0).all()
+    # the permutation test of a stored-type fit runs on the stored voxels too, and equals the test on the doubles
+    idx = api.draw_indices(10, 12, seed=5)
+    rs = api.mincRandomize(vs, R=12, idx=idx)
+    from rminc_b200 import core
+    m = np.load(maskfile).reshape(-1).astype(float)
+    tcols = [i for i, c in enumerate(vs.colnames) if c.startswith("tvalue-")]
+    np.testing.assert_allclose(np.asarray(rs["randomization_dist"]), core.randomize(Yq, X, idx, tcols, mask=m), rtol=1e-9)
+    assert api.thresholds(rs).shape == (4, 3)
     # float32 volumes need no range tables
     f32 = {f: api.StoredVolume(np.load(f).astype(np.float32)) for f in gf.jacobians}
     v32 = api.mincLm("jacobians ~ Sex", gf, reader=lambda item: f32[item])

@@ -254,6 +254,73 @@ def test_randomize_gemm_equals_refit_on_larger_case(core, monkeypatch):
     np.testing.assert_allclose(b, a, rtol=1e-10)
 
 
+def test_randomize_voxel_blocks_and_staging_ring(core, oracle, monkeypatch):
+    """rmg_randomize uploads Y in voxel blocks and runs every block's permutations as it lands; pageable input goes
+    through the pinned staging ring.  Block boundaries (incl. an odd tail that takes the refit path) change nothing."""
+    Y, X, mask = cfg1_data(dims=(16, 20, 13))           # V = 4160
+    Y = np.asfortranarray(Y[:4159])                     # odd V: the last block is odd
+    mask = mask[:4159]
+    n = X.shape[0]
+    idx = perm_indices(n, 33)
+    cols = [4, 5]
+    want = oracle.randomize(Y, X, idx, cols, two_sided=True, mask=mask)
+    for chunk, rows in (("1024", None), ("700", "3"), ("2048", "20"), ("100000", None)):
+        monkeypatch.setenv("RMG_PERM_CHUNK_VOXELS", chunk)
+        if rows:
+            monkeypatch.setenv("RMG_STAGING_ROWS", rows)
+        else:
+            monkeypatch.delenv("RMG_STAGING_ROWS", raising=False)
+        got = core.randomize(Y, X, idx, cols, two_sided=True, mask=mask)
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=0, err_msg=f"chunk={chunk} rows={rows}")
+    got = core.randomize(Y, X, idx, cols, two_sided=False, mask=None)
+    np.testing.assert_allclose(got, oracle.randomize(Y, X, idx, cols, two_sided=False, mask=None), rtol=RTOL)
+    # a sub-matrix (ldY > V) as input
+    monkeypatch.setenv("RMG_PERM_CHUNK_VOXELS", "1500")
+    import ctypes
+    from rminc_b200 import _lib
+    Yb = np.asfortranarray(np.vstack([Y, np.full((77, n), 9.0)]))
+    dist = np.empty((33, 2), order="F")
+    ix = np.asfortranarray(idx, dtype=np.int32)
+    cc = np.asarray(cols, dtype=np.int32)
+    Xf = np.asfortranarray(X)
+    err = _lib.errbuf()
+    rc = _lib.load().rmg_randomize(Yb.ctypes.data, 4159, Yb.shape[0], n, Xf.ctypes.data, X.shape[1], mask.ctypes.data, 0.5,
+                                   99999999.5, ix.ctypes.data, 33, cc.ctypes.data, 2, 1, dist.ctypes.data, 0, err, len(err))
+    assert rc == 0, err.value
+    np.testing.assert_allclose(dist, want, rtol=RTOL)
+
+
+def test_randomize_on_stored_volumes(core, oracle, monkeypatch):
+    """rmg_randomize_stored: uint16 / float32 samples expanded once on the device == randomize on the reader's doubles."""
+    U, X, scale, offset = _stored_case(5000, 48, 1000, seed=8)
+    V, n = U.shape
+    Y = oracle.expand_stored(U, scale, offset, voxel_min=100.0, slice_len=1000)
+    mask = (np.arange(V) % 5 > 0).astype(float)
+    idx = perm_indices(n, 21)
+    p = X.shape[1]
+    cols = list(range(p + 2, 2 * p + 2))
+    want = oracle.randomize(Y, X, idx, cols, two_sided=True, mask=mask)
+    for chunk, rows in ((None, None), ("1400", None), ("1024", "5")):
+        for k, v in (("RMG_PERM_CHUNK_VOXELS", chunk), ("RMG_STAGING_ROWS", rows)):
+            if v:
+                monkeypatch.setenv(k, v)
+            else:
+                monkeypatch.delenv(k, raising=False)
+        got = core.randomize_stored(U, X, idx, cols, scale=scale, offset=offset, voxel_min=100.0, slice_len=1000, mask=mask)
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=0, err_msg=f"chunk={chunk} rows={rows}")
+        # and exactly what the double path gives on the expanded matrix (same doubles, same kernels)
+        np.testing.assert_array_equal(got, core.randomize(Y, X, idx, cols, mask=mask))
+    got2 = core.randomize_stored(U, X, idx, cols, scale=scale, offset=offset, voxel_min=100.0, slice_len=1000, mask=mask,
+                                 n_gpus=1)
+    np.testing.assert_allclose(got2, want, rtol=RTOL)
+    F = np.asfortranarray(np.random.default_rng(4).normal(0, 0.2, (3000, 48)).astype(np.float32))
+    monkeypatch.setenv("RMG_PERM_CHUNK_VOXELS", "1024")
+    np.testing.assert_allclose(core.randomize_stored(F, X, idx, cols, two_sided=False),
+                               oracle.randomize(F.astype(np.float64), X, idx, cols, two_sided=False), rtol=RTOL)
+    with pytest.raises(core.RmincGpuError, match="voxel_min must be an integer"):
+        core.randomize_stored(U, X, idx, cols, scale=scale, offset=offset, voxel_min=0.5, slice_len=1000)
+
+
 def test_randomize_device_entry_point(core, oracle):
     import torch
     Y, X, mask = cfg1_data(dims=(12, 16, 10))
