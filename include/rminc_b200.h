@@ -270,6 +270,39 @@ int rmg_randomize_tfce_multi(const double *Y, int64_t V, int64_t ldY, int n, con
                              double E, double H, int nsteps, int side, double *dist, int n_gpus, char *err, size_t errlen);
 
 /*
+ * RMINC:::neighbour_list(x, y, z, n) (src/vertex_tfce.cpp:178-214): the adjacency of a regular grid in CSR form, vertex
+ * = k*y*x + j*x + i (first argument fastest), n = 6, 18 or 26.  Host only (no GPU needed).  Call with adj_ptr = adj_idx
+ * = NULL to get the number of entries in *nnz, then with adj_ptr[x*y*z + 1] and adj_idx[capacity >= nnz].
+ */
+int rmg_neighbour_list(int x, int y, int z, int n, int32_t *adj_ptr, int32_t *adj_idx, int64_t capacity, int64_t *nnz,
+                       char *err, size_t errlen);
+
+/*
+ * mincTFCE on volumes.  The reference writes the map to a file and shells out to the external `TFCE` program of
+ * minc-stuffs (mincTFCE.mincSingleDim, R/minc_voxel_statistics.R:1186-1243), which is NOT in the reference tree; the
+ * enhancement here is the tree's own algorithm (graph_tfce, src/vertex_tfce.cpp:92-157) run on the voxel grid, with the
+ * arguments mincTFCE passes on: height step d (instead of nsteps: thresholds d, 2d, ... up to the map maximum), E, H
+ * and the side.  Parity with the external program is therefore unpinned.
+ *   maps      V x nmaps, V = dims[0]*dims[1]*dims[2], row = v0*dims[1]*dims[2] + v1*dims[2] + v2 (mincLm's row order)
+ *   connectivity  6 (faces), 18 or 26;  voxel_volume  the extent of one voxel (cluster extent = voxels * volume)
+ *   side      0 "both", 1 "positive", 2 "negative"
+ * At most 253 thresholds per map (RMG_ERR_INVALID otherwise: increase d).
+ */
+int rmg_volume_tfce(const double *maps, const int64_t *dims, int nmaps, int connectivity, double voxel_volume,
+                    double d, double E, double H, int side, double *out, int device, char *err, size_t errlen);
+/*
+ * mincTFCE.mincLm's permutation test (R/minc_voxel_statistics.R:1382-1439 -> mincRandomize_core with
+ * post_proc = mincTFCE.matrix): per permutation refit (masked voxels 0), non-finite -> 0, volume TFCE of every column in
+ * `cols`, abs when two_sided, column maximum.  dist: R x ncols.  n_gpus > 1 splits the R permutations into contiguous
+ * blocks over devices 0..n_gpus-1 (one host thread per GPU, no exchange); otherwise device 0.
+ */
+int rmg_randomize_volume_tfce(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p,
+                              const double *mask, double mask_lo, double mask_hi,
+                              const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
+                              const int64_t *dims, int connectivity, double voxel_volume,
+                              double d, double E, double H, int side, double *dist, int n_gpus, char *err, size_t errlen);
+
+/*
  * Device-resident variant: dY/dmask on `device`; ddist is a device R x ncols matrix that
  * receives this device's maxima over ITS voxels (voxel shards on several GPUs are combined by
  * the caller with an element-wise max, e.g. ncclAllReduce(ncclMax)).  Enqueued on `stream`.

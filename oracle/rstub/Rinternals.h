@@ -35,6 +35,7 @@ SEXP STRING_ELT(SEXP s, R_xlen_t i);
 const char *CHAR(SEXP s);
 SEXP Rf_install(const char *name);
 int Rf_isReal(SEXP s);
+int Rf_isMatrix(SEXP s);
 int Rf_isInteger(SEXP s);
 int Rf_asInteger(SEXP s);
 int Rf_asLogical(SEXP s);

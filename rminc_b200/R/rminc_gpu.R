@@ -154,3 +154,55 @@ vertexTFCE_randomize_gpu <- function(lmod, adjacencies, R = 500, alternative = c
   colnames(dist) <- colnames(lmod)[columns]
   dist
 }
+
+
+# mincTFCE without the temporary files and the external TFCE program (R/minc_voxel_statistics.R:1186-1283): the tree's
+# graph TFCE on the voxel grid.  x: a mincSingleDim vector or a matrix with a likeVolume; NA / NaN -> 0 as
+# mincTFCE.matrix does.
+mincTFCE_gpu <- function(x, d = 0.1, E = .5, H = 2.0, side = c("both", "positive", "negative"),
+                         like_volume = likeVolume(x), connectivity = 6L) {
+  side <- match(match.arg(side), c("both", "positive", "negative")) - 1L
+  sizes <- minc.dimensions.sizes(like_volume)
+  vv <- prod(abs(minc.separation.sizes(like_volume)))
+  vals <- unclass(x); vals[!is.finite(vals) & is.na(vals)] <- 0
+  run <- function(m, step) .Call("rmincgpu_volume_tfce", m, as.double(sizes), as.integer(connectivity), as.double(vv),
+                                 as.double(step), as.double(E), as.double(H), side, PACKAGE = "rmincgpu")
+  if (is.matrix(vals) && length(d) > 1) {
+    out <- mapply(function(j, step) run(as.double(vals[, j]), step), seq_len(ncol(vals)), d)
+  } else {
+    storage.mode(vals) <- "double"
+    out <- run(vals, d[1])
+  }
+  if (is.matrix(vals)) colnames(out) <- colnames(x)
+  likeVolume(out) <- like_volume
+  out
+}
+
+# mincTFCE.mincLm (:1382-1439): enhanced t columns + the null of their maxima, all R permutations in one call.
+mincTFCE_mincLm_gpu <- function(lmod, R = 500, alternative = c("two.sided", "greater"), d = 0.1, E = .5, H = 2.0,
+                                side = c("both", "positive", "negative"), replace = FALSE, parallel = NULL,
+                                connectivity = 6L) {
+  alternative <- match.arg(alternative); side_name <- match.arg(side)
+  side <- match(side_name, c("both", "positive", "negative")) - 1L
+  columns <- grep("tvalue-", colnames(lmod))
+  like_vol <- likeVolume(lmod)
+  original <- mincTFCE_gpu(lmod[, columns], d = d, E = E, H = H, side = side_name, like_volume = like_vol,
+                           connectivity = connectivity)
+  n <- nrow(attr(lmod, "data"))
+  idx <- vapply(seq_len(R), function(i) sample(seq_len(n), replace = replace), integer(n))
+  Y <- rmincgpu_stage(attr(lmod, "filenames"))
+  cl <- attr(lmod, "call")
+  mask <- eval(cl$mask, parent.frame()); maskval <- eval(cl$maskval, parent.frame())
+  m <- if (is.null(mask)) NULL else as.double(mincGetVolume(mask))
+  lo <- if (is.null(maskval)) 1 else maskval
+  hi <- if (is.null(maskval)) 99999999 else maskval
+  dist <- .Call("rmincgpu_randomize_volume_tfce", Y, attr(lmod, "model"), m, as.double(lo), as.double(hi), idx,
+                as.integer(columns), alternative == "two.sided", as.double(minc.dimensions.sizes(like_vol)),
+                as.integer(connectivity), as.double(prod(abs(minc.separation.sizes(like_vol)))), as.double(d),
+                as.double(E), as.double(H), side, rmincgpu_n(parallel), PACKAGE = "rmincgpu")
+  colnames(dist) <- colnames(lmod)[columns]
+  structure(list(tfce = original, randomization_dist = dist,
+                 args = list(call = cl, side = side_name, alternative = alternative)),
+            class = c("mincTFCE_randomization", "minc_randomization"))
+}
+

@@ -574,6 +574,85 @@ def vertexTFCE(x, surface, R: int = 500, alternative: str = "two.sided", E: floa
 
 
 # ----------------------------------------------------------------------------- mincRandomize
+# ----------------------------------------------------------------------------- mincTFCE
+def volume_dims(like) -> tuple:
+    """Dimensions (file order) of a like-volume: a 3-tuple, a 3-D array, or a '.npy' path (likeVolume(x) in R is a MINC
+    file whose header carries the sizes)."""
+    if isinstance(like, (tuple, list)) and len(like) == 3 and all(isinstance(v, (int, np.integer)) for v in like):
+        return tuple(int(v) for v in like)
+    if isinstance(like, StoredVolume):
+        like = like.voxels
+    if isinstance(like, np.ndarray) and like.ndim == 3:
+        return tuple(int(v) for v in like.shape)
+    if isinstance(like, (str, os.PathLike)) and os.fspath(like).endswith(".npy") and os.path.exists(os.fspath(like)):
+        shp = np.load(os.fspath(like), mmap_mode="r").shape
+        if len(shp) == 3:
+            return tuple(int(v) for v in shp)
+    raise ValueError("like_volume must give three dimensions: a 3-tuple, a 3-D array or a .npy volume")
+
+
+def mincTFCE(x, d=0.1, E: float = 0.5, H: float = 2.0, side: str = "both", like_volume=None, R: int = 500,
+             alternative: str = "two.sided", replace: bool = False, parallel=None, seed=None, idx=None,
+             connectivity: int = 6, voxel_volume: float = 1.0, device: int = 0):
+    """Threshold-free cluster enhancement of volumes (R/minc_voxel_statistics.R:1186-1439).  Dispatch as in the
+    reference:
+      * numeric vector (mincSingleDim) -> enhanced vector
+      * matrix / mincMultiDim -> every column enhanced (NA / NaN -> 0 first; `d` may hold one step per column)
+      * mincLm result -> permutation test on every tvalue- column: list(tfce, randomization_dist, args) of class
+        c("mincTFCE_randomization","minc_randomization") (mincTFCE.mincLm).
+    The reference hands each volume to the external `TFCE` program of minc-stuffs; here the tree's own graph TFCE runs on
+    the voxel grid (see rmg_volume_tfce): `connectivity` 6 and `voxel_volume` = the product of the step sizes reproduce
+    what vertexTFCE(x, neighbour_list(.., 6), weights = voxel volume) gives (tests/testthat/test_mincTFCE.R:153-170)."""
+    if side not in core.TFCE_SIDES:
+        raise ValueError("'arg' should be one of 'both', 'positive', 'negative'")
+    if isinstance(x, MincMatrix) and "mincLm" in x.r_class:
+        if alternative not in ("two.sided", "greater"):
+            raise ValueError("'arg' should be one of 'two.sided', 'greater'")
+        if "_Y" not in x.attrs:
+            raise TypeError("x must be the result of mincLm on double volumes")
+        if np.ndim(d) != 0:
+            raise ValueError("the permutation test takes one height step d")
+        dims = volume_dims(x.attrs["likeVolume"] if like_volume is None else like_volume)
+        columns = [i for i, c in enumerate(x.colnames) if c.startswith("tvalue-")]
+        names = [x.colnames[c] for c in columns]
+        X = x.attrs["model"]
+        n = X.shape[0]
+        stats = np.nan_to_num(np.asarray(x)[:, columns], nan=0.0, posinf=np.inf, neginf=-np.inf)
+        original = core.volume_tfce(stats, dims, d=d, E=E, H=H, side=side, connectivity=connectivity,
+                                    voxel_volume=voxel_volume, device=device)
+        if idx is None:
+            idx = draw_indices(n, R, replace=replace, seed=seed)
+        idx = np.asarray(idx, dtype=np.int32)
+        if idx.shape != (n, R):
+            raise ValueError("idx must be n x R")
+        lo, hi = x.attrs["_mask_range"]
+        dist = core.randomize_volume_tfce(x.attrs["_Y"], X, idx, columns, dims, two_sided=(alternative == "two.sided"), d=d,
+                                          E=E, H=H, side=side, connectivity=connectivity, voxel_volume=voxel_volume,
+                                          mask=x.attrs["_mask"], mask_lo=lo, mask_hi=hi,
+                                          n_gpus=int(parallel[1]) if parallel is not None else None)
+        out = MincRandomization(tfce=MincMatrix(original, colnames=names, attrs={"likeVolume": x.attrs.get("likeVolume")}),
+                                randomization_dist=MincMatrix(dist, colnames=names),
+                                args=dict(call=x.attrs.get("call"), side=side, alternative=alternative))
+        out.r_class = ("mincTFCE_randomization", "minc_randomization")
+        return out
+    if like_volume is None and isinstance(x, MincMatrix):
+        like_volume = x.attrs.get("likeVolume")
+    A = np.asarray(x, dtype=np.float64)
+    if A.ndim == 3 and like_volume is None:
+        like_volume, A = A.shape, A.reshape(-1)
+    dims = volume_dims(like_volume)
+    A = np.nan_to_num(A, nan=0.0, posinf=np.inf, neginf=-np.inf)                    # setNA(0) %>% setNaN(0)
+    kw = dict(E=E, H=H, side=side, connectivity=connectivity, voxel_volume=voxel_volume, device=device)
+    if A.ndim == 2 and np.ndim(d) != 0:
+        steps = np.resize(np.asarray(d, dtype=np.float64), A.shape[1])              # mapply recycles d over the columns
+        res = np.column_stack([core.volume_tfce(A[:, j], dims, d=float(steps[j]), **kw) for j in range(A.shape[1])])
+    else:
+        res = core.volume_tfce(A, dims, d=float(np.asarray(d).reshape(-1)[0]), **kw)
+    if A.ndim == 2:
+        return MincMatrix(res, colnames=getattr(x, "colnames", None), attrs={"likeVolume": like_volume})
+    return res
+
+
 class MincRandomization(dict):
     """list(stats, randomization_dist, args) of class c("mincLm_randomization","minc_randomization")."""
     r_class = ("mincLm_randomization", "minc_randomization")

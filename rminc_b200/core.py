@@ -361,6 +361,66 @@ def randomize_tfce(Y, X, idx, cols, adjacency, two_sided=True, E=0.5, H=2.0, nst
     return dist
 
 
+def neighbour_list(x, y, z, n=6):
+    """RMINC:::neighbour_list (src/vertex_tfce.cpp:178-214) as a CSR pair (ptr, idx) that vertexTFCE / graph_tfce take:
+    the adjacency of an x*y*z grid, vertex = k*y*x + j*x + i.  Host only."""
+    import ctypes as C
+    lib = _lib.load()
+    err = _lib.errbuf()
+    nnz = C.c_int64(0)
+    _lib.check(lib.rmg_neighbour_list(int(x), int(y), int(z), int(n), None, None, 0, C.byref(nnz), err, len(err)), err)
+    ptr = np.empty(int(x) * int(y) * int(z) + 1, dtype=np.int32)
+    idx = np.empty(max(nnz.value, 1), dtype=np.int32)
+    _lib.check(lib.rmg_neighbour_list(int(x), int(y), int(z), int(n), ptr.ctypes.data, idx.ctypes.data, nnz.value,
+                                      C.byref(nnz), err, len(err)), err)
+    return ptr, idx[:nnz.value]
+
+
+def _dims3(dims, V=None):
+    d = np.ascontiguousarray(dims, dtype=np.int64).reshape(-1)
+    if d.size != 3 or (d < 1).any():
+        raise ValueError("dims must be three positive sizes (file dimension order)")
+    if V is not None and int(d.prod()) != V:
+        raise ValueError(f"dims {tuple(int(x) for x in d)} do not match {V} voxels")
+    return d
+
+
+def volume_tfce(maps, dims, d=0.1, E=0.5, H=2.0, side="both", connectivity=6, voxel_volume=1.0, device=0):
+    """mincTFCE's native step: maps is V or V x nmaps (V = prod(dims), file dimension order); returns the same shape.
+    The tree's graph TFCE on the voxel grid with the height step d (rmg_volume_tfce)."""
+    M = np.asarray(maps, dtype=np.float64)
+    one = M.ndim == 1
+    M = np.asfortranarray(M.reshape(-1, 1) if one else M)
+    V, nmaps = M.shape
+    dd = _dims3(dims, V)
+    out = np.empty((V, nmaps), order="F")
+    err = _lib.errbuf()
+    rc = _lib.load().rmg_volume_tfce(M.ctypes.data, dd.ctypes.data, nmaps, int(connectivity), float(voxel_volume), float(d),
+                                     float(E), float(H), TFCE_SIDES[side], out.ctypes.data, device, err, len(err))
+    _lib.check(rc, err)
+    return out[:, 0] if one else out
+
+
+def randomize_volume_tfce(Y, X, idx, cols, dims, two_sided=True, d=0.1, E=0.5, H=2.0, side="both", connectivity=6,
+                          voxel_volume=1.0, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, n_gpus=None):
+    """mincTFCE.mincLm's permutation loop: R x len(cols) maxima of the enhanced statistic volumes."""
+    Y, X, m = _prep_host(Y, X, mask)
+    V, n = Y.shape
+    p = X.shape[1]
+    idx, cols = _prep_perm(idx, n, cols)
+    dd = _dims3(dims, V)
+    R = idx.shape[1]
+    dist = np.empty((R, len(cols)), order="F")
+    err = _lib.errbuf()
+    rc = _lib.load().rmg_randomize_volume_tfce(
+        Y.ctypes.data, V, max(V, 1), n, X.ctypes.data, p, m.ctypes.data if m is not None else None, mask_lo, mask_hi,
+        idx.ctypes.data, R, cols.ctypes.data, len(cols), int(bool(two_sided)), dd.ctypes.data, int(connectivity),
+        float(voxel_volume), float(d), float(E), float(H), TFCE_SIDES[side], dist.ctypes.data,
+        int(n_gpus) if n_gpus is not None else 1, err, len(err))
+    _lib.check(rc, err)
+    return dist
+
+
 def vertex_wlm(Y, X, weights, device=0):
     """anatLm(weights=)'s native step (vertex_wlm_loop, src/weighted_least_squares.c:168)."""
     Y, X, _ = _prep_host(Y, X, None)

@@ -319,11 +319,14 @@ cleanup:
 // vertexTFCE.vertexLm's randomisation (R/minc_vertex_statistics.R:892-948): mincRandomize_core with
 // post_proc = vertexTFCE.matrix -- per permutation refit, non-finite -> 0, graph TFCE of every requested column, abs when
 // two-sided, column maximum.  Batches of permutations are fitted into a map stack and enhanced together.
-int rmg_randomize_tfce(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *idx, int R,
-                       const int32_t *cols, int ncols, int two_sided, const int32_t *adj_ptr, const int32_t *adj_idx,
-                       const double *weights, double E, double H, int nsteps, int side, double *dist, int device, char *err,
-                       size_t errlen)
+// mask (nullable; volumes): masked voxels are 0 in every statistic map, as in mincLm's result.  step > 0: thresholds
+// from a fixed height increment (mincTFCE's d) instead of nsteps.
+static int randomize_tfce_impl(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
+                               double mask_lo, double mask_hi, const int32_t *idx, int R, const int32_t *cols, int ncols,
+                               int two_sided, const int32_t *adj_ptr, const int32_t *adj_idx, const double *weights, double E,
+                               double H, int nsteps, double step, int side, double *dist, int device, char *err, size_t errlen)
 {
+    if (step > 0.0) nsteps = kTfceStepLevels;
     int rc = check_fit_args(Y, V, ldY, n, X, p, Y, ldY, err, errlen);
     if (rc) return rc;
     if (R < 0 || ncols < 0 || (R > 0 && !idx) || (ncols > 0 && !cols) || (R > 0 && ncols > 0 && !dist))
@@ -344,6 +347,7 @@ int rmg_randomize_tfce(const double *Y, int64_t V, int64_t ldY, int n, const dou
     const int64_t ldd = std::max<int64_t>(2, (V + 1) & ~int64_t(1));
     const int ncol_total = 2 * p + 3, KP = lm_padded_p(p);
     double *dY = nullptr, *scratch = nullptr, *maps = nullptr, *tf = nullptr, *dw = nullptr, *qt = nullptr, *dD = nullptr;
+    double *dM = nullptr;
     int *dptr = nullptr, *didx = nullptr;
     int32_t *dcols = nullptr;
     DevDesign *dd = nullptr;
@@ -354,9 +358,9 @@ int rmg_randomize_tfce(const double *Y, int64_t V, int64_t ldY, int n, const dou
     plan.sm_count = device_sm_count(device);
     int launches = 0;
     {
-        // permutations per batch: keep the TFCE scratch under ~4 GiB
+        // permutations per batch: keep the TFCE scratch under ~8 GiB
         const size_t per_map = tfce_workspace_bytes(V, 1, nsteps, side) + 2 * (size_t)V * 8;
-        const int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)R, (size_t(4) << 30) / (per_map * ncols)));
+        const int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)R, (size_t(8) << 30) / (per_map * ncols)));
         const size_t qstride = make_qt(pd.base, KP).size();
         std::vector<double> ones;
         if (!weights) ones.assign((size_t)V, 1.0);
@@ -379,6 +383,10 @@ int rmg_randomize_tfce(const double *Y, int64_t V, int64_t ldY, int n, const dou
         RMG_CUDA(cudaMemcpyAsync(didx, adj_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
         RMG_CUDA(cudaMemcpyAsync(dw, weights ? weights : ones.data(), (size_t)V * 8, cudaMemcpyHostToDevice, st));
         RMG_CUDA(cudaMemcpyAsync(dcols, cols, (size_t)ncols * 4, cudaMemcpyHostToDevice, st));
+        if (mask) {
+            RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dM), (size_t)V * 8, st));
+            RMG_CUDA(cudaMemcpyAsync(dM, mask, (size_t)V * 8, cudaMemcpyHostToDevice, st));
+        }
         keys_init_kernel<<<(R * ncols + 255) / 256, 256, 0, st>>>(keys, R * ncols);
         ++launches;
         const TfceGraph g{dptr, didx, dw};
@@ -397,14 +405,19 @@ int rmg_randomize_tfce(const double *Y, int64_t V, int64_t ldY, int n, const dou
             RMG_CUDA(cudaMemcpyAsync(qt, hqt.data(), sizeof(double) * (size_t)rb * qstride, cudaMemcpyHostToDevice, st));
             RMG_CUDA(cudaStreamSynchronize(st));          // the host images are reused by the next batch
             for (int i = 0; i < rb; ++i) {
-                LmArgs a{dY, V, ldd, n, p, qt + (size_t)i * qstride, dd + i, nullptr, 0.0, 0.0, scratch, ldd};
+                LmArgs a{dY, V, ldd, n, p, qt + (size_t)i * qstride, dd + i, dM, mask_lo, mask_hi, scratch, ldd};
                 LmLaunchInfo info;
                 RMG_CUDA(launch_lm_fit(a, plan, scr, st, &info));
                 launches += info.launches;
                 extract_maps_kernel<<<dim3(vb, (unsigned)ncols), 256, 0, st>>>(scratch, V, ldd, dcols, ncols, i, maps);
                 ++launches;
             }
-            RMG_CUDA(tfce_batch(maps, V, V, rb * ncols, g, E, H, nsteps, side, tf, V, ws, st, &launches));
+            const cudaError_t te = tfce_batch(maps, V, V, rb * ncols, g, E, H, nsteps, side, tf, V, ws, st, &launches, step);
+            if (te == cudaErrorNotSupported) {
+                rc = fail(err, errlen, RMG_ERR_INVALID, "more than %d thresholds between 0 and a map maximum: increase d", kTfceStepLevels);
+                goto cleanup;
+            }
+            RMG_CUDA(te);
             tfce_colmax_kernel<<<dim3(std::min<unsigned>(vb, 32u), (unsigned)(rb * ncols)), 256, 0, st>>>(tf, V, ncols, two_sided, keys, R, r0);
             ++launches;
             RMG_CUDA(cudaGetLastError());
@@ -417,7 +430,7 @@ int rmg_randomize_tfce(const double *Y, int64_t V, int64_t ldY, int n, const dou
 cleanup:
     g_launch_count += launches;
     {
-        void *all[] = {dY, scratch, maps, tf, ws, dptr, didx, dw, dcols, keys, dD, dd, qt};
+        void *all[] = {dY, scratch, maps, tf, ws, dptr, didx, dw, dcols, keys, dD, dd, qt, dM};
         for (void *x : all)
             if (x) cudaFreeAsync(x, st);
     }
@@ -430,12 +443,22 @@ cleanup:
     return rc;
 }
 
-// The TFCE permutation test shards over PERMUTATIONS (every permutation needs the whole surface): GPU g takes a
-// contiguous block of the R index vectors, one host thread per GPU, no exchange -- the rows of dist are independent.
-int rmg_randomize_tfce_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *idx, int R,
-                             const int32_t *cols, int ncols, int two_sided, const int32_t *adj_ptr, const int32_t *adj_idx,
-                             const double *weights, double E, double H, int nsteps, int side, double *dist, int n_gpus,
-                             char *err, size_t errlen)
+int rmg_randomize_tfce(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *idx, int R,
+                       const int32_t *cols, int ncols, int two_sided, const int32_t *adj_ptr, const int32_t *adj_idx,
+                       const double *weights, double E, double H, int nsteps, int side, double *dist, int device, char *err,
+                       size_t errlen)
+{
+    return randomize_tfce_impl(Y, V, ldY, n, X, p, nullptr, 0.0, 0.0, idx, R, cols, ncols, two_sided, adj_ptr, adj_idx, weights, E,
+                               H, nsteps, 0.0, side, dist, device, err, errlen);
+}
+
+}  // extern "C"
+
+// The TFCE permutation test shards over PERMUTATIONS (every permutation needs the whole surface / volume): GPU g takes
+// a contiguous block of the R index vectors, one host thread per GPU, no exchange -- the rows of dist are independent.
+// fn(g, idx_block, R_block, dist_block, err, errlen)
+template <class Fn>
+static int tfce_perm_sharded(int n, const int32_t *idx, int R, int ncols, double *dist, int n_gpus, char *err, size_t errlen, Fn fn)
 {
     const int have = rmg_device_count();
     if (have <= 0) return fail(err, errlen, RMG_ERR_NO_DEVICE, "no CUDA device available; rminc_b200 has no CPU fallback");
@@ -451,8 +474,7 @@ int rmg_randomize_tfce_multi(const double *Y, int64_t V, int64_t ldY, int n, con
             const int r0 = (int)((int64_t)R * g / G), r1 = (int)((int64_t)R * (g + 1) / G);
             if (r1 <= r0) return;
             part[g].assign((size_t)(r1 - r0) * std::max(ncols, 1), 0.0);
-            rcs[g] = rmg_randomize_tfce(Y, V, ldY, n, X, p, idx + (size_t)r0 * n, r1 - r0, cols, ncols, two_sided, adj_ptr, adj_idx,
-                                        weights, E, H, nsteps, side, part[g].data(), g, &msgs[g][0], msgs[g].size());
+            rcs[g] = fn(g, idx + (size_t)r0 * n, r1 - r0, part[g].data(), &msgs[g][0], msgs[g].size());
         });
     }
     for (auto &t : th) t.join();
@@ -464,6 +486,47 @@ int rmg_randomize_tfce_multi(const double *Y, int64_t V, int64_t ldY, int n, con
             for (int r = r0; r < r1; ++r) dist[(size_t)c * R + r] = part[g][(size_t)c * (r1 - r0) + (r - r0)];
     }
     return RMG_OK;
+}
+
+extern "C" {
+
+int rmg_randomize_tfce_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const int32_t *idx, int R,
+                             const int32_t *cols, int ncols, int two_sided, const int32_t *adj_ptr, const int32_t *adj_idx,
+                             const double *weights, double E, double H, int nsteps, int side, double *dist, int n_gpus,
+                             char *err, size_t errlen)
+{
+    return tfce_perm_sharded(n, idx, R, ncols, dist, n_gpus, err, errlen,
+                             [&](int g, const int32_t *ix, int Rb, double *part, char *e, size_t el) {
+        return rmg_randomize_tfce(Y, V, ldY, n, X, p, ix, Rb, cols, ncols, two_sided, adj_ptr, adj_idx, weights, E, H, nsteps, side,
+                                  part, g, e, el);
+    });
+}
+
+// mincTFCE.mincLm's permutation test (R/minc_voxel_statistics.R:1382-1439: mincRandomize_core with
+// post_proc = mincTFCE.matrix) on the voxel grid; n_gpus <= 1 runs on device 0.
+int rmg_randomize_volume_tfce(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
+                              double mask_lo, double mask_hi, const int32_t *idx, int R, const int32_t *cols, int ncols,
+                              int two_sided, const int64_t *dims, int connectivity, double voxel_volume, double d, double E,
+                              double H, int side, double *dist, int n_gpus, char *err, size_t errlen)
+{
+    if (!dims) return fail(err, errlen, RMG_ERR_INVALID, "dims is NULL");
+    if (dims[0] * dims[1] * dims[2] != V) return fail(err, errlen, RMG_ERR_INVALID, "dims do not multiply to V");
+    if (!(d > 0.0) || !std::isfinite(d)) return fail(err, errlen, RMG_ERR_INVALID, "d must be a positive step (got %g)", d);
+    if (!(voxel_volume > 0.0) || !std::isfinite(voxel_volume)) return fail(err, errlen, RMG_ERR_INVALID, "voxel_volume must be > 0");
+    if (rmg_device_count() <= 0) return fail(err, errlen, RMG_ERR_NO_DEVICE, "no CUDA device available; rminc_b200 has no CPU fallback");
+    std::vector<int32_t> ptr, aidx;
+    const int g = grid_adjacency(dims, connectivity, ptr, aidx);
+    if (g == 1) return fail(err, errlen, RMG_ERR_INVALID, "connectivity must be 6, 18 or 26 (got %d)", connectivity);
+    if (g) return fail(err, errlen, RMG_ERR_INVALID, "bad volume dimensions");
+    const std::vector<double> w((size_t)V, voxel_volume);
+    if (n_gpus <= 1)
+        return randomize_tfce_impl(Y, V, ldY, n, X, p, mask, mask_lo, mask_hi, idx, R, cols, ncols, two_sided, ptr.data(),
+                                   aidx.data(), w.data(), E, H, 0, d, side, dist, 0, err, errlen);
+    return tfce_perm_sharded(n, idx, R, ncols, dist, n_gpus, err, errlen,
+                             [&](int gpu, const int32_t *ix, int Rb, double *part, char *e, size_t el) {
+        return randomize_tfce_impl(Y, V, ldY, n, X, p, mask, mask_lo, mask_hi, ix, Rb, cols, ncols, two_sided, ptr.data(),
+                                   aidx.data(), w.data(), E, H, 0, d, side, part, gpu, e, el);
+    });
 }
 
 // mincRandomize on host data.  Y (doubles, or the volumes in their stored type) is uploaded ONCE, in voxel blocks on a

@@ -17,6 +17,8 @@
  *   rmincgpu_randomize_stored  the same on volumes in their stored type
  *   rmincgpu_graph_tfce      graph_tfce_wqu / graph_tfce (src/vertex_tfce.cpp:92-157), every column of a matrix at once
  *   rmincgpu_randomize_tfce  vertexTFCE.vertexLm's permutation loop (R/minc_vertex_statistics.R:892-948)
+ *   rmincgpu_volume_tfce, rmincgpu_randomize_volume_tfce   mincTFCE on volumes and mincTFCE.mincLm's permutation loop
+ *                            (R/minc_voxel_statistics.R:1186-1439) without the external TFCE program
  *   rmincgpu_fdr             mincFDR's p-value + p.adjust(., "fdr") + threshold step for one column (R/minc_FDR.R:385-505)
  *   rmincgpu_anova           per_voxel_anova / vertex_anova_loop (src/minc_anova.c:142, src/vertex_modelling.c:178)
  */
@@ -329,6 +331,57 @@ SEXP rmincgpu_randomize_tfce(SEXP Y, SEXP mmatrix, SEXP idx, SEXP columns, SEXP 
     return out;
 }
 
+/* mincTFCE.mincSingleDim / .matrix without the trip through a temporary file and the external TFCE program
+ * (R/minc_voxel_statistics.R:1186-1283): map is a vector or a V x nmaps matrix, sizes = minc.dimensions.sizes(likeVolume)
+ * (file order), voxel_volume = prod(abs(minc.separation.sizes(likeVolume))). */
+SEXP rmincgpu_volume_tfce(SEXP map, SEXP sizes, SEXP connectivity, SEXP voxel_volume, SEXP d, SEXP E, SEXP H, SEXP side)
+{
+    if (!Rf_isReal(map)) Rf_error("map must be double");
+    if (LENGTH(sizes) != 3) Rf_error("sizes must have three entries");
+    const int ismat = Rf_isMatrix(map);
+    const R_xlen_t V = ismat ? Rf_nrows(map) : XLENGTH(map);
+    const int nmaps = ismat ? Rf_ncols(map) : 1;
+    int64_t dims[3];
+    for (int i = 0; i < 3; ++i) dims[i] = (int64_t)(Rf_isReal(sizes) ? REAL(sizes)[i] : INTEGER(sizes)[i]);
+    if (dims[0] * dims[1] * dims[2] != V) Rf_error("sizes do not match the data");
+    SEXP out = PROTECT(ismat ? Rf_allocMatrix(REALSXP, (int)V, nmaps) : Rf_allocVector(REALSXP, V));
+    char err[512] = "";
+    int rc = rmg_volume_tfce(REAL(map), dims, nmaps, Rf_asInteger(connectivity), Rf_asReal(voxel_volume), Rf_asReal(d),
+                             Rf_asReal(E), Rf_asReal(H), Rf_asInteger(side), REAL(out), 0, err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
+/* mincTFCE.mincLm's mincRandomize_core(post_proc = mincTFCE.matrix) loop in one call (:1382-1439). */
+SEXP rmincgpu_randomize_volume_tfce(SEXP Y, SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP mask_upper, SEXP idx, SEXP columns,
+                                    SEXP two_sided, SEXP sizes, SEXP connectivity, SEXP voxel_volume, SEXP d, SEXP E, SEXP H,
+                                    SEXP side, SEXP ngpu)
+{
+    if (!Rf_isReal(Y) || !Rf_isReal(mmatrix) || !Rf_isInteger(idx) || !Rf_isInteger(columns))
+        Rf_error("Y/mmatrix must be double, idx/columns integer");
+    if (LENGTH(sizes) != 3) Rf_error("sizes must have three entries");
+    const R_xlen_t V = Rf_nrows(Y);
+    const int n = Rf_ncols(Y), p = Rf_ncols(mmatrix), R = Rf_ncols(idx), nc = LENGTH(columns);
+    if (Rf_nrows(idx) != n) Rf_error("idx must have one row per subject");
+    const double *m = mask_or_null(mask, V);
+    int64_t dims[3];
+    for (int i = 0; i < 3; ++i) dims[i] = (int64_t)(Rf_isReal(sizes) ? REAL(sizes)[i] : INTEGER(sizes)[i]);
+    int *idx0 = (int *)R_alloc((size_t)n * R, sizeof(int));
+    int *col0 = (int *)R_alloc((size_t)nc, sizeof(int));
+    for (R_xlen_t i = 0; i < (R_xlen_t)n * R; ++i) idx0[i] = INTEGER(idx)[i] - 1;
+    for (int i = 0; i < nc; ++i) col0[i] = INTEGER(columns)[i] - 1;
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, R, nc));
+    char err[512] = "";
+    int rc = rmg_randomize_volume_tfce(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, m, Rf_asReal(mask_lower),
+                                       Rf_asReal(mask_upper), idx0, R, col0, nc, Rf_asLogical(two_sided), dims,
+                                       Rf_asInteger(connectivity), Rf_asReal(voxel_volume), Rf_asReal(d), Rf_asReal(E),
+                                       Rf_asReal(H), Rf_asInteger(side), REAL(out), Rf_asInteger(ngpu), err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
 static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_vertex_lm_loop", (DL_FUNC)&rmincgpu_vertex_lm_loop, 3},
     {"rmincgpu_vertex_wlm_loop", (DL_FUNC)&rmincgpu_vertex_wlm_loop, 4},
@@ -341,6 +394,8 @@ static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_fdr", (DL_FUNC)&rmincgpu_fdr, 4},
     {"rmincgpu_graph_tfce", (DL_FUNC)&rmincgpu_graph_tfce, 7},
     {"rmincgpu_randomize_tfce", (DL_FUNC)&rmincgpu_randomize_tfce, 11},
+    {"rmincgpu_volume_tfce", (DL_FUNC)&rmincgpu_volume_tfce, 8},
+    {"rmincgpu_randomize_volume_tfce", (DL_FUNC)&rmincgpu_randomize_volume_tfce, 16},
     {NULL, NULL, 0}};
 
 void R_init_rmincgpu(DllInfo *dll)

@@ -4,6 +4,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <vector>
 
 namespace rmg {
 
@@ -14,12 +15,22 @@ struct TfceGraph {
     const double *weights;   // V  (vertex area; ones by default)
 };
 
+// Levels available when the thresholds come from a fixed step (volumes): levels are stored in one byte.
+constexpr int kTfceStepLevels = 253;
+
+// The voxel grid (file dimension order) as a CSR adjacency; connectivity 6, 18 or 26.  0, 1 (bad connectivity) or
+// 2 (bad / too large dimensions).  Host only.
+int grid_adjacency(const int64_t dims[3], int connectivity, std::vector<int32_t> &ptr, std::vector<int32_t> &idx);
+
 // Bytes of scratch tfce_batch needs for nmaps maps of V vertices.
 size_t tfce_workspace_bytes(int64_t V, int nmaps, int nsteps, int side);
 
 // dmaps: nmaps maps of V doubles (map m at dmaps + m * ld); dout likewise (ldo).  side: 0 both, 1 positive, 2 negative.
+// step > 0: thresholds are the multiples of `step` up to the map maximum (mincTFCE's d) and nsteps is ignored; returns
+// cudaErrorNotSupported when a map needs more than kTfceStepLevels of them.
 // Enqueued on st; synchronises the stream once (to read the number of threshold levels).
 cudaError_t tfce_batch(const double *dmaps, int64_t V, int64_t ld, int nmaps, const TfceGraph &g, double E, double H,
-                       int nsteps, int side, double *dout, int64_t ldo, void *workspace, cudaStream_t st, int *launches);
+                       int nsteps, int side, double *dout, int64_t ldo, void *workspace, cudaStream_t st, int *launches,
+                       double step = 0.0);
 
 }  // namespace rmg

@@ -64,6 +64,20 @@ def api(request, monkeypatch, oracle, lib):
             Y = oracle.expand_stored(U, scale, offset, voxel_min=voxel_min, slice_len=slice_len)
             return oracle.randomize(Y, X, idx, cols, two_sided=two_sided, mask=mask, lo=mask_lo, hi=mask_hi)
 
+        def volume_tfce(maps, dims, d=0.1, E=0.5, H=2.0, side="both", connectivity=6, voxel_volume=1.0, device=0):
+            M = np.asarray(maps, dtype=np.float64)
+            kw = dict(d=d, E=E, H=H, side=side, connectivity=connectivity, voxel_volume=voxel_volume)
+            if M.ndim == 1:
+                return oracle.volume_tfce(M, dims, **kw)
+            return np.column_stack([oracle.volume_tfce(M[:, j], dims, **kw) for j in range(M.shape[1])])
+
+        def randomize_volume_tfce(Y, X, idx, cols, dims, two_sided=True, d=0.1, E=0.5, H=2.0, side="both", connectivity=6,
+                                  voxel_volume=1.0, mask=None, mask_lo=1.0, mask_hi=99999999.0, n_gpus=None):
+            return oracle.randomize_volume_tfce(Y, X, idx, cols, dims, two_sided=two_sided, mask=mask, lo=mask_lo, hi=mask_hi,
+                                                d=d, E=E, H=H, side=side, connectivity=connectivity, voxel_volume=voxel_volume)
+
+        monkeypatch.setattr(core, "volume_tfce", volume_tfce)
+        monkeypatch.setattr(core, "randomize_volume_tfce", randomize_volume_tfce)
         monkeypatch.setattr(core, "randomize_stored", randomize_stored)
         monkeypatch.setattr(core, "graph_tfce", graph_tfce)
         monkeypatch.setattr(core, "randomize_tfce", randomize_tfce)
@@ -443,3 +457,42 @@ def test_vertexTFCE(api, tmp_path, oracle):
     assert th.shape == (4, 2)
     with pytest.raises(ValueError, match="should be one of"):
         api.vertexTFCE(t, adj, side="sideways")
+
+
+def test_mincTFCE(api, study, oracle):
+    """mincTFCE on a volume, a matrix and a mincLm result (R/minc_voxel_statistics.R:1186-1439); the shapes and classes
+    of tests/testthat/test_mincTFCE.R:77-149, the values against the restatement."""
+    gf, maskfile, _ = study
+    dims = (10, 10, 10)
+    vs = api.mincLm("jacobians ~ Sex", gf, mask=maskfile)
+    t = vs.col("tvalue-SexM")
+    one = api.mincTFCE(t, like_volume=dims, d=0.05)
+    assert one.shape == (1000,) and np.allclose(one, oracle.volume_tfce(t, dims, d=0.05), rtol=1e-9, atol=1e-12)
+    assert (one[np.load(maskfile).reshape(-1) < 0.5] == 0).all()
+    # a 3-D array carries its own dimensions; voxel volume and the other sides
+    vol3 = t.reshape(dims)
+    pos = api.mincTFCE(vol3, d=0.1, E=1.0, H=1.0, side="positive", voxel_volume=0.001)
+    assert np.allclose(pos, oracle.volume_tfce(t, dims, d=0.1, E=1.0, H=1.0, side="positive", voxel_volume=0.001),
+                       rtol=1e-9, atol=1e-15)
+    # matrix: every column, NaN -> 0, one d per column; third column of zeros stays zero (test_mincTFCE.R:96-118)
+    tn = t.copy()
+    tn[5] = np.nan
+    mat = api.mincTFCE(np.column_stack([tn, t, np.zeros_like(t)]), like_volume=gf.jacobians[0], d=[0.05, 0.1, 0.05])
+    t0 = np.where(np.isnan(tn), 0.0, tn)
+    assert mat.shape == (1000, 3) and (np.asarray(mat)[:, 2] == 0).all()
+    assert np.allclose(np.asarray(mat)[:, 0], oracle.volume_tfce(t0, dims, d=0.05), rtol=1e-9, atol=1e-12)
+    assert np.allclose(np.asarray(mat)[:, 1], oracle.volume_tfce(t, dims, d=0.1), rtol=1e-9, atol=1e-12)
+    # mincLm result: permutation test with the enhancement as post-processing
+    res = api.mincTFCE(vs, R=5, seed=3, d=0.1)
+    assert res.r_class == ("mincTFCE_randomization", "minc_randomization")
+    assert res["tfce"].colnames == ["tvalue-(Intercept)", "tvalue-SexM"] and res["tfce"].shape == (1000, 2)
+    assert res["randomization_dist"].shape == (5, 2) and res["args"]["side"] == "both"
+    idx = api.draw_indices(10, 5, seed=3)
+    want = oracle.randomize_volume_tfce(vs.attrs["_Y"], vs.attrs["model"], idx, [4, 5], dims, mask=vs.attrs["_mask"], d=0.1)
+    assert np.asarray(res["randomization_dist"]) == pytest.approx(want, rel=1e-8)
+    assert api.thresholds(res).shape == (4, 2)
+    with pytest.raises(ValueError, match="should be one of"):
+        api.mincTFCE(t, like_volume=dims, side="sideways")
+    with pytest.raises(ValueError):
+        api.mincTFCE(t, like_volume=(10, 10))
+

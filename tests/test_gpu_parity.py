@@ -777,3 +777,73 @@ def test_randomize_tfce_matches_literal_loop(core, oracle):
     G = min(2, core.device_count())
     np.testing.assert_allclose(core.randomize_tfce(Y, X, idx, cols, adj, two_sided=False, side="positive", nsteps=50, n_gpus=G),
                                want, rtol=1e-8)
+
+
+# ------------------------------------------------------------------ mincTFCE on volumes
+def test_volume_tfce_matches_restatement_and_the_graph_path(core, oracle):
+    """rmg_volume_tfce against the scipy-labelling restatement (every connectivity, side, exponents, several maps at
+    once), and against the graph path on the reference's neighbour_list with the thresholds made to coincide."""
+    rng = np.random.default_rng(21)
+    dims = (12, 17, 9)
+    V = int(np.prod(dims))
+    M = rng.standard_normal((V, 5))
+    blob = np.zeros(dims)
+    blob[3:8, 4:11, 2:6] = 2.5
+    M[:, 0] += blob.reshape(-1)
+    M[:, 1] = np.round(M[:, 1], 1)                 # exact ties, values sitting on thresholds
+    M[::3, 2] = 0.0                                # masked-out voxels are zeros
+    M[:, 3] = -np.abs(M[:, 3]) - 0.2               # nothing positive
+    M[:, 4] *= 0.01                                # below the first threshold everywhere -> all zero
+    for conn in (6, 18, 26):
+        for side in ("both", "positive", "negative"):
+            for d, E, H, vv in ((0.1, 0.5, 2.0, 1.0), (0.25, 1.0, 1.0, 0.001), (0.05, 0.66, 2.0, 0.056 ** 3)):
+                got = core.volume_tfce(M, dims, d=d, E=E, H=H, side=side, connectivity=conn, voxel_volume=vv)
+                want = np.column_stack([oracle.volume_tfce(M[:, j], dims, d=d, E=E, H=H, side=side, connectivity=conn,
+                                                           voxel_volume=vv) for j in range(M.shape[1])])
+                scale = np.abs(want).max() + 1e-300
+                assert np.abs(got - want).max() <= 1e-10 * scale, (conn, side, d)
+                assert np.array_equal(got == 0, want == 0)
+                assert (got[:, 4] == 0).all()
+    # test_mincTFCE.R:153-170: vertexTFCE on neighbour_list(.., 6) with weights = voxel volume is the same enhancement
+    z, y, x = dims
+    v = M[:, 0].copy()
+    v[v > 3.0] = 3.0
+    v[100] = 3.0                                    # hmax = 30 d
+    nl = core.neighbour_list(x, y, z, 6)
+    a = core.volume_tfce(v, dims, d=0.1, voxel_volume=0.001)
+    b = core.graph_tfce(v, nl, nsteps=30, weights=0.001)
+    # (graph_tfce's negative side has its own hmax, so compare where the positive side decides)
+    pos = core.volume_tfce(v, dims, d=0.1, voxel_volume=0.001, side="positive")
+    np.testing.assert_allclose(pos, core.graph_tfce(v, nl, nsteps=30, weights=0.001, side="positive"), rtol=1e-9, atol=1e-18)
+    assert a.shape == b.shape
+    # argument contract
+    with pytest.raises(core.RmincGpuError, match="increase d"):
+        core.volume_tfce(v * 100, dims, d=0.1)
+    with pytest.raises(core.RmincGpuError, match="connectivity must be 6, 18 or 26"):
+        core.volume_tfce(v, dims, connectivity=8)
+    with pytest.raises(ValueError):
+        core.volume_tfce(v, (12, 17, 8))
+
+
+def test_randomize_volume_tfce_matches_literal_loop(core, oracle):
+    """mincTFCE.mincLm's permutation test with a mask: refit -> non-finite to 0 -> enhance -> abs -> maximum."""
+    rng = np.random.default_rng(23)
+    dims, n = (9, 10, 8), 14
+    V = int(np.prod(dims))
+    X = np.column_stack([np.ones(n), np.arange(n) % 2, rng.normal(size=n)])
+    Y = np.asfortranarray(rng.normal(0, 0.3, (V, n)))
+    eff = np.zeros(dims)
+    eff[2:6, 3:7, 2:5] = 0.5
+    Y += np.outer(eff.reshape(-1), X[:, 1])
+    Y[11] = 0.0
+    mask = ellipsoid_mask(dims)
+    idx = np.column_stack([rng.permutation(n) for _ in range(9)]).astype(np.int32)
+    cols = [5, 6, 7]
+    for two_sided, side, m in ((True, "both", mask), (False, "positive", None)):
+        got = core.randomize_volume_tfce(Y, X, idx, cols, dims, two_sided=two_sided, side=side, d=0.2, mask=m, voxel_volume=0.5)
+        want = oracle.randomize_volume_tfce(Y, X, idx, cols, dims, two_sided=two_sided, side=side, d=0.2, mask=m, voxel_volume=0.5)
+        np.testing.assert_allclose(got, want, rtol=1e-8)
+    G = min(2, core.device_count())
+    np.testing.assert_allclose(core.randomize_volume_tfce(Y, X, idx, cols, dims, two_sided=False, side="positive", d=0.2,
+                                                          voxel_volume=0.5, n_gpus=G), want, rtol=1e-8)
+

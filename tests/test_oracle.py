@@ -396,3 +396,31 @@ def test_graph_tfce_restatement(oracle):
                                                                use_ref=True))
                 assert (a >= 0).all() if side == "positive" else True
     assert (oracle.graph_tfce(-np.abs(x) - 1, ptr, idx, side="positive") == 0).all()        # hmax <= 0: all zero
+
+
+def test_volume_tfce_restatement_agrees_with_the_graph_algorithm_on_a_neighbour_list(oracle, lib):
+    """The reference pins mincTFCE only through vertexTFCE on RMINC:::neighbour_list(.., 6) with weights = voxel volume
+    (tests/testthat/test_mincTFCE.R:153-170).  The scipy-labelling restatement of the volume enhancement and the
+    restated graph_tfce (pinned to the reference's object code) must then agree when the graph algorithm is given the
+    same thresholds: with hmax an exact multiple of d, nsteps = hmax / d makes graph_tfce's thresholds hmax - k * d."""
+    from rminc_b200 import core
+    rng = np.random.default_rng(5)
+    x, y, z = 7, 6, 5                                    # neighbour_list's (fastest, middle, slowest)
+    dims = (z, y, x)                                      # file order: slowest first
+    vol = np.round(rng.normal(0, 1, x * y * z), 2)
+    d = 0.25
+    vol[17] = 3.0                                         # hmax = 12 d exactly
+    vol[vol > 3.0] = 2.5
+    nl = oracle.neighbour_list(x, y, z, 6)
+    ptr, idx = oracle.adjacency_csr(nl)
+    got = oracle.volume_tfce(vol, dims, d=d, side="positive", voxel_volume=0.001)
+    want = oracle.graph_tfce(vol, ptr, idx, nsteps=12, side="positive", weights=np.full(vol.size, 0.001))
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-15)
+    # the product's neighbour_list (host code, no GPU) is the reference's, for every connectivity
+    for n in (6, 18, 26):
+        p2, i2 = core.neighbour_list(4, 3, 5, n)
+        want_nl = oracle.neighbour_list(4, 3, 5, n)
+        assert [sorted(i2[p2[v]:p2[v + 1]].tolist()) for v in range(60)] == [sorted(w) for w in want_nl]
+    with pytest.raises(core.RmincGpuError, match="connectivity must be 6,18, or 26"):
+        core.neighbour_list(3, 3, 3, 8)
+
