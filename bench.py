@@ -426,6 +426,24 @@ def run_gpu_arm(args):
                 "cpu_restatement_ms_per_map": cpu_ms, "speedup_vs_one_core": (cpu_ms * 1e-3 * Rt * pv) / sec,
                 "timing": "wall clock around the host-buffer C-ABI call (upload, refits, enhancement, maxima, download)"}
         del Yt_h
+        if not args.small:
+            # mincTFCE at config-2 volume size: smooth unit-variance maps (box-filtered noise), d = 0.1, both sides
+            g = torch.Generator(device=dev).manual_seed(11)
+            vols = torch.randn((4, 1) + tuple(DIMS), generator=g, device=dev, dtype=torch.float32)
+            for _ in range(2):
+                vols = torch.nn.functional.avg_pool3d(vols, 3, stride=1, padding=1)
+            vols = (vols / vols.std(dim=(2, 3, 4), keepdim=True)).to(torch.float64)
+            Mh = np.asfortranarray(vols.reshape(4, -1).T.cpu().numpy())
+            del vols
+            core.volume_tfce(Mh[:, :1], DIMS, d=0.1)                                # warm-up
+            t0 = time.perf_counter()
+            tv = core.volume_tfce(Mh, DIMS, d=0.1)
+            secv = time.perf_counter() - t0
+            assert np.isfinite(tv).all() and np.abs(tv).max() > 0
+            tfce["mincTFCE"] = {"workload": f"mincTFCE of 4 maps of {DIMS[0]}x{DIMS[1]}x{DIMS[2]} voxels, d 0.1, both sides, 6-connected",
+                                "seconds": secv, "maps_per_s": 4 / secv, "max_abs_t": float(np.abs(Mh).max()),
+                                "timing": "wall clock around the host-buffer C-ABI call (grid adjacency, upload, enhancement, download)"}
+            del Mh, tv
 
     # ---- mincRandomize (config 4): voxel-sharded, all ranks evaluate every permutation, one all-reduce(MAX)
     rand = None
@@ -545,7 +563,7 @@ def run_gpu_arm(args):
             barrier()
             t0 = time.perf_counter()
             perm_step(Rn)
-            dd = torch.from_numpy(dist_h).to(dev)
+            dd = torch.from_numpy(np.ascontiguousarray(dist_h)).to(dev)
             if world > 1:
                 dist.all_reduce(dd, op=dist.ReduceOp.MAX)
             torch.cuda.synchronize()
@@ -624,7 +642,7 @@ def run_gpu_arm(args):
             barrier()
             t0 = time.perf_counter()
             perm_u16(Rn)
-            dd = torch.from_numpy(dist_h).to(dev)
+            dd = torch.from_numpy(np.ascontiguousarray(dist_h)).to(dev)
             if world > 1:
                 dist.all_reduce(dd, op=dist.ReduceOp.MAX)
             torch.cuda.synchronize()
@@ -659,6 +677,20 @@ def run_gpu_arm(args):
         if e2e is None:
             e2e = {}
         e2e["pageable_host"] = {"value": Vp / dtp, "unit": UNIT, "voxels": Vp, "gbs": Vp * n * 8 / dtp / 1e9}
+        # mincRandomize from the same pageable matrix (what R's heap is): blocks staged through the pinned ring
+        Rp = min(args.perms, 1000)
+        rngp = np.random.default_rng(4)
+        idx_p = np.asfortranarray(np.column_stack([rngp.permutation(n) for _ in range(Rp)]).astype(np.int32))
+        cols_p = np.arange(p + 2, 2 * p + 2, dtype=np.int32)
+        dist_p = np.empty((Rp, p), order="F")
+        for R_ in (8, Rp):
+            t0 = time.perf_counter()
+            rc = lib.rmg_randomize(Yp.ctypes.data, Vp, Vp, n, Xf2.ctypes.data, p, None, 1.0, 99999999.0, idx_p.ctypes.data, R_,
+                                   cols_p.ctypes.data, p, 1, dist_p.ctypes.data, local_rank, err, len(err))
+            _lib.check(rc, err)
+            dtr = time.perf_counter() - t0
+        e2e["pageable_host"]["randomize"] = {"R": Rp, "voxels": Vp, "seconds": dtr, "perms_per_s": Rp / dtr,
+                                             "gemm_window_ms": core.last_kernel_ms()}
         del Yp, Op
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload

@@ -323,8 +323,8 @@ cleanup:
 // from a fixed height increment (mincTFCE's d) instead of nsteps.
 static int randomize_tfce_impl(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p, const double *mask,
                                double mask_lo, double mask_hi, const int32_t *idx, int R, const int32_t *cols, int ncols,
-                               int two_sided, const int32_t *adj_ptr, const int32_t *adj_idx, const double *weights, double E,
-                               double H, int nsteps, double step, int side, double *dist, int device, char *err, size_t errlen)
+                               int two_sided, const HostTfceGraph &hg, double E, double H, int nsteps, double step, int side,
+                               double *dist, int device, char *err, size_t errlen)
 {
     if (step > 0.0) nsteps = kTfceStepLevels;
     int rc = check_fit_args(Y, V, ldY, n, X, p, Y, ldY, err, errlen);
@@ -333,11 +333,9 @@ static int randomize_tfce_impl(const double *Y, int64_t V, int64_t ldY, int n, c
         return fail(err, errlen, RMG_ERR_INVALID, "bad permutation arguments");
     for (int c = 0; c < ncols; ++c)
         if (cols[c] < 0 || cols[c] >= 2 * p + 3) return fail(err, errlen, RMG_ERR_INVALID, "cols[%d] out of range", c);
-    if (V > 0x7fffffffLL || (V > 0 && !adj_ptr)) return fail(err, errlen, RMG_ERR_INVALID, "bad graph arguments");
+    if (V > 0x7fffffffLL) return fail(err, errlen, RMG_ERR_INVALID, "bad graph arguments");
     if (side < 0 || side > 2 || nsteps < 1 || nsteps > 253) return fail(err, errlen, RMG_ERR_INVALID, "bad TFCE arguments");
-    const int64_t nnz = V > 0 ? adj_ptr[V] : 0;
-    for (int64_t e = 0; e < nnz; ++e)
-        if (adj_idx[e] < 0 || adj_idx[e] >= V) return fail(err, errlen, RMG_ERR_INVALID, "Mismatch between adjacency list and data");
+    if ((rc = check_csr(hg, V, err, errlen))) return rc;
     PermSet pd;
     if ((rc = factor_permutations(X, n, p, idx, R, pd, err, errlen))) return rc;
     if ((rc = select_device(device, err, errlen))) return rc;
@@ -357,31 +355,25 @@ static int randomize_tfce_impl(const double *Y, int64_t V, int64_t ldY, int n, c
     LmPlan plan;
     plan.sm_count = device_sm_count(device);
     int launches = 0;
+    TfceGraph g;
     {
         // permutations per batch: keep the TFCE scratch under ~8 GiB
         const size_t per_map = tfce_workspace_bytes(V, 1, nsteps, side) + 2 * (size_t)V * 8;
         const int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)R, (size_t(8) << 30) / (per_map * ncols)));
         const size_t qstride = make_qt(pd.base, KP).size();
-        std::vector<double> ones;
-        if (!weights) ones.assign((size_t)V, 1.0);
         RMG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        if ((rc = upload_graph(hg, V, st, g, &dptr, &didx, &dw, err, errlen))) goto cleanup;
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dY), (size_t)ldd * n * 8, st));
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)ldd * ncol_total * 8, st));
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&maps), (size_t)B * ncols * V * 8, st));
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&tf), (size_t)B * ncols * V * 8, st));
         RMG_CUDA(cudaMallocAsync(&ws, tfce_workspace_bytes(V, B * ncols, nsteps, side), st));
-        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dptr), (size_t)(V + 1) * 4, st));
-        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&didx), (size_t)std::max<int64_t>(nnz, 1) * 4, st));
-        RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dw), (size_t)V * 8, st));
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dcols), (size_t)ncols * 4, st));
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&keys), (size_t)R * ncols * 8, st));
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dD), (size_t)R * ncols * 8, st));
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dd), sizeof(DevDesign) * (size_t)B, st));
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&qt), sizeof(double) * (size_t)B * qstride, st));
         RMG_CUDA(cudaMemcpy2DAsync(dY, (size_t)ldd * 8, Y, (size_t)ldY * 8, (size_t)V * 8, (size_t)n, cudaMemcpyHostToDevice, st));
-        RMG_CUDA(cudaMemcpyAsync(dptr, adj_ptr, (size_t)(V + 1) * 4, cudaMemcpyHostToDevice, st));
-        RMG_CUDA(cudaMemcpyAsync(didx, adj_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
-        RMG_CUDA(cudaMemcpyAsync(dw, weights ? weights : ones.data(), (size_t)V * 8, cudaMemcpyHostToDevice, st));
         RMG_CUDA(cudaMemcpyAsync(dcols, cols, (size_t)ncols * 4, cudaMemcpyHostToDevice, st));
         if (mask) {
             RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dM), (size_t)V * 8, st));
@@ -389,7 +381,6 @@ static int randomize_tfce_impl(const double *Y, int64_t V, int64_t ldY, int n, c
         }
         keys_init_kernel<<<(R * ncols + 255) / 256, 256, 0, st>>>(keys, R * ncols);
         ++launches;
-        const TfceGraph g{dptr, didx, dw};
         std::vector<DevDesign> hdd(B);
         std::vector<double> hqt((size_t)B * qstride);
         const unsigned vb = (unsigned)((V + 255) / 256);
@@ -448,8 +439,12 @@ int rmg_randomize_tfce(const double *Y, int64_t V, int64_t ldY, int n, const dou
                        const double *weights, double E, double H, int nsteps, int side, double *dist, int device, char *err,
                        size_t errlen)
 {
-    return randomize_tfce_impl(Y, V, ldY, n, X, p, nullptr, 0.0, 0.0, idx, R, cols, ncols, two_sided, adj_ptr, adj_idx, weights, E,
-                               H, nsteps, 0.0, side, dist, device, err, errlen);
+    HostTfceGraph hg;
+    hg.adj_ptr = adj_ptr;
+    hg.adj_idx = adj_idx;
+    hg.weights = weights;
+    return randomize_tfce_impl(Y, V, ldY, n, X, p, nullptr, 0.0, 0.0, idx, R, cols, ncols, two_sided, hg, E, H, nsteps, 0.0, side,
+                               dist, device, err, errlen);
 }
 
 }  // extern "C"
@@ -514,18 +509,16 @@ int rmg_randomize_volume_tfce(const double *Y, int64_t V, int64_t ldY, int n, co
     if (!(d > 0.0) || !std::isfinite(d)) return fail(err, errlen, RMG_ERR_INVALID, "d must be a positive step (got %g)", d);
     if (!(voxel_volume > 0.0) || !std::isfinite(voxel_volume)) return fail(err, errlen, RMG_ERR_INVALID, "voxel_volume must be > 0");
     if (rmg_device_count() <= 0) return fail(err, errlen, RMG_ERR_NO_DEVICE, "no CUDA device available; rminc_b200 has no CPU fallback");
-    std::vector<int32_t> ptr, aidx;
-    const int g = grid_adjacency(dims, connectivity, ptr, aidx);
-    if (g == 1) return fail(err, errlen, RMG_ERR_INVALID, "connectivity must be 6, 18 or 26 (got %d)", connectivity);
-    if (g) return fail(err, errlen, RMG_ERR_INVALID, "bad volume dimensions");
-    const std::vector<double> w((size_t)V, voxel_volume);
+    HostTfceGraph hg;
+    int rc = volume_graph(dims, connectivity, voxel_volume, hg, err, errlen);
+    if (rc) return rc;
     if (n_gpus <= 1)
-        return randomize_tfce_impl(Y, V, ldY, n, X, p, mask, mask_lo, mask_hi, idx, R, cols, ncols, two_sided, ptr.data(),
-                                   aidx.data(), w.data(), E, H, 0, d, side, dist, 0, err, errlen);
+        return randomize_tfce_impl(Y, V, ldY, n, X, p, mask, mask_lo, mask_hi, idx, R, cols, ncols, two_sided, hg, E, H, 0, d, side,
+                                   dist, 0, err, errlen);
     return tfce_perm_sharded(n, idx, R, ncols, dist, n_gpus, err, errlen,
                              [&](int gpu, const int32_t *ix, int Rb, double *part, char *e, size_t el) {
-        return randomize_tfce_impl(Y, V, ldY, n, X, p, mask, mask_lo, mask_hi, ix, Rb, cols, ncols, two_sided, ptr.data(),
-                                   aidx.data(), w.data(), E, H, 0, d, side, part, gpu, e, el);
+        return randomize_tfce_impl(Y, V, ldY, n, X, p, mask, mask_lo, mask_hi, ix, Rb, cols, ncols, two_sided, hg, E, H, 0, d, side,
+                                   part, gpu, e, el);
     });
 }
 

@@ -12,8 +12,32 @@ namespace rmg {
 struct TfceGraph {
     const int *adj_ptr;      // V + 1
     const int *adj_idx;      // adj_ptr[V]
-    const double *weights;   // V  (vertex area; ones by default)
+    const double *weights;   // V  (vertex area; ones by default); null -> every vertex weighs uniform_weight
+    // connectivity != 0: the vertices are the voxels of an s0 x s1 x s2 grid (v = (i * s1 + j) * s2 + k) and the
+    // neighbours are computed, not stored (6 / 18 / 26: Manhattan distance <= 1 / 2 / 3 inside the 3x3x3 box,
+    // src/vertex_tfce.cpp:178-214); adj_ptr / adj_idx are then unused.
+    int connectivity = 0;
+    int s0 = 0, s1 = 0, s2 = 0;
+    double uniform_weight = 1.0;
 };
+
+// The graph as the host entry points receive it: a CSR adjacency (+ optional weights), or a voxel grid (connectivity
+// 6 / 18 / 26, dims in file order, every voxel weighing uniform_weight) whose neighbours are never materialised.
+struct HostTfceGraph {
+    const int32_t *adj_ptr = nullptr, *adj_idx = nullptr;
+    const double *weights = nullptr;
+    int connectivity = 0;
+    int64_t dims[3] = {0, 0, 0};
+    double uniform_weight = 1.0;
+};
+
+// Fills hg for the voxel grid `dims` (validated; RMG_ERR_INVALID + message otherwise).
+int volume_graph(const int64_t *dims, int connectivity, double voxel_volume, HostTfceGraph &hg, char *err, size_t errlen);
+// Argument checks of hg against V vertices.
+int check_csr(const HostTfceGraph &hg, int64_t V, char *err, size_t errlen);
+// Device image of hg (stream-ordered allocations returned through dptr / didx / dw for the caller to free).
+int upload_graph(const HostTfceGraph &hg, int64_t V, cudaStream_t st, TfceGraph &g, int **dptr, int **didx, double **dw,
+                 char *err, size_t errlen);
 
 // Levels available when the thresholds come from a fixed step (volumes): levels are stored in one byte.
 constexpr int kTfceStepLevels = 253;
