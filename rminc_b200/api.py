@@ -531,13 +531,14 @@ def anatFDR(buffer: MincMatrix, **kw) -> MincMatrix:
 # ----------------------------------------------------------------------------- vertexTFCE
 def vertexTFCE(x, surface, R: int = 500, alternative: str = "two.sided", E: float = 0.5, H: float = 2.0, nsteps: int = 100,
                weights=None, side: str = "both", replace: bool = False, parallel=None, seed=None, idx=None,
-               device: int = 0):
-    """Threshold-free cluster enhancement on a surface graph (R/minc_vertex_statistics.R:731-948).
+               device: int = 0, column: int = 1):
+    """Threshold-free cluster enhancement on a surface graph (R/minc_vertex_statistics.R:731-990).
 
     `surface`: the 0-based adjacency list form vertexTFCE accepts (one neighbour array per vertex), or a CSR pair
     (ptr, idx); mesh objects / igraph are outside this package.  Dispatch as in the reference:
       * numeric vector -> enhanced vector (vertexTFCE.numeric)
       * plain matrix   -> every column enhanced (vertexTFCE.matrix)
+      * file name(s)   -> read with vertexTable(column=) then as above (vertexTFCE.character)
       * vertexLm result -> permutation test on every tvalue- column: list(tfce, randomization_dist, args) of class
         c("vertexTFCE_randomization","vertex_randomization") (vertexTFCE.vertexLm)."""
     if side not in core.TFCE_SIDES:
@@ -566,6 +567,10 @@ def vertexTFCE(x, surface, R: int = 500, alternative: str = "two.sided", E: floa
                                 args=dict(call=x.attrs.get("call"), side=side, alternative=alternative))
         out.r_class = ("vertexTFCE_randomization", "vertex_randomization")
         return out
+    if isinstance(x, (str, os.PathLike)):                       # vertexTFCE.character: one file -> a vector
+        x = vertexTable([x], column=column)[:, 0]
+    elif isinstance(x, (list, tuple)) and len(x) and all(isinstance(f, (str, os.PathLike)) for f in x):
+        x = vertexTable(list(x), column=column)[:, 0] if len(x) == 1 else vertexTable(list(x), column=column)
     A = np.asarray(x, dtype=np.float64)
     res = core.graph_tfce(A, surface, E=E, H=H, nsteps=nsteps, side=side, weights=weights, device=device)
     if A.ndim == 2:
@@ -709,9 +714,24 @@ def mincRandomize(x: MincMatrix, R: int = 500, alternative: str = "two.sided", r
     return out
 
 
+def vertexRandomize(x: MincMatrix, R: int = 500, alternative: str = "two.sided", replace: bool = False, parallel=None,
+                    columns: Optional[Sequence[int]] = None, seed=None, idx=None, device: int = 0) -> MincRandomization:
+    """vertexRandomize.vertexLm (R/minc_vertex_statistics.R:992-1024): the same permutation loop on a vertexLm result,
+    returned with class c("vertexLm_randomization","vertex_randomization")."""
+    if not isinstance(x, MincMatrix) or "vertexLm" not in x.r_class:
+        raise TypeError("x must be the result of vertexLm")
+    out = mincRandomize(x, R=R, alternative=alternative, replace=replace, parallel=parallel, columns=columns, seed=seed,
+                        idx=idx, device=device)
+    out.r_class = ("vertexLm_randomization", "vertex_randomization")
+    return out
+
+
 def thresholds(x: MincRandomization, probs=(0.01, 0.05, 0.1, 0.2)) -> MincMatrix:
     """apply(dist, 2, quantile, probs = 1 - probs) with rownames "1%", "5%", ... (:1577-1581).
-    R's default quantile type 7 == numpy's default 'linear' method."""
+    R's default quantile type 7 == numpy's default 'linear' method.  For a mincFDR result (thresholds.mincQvals,
+    R/minc_FDR.R:659-664) it returns the stored thresholds attribute."""
+    if isinstance(x, MincMatrix) and "mincQvals" in x.r_class:
+        return x.attrs["thresholds"]
     d = np.asarray(x["randomization_dist"])
     q = np.quantile(d, [1 - p for p in probs], axis=0)
     return MincMatrix(q, colnames=x["randomization_dist"].colnames, rownames=[f"{p * 100:g}%" for p in probs])

@@ -394,6 +394,7 @@ def test_mincFDR(api, study):
     assert qv.r_class == ("mincQvals", "mincMultiDim", "matrix")
     assert qv.colnames == ["qvalue-F-statistic", "qvalue-tvalue-(Intercept)", "qvalue-tvalue-SexM"]
     assert qv.attrs["thresholds"].shape == (5, 3) and qv.attrs["thresholds"].rownames == ["0.01", "0.05", "0.1", "0.15", "0.2"]
+    assert api.thresholds(qv) is qv.attrs["thresholds"]                      # thresholds.mincQvals
     assert qv.attrs["DF"] == [[1, 8], 8, 8]
     inside = np.load(maskfile).reshape(-1) > 0.5
     assert (np.asarray(qv)[~inside] == 1).all()
@@ -455,6 +456,15 @@ def test_vertexTFCE(api, tmp_path, oracle):
     assert np.asarray(res["randomization_dist"]) == pytest.approx(want, rel=1e-8)
     th = api.thresholds(res)
     assert th.shape == (4, 2)
+    # vertexTFCE.character: one file is a vector, several files the columns of a matrix
+    assert np.allclose(api.vertexTFCE(files[0], adj), oracle.graph_tfce(np.loadtxt(files[0]), ptr, aidx), rtol=1e-9, atol=1e-12)
+    assert api.vertexTFCE(files[:3], adj).shape == (V, 3)
+    # vertexRandomize.vertexLm: mincRandomize's loop with the vertex classes
+    vr = api.vertexRandomize(vs, R=6, seed=2)
+    assert vr.r_class == ("vertexLm_randomization", "vertex_randomization") and vr["randomization_dist"].shape == (6, 2)
+    assert np.allclose(np.asarray(vr["randomization_dist"]), np.asarray(api.mincRandomize(vs, R=6, seed=2)["randomization_dist"]))
+    with pytest.raises(TypeError):
+        api.vertexRandomize(np.zeros((3, 3)))
     with pytest.raises(ValueError, match="should be one of"):
         api.vertexTFCE(t, adj, side="sideways")
 

@@ -274,3 +274,28 @@ def test_config5_whole_volume_as_uint16_on_one_gpu(torch_mod, oracle):
     Ys = (Us.astype(np.float64) - 0.0) * sc_h.T[sl, :] + of_h.T[sl, :]
     assert_rows_match(out[:, st].cpu().numpy().T, oracle.vertex_lm_loop(Ys, X), RTOL, "cfg5 uint16 sample")
     assert bool(torch.isfinite(out).all())
+
+
+def test_randomize_host_pipeline_at_a_realistic_size(torch_mod):
+    """rmg_randomize from (pageable) host memory with its default blocking -- 8 voxel blocks uploaded through the pinned
+    ring while the permutation GEMM runs -- equals the device-resident entry point on the same data; and so does the
+    same matrix shipped as float32 stored volumes (rmg_randomize_stored)."""
+    torch, core, free = torch_mod
+    V, n, R = 1_200_000, 64, 48                              # 614 MB of doubles: above the staging threshold
+    X = design_cfg2(n)
+    p = X.shape[1]
+    Yt = gen(torch, V, n, seed=5).to(torch.float32).to(torch.float64)      # float32-representable, for the stored leg
+    Yt[:, 1000:1010] = 0.0                                   # degenerate voxels: statistics -> 0
+    mask = ellipsoid_mask((100, 100, 120))
+    mt = torch.from_numpy(mask).cuda()
+    rng = np.random.default_rng(6)
+    idx = np.column_stack([rng.permutation(n) for _ in range(R)]).astype(np.int32)
+    cols = list(range(p + 2, 2 * p + 2))
+    want = core.randomize_torch(Yt, X, idx, cols, mask=mt).cpu().numpy().T
+    Yh = np.asfortranarray(Yt.cpu().numpy().T)               # plain numpy: pageable
+    got = core.randomize(Yh, X, idx, cols, mask=mask)
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=0)
+    got32 = core.randomize_stored(np.asfortranarray(Yh.astype(np.float32)), X, idx, cols, mask=mask)
+    np.testing.assert_allclose(got32, want, rtol=1e-10, atol=0)
+    assert np.isfinite(got).all() and (got > 0).all()
+
