@@ -2,11 +2,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -133,6 +135,48 @@ inline bool is_pinned_host(const void *p)
         return false;
     }
     return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+// Should a host matrix of total_bytes travel through the ring, and with how many rows (subjects) per ~128 MiB slot?
+// RMG_STAGING_ROWS=k forces the ring with k rows per slot at any size (tests); RMG_NO_STAGING disables it.
+inline bool staging_plan(const void *src, double total_bytes, size_t row_bytes, int n, int &rows_per_slot)
+{
+    const int forced_rows = std::getenv("RMG_STAGING_ROWS") ? std::atoi(std::getenv("RMG_STAGING_ROWS")) : 0;
+    rows_per_slot = forced_rows > 0 ? std::min(forced_rows, n)
+        : (int)std::max<int64_t>(1, std::min<int64_t>(n, (128ll << 20) / (int64_t)std::max<size_t>(row_bytes, 1)));
+    return total_bytes > 0 && !is_pinned_host(src) && !std::getenv("RMG_NO_STAGING") &&
+           (forced_rows > 0 || total_bytes >= 256.0 * 1024 * 1024);
+}
+
+// n rows of row_bytes bytes (source pitch spitch) -> device rows of pitch dpitch, queued on `up`.  ring == nullptr:
+// one strided copy (pinned or small sources); else all host threads copy groups of rows into the next free pinned
+// slot and the DMA engine drains the slots behind them.
+inline cudaError_t upload_rows(PinnedRing *ring, int rows_per_slot, char *dst, size_t dpitch, const char *src, size_t spitch,
+                               size_t row_bytes, int n, cudaStream_t up)
+{
+    if (row_bytes == 0 || n <= 0) return cudaSuccess;
+    if (!ring) return cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, (size_t)n, cudaMemcpyHostToDevice, up);
+    for (int r0 = 0; r0 < n; r0 += rows_per_slot) {
+        const int rows = std::min(rows_per_slot, n - r0);
+        int slot = 0;
+        cudaError_t e = ring->acquire(slot);
+        if (e != cudaSuccess) return e;
+        char *buf = ring->buf[slot];
+        const int pieces = rows * 8;                   // 8 column pieces per row keep every thread busy
+        parallel_for(pieces, [&](int i0, int i1) {
+            for (int i = i0; i < i1; ++i) {
+                const int r = i / 8, part = i % 8;
+                const size_t a0 = row_bytes * part / 8, a1 = row_bytes * (part + 1) / 8;
+                std::memcpy(buf + (size_t)r * row_bytes + a0, src + (size_t)(r0 + r) * spitch + a0, a1 - a0);
+            }
+        });
+        e = cudaMemcpy2DAsync(dst + (size_t)r0 * dpitch, dpitch, buf, row_bytes, row_bytes, (size_t)rows, cudaMemcpyHostToDevice, up);
+        if (e != cudaSuccess) return e;
+        e = cudaEventRecord(ring->done[slot], up);
+        if (e != cudaSuccess) return e;
+        ring->busy[slot] = true;
+    }
+    return cudaSuccess;
 }
 
 // Volumes in their stored type (rmg_lm_fit_stored): Y is then V x n samples of `dtype`, not doubles.

@@ -356,6 +356,7 @@ static int randomize_tfce_impl(const double *Y, int64_t V, int64_t ldY, int n, c
     plan.sm_count = device_sm_count(device);
     int launches = 0;
     TfceGraph g;
+    PinnedRing ring;
     {
         // permutations per batch: keep the TFCE scratch under ~8 GiB
         const size_t per_map = tfce_workspace_bytes(V, 1, nsteps, side) + 2 * (size_t)V * 8;
@@ -373,7 +374,13 @@ static int randomize_tfce_impl(const double *Y, int64_t V, int64_t ldY, int n, c
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dD), (size_t)R * ncols * 8, st));
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dd), sizeof(DevDesign) * (size_t)B, st));
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&qt), sizeof(double) * (size_t)B * qstride, st));
-        RMG_CUDA(cudaMemcpy2DAsync(dY, (size_t)ldd * 8, Y, (size_t)ldY * 8, (size_t)V * 8, (size_t)n, cudaMemcpyHostToDevice, st));
+        {   // pageable Y (R's heap) goes through the pinned ring
+            int rows_per_slot = 1;
+            const bool staged = staging_plan(Y, (double)V * n * 8.0, (size_t)V * 8, n, rows_per_slot);
+            if (staged) RMG_CUDA(ring.init((size_t)rows_per_slot * (size_t)V * 8));
+            RMG_CUDA(upload_rows(staged ? &ring : nullptr, rows_per_slot, reinterpret_cast<char *>(dY), (size_t)ldd * 8,
+                                 reinterpret_cast<const char *>(Y), (size_t)ldY * 8, (size_t)V * 8, n, st));
+        }
         RMG_CUDA(cudaMemcpyAsync(dcols, cols, (size_t)ncols * 4, cudaMemcpyHostToDevice, st));
         if (mask) {
             RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dM), (size_t)V * 8, st));
@@ -430,6 +437,7 @@ cleanup:
         cudaStreamSynchronize(st);
         cudaStreamDestroy(st);
     }
+    ring.release_all();
     if (rc != RMG_OK) cudaGetLastError();
     return rc;
 }
@@ -564,11 +572,8 @@ static int randomize_host_impl(const void *Yv, const StoredSpec *pk, int64_t V, 
     PinnedRing ring;
     int64_t launches = 0;
     g_last_kernel_ms = 0.0;
-    const int forced_rows = std::getenv("RMG_STAGING_ROWS") ? std::atoi(std::getenv("RMG_STAGING_ROWS")) : 0;
-    const bool staged = V > 0 && !is_pinned_host(Yv) && !std::getenv("RMG_NO_STAGING") &&
-                        (forced_rows > 0 || (double)V * n * (double)es >= 256.0 * 1024 * 1024);
-    const int rows_per_slot = forced_rows > 0 ? std::min(forced_rows, n)
-        : (int)std::max<int64_t>(1, std::min<int64_t>(n, (128ll << 20) / ((int64_t)es * std::max<int64_t>(CV, 1))));
+    int rows_per_slot = 1;
+    const bool staged = V > 0 && staging_plan(Yv, (double)V * n * (double)es, (size_t)CV * es, n, rows_per_slot);
     {
         RMG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         RMG_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
@@ -603,30 +608,8 @@ static int randomize_host_impl(const void *Yv, const StoredSpec *pk, int64_t V, 
                 // ---- the block's samples: host -> device on the copy stream (straight into Y for doubles)
                 char *dstdev = pk ? dU : reinterpret_cast<char *>(dY + v0);
                 const size_t dpitch = pk ? (size_t)CV * es : (size_t)ldd * 8;
-                if (!staged) {
-                    RMG_CUDA(cudaMemcpy2DAsync(dstdev, dpitch, Yb + (size_t)v0 * es, (size_t)ldY * es, (size_t)cv * es, (size_t)n,
-                                               cudaMemcpyHostToDevice, up));
-                } else {
-                    for (int r0 = 0; r0 < n; r0 += rows_per_slot) {
-                        const int rows = std::min(rows_per_slot, n - r0);
-                        int slot = 0;
-                        RMG_CUDA(ring.acquire(slot));
-                        char *dst = ring.buf[slot];
-                        const int64_t pieces = (int64_t)rows * 8;
-                        parallel_for((int)pieces, [&](int i0, int i1) {
-                            for (int i = i0; i < i1; ++i) {
-                                const int r = i / 8, part = i % 8;
-                                const int64_t a0 = cv * part / 8, a1 = cv * (part + 1) / 8;
-                                std::memcpy(dst + ((size_t)r * cv + a0) * es, Yb + ((size_t)v0 + (size_t)(r0 + r) * ldY + a0) * es,
-                                            (size_t)(a1 - a0) * es);
-                            }
-                        });
-                        RMG_CUDA(cudaMemcpy2DAsync(dstdev + (size_t)r0 * dpitch, dpitch, dst, (size_t)cv * es, (size_t)cv * es,
-                                                   (size_t)rows, cudaMemcpyHostToDevice, up));
-                        RMG_CUDA(cudaEventRecord(ring.done[slot], up));
-                        ring.busy[slot] = true;
-                    }
-                }
+                RMG_CUDA(upload_rows(staged ? &ring : nullptr, rows_per_slot, dstdev, dpitch, Yb + (size_t)v0 * es, (size_t)ldY * es,
+                                     (size_t)cv * es, n, up));
                 // stored samples become the reader's doubles on the copy stream too: stream order then protects the
                 // one staging block, and the expansion (~1 ms) is noise next to the block's transfer
                 if (pk) {

@@ -756,7 +756,7 @@ def test_graph_tfce_matches_oracle(core, oracle):
         core.graph_tfce(M[:, 0], adj, nsteps=1000)
 
 
-def test_randomize_tfce_matches_literal_loop(core, oracle):
+def test_randomize_tfce_matches_literal_loop(core, oracle, monkeypatch):
     """vertexTFCE.vertexLm's permutation test: per permutation refit -> non-finite to 0 -> enhance -> abs -> maximum."""
     from helpers import grid_adjacency, tfce_randomize_oracle
     rng = np.random.default_rng(9)
@@ -777,6 +777,9 @@ def test_randomize_tfce_matches_literal_loop(core, oracle):
     G = min(2, core.device_count())
     np.testing.assert_allclose(core.randomize_tfce(Y, X, idx, cols, adj, two_sided=False, side="positive", nsteps=50, n_gpus=G),
                                want, rtol=1e-8)
+    # pageable Y through the pinned staging ring (forced at this size)
+    monkeypatch.setenv("RMG_STAGING_ROWS", "3")
+    np.testing.assert_allclose(core.randomize_tfce(Y, X, idx, cols, adj, two_sided=False, side="positive", nsteps=50), want, rtol=1e-8)
 
 
 # ------------------------------------------------------------------ mincTFCE on volumes
