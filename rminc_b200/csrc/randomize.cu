@@ -185,6 +185,7 @@ int randomize_block(const PermSet &pd, const double *dY, int64_t V, int64_t ldY,
                     size_t errlen)
 {
     int rc = RMG_OK;
+    if (V <= 0) return rc;                     // nothing to reduce: the keys keep key(-inf), max over no voxels
     double *scratch = nullptr;
     void *gemm_ws = nullptr;
     LmScratch scr;
