@@ -153,3 +153,60 @@ def test_rshim_compiles_against_r_api_declarations():
     src = open(os.path.join(ROOT, "rminc_b200", "csrc", "rshim.c")).read()
     for name in ("rmincgpu_vertex_lm_loop", "rmincgpu_lm", "rmincgpu_randomize"):
         assert name in src and name in open(os.path.join(ROOT, "rminc_b200", "R", "rminc_gpu.R")).read()
+
+
+def _split_top_level_args(text):
+    """Split 'a, f(b, c), d' at commas outside parentheses / brackets / quotes."""
+    args, depth, cur, quote = [], 0, [], None
+    for ch in text:
+        if quote:
+            cur.append(ch)
+            if ch == quote:
+                quote = None
+            continue
+        if ch in "\"'":
+            quote = ch
+            cur.append(ch)
+        elif ch in "([{":
+            depth += 1
+            cur.append(ch)
+        elif ch in ")]}":
+            depth -= 1
+            cur.append(ch)
+        elif ch == "," and depth == 0:
+            args.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(ch)
+    if "".join(cur).strip():
+        args.append("".join(cur).strip())
+    return args
+
+
+def test_r_wrappers_match_the_registered_routines():
+    """R cannot run here, so the binding is checked statically: every .Call("name", ...) in rminc_b200/R/rminc_gpu.R
+    names a routine of rshim.c's R_CallMethodDef table (the analogue of src/RMINC_init.c:57-82) and passes exactly the
+    registered number of arguments, and every registered routine is defined with that many SEXP parameters."""
+    import re
+    csrc = open(os.path.join(ROOT, "rminc_b200", "csrc", "rshim.c")).read()
+    rsrc = re.sub(r"#.*", "", open(os.path.join(ROOT, "rminc_b200", "R", "rminc_gpu.R")).read())      # comments out
+    table = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"(rmincgpu_\w+)",\s*\(DL_FUNC\)&\1,\s*(\d+)\}', csrc)}
+    assert len(table) >= 13
+    for name, arity in table.items():
+        m = re.search(r"SEXP\s+" + name + r"\s*\(([^)]*)\)", csrc)
+        assert m, f"{name} is registered but not defined"
+        assert len([a for a in m.group(1).split(",") if a.strip()]) == arity, f"{name}: definition vs registered arity {arity}"
+    calls = 0
+    for m in re.finditer(r'\.Call\(', rsrc):
+        depth, i = 1, m.end()
+        while depth:
+            depth += {"(": 1, ")": -1}.get(rsrc[i], 0)
+            i += 1
+        args = _split_top_level_args(rsrc[m.end():i - 1])
+        name = args[0].strip("\"'")
+        assert name in table, f".Call to unregistered routine {name}"
+        passed = [a for a in args[1:] if not a.startswith("PACKAGE")]
+        assert len(passed) == table[name], f".Call({name}) passes {len(passed)} arguments, {table[name]} registered"
+        calls += 1
+    assert calls >= 12
+
