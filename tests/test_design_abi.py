@@ -109,6 +109,61 @@ def test_no_cpu_fallback(lib):
         with pytest.raises(core.RmincGpuError) as e:
             call()
         assert e.value.code == 4 and "no CPU fallback" in str(e.value)
+    # ... and so does every entry point of the rows next to the path
+    F = np.asfortranarray(Y.astype(np.float32))
+    idx = np.arange(20)[:, None]
+    adj = [[1]] + [[v - 1, v + 1] for v in range(1, 63)] + [[62]]
+    more = {
+        "randomize_stored": lambda: core.randomize_stored(F, X, idx, [4]),
+        "randomize_stored n_gpus": lambda: core.randomize_stored(F, X, idx, [4], n_gpus=2),
+        "volume_tfce": lambda: core.volume_tfce(Y[:, 0], (4, 4, 4)),
+        "randomize_volume_tfce": lambda: core.randomize_volume_tfce(Y, X, idx, [4], (4, 4, 4)),
+        "randomize_volume_tfce n_gpus": lambda: core.randomize_volume_tfce(Y, X, idx, [4], (4, 4, 4), n_gpus=2),
+        "graph_tfce": lambda: core.graph_tfce(Y[:, 0], adj),
+        "randomize_tfce": lambda: core.randomize_tfce(Y, X, idx, [4], adj),
+        "randomize_tfce n_gpus": lambda: core.randomize_tfce(Y, X, idx, [4], adj, n_gpus=2),
+        "lm_fit_stored": lambda: core.lm_fit_stored(F, X),
+        "lm_fit_stored n_gpus": lambda: core.lm_fit_stored(F, X, n_gpus=2),
+        "lm_fit_cov": lambda: core.lm_fit_cov(Y, Y[:, ::-1].copy(), X),
+        "anova_fit": lambda: core.anova_fit(Y, X, [0, 1]),
+        "vertex_wlm": lambda: core.vertex_wlm(Y, X, np.ones(20)),
+        "fdr": lambda: core.fdr(Y[:, 0], core.STAT_T, 18),
+    }
+    for name, call in more.items():
+        with pytest.raises(core.RmincGpuError) as e:
+            call()
+        assert e.value.code == 4 and "no CUDA device" in str(e.value), name
+    # the one host-only routine works without a device
+    ptr, nb = core.neighbour_list(3, 2, 2, 6)
+    assert ptr[-1] == nb.size == 2 * (2 * 2 * 2 + 3 * 1 * 2 + 3 * 2 * 1)
+
+
+def test_ctypes_signatures_match_the_header():
+    """A ctypes call with the wrong number or width of arguments corrupts the call silently: every prototype of
+    include/rminc_b200.h is parsed and compared, parameter by parameter, with rminc_b200/_lib.py's SIGNATURES."""
+    from rminc_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "rminc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(int|double|int64_t)\s+(rmg_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src)
+    assert len(protos) == len(_lib.SIGNATURES)
+
+    def kind(ctype):
+        if ctype in (C.c_void_p, C.c_char_p) or isinstance(ctype, type(C.POINTER(C.c_int))) and hasattr(ctype, "contents"):
+            return "ptr"
+        return {C.c_int: "int", C.c_int64: "int64", C.c_double: "double", C.c_size_t: "size_t"}[ctype]
+
+    for ret, name, params in protos:
+        res, args = _lib.SIGNATURES[name]
+        assert kind(res) == {"int": "int", "double": "double", "int64_t": "int64"}[ret], name
+        plist = [p.strip() for p in params.split(",") if p.strip() and p.strip() != "void"]
+        assert len(plist) == len(args), f"{name}: header has {len(plist)} parameters, ctypes {len(args)}"
+        for i, (decl, a) in enumerate(zip(plist, args)):
+            if "*" in decl:
+                want = "ptr"
+            else:
+                base = decl.replace("const ", "").split()[0]
+                want = {"int": "int", "int32_t": "int", "int64_t": "int64", "double": "double", "size_t": "size_t"}[base]
+            assert kind(a) == want, f"{name}, parameter {i + 1} ({decl}): ctypes says {kind(a)}"
 
 
 def test_pvalue_function_matches_textbook_and_scipy(lib):
