@@ -423,9 +423,25 @@ def graph_tfce(x, adj_ptr, adj_idx, E=0.5, H=2.0, nsteps=100, side="both", weigh
     return out
 
 
-def neighbour_list(x, y, z, n):
+def neighbour_list(x, y, z, n, use_ref=False):
     """RMINC:::neighbour_list (src/vertex_tfce.cpp:178-214), literally: vertex = k*y*x + j*x + i (i fastest), neighbours
-    within Manhattan distance 1 / 2 / 3 for n = 6 / 18 / 26.  Pure-Python loops: small grids only."""
+    within Manhattan distance 1 / 2 / 3 for n = 6 / 18 / 26.  Pure-Python loops: small grids only.
+    use_ref: run the reference's own compiled function instead (oracle/_ref/librminc_ref_tfce.so)."""
+    global _ref_tfce
+    if use_ref:
+        if _ref_tfce is None:
+            _ref_tfce = _load(_REF_TFCE)
+            _ref_tfce.ref_graph_tfce.restype = C.c_int
+        ptr = np.zeros(x * y * z + 1, dtype=np.int32)
+        nnz = C.c_int64(0)
+        err = C.create_string_buffer(256)
+        pp = ptr.ctypes.data_as(C.c_void_p)
+        if _ref_tfce.ref_neighbour_list(C.c_int(x), C.c_int(y), C.c_int(z), C.c_int(n), pp, None, C.byref(nnz), err, C.c_size_t(256)):
+            raise OracleError(err.value.decode())
+        idx = np.zeros(max(nnz.value, 1), dtype=np.int32)
+        _ref_tfce.ref_neighbour_list(C.c_int(x), C.c_int(y), C.c_int(z), C.c_int(n), pp, idx.ctypes.data_as(C.c_void_p),
+                                     C.byref(nnz), err, C.c_size_t(256))
+        return [idx[ptr[v]:ptr[v + 1]].tolist() for v in range(x * y * z)]
     maxdist = {6: 1, 18: 2, 26: 3}.get(n)
     if maxdist is None:
         raise OracleError("Nearest neighbour connectivity must be 6,18, or 26")

@@ -36,3 +36,29 @@ extern "C" int ref_graph_tfce(const double *map, int64_t V, const int32_t *adj_p
         return 1;
     }
 }
+
+std::vector<std::vector<int> > neighbour_list(double x, double y, double z, int n);
+
+// The reference's own neighbour_list (src/vertex_tfce.cpp:178-214), flattened to CSR.  Call with adj_idx == NULL to get
+// the number of entries in *nnz (adj_ptr, x*y*z + 1 entries, is always filled).
+extern "C" int ref_neighbour_list(int x, int y, int z, int n, int32_t *adj_ptr, int32_t *adj_idx, int64_t *nnz, char *err,
+                                  size_t errlen)
+{
+    try {
+        const std::vector<std::vector<int> > nl = neighbour_list(x, y, z, n);
+        int64_t tot = 0;
+        adj_ptr[0] = 0;
+        for (size_t v = 0; v < nl.size(); ++v) {
+            if (adj_idx)
+                for (size_t k = 0; k < nl[v].size(); ++k) adj_idx[tot + (int64_t)k] = nl[v][k];
+            tot += (int64_t)nl[v].size();
+            adj_ptr[v + 1] = (int32_t)tot;
+        }
+        *nnz = tot;
+        return 0;
+    } catch (const std::exception &e) {
+        if (err && errlen) snprintf(err, errlen, "%s", e.what());
+        return 1;
+    }
+}
+

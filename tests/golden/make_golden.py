@@ -68,6 +68,22 @@ def main():
     out["E_Xs"], out["E_Y"], out["E_Z"] = Xs, Y, Z
     out["E_out_static"] = O.lm_loop_cov(Y, Z, Xs, use_ref=True)
     out["E_out_nostatic"] = O.lm_loop_cov(Y, Z, None, use_ref=True)
+    # case F: the reference's own neighbour_list + graph_tfce on a voxel grid (what tests/testthat/test_mincTFCE.R:153-170
+    # equates with mincTFCE): a 6 x 5 x 4 volume (x fastest), weights = voxel volume, hmax an exact multiple of the step
+    x, y, z = 6, 5, 4
+    for conn in (6, 18, 26):
+        nl = O.neighbour_list(x, y, z, conn, use_ref=True)
+        ptr, idx = O.adjacency_csr(nl)
+        out[f"F_ptr{conn}"], out[f"F_idx{conn}"] = ptr, idx
+    vol = np.round(rng.normal(0, 1, x * y * z), 2)
+    vol[vol > 2.0] = 1.5
+    vol[vol < -2.0] = -1.5
+    vol[31], vol[77] = 2.0, -2.0                      # hmax = 2.0 on both sides = 8 steps of 0.25
+    out["F_dims"], out["F_vol"] = np.array([z, y, x]), vol
+    for conn in (6, 18, 26):
+        for side in ("positive", "negative", "both"):
+            out[f"F_tfce{conn}_{side}"] = O.graph_tfce(vol, out[f"F_ptr{conn}"], out[f"F_idx{conn}"], nsteps=8, side=side,
+                                                       weights=np.full(vol.size, 0.001), use_ref=True)
     np.savez_compressed(os.path.join(os.path.dirname(__file__), "ref_golden.npz"), **out)
     print("wrote ref_golden.npz:", {k: v.shape for k, v in out.items()})
 

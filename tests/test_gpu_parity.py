@@ -850,3 +850,19 @@ def test_randomize_volume_tfce_matches_literal_loop(core, oracle):
     np.testing.assert_allclose(core.randomize_volume_tfce(Y, X, idx, cols, dims, two_sided=False, side="positive", d=0.2,
                                                           voxel_volume=0.5, n_gpus=G), want, rtol=1e-8)
 
+
+def test_volume_tfce_golden_vectors_of_the_reference_object_code(core):
+    """Golden case F: the reference's compiled neighbour_list + graph_tfce on a voxel grid (weights = voxel volume, 8 steps
+    of 0.25 up to hmax = 2) against rmg_volume_tfce with d = 0.25, and against rmg_graph_tfce on the golden adjacency."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_golden.npz"))
+    dims = tuple(int(v) for v in G["F_dims"])
+    vol = G["F_vol"]
+    for conn in (6, 18, 26):
+        for side in ("positive", "negative", "both"):
+            want = G[f"F_tfce{conn}_{side}"]
+            tol = 1e-10 * np.abs(want).max()
+            got = core.volume_tfce(vol, dims, d=0.25, side=side, connectivity=conn, voxel_volume=0.001)
+            assert np.abs(got - want).max() <= tol and np.array_equal(got == 0, want == 0), (conn, side)
+            g2 = core.graph_tfce(vol, (G[f"F_ptr{conn}"], G[f"F_idx{conn}"]), nsteps=8, side=side, weights=0.001)
+            assert np.abs(g2 - want).max() <= tol and np.array_equal(g2 == 0, want == 0), (conn, side)
+

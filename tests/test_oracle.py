@@ -424,3 +424,31 @@ def test_volume_tfce_restatement_agrees_with_the_graph_algorithm_on_a_neighbour_
     with pytest.raises(core.RmincGpuError, match="connectivity must be 6,18, or 26"):
         core.neighbour_list(3, 3, 3, 8)
 
+
+def test_grid_tfce_golden_vectors_of_the_reference_object_code(oracle, lib):
+    """Golden case F (tests/golden/make_golden.py): the reference's own compiled neighbour_list and graph_tfce on a
+    6 x 5 x 4 voxel grid with weights = voxel volume -- the enhancement the reference's tests equate with mincTFCE
+    (tests/testthat/test_mincTFCE.R:153-170).  Pins (a) the restated neighbour_list, (b) the product's
+    rmg_neighbour_list (host code), (c) the scipy-labelling restatement of the volume enhancement, for every
+    connectivity and side; and, where the reference is present, the compiled function itself once more."""
+    from rminc_b200 import core
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_golden.npz"))
+    z, y, x = (int(v) for v in G["F_dims"])
+    vol = G["F_vol"]
+    for conn in (6, 18, 26):
+        ptr, idx = G[f"F_ptr{conn}"], G[f"F_idx{conn}"]
+        want_nl = [sorted(idx[ptr[v]:ptr[v + 1]].tolist()) for v in range(x * y * z)]
+        assert [sorted(a) for a in oracle.neighbour_list(x, y, z, conn)] == want_nl
+        p2, i2 = core.neighbour_list(x, y, z, conn)
+        assert [sorted(i2[p2[v]:p2[v + 1]].tolist()) for v in range(x * y * z)] == want_nl
+        if oracle.have_ref_tfce():
+            assert [sorted(a) for a in oracle.neighbour_list(x, y, z, conn, use_ref=True)] == want_nl
+        for side in ("positive", "negative", "both"):
+            want = G[f"F_tfce{conn}_{side}"]
+            got = oracle.volume_tfce(vol, (z, y, x), d=0.25, side=side, connectivity=conn, voxel_volume=0.001)
+            assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), (conn, side)
+            assert np.array_equal(got == 0, want == 0)
+            # and the restated graph algorithm on the golden adjacency, with the reference's nsteps
+            g2 = oracle.graph_tfce(vol, ptr, idx, nsteps=8, side=side, weights=np.full(vol.size, 0.001))
+            assert np.array_equal(g2, want), (conn, side)
+
