@@ -162,6 +162,15 @@ def mincTableStored(vols: Sequence["StoredVolume"]):
     return U, scale, offset, first.valid_min, (V // nsl if nsl > 1 else max(V, 1))
 
 
+def _expand_stored(U, scale, offset, voxel_min, slice_len):
+    """The doubles the CPU reader would produce from mincTableStored's pieces (StoredVolume.real() for all volumes at
+    once): ((double)u - valid_min) * scale[slice, j] + offset[slice, j], each operation rounded once."""
+    if U.dtype == np.float32:
+        return np.asfortranarray(U, dtype=np.float64)
+    sl = np.minimum(np.arange(U.shape[0]) // int(slice_len), scale.shape[0] - 1)
+    return np.asfortranarray((U.astype(np.float64) - float(voxel_min)) * scale[sl, :] + offset[sl, :])
+
+
 def mincTable(filenames: Sequence, mask=None, reader: Callable = default_reader) -> np.ndarray:
     """V x n matrix, one column per file (R/minc_interface.R:1031-1077), Fortran order."""
     first = reader(filenames[0])
@@ -613,8 +622,8 @@ def mincTFCE(x, d=0.1, E: float = 0.5, H: float = 2.0, side: str = "both", like_
     if isinstance(x, MincMatrix) and "mincLm" in x.r_class:
         if alternative not in ("two.sided", "greater"):
             raise ValueError("'arg' should be one of 'two.sided', 'greater'")
-        if "_Y" not in x.attrs:
-            raise TypeError("x must be the result of mincLm on double volumes")
+        if "_Y" not in x.attrs and "_stored" not in x.attrs:
+            raise TypeError("x must be the result of mincLm")
         if np.ndim(d) != 0:
             raise ValueError("the permutation test takes one height step d")
         dims = volume_dims(x.attrs["likeVolume"] if like_volume is None else like_volume)
@@ -631,7 +640,8 @@ def mincTFCE(x, d=0.1, E: float = 0.5, H: float = 2.0, side: str = "both", like_
         if idx.shape != (n, R):
             raise ValueError("idx must be n x R")
         lo, hi = x.attrs["_mask_range"]
-        dist = core.randomize_volume_tfce(x.attrs["_Y"], X, idx, columns, dims, two_sided=(alternative == "two.sided"), d=d,
+        Yd = x.attrs["_Y"] if "_Y" in x.attrs else _expand_stored(**x.attrs["_stored"])
+        dist = core.randomize_volume_tfce(Yd, X, idx, columns, dims, two_sided=(alternative == "two.sided"), d=d,
                                           E=E, H=H, side=side, connectivity=connectivity, voxel_volume=voxel_volume,
                                           mask=x.attrs["_mask"], mask_lo=lo, mask_hi=hi,
                                           n_gpus=int(parallel[1]) if parallel is not None else None)

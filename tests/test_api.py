@@ -375,6 +375,11 @@ def test_mincLm_on_stored_volumes(api, study):
     tcols = [i for i, c in enumerate(vs.colnames) if c.startswith("tvalue-")]
     np.testing.assert_allclose(np.asarray(rs["randomization_dist"]), core.randomize(Yq, X, idx, tcols, mask=m), rtol=1e-9)
     assert api.thresholds(rs).shape == (4, 3)
+    # mincTFCE of a stored-type fit: the permutation test sees the doubles the CPU reader would have produced
+    tf = api.mincTFCE(vs, R=3, idx=idx[:, :3], d=0.2, like_volume=(10, 10, 10))
+    want_tf = core.randomize_volume_tfce(Yq, X, idx[:, :3], tcols, (10, 10, 10), d=0.2, mask=m)
+    np.testing.assert_allclose(np.asarray(tf["randomization_dist"]), want_tf, rtol=1e-9)
+    np.testing.assert_array_equal(api._expand_stored(**vs.attrs["_stored"]), Yq)
     # float32 volumes need no range tables
     f32 = {f: api.StoredVolume(np.load(f).astype(np.float32)) for f in gf.jacobians}
     v32 = api.mincLm("jacobians ~ Sex", gf, reader=lambda item: f32[item])
