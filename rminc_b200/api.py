@@ -745,3 +745,55 @@ def thresholds(x: MincRandomization, probs=(0.01, 0.05, 0.1, 0.2)) -> MincMatrix
     d = np.asarray(x["randomization_dist"])
     q = np.quantile(d, [1 - p for p in probs], axis=0)
     return MincMatrix(q, colnames=x["randomization_dist"].colnames, rownames=[f"{p * 100:g}%" for p in probs])
+
+
+# ----------------------------------------------------------------------------- model selection on the logLik column
+def _model_size(x: MincMatrix):
+    if not isinstance(x, MincMatrix) or "model" not in x.attrs or "logLik" not in (x.colnames or []):
+        raise TypeError("expected a mincLm / vertexLm / anatLm result")
+    X = np.asarray(x.attrs["model"])
+    return X.shape[0], X.shape[1] + 1                  # n; parameters + 1 for the error scale
+
+
+def AIC(x: MincMatrix, k: float = 2.0) -> np.ndarray:
+    """AIC.mincLm / .vertexLm / .anatModel (R/minc_model_selection.R:2-17): k * (dfs - logLik), one value per row --
+    the reference's own expression, including its use of k as the overall factor."""
+    _, dfs = _model_size(x)
+    return k * (dfs - x.col("logLik"))
+
+
+def AICc(x: MincMatrix) -> np.ndarray:
+    """AICc.mincLm (R/minc_model_selection.R:33-39): AIC + 2 (k + 1)(k + 2) / (n - k - 2) with k = ncol(model) + 1."""
+    n, k = _model_size(x)
+    return AIC(x) + 2.0 * (k + 1) * (k + 2) / (n - k - 2)
+
+
+def BIC(x: MincMatrix) -> np.ndarray:
+    """BIC.mincLm (R/minc_model_selection.R:52-58): -2 logLik + k log(n)."""
+    n, k = _model_size(x)
+    return -2.0 * x.col("logLik") + k * np.log(n)
+
+
+def compare_models(*models: MincMatrix, metric: Callable = AICc) -> MincMatrix:
+    """compare_models (R/minc_model_selection.R:104-127): rows x models matrix of the metric (lower is better), class
+    c("model_comparison","matrix"), attributes formulae and metric."""
+    if len(models) < 2:
+        raise ValueError("more than one model must be supplied")                      # check_model_list, :66-68
+    if any(not isinstance(m, MincMatrix) or m.r_class != models[0].r_class for m in models):
+        raise ValueError("all models must be the same type")
+    if any(m.shape[0] != models[0].shape[0] for m in models):
+        raise ValueError("all models must have the same number of rows")
+    table = np.column_stack([np.asarray(metric(m)) for m in models])
+    return MincMatrix(table, attrs={"formulae": [(m.attrs.get("call") or {}).get("formula") for m in models],
+                                    "metric": getattr(metric, "__name__", str(metric))},
+                      r_class=("model_comparison", "matrix"))
+
+
+def summary_model_comparison(comp: MincMatrix):
+    """summary.model_comparison (R/minc_model_selection.R:168-190): wins per model (ties count for every minimiser),
+    as a list of dict(model, formula, wins) sorted by wins."""
+    t = np.asarray(comp)
+    wins = (t == t.min(axis=1, keepdims=True)).sum(axis=0)
+    rows = [dict(model=str(j + 1), formula=f, wins=int(w)) for j, (f, w) in enumerate(zip(comp.attrs["formulae"], wins))]
+    return sorted(rows, key=lambda r: r["wins"])
+

@@ -511,3 +511,34 @@ def test_mincTFCE(api, study, oracle):
     with pytest.raises(ValueError):
         api.mincTFCE(t, like_volume=(10, 10))
 
+
+def test_model_selection_on_the_logLik_column(api, study):
+    """AIC / BIC at a row against the closed-form lm values (tests/testthat/test_mincLm.R:54-55), AICc's correction and
+    compare_models / its summary (test_mincLm.R:211-232)."""
+    gf, maskfile, _ = study
+    fits = [api.mincLm(f, gf) for f in ("jacobians ~ Sex", "jacobians ~ Scale", "jacobians ~ Sex + Scale", "jacobians ~ Coil")]
+    vs = fits[0]
+    n, v = 10, 7
+    y = np.load(gf.jacobians[0]).reshape(-1)[v], None
+    Y = np.array([np.load(f).reshape(-1)[v] for f in gf.jacobians])
+    X = np.asarray(vs.attrs["model"])
+    beta, rss = np.linalg.lstsq(X, Y, rcond=None)[:2]
+    loglik = -0.5 * n * (np.log(2 * np.pi) + 1 - np.log(n) + np.log(rss[0]))
+    p1 = X.shape[1] + 1
+    assert api.AIC(vs)[v] == pytest.approx(-2 * loglik + 2 * p1, rel=1e-9)               # stats::AIC of the same lm
+    assert api.BIC(vs)[v] == pytest.approx(-2 * loglik + np.log(n) * p1, rel=1e-9)       # stats::BIC
+    assert api.AICc(vs)[v] == pytest.approx(api.AIC(vs)[v] + 2 * (p1 + 1) * (p1 + 2) / (n - p1 - 2), rel=1e-12)
+    comp1 = api.compare_models(*fits, metric=api.AIC)
+    comp2 = api.compare_models(*fits)
+    params = np.array([np.asarray(m.attrs["model"]).shape[1] + 1 for m in fits])
+    corr = 2 * (params + 1) * (params + 2) / (n - params - 2)
+    assert comp2.r_class == ("model_comparison", "matrix") and comp2.shape == (1000, 4)
+    np.testing.assert_allclose(np.asarray(comp2), np.asarray(comp1) + corr[None, :], rtol=1e-12)
+    assert comp2.attrs["formulae"] == ["jacobians ~ Sex", "jacobians ~ Scale", "jacobians ~ Sex + Scale", "jacobians ~ Coil"]
+    summ = api.summary_model_comparison(comp2)
+    assert sum(r["wins"] for r in summ) >= 1000 and [r["wins"] for r in summ] == sorted(r["wins"] for r in summ)
+    with pytest.raises(ValueError, match="more than one model"):
+        api.compare_models(vs)
+    with pytest.raises(TypeError):
+        api.AIC(np.zeros((3, 3)))
+
