@@ -66,7 +66,8 @@ mincRandomize_core <- function(x, R = 500, replace = FALSE, parallel = NULL,
                                columns = grep("tvalue-", colnames(x)),
                                alternative = c("two.sided", "greater"), post_proc = identity, ...) {
   alternative <- match.arg(alternative)
-  if (!identical(post_proc, identity)) stop("post_proc (TFCE) is not on the GPU path yet")
+  if (!identical(post_proc, identity))
+    stop("a post_proc runs in its own routine: mincTFCE_mincLm_gpu() for mincTFCE.matrix, vertexTFCE_randomize_gpu() for vertexTFCE.matrix")
   lmod <- x
   n <- nrow(attr(lmod, "data"))
   idx <- vapply(seq_len(R), function(i) sample(seq_len(n), replace = replace), integer(n))
