@@ -642,6 +642,7 @@ def run_gpu_arm(args):
             barrier()
             t0 = time.perf_counter()
             perm_u16(Rn)
+            call_sec = time.perf_counter() - t0          # the C-ABI call alone, before the max-reduce over ranks
             dd = torch.from_numpy(np.ascontiguousarray(dist_h)).to(dev)
             if world > 1:
                 dist.all_reduce(dd, op=dist.ReduceOp.MAX)
@@ -653,6 +654,7 @@ def run_gpu_arm(args):
             sec = float(tt.item())
             assert bool(torch.isfinite(dd).all()) and bool((dd > 0).all())
             rand["e2e_stored_u16"] = {"value": Rn / sec, "unit": "perms/s", "seconds": sec, "h2d_bytes": (sb - sa) * n * 2,
+                                      "call_seconds_this_rank": call_sec, "gemm_window_ms": core.last_kernel_ms(),
                                       "api": "rmg_randomize_stored (C ABI, pinned host uint16 voxels -> blocks expanded once "
                                              "on the device -> all R permutations per block)"}
         del hU, hO
