@@ -10,15 +10,10 @@ that become active and the current roots:
     (parentH), so that  value(v) = sum of off[] along v's history path + acc[final root];
   * the history paths are resolved once at the end by pointer jumping (log-depth, data-parallel).
 
-This file emulates that scheme sequentially and checks it against the restated reference algorithm; run
-`python tools/proto/tfce_lazy.py` (needs oracle/liboracle.so).
+This file emulates that scheme sequentially and checks it against the restated reference algorithm (a CPU test: it
+lives under tests/ because it uses the oracle as its checker).
 """
-import os
-import sys
-
 import numpy as np
-
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 
 def tfce_lazy_positive(x, ptr, idx, w, E=0.5, H=2.0, nsteps=100):
@@ -93,9 +88,8 @@ def tfce_lazy_positive(x, ptr, idx, w, E=0.5, H=2.0, nsteps=100):
     return out
 
 
-def main():
-    from oracle import oracle as O
-    O.build(ref=False)
+def test_lazy_tfce_scheme_agrees_with_the_restated_reference_algorithm(oracle):
+    O = oracle
     rng = np.random.default_rng(0)
     worst = 0.0
     for case in range(6):
@@ -122,8 +116,3 @@ def main():
         # product's tests compare within 1e-10 of the map maximum, which this meets; an exact zero pattern it does not.
         assert np.abs(got[want == 0]).max(initial=0.0) <= 1e-12 * np.abs(want).max()
     assert worst < 1e-10, worst
-    print("lazy TFCE scheme agrees with the restated reference algorithm")
-
-
-if __name__ == "__main__":
-    main()
