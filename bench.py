@@ -194,6 +194,230 @@ def gen_Y(torch, V, n, device, seed, mean=0.0, sd=0.2):
     return Yt
 
 
+def pinned_numpy(lib, shape, dtype):
+    """A page-locked, NUMA-interleaved host array from the library's own allocator (rmg_host_alloc); (array, pointer)."""
+    import ctypes as C
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = lib.rmg_host_alloc(nbytes)
+    if not ptr:
+        raise SystemExit("bench.py: rmg_host_alloc failed")
+    buf = (C.c_char * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape), ptr
+
+
+def single_process_multi(args, core, Yt, X, G, d_ref, perms, idx):
+    """Rank 0 alone drives G GPUs through the C ABI (what an R session does): rmg_h2d_probe (the box's concurrent
+    host-link ceiling), rmg_lm_fit_multi and rmg_randomize_multi on ONE pinned config-2 matrix strong-sharded over the
+    G links, then the resident handle: one upload -> fit -> randomize -> FDR."""
+    import ctypes as C
+    import torch
+    from rminc_b200 import _lib
+    lib = _lib.load()
+    err = _lib.errbuf()
+    n, V = Yt.shape
+    p = X.shape[1]
+    res = {"n_gpus": G, "api": "one process, one host thread; voxel shards over devices 0..G-1"}
+    Yh_nv, yptr = pinned_numpy(lib, (n, V), np.float64)           # (n, V) C-order == V x n column-major
+    Oh_cv, optr = pinned_numpy(lib, (2 * p + 3, V), np.float64)
+    torch.from_numpy(Yh_nv).copy_(Yt)
+    Xf = np.asfortranarray(X)
+    # -- the ceiling: every link at once, 2 GiB per device per repeat
+    per = min(2 << 30, (V * n * 8) // G // 4096 * 4096)
+    gbs = (C.c_double * G)()
+    agg = C.c_double(0.0)
+    _lib.check(lib.rmg_h2d_probe(yptr, per, G, 3, gbs, C.byref(agg), err, len(err)), err)
+    one = C.c_double(0.0)
+    _lib.check(lib.rmg_h2d_probe(yptr, per, 1, 3, None, C.byref(one), err, len(err)), err)
+    res["h2d_probe"] = {"aggregate_gbs": agg.value, "per_gpu_gbs": [round(x, 2) for x in gbs], "one_gpu_alone_gbs": one.value,
+                        "bytes_per_gpu": per, "memory": "rmg_host_alloc: pinned, pages interleaved over the NUMA nodes"}
+    # -- mincLm, strong-sharded: one 28.3 GB volume over G links
+    def fit():
+        _lib.check(lib.rmg_lm_fit_multi(yptr, V, V, n, Xf.ctypes.data, p, None, 1.0, 99999999.0, optr, V, G, err, len(err)), err)
+    fit()
+    k = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        fit()
+    dt = (time.perf_counter() - t0) / k
+    h2d = V * n * 8
+    res["fit_e2e"] = {"value": V / dt, "unit": UNIT, "seconds": dt, "n_gpus": G, "scaling": "strong", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": V * (2 * p + 3) * 8, "host_link_gbs": h2d / dt / 1e9,
+                      "frac_of_h2d_probe": h2d / dt / 1e9 / agg.value,
+                      "api": "rmg_lm_fit_multi (C ABI; pinned host Y, V x n doubles, contiguous voxel shards over G links)"}
+    ref = core.lm_fit_torch(Yt[:, :4096], X)
+    far = core.lm_fit_torch(Yt[:, V - 4096:], X)
+    torch.cuda.synchronize()
+    parity = True
+    for blk, r in ((slice(0, 4096), ref), (slice(V - 4096, V), far)):
+        chk = torch.from_numpy(np.ascontiguousarray(Oh_cv[:, blk])).to(r.device)
+        scale = torch.maximum(r.abs(), r.square().mean(dim=1, keepdim=True).sqrt())
+        parity = parity and bool(((chk - r).abs() <= 1e-9 * scale).all())
+    # -- mincRandomize from the same host matrix, strong-sharded; upload hidden behind the permutation GEMM
+    if idx is not None:
+        cols_a = np.arange(p + 2, 2 * p + 2, dtype=np.int32)
+        idx_f = np.asfortranarray(idx, dtype=np.int32)
+        dist_h = np.empty((perms, p), order="F")
+
+        def perm(R_):
+            _lib.check(lib.rmg_randomize_multi(yptr, V, V, n, Xf.ctypes.data, p, None, 1.0, 99999999.0, idx_f.ctypes.data, R_,
+                                               cols_a.ctypes.data, p, 1, dist_h.ctypes.data, G, err, len(err)), err)
+        perm(8)
+        t0 = time.perf_counter()
+        perm(perms)
+        sec = time.perf_counter() - t0
+        res["randomize_e2e"] = {"value": perms / sec, "unit": "perms/s", "seconds": sec, "R": perms, "n_gpus": G, "h2d_bytes": h2d,
+                                "gemm_window_ms": core.last_kernel_ms(),
+                                "api": "rmg_randomize_multi (C ABI; pinned host Y -> voxel blocks per device on copy streams -> "
+                                       "all R permutations per block as it lands; designs factored and packed once for all devices)"}
+        if d_ref is not None:
+            parity = parity and bool(np.allclose(dist_h.T, d_ref.cpu().numpy(), rtol=1e-9, atol=0))
+    # -- the resident handle: one upload, then fit -> randomize -> FDR on the shards
+    h = C.c_void_p()
+    t0 = time.perf_counter()
+    _lib.check(lib.rmg_dataset_create(yptr, V, V, n, None, 1.0, 99999999.0, G, C.byref(h), err, len(err)), err)
+    _lib.check(lib.rmg_dataset_sync(h, err, len(err)), err)
+    t_up = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    _lib.check(lib.rmg_dataset_lm_fit(h, Xf.ctypes.data, p, optr, V, err, len(err)), err)
+    t_fit = time.perf_counter() - t0
+    fit_kernel_ms = core.last_kernel_ms()
+    t0 = time.perf_counter()
+    _lib.check(lib.rmg_dataset_lm_fit(h, Xf.ctypes.data, p, None, V, err, len(err)), err)
+    t_fit_resident = time.perf_counter() - t0
+    ds = {"upload_seconds": t_up, "upload_gbs": h2d / t_up / 1e9, "lm_fit_seconds_incl_d2h": t_fit,
+          "lm_fit_seconds_result_kept_on_device": t_fit_resident, "lm_fit_kernel_ms": fit_kernel_ms}
+    if idx is not None:
+        for name in ("randomize_seconds_first", "randomize_seconds_again"):
+            t0 = time.perf_counter()
+            _lib.check(lib.rmg_dataset_randomize(h, Xf.ctypes.data, p, idx_f.ctypes.data, perms, cols_a.ctypes.data, p, 1,
+                                                 dist_h.ctypes.data, err, len(err)), err)
+            ds[name] = time.perf_counter() - t0
+        ds["randomize_perms_per_s"] = perms / ds["randomize_seconds_again"]
+        ds["randomize_gemm_window_ms"] = core.last_kernel_ms()
+        if d_ref is not None:
+            parity = parity and bool(np.allclose(dist_h.T, d_ref.cpu().numpy(), rtol=1e-9, atol=0))
+    q = np.empty(V)
+    th = np.empty(5)
+    t0 = time.perf_counter()
+    _lib.check(lib.rmg_dataset_fdr(h, p + 3, core.STAT_T, float(n - p), 0.0, q.ctypes.data, th.ctypes.data, err, len(err)), err)
+    ds["fdr_seconds_one_column"] = time.perf_counter() - t0
+    parity = parity and bool(np.isfinite(q).all()) and bool((q >= 0).all() and (q <= 1).all())
+    lib.rmg_dataset_free(h)
+    ds["sequence"] = "rmg_dataset_create -> rmg_dataset_lm_fit -> rmg_dataset_randomize (x2) -> rmg_dataset_fdr -> rmg_dataset_free"
+    res["resident_dataset"] = ds
+    res["multi_parity"] = parity
+    lib.rmg_host_free(yptr)
+    lib.rmg_host_free(optr)
+    return res
+
+
+def config5(args, torch, dist, core, dev, rank, world, local_rank, barrier, design_fn):
+    """BASELINE config 5: mincLm on a 400x560x340 volume x 200 subjects, voxel-sharded across 8 GPUs.  Every rank fits
+    shard `rank` of 8 (9.52 M voxels, 15.23 GB of doubles generated on the device); rank 0 also fits the WHOLE volume
+    as uint16 on one GPU (30.5 GB; int64 offsets) and every rank times its shard end to end from pinned host memory."""
+    import psutil
+    from rminc_b200 import _lib
+    lib = _lib.load()
+    err = _lib.errbuf()
+    dims5, n5, p5, shards = (400, 560, 340), 200, 4, 8
+    V5 = int(np.prod(dims5))
+    Vs = V5 // shards
+    X5 = design_fn(n5, seed=5)
+    stream = torch.cuda.current_stream()
+    free0, total = torch.cuda.mem_get_info()
+    Ys = gen_Y(torch, Vs, n5, dev, seed=500 + rank)
+    outs = torch.empty((2 * p5 + 3, Vs), dtype=torch.float64, device=dev)
+    for _ in range(3):
+        core.lm_fit_torch(Ys, X5, out=outs)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        core.lm_fit_torch(Ys, X5, out=outs)
+    e1.record(stream)
+    barrier()
+    tt = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    bytes_shard = Vs * (8 * n5 + 8 * (2 * p5 + 3))
+    peak = measured_hbm_peak()[0]
+    res = {"workload": f"mincLm, 400x560x340 x 200 subjects, p = 4: {shards} voxel shards of {Vs} voxels (15.23 GB each)",
+           "shards_fitted": world, "shards_total": shards, "ms_per_shard": ms, "voxels_per_s": world * Vs / (ms * 1e-3),
+           "whole_volume_seconds_on_8_gpus": ms * 1e-3 * max(1, shards // world),
+           "achieved_gbs_per_gpu": bytes_shard / (ms * 1e-3) / 1e9, "frac": bytes_shard / (ms * 1e-3) / 1e9 / peak,
+           "kernel": core.last_fit_variant(), "hbm_used_gb_per_gpu": (free0 - torch.cuda.mem_get_info()[0]) / 1e9,
+           "hbm_total_gb": total / 1e9}
+    # end to end from this rank's pinned host shard
+    need = Vs * n5 * 8
+    if psutil.virtual_memory().available > need * world * 1.2 + (8 << 30):
+        bind_to_gpu_numa(local_rank)
+        hY = torch.empty((n5, Vs), dtype=torch.float64, pin_memory=True)
+        hY.copy_(Ys)
+        hO = torch.empty((2 * p5 + 3, Vs), dtype=torch.float64, pin_memory=True)
+        Xf = np.asfortranarray(X5)
+
+        def step():
+            _lib.check(lib.rmg_lm_fit(hY.data_ptr(), Vs, Vs, n5, Xf.ctypes.data, p5, None, 1.0, 99999999.0, hO.data_ptr(), Vs,
+                                      local_rank, err, len(err)), err)
+        step()
+        barrier()
+        t0 = time.perf_counter()
+        step()
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sec = float(tt.item())
+        res["e2e"] = {"value": world * Vs / sec, "unit": UNIT, "seconds": sec, "h2d_bytes_per_gpu": need,
+                      "host_link_gbs_per_gpu": need / sec / 1e9, "api": "rmg_lm_fit per rank on its pinned host shard"}
+        chk = hO[:, :4096].to(dev)
+        scl = torch.maximum(outs[:, :4096].abs(), outs[:, :4096].square().mean(dim=1, keepdim=True).sqrt())
+        assert bool(((chk - outs[:, :4096]).abs() <= 1e-9 * scl).all()), "config-5 e2e result differs from the device result"
+        del hY, hO
+    del Ys, outs
+    torch.cuda.empty_cache()
+    # the whole volume as uint16 on ONE GPU (rank 0): 15.2e9 samples -> 64-bit offsets everywhere
+    if rank == 0:
+        g = torch.Generator(device=dev).manual_seed(55)
+        U = torch.empty((n5, V5), dtype=torch.uint16, device=dev)
+        for j0 in range(0, n5, 10):
+            j1 = min(n5, j0 + 10)
+            blk = torch.empty((j1 - j0, V5), dtype=torch.float32, device=dev).normal_(30000.0, 400.0, generator=g)
+            U[j0:j1] = blk.round_().clamp_(0, 32767).to(torch.int16).view(torch.uint16)
+        del blk
+        nsl, slice_len = dims5[0], dims5[1] * dims5[2]
+        rs = np.random.default_rng(6)
+        smin = rs.normal(-0.8, 0.05, (n5, nsl))
+        sc = torch.from_numpy(np.ascontiguousarray(rs.uniform(1.5, 2.5, (n5, nsl)) / 65535.0)).to(dev)
+        of = torch.from_numpy(np.ascontiguousarray(smin)).to(dev)
+        ou = torch.empty((2 * p5 + 3, V5), dtype=torch.float64, device=dev)
+        for _ in range(2):
+            core.lm_fit_stored_torch(U, X5, sc, of, slice_len=slice_len, out=ou)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(max(1, args.steps // 2)):
+            core.lm_fit_stored_torch(U, X5, sc, of, slice_len=slice_len, out=ou)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        msu = e0.elapsed_time(e1) / max(1, args.steps // 2)
+        # int64 sanity row: the last 4096 voxels start 15.2e9 samples into U; refit them alone (as a shard that keeps its
+        # global slice index) and compare
+        tail = core.lm_fit_stored_torch(U[:, V5 - 4096:], X5, sc, of, slice_len=slice_len, v_offset=V5 - 4096)
+        torch.cuda.synchronize()
+        scl = torch.maximum(tail.abs(), tail.square().mean(dim=1, keepdim=True).sqrt())
+        ok = bool(((ou[:, V5 - 4096:] - tail).abs() <= 1e-9 * scl).all()) and bool(torch.isfinite(ou[0]).all())
+        res["whole_volume_uint16_one_gpu"] = {"voxels": V5, "ms": msu, "voxels_per_s": V5 / (msu * 1e-3),
+                                              "hbm_used_gb": (total - torch.cuda.mem_get_info()[0]) / 1e9,
+                                              "first_sample_offset_of_the_checked_rows": int((V5 - 4096)),
+                                              "samples_before_the_last_subject_row": int((n5 - 1) * V5),
+                                              "int64_offset_rows_match": ok, "kernel": core.last_fit_variant()}
+        del U, ou, sc, of
+        torch.cuda.empty_cache()
+    barrier()
+    return res
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -208,8 +432,10 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device; rminc_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")      # host-side barrier: waiting ranks must not spin a kernel
 
     def barrier():
         if world > 1:
@@ -695,6 +921,26 @@ def run_gpu_arm(args):
                                              "gemm_window_ms": core.last_kernel_ms()}
         del Yp, Op
 
+    # ---- the form R calls: ONE process (rank 0) driving all N GPUs through the C ABI, one config-2 volume strong-sharded
+    #      over the N host links; the other ranks wait on a host barrier
+    multi = None
+    if "multi" in args.parts and not args.small:
+        if rank == 0:
+            multi = single_process_multi(args, core, Yt, X, world, d_ref=(d if rand is not None else None),
+                                         perms=args.perms, idx=(idx if rand is not None else None))
+            if rand is not None and "randomize_e2e" in multi:
+                rand["e2e_single_process_multi"] = multi["randomize_e2e"]
+        if world > 1:
+            dist.barrier(group=host_group)
+    barrier()
+
+    # ---- config 5 (capacity): 400x560x340 x 200 subjects = 121.9 GB of doubles in 8 voxel shards of 9.52 M voxels
+    cfg5 = None
+    if "cfg5" in args.parts and not args.small:
+        del Yt, out
+        torch.cuda.empty_cache()
+        cfg5 = config5(args, torch, dist, core, dev, rank, world, local_rank, barrier, design)
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and "cpu" in args.parts:
@@ -716,7 +962,10 @@ def run_gpu_arm(args):
                        "sharding": "contiguous voxel shards, no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
             "masked_variant": masked, "vertexLm": vertex, "covariate": cov, "stored_u16": stored, "vertexTFCE": tfce, "randomize": rand,
+            "single_process_multi": multi, "multi_parity": (multi or {}).get("multi_parity"), "config5": cfg5,
         }
+        if e2e is not None and multi is not None:
+            e2e["single_process_multi"] = multi.get("fit_e2e")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -733,10 +982,12 @@ def main():
     ap.add_argument("--skip-extras", action="store_true", help="only the device-resident headline")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--tfce-perms", type=int, default=64, help="permutations timed for the vertexTFCE line")
-    ap.add_argument("--parts", default="masked,vertex,cov,stored,tfce,randomize,e2e,e2e_u16,cpu",
+    ap.add_argument("--parts", default="masked,vertex,cov,stored,tfce,randomize,e2e,e2e_u16,multi,cpu",
                     help="which extra measurements to run beside the headline (comma list)")
     args = ap.parse_args()
     args.parts = set() if args.skip_extras else set(args.parts.split(","))
+    if not args.skip_extras and args.gpus == 8 and "nocfg5" not in args.parts:
+        args.parts.add("cfg5")                      # the capacity configuration is quoted on 8 GPUs
     if args.skip_cpu:
         args.parts.discard("cpu")
     if args.impl == "reference":

@@ -337,6 +337,57 @@ int rmg_randomize_stored_multi(const void *U, int dtype, int64_t V, int64_t ldU,
                                const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
                                double *dist, int n_gpus, char *err, size_t errlen);
 
+/*
+ * The resident dataset.  mincLm stores `data` and the call so that mincRandomize, mincAnova and mincFDR can be run on
+ * the same files later (R/minc_voxel_statistics.R:911-912, :1296-1297, :1457-1477); the reference re-reads every file
+ * each time.  Here the staged subjects x voxels matrix is uploaded ONCE, sharded over n_gpus devices of the box in
+ * contiguous voxel ranges inside this one process (create_parallel_mask + mclapply, :848-906), and stays in HBM behind
+ * an opaque handle until rmg_dataset_free.  Every routine below runs on the resident shards; the only exchange of the
+ * path is the element-wise max of the per-shard R x ncols permutation maxima.
+ *   rmg_dataset_create          Y V x n host doubles (pinned or pageable), mask / mask_lo / mask_hi as rmg_lm_fit;
+ *                               n_gpus <= 0: every visible device.  The upload is queued in voxel blocks and the call
+ *                               returns while it is still in flight (for pinned Y); consumers wait block by block.
+ *   rmg_dataset_create_stored   the volumes in their stored type (arguments as rmg_lm_fit_stored); the samples cross the
+ *                               host link as stored and are expanded once on the device into the resident doubles.
+ *   rmg_dataset_sync            waits until the whole matrix is resident.
+ *   rmg_dataset_lm_fit / _anova the fit of rmg_lm_fit / rmg_anova_fit; out (host, V x ncol, may be NULL) receives the
+ *                               result, which ALSO stays resident for rmg_dataset_fdr.
+ *   rmg_dataset_randomize       rmg_randomize on the resident matrix (the per-voxel sums every permutation shares are
+ *                               kept on the handle, so a second test pays no pass over Y for them).
+ *   rmg_dataset_fdr             rmg_fdr on column `column` of the resident result of the last fit, with the dataset's mask.
+ */
+typedef struct rmg_dataset rmg_dataset;
+int rmg_dataset_create(const double *Y, int64_t V, int64_t ldY, int n, const double *mask, double mask_lo, double mask_hi,
+                       int n_gpus, rmg_dataset **ds, char *err, size_t errlen);
+int rmg_dataset_create_stored(const void *U, int dtype, int64_t V, int64_t ldU, int n, const double *scale, const double *offset,
+                              double voxel_min, int64_t slice_len, const double *mask, double mask_lo, double mask_hi,
+                              int n_gpus, rmg_dataset **ds, char *err, size_t errlen);
+void rmg_dataset_free(rmg_dataset *ds);
+int64_t rmg_dataset_voxels(const rmg_dataset *ds);
+int rmg_dataset_subjects(const rmg_dataset *ds);
+int rmg_dataset_gpus(const rmg_dataset *ds);
+int rmg_dataset_sync(rmg_dataset *ds, char *err, size_t errlen);
+int rmg_dataset_lm_fit(rmg_dataset *ds, const double *X, int p, double *out, int64_t ldOut, char *err, size_t errlen);
+int rmg_dataset_anova(rmg_dataset *ds, const double *X, int p, const int32_t *asgn, double *out, int64_t ldOut,
+                      char *err, size_t errlen);
+int rmg_dataset_randomize(rmg_dataset *ds, const double *X, int p, const int32_t *idx, int R, const int32_t *cols, int ncols,
+                          int two_sided, double *dist, char *err, size_t errlen);
+int rmg_dataset_fdr(rmg_dataset *ds, int column, int stat_type, double df1, double df2, double *qvalues, double *thresholds,
+                    char *err, size_t errlen);
+/* Pinned host staging buffers (the ring of pageable uploads, the packed permutation operand) are kept across calls;
+ * this returns every idle one to the OS. */
+void rmg_release_host_buffers(void);
+/* Page-locked host memory with its pages interleaved over the NUMA nodes the process may allocate on: where a host
+ * layer should stage Y (mincTable's matrix, R/minc_interface.R:1031-1077) so that every GPU's copy engine reads it
+ * at the link rate.  NULL without a CUDA device or when the allocation fails. */
+void *rmg_host_alloc(size_t bytes);
+void rmg_host_free(void *ptr);
+/* Concurrent pinned host -> device copy rate of the box: device g copies bytes_per_gpu bytes starting at
+ * host + g * bytes_per_gpu, all n_gpus devices at once, `repeats` times.  gbs[g] (nullable): GB/s seen by device g;
+ * *aggregate_gbs (nullable): all bytes / wall time.  The ceiling end-to-end numbers are reported against. */
+int rmg_h2d_probe(const void *host, size_t bytes_per_gpu, int n_gpus, int repeats, double *gbs, double *aggregate_gbs,
+                  char *err, size_t errlen);
+
 /* Timing of the most recent rmg_*_device / host call on this thread, for bench.py:
  * milliseconds spent in the dominant kernel(s), measured with CUDA events on the stream the
  * kernels were launched on (host entry points only; 0 if unavailable). */

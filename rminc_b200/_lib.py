@@ -72,6 +72,22 @@ SIGNATURES = {
     "rmg_randomize_stored_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_double, C.c_int64, C.c_void_p, C.c_int] + _MASK + _PERM
                                    + [C.c_void_p, C.c_int] + _ERR),
+    "rmg_dataset_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int] + _MASK + [C.c_int, C.POINTER(C.c_void_p)] + _ERR),
+    "rmg_dataset_create_stored": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
+                                            C.c_int64] + _MASK + [C.c_int, C.POINTER(C.c_void_p)] + _ERR),
+    "rmg_dataset_free": (None, [C.c_void_p]),
+    "rmg_dataset_voxels": (C.c_int64, [C.c_void_p]),
+    "rmg_dataset_subjects": (C.c_int, [C.c_void_p]),
+    "rmg_dataset_gpus": (C.c_int, [C.c_void_p]),
+    "rmg_dataset_sync": (C.c_int, [C.c_void_p] + _ERR),
+    "rmg_dataset_lm_fit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64] + _ERR),
+    "rmg_dataset_anova": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64] + _ERR),
+    "rmg_dataset_randomize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + _PERM + [C.c_void_p] + _ERR),
+    "rmg_dataset_fdr": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p] + _ERR),
+    "rmg_release_host_buffers": (None, []),
+    "rmg_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "rmg_host_free": (None, [C.c_void_p]),
+    "rmg_h2d_probe": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)] + _ERR),
     "rmg_last_kernel_ms": (C.c_double, []),
     "rmg_last_fit_variant": (C.c_int, []),
     "rmg_launch_count": (C.c_int64, []),

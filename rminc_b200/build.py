@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librminc_b200.so")
 
-SOURCES = ["capi.cu", "lm_kernels.cu", "lm_cov.cu", "lm_packed.cu", "fdr.cu", "tfce.cu", "randomize.cu", "perm_gemm.cu", "design.cpp"]
+SOURCES = ["capi.cu", "lm_kernels.cu", "lm_cov.cu", "lm_packed.cu", "fdr.cu", "tfce.cu", "randomize.cu", "dataset.cu", "perm_gemm.cu", "design.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -46,18 +46,34 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     build_dir = os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
+    import re
+
+    def deps_time(path, seen=None):
+        """Newest mtime of `path` and of every header it includes (quoted includes, recursively)."""
+        seen = seen if seen is not None else set()
+        path = os.path.normpath(path)
+        if path in seen or not os.path.exists(path):
+            return 0.0
+        seen.add(path)
+        t = os.path.getmtime(path)
+        for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', open(path).read(), flags=re.M):
+            t = max(t, deps_time(os.path.join(os.path.dirname(path), inc), seen))
+        return t
+
     procs = []
     for src in SOURCES:
         path = os.path.join(CSRC, src)
         if not os.path.exists(path):
             continue
         obj = os.path.join(build_dir, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(deps_time(path), os.path.getmtime(__file__)):
+            continue
         cmd = [nvcc(), *NVCC_FLAGS, "-c", path, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
     for cmd, pr in procs:
         out, _ = pr.communicate()
         if pr.returncode != 0:

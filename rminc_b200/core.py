@@ -548,6 +548,132 @@ def randomize_stored(U, X, idx, cols, scale=None, offset=None, voxel_min=0.0, sl
     return dist
 
 
+# ------------------------------------------------------------------ the resident dataset
+class Dataset:
+    """Y uploaded once, sharded over `n_gpus` devices of the box inside this process, resident until close().
+
+    mincLm keeps `data` and the call so mincRandomize / mincAnova / mincFDR can be run on the same files later
+    (R/minc_voxel_statistics.R:911-912, :1457-1477) and each re-reads every file; here the staged matrix stays in
+    HBM (rmg_dataset_*).  Y: V x n doubles, or uint16 / float32 stored samples with scale / offset tables
+    (lm_fit_stored's arguments).  mask / mask_lo / mask_hi as lm_fit.  n_gpus None: every visible device."""
+
+    def __init__(self, Y, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, n_gpus=None, scale=None, offset=None,
+                 voxel_min=0.0, slice_len=None):
+        Y = np.asarray(Y)
+        if Y.ndim != 2:
+            raise ValueError("Y must be V x n")
+        stored = Y.dtype in (np.uint16, np.float32)
+        if not stored and not (Y.dtype == np.float64 and Y.flags.f_contiguous):
+            Y = _lib.as_f64_fortran(Y)
+        if stored and not Y.flags.f_contiguous:
+            Y = np.asfortranarray(Y)
+        V, n = Y.shape
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(np.asarray(mask, dtype=np.float64).reshape(-1))
+            if m.shape[0] != V:
+                raise ValueError("mask length must equal the number of voxels")
+        self._handle = C.c_void_p()
+        self.V, self.n = V, n
+        self.out_cols = 0
+        err = _lib.errbuf()
+        lib = _lib.load()
+        g = 0 if n_gpus is None else int(n_gpus)
+        mp = m.ctypes.data if m is not None else None
+        if stored:
+            dtype, sc, of, slice_len = _stored_tables(Y.dtype, V, n, scale, offset, slice_len)
+            rc = lib.rmg_dataset_create_stored(Y.ctypes.data, dtype, V, max(V, 1), n, sc.ctypes.data if sc is not None else None,
+                                               of.ctypes.data if of is not None else None, float(voxel_min), slice_len, mp,
+                                               mask_lo, mask_hi, g, C.byref(self._handle), err, len(err))
+        else:
+            rc = lib.rmg_dataset_create(Y.ctypes.data, V, max(V, 1), n, mp, mask_lo, mask_hi, g, C.byref(self._handle), err, len(err))
+        _lib.check(rc, err)
+        self._keep = (Y, m)          # pinned sources may still be read by the queued upload until sync()
+        self.n_gpus = lib.rmg_dataset_gpus(self._handle)
+
+    def _h(self):
+        if not self._handle:
+            raise RmincGpuError(_lib.RMG_ERR_INVALID, "the dataset has been closed")
+        return self._handle
+
+    def sync(self):
+        err = _lib.errbuf()
+        _lib.check(_lib.load().rmg_dataset_sync(self._h(), err, len(err)), err)
+        self._keep = None
+        return self
+
+    def lm_fit(self, X, want_result=True):
+        """mincLm's native step on the resident matrix: V x (2p+3) (None when want_result is False; the result also
+        stays resident for fdr())."""
+        X = _lib.as_f64_fortran(X)
+        if X.ndim != 2 or X.shape[0] != self.n:
+            raise ValueError("X must be n x p with n == ncol(Y)")
+        p = X.shape[1]
+        out = np.empty((self.V, 2 * p + 3), order="F") if want_result else None
+        err = _lib.errbuf()
+        rc = _lib.load().rmg_dataset_lm_fit(self._h(), X.ctypes.data, p, out.ctypes.data if want_result else None, max(self.V, 1),
+                                            err, len(err))
+        _lib.check(rc, err)
+        self.out_cols = 2 * p + 3
+        return out
+
+    def anova(self, X, asgn):
+        X = _lib.as_f64_fortran(X)
+        p = X.shape[1]
+        asgn = np.ascontiguousarray(asgn, dtype=np.int32)
+        if asgn.shape != (p,):
+            raise ValueError("asgn must have one entry per design column")
+        nterms = int(asgn.max()) if p else 0
+        out = np.empty((self.V, nterms), order="F")
+        err = _lib.errbuf()
+        rc = _lib.load().rmg_dataset_anova(self._h(), X.ctypes.data, p, asgn.ctypes.data, out.ctypes.data, max(self.V, 1), err, len(err))
+        _lib.check(rc, err)
+        self.out_cols = nterms
+        return out
+
+    def randomize(self, X, idx, cols, two_sided=True):
+        X = _lib.as_f64_fortran(X)
+        p = X.shape[1]
+        idx, cols = _prep_perm(idx, self.n, cols)
+        if cols.size and (cols.min() < 0 or cols.max() >= 2 * p + 3):
+            raise ValueError("cols entries must be in 0..2p+2")
+        R = idx.shape[1]
+        dist = np.empty((R, len(cols)), order="F")
+        err = _lib.errbuf()
+        rc = _lib.load().rmg_dataset_randomize(self._h(), X.ctypes.data, p, idx.ctypes.data, R, cols.ctypes.data, len(cols),
+                                               int(bool(two_sided)), dist.ctypes.data, err, len(err))
+        _lib.check(rc, err)
+        return dist
+
+    def fdr(self, column, stat_type, df1, df2=0.0):
+        """mincFDR's native step on one column of the resident result of the last fit: (q-values [V], thresholds [5])."""
+        q = np.empty(self.V)
+        th = np.empty(5)
+        err = _lib.errbuf()
+        rc = _lib.load().rmg_dataset_fdr(self._h(), int(column), int(stat_type), float(df1), float(df2), q.ctypes.data,
+                                         th.ctypes.data, err, len(err))
+        _lib.check(rc, err)
+        return q, th
+
+    def close(self):
+        if self._handle:
+            _lib.load().rmg_dataset_free(self._handle)
+            self._handle = C.c_void_p()
+            self._keep = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
 # ------------------------------------------------------------------ device-resident (torch) forms
 def _torch_stream(t):
     import torch

@@ -11,6 +11,11 @@
 #include <mutex>
 #include <thread>
 
+#if defined(__linux__)
+#include <sys/syscall.h>
+#include <unistd.h>
+#endif
+
 #include "capi_common.hpp"
 
 namespace rmg {
@@ -55,13 +60,103 @@ int host_threads()
     int nt = 0;
     if (const char *e = std::getenv("RMG_HOST_THREADS")) nt = std::atoi(e);
     if (nt <= 0) {
+        // hardware_concurrency() honours the cpuset of the container.  Under torchrun the ranks of the box share the
+        // cores; a single process (R, or rank 0 driving every GPU) owns them all.  (Dividing by the number of VISIBLE
+        // GPUs, as round 1 did, left a one-GPU call on an 8-GPU box with an eighth of the cores.)
         const unsigned hw = std::thread::hardware_concurrency();
-        int gpus = 0;
-        if (cudaGetDeviceCount(&gpus) != cudaSuccess) { cudaGetLastError(); gpus = 1; }
-        nt = (int)(hw ? hw : 1) / std::max(1, gpus);
+        int ranks = 1;
+        if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, std::atoi(e));
+        nt = (int)(hw ? hw : 1) / ranks;
     }
-    cached = std::max(1, std::min(nt, 16));
+    cached = std::max(1, std::min(nt, 64));
     return cached;
+}
+
+// ---- pinned host pool
+namespace {
+struct PinnedBuf {
+    void *ptr;
+    size_t bytes;
+    bool in_use;
+};
+std::mutex g_pin_mu;
+std::vector<PinnedBuf> g_pin;
+
+// Interleave the pages of the next allocations over every NUMA node this process may allocate on (raw syscalls:
+// libnuma is not a dependency).  Best effort; restores the default policy on destruction.
+struct ScopedInterleave {
+    bool active = false;
+    ScopedInterleave()
+    {
+#if defined(__linux__) && defined(SYS_set_mempolicy) && defined(SYS_get_mempolicy)
+        if (std::getenv("RMG_NO_NUMA_INTERLEAVE")) return;
+        unsigned long mask[16] = {0};
+        // MPOL_F_MEMS_ALLOWED = 4: the nodes the cpuset lets us allocate on
+        if (syscall(SYS_get_mempolicy, nullptr, mask, sizeof(mask) * 8, nullptr, 4) != 0) return;
+        int nodes = 0;
+        for (unsigned long w : mask) nodes += __builtin_popcountl(w);
+        if (nodes < 2) return;
+        active = syscall(SYS_set_mempolicy, 3 /* MPOL_INTERLEAVE */, mask, sizeof(mask) * 8) == 0;
+#endif
+    }
+    ~ScopedInterleave()
+    {
+#if defined(__linux__) && defined(SYS_set_mempolicy)
+        if (active) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+#endif
+    }
+};
+}  // namespace
+
+void *pinned_acquire(size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        PinnedBuf *best = nullptr;
+        for (auto &b : g_pin)
+            if (!b.in_use && b.bytes >= bytes && (!best || b.bytes < best->bytes)) best = &b;
+        // a much larger idle buffer is not worth holding hostage for a small request
+        if (best && best->bytes <= 4 * bytes + (1u << 20)) {
+            best->in_use = true;
+            return best->ptr;
+        }
+    }
+    void *p = nullptr;
+    {
+        ScopedInterleave numa;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+    }
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pin.push_back({p, bytes, true});
+    return p;
+}
+
+void pinned_release(void *ptr)
+{
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (auto &b : g_pin)
+        if (b.ptr == ptr) b.in_use = false;
+}
+
+void pinned_trim()
+{
+    std::vector<void *> dead;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        for (size_t i = 0; i < g_pin.size();)
+            if (!g_pin[i].in_use) {
+                dead.push_back(g_pin[i].ptr);
+                g_pin.erase(g_pin.begin() + i);
+            } else {
+                ++i;
+            }
+    }
+    for (void *p : dead) cudaFreeHost(p);
+    cudaGetLastError();
 }
 
 int device_sm_count(int device)
@@ -151,46 +246,16 @@ int factor_or_fail(const double *X, int n, int p, Design &D, char *err, size_t e
 }
 
 namespace {
-
-// Device-resident design constants, cached per (device, X).  A mincLm call, every chunk of
-// the host pipeline and repeated calls with the same model matrix share one entry, so the
-// steady-state cost of a call is the kernel launch alone: no re-factorisation, no upload and
-// no allocation on the caller's stream.  Entries are immutable once `ready` has fired; consumers
-// make their stream wait on it.
-struct CachedDesign {
-    int device = -1;
-    std::vector<double> X;   // n x p, the key ...
-    std::vector<int32_t> asgn;   // ... together with the term assignment (empty = lm epilogue)
-    std::vector<double> w;       // ... and the observation weights (empty = unweighted)
-    Design D;
-    DevDesign *dd = nullptr;
-    double *qt = nullptr;
-    double *rowscale = nullptr;  // device copy of sqrt(w) (weighted fits)
-    cudaEvent_t ready = nullptr;
-    uint64_t last_use = 0;
-    ~CachedDesign()
-    {
-        // cudaFree synchronises the device: no kernel can still be reading the buffers
-        int cur = 0;
-        if (device >= 0 && cudaGetDevice(&cur) == cudaSuccess) {
-            cudaSetDevice(device);
-            if (dd) cudaFree(dd);
-            if (qt) cudaFree(qt);
-            if (rowscale) cudaFree(rowscale);
-            if (ready) cudaEventDestroy(ready);
-            cudaSetDevice(cur);
-        }
-    }
-};
-
 std::mutex g_cache_mu;
 std::vector<std::shared_ptr<CachedDesign>> g_cache;
 uint64_t g_cache_tick = 0;
 constexpr size_t kCacheEntries = 16;
 
+}  // namespace
+
 // Looks up (or builds) the cached design for X on the current device.  rc != RMG_OK on error.
 std::shared_ptr<CachedDesign> design_cache_get(int device, const double *X, int n, int p, const int32_t *asgn,
-                                               int &rc, char *err, size_t errlen, const double *w = nullptr)
+                                               int &rc, char *err, size_t errlen, const double *w)
 {
     const size_t cnt = (size_t)n * p;
     {
@@ -273,7 +338,6 @@ LmPlan plan_from_env(int device)
     return plan;
 }
 
-}  // namespace
 }  // namespace rmg
 
 using namespace rmg;
@@ -462,8 +526,7 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
                     });
                     RMG_CUDA(cudaMemcpy2DAsync(dstdev + (size_t)r0 * ldc * es, (size_t)ldc * es, dst, (size_t)cv * es, (size_t)cv * es,
                                                (size_t)rows, cudaMemcpyHostToDevice, st[b]));
-                    RMG_CUDA(cudaEventRecord(ring.done[slot], st[b]));
-                    ring.busy[slot] = true;
+                    RMG_CUDA(ring.mark(slot, device, st[b]));
                 }
             }
             if (mask) RMG_CUDA(cudaMemcpyAsync(dM[b], mask + v0, (size_t)cv * 8, cudaMemcpyHostToDevice, st[b]));

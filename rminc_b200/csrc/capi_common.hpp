@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -59,16 +60,28 @@ void fill_dev_design(const Design &D, DevDesign &dd);
 // Row-major [n][KP] copy of Q (columns >= rank zero).
 std::vector<double> make_qt(const Design &D, int KP);
 
-// Runs fn(begin, end) over [0, count) on up to hardware_concurrency host threads (host-side
-// preparation of the permutation test: factorisations and operand packing).
-// Host worker threads for this process: the cores are shared with the other ranks of the box (one
-// process per GPU), so take hardware_concurrency / visible GPUs, at most 16 (RMG_HOST_THREADS overrides).
+// Process-wide pool of pinned (page-locked, portable) host buffers.  cudaHostAlloc costs ~0.3 ms per MiB, so the staging
+// ring of a pageable upload (4 x 128 MiB) and the packed permutation operand are leased from here and kept across
+// calls; rmg_release_host_buffers() returns every idle buffer to the OS.  Buffers are allocated with the pages
+// interleaved over the NUMA nodes the process may use, so that the DMA engines of GPUs on either socket read them at
+// the same rate.
+void *pinned_acquire(size_t bytes);       // nullptr when the allocation fails
+void pinned_release(void *ptr);
+void pinned_trim();
+
+// Host worker threads available to THIS caller.  One process per GPU (torchrun): the cores are shared with the other
+// ranks of the box (LOCAL_WORLD_SIZE); a single process driving several GPUs owns them all.  RMG_HOST_THREADS overrides.
 int host_threads();
+// > 1 while this thread is one of several concurrent per-GPU workers of a call: parallel_for takes its share of the cores
+extern thread_local int tl_host_share;
+
+// Runs fn(begin, end) over [0, count) on up to host_threads() threads (host-side preparation of the
+// permutation test: factorisations and operand packing; staging copies of pageable uploads).
 
 template <class Fn>
 inline void parallel_for(int count, Fn fn)
 {
-    int nt = host_threads();
+    int nt = std::max(1, host_threads() / std::max(1, tl_host_share));
     if (nt > count / 8) nt = count / 8;
     if (nt <= 1) {
         fn(0, count);
@@ -85,22 +98,22 @@ inline void parallel_for(int count, Fn fn)
 // Pageable host memory (R's heap, plain numpy) reaches only ~9.5 GB/s through cudaMemcpy2DAsync
 // (the driver stages it single-threaded); pinned memory reaches the PCIe rate (55 GB/s).  For
 // pageable Y the rows of a chunk are therefore copied by all host threads into a small ring of
-// pinned staging buffers, and the DMA engine drains the ring while the next buffer is being filled.
+// pinned staging buffers, and the DMA engines drain the ring while the next buffer is being filled.
+// One ring can feed several devices: a slot remembers the device whose stream last read it.
 struct PinnedRing {
     static constexpr int kSlots = 4;
+    static constexpr int kMaxDev = 16;
     char *buf[kSlots] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
-    bool busy[kSlots] = {false, false, false, false};
+    cudaEvent_t done[kSlots][kMaxDev] = {};
+    int busy_dev[kSlots] = {-1, -1, -1, -1};
     size_t slot_bytes = 0;
     int next = 0;
     cudaError_t init(size_t bytes)
     {
         slot_bytes = bytes;
         for (int s = 0; s < kSlots; ++s) {
-            cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&buf[s]), bytes, cudaHostAllocDefault);
-            if (e != cudaSuccess) return e;
-            e = cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming);
-            if (e != cudaSuccess) return e;
+            buf[s] = static_cast<char *>(pinned_acquire(bytes));
+            if (!buf[s]) return cudaErrorMemoryAllocation;
         }
         return cudaSuccess;
     }
@@ -109,20 +122,38 @@ struct PinnedRing {
     {
         slot = next;
         next = (next + 1) % kSlots;
-        if (busy[slot]) {
-            cudaError_t e = cudaEventSynchronize(done[slot]);
+        if (busy_dev[slot] >= 0) {
+            cudaError_t e = cudaEventSynchronize(done[slot][busy_dev[slot]]);
             if (e != cudaSuccess) return e;
-            busy[slot] = false;
+            busy_dev[slot] = -1;
         }
         return cudaSuccess;
     }
+    // the copy out of `slot` has been queued on `st`, a stream of `device` (which is current)
+    cudaError_t mark(int slot, int device, cudaStream_t st)
+    {
+        if (device < 0 || device >= kMaxDev) return cudaErrorInvalidDevice;
+        if (!done[slot][device]) {
+            cudaError_t e = cudaEventCreateWithFlags(&done[slot][device], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        cudaError_t e = cudaEventRecord(done[slot][device], st);
+        if (e == cudaSuccess) busy_dev[slot] = device;
+        return e;
+    }
+    // waits for every queued copy, then hands the slots back to the pool
     void release_all()
     {
         for (int s = 0; s < kSlots; ++s) {
-            if (done[s]) cudaEventDestroy(done[s]);
-            if (buf[s]) cudaFreeHost(buf[s]);
+            if (busy_dev[s] >= 0) cudaEventSynchronize(done[s][busy_dev[s]]);
+            busy_dev[s] = -1;
+            for (int d = 0; d < kMaxDev; ++d)
+                if (done[s][d]) {
+                    cudaEventDestroy(done[s][d]);
+                    done[s][d] = nullptr;
+                }
+            if (buf[s]) pinned_release(buf[s]);
             buf[s] = nullptr;
-            done[s] = nullptr;
         }
     }
 };
@@ -148,18 +179,21 @@ inline bool staging_plan(const void *src, double total_bytes, size_t row_bytes, 
            (forced_rows > 0 || total_bytes >= 256.0 * 1024 * 1024);
 }
 
-// n rows of row_bytes bytes (source pitch spitch) -> device rows of pitch dpitch, queued on `up`.  ring == nullptr:
-// one strided copy (pinned or small sources); else all host threads copy groups of rows into the next free pinned
-// slot and the DMA engine drains the slots behind them.
+// n rows of row_bytes bytes (source pitch spitch) -> device rows of pitch dpitch, queued on `up`, a stream of `device`
+// (made current).  ring == nullptr: one strided copy (pinned or small sources); else all host threads copy groups of
+// rows into the next free pinned slot and the DMA engine drains the slots behind them.
 inline cudaError_t upload_rows(PinnedRing *ring, int rows_per_slot, char *dst, size_t dpitch, const char *src, size_t spitch,
-                               size_t row_bytes, int n, cudaStream_t up)
+                               size_t row_bytes, int n, cudaStream_t up, int device)
 {
     if (row_bytes == 0 || n <= 0) return cudaSuccess;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return e;
     if (!ring) return cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, (size_t)n, cudaMemcpyHostToDevice, up);
+    rows_per_slot = (int)std::max<size_t>(1, std::min<size_t>((size_t)rows_per_slot, ring->slot_bytes / row_bytes));
     for (int r0 = 0; r0 < n; r0 += rows_per_slot) {
         const int rows = std::min(rows_per_slot, n - r0);
         int slot = 0;
-        cudaError_t e = ring->acquire(slot);
+        e = ring->acquire(slot);
         if (e != cudaSuccess) return e;
         char *buf = ring->buf[slot];
         const int pieces = rows * 8;                   // 8 column pieces per row keep every thread busy
@@ -172,9 +206,8 @@ inline cudaError_t upload_rows(PinnedRing *ring, int rows_per_slot, char *dst, s
         });
         e = cudaMemcpy2DAsync(dst + (size_t)r0 * dpitch, dpitch, buf, row_bytes, row_bytes, (size_t)rows, cudaMemcpyHostToDevice, up);
         if (e != cudaSuccess) return e;
-        e = cudaEventRecord(ring->done[slot], up);
+        e = ring->mark(slot, device, up);
         if (e != cudaSuccess) return e;
-        ring->busy[slot] = true;
     }
     return cudaSuccess;
 }
@@ -203,6 +236,41 @@ inline int check_stored_args(int dtype, const double *scale, const double *offse
     }
     return RMG_OK;
 }
+
+// Device-resident design constants, cached per (device, X).  A mincLm call, every chunk of
+// the host pipeline and repeated calls with the same model matrix share one entry, so the
+// steady-state cost of a call is the kernel launch alone: no re-factorisation, no upload and
+// no allocation on the caller's stream.  Entries are immutable once `ready` has fired; consumers
+// make their stream wait on it.
+struct CachedDesign {
+    int device = -1;
+    std::vector<double> X;   // n x p, the key ...
+    std::vector<int32_t> asgn;   // ... together with the term assignment (empty = lm epilogue)
+    std::vector<double> w;       // ... and the observation weights (empty = unweighted)
+    Design D;
+    DevDesign *dd = nullptr;
+    double *qt = nullptr;
+    double *rowscale = nullptr;  // device copy of sqrt(w) (weighted fits)
+    cudaEvent_t ready = nullptr;
+    uint64_t last_use = 0;
+    ~CachedDesign()
+    {
+        // cudaFree synchronises the device: no kernel can still be reading the buffers
+        int cur = 0;
+        if (device >= 0 && cudaGetDevice(&cur) == cudaSuccess) {
+            cudaSetDevice(device);
+            if (dd) cudaFree(dd);
+            if (qt) cudaFree(qt);
+            if (rowscale) cudaFree(rowscale);
+            if (ready) cudaEventDestroy(ready);
+            cudaSetDevice(cur);
+        }
+    }
+};
+
+std::shared_ptr<CachedDesign> design_cache_get(int device, const double *X, int n, int p, const int32_t *asgn,
+                                               int &rc, char *err, size_t errlen, const double *w = nullptr);
+LmPlan plan_from_env(int device);
 
 // Factor X and translate the reference's error contract.  0 or RMG_ERR_*.
 int factor_or_fail(const double *X, int n, int p, Design &D, char *err, size_t errlen, const double *w = nullptr);

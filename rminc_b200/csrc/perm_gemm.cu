@@ -36,30 +36,11 @@ __device__ __forceinline__ double rcp_pos(double x)
     return r;
 }
 
-struct PermKernelParams {
-    const double *Y;
-    int64_t V, ldY;
-    int n, p, R, ncols, two_sided, shift;   // R: permutations of THIS launch (a batch)
-    int Rstride;                             // permutations of the whole call (row stride of keys)
-    int tcol[kPermMaxCols];          // coefficient index of each requested t-column
-    const double *Apack;             // [n_pt][n_kc][A chunk] fragment-major
-    const PermConst *pc;             // [R]
-    const double *y0;                // [V] first sample (0 when !shift)
-    const double *yy;                // [V] |y - y0|^2, or -1 for voxels outside the mask
-    const double *ys;                // [V] sum_j (y_j - y0)  (only when the intercept row is skipped)
-    unsigned long long *keys;        // [ncols][R]
-    // geometry of Apack, so the (rare) exact path can read Q_r[j][k] back out of the packed operand
-    int inv, kg, pg, wm, warps_m, a_chunk, perms_per_cta;
-    unsigned char *vflag;            // [V] set when some permutation's one-pass rss lost too many digits
-    int n_pt, n_kc;
-    int debug_skip;                  // diagnostics only: 1 = skip the statistics epilogue, 2 = skip the MMAs
-};
-
 // ---- K5: one pass over Y for the per-voxel quantities every permutation shares.
 __global__ void __launch_bounds__(256)
 perm_prepass_kernel(const double *__restrict__ Y, int64_t V, int64_t ldY, int n, const double *__restrict__ mask,
                     double lo, double hi, int shift, double *__restrict__ y0, double *__restrict__ yy,
-                    double *__restrict__ ys, unsigned char *__restrict__ vflag, int *__restrict__ any_zero_row)
+                    double *__restrict__ ys, int *__restrict__ any_zero_row)
 {
     const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (v >= V) return;
@@ -106,12 +87,10 @@ perm_prepass_kernel(const double *__restrict__ Y, int64_t V, int64_t ldY, int n,
     y0[v] = f0;
     yy[v] = a0 ? s0 : -1.0;
     ys[v] = t0;
-    vflag[v] = 0;
     if (two) {
         y0[v + 1] = f1;
         yy[v + 1] = a1 ? s1 : -1.0;
         ys[v + 1] = t1;
-        vflag[v + 1] = 0;
     }
     if ((!a0 || (two && !a1)) && *any_zero_row == 0) *any_zero_row = 1;  // benign race: all writers store 1
 }
@@ -121,6 +100,13 @@ __global__ void perm_floor_keys_kernel(unsigned long long *keys, int nk, const i
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nk && *any_zero_row) atomicMax(&keys[i], ordered_key(0.0));
+}
+
+// An odd voxel count: the GEMM tiles cover an even number of voxels (16-byte bulk copies); the last voxel of the shard
+// is handed to the explicit-residual kernel instead (unless it lies outside the mask).
+__global__ void perm_flag_voxel_kernel(unsigned char *vflag, const double *yy, int64_t v)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0 && yy[v] >= 0.0) vflag[v] = 1;
 }
 
 // final: monotone proxy m = sign(b) b^2 / rss  ->  t = sign(m) sqrt(|m| * rdf / ct)
@@ -470,29 +456,21 @@ bool perm_gemm_supported(int n, int p, int64_t V, int64_t ldY, const double *dY,
     if (ncols < 1 || ncols > kPermMaxCols) return false;
     for (int c = 0; c < ncols; ++c)
         if (hcols[c] < p + 2 || hcols[c] > 2 * p + 1) return false;  // fused epilogue covers the tvalue- columns
-    return p >= 1 && p <= 8 && n >= 4 && V >= 2 && V % 2 == 0 && ldY % 2 == 0 && V < 0x7fffffffLL &&
+    // an odd V is fine (the last voxel takes the explicit-residual kernel); rows must stay 16-byte aligned
+    return p >= 1 && p <= 8 && n >= 4 && V >= 2 && ldY % 2 == 0 && V < 0x7fffffffLL &&
            (reinterpret_cast<uintptr_t>(dY) & 15) == 0;
 }
 
-cudaError_t perm_gemm_run(const PermGemmArgs &a, const PermSet &ps, int sm_count, cudaStream_t st, int *launches,
-                          void **workspace_out)
+// ---- host side: geometry + packing
+cudaError_t perm_pack_plan(const PermSet &ps, int n, int p, PermPack &pk)
 {
-    const bool all_intercept = ps.all_intercept;
-    const int R = a.R, n = a.n, p = a.p, KP = p;
-    const bool timing = std::getenv("RMG_TIMING") != nullptr;
-    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t_start = now();
-    double t_mark = t_start;
-    auto lap = [&](const char *what) {
-        if (!timing) return;
-        const double t = now();
-        std::fprintf(stderr, "[rmg perm] %-28s %8.3f ms\n", what, t - t_mark);
-        t_mark = t;
-    };
+    const int R = ps.R, KP = p;
+    pk.R = R; pk.n = n; pk.p = p;
+    pk.shift = ps.all_intercept ? 1 : 0;
     // Is component 0 of every permuted design the same constant column (the intercept, first in
     // pivot order)?  Then e_0 = c0 * sum(y) is permutation-invariant and needs no tensor-core row.
-    int INV = (KP >= 2 && all_intercept && !std::getenv("RMG_PERM_NO_INV")) ? 1 : 0;
-    std::vector<double> c0(R, 0.0);
+    int INV = (KP >= 2 && ps.all_intercept && !std::getenv("RMG_PERM_NO_INV")) ? 1 : 0;
+    pk.c0.assign(R, 0.0);
     auto constant_column = [&](const Design &D, double &value) {
         if (D.k < 1) return false;
         const double *q = D.Q.data();
@@ -506,168 +484,254 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const PermSet &ps, int sm_count
     for (int r = 0; r < R && INV; ++r) {
         if (ps.is_perm(r)) {
             if (!base_const) INV = 0;
-            c0[r] = base_c0;
-        } else if (!constant_column(ps.own[r], c0[r])) {
+            pk.c0[r] = base_c0;
+        } else if (!constant_column(ps.own[r], pk.c0[r])) {
             INV = 0;
         }
     }
-    const int KG = KP - INV;
-    const int PG = pg_for(KG);
-    const int WM = KG * PG;
-    const int KC = 16;
+    pk.INV = INV;
+    pk.KG = KP - INV;
+    pk.PG = pg_for(pk.KG);
+    pk.WM = pk.KG * pk.PG;
+    pk.KC = 16;
     // 4 x 2 consumer warps, one CTA per SM.  (2 x 2 warps with two CTAs per SM measured the same
     // 1.30e3 perms/s but re-reads Y more: 35 GB vs 28.5 GB of DRAM traffic per 64 permutations.)
-    int WARPS_M = 4;
-    if (const char *e = std::getenv("RMG_PERM_CTAS")) WARPS_M = std::atoi(e) == 2 ? 2 : 4;
-    const int A_CHUNK = WARPS_M * (KC / 4) * WM * 32;
-    const int perms_per_cta = WARPS_M * PG * 8;
-    const int n_pt = (R + perms_per_cta - 1) / perms_per_cta;
-    const int n_kc = (n + KC - 1) / KC;
+    pk.WARPS_M = 4;
+    if (const char *e = std::getenv("RMG_PERM_CTAS")) pk.WARPS_M = std::atoi(e) == 2 ? 2 : 4;
+    pk.A_CHUNK = pk.WARPS_M * (pk.KC / 4) * pk.WM * 32;
+    pk.perms_per_cta = pk.WARPS_M * pk.PG * 8;
+    pk.n_pt = (R + pk.perms_per_cta - 1) / pk.perms_per_cta;
+    pk.n_kc = (n + pk.KC - 1) / pk.KC;
+    pk.tiles_per_batch = std::max(1, 256 / pk.perms_per_cta);
+    pk.nbatch = (pk.n_pt + pk.tiles_per_batch - 1) / pk.tiles_per_batch;
+    pk.apack_doubles = (size_t)pk.n_pt * pk.n_kc * pk.A_CHUNK;
+    // pinned staging (leased from the process-wide pool: the DMA engines of every device read it directly)
+    const size_t bytesA = (pk.apack_doubles * 8 + 255) & ~size_t(255);
+    char *base = static_cast<char *>(pinned_acquire(bytesA + (size_t)std::max(R, 1) * sizeof(PermConst)));
+    if (!base) return cudaErrorMemoryAllocation;
+    pk.lease = base;
+    pk.hA = reinterpret_cast<double *>(base);
+    pk.hpc = reinterpret_cast<PermConst *>(base + bytesA);
+    return cudaSuccess;
+}
 
-    // ---- device workspace; the prepass (which needs only Y) starts before any host packing
-    size_t off = 0;
-    auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
-    const size_t apack_doubles = (size_t)n_pt * n_kc * A_CHUNK;
-    const size_t oA = carve(apack_doubles * 8), oP = carve((size_t)R * sizeof(PermConst));
-    const size_t oY0 = carve((size_t)a.V * 8), oYY = carve((size_t)a.V * 8), oYS = carve((size_t)a.V * 8);
-    const size_t oFlag = carve(256), oVf = carve((size_t)a.V);
-    char *ws = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ws), off, st);
-    if (e != cudaSuccess) return e;
-    *workspace_out = ws;
-    e = cudaMemsetAsync(ws + oFlag, 0, 256, st);
-    if (e != cudaSuccess) return e;
+void perm_pack_release(PermPack &pk)
+{
+    if (pk.lease) pinned_release(pk.lease);
+    pk.lease = nullptr;
+    pk.hA = nullptr;
+    pk.hpc = nullptr;
+}
 
-    PermKernelParams P;
-    std::memset(&P, 0, sizeof P);
-    P.Y = a.Y; P.V = a.V; P.ldY = a.ldY; P.n = n; P.p = p; P.R = R; P.Rstride = R; P.ncols = a.ncols;
-    P.two_sided = a.two_sided;
-    P.shift = all_intercept ? 1 : 0;
-    P.Apack = reinterpret_cast<double *>(ws + oA);
-    P.pc = reinterpret_cast<PermConst *>(ws + oP);
-    P.y0 = reinterpret_cast<double *>(ws + oY0);
-    P.yy = reinterpret_cast<double *>(ws + oYY);
-    P.ys = reinterpret_cast<double *>(ws + oYS);
-    P.keys = a.keys;
-    P.inv = INV; P.kg = KG; P.pg = PG; P.wm = WM; P.warps_m = WARPS_M; P.a_chunk = A_CHUNK; P.perms_per_cta = perms_per_cta;
-    P.vflag = reinterpret_cast<unsigned char *>(ws + oVf);
-    P.n_pt = n_pt;
-    P.n_kc = n_kc;
-    if (const char *dbg = std::getenv("RMG_PERM_DEBUG_SKIP")) P.debug_skip = std::atoi(dbg);
-    int *any_zero = reinterpret_cast<int *>(ws + oFlag);
-    for (int c = 0; c < a.ncols; ++c) P.tcol[c] = a.hcols[c] - (p + 2);
-
-    const int64_t pairs = (a.V + 1) / 2;
-    perm_prepass_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(a.Y, a.V, a.ldY, n, a.mask, a.mask_lo, a.mask_hi,
-                                                                           P.shift, reinterpret_cast<double *>(ws + oY0),
-                                                                           reinterpret_cast<double *>(ws + oYY),
-                                                                           reinterpret_cast<double *>(ws + oYS), P.vflag, any_zero);
-    const int nk = R * a.ncols;
-    perm_floor_keys_kernel<<<(nk + 255) / 256, 256, 0, st>>>(a.keys, nk, any_zero);
-    *launches += 2;
-    lap("alloc + prepass launch");
-
-    // ---- batches of permutations: pack on the host (all cores), upload on a side stream, launch the
-    //      GEMM of the batch; the host packs batch b+1 while the GPU multiplies batch b.
-    //      Host staging persists across calls (first-touch page faults of fresh 10+ MB vectors cost more
-    //      than the packing itself).
-    static thread_local std::vector<double> tl_apack;
-    static thread_local std::vector<PermConst> tl_pc;
-    // bind the calling thread's instances: a thread_local named inside a worker lambda would resolve
-    // to the WORKER's (empty) instance
-    std::vector<double> &Apack = tl_apack;
-    std::vector<PermConst> &pc = tl_pc;
-    Apack.resize(apack_doubles);
-    pc.resize(R);
-    const int tiles_per_batch = std::max(1, 256 / perms_per_cta);
-    const int nbatch = (n_pt + tiles_per_batch - 1) / tiles_per_batch;
-    cudaStream_t cs = nullptr;
-    std::vector<cudaEvent_t> ev(nbatch, nullptr);
-    e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
-    for (int b = 0; b < nbatch && e == cudaSuccess; ++b) {
-        const int pt0 = b * tiles_per_batch, pt1 = std::min(n_pt, pt0 + tiles_per_batch);
-        const int r0 = pt0 * perms_per_cta, r1 = std::min(R, pt1 * perms_per_cta);
-        double *hA = Apack.data() + (size_t)pt0 * n_kc * A_CHUNK;
-        const size_t nA = (size_t)(pt1 - pt0) * n_kc * A_CHUNK;
-        std::memset(hA, 0, nA * sizeof(double));   // padding: permutations past R, subjects past n
-        parallel_for(r1 - r0, [&](int i0, int i1) {
-            for (int r = r0 + i0; r < r0 + i1; ++r) {
-                const Design &D = ps.design(r);
-                const bool gather = ps.is_perm(r);
-                const int32_t *ix = ps.idx + (size_t)r * n;
-                PermConst &c = pc[r];
-                std::memset(&c, 0, sizeof c);
-                for (int i = 0; i < p; ++i) {
-                    c.q1[i] = D.q1[i];
-                    c.ct[i] = D.ct[i];
-                    for (int j = 0; j < p; ++j) c.Rinv[i * 8 + j] = D.Rinv[i + (size_t)j * p];
-                }
-                c.rdf = (double)(n - p);
-                c.c0 = c0[r];
-                const int pt = r / perms_per_cta, rr = r % perms_per_cta;
-                const int warp_m = rr / (PG * 8), pg = (rr / 8) % PG, g = rr % 8;
-                for (int k = INV; k < D.k; ++k) {
-                    const double *qcol = D.Q.data() + (size_t)k * n;
-                    const int mt = pg * KG + (k - INV);
-                    for (int j = 0; j < n; ++j) {
-                        const int kc = j / KC, jj = j % KC, ks = jj / 4, q = jj % 4;
-                        const int lane = g * 4 + q;
-                        // [pt][kc] chunk, inside: [warp_m][ks][mt][lane]  (one MMA A-fragment = 32 consecutive doubles)
-                        Apack[(((size_t)pt * n_kc + kc) * A_CHUNK) + (((size_t)warp_m * (KC / 4) + ks) * WM + mt) * 32 + lane] =
-                            gather ? qcol[ix[j]] : qcol[j];
-                    }
+void perm_pack_batch(const PermSet &ps, PermPack &pk, int b)
+{
+    const int n = pk.n, p = pk.p, INV = pk.INV, KG = pk.KG, PG = pk.PG, WM = pk.WM, KC = pk.KC, A_CHUNK = pk.A_CHUNK;
+    const int perms_per_cta = pk.perms_per_cta, n_kc = pk.n_kc;
+    const int pt0 = b * pk.tiles_per_batch, pt1 = std::min(pk.n_pt, pt0 + pk.tiles_per_batch);
+    const int r0 = pk.batch_r0(b), r1 = pk.batch_r1(b);
+    double *Apack = pk.hA;
+    PermConst *pc = pk.hpc;
+    std::memset(Apack + (size_t)pt0 * n_kc * A_CHUNK, 0, (size_t)(pt1 - pt0) * n_kc * A_CHUNK * sizeof(double));   // padding
+    parallel_for(r1 - r0, [&](int i0, int i1) {
+        for (int r = r0 + i0; r < r0 + i1; ++r) {
+            const Design &D = ps.design(r);
+            const bool gather = ps.is_perm(r);
+            const int32_t *ix = ps.idx + (size_t)r * n;
+            PermConst &c = pc[r];
+            std::memset(&c, 0, sizeof c);
+            for (int i = 0; i < p; ++i) {
+                c.q1[i] = D.q1[i];
+                c.ct[i] = D.ct[i];
+                for (int j = 0; j < p; ++j) c.Rinv[i * 8 + j] = D.Rinv[i + (size_t)j * p];
+            }
+            c.rdf = (double)(n - p);
+            c.c0 = pk.c0[r];
+            const int pt = r / perms_per_cta, rr = r % perms_per_cta;
+            const int warp_m = rr / (PG * 8), pg = (rr / 8) % PG, g = rr % 8;
+            for (int k = INV; k < D.k; ++k) {
+                const double *qcol = D.Q.data() + (size_t)k * n;
+                const int mt = pg * KG + (k - INV);
+                for (int j = 0; j < n; ++j) {
+                    const int kc = j / KC, jj = j % KC, ks = jj / 4, q = jj % 4;
+                    const int lane = g * 4 + q;
+                    // [pt][kc] chunk, inside: [warp_m][ks][mt][lane]  (one MMA A-fragment = 32 consecutive doubles)
+                    Apack[(((size_t)pt * n_kc + kc) * A_CHUNK) + (((size_t)warp_m * (KC / 4) + ks) * WM + mt) * 32 + lane] =
+                        gather ? qcol[ix[j]] : qcol[j];
                 }
             }
-        });
-        e = cudaMemcpyAsync(ws + oA + (size_t)pt0 * n_kc * A_CHUNK * 8, hA, nA * 8, cudaMemcpyHostToDevice, cs);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(ws + oP + (size_t)r0 * sizeof(PermConst), pc.data() + r0, (size_t)(r1 - r0) * sizeof(PermConst),
-                                cudaMemcpyHostToDevice, cs);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventRecord(ev[b], cs);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev[b], 0);
-        if (e != cudaSuccess) break;
-        PermKernelParams Pb = P;
-        Pb.Apack = P.Apack + (size_t)pt0 * n_kc * A_CHUNK;
-        Pb.pc = P.pc + r0;
-        Pb.keys = P.keys + r0;
-        Pb.R = r1 - r0;
-        Pb.n_pt = pt1 - pt0;
-        switch (KP * 2 + INV) {
-#define RMG_PG_CASE(K) case K * 2: e = launch_gemm<K, pg_for(K), 0>(Pb, sm_count, st, WARPS_M); break;
-#define RMG_PG_CASE1(K) case K * 2 + 1: e = launch_gemm<K, pg_for(K - 1), 1>(Pb, sm_count, st, WARPS_M); break;
-            RMG_PG_CASE(1) RMG_PG_CASE(2) RMG_PG_CASE(3) RMG_PG_CASE(4) RMG_PG_CASE(5) RMG_PG_CASE(6) RMG_PG_CASE(7) RMG_PG_CASE(8)
-            RMG_PG_CASE1(2) RMG_PG_CASE1(3) RMG_PG_CASE1(4) RMG_PG_CASE1(5) RMG_PG_CASE1(6) RMG_PG_CASE1(7) RMG_PG_CASE1(8)
+        }
+    });
+}
+
+// ---- device side
+cudaError_t perm_dev_begin(PermDevice &d, const PermPack &pk, int device, int sm_count, const PermGemmArgs &a, cudaStream_t st,
+                           const PermPre *resident_pre, int *launches)
+{
+    d.device = device;
+    d.sm_count = sm_count;
+    d.st = st;
+    d.V = a.V;
+    d.own_pre = resident_pre == nullptr;
+    const int R = pk.R;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+    const size_t oA = carve(pk.apack_doubles * 8), oP = carve((size_t)R * sizeof(PermConst)), oVf = carve((size_t)a.V);
+    size_t oY0 = 0, oYY = 0, oYS = 0, oFlag = 0;
+    if (d.own_pre) {
+        oY0 = carve((size_t)a.V * 8); oYY = carve((size_t)a.V * 8); oYS = carve((size_t)a.V * 8); oFlag = carve(256);
+    }
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&d.ws), off, st);
+    if (e != cudaSuccess) return e;
+    if (d.own_pre) {
+        d.pre.y0 = reinterpret_cast<double *>(d.ws + oY0);
+        d.pre.yy = reinterpret_cast<double *>(d.ws + oYY);
+        d.pre.ys = reinterpret_cast<double *>(d.ws + oYS);
+        d.pre.any_zero = reinterpret_cast<int *>(d.ws + oFlag);
+        if ((e = cudaMemsetAsync(d.ws + oFlag, 0, 256, st)) != cudaSuccess) return e;
+    } else {
+        d.pre = *resident_pre;
+    }
+    if ((e = cudaMemsetAsync(d.ws + oVf, 0, (size_t)a.V, st)) != cudaSuccess) return e;   // exact-path flags of THIS call
+
+    PermKernelParams &P = d.P;
+    std::memset(&P, 0, sizeof P);
+    P.Y = a.Y; P.V = a.V; P.ldY = a.ldY; P.n = pk.n; P.p = pk.p; P.R = R; P.Rstride = R; P.ncols = a.ncols;
+    P.two_sided = a.two_sided;
+    P.shift = pk.shift;
+    P.Apack = reinterpret_cast<double *>(d.ws + oA);
+    P.pc = reinterpret_cast<PermConst *>(d.ws + oP);
+    P.y0 = d.pre.y0; P.yy = d.pre.yy; P.ys = d.pre.ys;
+    P.keys = a.keys;
+    P.inv = pk.INV; P.kg = pk.KG; P.pg = pk.PG; P.wm = pk.WM; P.warps_m = pk.WARPS_M; P.a_chunk = pk.A_CHUNK;
+    P.perms_per_cta = pk.perms_per_cta;
+    P.vflag = reinterpret_cast<unsigned char *>(d.ws + oVf);
+    P.n_pt = pk.n_pt;
+    P.n_kc = pk.n_kc;
+    if (const char *dbg = std::getenv("RMG_PERM_DEBUG_SKIP")) P.debug_skip = std::atoi(dbg);
+    for (int c = 0; c < a.ncols; ++c) P.tcol[c] = a.hcols[c] - (pk.p + 2);
+    d.ev.assign(pk.nbatch, nullptr);
+    if ((e = cudaStreamCreateWithFlags(&d.cs, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    (void)launches;
+    return cudaSuccess;
+}
+
+cudaError_t perm_dev_prepass(PermDevice &d, const PermGemmArgs &a, int64_t v0, int64_t cv, int *launches)
+{
+    if (cv <= 0) return cudaSuccess;
+    const int64_t pairs = (cv + 1) / 2;
+    perm_prepass_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, d.st>>>(a.Y + v0, cv, a.ldY, a.n, a.mask ? a.mask + v0 : nullptr,
+                                                                            a.mask_lo, a.mask_hi, d.P.shift, d.pre.y0 + v0,
+                                                                            d.pre.yy + v0, d.pre.ys + v0, d.pre.any_zero);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t perm_dev_upload(PermDevice &d, const PermPack &pk, int b)
+{
+    const int pt0 = b * pk.tiles_per_batch, pt1 = std::min(pk.n_pt, pt0 + pk.tiles_per_batch);
+    const int r0 = pk.batch_r0(b), r1 = pk.batch_r1(b);
+    const size_t offA = (size_t)pt0 * pk.n_kc * pk.A_CHUNK, nA = (size_t)(pt1 - pt0) * pk.n_kc * pk.A_CHUNK;
+    cudaError_t e = cudaMemcpyAsync(const_cast<double *>(d.P.Apack) + offA, pk.hA + offA, nA * 8, cudaMemcpyHostToDevice, d.cs);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(const_cast<PermConst *>(d.P.pc) + r0, pk.hpc + r0, (size_t)(r1 - r0) * sizeof(PermConst),
+                            cudaMemcpyHostToDevice, d.cs);
+    if (e == cudaSuccess && !d.ev[b]) e = cudaEventCreateWithFlags(&d.ev[b], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(d.ev[b], d.cs);
+    return e;
+}
+
+cudaError_t perm_dev_launch(PermDevice &d, const PermPack &pk, int b0, int b1, int64_t v0, int64_t cv, int *launches)
+{
+    if (cv <= 0 || b1 <= b0) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    if (cv & 1) {
+        perm_flag_voxel_kernel<<<1, 32, 0, d.st>>>(d.P.vflag, d.P.yy, v0 + cv - 1);
+        *launches += 1;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (--cv == 0) return cudaSuccess;
+    }
+    for (int b = b0; b < b1; ++b)
+        if ((e = cudaStreamWaitEvent(d.st, d.ev[b], 0)) != cudaSuccess) return e;
+    const int pt0 = b0 * pk.tiles_per_batch, pt1 = std::min(pk.n_pt, b1 * pk.tiles_per_batch);
+    const int r0 = pk.batch_r0(b0), r1 = pk.batch_r1(b1 - 1);
+    PermKernelParams Pb = d.P;
+    Pb.Y = d.P.Y + v0;
+    Pb.V = cv;
+    Pb.y0 = d.P.y0 + v0;
+    Pb.yy = d.P.yy + v0;
+    Pb.ys = d.P.ys + v0;
+    Pb.vflag = d.P.vflag + v0;
+    Pb.Apack = d.P.Apack + (size_t)pt0 * pk.n_kc * pk.A_CHUNK;
+    Pb.pc = d.P.pc + r0;
+    Pb.keys = d.P.keys + r0;
+    Pb.R = r1 - r0;
+    Pb.n_pt = pt1 - pt0;
+    switch (pk.p * 2 + pk.INV) {
+#define RMG_PG_CASE(K) case K * 2: e = launch_gemm<K, pg_for(K), 0>(Pb, d.sm_count, d.st, pk.WARPS_M); break;
+#define RMG_PG_CASE1(K) case K * 2 + 1: e = launch_gemm<K, pg_for(K - 1), 1>(Pb, d.sm_count, d.st, pk.WARPS_M); break;
+        RMG_PG_CASE(1) RMG_PG_CASE(2) RMG_PG_CASE(3) RMG_PG_CASE(4) RMG_PG_CASE(5) RMG_PG_CASE(6) RMG_PG_CASE(7) RMG_PG_CASE(8)
+        RMG_PG_CASE1(2) RMG_PG_CASE1(3) RMG_PG_CASE1(4) RMG_PG_CASE1(5) RMG_PG_CASE1(6) RMG_PG_CASE1(7) RMG_PG_CASE1(8)
 #undef RMG_PG_CASE
 #undef RMG_PG_CASE1
-        default: e = cudaErrorInvalidValue;
-        }
-        *launches += 1;
+    default: e = cudaErrorInvalidValue;
     }
-    lap("pack + upload + GEMM launches");
-    if (e == cudaSuccess) {
-        const int eg = (int)std::min<int64_t>((a.V + 127) / 128, (int64_t)sm_count * 16);
-        switch (KP) {
-#define RMG_EX_CASE(K) case K: perm_exact_voxels_kernel<K><<<eg, 128, 0, st>>>(P); break;
+    *launches += 1;
+    return e;
+}
+
+cudaError_t perm_dev_end(PermDevice &d, const PermPack &pk, int *launches)
+{
+    const PermKernelParams &P = d.P;
+    const int nk = pk.R * P.ncols;
+    if (nk == 0) return cudaSuccess;
+    // masked rows are 0 in every column and take part in the maximum
+    perm_floor_keys_kernel<<<(nk + 255) / 256, 256, 0, d.st>>>(P.keys, nk, d.pre.any_zero);
+    const int eg = (int)std::min<int64_t>((P.V + 127) / 128, (int64_t)d.sm_count * 16);
+    if (eg > 0) {
+        switch (pk.p) {
+#define RMG_EX_CASE(K) case K: perm_exact_voxels_kernel<K><<<eg, 128, 0, d.st>>>(P); break;
             RMG_EX_CASE(1) RMG_EX_CASE(2) RMG_EX_CASE(3) RMG_EX_CASE(4) RMG_EX_CASE(5) RMG_EX_CASE(6) RMG_EX_CASE(7) RMG_EX_CASE(8)
 #undef RMG_EX_CASE
         }
-        perm_finalize_keys_kernel<<<(nk + 255) / 256, 256, 0, st>>>(a.keys, P.pc, P);
-        *launches += 2;
-        e = cudaGetLastError();
     }
-    // the staging buffers are reused by the next call: wait for the (long finished) uploads
-    if (cs) {
-        cudaError_t e2 = cudaStreamSynchronize(cs);
-        if (e == cudaSuccess) e = e2;
-        cudaStreamDestroy(cs);
+    perm_finalize_keys_kernel<<<(nk + 255) / 256, 256, 0, d.st>>>(P.keys, P.pc, P);
+    *launches += 3;
+    return cudaGetLastError();
+}
+
+void perm_dev_release(PermDevice &d)
+{
+    if (d.cs) {
+        cudaStreamSynchronize(d.cs);     // the pinned operand is handed back to the pool after this
+        cudaStreamDestroy(d.cs);
+        d.cs = nullptr;
     }
-    for (auto evb : ev)
-        if (evb) cudaEventDestroy(evb);
-    if (timing) {
-        cudaStreamSynchronize(st);
-        lap("GPU work (sync, timing only)");
+    for (auto e : d.ev)
+        if (e) cudaEventDestroy(e);
+    d.ev.clear();
+    if (d.ws) cudaFreeAsync(d.ws, d.st);
+    d.ws = nullptr;
+}
+
+cudaError_t perm_gemm_run(const PermGemmArgs &a, const PermSet &ps, int sm_count, cudaStream_t st, int *launches)
+{
+    PermPack pk;
+    PermDevice d;
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e == cudaSuccess) e = perm_pack_plan(ps, a.n, a.p, pk);
+    if (e == cudaSuccess) e = perm_dev_begin(d, pk, device, sm_count, a, st, nullptr, launches);
+    if (e == cudaSuccess) e = perm_dev_prepass(d, a, 0, a.V, launches);     // needs only Y: runs while the host packs
+    // batches of permutations: pack on the host (all cores), upload on the side stream, launch the GEMM of the
+    // batch; the host packs batch b+1 while the GPU multiplies batch b
+    for (int b = 0; b < pk.nbatch && e == cudaSuccess; ++b) {
+        perm_pack_batch(ps, pk, b);
+        e = perm_dev_upload(d, pk, b);
+        if (e == cudaSuccess) e = perm_dev_launch(d, pk, b, b + 1, 0, a.V, launches);
     }
+    if (e == cudaSuccess) e = perm_dev_end(d, pk, launches);
+    perm_dev_release(d);
+    perm_pack_release(pk);
     return e;
 }
 

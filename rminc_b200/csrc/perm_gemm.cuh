@@ -120,7 +120,82 @@ struct PermSet {
 
 bool perm_gemm_supported(int n, int p, int64_t V, int64_t ldY, const double *dY, const int32_t *hcols, int ncols);
 
-cudaError_t perm_gemm_run(const PermGemmArgs &a, const PermSet &ps, int sm_count, cudaStream_t st, int *launches,
-                          void **workspace_out);
+// ---- the GEMM path in pieces, so that one call can drive several devices (voxel shards) and several resident
+//      voxel blocks per device from ONE host-side packing of the permuted designs:
+//        perm_pack_plan      geometry of the stacked operand (invariant-row skip, tile shape) + pinned host staging
+//        perm_pack_batch     host threads pack one batch of permutations in MMA-fragment order
+//        perm_dev_begin      per device: workspace (packed operand, per-permutation constants, per-voxel sums, flags)
+//        perm_dev_prepass    per resident voxel block: y0, |y - y0|^2, sum(y - y0)   (skipped when the caller holds them)
+//        perm_dev_upload     per device and batch: packed operand -> device on a side stream
+//        perm_dev_launch     per device, batch and voxel block: the GEMM + fused statistics
+//        perm_dev_end        per device: 0 floor, exact refits of flagged voxels, proxy -> t
+struct PermKernelParams {
+    const double *Y;
+    int64_t V, ldY;
+    int n, p, R, ncols, two_sided, shift;   // R: permutations of THIS launch (a batch)
+    int Rstride;                             // permutations of the whole call (row stride of keys)
+    int tcol[kPermMaxCols];          // coefficient index of each requested t-column
+    const double *Apack;             // [n_pt][n_kc][A chunk] fragment-major
+    const PermConst *pc;             // [R]
+    const double *y0;                // [V] first sample (0 when !shift)
+    const double *yy;                // [V] |y - y0|^2, or -1 for voxels outside the mask
+    const double *ys;                // [V] sum_j (y_j - y0)  (only when the intercept row is skipped)
+    unsigned long long *keys;        // [ncols][R]
+    // geometry of Apack, so the (rare) exact path can read Q_r[j][k] back out of the packed operand
+    int inv, kg, pg, wm, warps_m, a_chunk, perms_per_cta;
+    unsigned char *vflag;            // [V] set when some permutation's one-pass rss lost too many digits
+    int n_pt, n_kc;
+    int debug_skip;                  // diagnostics only: 1 = skip the statistics epilogue, 2 = skip the MMAs
+};
+
+// Per-voxel quantities every permutation shares (the prepass output), device-resident.  A resident dataset keeps
+// them across calls (they depend on Y, the mask and `shift` only).
+struct PermPre {
+    double *y0 = nullptr, *yy = nullptr, *ys = nullptr;
+    int *any_zero = nullptr;         // raised when some voxel is outside the mask (the global 0 floor, Q6)
+};
+
+struct PermPack {
+    int R = 0, n = 0, p = 0;
+    int INV = 0, KG = 0, PG = 0, WM = 0, KC = 16, WARPS_M = 4, A_CHUNK = 0, perms_per_cta = 0, n_pt = 0, n_kc = 0;
+    int tiles_per_batch = 1, nbatch = 0;
+    int shift = 0;                   // every permuted design spans the constant: voxels are centred on their first sample
+    std::vector<double> c0;          // [R] constant value of Q_r[:, 0] (INV)
+    size_t apack_doubles = 0;
+    double *hA = nullptr;            // pinned host [n_pt][n_kc][A_CHUNK]
+    PermConst *hpc = nullptr;        // pinned host [R]
+    void *lease = nullptr;           // pinned-pool lease behind hA / hpc (perm_pack_release)
+    int batch_r0(int b) const { return std::min(R, b * tiles_per_batch * perms_per_cta); }
+    int batch_r1(int b) const { return std::min(R, (b + 1) * tiles_per_batch * perms_per_cta); }
+};
+
+cudaError_t perm_pack_plan(const PermSet &ps, int n, int p, PermPack &pk);
+void perm_pack_batch(const PermSet &ps, PermPack &pk, int b);
+void perm_pack_release(PermPack &pk);
+
+struct PermDevice {
+    int device = 0, sm_count = 148;
+    cudaStream_t st = nullptr;       // compute stream (the caller's)
+    cudaStream_t cs = nullptr;       // side stream of the operand uploads
+    char *ws = nullptr;              // one stream-ordered allocation behind everything below
+    PermKernelParams P{};            // whole-shard parameters; launches offset them per voxel block / batch
+    PermPre pre;                     // points into ws unless the caller supplied resident sums
+    bool own_pre = true;
+    std::vector<cudaEvent_t> ev;     // ev[b]: batch b's operand has landed
+    int64_t V = 0;
+};
+
+// keys: device [ncols][R], initialised to key(-inf).  resident_pre: per-voxel sums kept by the caller (else null).
+cudaError_t perm_dev_begin(PermDevice &d, const PermPack &pk, int device, int sm_count, const PermGemmArgs &a, cudaStream_t st,
+                           const PermPre *resident_pre, int *launches);
+cudaError_t perm_dev_prepass(PermDevice &d, const PermGemmArgs &a, int64_t v0, int64_t cv, int *launches);
+cudaError_t perm_dev_upload(PermDevice &d, const PermPack &pk, int b);
+// batches [b0, b1) of permutations on the voxel block [v0, v0 + cv) of the shard, in one launch
+cudaError_t perm_dev_launch(PermDevice &d, const PermPack &pk, int b0, int b1, int64_t v0, int64_t cv, int *launches);
+cudaError_t perm_dev_end(PermDevice &d, const PermPack &pk, int *launches);
+void perm_dev_release(PermDevice &d);     // waits for the side stream; frees ws in stream order
+
+// One device, one resident block: plan + begin + prepass + (pack, upload, launch per batch) + end.
+cudaError_t perm_gemm_run(const PermGemmArgs &a, const PermSet &ps, int sm_count, cudaStream_t st, int *launches);
 
 }  // namespace rmg

@@ -144,17 +144,19 @@ def test_ctypes_signatures_match_the_header():
     from rminc_b200 import _lib
     src = open(os.path.join(ROOT, "include", "rminc_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    protos = re.findall(r"\b(int|double|int64_t)\s+(rmg_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src)
+    protos = re.findall(r"\b(int|double|int64_t|void|void \*)\s*(rmg_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src)
     assert len(protos) == len(_lib.SIGNATURES)
 
     def kind(ctype):
+        if ctype is None:
+            return "void"
         if ctype in (C.c_void_p, C.c_char_p) or isinstance(ctype, type(C.POINTER(C.c_int))) and hasattr(ctype, "contents"):
             return "ptr"
         return {C.c_int: "int", C.c_int64: "int64", C.c_double: "double", C.c_size_t: "size_t"}[ctype]
 
     for ret, name, params in protos:
         res, args = _lib.SIGNATURES[name]
-        assert kind(res) == {"int": "int", "double": "double", "int64_t": "int64"}[ret], name
+        assert kind(res) == {"int": "int", "double": "double", "int64_t": "int64", "void": "void", "void *": "ptr"}[ret], name
         plist = [p.strip() for p in params.split(",") if p.strip() and p.strip() != "void"]
         assert len(plist) == len(args), f"{name}: header has {len(plist)} parameters, ctypes {len(args)}"
         for i, (decl, a) in enumerate(zip(plist, args)):

@@ -239,6 +239,58 @@ def test_randomize_with_replacement_and_other_columns(core, oracle):
         core.randomize(Y, X, bad, [4, 5], mask=mask)
 
 
+def test_randomize_with_replacement_default_t_columns_both_paths(core, oracle, perm_path):
+    """replace = TRUE index vectors with the default tvalue- columns (R/minc_voxel_statistics.R:1470-1492): every such
+    permutation changes the column space, so the GEMM path factors it from scratch and packs its own Q (and, when a
+    resample drops the balance, its own constant column) -- the branch true permutations never take."""
+    rng = np.random.default_rng(5)
+    V, n = 2500, 40
+    X = design_cfg2(n)
+    p = X.shape[1]
+    Y = np.asfortranarray(5 + 0.2 * rng.standard_normal((V, n)) + 0.1 * np.outer(rng.random(V), X[:, 1]))
+    mask = (np.arange(V) % 7 > 0).astype(float)
+    idx = np.column_stack([perm_indices(n, 30, seed=9, replace=True), perm_indices(n, 6, seed=10)])   # mixed
+    keep = [r for r in range(idx.shape[1]) if np.linalg.matrix_rank(X[idx[:, r]]) == p]
+    idx = idx[:, keep]
+    assert idx.shape[1] >= 30
+    cols = list(range(p + 2, 2 * p + 2))
+    for two_sided in (True, False):
+        want = oracle.randomize(Y, X, idx, cols, two_sided=two_sided, mask=mask)
+        got = core.randomize(Y, X, idx, cols, two_sided=two_sided, mask=mask)
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=0, err_msg=f"{perm_path} two_sided={two_sided}")
+
+
+def test_randomize_rank_deficient_and_no_intercept_designs(core, oracle, perm_path):
+    """a rank-deficient base design [1, g, 1-g, age] (pivot [0,1,3,2], rank 3) and a design without an
+    intercept, through rmg_randomize on both paths."""
+    rng = np.random.default_rng(6)
+    V, n = 1500, 36
+    g = (np.arange(n) % 2).astype(float)
+    age = np.round(rng.normal(60, 10, n), 1)
+    Y = np.asfortranarray(2 + 0.3 * rng.standard_normal((V, n)) + 0.01 * np.outer(rng.random(V), age))
+    idx = perm_indices(n, 17, seed=11)
+    Xd = np.column_stack([np.ones(n), g, 1 - g, age])
+    cols = [6, 7, 8, 9]
+    want = oracle.randomize(Y, Xd, idx, cols)
+    got = core.randomize(Y, Xd, idx, cols)
+    # beta stays in pivoted order while se is un-pivoted (Q2): the age coefficient (slot 2) is divided by the aliased
+    # column's huge se, slot 3's zero coefficient by the finite one -- every t is rounding noise or an exact 0, in the
+    # reference (|t| ~ 1e-14) as here; "identical" means the same ~0 pattern (SURVEY A.3)
+    assert got.shape == want.shape
+    assert (np.abs(want) < 1e-6).all() and (np.abs(got) < 1e-6).all(), perm_path
+    assert (got[:, 3] == 0).all() and (want[:, 3] == 0).all()
+    # no intercept: nothing is centred, nothing is skipped
+    X0 = np.column_stack([g, age / 60.0])
+    for two_sided in (True, False):
+        np.testing.assert_allclose(core.randomize(Y, X0, idx, [4, 5], two_sided=two_sided),
+                                   oracle.randomize(Y, X0, idx, [4, 5], two_sided=two_sided), rtol=RTOL, atol=0,
+                                   err_msg=f"{perm_path} no intercept two_sided={two_sided}")
+    # ... and with a mask, where the 0 floor of masked rows takes part in a one-sided maximum (Q6)
+    mask = (np.arange(V) % 3 > 0).astype(float)
+    np.testing.assert_allclose(core.randomize(Y, X0, idx, [4, 5], two_sided=False, mask=mask),
+                               oracle.randomize(Y, X0, idx, [4, 5], two_sided=False, mask=mask), rtol=RTOL, atol=0)
+
+
 def test_randomize_gemm_equals_refit_on_larger_case(core, monkeypatch):
     rng = np.random.default_rng(13)
     V, n = 20000, 100
