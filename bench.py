@@ -269,8 +269,12 @@ def single_process_multi(args, core, Yt, X, G, d_ref, perms, idx):
                                 "gemm_window_ms": core.last_kernel_ms(),
                                 "api": "rmg_randomize_multi (C ABI; pinned host Y -> voxel blocks per device on copy streams -> "
                                        "all R permutations per block as it lands; designs factored and packed once for all devices)"}
-        if d_ref is not None:
-            parity = parity and bool(np.allclose(dist_h.T, d_ref.cpu().numpy(), rtol=1e-9, atol=0))
+        # reference: the device-resident one-GPU path on rank 0's own matrix (under torchrun every rank holds a
+        # different synthetic volume, so the distributed result is not comparable), first 64 permutations
+        d64 = core.randomize_torch(Yt, X, idx[:, :64], list(range(p + 2, 2 * p + 2)))
+        torch.cuda.synchronize()
+        d64 = d64.cpu().numpy().T
+        parity = parity and bool(np.allclose(dist_h[:64], d64, rtol=1e-9, atol=0))
     # -- the resident handle: one upload, then fit -> randomize -> FDR on the shards
     h = C.c_void_p()
     t0 = time.perf_counter()
@@ -294,8 +298,7 @@ def single_process_multi(args, core, Yt, X, G, d_ref, perms, idx):
             ds[name] = time.perf_counter() - t0
         ds["randomize_perms_per_s"] = perms / ds["randomize_seconds_again"]
         ds["randomize_gemm_window_ms"] = core.last_kernel_ms()
-        if d_ref is not None:
-            parity = parity and bool(np.allclose(dist_h.T, d_ref.cpu().numpy(), rtol=1e-9, atol=0))
+        parity = parity and bool(np.allclose(dist_h[:64], d64, rtol=1e-9, atol=0))
     q = np.empty(V)
     th = np.empty(5)
     t0 = time.perf_counter()

@@ -47,6 +47,8 @@ int select_device(int device, char *err, size_t errlen)
             uint64_t keep = ~0ull;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
+        // experiment knob: L2 fetch granularity in bytes (32 / 64 / 128) for the scattered row segments of masked fits
+        if (const char *g = std::getenv("RMG_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g));
         cudaGetLastError();
         pool_ready.fetch_or(1ull << device);
     }
@@ -125,7 +127,7 @@ void *pinned_acquire(size_t bytes)
     void *p = nullptr;
     {
         ScopedInterleave numa;
-        if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
             cudaGetLastError();
             return nullptr;
         }

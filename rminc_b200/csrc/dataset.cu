@@ -41,13 +41,19 @@ __global__ void keys_decode_kernel(const unsigned long long *keys, double *dist,
 
 // Column maxima of one fitted result matrix (V x ncol_total, ld) for the selected columns,
 // merged into keys[c * R + r].
+// (the requested columns travel as a kernel argument: a host -> device copy of them would queue behind a dataset
+// upload still in flight on the copy engine)
+struct ColList {
+    int32_t c[2 * RMG_MAX_P + 3];
+};
+
 __global__ void __launch_bounds__(256)
-colmax_kernel(const double *__restrict__ out, int64_t V, int64_t ld, const int32_t *__restrict__ cols, int ncols,
+colmax_kernel(const double *__restrict__ out, int64_t V, int64_t ld, const ColList cols, int ncols,
               int two_sided, unsigned long long *__restrict__ keys, int R, int r)
 {
     __shared__ double red[8];
     for (int c = 0; c < ncols; ++c) {
-        const double *col = out + (int64_t)cols[c] * ld;
+        const double *col = out + (int64_t)cols.c[c] * ld;
         double best = -INFINITY;
         for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x)
             best = fmax(best, perm_stat_filter(col[v], two_sided));
@@ -81,7 +87,7 @@ double now_ms()
 
 // Refit path for one shard: one streaming fit per permutation into a scratch result matrix + column maxima.  Used for
 // result columns other than tvalue-*, p > 8 and odd layouts; also the validation twin of the GEMM.
-int refit_shard(const PermSet &pd, const PermShard &s, int n, int p, double mask_lo, double mask_hi, const int32_t *dcols,
+int refit_shard(const PermSet &pd, const PermShard &s, int n, int p, double mask_lo, double mask_hi, const int32_t *cols,
                 int ncols, int two_sided, unsigned long long *keys, int R, int64_t &launches, char *err, size_t errlen)
 {
     int rc = RMG_OK;
@@ -94,6 +100,9 @@ int refit_shard(const PermSet &pd, const PermShard &s, int n, int p, double mask
     const int ncol_total = 2 * p + 3, KP = lm_padded_p(p);
     const int64_t ldo = (s.cv + 1) & ~int64_t(1);
     const size_t qstride = make_qt(pd.base, KP).size();   // rows padded for the TMA kernel
+    ColList cl;
+    std::memset(&cl, 0, sizeof cl);
+    for (int c = 0; c < ncols && c < 2 * RMG_MAX_P + 3; ++c) cl.c[c] = cols[c];
     {
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)ldo * ncol_total * sizeof(double), st));
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dd), sizeof(DevDesign) * (size_t)R, st));
@@ -117,7 +126,7 @@ int refit_shard(const PermSet &pd, const PermShard &s, int n, int p, double mask
             LmLaunchInfo info;
             RMG_CUDA(launch_lm_fit(a, plan, scr, st, &info));
             launches += info.launches;
-            colmax_kernel<<<cm_grid, 256, 0, st>>>(scratch, s.cv, ldo, dcols, ncols, two_sided, keys, R, r);
+            colmax_kernel<<<cm_grid, 256, 0, st>>>(scratch, s.cv, ldo, cl, ncols, two_sided, keys, R, r);
             ++launches;
             RMG_CUDA(cudaGetLastError());
         }
@@ -181,6 +190,7 @@ int check_perm_args(int p, const int32_t *idx, int R, const int32_t *cols, int n
 {
     if (R < 0 || ncols < 0 || (R > 0 && !idx) || (ncols > 0 && !cols) || (R > 0 && ncols > 0 && !dist))
         return fail(err, errlen, RMG_ERR_INVALID, "bad permutation arguments");
+    if (ncols > 2 * RMG_MAX_P + 3) return fail(err, errlen, RMG_ERR_INVALID, "more columns requested than a result has");
     for (int c = 0; c < ncols; ++c)
         if (cols[c] < 0 || cols[c] >= 2 * p + 3) return fail(err, errlen, RMG_ERR_INVALID, "cols[%d] out of range", c);
     return RMG_OK;
@@ -220,7 +230,6 @@ int randomize_shards(std::vector<PermShard> &S, int n, int p, const double *X, d
         return fail(err, errlen, RMG_ERR_INVALID, "RMG_PERM_PATH=gemm but the GEMM path does not support this shape");
 
     std::vector<unsigned long long *> keys(G, nullptr);
-    std::vector<int32_t *> dcols(G, nullptr);
     std::vector<double *> dD(G, nullptr);
     std::vector<PermDevice> dev(G);
     std::vector<char> begun(G, 0);
@@ -237,9 +246,7 @@ int randomize_shards(std::vector<PermShard> &S, int n, int p, const double *X, d
             RMG_CUDA(cudaEventCreate(&e0[g]));
             RMG_CUDA(cudaEventCreate(&e1[g]));
             RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&keys[g]), (size_t)nk * sizeof(unsigned long long), s.st));
-            RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dcols[g]), (size_t)ncols * sizeof(int32_t), s.st));
             if (!s.ddist) RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dD[g]), (size_t)nk * sizeof(double), s.st));
-            RMG_CUDA(cudaMemcpyAsync(dcols[g], cols, (size_t)ncols * sizeof(int32_t), cudaMemcpyHostToDevice, s.st));
             keys_init_kernel<<<(nk + 255) / 256, 256, 0, s.st>>>(keys[g], nk);
             ++launches[g];
             RMG_CUDA(cudaGetLastError());
@@ -338,7 +345,7 @@ int randomize_shards(std::vector<PermShard> &S, int n, int p, const double *X, d
                     for (cudaEvent_t ev : s.landed)
                         if (ev) cudaStreamWaitEvent(s.st, ev, 0);
                     tl_host_share = G;
-                    rcs[g] = refit_shard(pd, s, n, p, mask_lo, mask_hi, dcols[g], ncols, two_sided, keys[g], R, launches[g],
+                    rcs[g] = refit_shard(pd, s, n, p, mask_lo, mask_hi, cols, ncols, two_sided, keys[g], R, launches[g],
                                          &msgs[g][0], msgs[g].size());
                 });
             }
@@ -381,7 +388,6 @@ cleanup:
         g_launch_count += launches[g];
         if (begun[g]) perm_dev_release(dev[g]);
         if (keys[g]) cudaFreeAsync(keys[g], S[g].st);
-        if (dcols[g]) cudaFreeAsync(dcols[g], S[g].st);
         if (dD[g]) cudaFreeAsync(dD[g], S[g].st);
         if (e0[g]) cudaEventDestroy(e0[g]);
         if (e1[g]) cudaEventDestroy(e1[g]);

@@ -102,6 +102,16 @@ __global__ void perm_floor_keys_kernel(unsigned long long *keys, int nk, const i
     if (i < nk && *any_zero_row) atomicMax(&keys[i], ordered_key(0.0));
 }
 
+// The packed operand reaches the device through a kernel that reads the pinned host buffer directly (zero-copy over the
+// host link) instead of a DMA copy: copies queued on the copy engines run in submission order, so a 3 MB operand
+// batch submitted behind a 28 GB upload of Y would land only after it -- and the first voxel block could not start
+// its permutations while the rest of Y is still on the link.
+__global__ void __launch_bounds__(256)
+perm_fetch_kernel(double2 *__restrict__ dst, const double2 *__restrict__ src_host, size_t n2)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) dst[i] = src_host[i];
+}
+
 // An odd voxel count: the GEMM tiles cover an even number of voxels (16-byte bulk copies); the last voxel of the shard
 // is handed to the explicit-residual kernel instead (unless it lies outside the mask).
 __global__ void perm_flag_voxel_kernel(unsigned char *vflag, const double *yy, int64_t v)
@@ -234,7 +244,10 @@ __device__ __forceinline__ void consume_chunk(double (&acc)[WM][WN][2], const do
 // KP design columns; INV = 1 when component 0 of every permuted design is the (permutation-
 // invariant) constant column c0 * 1: its e_0 = c0 * sum_j y_j comes from the prepass and only
 // KG = KP - INV components per permutation go through the tensor cores.
-template <int KP, int PG, int INV, int KC, int STAGES, bool PREFETCH, int WARPS_M>
+// TWO: alternative = "two.sided" (the default): every statistic is >= 0, so pairs without a contribution (outside the
+// mask, past V, handed to the exact path, padding permutations) may simply contribute 0 and the statistics loop is
+// straight-line code.  The one-sided variant keeps them apart (a 0 must not beat an all-negative column).
+template <int KP, int PG, int INV, int KC, int STAGES, bool TWO, int WARPS_M>
 __global__ void __launch_bounds__((WARPS_M * WARPS_N + 1) * 32, WARPS_M == 4 ? 1 : 2)
 perm_gemm_kernel(PermKernelParams P)
 {
@@ -307,7 +320,7 @@ perm_gemm_kernel(PermKernelParams P)
         if (tid < NT) {
             const int64_t v = vt * NT + tid;
             const bool ok = v < P.V;
-            sv[tid] = ok ? P.yy[v] : -1.0;
+            sv[tid] = ok ? P.yy[v] : -1.0;             // -1: no contribution (outside the mask or past V)
             sv[NT + tid] = ok ? P.y0[v] : 0.0;
             sv[2 * NT + tid] = (ok && INV) ? P.ys[v] : 0.0;
         }
@@ -324,12 +337,10 @@ perm_gemm_kernel(PermKernelParams P)
                 mbar_wait(&full[stage], phase);
                 const double *As = sA + (size_t)stage * A_CHUNK + (size_t)warp_m * (KC / 4) * WM * 32 + lane;
                 const double *Bs = sB + (size_t)stage * B_CHUNK + q * PITCH + warp_n * 32 + g;
-                if (P.debug_skip == 2) {
-                    acc[0][0][0] += As[0] * Bs[0];
-                } else if (tail_guard && kc == P.n_kc - 1)
-                    consume_chunk<WM, KC, true, PREFETCH>(acc, As, Bs, (n - j0 + 3) / 4, j0, q, n);
+                if (tail_guard && kc == P.n_kc - 1)
+                    consume_chunk<WM, KC, true, false>(acc, As, Bs, (n - j0 + 3) / 4, j0, q, n);
                 else
-                    consume_chunk<WM, KC, false, PREFETCH>(acc, As, Bs, KC / 4, j0, q, n);
+                    consume_chunk<WM, KC, false, false>(acc, As, Bs, KC / 4, j0, q, n);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -343,47 +354,41 @@ perm_gemm_kernel(PermKernelParams P)
                 const int r = pt * PERMS_PER_CTA + (warp_m * PG + pg) * 8 + g;
                 const bool rvalid = r < P.R;
                 const PermConst &pc = P.pc[rvalid ? r : 0];
-                // inv > 0: 1/rss of a regular fit; 0: non-finite statistic (counts as 0); < 0: no contribution
-                double inv[WN][2];
+                // w > 0: 1/rss of a regular fit; 0: the statistic counts as 0 (non-finite in the reference; for TWO also
+                // every pair without a contribution); < 0 (one-sided only): no contribution
+                double w[WN][2];
                 double e0[WN][2];   // INV: the un-shifted invariant component
                 {
                     double q1[KP];
 #pragma unroll
                     for (int k = 0; k < KP; ++k) q1[k] = pc.q1[k];
+                    const double c0 = INV ? pc.c0 : 0.0;
 #pragma unroll
                     for (int nt = 0; nt < WN; ++nt) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const int64_t v = vbase + nt * 8 + h;
                             const int col = cbase + nt * 8 + h;
-                            double w = -1.0;
+                            const double yy = sv[col];
+                            const double y0 = sv[NT + col];
+                            double ee = 0.0;
                             e0[nt][h] = 0.0;
-                            if (rvalid && v < P.V) {
-                                const double yy = sv[col];
-                                if (yy >= 0.0) {  // yy < 0 marks a voxel outside the mask (global 0 floor)
-                                    const double y0 = sv[NT + col];
-                                    double ee = 0.0;
-                                    if (INV) {
-                                        const double es = pc.c0 * sv[2 * NT + col];   // c0 * sum(y - y0)
-                                        ee = es * es;
-                                        e0[nt][h] = fma(y0, q1[0], es);
-                                    }
-#pragma unroll
-                                    for (int k = 0; k < KG; ++k) {
-                                        const double es = fma(-y0, q1[k + INV], acc[pg * KG + k][nt][h]);
-                                        ee = fma(es, es, ee);
-                                    }
-                                    const double rss = yy - ee;
-                                    if (yy > 0.0 && rss <= kExactThreshold * yy) {
-                                        P.vflag[v] = 1;  // model explains ~everything: explicit residuals later
-                                    } else if (rss > 1e-290 && rss < 1e290) {
-                                        w = rcp_pos(rss);
-                                    } else {
-                                        w = 0.0;
-                                    }
-                                }
+                            if (INV) {
+                                const double es = c0 * sv[2 * NT + col];   // c0 * sum(y - y0)
+                                ee = es * es;
+                                e0[nt][h] = fma(y0, q1[0], es);
                             }
-                            inv[nt][h] = w;
+#pragma unroll
+                            for (int k = 0; k < KG; ++k) {
+                                const double es = fma(-y0, q1[k + INV], acc[pg * KG + k][nt][h]);
+                                ee = fma(es, es, ee);
+                            }
+                            const double rss = yy - ee;
+                            const bool ok = rvalid && yy >= 0.0;                       // NaN sums fail this too
+                            const bool exact = ok && yy > 0.0 && rss <= kExactThreshold * yy;
+                            if (exact) P.vflag[vbase + nt * 8 + h] = 1;  // model explains ~everything: explicit residuals later
+                            const bool good = ok && !exact && rss > 1e-290 && rss < 1e290;
+                            const double inv = rcp_pos(good ? rss : 1.0);
+                            w[nt][h] = good ? inv : (TWO || (ok && !exact)) ? 0.0 : -1.0;
                         }
                     }
                 }
@@ -393,23 +398,22 @@ perm_gemm_kernel(PermKernelParams P)
                     double rrow[KP];
 #pragma unroll
                     for (int j = 0; j < KP; ++j) rrow[j] = pc.Rinv[ci * 8 + j];
-                    double best = -INFINITY;
+                    double best = TWO ? 0.0 : -INFINITY;
 #pragma unroll
                     for (int nt = 0; nt < WN; ++nt) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const double w = inv[nt][h];
-                            if (w > 0.0) {
-                                double b = INV ? rrow[0] * e0[nt][h] : 0.0;
+                            double b = INV ? rrow[0] * e0[nt][h] : 0.0;
 #pragma unroll
-                                for (int j = 0; j < KG; ++j) b = fma(rrow[j + INV], acc[pg * KG + j][nt][h], b);
-                                double s = b * b * w;
-                                if (!P.two_sided && b < 0.0) s = -s;
-                                if (!isfinite(s)) s = 0.0;
-                                best = fmax(best, s);
-                            } else if (w == 0.0) {
-                                best = fmax(best, 0.0);
-                            }
+                            for (int j = 0; j < KG; ++j) b = fma(rrow[j + INV], acc[pg * KG + j][nt][h], b);
+                            const double ww = w[nt][h];
+                            double s = b * b * fabs(ww);
+                            if (!TWO) s = b < 0.0 ? -s : s;
+                            s = fabs(s) < INFINITY ? s : 0.0;          // non-finite -> 0 (R/minc_voxel_statistics.R:1478)
+                            if (TWO)
+                                best = s > best ? s : best;
+                            else
+                                best = (ww >= 0.0 && s > best) ? s : best;
                         }
                     }
                     // the 4 lanes of a quad hold different voxels of the same permutation
@@ -422,7 +426,7 @@ perm_gemm_kernel(PermKernelParams P)
     }
 }
 
-template <int KP, int PG, int INV, int KC, int STAGES, bool PREFETCH, int WARPS_M>
+template <int KP, int PG, int INV, int KC, int STAGES, bool TWO, int WARPS_M>
 cudaError_t launch_gemm_cfg(const PermKernelParams &P, int sm_count, cudaStream_t st)
 {
     constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
@@ -430,7 +434,7 @@ cudaError_t launch_gemm_cfg(const PermKernelParams &P, int sm_count, cudaStream_
     constexpr int A_CHUNK = WARPS_M * (KC / 4) * WM * 32;
     const size_t smem = (size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + 2 * STAGES * 8 + 3 * NT * 8;
     static_assert((size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + 2 * STAGES * 8 + 3 * NT * 8 <= 227 * 1024, "ring does not fit");
-    auto kern = perm_gemm_kernel<KP, PG, INV, KC, STAGES, PREFETCH, WARPS_M>;
+    auto kern = perm_gemm_kernel<KP, PG, INV, KC, STAGES, TWO, WARPS_M>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t n_vt = (P.V + NT - 1) / NT;
@@ -442,6 +446,9 @@ cudaError_t launch_gemm_cfg(const PermKernelParams &P, int sm_count, cudaStream_
 template <int KP, int PG, int INV>
 cudaError_t launch_gemm(const PermKernelParams &P, int sm_count, cudaStream_t st, int warps_m)
 {
+    if (P.two_sided)
+        return warps_m == 4 ? launch_gemm_cfg<KP, PG, INV, 16, 4, true, 4>(P, sm_count, st)
+                            : launch_gemm_cfg<KP, PG, INV, 16, 4, true, 2>(P, sm_count, st);
     return warps_m == 4 ? launch_gemm_cfg<KP, PG, INV, 16, 4, false, 4>(P, sm_count, st)
                         : launch_gemm_cfg<KP, PG, INV, 16, 4, false, 2>(P, sm_count, st);
 }
@@ -631,10 +638,23 @@ cudaError_t perm_dev_upload(PermDevice &d, const PermPack &pk, int b)
     const int pt0 = b * pk.tiles_per_batch, pt1 = std::min(pk.n_pt, pt0 + pk.tiles_per_batch);
     const int r0 = pk.batch_r0(b), r1 = pk.batch_r1(b);
     const size_t offA = (size_t)pt0 * pk.n_kc * pk.A_CHUNK, nA = (size_t)(pt1 - pt0) * pk.n_kc * pk.A_CHUNK;
-    cudaError_t e = cudaMemcpyAsync(const_cast<double *>(d.P.Apack) + offA, pk.hA + offA, nA * 8, cudaMemcpyHostToDevice, d.cs);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(const_cast<PermConst *>(d.P.pc) + r0, pk.hpc + r0, (size_t)(r1 - r0) * sizeof(PermConst),
-                            cudaMemcpyHostToDevice, d.cs);
+    static_assert(sizeof(PermConst) % 16 == 0, "PermConst is fetched in 16-byte pieces");
+    void *devA = nullptr, *devP = nullptr;       // device-side addresses of the pinned host staging
+    cudaError_t e = cudaHostGetDevicePointer(&devA, pk.hA, 0);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&devP, pk.hpc, 0);
+    if (e != cudaSuccess) return e;
+    const size_t nA2 = nA / 2, nP2 = (size_t)(r1 - r0) * sizeof(PermConst) / 16;
+    if (nA2) {
+        const unsigned blocks = (unsigned)std::min<size_t>(64, (nA2 + 255) / 256);
+        perm_fetch_kernel<<<blocks, 256, 0, d.cs>>>(reinterpret_cast<double2 *>(const_cast<double *>(d.P.Apack) + offA),
+                                                    reinterpret_cast<const double2 *>(static_cast<double *>(devA) + offA), nA2);
+    }
+    if (nP2) {
+        const unsigned blocks = (unsigned)std::min<size_t>(16, (nP2 + 255) / 256);
+        perm_fetch_kernel<<<blocks, 256, 0, d.cs>>>(reinterpret_cast<double2 *>(const_cast<PermConst *>(d.P.pc) + r0),
+                                                    reinterpret_cast<const double2 *>(static_cast<PermConst *>(devP) + r0), nP2);
+    }
+    e = cudaGetLastError();
     if (e == cudaSuccess && !d.ev[b]) e = cudaEventCreateWithFlags(&d.ev[b], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventRecord(d.ev[b], d.cs);
     return e;

@@ -125,7 +125,7 @@ def test_dataset_error_contract(core):
     Y, X, mask = cfg1_data(dims=(8, 8, 8))
     n = X.shape[0]
     with core.Dataset(Y, mask=mask, n_gpus=1) as ds:
-        Xs = np.column_stack([X, X[:, 1]])                       # exact duplicate column: dpotri info = 3
+        Xs = np.column_stack([X, np.zeros(n)])                   # a zero column: R[3,3] == 0 exactly, dpotri info = 3
         with pytest.raises(core.SingularDesignError, match=r"element \(3, 3\) is zero"):
             ds.lm_fit(Xs)
         bad = perm_indices(n, 6, replace=True)
