@@ -15,6 +15,12 @@ typedef unsigned int SEXPTYPE;
 #define CHARSXP 9
 #define RAWSXP 24
 #define VECSXP 19
+#define EXTPTRSXP 22
+#define SYMSXP 1
+#include <limits.h>
+#define NA_INTEGER INT_MIN
+#define NA_LOGICAL INT_MIN
+typedef int Rboolean;
 typedef ptrdiff_t R_xlen_t;
 extern SEXP R_NilValue;
 SEXP Rf_allocVector(SEXPTYPE type, R_xlen_t n);
@@ -42,11 +48,15 @@ int Rf_asLogical(SEXP s);
 double Rf_asReal(SEXP s);
 SEXP Rf_GetOption1(SEXP tag);
 R_xlen_t XLENGTH(SEXP s);
-int TYPEOF(SEXP s);               /* declaration only: used by rminc_b200/csrc/rshim.c's syntax check */
+int TYPEOF(SEXP s);
 unsigned char *RAW(SEXP s);
 SEXP SET_VECTOR_ELT(SEXP x, R_xlen_t i, SEXP v);
 SEXP VECTOR_ELT(SEXP x, R_xlen_t i);
 char *R_alloc(size_t n, int size);
+SEXP R_MakeExternalPtr(void *p, SEXP tag, SEXP prot);
+void *R_ExternalPtrAddr(SEXP s);
+void R_ClearExternalPtr(SEXP s);
+void R_RegisterCFinalizerEx(SEXP s, void (*fun)(SEXP), Rboolean onexit);
 #ifndef FALSE
 #define FALSE 0
 #define TRUE 1

@@ -5,7 +5,12 @@
  * src/modelling_functions.c (voxel_lm, minc2_model) and src/vertex_modelling.c
  * (vertex_lm_loop), compiled from /root/reference where they lie, on in-memory
  * data.  Plus the plain-C harness entry points (ref_*) that tests call through
- * ctypes.  LINPACK dqrls_ and LAPACK dpotri_ (third-party, not in the
+ * ctypes, and (last section) the rest of the R API that the product's .Call shim
+ * (rminc_b200/csrc/rshim.c) uses together with a .Call dispatcher over the routine
+ * tables R_registerRoutines receives, so that tests can EXECUTE the shim: mini-SEXPs
+ * in, SEXP out, Rf_error -> longjmp, R's collect-the-unprotected contract included.
+ * -DRSTUB_NO_REFERENCE leaves out everything that needs the reference's sources.
+ * LINPACK dqrls_ and LAPACK dpotri_ (third-party, not in the
  * reference tree) are forwarded to oracle/rminc_oracle.c's restatements.
  */
 #include <setjmp.h>
@@ -13,6 +18,7 @@
 #include <stdint.h>
 #include "Rinternals.h"
 #include "R_ext/Utils.h"
+#include "R_ext/Rdynload.h"
 #include "minc2.h"
 
 /* ------------------------------------------------------------ mini SEXPs */
@@ -25,9 +31,10 @@ struct rstub_sexp {
     void *data;
     struct rstub_sexp *next_zero; /* list of objects with protect_count == 0 */
     int in_zero;
+    void (*finalizer)(struct rstub_sexp *); /* external pointers */
 };
 
-static struct rstub_sexp nil_obj = {NILSXP, 0, 0, -1, 0, 1, NULL, NULL, 0};
+static struct rstub_sexp nil_obj = {NILSXP, 0, 0, -1, 0, 1, NULL, NULL, 0, NULL};
 SEXP R_NilValue = &nil_obj;
 
 static SEXP zero_list = NULL;
@@ -57,7 +64,8 @@ static void sweep(void)
         SEXP nx = s->next_zero;
         s->in_zero = 0;
         if (s->protect_count == 0 && !s->permanent) {
-            free(s->data);
+            if (s->finalizer) s->finalizer(s);          /* R runs a C finalizer when it collects the pointer */
+            if (s->type != EXTPTRSXP) free(s->data);
             free(s);
         }
         s = nx;
@@ -69,7 +77,7 @@ static size_t elt_size(SEXPTYPE t)
     switch (t) {
     case REALSXP: return sizeof(double);
     case INTSXP: case LGLSXP: return sizeof(int);
-    case STRSXP: return sizeof(SEXP);
+    case STRSXP: case VECSXP: return sizeof(SEXP);
     case CHARSXP: return 1;
     default: return 1;
     }
@@ -129,7 +137,7 @@ int Rf_isNumeric(SEXP s) { return s->type == REALSXP || s->type == INTSXP || s->
 int Rf_isNull(SEXP s) { return s->type == NILSXP; }
 SEXP STRING_ELT(SEXP s, R_xlen_t i) { return ((SEXP *)s->data)[i]; }
 const char *CHAR(SEXP s) { return (const char *)s->data; }
-SEXP Rf_install(const char *name) { (void)name; return R_NilValue; }
+
 SEXP Rf_lang2(SEXP a, SEXP b) { (void)a; (void)b; return R_NilValue; }
 SEXP Rf_eval(SEXP e, SEXP rho) { (void)e; (void)rho; Rf_error("rstub: eval() is not available"); }
 void Rf_defineVar(SEXP a, SEXP b, SEXP c) { (void)a; (void)b; (void)c; }
@@ -237,19 +245,7 @@ int miget_real_value_hyperslab(mihandle_t volume, int buffer_data_type, const mi
     return MI_NOERROR;
 }
 
-/* ------------------------------------------------------- harness entry points */
-SEXP voxel_lm(SEXP Sy, SEXP Sx, int n, int p, double *coefficients, double *residuals,
-              double *effects, double *work, double *qraux, double *v, int *pivot,
-              double *se, double *t);
-SEXP vertex_lm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix);
-SEXP vertex_anova_loop(SEXP data, SEXP Sx, SEXP asgn);
-SEXP vertex_wlm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix, SEXP ws);
-SEXP per_voxel_anova(SEXP filenames, SEXP Sx, SEXP asgn, SEXP have_mask, SEXP mask, SEXP mask_lower_value,
-                     SEXP mask_upper_value);
-SEXP minc2_model(SEXP filenames, SEXP filenames_right, SEXP mmatrix, SEXP asgn, SEXP have_mask,
-                 SEXP mask, SEXP mask_lower_value, SEXP mask_upper_value, SEXP rho,
-                 SEXP nresults, SEXP method);
-
+/* ------------------------------------------------------- objects owned by the harness */
 static SEXP perm_real(const double *src, R_xlen_t n, int nrow, int ncol)
 {
     SEXP s = alloc_obj(REALSXP, n, 1);
@@ -288,6 +284,20 @@ static void reset_after_call(void)
     while (pstack_top > 0) { SEXP s = pstack[--pstack_top]; if (--s->protect_count == 0) zero_push(s); }
     sweep();
 }
+
+#ifndef RSTUB_NO_REFERENCE
+/* ------------------------------------------------------- harness entry points */
+SEXP voxel_lm(SEXP Sy, SEXP Sx, int n, int p, double *coefficients, double *residuals,
+              double *effects, double *work, double *qraux, double *v, int *pivot,
+              double *se, double *t);
+SEXP vertex_lm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix);
+SEXP vertex_anova_loop(SEXP data, SEXP Sx, SEXP asgn);
+SEXP vertex_wlm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix, SEXP ws);
+SEXP per_voxel_anova(SEXP filenames, SEXP Sx, SEXP asgn, SEXP have_mask, SEXP mask, SEXP mask_lower_value,
+                     SEXP mask_upper_value);
+SEXP minc2_model(SEXP filenames, SEXP filenames_right, SEXP mmatrix, SEXP asgn, SEXP have_mask,
+                 SEXP mask, SEXP mask_lower_value, SEXP mask_upper_value, SEXP rho,
+                 SEXP nresults, SEXP method);
 
 /* one voxel through the reference's voxel_lm.  stats = [F, t.., R2, logLik]. */
 int ref_voxel_lm(const double *y, const double *X, int n, int p, double *coef, double *stats,
@@ -513,4 +523,280 @@ int ref_vertex_lm_loop_cov(const double *Y, const double *Z, int64_t V, int n, c
     left->data = NULL; right->data = NULL;
     perm_free(left); perm_free(right); perm_free(mm);
     return rc;
+}
+#endif /* RSTUB_NO_REFERENCE */
+
+/* ================================================================================================================
+ * The rest of the R API used by the product's .Call shim (rminc_b200/csrc/rshim.c), and a .Call dispatcher.
+ *
+ * The shim is compiled UNCHANGED against these stand-ins (make rshim / make ref) and executed by tests/: arguments are
+ * built as mini-SEXPs, the routine is looked up by name in the table the shim hands to R_registerRoutines (the analogue
+ * of src/RMINC_init.c:57-88), the argument count is checked as R's .Call checks it, Rf_error longjmps back here, and
+ * every unprotected object is collected at the next allocation -- so a missing PROTECT in the shim shows up as garbage.
+ * ================================================================================================================ */
+int Rf_isReal(SEXP s) { return s->type == REALSXP; }
+int Rf_isInteger(SEXP s) { return s->type == INTSXP; }
+int Rf_isMatrix(SEXP s) { return s->ncol >= 0; }
+int TYPEOF(SEXP s) { return (int)s->type; }
+R_xlen_t XLENGTH(SEXP s) { return s->len; }
+unsigned char *RAW(SEXP s) { return (unsigned char *)s->data; }
+
+int Rf_asInteger(SEXP s)
+{
+    if (s->len < 1) return NA_INTEGER;
+    switch (s->type) {
+    case INTSXP: case LGLSXP: return ((int *)s->data)[0];
+    case REALSXP: { double d = ((double *)s->data)[0]; return (d != d || d >= 2147483648.0 || d <= -2147483649.0) ? NA_INTEGER : (int)d; }
+    default: return NA_INTEGER;
+    }
+}
+int Rf_asLogical(SEXP s)
+{
+    if (s->len < 1) return NA_LOGICAL;
+    switch (s->type) {
+    case LGLSXP: return ((int *)s->data)[0];
+    case INTSXP: { int v = ((int *)s->data)[0]; return v == NA_INTEGER ? NA_LOGICAL : v != 0; }
+    case REALSXP: { double d = ((double *)s->data)[0]; return d != d ? NA_LOGICAL : d != 0.0; }
+    default: return NA_LOGICAL;
+    }
+}
+double Rf_asReal(SEXP s)
+{
+    if (s->len < 1) return NAN;
+    switch (s->type) {
+    case REALSXP: return ((double *)s->data)[0];
+    case INTSXP: case LGLSXP: { int v = ((int *)s->data)[0]; return v == NA_INTEGER ? NAN : (double)v; }
+    default: return NAN;
+    }
+}
+
+SEXP VECTOR_ELT(SEXP x, R_xlen_t i) { return ((SEXP *)x->data)[i]; }
+SEXP SET_VECTOR_ELT(SEXP x, R_xlen_t i, SEXP v)
+{
+    ((SEXP *)x->data)[i] = v;
+    v->protect_count++;          /* reachable from the list: survives as long as the list does (never collected here) */
+    return v;
+}
+
+/* R_alloc: transient storage R frees at the end of the .Call */
+static void *ralloc_list[4096];
+static int ralloc_top = 0;
+char *R_alloc(size_t n, int size)
+{
+    if (ralloc_top >= 4096) Rf_error("R_alloc: too many transient allocations");
+    void *p = calloc(n > 0 ? n : 1, (size_t)size);
+    if (!p) Rf_error("R_alloc: cannot allocate");
+    ralloc_list[ralloc_top++] = p;
+    return (char *)p;
+}
+static void ralloc_reset(void)
+{
+    while (ralloc_top > 0) free(ralloc_list[--ralloc_top]);
+}
+
+/* symbols and options(): Rf_install interns the name, Rf_GetOption1 reads a small table tests can set */
+#define MAX_SYMS 64
+static SEXP sym_table[MAX_SYMS];
+static int n_syms = 0;
+SEXP Rf_install(const char *name)
+{
+    for (int i = 0; i < n_syms; ++i)
+        if (strcmp((const char *)sym_table[i]->data, name) == 0) return sym_table[i];
+    if (n_syms >= MAX_SYMS) Rf_error("rstub: symbol table full");
+    size_t L = strlen(name);
+    SEXP s = alloc_obj(CHARSXP, (R_xlen_t)L, 1);
+    s->type = SYMSXP;
+    memcpy(s->data, name, L + 1);
+    return sym_table[n_syms++] = s;
+}
+static struct { SEXP sym, value; } opt_table[MAX_SYMS];
+static int n_opts = 0;
+SEXP Rf_GetOption1(SEXP tag)
+{
+    for (int i = 0; i < n_opts; ++i)
+        if (opt_table[i].sym == tag) return opt_table[i].value;
+    return R_NilValue;
+}
+/* options(name = value) for an integer value; value == NA_INTEGER removes the option */
+void rstub_set_option_int(const char *name, int value)
+{
+    SEXP sym = Rf_install(name);
+    int slot = -1;
+    for (int i = 0; i < n_opts; ++i)
+        if (opt_table[i].sym == sym) slot = i;
+    if (value == NA_INTEGER) {
+        if (slot >= 0) opt_table[slot] = opt_table[--n_opts];
+        return;
+    }
+    if (slot < 0) slot = n_opts++;
+    SEXP v = alloc_obj(INTSXP, 1, 1);
+    ((int *)v->data)[0] = value;
+    opt_table[slot].sym = sym;
+    opt_table[slot].value = v;
+}
+
+/* external pointers: data is the address itself */
+SEXP R_MakeExternalPtr(void *p, SEXP tag, SEXP prot)
+{
+    (void)tag; (void)prot;
+    SEXP s = alloc_obj(EXTPTRSXP, 0, 0);
+    free(s->data);
+    s->data = p;
+    return s;
+}
+void *R_ExternalPtrAddr(SEXP s) { return s->type == EXTPTRSXP ? s->data : NULL; }
+void R_ClearExternalPtr(SEXP s) { if (s->type == EXTPTRSXP) s->data = NULL; }
+void R_RegisterCFinalizerEx(SEXP s, void (*fun)(SEXP), Rboolean onexit) { (void)onexit; s->finalizer = fun; }
+
+/* routine tables */
+#define MAX_TABLES 4
+static const R_CallMethodDef *call_tables[MAX_TABLES];
+static int n_tables = 0;
+int R_registerRoutines(DllInfo *info, const void *c, const R_CallMethodDef *call, const void *f, const void *e)
+{
+    (void)info; (void)c; (void)f; (void)e;
+    for (int i = 0; i < n_tables; ++i)
+        if (call_tables[i] == call) return 1;
+    if (call && n_tables < MAX_TABLES) call_tables[n_tables++] = call;
+    return 1;
+}
+int R_useDynamicSymbols(DllInfo *info, int value) { (void)info; (void)value; return 1; }
+
+#ifndef RSTUB_NO_REFERENCE
+/* the reference's own registration lines for the routines compiled into this library (src/RMINC_init.c:57-88) */
+static const R_CallMethodDef ref_call_methods[] = {
+    {"vertex_lm_loop", (DL_FUNC)&vertex_lm_loop, 3},
+    {"vertex_anova_loop", (DL_FUNC)&vertex_anova_loop, 3},
+    {"vertex_wlm_loop", (DL_FUNC)&vertex_wlm_loop, 4},
+    {"per_voxel_anova", (DL_FUNC)&per_voxel_anova, 7},
+    {"minc2_model", (DL_FUNC)&minc2_model, 11},
+    {NULL, NULL, 0}};
+#endif
+
+void R_init_rmincgpu(DllInfo *dll) __attribute__((weak));     /* present when rshim.c is linked in */
+
+/* dyn.load(): runs the shim's R_init_rmincgpu (and registers the reference's routines where they are compiled in).
+ * Returns the number of routines that can be .Call'ed. */
+int rstub_dyn_load(void)
+{
+    if (R_init_rmincgpu) R_init_rmincgpu(NULL);
+#ifndef RSTUB_NO_REFERENCE
+    R_registerRoutines(NULL, NULL, ref_call_methods, NULL, NULL);
+#endif
+    int count = 0;
+    for (int t = 0; t < n_tables; ++t)
+        for (const R_CallMethodDef *m = call_tables[t]; m->name; ++m) ++count;
+    return count;
+}
+/* name and arity of the i-th registered routine (NULL past the end) */
+const char *rstub_routine(int i, int *nargs)
+{
+    for (int t = 0; t < n_tables; ++t)
+        for (const R_CallMethodDef *m = call_tables[t]; m->name; ++m)
+            if (i-- == 0) { if (nargs) *nargs = m->numArgs; return m->name; }
+    return NULL;
+}
+
+typedef SEXP (*rcall_fn)();
+/* .Call(name, args...).  0 = ok (*result is kept alive until rstub_release), 1 = the routine raised an R error (message
+ * in err), 2 = no such routine, 3 = wrong number of arguments (R's own checks for a registered routine). */
+int rstub_dotcall(const char *name, int nargs, SEXP *a, SEXP *result, char *err, size_t errlen)
+{
+    const R_CallMethodDef *hit = NULL;
+    for (int t = 0; t < n_tables && !hit; ++t)
+        for (const R_CallMethodDef *m = call_tables[t]; m->name; ++m)
+            if (strcmp(m->name, name) == 0) { hit = m; break; }
+    if (!hit) { snprintf(err, errlen, "C symbol name \"%s\" not in load table", name); return 2; }
+    if (hit->numArgs != nargs) {
+        snprintf(err, errlen, "Incorrect number of arguments (%d), expecting %d for '%s'", nargs, hit->numArgs, name);
+        return 3;
+    }
+    rcall_fn f = (rcall_fn)hit->fun;
+    int rc = 0;
+    SEXP out = R_NilValue;
+    err_armed = 1;
+    if (setjmp(err_jmp) == 0) {
+        switch (nargs) {
+        case 0: out = f(); break;
+        case 1: out = f(a[0]); break;
+        case 2: out = f(a[0], a[1]); break;
+        case 3: out = f(a[0], a[1], a[2]); break;
+        case 4: out = f(a[0], a[1], a[2], a[3]); break;
+        case 5: out = f(a[0], a[1], a[2], a[3], a[4]); break;
+        case 6: out = f(a[0], a[1], a[2], a[3], a[4], a[5]); break;
+        case 7: out = f(a[0], a[1], a[2], a[3], a[4], a[5], a[6]); break;
+        case 8: out = f(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]); break;
+        case 9: out = f(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]); break;
+        case 10: out = f(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9]); break;
+        case 11: out = f(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]); break;
+        case 12: out = f(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11]); break;
+        case 13: out = f(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12]); break;
+        case 14: out = f(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13]); break;
+        case 15: out = f(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14]); break;
+        case 16: out = f(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]); break;
+        default: snprintf(err, errlen, "rstub: %d arguments not supported", nargs); rc = 3;
+        }
+        if (rc == 0 && out && out != R_NilValue) out->protect_count++;      /* the value returned to "R" stays alive */
+    } else {
+        rc = 1;
+        snprintf(err, errlen, "%s", err_msg);
+        out = R_NilValue;
+    }
+    err_armed = 0;
+    reset_after_call();       /* the protection stack unwinds, unprotected objects are collected */
+    ralloc_reset();
+    if (result) *result = out;
+    return rc;
+}
+
+/* ---- objects built by the tests (permanent until rstub_release) */
+SEXP rstub_nil(void) { return R_NilValue; }
+SEXP rstub_new_real(const double *src, R_xlen_t n, int nrow, int ncol) { return perm_real(src, n, nrow, ncol); }
+SEXP rstub_new_int(const int *src, R_xlen_t n, int nrow, int ncol, int logical)
+{
+    SEXP s = alloc_obj(logical ? LGLSXP : INTSXP, n, 1);
+    if (ncol >= 0) { s->nrow = nrow; s->ncol = ncol; }
+    if (src) memcpy(s->data, src, (size_t)n * sizeof(int));
+    return s;
+}
+SEXP rstub_new_raw(const unsigned char *src, R_xlen_t n)
+{
+    SEXP s = alloc_obj(RAWSXP, n, 1);
+    if (src) memcpy(s->data, src, (size_t)n);
+    return s;
+}
+SEXP rstub_new_strings(const char *const *strs, int n) { return perm_string(strs, n); }
+SEXP rstub_new_list(R_xlen_t n)
+{
+    SEXP s = alloc_obj(VECSXP, n, 1);
+    for (R_xlen_t i = 0; i < n; ++i) ((SEXP *)s->data)[i] = R_NilValue;
+    return s;
+}
+void rstub_list_set(SEXP list, R_xlen_t i, SEXP v) { ((SEXP *)list->data)[i] = v; }
+int rstub_type(SEXP s) { return (int)s->type; }
+R_xlen_t rstub_length(SEXP s) { return s->len; }
+int rstub_nrow(SEXP s) { return s->nrow; }
+int rstub_ncol(SEXP s) { return s->ncol; }
+void *rstub_data(SEXP s) { return s->data; }
+SEXP rstub_list_get(SEXP s, R_xlen_t i) { return ((SEXP *)s->data)[i]; }
+/* drops an object built by rstub_new_* or returned by rstub_dotcall (a list releases its elements; an external
+ * pointer runs its finalizer, as R's collector would) */
+void rstub_release(SEXP s)
+{
+    if (!s || s == R_NilValue) return;
+    if (s->type == VECSXP)
+        for (R_xlen_t i = 0; i < s->len; ++i) {
+            SEXP e = ((SEXP *)s->data)[i];
+            if (e && e != R_NilValue) { if (e->protect_count > 0) e->protect_count--; rstub_release(e); }
+        }
+    if (s->type == STRSXP) { perm_free(s); return; }
+    if (s->finalizer) s->finalizer(s);
+    if (s->in_zero) {           /* still on the collector's list: let the next sweep free it */
+        s->protect_count = 0;
+        s->permanent = 0;
+        s->finalizer = NULL;
+        return;
+    }
+    if (s->type != EXTPTRSXP) free(s->data);
+    free(s);
 }

@@ -1,15 +1,35 @@
 # rminc_gpu.R -- R wrappers that make the GPU path a drop-in inside RMINC.
 #
-# Source this after library(RMINC) (or add it to RMINC's R/ directory).  It re-defines the three
-# call sites of the native per-voxel OLS loop and nothing else; formula handling, attributes,
-# classes and every downstream consumer (mincFDR, AIC/BIC, mincWriteVolume, ...) are RMINC's own.
+# Either add this file to RMINC's R/ directory (its definitions then replace RMINC's own inside the namespace), or
+# source() it after library(RMINC) AND call rmincgpu_install(): RMINC::mincLm, mincRandomize and mincTFCE resolve
+# mincLm_c_wrapper / mincRandomize_core inside namespace:RMINC, so definitions that only live in the global
+# environment are never reached by them -- rmincgpu_install() assigns them into the namespace
+# (utils::assignInNamespace) and rmincgpu_uninstall() puts RMINC's own back.  It re-defines the call sites of the
+# native per-voxel OLS loop and nothing else; formula handling, attributes, classes and every downstream consumer
+# (mincFDR, AIC/BIC, mincWriteVolume, ...) are RMINC's own.
 #
 #   mincLm_c_wrapper   R/minc_voxel_statistics.R:695-712   -> .Call("rmincgpu_lm")
 #   vertex_lm_loop     call sites R/minc_vertex_statistics.R:408-414, R/minc_anatomy.R:1144-1150
 #                                                           -> .Call("rmincgpu_vertex_lm_loop")
 #   mincRandomize_core R/minc_voxel_statistics.R:1441-1531 -> .Call("rmincgpu_randomize")
 #
-# options(RMINC_GPU_N = k) shards voxels over k GPUs of the box (default 1).
+# options(RMINC_GPU_N = k) shards voxels over k GPUs of the box (default 1); options(RMINC_GPU_DEVICE = d) picks the
+# device of the single-GPU routines (default 0).
+
+.rmincgpu_saved <- new.env()
+
+# Make RMINC's own mincLm / mincRandomize / mincTFCE.mincLm use the GPU: replace the two internal functions they call.
+rmincgpu_install <- function() {
+  for (nm in c("mincLm_c_wrapper", "mincRandomize_core")) {
+    if (is.null(.rmincgpu_saved[[nm]])) .rmincgpu_saved[[nm]] <- get(nm, envir = asNamespace("RMINC"))
+    utils::assignInNamespace(nm, get(nm, envir = globalenv()), ns = "RMINC")
+  }
+  invisible(TRUE)
+}
+rmincgpu_uninstall <- function() {
+  for (nm in ls(.rmincgpu_saved)) utils::assignInNamespace(nm, .rmincgpu_saved[[nm]], ns = "RMINC")
+  invisible(TRUE)
+}
 
 rmincgpu_n <- function(parallel = NULL) {
   if (!is.null(parallel)) return(as.integer(parallel[2]))
@@ -41,12 +61,15 @@ mincLm_c_wrapper <- function(plm, mask, mask_min, mask_max, n_gpus = rmincgpu_n(
 }
 
 # mincLm(parallel = c("local", N)) on the GPU path means N GPUs, not N forked processes: a CUDA
-# context must never be forked.  The sequential branch of mincLm (R/minc_voxel_statistics.R:841-847)
-# is reused with n_gpus = N; the masked rows come back as 0 in every column, as the reference's
-# parallel branch produces (:898-905).
+# context must never be forked.  RMINC's own mincLm is run with parallel = NULL -- its sequential branch
+# (R/minc_voxel_statistics.R:841-847) calls mincLm_c_wrapper, which rmincgpu_install() has pointed at the GPU wrapper
+# above -- and n_gpus = N travels in options(RMINC_GPU_N); the masked rows come back as 0 in every column, as the
+# reference's parallel branch produces (:898-905).
 mincLm_gpu <- function(formula, data = NULL, subset = NULL, mask = NULL, maskval = NULL, parallel = NULL) {
+  if (!identical(get("mincLm_c_wrapper", envir = asNamespace("RMINC")), get("mincLm_c_wrapper", envir = globalenv())))
+    stop("call rmincgpu_install() first: RMINC::mincLm still resolves RMINC's CPU mincLm_c_wrapper")
   old <- options(RMINC_GPU_N = rmincgpu_n(parallel)); on.exit(options(old))
-  cl <- match.call(); cl[[1]] <- as.name("mincLm"); cl$parallel <- NULL
+  cl <- match.call(); cl[[1]] <- quote(RMINC::mincLm); cl$parallel <- NULL
   eval(cl, parent.frame())
 }
 
@@ -207,3 +230,41 @@ mincTFCE_mincLm_gpu <- function(lmod, R = 500, alternative = c("two.sided", "gre
             class = c("mincTFCE_randomization", "minc_randomization"))
 }
 
+
+# ---- the resident dataset: Y is staged and uploaded ONCE (sharded over n_gpus devices) and stays in GPU memory behind an
+# external pointer; mincLm, mincAnova, mincRandomize and mincFDR then run on the resident shards.  The reference re-reads
+# every file for each of them (R/minc_voxel_statistics.R:1477).  The handle frees itself when it is garbage collected;
+# rmincgpu_dataset_free() does it at once.
+rmincgpu_dataset <- function(filenames, mask = NULL, maskval = NULL, n_gpus = rmincgpu_n()) {
+  Y <- rmincgpu_stage(as.character(filenames))
+  m <- if (is.null(mask)) NULL else as.double(mincGetVolume(mask))
+  lo <- if (is.null(maskval)) 1 else maskval
+  hi <- if (is.null(maskval)) 99999999 else maskval
+  h <- .Call("rmincgpu_dataset_create", Y, m, as.double(lo), as.double(hi), as.integer(n_gpus), PACKAGE = "rmincgpu")
+  structure(list(handle = h, filenames = as.character(filenames), mask = mask), class = "rmincgpu_dataset")
+}
+rmincgpu_dataset_free <- function(ds) invisible(.Call("rmincgpu_dataset_free", ds$handle, PACKAGE = "rmincgpu"))
+
+# the native step of mincLm / mincAnova on the handle (the matrices RMINC's R layer then decorates)
+rmincgpu_dataset_lm <- function(ds, mmatrix) .Call("rmincgpu_dataset_lm", ds$handle, as.matrix(mmatrix), PACKAGE = "rmincgpu")
+rmincgpu_dataset_anova <- function(ds, mmatrix)
+  .Call("rmincgpu_dataset_anova", ds$handle, mmatrix, as.integer(attr(mmatrix, "assign")), PACKAGE = "rmincgpu")
+
+# mincRandomize on the handle: lmod is the mincLm object fitted on the same files
+rmincgpu_dataset_randomize <- function(ds, lmod, R = 500, replace = FALSE, columns = grep("tvalue-", colnames(lmod)),
+                                       alternative = c("two.sided", "greater")) {
+  alternative <- match.arg(alternative)
+  n <- nrow(attr(lmod, "data"))
+  idx <- vapply(seq_len(R), function(i) sample(seq_len(n), replace = replace), integer(n))
+  dist <- .Call("rmincgpu_dataset_randomize", ds$handle, attr(lmod, "model"), idx, as.integer(columns),
+                alternative == "two.sided", PACKAGE = "rmincgpu")
+  colnames(dist) <- colnames(lmod)[columns]
+  dist
+}
+
+# mincFDR's per-column step on the result of the LAST fit on the handle (column: its 1-based column number)
+rmincgpu_dataset_fdr <- function(ds, column, stat_type, df) {
+  res <- .Call("rmincgpu_dataset_fdr", ds$handle, as.integer(column), if (stat_type == "F") 2L else 1L, as.double(df),
+               PACKAGE = "rmincgpu")
+  list(qvalue = res[[1]], thresholds = res[[2]])
+}

@@ -3,7 +3,7 @@
 # It compares every routine of rminc_gpu.R with RMINC's own CPU result on RMINC's test data, in the style of
 # tests/testthat/test_mincLm.R, test_vertexLm.R, test_anatLm.R, test_mincAnova.R, test_mincFDR.R and test_mincTFCE.R.
 #
-#   library(RMINC); dyn.load("rmincgpu.so"); source("rminc_gpu.R"); testthat::test_file("test_rminc_gpu.R")
+#   library(RMINC); dyn.load("rmincgpu.so"); source("rminc_gpu.R"); rmincgpu_install(); testthat::test_file("test_rminc_gpu.R")
 library(testthat)
 context("rminc-b200 against RMINC")
 
@@ -66,4 +66,30 @@ test_that("TFCE: graph routine equals RMINC's, volume routine equals vertexTFCE 
   hmax <- max(abs(vol))
   got <- .Call("rmincgpu_volume_tfce", as.numeric(vol), as.double(sizes), 6L, .001, hmax / 100, .5, 2, 0L, PACKAGE = "rmincgpu")
   expect_false(any(abs(got - ref) > 1e-4 * max(abs(ref))))     # thresholds differ by the floating residue of the R loop
+})
+
+test_that("RMINC's own mincLm reaches the GPU after rmincgpu_install()", {
+  # the advisor's finding: sourcing rminc_gpu.R alone leaves RMINC::mincLm on the CPU .Call("minc2_model")
+  launches <- function() .Call("rmincgpu_launch_count", PACKAGE = "rmincgpu")
+  before <- launches()
+  got <- verboseRun(mincLm(jacobians_fixed_2 ~ Sex + Age, gf, mask = mask))
+  expect_gt(launches(), before)
+  rmincgpu_uninstall()
+  ref <- verboseRun(mincLm(jacobians_fixed_2 ~ Sex + Age, gf, mask = mask))
+  rmincgpu_install()
+  inside <- mincGetVolume(mask) > 0.5
+  expect_equal(unclass(got)[inside, ], unclass(ref)[inside, ], tolerance = tol, check.attributes = FALSE)
+})
+
+test_that("one upload: mincLm, mincRandomize and mincFDR on the resident dataset", {
+  ds <- rmincgpu_dataset(gf$jacobians_fixed_2, mask = mask)
+  X <- model.matrix(~ Sex + Age, gf)
+  ref <- verboseRun(mincLm(jacobians_fixed_2 ~ Sex + Age, gf, mask = mask))
+  inside <- mincGetVolume(mask) > 0.5
+  expect_equal(rmincgpu_dataset_lm(ds, X)[inside, ], unclass(ref)[inside, ], tolerance = tol, check.attributes = FALSE)
+  set.seed(1); d <- rmincgpu_dataset_randomize(ds, ref, R = 20)
+  expect_equal(dim(d), c(20L, 3L))
+  q <- rmincgpu_dataset_fdr(ds, which(colnames(ref) == "tvalue-Age"), "t", attr(ref, "df")[[2]])
+  expect_true(all(q$qvalue[inside] >= 0 & q$qvalue[inside] <= 1))
+  rmincgpu_dataset_free(ds)
 })

@@ -15,6 +15,17 @@ constexpr int NT = kPermNT, PITCH = kPermPitch;
 // 4 * (KC/4) * WM * 32 doubles, so WM <= 6 affords 32-subject stages (3 of them), WM = 7..8 keeps 16 (4).
 
 constexpr int WARPS_N = 2, WN = 4;  // warp tile: WM m8-tiles x 4 n8-tiles (32 voxels)
+
+// Ring depth: as many stages as fit (at most 6).  The two consumer warps that share an SM sub-partition run skewed by
+// about three stages (see the kernel), so that one of them always has MMAs to issue while the other is in its
+// statistics epilogue; the ring has to cover that skew plus the producer's lead.
+constexpr int stages_for(int wm, int warps_m, int kc)
+{
+    const int stage_bytes = (warps_m * (kc / 4) * wm * 32 + kc * kPermPitch) * 8;
+    const int budget = (warps_m == 4 ? 224 : 110) * 1024 - 2 * 8 * 8 - warps_m * WARPS_N * 3 * 32 * 8;
+    const int s = budget / stage_bytes;
+    return s > 6 ? 6 : s < 2 ? 2 : s;
+}
 // Consumer warps along M and CTAs per SM come in two shapes: 4 x 2 warps, one CTA per SM (default),
 // or 2 x 2 warps, two CTAs per SM (RMG_PERM_CTAS=2; same throughput, more L2/DRAM traffic).
 
@@ -262,9 +273,9 @@ perm_gemm_kernel(PermKernelParams P)
     double *sB = sA + (size_t)STAGES * A_CHUNK;
     uint64_t *full = reinterpret_cast<uint64_t *>(sB + (size_t)STAGES * B_CHUNK);
     uint64_t *empty = full + STAGES;
-    // per-voxel constants of the current voxel tile (|y'|^2, y0, sum y'), staged once per tile so the
-    // epilogue never waits on a chain of dependent global loads
-    double *sv = reinterpret_cast<double *>(empty + STAGES);   // [3][NT]
+    // per-voxel constants (|y'|^2, y0, sum y') of each warp's 32 voxels of the current voxel tile, staged by the warp
+    // itself (no CTA-wide barrier: the warps of a CTA deliberately do not run in lockstep)
+    double *sv_all = reinterpret_cast<double *>(empty + STAGES);   // [CONSUMER_WARPS][3][32]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -313,18 +324,33 @@ perm_gemm_kernel(PermKernelParams P)
     uint32_t stage = 0, phase = 0;
     const bool tail_guard = (n % KC) != 0;
 
+    double *sv = sv_all + warp * 96;                          // [3][32]
+    // this lane's voxel of the warp's 32: its per-voxel sums are fetched one voxel tile ahead
+    double pf_yy = -1.0, pf_y0 = 0.0, pf_ys = 0.0;
+    auto prefetch = [&](int64_t vt) {
+        const int64_t v = vt * NT + warp_n * 32 + lane;
+        const bool ok = vt < n_vt && v < P.V;
+        pf_yy = ok ? P.yy[v] : -1.0;                   // -1: no contribution (outside the mask or past V)
+        pf_y0 = ok ? P.y0[v] : 0.0;
+        pf_ys = (ok && INV) ? P.ys[v] : 0.0;
+    };
+    prefetch(blockIdx.x);
+    // Skew: warps w and w + 4 share an SM sub-partition and its DMMA pipe.  Holding the second one back by about three
+    // stages once, at the start, lets each run its epilogue while the other still issues MMAs; the skew then persists
+    // (whoever is alone on the pipe runs twice as fast, for exactly as long as the other's epilogue takes).
+    if (WARPS_M == 4 && warp >= CONSUMER_WARPS / 2 && STAGES >= 5) {
+        for (int i = 0; i < 3; ++i) __nanosleep(800);
+    }
+
     for (int64_t vt = blockIdx.x; vt < n_vt; vt += gridDim.x) {
         const int64_t vbase = vt * NT + warp_n * 32 + 2 * q;  // + nt*8 + h
-        const int cbase = warp_n * 32 + 2 * q;                // column of this thread inside the tile
-        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");   // previous tile's epilogues are done
-        if (tid < NT) {
-            const int64_t v = vt * NT + tid;
-            const bool ok = v < P.V;
-            sv[tid] = ok ? P.yy[v] : -1.0;             // -1: no contribution (outside the mask or past V)
-            sv[NT + tid] = ok ? P.y0[v] : 0.0;
-            sv[2 * NT + tid] = (ok && INV) ? P.ys[v] : 0.0;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
+        const int cbase = 2 * q;                              // column of this thread inside the warp's 32 voxels
+        __syncwarp();                                         // the previous tile's epilogue has read sv
+        sv[lane] = pf_yy;
+        sv[32 + lane] = pf_y0;
+        sv[64 + lane] = pf_ys;
+        __syncwarp();
+        prefetch(vt + gridDim.x);
         for (int pt = 0; pt < P.n_pt; ++pt) {
             double acc[WM][WN][2];
 #pragma unroll
@@ -369,11 +395,11 @@ perm_gemm_kernel(PermKernelParams P)
                         for (int h = 0; h < 2; ++h) {
                             const int col = cbase + nt * 8 + h;
                             const double yy = sv[col];
-                            const double y0 = sv[NT + col];
+                            const double y0 = sv[32 + col];
                             double ee = 0.0;
                             e0[nt][h] = 0.0;
                             if (INV) {
-                                const double es = c0 * sv[2 * NT + col];   // c0 * sum(y - y0)
+                                const double es = c0 * sv[64 + col];   // c0 * sum(y - y0)
                                 ee = es * es;
                                 e0[nt][h] = fma(y0, q1[0], es);
                             }
@@ -432,8 +458,8 @@ cudaError_t launch_gemm_cfg(const PermKernelParams &P, int sm_count, cudaStream_
     constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
     constexpr int WM = (KP - INV) * PG;
     constexpr int A_CHUNK = WARPS_M * (KC / 4) * WM * 32;
-    const size_t smem = (size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + 2 * STAGES * 8 + 3 * NT * 8;
-    static_assert((size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + 2 * STAGES * 8 + 3 * NT * 8 <= 227 * 1024, "ring does not fit");
+    const size_t smem = (size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + 2 * STAGES * 8 + CONSUMER_WARPS * 96 * 8;
+    static_assert((size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + 2 * STAGES * 8 + CONSUMER_WARPS * 96 * 8 <= 227 * 1024, "ring does not fit");
     auto kern = perm_gemm_kernel<KP, PG, INV, KC, STAGES, TWO, WARPS_M>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -446,11 +472,13 @@ cudaError_t launch_gemm_cfg(const PermKernelParams &P, int sm_count, cudaStream_
 template <int KP, int PG, int INV>
 cudaError_t launch_gemm(const PermKernelParams &P, int sm_count, cudaStream_t st, int warps_m)
 {
+    constexpr int WM = (KP - INV) * PG;
+    constexpr int S4 = stages_for(WM, 4, 16), S2 = stages_for(WM, 2, 16);
     if (P.two_sided)
-        return warps_m == 4 ? launch_gemm_cfg<KP, PG, INV, 16, 4, true, 4>(P, sm_count, st)
-                            : launch_gemm_cfg<KP, PG, INV, 16, 4, true, 2>(P, sm_count, st);
-    return warps_m == 4 ? launch_gemm_cfg<KP, PG, INV, 16, 4, false, 4>(P, sm_count, st)
-                        : launch_gemm_cfg<KP, PG, INV, 16, 4, false, 2>(P, sm_count, st);
+        return warps_m == 4 ? launch_gemm_cfg<KP, PG, INV, 16, S4, true, 4>(P, sm_count, st)
+                            : launch_gemm_cfg<KP, PG, INV, 16, S2, true, 2>(P, sm_count, st);
+    return warps_m == 4 ? launch_gemm_cfg<KP, PG, INV, 16, S4, false, 4>(P, sm_count, st)
+                        : launch_gemm_cfg<KP, PG, INV, 16, S2, false, 2>(P, sm_count, st);
 }
 
 // permutation groups (of 8) per warp for KG GEMM components per permutation: KG * PG <= 8 m-tiles

@@ -21,7 +21,15 @@
  *                            (R/minc_voxel_statistics.R:1186-1439) without the external TFCE program
  *   rmincgpu_fdr             mincFDR's p-value + p.adjust(., "fdr") + threshold step for one column (R/minc_FDR.R:385-505)
  *   rmincgpu_anova           per_voxel_anova / vertex_anova_loop (src/minc_anova.c:142, src/vertex_modelling.c:178)
+ *   rmincgpu_dataset_*       the resident dataset: one upload, then mincLm / mincAnova / mincRandomize / mincFDR on the
+ *                            shards (an external pointer with a finalizer; R/minc_voxel_statistics.R:911-912, :1457-1477)
+ *
+ * Single-GPU routines run on device getOption("RMINC_GPU_DEVICE", 0); the sharded ones take the GPU count as an argument
+ * (options(RMINC_GPU_N) on the R side).
  */
+#include <limits.h>
+#include <stdint.h>
+
 #include <R.h>
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
@@ -31,6 +39,65 @@
 static void check(int rc, const char *msg)
 {
     if (rc != RMG_OK) Rf_error("%s", msg);   /* e.g. "element (4, 4) is zero, so the inverse cannot be computed" */
+}
+
+/* device of the single-GPU routines: options(RMINC_GPU_DEVICE = d), default 0 */
+static int gpu_device(void)
+{
+    SEXP o = Rf_GetOption1(Rf_install("RMINC_GPU_DEVICE"));
+    if (Rf_isNull(o)) return 0;
+    const int d = Rf_asInteger(o);
+    if (d == NA_INTEGER || d < 0) Rf_error("options(RMINC_GPU_DEVICE) must be a non-negative device number");
+    return d;
+}
+
+/* an R matrix has int dimensions */
+static int matrix_rows(R_xlen_t V)
+{
+    if (V > INT_MAX) Rf_error("%.0f voxels do not fit the rows of an R matrix (at most %d)", (double)V, INT_MAX);
+    return (int)V;
+}
+
+static int flag_arg(SEXP s, const char *what)
+{
+    const int v = Rf_asLogical(s);
+    if (v == NA_LOGICAL) Rf_error("%s must be TRUE or FALSE", what);
+    return v;
+}
+
+static int count_arg(SEXP s, const char *what)
+{
+    const int v = Rf_asInteger(s);
+    if (v == NA_INTEGER) Rf_error("%s must not be NA", what);
+    return v;
+}
+
+/* 1-based R indices -> 0-based, in R_alloc'd memory (freed by R at the end of the .Call) */
+static int *zero_based(SEXP x, R_xlen_t count, const char *what)
+{
+    int *out = (int *)R_alloc((size_t)(count > 0 ? count : 1), sizeof(int));
+    for (R_xlen_t i = 0; i < count; ++i) {
+        if (INTEGER(x)[i] == NA_INTEGER) Rf_error("%s must not contain NA", what);
+        out[i] = INTEGER(x)[i] - 1;
+    }
+    return out;
+}
+
+/* Arguments of the stored-type routines.  The C ABI reads ceil(V / slice_len) x n doubles from scale and offset: a table
+ * with fewer rows, a slice length < 1 or NA would be an out-of-bounds host read there, so it is an R error here. */
+static int64_t stored_slice_len(int dt, SEXP scale, SEXP offset, int n, R_xlen_t V, SEXP slice_len)
+{
+    if (dt != RMG_STORED_U16 && dt != RMG_STORED_F32) Rf_error("dtype must be 1 (uint16) or 2 (float32)");
+    if (dt != RMG_STORED_U16) return V > 0 ? (int64_t)V : 1;
+    const double sl = Rf_asReal(slice_len);
+    if (!(sl >= 1.0) || sl != (double)(int64_t)sl) Rf_error("slice_len must be a whole number >= 1");
+    if (!Rf_isReal(scale) || !Rf_isReal(offset) || Rf_ncols(scale) != n || Rf_ncols(offset) != n)
+        Rf_error("scale and offset must be nslices x n double matrices");
+    const int64_t nslices = V > 0 ? ((int64_t)V + (int64_t)sl - 1) / (int64_t)sl : 0;
+    if ((int64_t)Rf_nrows(scale) != nslices || (int64_t)Rf_nrows(offset) != nslices)
+        Rf_error("scale and offset must have ceiling(V / slice_len) = %.0f rows (got %d and %d)", (double)nslices,
+                 Rf_nrows(scale), Rf_nrows(offset));
+    return (int64_t)sl;
 }
 
 static const double *mask_or_null(SEXP mask, R_xlen_t V)
@@ -51,10 +118,10 @@ static SEXP vertex_lm_loop_cov(SEXP data_left, SEXP data_right, SEXP mmatrix)
     const int has_static = !Rf_isLogical(mmatrix);
     if (has_static && (!Rf_isReal(mmatrix) || Rf_nrows(mmatrix) != n)) Rf_error("model matrix does not match the data");
     const int ps = has_static ? Rf_ncols(mmatrix) : 0, p = has_static ? ps + 1 : 2;
-    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, 2 * p + 3));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, matrix_rows(V), 2 * p + 3));
     char err[512] = "";
     int rc = rmg_vertex_lm_cov(REAL(data_left), REAL(data_right), V, V > 0 ? V : 1, n, has_static ? REAL(mmatrix) : NULL, ps,
-                               REAL(out), V > 0 ? V : 1, 0, err, sizeof err);
+                               REAL(out), V > 0 ? V : 1, gpu_device(), err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
     return out;
@@ -67,11 +134,9 @@ SEXP rmincgpu_vertex_lm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix)
     const R_xlen_t V = Rf_nrows(data_left);
     const int n = Rf_ncols(data_left), p = Rf_ncols(mmatrix);
     if (Rf_nrows(mmatrix) != n) Rf_error("model matrix has %d rows, data has %d subjects", Rf_nrows(mmatrix), n);
-    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, 2 * p + 3));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, matrix_rows(V), 2 * p + 3));
     char err[512] = "";
-    int rc = rmg_vertex_lm(REAL(data_left), V, V > 0 ? V : 1, n, REAL(mmatrix), p, REAL(out), V > 0 ? V : 1,
-                           Rf_asInteger(Rf_GetOption1(Rf_install("RMINC_GPU_DEVICE"))) > 0
-                               ? Rf_asInteger(Rf_GetOption1(Rf_install("RMINC_GPU_DEVICE"))) : 0,
+    int rc = rmg_vertex_lm(REAL(data_left), V, V > 0 ? V : 1, n, REAL(mmatrix), p, REAL(out), V > 0 ? V : 1, gpu_device(),
                            err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
@@ -87,10 +152,10 @@ SEXP rmincgpu_vertex_wlm_loop(SEXP data_left, SEXP data_right, SEXP mmatrix, SEX
     const R_xlen_t V = Rf_nrows(data_left);
     const int n = Rf_ncols(data_left), p = Rf_ncols(mmatrix);
     if (Rf_nrows(mmatrix) != n || LENGTH(ws) != n) Rf_error("Incorrect number of weights supplied, need one per observation");
-    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, 2 * p + 3));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, matrix_rows(V), 2 * p + 3));
     char err[512] = "";
-    int rc = rmg_vertex_wlm(REAL(data_left), V, V > 0 ? V : 1, n, REAL(mmatrix), p, REAL(ws), REAL(out), V > 0 ? V : 1, 0,
-                            err, sizeof err);
+    int rc = rmg_vertex_wlm(REAL(data_left), V, V > 0 ? V : 1, n, REAL(mmatrix), p, REAL(ws), REAL(out), V > 0 ? V : 1,
+                            gpu_device(), err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
     return out;
@@ -103,13 +168,13 @@ SEXP rmincgpu_lm(SEXP Y, SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP mask_upp
     const int n = Rf_ncols(Y), p = Rf_ncols(mmatrix);
     if (Rf_nrows(mmatrix) != n) Rf_error("model matrix has %d rows, data has %d subjects", Rf_nrows(mmatrix), n);
     const double *m = mask_or_null(mask, V);
-    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, 2 * p + 3));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, matrix_rows(V), 2 * p + 3));
     char err[512] = "";
-    const int G = Rf_asInteger(ngpu);
+    const int G = count_arg(ngpu, "ngpu");
     int rc = G > 1 ? rmg_lm_fit_multi(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, m, Rf_asReal(mask_lower),
                                       Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, G, err, sizeof err)
                    : rmg_lm_fit(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, m, Rf_asReal(mask_lower),
-                                Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, 0, err, sizeof err);
+                                Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, gpu_device(), err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
     return out;
@@ -126,10 +191,10 @@ SEXP rmincgpu_lm_cov(SEXP Y, SEXP Z, SEXP mmatrix, SEXP mask, SEXP mask_lower, S
     if (has_static && (!Rf_isReal(mmatrix) || Rf_nrows(mmatrix) != n)) Rf_error("model matrix does not match the data");
     const int ps = has_static ? Rf_ncols(mmatrix) : 0, p = has_static ? ps + 1 : 2;
     const double *m = mask_or_null(mask, V);
-    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, 2 * p + 3));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, matrix_rows(V), 2 * p + 3));
     char err[512] = "";
     int rc = rmg_lm_fit_cov(REAL(Y), REAL(Z), V, V > 0 ? V : 1, n, has_static ? REAL(mmatrix) : NULL, ps, m,
-                            Rf_asReal(mask_lower), Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, 0, err, sizeof err);
+                            Rf_asReal(mask_lower), Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, gpu_device(), err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
     return out;
@@ -142,20 +207,20 @@ SEXP rmincgpu_lm_stored(SEXP U, SEXP dtype, SEXP nvoxels, SEXP scale, SEXP offse
                         SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP mask_upper)
 {
     if (TYPEOF(U) != RAWSXP || !Rf_isReal(mmatrix)) Rf_error("U must be a raw vector and mmatrix a double matrix");
-    const int dt = Rf_asInteger(dtype);
+    const int dt = count_arg(dtype, "dtype");
+    if (dt != RMG_STORED_U16 && dt != RMG_STORED_F32) Rf_error("dtype must be 1 (uint16) or 2 (float32)");
     const size_t es = dt == RMG_STORED_U16 ? 2 : 4;
     const R_xlen_t V = (R_xlen_t)Rf_asReal(nvoxels);
     const int n = Rf_nrows(mmatrix), p = Rf_ncols(mmatrix);
-    if ((R_xlen_t)(XLENGTH(U) / es) != V * n) Rf_error("U holds %.0f samples, expected %.0f", (double)(XLENGTH(U) / es), (double)V * n);
+    if (V < 0 || (R_xlen_t)(XLENGTH(U) / es) != V * n) Rf_error("U holds %.0f samples, expected %.0f", (double)(XLENGTH(U) / es), (double)V * n);
     const int scaled = dt == RMG_STORED_U16;
-    if (scaled && (!Rf_isReal(scale) || !Rf_isReal(offset) || Rf_ncols(scale) != n || Rf_ncols(offset) != n))
-        Rf_error("scale and offset must be nslices x n double matrices");
+    const int64_t sl = stored_slice_len(dt, scale, offset, n, V, slice_len);
     const double *m = mask_or_null(mask, V);
-    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, 2 * p + 3));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, matrix_rows(V), 2 * p + 3));
     char err[512] = "";
     int rc = rmg_lm_fit_stored(RAW(U), dt, V, V > 0 ? V : 1, n, scaled ? REAL(scale) : NULL, scaled ? REAL(offset) : NULL,
-                               Rf_asReal(voxel_min), (int64_t)Rf_asReal(slice_len), REAL(mmatrix), p, m,
-                               Rf_asReal(mask_lower), Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, 0, err, sizeof err);
+                               Rf_asReal(voxel_min), sl, REAL(mmatrix), p, m, Rf_asReal(mask_lower), Rf_asReal(mask_upper),
+                               REAL(out), V > 0 ? V : 1, gpu_device(), err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
     return out;
@@ -171,19 +236,17 @@ SEXP rmincgpu_randomize(SEXP Y, SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP m
     if (Rf_nrows(idx) != n) Rf_error("idx must have one row per subject");
     const double *m = mask_or_null(mask, V);
     /* R is 1-based: idx holds sample(seq_len(n)), columns are column numbers of the mincLm matrix */
-    int *idx0 = (int *)R_alloc((size_t)n * R, sizeof(int));
-    int *col0 = (int *)R_alloc((size_t)nc, sizeof(int));
-    for (R_xlen_t i = 0; i < (R_xlen_t)n * R; ++i) idx0[i] = INTEGER(idx)[i] - 1;
-    for (int i = 0; i < nc; ++i) col0[i] = INTEGER(columns)[i] - 1;
+    int *idx0 = zero_based(idx, (R_xlen_t)n * R, "idx");
+    int *col0 = zero_based(columns, nc, "columns");
     SEXP out = PROTECT(Rf_allocMatrix(REALSXP, R, nc));
     char err[512] = "";
-    const int G = Rf_asInteger(ngpu);
+    const int G = count_arg(ngpu, "ngpu");
     int rc = G > 1 ? rmg_randomize_multi(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, m, Rf_asReal(mask_lower),
-                                         Rf_asReal(mask_upper), idx0, R, col0, nc, Rf_asLogical(two_sided),
+                                         Rf_asReal(mask_upper), idx0, R, col0, nc, flag_arg(two_sided, "two_sided"),
                                          REAL(out), G, err, sizeof err)
                    : rmg_randomize(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, m, Rf_asReal(mask_lower),
-                                   Rf_asReal(mask_upper), idx0, R, col0, nc, Rf_asLogical(two_sided), REAL(out), 0,
-                                   err, sizeof err);
+                                   Rf_asReal(mask_upper), idx0, R, col0, nc, flag_arg(two_sided, "two_sided"), REAL(out),
+                                   gpu_device(), err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
     return out;
@@ -196,32 +259,30 @@ SEXP rmincgpu_randomize_stored(SEXP U, SEXP dtype, SEXP nvoxels, SEXP scale, SEX
 {
     if (TYPEOF(U) != RAWSXP || !Rf_isReal(mmatrix) || !Rf_isInteger(idx) || !Rf_isInteger(columns))
         Rf_error("U must be a raw vector, mmatrix double, idx/columns integer");
-    const int dt = Rf_asInteger(dtype);
+    const int dt = count_arg(dtype, "dtype");
+    if (dt != RMG_STORED_U16 && dt != RMG_STORED_F32) Rf_error("dtype must be 1 (uint16) or 2 (float32)");
     const size_t es = dt == RMG_STORED_U16 ? 2 : 4;
     const R_xlen_t V = (R_xlen_t)Rf_asReal(nvoxels);
     const int n = Rf_nrows(mmatrix), p = Rf_ncols(mmatrix), R = Rf_ncols(idx), nc = LENGTH(columns);
-    if ((R_xlen_t)(XLENGTH(U) / es) != V * n) Rf_error("U holds %.0f samples, expected %.0f", (double)(XLENGTH(U) / es), (double)V * n);
+    if (V < 0 || (R_xlen_t)(XLENGTH(U) / es) != V * n) Rf_error("U holds %.0f samples, expected %.0f", (double)(XLENGTH(U) / es), (double)V * n);
     if (Rf_nrows(idx) != n) Rf_error("idx must have one row per subject");
     const int scaled = dt == RMG_STORED_U16;
-    if (scaled && (!Rf_isReal(scale) || !Rf_isReal(offset) || Rf_ncols(scale) != n || Rf_ncols(offset) != n))
-        Rf_error("scale and offset must be nslices x n double matrices");
+    const int64_t sl = stored_slice_len(dt, scale, offset, n, V, slice_len);
     const double *m = mask_or_null(mask, V);
-    int *idx0 = (int *)R_alloc((size_t)n * R, sizeof(int));
-    int *col0 = (int *)R_alloc((size_t)nc, sizeof(int));
-    for (R_xlen_t i = 0; i < (R_xlen_t)n * R; ++i) idx0[i] = INTEGER(idx)[i] - 1;
-    for (int i = 0; i < nc; ++i) col0[i] = INTEGER(columns)[i] - 1;
+    int *idx0 = zero_based(idx, (R_xlen_t)n * R, "idx");
+    int *col0 = zero_based(columns, nc, "columns");
     SEXP out = PROTECT(Rf_allocMatrix(REALSXP, R, nc));
     char err[512] = "";
-    const int G = Rf_asInteger(ngpu);
+    const int G = count_arg(ngpu, "ngpu");
     const double *sc = scaled ? REAL(scale) : NULL, *of = scaled ? REAL(offset) : NULL;
     int rc = G > 1 ? rmg_randomize_stored_multi(RAW(U), dt, V, V > 0 ? V : 1, n, sc, of, Rf_asReal(voxel_min),
-                                                (int64_t)Rf_asReal(slice_len), REAL(mmatrix), p, m, Rf_asReal(mask_lower),
-                                                Rf_asReal(mask_upper), idx0, R, col0, nc, Rf_asLogical(two_sided), REAL(out),
+                                                sl, REAL(mmatrix), p, m, Rf_asReal(mask_lower),
+                                                Rf_asReal(mask_upper), idx0, R, col0, nc, flag_arg(two_sided, "two_sided"), REAL(out),
                                                 G, err, sizeof err)
                    : rmg_randomize_stored(RAW(U), dt, V, V > 0 ? V : 1, n, sc, of, Rf_asReal(voxel_min),
-                                          (int64_t)Rf_asReal(slice_len), REAL(mmatrix), p, m, Rf_asReal(mask_lower),
-                                          Rf_asReal(mask_upper), idx0, R, col0, nc, Rf_asLogical(two_sided), REAL(out), 0,
-                                          err, sizeof err);
+                                          sl, REAL(mmatrix), p, m, Rf_asReal(mask_lower),
+                                          Rf_asReal(mask_upper), idx0, R, col0, nc, flag_arg(two_sided, "two_sided"), REAL(out),
+                                          gpu_device(), err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
     return out;
@@ -237,10 +298,10 @@ SEXP rmincgpu_anova(SEXP Y, SEXP mmatrix, SEXP asgn, SEXP mask, SEXP mask_lower,
     int nterms = 0;
     for (int i = 0; i < p; ++i) if (INTEGER(asgn)[i] > nterms) nterms = INTEGER(asgn)[i];
     const double *m = mask_or_null(mask, V);
-    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)V, nterms));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, matrix_rows(V), nterms));
     char err[512] = "";
     int rc = rmg_anova_fit(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, INTEGER(asgn), m, Rf_asReal(mask_lower),
-                           Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, 0, err, sizeof err);
+                           Rf_asReal(mask_upper), REAL(out), V > 0 ? V : 1, gpu_device(), err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
     return out;
@@ -257,7 +318,7 @@ SEXP rmincgpu_fdr(SEXP stat, SEXP stat_type, SEXP df, SEXP mask)
     SEXP th = PROTECT(Rf_allocVector(REALSXP, 5));
     char err[512] = "";
     int rc = rmg_fdr(REAL(stat), V, Rf_asInteger(stat_type), REAL(df)[0], LENGTH(df) > 1 ? REAL(df)[1] : 0.0, m, REAL(q),
-                     REAL(th), 0, err, sizeof err);
+                     REAL(th), gpu_device(), err, sizeof err);
     if (rc != RMG_OK) {
         UNPROTECT(2);
         check(rc, err);
@@ -297,10 +358,10 @@ SEXP rmincgpu_graph_tfce(SEXP map, SEXP adjacencies, SEXP E, SEXP H, SEXP nsteps
     if (XLENGTH(adjacencies) != V) Rf_error("Mismatch between adjacency list and data");
     int *ptr, *idx;
     adjacency_to_csr(adjacencies, &ptr, &idx);
-    SEXP out = PROTECT(ismat ? Rf_allocMatrix(REALSXP, (int)V, nmaps) : Rf_allocVector(REALSXP, V));
+    SEXP out = PROTECT(ismat ? Rf_allocMatrix(REALSXP, matrix_rows(V), nmaps) : Rf_allocVector(REALSXP, V));
     char err[512] = "";
     int rc = rmg_graph_tfce(REAL(map), V, nmaps, ptr, idx, XLENGTH(weights) == V ? REAL(weights) : NULL, Rf_asReal(E),
-                            Rf_asReal(H), Rf_asInteger(nsteps), Rf_asInteger(side), REAL(out), 0, err, sizeof err);
+                            Rf_asReal(H), Rf_asInteger(nsteps), Rf_asInteger(side), REAL(out), gpu_device(), err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
     return out;
@@ -315,17 +376,15 @@ SEXP rmincgpu_randomize_tfce(SEXP Y, SEXP mmatrix, SEXP idx, SEXP columns, SEXP 
     const R_xlen_t V = Rf_nrows(Y);
     const int n = Rf_ncols(Y), p = Rf_ncols(mmatrix), R = Rf_ncols(idx), nc = LENGTH(columns);
     if (Rf_nrows(idx) != n || XLENGTH(adjacencies) != V) Rf_error("idx / adjacency list do not match the data");
-    int *idx0 = (int *)R_alloc((size_t)n * R, sizeof(int));
-    int *col0 = (int *)R_alloc((size_t)nc, sizeof(int));
-    for (R_xlen_t i = 0; i < (R_xlen_t)n * R; ++i) idx0[i] = INTEGER(idx)[i] - 1;
-    for (int i = 0; i < nc; ++i) col0[i] = INTEGER(columns)[i] - 1;
+    int *idx0 = zero_based(idx, (R_xlen_t)n * R, "idx");
+    int *col0 = zero_based(columns, nc, "columns");
     int *ptr, *aidx;
     adjacency_to_csr(adjacencies, &ptr, &aidx);
     SEXP out = PROTECT(Rf_allocMatrix(REALSXP, R, nc));
     char err[512] = "";
-    int rc = rmg_randomize_tfce(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, idx0, R, col0, nc, Rf_asLogical(two_sided), ptr,
+    int rc = rmg_randomize_tfce(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, idx0, R, col0, nc, flag_arg(two_sided, "two_sided"), ptr,
                                 aidx, Rf_isReal(weights) && XLENGTH(weights) == V ? REAL(weights) : NULL, Rf_asReal(E),
-                                Rf_asReal(H), Rf_asInteger(nsteps), Rf_asInteger(side), REAL(out), 0, err, sizeof err);
+                                Rf_asReal(H), Rf_asInteger(nsteps), Rf_asInteger(side), REAL(out), gpu_device(), err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
     return out;
@@ -344,10 +403,10 @@ SEXP rmincgpu_volume_tfce(SEXP map, SEXP sizes, SEXP connectivity, SEXP voxel_vo
     int64_t dims[3];
     for (int i = 0; i < 3; ++i) dims[i] = (int64_t)(Rf_isReal(sizes) ? REAL(sizes)[i] : INTEGER(sizes)[i]);
     if (dims[0] * dims[1] * dims[2] != V) Rf_error("sizes do not match the data");
-    SEXP out = PROTECT(ismat ? Rf_allocMatrix(REALSXP, (int)V, nmaps) : Rf_allocVector(REALSXP, V));
+    SEXP out = PROTECT(ismat ? Rf_allocMatrix(REALSXP, matrix_rows(V), nmaps) : Rf_allocVector(REALSXP, V));
     char err[512] = "";
     int rc = rmg_volume_tfce(REAL(map), dims, nmaps, Rf_asInteger(connectivity), Rf_asReal(voxel_volume), Rf_asReal(d),
-                             Rf_asReal(E), Rf_asReal(H), Rf_asInteger(side), REAL(out), 0, err, sizeof err);
+                             Rf_asReal(E), Rf_asReal(H), Rf_asInteger(side), REAL(out), gpu_device(), err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
     return out;
@@ -367,18 +426,143 @@ SEXP rmincgpu_randomize_volume_tfce(SEXP Y, SEXP mmatrix, SEXP mask, SEXP mask_l
     const double *m = mask_or_null(mask, V);
     int64_t dims[3];
     for (int i = 0; i < 3; ++i) dims[i] = (int64_t)(Rf_isReal(sizes) ? REAL(sizes)[i] : INTEGER(sizes)[i]);
-    int *idx0 = (int *)R_alloc((size_t)n * R, sizeof(int));
-    int *col0 = (int *)R_alloc((size_t)nc, sizeof(int));
-    for (R_xlen_t i = 0; i < (R_xlen_t)n * R; ++i) idx0[i] = INTEGER(idx)[i] - 1;
-    for (int i = 0; i < nc; ++i) col0[i] = INTEGER(columns)[i] - 1;
+    int *idx0 = zero_based(idx, (R_xlen_t)n * R, "idx");
+    int *col0 = zero_based(columns, nc, "columns");
     SEXP out = PROTECT(Rf_allocMatrix(REALSXP, R, nc));
     char err[512] = "";
     int rc = rmg_randomize_volume_tfce(REAL(Y), V, V > 0 ? V : 1, n, REAL(mmatrix), p, m, Rf_asReal(mask_lower),
-                                       Rf_asReal(mask_upper), idx0, R, col0, nc, Rf_asLogical(two_sided), dims,
+                                       Rf_asReal(mask_upper), idx0, R, col0, nc, flag_arg(two_sided, "two_sided"), dims,
                                        Rf_asInteger(connectivity), Rf_asReal(voxel_volume), Rf_asReal(d), Rf_asReal(E),
-                                       Rf_asReal(H), Rf_asInteger(side), REAL(out), Rf_asInteger(ngpu), err, sizeof err);
+                                       Rf_asReal(H), Rf_asInteger(side), REAL(out), count_arg(ngpu, "ngpu"), err, sizeof err);
     UNPROTECT(1);
     check(rc, err);
+    return out;
+}
+
+/* ---- the resident dataset: Y is uploaded once (sharded over ngpu devices) and stays in HBM behind an external pointer;
+ *      mincLm, mincAnova, mincRandomize and mincFDR then run on the resident shards (rmg_dataset_*).  The pointer's
+ *      finalizer frees the device memory when R collects the handle; rmincgpu_dataset_free does it at once. */
+static void dataset_finalizer(SEXP h)
+{
+    rmg_dataset *ds = (rmg_dataset *)R_ExternalPtrAddr(h);
+    if (ds) rmg_dataset_free(ds);
+    R_ClearExternalPtr(h);
+}
+
+static rmg_dataset *dataset_of(SEXP h)
+{
+    if (TYPEOF(h) != EXTPTRSXP) Rf_error("not a GPU dataset handle");
+    rmg_dataset *ds = (rmg_dataset *)R_ExternalPtrAddr(h);
+    if (!ds) Rf_error("the GPU dataset has been freed");
+    return ds;
+}
+
+SEXP rmincgpu_dataset_create(SEXP Y, SEXP mask, SEXP mask_lower, SEXP mask_upper, SEXP ngpu)
+{
+    if (!Rf_isReal(Y) || !Rf_isMatrix(Y)) Rf_error("Y must be a double matrix (voxels x subjects)");
+    const R_xlen_t V = Rf_nrows(Y);
+    const int n = Rf_ncols(Y);
+    const double *m = mask_or_null(mask, V);
+    rmg_dataset *ds = NULL;
+    char err[512] = "";
+    int rc = rmg_dataset_create(REAL(Y), V, V > 0 ? V : 1, n, m, Rf_asReal(mask_lower), Rf_asReal(mask_upper),
+                                count_arg(ngpu, "ngpu"), &ds, err, sizeof err);
+    /* Y lives on R's heap, which the collector may move or free after this call returns: wait for the upload */
+    if (rc == RMG_OK) rc = rmg_dataset_sync(ds, err, sizeof err);
+    if (rc != RMG_OK) {
+        if (ds) rmg_dataset_free(ds);
+        check(rc, err);
+    }
+    SEXP h = PROTECT(R_MakeExternalPtr(ds, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(h, dataset_finalizer, TRUE);
+    UNPROTECT(1);
+    return h;
+}
+
+SEXP rmincgpu_dataset_free(SEXP h)
+{
+    if (TYPEOF(h) != EXTPTRSXP) Rf_error("not a GPU dataset handle");
+    dataset_finalizer(h);
+    return R_NilValue;
+}
+
+SEXP rmincgpu_dataset_lm(SEXP h, SEXP mmatrix)
+{
+    rmg_dataset *ds = dataset_of(h);
+    if (!Rf_isReal(mmatrix)) Rf_error("mmatrix must be a double matrix");
+    const R_xlen_t V = (R_xlen_t)rmg_dataset_voxels(ds);
+    const int n = rmg_dataset_subjects(ds), p = Rf_ncols(mmatrix);
+    if (Rf_nrows(mmatrix) != n) Rf_error("model matrix has %d rows, data has %d subjects", Rf_nrows(mmatrix), n);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, matrix_rows(V), 2 * p + 3));
+    char err[512] = "";
+    int rc = rmg_dataset_lm_fit(ds, REAL(mmatrix), p, REAL(out), V > 0 ? V : 1, err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
+SEXP rmincgpu_dataset_anova(SEXP h, SEXP mmatrix, SEXP asgn)
+{
+    rmg_dataset *ds = dataset_of(h);
+    if (!Rf_isReal(mmatrix) || !Rf_isInteger(asgn)) Rf_error("mmatrix must be double, asgn integer");
+    const R_xlen_t V = (R_xlen_t)rmg_dataset_voxels(ds);
+    const int n = rmg_dataset_subjects(ds), p = Rf_ncols(mmatrix);
+    if (Rf_nrows(mmatrix) != n || LENGTH(asgn) != p) Rf_error("model matrix / assign do not match the data");
+    int nterms = 0;
+    for (int i = 0; i < p; ++i) if (INTEGER(asgn)[i] > nterms) nterms = INTEGER(asgn)[i];
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, matrix_rows(V), nterms));
+    char err[512] = "";
+    int rc = rmg_dataset_anova(ds, REAL(mmatrix), p, INTEGER(asgn), REAL(out), V > 0 ? V : 1, err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
+SEXP rmincgpu_dataset_randomize(SEXP h, SEXP mmatrix, SEXP idx, SEXP columns, SEXP two_sided)
+{
+    rmg_dataset *ds = dataset_of(h);
+    if (!Rf_isReal(mmatrix) || !Rf_isInteger(idx) || !Rf_isInteger(columns)) Rf_error("mmatrix must be double, idx/columns integer");
+    const int n = rmg_dataset_subjects(ds), p = Rf_ncols(mmatrix), R = Rf_ncols(idx), nc = LENGTH(columns);
+    if (Rf_nrows(mmatrix) != n || Rf_nrows(idx) != n) Rf_error("model matrix / idx must have one row per subject");
+    int *idx0 = zero_based(idx, (R_xlen_t)n * R, "idx");
+    int *col0 = zero_based(columns, nc, "columns");
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, R, nc));
+    char err[512] = "";
+    int rc = rmg_dataset_randomize(ds, REAL(mmatrix), p, idx0, R, col0, nc, flag_arg(two_sided, "two_sided"), REAL(out), err,
+                                   sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
+/* mincFDR's step for column `column` (1-based) of the result of the last fit on the handle */
+SEXP rmincgpu_dataset_fdr(SEXP h, SEXP column, SEXP stat_type, SEXP df)
+{
+    rmg_dataset *ds = dataset_of(h);
+    if (!Rf_isReal(df) || LENGTH(df) < 1) Rf_error("df must be a double vector");
+    const R_xlen_t V = (R_xlen_t)rmg_dataset_voxels(ds);
+    SEXP q = PROTECT(Rf_allocVector(REALSXP, V));
+    SEXP th = PROTECT(Rf_allocVector(REALSXP, 5));
+    char err[512] = "";
+    int rc = rmg_dataset_fdr(ds, count_arg(column, "column") - 1, count_arg(stat_type, "stat_type"), REAL(df)[0],
+                             LENGTH(df) > 1 ? REAL(df)[1] : 0.0, REAL(q), REAL(th), err, sizeof err);
+    if (rc != RMG_OK) {
+        UNPROTECT(2);
+        check(rc, err);
+    }
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, q);
+    SET_VECTOR_ELT(out, 1, th);
+    UNPROTECT(3);
+    return out;
+}
+
+/* kernel launches issued by the library since it was loaded: lets a test assert that a call really ran on the GPU */
+SEXP rmincgpu_launch_count(void)
+{
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, 1));
+    REAL(out)[0] = (double)rmg_launch_count();
+    UNPROTECT(1);
     return out;
 }
 
@@ -396,6 +580,13 @@ static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_randomize_tfce", (DL_FUNC)&rmincgpu_randomize_tfce, 11},
     {"rmincgpu_volume_tfce", (DL_FUNC)&rmincgpu_volume_tfce, 8},
     {"rmincgpu_randomize_volume_tfce", (DL_FUNC)&rmincgpu_randomize_volume_tfce, 16},
+    {"rmincgpu_dataset_create", (DL_FUNC)&rmincgpu_dataset_create, 5},
+    {"rmincgpu_dataset_free", (DL_FUNC)&rmincgpu_dataset_free, 1},
+    {"rmincgpu_dataset_lm", (DL_FUNC)&rmincgpu_dataset_lm, 2},
+    {"rmincgpu_dataset_anova", (DL_FUNC)&rmincgpu_dataset_anova, 3},
+    {"rmincgpu_dataset_randomize", (DL_FUNC)&rmincgpu_dataset_randomize, 5},
+    {"rmincgpu_dataset_fdr", (DL_FUNC)&rmincgpu_dataset_fdr, 4},
+    {"rmincgpu_launch_count", (DL_FUNC)&rmincgpu_launch_count, 0},
     {NULL, NULL, 0}};
 
 void R_init_rmincgpu(DllInfo *dll)
