@@ -16,18 +16,16 @@ constexpr int NT = kPermNT, PITCH = kPermPitch;
 
 constexpr int WARPS_N = 2, WN = 4;  // warp tile: WM m8-tiles x 4 n8-tiles (32 voxels)
 
-// Ring depth: as many stages as fit (at most 6).  The two consumer warps that share an SM sub-partition run skewed by
-// about three stages (see the kernel), so that one of them always has MMAs to issue while the other is in its
-// statistics epilogue; the ring has to cover that skew plus the producer's lead.
+// Ring depth: as many stages as fit, at most 4.  (Tried in round 2: a 6-stage ring with the two warps of an SM
+// sub-partition skewed by three stages, so that one could issue MMAs during the other's epilogue -- tensor pipe 85.9 %
+// against 87.4 % in lockstep: the slower warp frees the stages, so the skew eats the producer's lead.)
 constexpr int stages_for(int wm, int warps_m, int kc)
 {
     const int stage_bytes = (warps_m * (kc / 4) * wm * 32 + kc * kPermPitch) * 8;
     const int budget = (warps_m == 4 ? 224 : 110) * 1024 - 2 * 8 * 8 - warps_m * WARPS_N * 3 * 32 * 8;
     const int s = budget / stage_bytes;
-    return s > 6 ? 6 : s < 2 ? 2 : s;
+    return s > 4 ? 4 : s < 2 ? 2 : s;
 }
-// Consumer warps along M and CTAs per SM come in two shapes: 4 x 2 warps, one CTA per SM (default),
-// or 2 x 2 warps, two CTAs per SM (RMG_PERM_CTAS=2; same throughput, more L2/DRAM traffic).
 
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
 {
@@ -335,12 +333,6 @@ perm_gemm_kernel(PermKernelParams P)
         pf_ys = (ok && INV) ? P.ys[v] : 0.0;
     };
     prefetch(blockIdx.x);
-    // Skew: warps w and w + 4 share an SM sub-partition and its DMMA pipe.  Holding the second one back by about three
-    // stages once, at the start, lets each run its epilogue while the other still issues MMAs; the skew then persists
-    // (whoever is alone on the pipe runs twice as fast, for exactly as long as the other's epilogue takes).
-    if (WARPS_M == 4 && warp >= CONSUMER_WARPS / 2 && STAGES >= 5) {
-        for (int i = 0; i < 3; ++i) __nanosleep(800);
-    }
 
     for (int64_t vt = blockIdx.x; vt < n_vt; vt += gridDim.x) {
         const int64_t vbase = vt * NT + warp_n * 32 + 2 * q;  // + nt*8 + h
