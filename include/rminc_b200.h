@@ -206,6 +206,39 @@ int rmg_fdr(const double *stat, int64_t V, int stat_type, double df1, double df2
  * thresholds are host values). */
 int rmg_fdr_device(const double *dstat, int64_t V, int stat_type, double df1, double df2, const double *dmask,
                    double *dq, double *thresholds, int device, void *stream, char *err, size_t errlen);
+/*
+ * The other q-value methods of mincFDR (R/minc_FDR.R:429-438).  Same arguments as rmg_fdr plus
+ *   method   RMG_FDR_BH      "FDR" / "p.adjust": p.adjust(p, "fdr")                                  (:432-434)
+ *            RMG_FDR_BY      "BY": p.adjust(p, "BY") = pmin(1, cummin(c n / i p)), c = sum(1 / (1:n))   (:435-437)
+ *            RMG_FDR_STOREY  "pFDR" / "fastqvalue": fast.qvalue (R/minc_misc.R:366-560): pi0 m p / #{p' <= p},
+ *                            then the reference's qvalue_min (src/modelling_functions.c:15-46) exactly as written: a
+ *                            minimum with the NEXT-ranked raw value (not a running minimum); the largest p keeps its
+ *                            raw value unless the raw value of the element after it in the masked vector exceeds 1
+ *                            (the reference's 1-based index used 0-based), then it becomes 1
+ *            RMG_FDR_QVALUE  "qvalue": qvalue::qvalue (third party, Suggests: of the reference's DESCRIPTION; its
+ *                            published form since 2.0): pi0 pmin(1, cummin(m / i p))
+ *   pi0      for _STOREY / _QVALUE: the estimated proportion of true nulls, in (0, 1] (else RMG_ERR_INVALID with the
+ *            reference's message).  Its default estimator is stats::smooth.spline (R, third party) over
+ *            mean(p >= lambda) / (1 - lambda); rmg_fdr_pi0_fractions supplies the means, the caller smooths.
+ * _STOREY and _QVALUE fail with RMG_ERR_INVALID when a selected voxel has a NaN statistic (the reference's
+ * `if (min(p) < 0 || max(p) > 1)` is R's "missing value where TRUE/FALSE needed").  At most 2^31 - 1 voxels per call.
+ */
+#define RMG_FDR_BH 0
+#define RMG_FDR_BY 1
+#define RMG_FDR_STOREY 2
+#define RMG_FDR_QVALUE 3
+int rmg_fdr_method(const double *stat, int64_t V, int stat_type, double df1, double df2, const double *mask,
+                   double *qvalues, double *thresholds, int method, double pi0, int device, char *err, size_t errlen);
+int rmg_fdr_method_device(const double *dstat, int64_t V, int stat_type, double df1, double df2, const double *dmask,
+                          double *dq, double *thresholds, int method, double pi0, int device, void *stream, char *err,
+                          size_t errlen);
+/* fractions[i] = mean(p >= lambda[i]) over the participating voxels, 1 <= nlambda <= 64, lambda in [0, 1)
+ * (R/minc_misc.R:439-441); lambda and fractions are host arrays in both forms. */
+int rmg_fdr_pi0_fractions(const double *stat, int64_t V, int stat_type, double df1, double df2, const double *mask,
+                          const double *lambda, int nlambda, double *fractions, int device, char *err, size_t errlen);
+int rmg_fdr_pi0_fractions_device(const double *dstat, int64_t V, int stat_type, double df1, double df2,
+                                 const double *dmask, const double *lambda, int nlambda, double *fractions, int device,
+                                 void *stream, char *err, size_t errlen);
 /* p-value of one statistic, evaluated on the host by the same code the device runs. */
 double rmg_pvalue(double stat, int stat_type, double df1, double df2);
 

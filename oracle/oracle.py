@@ -359,10 +359,84 @@ def p_adjust_bh(p):
     return q
 
 
-def fdr(stat, stat_type, df1, df2=None, mask=None):
+def p_adjust_by(p):
+    """R's p.adjust(p, "BY"): q <- sum(1 / (1L:n)); pmin(1, cummin(q * n / i * p[o]))[ro].  R's sum() accumulates in long
+    double and rounds once."""
+    p = np.asarray(p, dtype=np.float64)
+    q = np.full(p.shape, np.nan)
+    ok = ~np.isnan(p)
+    pp = p[ok]
+    n = pp.size
+    if n == 0:
+        return q
+    c = float(np.sum(1.0 / np.arange(1, n + 1, dtype=np.float64), dtype=np.longdouble))
+    o = np.argsort(-pp, kind="stable")
+    i = np.arange(n, 0, -1)
+    adj = np.minimum(1.0, np.minimum.accumulate(c * n / i * pp[o]))
+    out = np.empty(n)
+    out[o] = adj
+    q[ok] = out
+    return q
+
+
+def qvalue_min(qvalue, u, use_ref=False):
+    """The reference's qvalue_min (src/modelling_functions.c:15-46), restated with its indices as written: u is R's
+    1-based order(p).  The last-ranked element is tested through qvalue[u[m-1]] (1-based index used 0-based = the element
+    AFTER it in the vector; one past the end when it is the last element: read as "not above 1" here, and the caller of
+    the object code below pads the vector with a 0 there); every other element takes the smaller of its own and the
+    next-ranked RAW value, or 1 when both exceed 1."""
+    qv = np.ascontiguousarray(qvalue, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.int32)
+    m = qv.shape[0]
+    out = np.zeros(m)
+    if use_ref:
+        padded = np.concatenate([qv, [0.0]])
+        length = np.array([m], dtype=np.int32)
+        ref().qvalue_min(padded.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p), length.ctypes.data_as(C.c_void_p),
+                         out.ctypes.data_as(C.c_void_p))
+        return out
+    last = m - 1
+    probe = qv[u[last]] if u[last] < m else 0.0
+    out[u[last] - 1] = 1.0 if probe > 1 else qv[u[last] - 1]
+    for i in range(last - 1, -1, -1):
+        a, b = qv[u[i] - 1], qv[u[i + 1] - 1]
+        out[u[i] - 1] = 1.0 if (a > 1 and b > 1) else (a if a < b else b)
+    return out
+
+
+def fast_qvalue(p, pi0, use_ref=False):
+    """fast.qvalue's q-values for a given pi0 (R/minc_misc.R:503-531): v = qvalue.rank(p) = number of p' <= p,
+    qvalue = pi0 * m * p / v, then qvalue_min over u = order(p)."""
+    p = np.asarray(p, dtype=np.float64)
+    m = p.shape[0]
+    u = np.argsort(p, kind="stable") + 1
+    v = np.searchsorted(np.sort(p), p, side="right")
+    return qvalue_min(pi0 * m * p / v, u, use_ref=use_ref)
+
+
+def pi0_fractions(p, lambdas):
+    """mean(p >= lambda[i]) (R/minc_misc.R:439-441)."""
+    p = np.asarray(p, dtype=np.float64)
+    return np.array([np.mean(p >= l) for l in lambdas])
+
+
+def qvalue_package(p, pi0):
+    """qvalue::qvalue's q-values for a given pi0 (third party; its published form since 2.0):
+    i <- m:1; o <- order(p, decreasing = TRUE); ro <- order(o); pi0 * pmin(1, cummin(p[o] * m / i))[ro]."""
+    p = np.asarray(p, dtype=np.float64)
+    m = p.shape[0]
+    o = np.argsort(-p, kind="stable")
+    i = np.arange(m, 0, -1)
+    out = np.empty(m)
+    out[o] = pi0 * np.minimum(1.0, np.minimum.accumulate(p[o] * m / i))
+    return out
+
+
+def fdr(stat, stat_type, df1, df2=None, mask=None, method="FDR", pi0=1.0):
     """mincFDR.mincMultiDim for one column (R/minc_FDR.R:385-505): p-values (pt2 = 2 pt(-|t|, df) for "t",
-    pf(F, df1, df2, lower.tail = FALSE) for "F"; scipy's t / f distributions stand in for R's nmath), BH q-values
-    over mask > 0.5, output 1 outside the mask, thresholds qt(max p / 2, df, lower = FALSE) / qf(max p, ...)."""
+    pf(F, df1, df2, lower.tail = FALSE) for "F"; scipy's t / f distributions stand in for R's nmath), q-values by
+    `method` over mask > 0.5 (:429-438), output 1 outside the mask, thresholds qt(max p / 2, df, lower = FALSE) /
+    qf(max p, ...) of the largest p among q <= level (:444-475)."""
     from scipy import stats as S
     s = np.asarray(stat, dtype=np.float64).reshape(-1)
     sel = np.ones(s.shape, bool) if mask is None else (np.asarray(mask).reshape(-1) > 0.5)
@@ -371,7 +445,16 @@ def fdr(stat, stat_type, df1, df2=None, mask=None):
     else:
         p = S.f.sf(s[sel], df1, df2)
     p = np.where(np.isnan(s[sel]), np.nan, p)
-    q = p_adjust_bh(p)
+    if method in ("FDR", "p.adjust"):
+        q = p_adjust_bh(p)
+    elif method == "BY":
+        q = p_adjust_by(p)
+    elif method in ("pFDR", "fastqvalue"):
+        q = fast_qvalue(p, pi0)
+    elif method == "qvalue":
+        q = qvalue_package(p, pi0)
+    else:
+        raise ValueError(method)
     out = np.ones(s.shape)
     out[sel] = q
     th = np.full(len(FDR_LEVELS), np.nan)

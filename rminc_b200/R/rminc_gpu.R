@@ -145,10 +145,21 @@ vertex_anova_loop_gpu <- function(data.matrix, mmatrix)
 
 # mincFDR's inner loop body on the GPU (R/minc_FDR.R:385-505): p-values, p.adjust(., "fdr") and the thresholds of one
 # column.  stat_type "t" / "F"; df as in attr(buffer, "df")[[column]]; mask a numeric vector or NULL.
-rmincgpu_fdr_column <- function(stat, stat_type, df, mask = NULL) {
-  res <- .Call("rmincgpu_fdr", as.double(stat), if (stat_type == "F") 2L else 1L, as.double(df),
-               if (is.null(mask)) NULL else as.double(mask), PACKAGE = "rmincgpu")
-  list(qvalue = res[[1]], thresholds = res[[2]])
+# method: mincFDR's (R/minc_FDR.R:429-438).  For "pFDR" / "fastqvalue" / "qvalue" pi0 is estimated as fast.qvalue does
+# (R/minc_misc.R:437-451): mean(p >= lambda) / (1 - lambda) from the device, smooth.spline(df = 3) here.
+rmincgpu_fdr_column <- function(stat, stat_type, df, mask = NULL, method = "FDR") {
+  code <- c(FDR = 0L, p.adjust = 0L, BY = 1L, pFDR = 2L, fastqvalue = 2L, qvalue = 3L)[[method]]
+  type <- if (stat_type == "F") 2L else 1L
+  m <- if (is.null(mask)) NULL else as.double(mask)
+  pi0 <- 1
+  if (code >= 2L) {
+    lambda <- if (code == 2L) seq(0, 0.9, 0.05) else seq(0.05, 0.95, 0.05)
+    frac <- .Call("rmincgpu_fdr_pi0", as.double(stat), type, as.double(df), m, as.double(lambda), PACKAGE = "rmincgpu")
+    spi0 <- smooth.spline(lambda, frac / (1 - lambda), df = 3)
+    pi0 <- min(predict(spi0, x = max(lambda))$y, 1)
+  }
+  res <- .Call("rmincgpu_fdr_method", as.double(stat), type, as.double(df), m, code, as.double(pi0), PACKAGE = "rmincgpu")
+  list(qvalue = res[[1]], thresholds = res[[2]], pi0 = pi0)
 }
 
 

@@ -45,6 +45,14 @@ SIGNATURES = {
     "rmg_fdr": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + _ERR),
     "rmg_fdr_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int, C.c_void_p] + _ERR),
+    "rmg_fdr_method": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_double, C.c_int] + _ERR),
+    "rmg_fdr_method_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_double, C.c_int, C.c_void_p] + _ERR),
+    "rmg_fdr_pi0_fractions": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_int] + _ERR),
+    "rmg_fdr_pi0_fractions_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                               C.c_int, C.c_void_p, C.c_int, C.c_void_p] + _ERR),
     "rmg_pvalue": (C.c_double, [C.c_double, C.c_int, C.c_double, C.c_double]),
     "rmg_lm_fit_cov_multi": (C.c_int, [C.c_void_p] + _FIT_HEAD + _MASK + [C.c_void_p, C.c_int64, C.c_int] + _ERR),
     "rmg_lm_fit_stored_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_double,

@@ -468,17 +468,68 @@ def anatAnova(formula: str, data, anat, subset=None, device: int = 0) -> MincMat
 
 
 # ----------------------------------------------------------------------------- mincFDR
+def smooth_spline_at_last_knot(x, y, df: float = 3.0) -> float:
+    """predict(smooth.spline(x, y, df = df), x = max(x))$y for distinct knots x (all of them are knots when there are
+    fewer than 50, R's rule): the natural cubic smoothing spline g minimising sum (y - g(x))^2 + lam * int g''^2 with lam
+    chosen so that the trace of the smoother matrix equals `df`.  stats::smooth.spline is R's (third party, not in the
+    reference tree); this is the textbook Reinsch form (Green & Silverman 1994, section 2.3).  R matches `df` only to the
+    tolerance of its spar search (control.spar tol 1e-4), so agreement with R is to ~1e-4, not to the bit."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n = x.shape[0]
+    if n < 4 or np.any(np.diff(x) <= 0):
+        raise ValueError("smooth.spline needs at least four increasing, distinct x values")
+    if not 1.0 < df <= n:
+        raise ValueError("you must supply 1 < df <= n")
+    h = np.diff(x)
+    Q = np.zeros((n, n - 2))
+    Rm = np.zeros((n - 2, n - 2))
+    for i in range(n - 2):
+        Q[i, i] = 1.0 / h[i]
+        Q[i + 1, i] = -1.0 / h[i] - 1.0 / h[i + 1]
+        Q[i + 2, i] = 1.0 / h[i + 1]
+        Rm[i, i] = (h[i] + h[i + 1]) / 3.0
+        if i + 1 < n - 2:
+            Rm[i, i + 1] = Rm[i + 1, i] = h[i + 1] / 6.0
+    K = Q @ np.linalg.solve(Rm, Q.T)
+    d, U = np.linalg.eigh(0.5 * (K + K.T))
+    d = np.maximum(d, 0.0)                      # two exact zeros: constants and lines are not penalised
+    lo, hi = -60.0, 60.0                        # bisection on log(lam): trace falls from n to 2
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        if np.sum(1.0 / (1.0 + np.exp(mid) * d)) > df:
+            lo = mid
+        else:
+            hi = mid
+    lam = np.exp(0.5 * (lo + hi))
+    g = U @ ((U.T @ y) / (1.0 + lam * d))
+    return float(g[-1])
+
+
+def _estimate_pi0(stat, stat_type, df1, df2, mask, method, device):
+    """pi0 of fast.qvalue (lambda = seq(0, 0.9, 0.05), pi0.method = "smoother", smooth.df = 3; R/minc_misc.R:367-374,
+    437-451) or of qvalue::pi0est (lambda = seq(0.05, 0.95, 0.05)): mean(p >= lambda) / (1 - lambda) on the GPU,
+    smoothed on the host, evaluated at max(lambda), capped at 1."""
+    lam = np.arange(0, 19) * 0.05 if method in ("pFDR", "fastqvalue") else np.arange(1, 20) * 0.05
+    frac = core.fdr_pi0_fractions(stat, stat_type, df1, df2, mask=mask, lambdas=lam, device=device)
+    pi0 = min(smooth_spline_at_last_knot(lam, frac / (1.0 - lam), 3.0), 1.0)
+    if pi0 <= 0:
+        raise ValueError("ERROR: The estimated pi0 <= 0. Check that you have valid p-values or use another lambda method.")
+    return pi0
+
+
 def mincFDR(buffer: MincMatrix, columns: Optional[Sequence[str]] = None, mask=None, df=None, method: str = "FDR",
             statType=None, reader: Callable = default_reader, device: int = 0) -> MincMatrix:
     """False discovery rate q-values of a mincLm / mincAnova / vertexLm / anatLm result
     (mincFDR.mincMultiDim, R/minc_FDR.R:254-520).
 
     The beta, R-squared and logLik columns are dropped (:267-292); every remaining t / F column is converted to
-    p-values (pt2 / pf) and Benjamini-Hochberg adjusted over the voxels with mask > 0.5 on the GPU.  Returns a
-    V x ncols matrix of class c("mincQvals","mincMultiDim","matrix") with colnames "qvalue-<column>", 1 outside the
-    mask, and attributes `thresholds` (5 x ncols, rows 0.01 .. 0.2), `likeVolume`, `DF`."""
-    if method not in ("FDR", "p.adjust"):
-        raise ValueError("only method = 'FDR' / 'p.adjust' (Benjamini-Hochberg) is on the GPU path")
+    p-values (pt2 / pf) and adjusted over the voxels with mask > 0.5 on the GPU: method "FDR" / "p.adjust"
+    (Benjamini-Hochberg), "BY", "pFDR" / "fastqvalue" (fast.qvalue, R/minc_misc.R:366-560) or "qvalue" (:429-438).
+    Returns a V x ncols matrix of class c("mincQvals","mincMultiDim","matrix") with colnames "qvalue-<column>", 1
+    outside the mask, and attributes `thresholds` (5 x ncols, rows 0.01 .. 0.2), `likeVolume`, `DF`."""
+    if method not in core.FDR_METHODS:
+        raise ValueError(f"unknown method {method!r}: one of {sorted(core.FDR_METHODS)}")
     if not isinstance(buffer, MincMatrix):
         raise TypeError("buffer must be the result of mincLm / mincAnova / vertexLm / anatLm")
     stattype = list(statType) if statType is not None else buffer.attrs.get("stat-type")
@@ -515,10 +566,13 @@ def mincFDR(buffer: MincMatrix, columns: Optional[Sequence[str]] = None, mask=No
         d = dfl[c]
         new_dfs.append(d)
         if stattype[c] == "t":
-            d1 = float(d[0] if isinstance(d, (list, tuple, np.ndarray)) else d)
-            q, th = core.fdr(A[:, c], core.STAT_T, d1, 0.0, mask=m, device=device)
+            st, d1, d2 = core.STAT_T, float(d[0] if isinstance(d, (list, tuple, np.ndarray)) else d), 0.0
         else:
-            q, th = core.fdr(A[:, c], core.STAT_F, float(d[0]), float(d[1]), mask=m, device=device)
+            st, d1, d2 = core.STAT_F, float(d[0]), float(d[1])
+        pi0 = 1.0
+        if core.FDR_METHODS[method] >= 2:
+            pi0 = _estimate_pi0(A[:, c], st, d1, d2, m, method, device)
+        q, th = core.fdr(A[:, c], st, d1, d2, mask=m, device=device, method=method, pi0=pi0)
         out[:, i] = q
         thresholds[:, i] = th
     th = MincMatrix(thresholds, colnames=list(columns), rownames=[f"{x:g}" for x in core.FDR_LEVELS])

@@ -256,9 +256,10 @@ def pvalue(stat, stat_type, df1, df2=0.0) -> float:
     return _lib.load().rmg_pvalue(float(stat), int(stat_type), float(df1), float(df2))
 
 
-def fdr(stat, stat_type, df1, df2=0.0, mask=None, device=0):
-    """mincFDR's native step for one column: (q-values [V], thresholds [5]) -- Benjamini-Hochberg over the voxels
-    with mask > 0.5 (R/minc_FDR.R:254-520)."""
+FDR_METHODS = {"FDR": 0, "p.adjust": 0, "BY": 1, "pFDR": 2, "fastqvalue": 2, "qvalue": 3}   # R/minc_FDR.R:429-438
+
+
+def _fdr_inputs(stat, mask):
     s = np.ascontiguousarray(stat, dtype=np.float64).reshape(-1)
     V = s.shape[0]
     m = None
@@ -266,13 +267,38 @@ def fdr(stat, stat_type, df1, df2=0.0, mask=None, device=0):
         m = np.ascontiguousarray(mask, dtype=np.float64).reshape(-1)
         if m.shape[0] != V:
             raise ValueError("mask length must equal the number of voxels")
+    return s, m, V
+
+
+def fdr(stat, stat_type, df1, df2=0.0, mask=None, device=0, method="FDR", pi0=1.0):
+    """mincFDR's native step for one column: (q-values [V], thresholds [5]) over the voxels with mask > 0.5
+    (R/minc_FDR.R:254-520).  method: "FDR" / "p.adjust" (Benjamini-Hochberg), "BY", "pFDR" / "fastqvalue" (the
+    reference's fast.qvalue with its qvalue_min step as written) or "qvalue" (the qvalue package's published form);
+    the last two take the estimated pi0 (see fdr_pi0_fractions)."""
+    if method not in FDR_METHODS:
+        raise ValueError(f"unknown FDR method {method!r}")
+    s, m, V = _fdr_inputs(stat, mask)
     q = np.empty(V)
     th = np.empty(5)
     err = _lib.errbuf()
-    rc = _lib.load().rmg_fdr(s.ctypes.data, V, int(stat_type), float(df1), float(df2), m.ctypes.data if m is not None else None,
-                             q.ctypes.data, th.ctypes.data, device, err, len(err))
+    rc = _lib.load().rmg_fdr_method(s.ctypes.data, V, int(stat_type), float(df1), float(df2), m.ctypes.data if m is not None else None,
+                                    q.ctypes.data, th.ctypes.data, FDR_METHODS[method], float(pi0), device, err, len(err))
     _lib.check(rc, err)
     return q, th
+
+
+def fdr_pi0_fractions(stat, stat_type, df1, df2=0.0, mask=None, lambdas=None, device=0):
+    """mean(p >= lambda) for every lambda over the voxels with mask > 0.5: the grid fast.qvalue smooths into pi0
+    (R/minc_misc.R:439-441).  The p-values never leave the device."""
+    lam = np.ascontiguousarray(np.arange(0.0, 0.91, 0.05) if lambdas is None else lambdas, dtype=np.float64).reshape(-1)
+    s, m, V = _fdr_inputs(stat, mask)
+    out = np.empty(lam.shape[0])
+    err = _lib.errbuf()
+    rc = _lib.load().rmg_fdr_pi0_fractions(s.ctypes.data, V, int(stat_type), float(df1), float(df2),
+                                           m.ctypes.data if m is not None else None, lam.ctypes.data, lam.shape[0],
+                                           out.ctypes.data, device, err, len(err))
+    _lib.check(rc, err)
+    return out
 
 
 def fdr_torch(stat_t, stat_type, df1, df2=0.0, mask=None, out=None):

@@ -253,7 +253,7 @@ int randomize_shards(std::vector<PermShard> &S, int n, int p, const double *X, d
             RMG_CUDA(cudaEventRecord(e0[g], s.st));
         }
         if (gemm) {
-            RMG_CUDA(perm_pack_plan(pd, n, p, pk));
+            RMG_CUDA(perm_pack_plan(pd, n, p, cols, ncols, pk));
             planned = true;
             const int shift = pk.shift;
             std::vector<PermGemmArgs> ga(G);

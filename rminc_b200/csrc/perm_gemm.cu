@@ -19,10 +19,11 @@ constexpr int WARPS_N = 2, WN = 4;  // warp tile: WM m8-tiles x 4 n8-tiles (32 v
 // Ring depth: as many stages as fit, at most 4.  (Tried in round 2: a 6-stage ring with the two warps of an SM
 // sub-partition skewed by three stages, so that one could issue MMAs during the other's epilogue -- tensor pipe 85.9 %
 // against 87.4 % in lockstep: the slower warp frees the stages, so the skew eats the producer's lead.)
-constexpr int stages_for(int wm, int warps_m, int kc)
+constexpr int stages_for(int kp, int wm, int pg, int warps_m, int kc)
 {
     const int stage_bytes = (warps_m * (kc / 4) * wm * 32 + kc * kPermPitch) * 8;
-    const int budget = (warps_m == 4 ? 224 : 110) * 1024 - 2 * 8 * 8 - warps_m * WARPS_N * 3 * 32 * 8;
+    const int epi_bytes = warps_m * pg * 8 * (kp + 1 + kPermMaxCols * kp) * 8;     // worst case: every column requested
+    const int budget = (warps_m == 4 ? 226 : 112) * 1024 - 4 * 8 * 8 - warps_m * WARPS_N * 3 * 32 * 8 - epi_bytes;
     const int s = budget / stage_bytes;
     return s > 4 ? 4 : s < 2 ? 2 : s;
 }
@@ -271,9 +272,13 @@ perm_gemm_kernel(PermKernelParams P)
     double *sB = sA + (size_t)STAGES * A_CHUNK;
     uint64_t *full = reinterpret_cast<uint64_t *>(sB + (size_t)STAGES * B_CHUNK);
     uint64_t *empty = full + STAGES;
+    uint64_t *epi_full = empty + STAGES, *epi_empty = epi_full + 1;
     // per-voxel constants (|y'|^2, y0, sum y') of each warp's 32 voxels of the current voxel tile, staged by the warp
     // itself (no CTA-wide barrier: the warps of a CTA deliberately do not run in lockstep)
-    double *sv_all = reinterpret_cast<double *>(empty + STAGES);   // [CONSUMER_WARPS][3][32]
+    double *sv_all = reinterpret_cast<double *>(epi_empty + 1);    // [CONSUMER_WARPS][3][32]
+    // the epilogue's per-permutation constants of the current permutation tile (q1, c0, the requested rows of R^-1),
+    // bulk-copied by the producer while the tile's MMAs run: no global load is left in the epilogue
+    double *sE = sv_all + CONSUMER_WARPS * 96;                     // [PERMS_PER_CTA][epi_stride]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -281,6 +286,8 @@ perm_gemm_kernel(PermKernelParams P)
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], CONSUMER_WARPS);
         }
+        mbar_init(epi_full, 1);
+        mbar_init(epi_empty, CONSUMER_WARPS);
         fence_barrier_init();
     }
     __syncthreads();
@@ -291,13 +298,24 @@ perm_gemm_kernel(PermKernelParams P)
     if (warp == CONSUMER_WARPS) {
         // ===== producer
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, phase = 0, epi_phase = 0;
+            const uint32_t epi_bytes = (uint32_t)(PERMS_PER_CTA * P.epi_stride * 8);
+            // The constants of tile pt replace those of tile pt - 1 once every consumer warp has left that tile's
+            // epilogue (epi_empty).  Issued a few stages into the tile, so the wait never holds up the ring refill
+            // that runs during the epilogue.
+            const int kc_epi = min(STAGES, P.n_kc - 1);
             for (int64_t vt = blockIdx.x; vt < n_vt; vt += gridDim.x) {
                 const int64_t v0 = vt * NT;
                 const int cols_here = (int)min((int64_t)NT, P.V - v0);
                 const uint32_t row_bytes = (uint32_t)cols_here * 8u;
                 for (int pt = 0; pt < P.n_pt; ++pt) {
                     for (int kc = 0; kc < P.n_kc; ++kc) {
+                        if (kc == kc_epi) {
+                            mbar_wait(epi_empty, epi_phase ^ 1);
+                            mbar_expect_tx(epi_full, epi_bytes);
+                            bulk_load_1d(sE, P.epi + (size_t)pt * PERMS_PER_CTA * P.epi_stride, epi_bytes, epi_full);
+                            epi_phase ^= 1;
+                        }
                         const int j0 = kc * KC;
                         const int rows = min(KC, n - j0);
                         mbar_wait(&empty[stage], phase ^ 1);
@@ -319,8 +337,9 @@ perm_gemm_kernel(PermKernelParams P)
     // ===== consumers
     const int warp_m = warp / WARPS_N, warp_n = warp % WARPS_N;
     const int g = lane >> 2, q = lane & 3;
-    uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0, epi_phase = 0;
     const bool tail_guard = (n % KC) != 0;
+    const int estride = P.epi_stride;
 
     double *sv = sv_all + warp * 96;                          // [3][32]
     // this lane's voxel of the warp's 32: its per-voxel sums are fetched one voxel tile ahead
@@ -364,14 +383,15 @@ perm_gemm_kernel(PermKernelParams P)
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
 
-            if (P.debug_skip == 1) continue;
+            mbar_wait(epi_full, epi_phase);
+            epi_phase ^= 1;
             // ---- fused epilogue: this thread holds, for PG permutations, the KG GEMM components of
             //      e = Q_r'y for 8 voxels (nt = 0..3, h = 0..1).
 #pragma unroll
             for (int pg = 0; pg < PG; ++pg) {
                 const int r = pt * PERMS_PER_CTA + (warp_m * PG + pg) * 8 + g;
                 const bool rvalid = r < P.R;
-                const PermConst &pc = P.pc[rvalid ? r : 0];
+                const double *ep = sE + (size_t)((warp_m * PG + pg) * 8 + g) * estride;   // zeros for padding permutations
                 // w > 0: 1/rss of a regular fit; 0: the statistic counts as 0 (non-finite in the reference; for TWO also
                 // every pair without a contribution); < 0 (one-sided only): no contribution
                 double w[WN][2];
@@ -379,8 +399,8 @@ perm_gemm_kernel(PermKernelParams P)
                 {
                     double q1[KP];
 #pragma unroll
-                    for (int k = 0; k < KP; ++k) q1[k] = pc.q1[k];
-                    const double c0 = INV ? pc.c0 : 0.0;
+                    for (int k = 0; k < KP; ++k) q1[k] = ep[k];
+                    const double c0 = INV ? ep[KP] : 0.0;
 #pragma unroll
                     for (int nt = 0; nt < WN; ++nt) {
 #pragma unroll
@@ -412,10 +432,9 @@ perm_gemm_kernel(PermKernelParams P)
                 }
 #pragma unroll 1
                 for (int c = 0; c < P.ncols; ++c) {
-                    const int ci = P.tcol[c];
                     double rrow[KP];
 #pragma unroll
-                    for (int j = 0; j < KP; ++j) rrow[j] = pc.Rinv[ci * 8 + j];
+                    for (int j = 0; j < KP; ++j) rrow[j] = ep[KP + 1 + c * KP + j];
                     double best = TWO ? 0.0 : -INFINITY;
 #pragma unroll
                     for (int nt = 0; nt < WN; ++nt) {
@@ -440,6 +459,8 @@ perm_gemm_kernel(PermKernelParams P)
                     if (q == 0 && rvalid && best > -INFINITY) atomicMax(&P.keys[(size_t)c * P.Rstride + r], ordered_key(best));
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(epi_empty);     // this warp is done with the tile's constants
         }
     }
 }
@@ -450,8 +471,11 @@ cudaError_t launch_gemm_cfg(const PermKernelParams &P, int sm_count, cudaStream_
     constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
     constexpr int WM = (KP - INV) * PG;
     constexpr int A_CHUNK = WARPS_M * (KC / 4) * WM * 32;
-    const size_t smem = (size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + 2 * STAGES * 8 + CONSUMER_WARPS * 96 * 8;
-    static_assert((size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + 2 * STAGES * 8 + CONSUMER_WARPS * 96 * 8 <= 227 * 1024, "ring does not fit");
+    constexpr int PERMS_PER_CTA = WARPS_M * PG * 8;
+    const size_t smem = (size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + (2 * STAGES + 2) * 8 + CONSUMER_WARPS * 96 * 8 +
+                        (size_t)PERMS_PER_CTA * P.epi_stride * 8;
+    static_assert((size_t)STAGES * (A_CHUNK + KC * PITCH) * 8 + (2 * STAGES + 2) * 8 + CONSUMER_WARPS * 96 * 8 +
+                      (size_t)PERMS_PER_CTA * (KP + 1 + kPermMaxCols * KP) * 8 <= 227 * 1024, "ring does not fit");
     auto kern = perm_gemm_kernel<KP, PG, INV, KC, STAGES, TWO, WARPS_M>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -465,7 +489,7 @@ template <int KP, int PG, int INV>
 cudaError_t launch_gemm(const PermKernelParams &P, int sm_count, cudaStream_t st, int warps_m)
 {
     constexpr int WM = (KP - INV) * PG;
-    constexpr int S4 = stages_for(WM, 4, 16), S2 = stages_for(WM, 2, 16);
+    constexpr int S4 = stages_for(KP, WM, PG, 4, 16), S2 = stages_for(KP, WM, PG, 2, 16);
     if (P.two_sided)
         return warps_m == 4 ? launch_gemm_cfg<KP, PG, INV, 16, S4, true, 4>(P, sm_count, st)
                             : launch_gemm_cfg<KP, PG, INV, 16, S2, true, 2>(P, sm_count, st);
@@ -489,10 +513,13 @@ bool perm_gemm_supported(int n, int p, int64_t V, int64_t ldY, const double *dY,
 }
 
 // ---- host side: geometry + packing
-cudaError_t perm_pack_plan(const PermSet &ps, int n, int p, PermPack &pk)
+cudaError_t perm_pack_plan(const PermSet &ps, int n, int p, const int32_t *hcols, int ncols, PermPack &pk)
 {
     const int R = ps.R, KP = p;
     pk.R = R; pk.n = n; pk.p = p;
+    pk.ncols = ncols;
+    for (int c = 0; c < ncols && c < kPermMaxCols; ++c) pk.tcol[c] = hcols[c] - (p + 2);
+    pk.epi_stride = p + 1 + ncols * p;
     pk.shift = ps.all_intercept ? 1 : 0;
     // Is component 0 of every permuted design the same constant column (the intercept, first in
     // pivot order)?  Then e_0 = c0 * sum(y) is permutation-invariant and needs no tensor-core row.
@@ -534,11 +561,14 @@ cudaError_t perm_pack_plan(const PermSet &ps, int n, int p, PermPack &pk)
     pk.apack_doubles = (size_t)pk.n_pt * pk.n_kc * pk.A_CHUNK;
     // pinned staging (leased from the process-wide pool: the DMA engines of every device read it directly)
     const size_t bytesA = (pk.apack_doubles * 8 + 255) & ~size_t(255);
-    char *base = static_cast<char *>(pinned_acquire(bytesA + (size_t)std::max(R, 1) * sizeof(PermConst)));
+    const size_t bytesP = ((size_t)std::max(R, 1) * sizeof(PermConst) + 255) & ~size_t(255);
+    const size_t bytesE = (size_t)pk.n_pt * pk.perms_per_cta * pk.epi_stride * 8;
+    char *base = static_cast<char *>(pinned_acquire(bytesA + bytesP + bytesE));
     if (!base) return cudaErrorMemoryAllocation;
     pk.lease = base;
     pk.hA = reinterpret_cast<double *>(base);
     pk.hpc = reinterpret_cast<PermConst *>(base + bytesA);
+    pk.hE = reinterpret_cast<double *>(base + bytesA + bytesP);
     return cudaSuccess;
 }
 
@@ -548,6 +578,7 @@ void perm_pack_release(PermPack &pk)
     pk.lease = nullptr;
     pk.hA = nullptr;
     pk.hpc = nullptr;
+    pk.hE = nullptr;
 }
 
 void perm_pack_batch(const PermSet &ps, PermPack &pk, int b)
@@ -559,6 +590,8 @@ void perm_pack_batch(const PermSet &ps, PermPack &pk, int b)
     double *Apack = pk.hA;
     PermConst *pc = pk.hpc;
     std::memset(Apack + (size_t)pt0 * n_kc * A_CHUNK, 0, (size_t)(pt1 - pt0) * n_kc * A_CHUNK * sizeof(double));   // padding
+    const int es = pk.epi_stride;
+    std::memset(pk.hE + (size_t)pt0 * perms_per_cta * es, 0, (size_t)(pt1 - pt0) * perms_per_cta * es * sizeof(double));
     parallel_for(r1 - r0, [&](int i0, int i1) {
         for (int r = r0 + i0; r < r0 + i1; ++r) {
             const Design &D = ps.design(r);
@@ -573,6 +606,11 @@ void perm_pack_batch(const PermSet &ps, PermPack &pk, int b)
             }
             c.rdf = (double)(n - p);
             c.c0 = pk.c0[r];
+            double *e = pk.hE + (size_t)r * es;
+            for (int i = 0; i < p; ++i) e[i] = D.q1[i];
+            e[p] = pk.c0[r];
+            for (int cc = 0; cc < pk.ncols; ++cc)
+                for (int j = 0; j < p; ++j) e[p + 1 + cc * p + j] = D.Rinv[pk.tcol[cc] + (size_t)j * p];
             const int pt = r / perms_per_cta, rr = r % perms_per_cta;
             const int warp_m = rr / (PG * 8), pg = (rr / 8) % PG, g = rr % 8;
             for (int k = INV; k < D.k; ++k) {
@@ -603,6 +641,7 @@ cudaError_t perm_dev_begin(PermDevice &d, const PermPack &pk, int device, int sm
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
     const size_t oA = carve(pk.apack_doubles * 8), oP = carve((size_t)R * sizeof(PermConst)), oVf = carve((size_t)a.V);
+    const size_t oE = carve((size_t)pk.n_pt * pk.perms_per_cta * pk.epi_stride * 8);
     size_t oY0 = 0, oYY = 0, oYS = 0, oFlag = 0;
     if (d.own_pre) {
         oY0 = carve((size_t)a.V * 8); oYY = carve((size_t)a.V * 8); oYS = carve((size_t)a.V * 8); oFlag = carve(256);
@@ -634,8 +673,9 @@ cudaError_t perm_dev_begin(PermDevice &d, const PermPack &pk, int device, int sm
     P.vflag = reinterpret_cast<unsigned char *>(d.ws + oVf);
     P.n_pt = pk.n_pt;
     P.n_kc = pk.n_kc;
-    if (const char *dbg = std::getenv("RMG_PERM_DEBUG_SKIP")) P.debug_skip = std::atoi(dbg);
-    for (int c = 0; c < a.ncols; ++c) P.tcol[c] = a.hcols[c] - (pk.p + 2);
+    P.epi = reinterpret_cast<double *>(d.ws + oE);
+    P.epi_stride = pk.epi_stride;
+    for (int c = 0; c < a.ncols; ++c) P.tcol[c] = pk.tcol[c];
     d.ev.assign(pk.nbatch, nullptr);
     if ((e = cudaStreamCreateWithFlags(&d.cs, cudaStreamNonBlocking)) != cudaSuccess) return e;
     (void)launches;
@@ -663,6 +703,13 @@ cudaError_t perm_dev_upload(PermDevice &d, const PermPack &pk, int b)
     cudaError_t e = cudaHostGetDevicePointer(&devA, pk.hA, 0);
     if (e == cudaSuccess) e = cudaHostGetDevicePointer(&devP, pk.hpc, 0);
     if (e != cudaSuccess) return e;
+    void *devE = nullptr;
+    if ((e = cudaHostGetDevicePointer(&devE, pk.hE, 0)) != cudaSuccess) return e;
+    const size_t offE = (size_t)pt0 * pk.perms_per_cta * pk.epi_stride, nE2 = (size_t)(pt1 - pt0) * pk.perms_per_cta * pk.epi_stride / 2;
+    if (nE2)
+        perm_fetch_kernel<<<(unsigned)std::min<size_t>(16, (nE2 + 255) / 256), 256, 0, d.cs>>>(
+            reinterpret_cast<double2 *>(const_cast<double *>(d.P.epi) + offE),
+            reinterpret_cast<const double2 *>(static_cast<double *>(devE) + offE), nE2);
     const size_t nA2 = nA / 2, nP2 = (size_t)(r1 - r0) * sizeof(PermConst) / 16;
     if (nA2) {
         const unsigned blocks = (unsigned)std::min<size_t>(64, (nA2 + 255) / 256);
@@ -703,6 +750,7 @@ cudaError_t perm_dev_launch(PermDevice &d, const PermPack &pk, int b0, int b1, i
     Pb.vflag = d.P.vflag + v0;
     Pb.Apack = d.P.Apack + (size_t)pt0 * pk.n_kc * pk.A_CHUNK;
     Pb.pc = d.P.pc + r0;
+    Pb.epi = d.P.epi + (size_t)pt0 * pk.perms_per_cta * pk.epi_stride;
     Pb.keys = d.P.keys + r0;
     Pb.R = r1 - r0;
     Pb.n_pt = pt1 - pt0;
@@ -759,7 +807,7 @@ cudaError_t perm_gemm_run(const PermGemmArgs &a, const PermSet &ps, int sm_count
     PermDevice d;
     int device = 0;
     cudaError_t e = cudaGetDevice(&device);
-    if (e == cudaSuccess) e = perm_pack_plan(ps, a.n, a.p, pk);
+    if (e == cudaSuccess) e = perm_pack_plan(ps, a.n, a.p, a.hcols, a.ncols, pk);
     if (e == cudaSuccess) e = perm_dev_begin(d, pk, device, sm_count, a, st, nullptr, launches);
     if (e == cudaSuccess) e = perm_dev_prepass(d, a, 0, a.V, launches);     // needs only Y: runs while the host packs
     // batches of permutations: pack on the host (all cores), upload on the side stream, launch the GEMM of the

@@ -145,7 +145,10 @@ struct PermKernelParams {
     int inv, kg, pg, wm, warps_m, a_chunk, perms_per_cta;
     unsigned char *vflag;            // [V] set when some permutation's one-pass rss lost too many digits
     int n_pt, n_kc;
-    int debug_skip;                  // diagnostics only: 1 = skip the statistics epilogue, 2 = skip the MMAs
+    // per-permutation constants of the statistics epilogue, compact: [n_pt * perms_per_cta][epi_stride] doubles =
+    // q1[p], c0, then Rinv row of every requested column (ncols x p); one bulk copy per permutation tile
+    const double *epi;
+    int epi_stride;
 };
 
 // Per-voxel quantities every permutation shares (the prepass output), device-resident.  A resident dataset keeps
@@ -164,12 +167,15 @@ struct PermPack {
     size_t apack_doubles = 0;
     double *hA = nullptr;            // pinned host [n_pt][n_kc][A_CHUNK]
     PermConst *hpc = nullptr;        // pinned host [R]
+    double *hE = nullptr;            // pinned host [n_pt * perms_per_cta][epi_stride]
+    int ncols = 0, epi_stride = 0;
+    int tcol[kPermMaxCols] = {0};    // coefficient index of each requested t-column
     void *lease = nullptr;           // pinned-pool lease behind hA / hpc (perm_pack_release)
     int batch_r0(int b) const { return std::min(R, b * tiles_per_batch * perms_per_cta); }
     int batch_r1(int b) const { return std::min(R, (b + 1) * tiles_per_batch * perms_per_cta); }
 };
 
-cudaError_t perm_pack_plan(const PermSet &ps, int n, int p, PermPack &pk);
+cudaError_t perm_pack_plan(const PermSet &ps, int n, int p, const int32_t *hcols, int ncols, PermPack &pk);
 void perm_pack_batch(const PermSet &ps, PermPack &pk, int b);
 void perm_pack_release(PermPack &pk);
 

@@ -330,6 +330,47 @@ SEXP rmincgpu_fdr(SEXP stat, SEXP stat_type, SEXP df, SEXP mask)
     return out;
 }
 
+/* The same with mincFDR's `method` (R/minc_FDR.R:429-438): 0 = "FDR" / "p.adjust", 1 = "BY", 2 = "pFDR" / "fastqvalue",
+ * 3 = "qvalue"; pi0 (methods 2 and 3) is what the R side gets by smoothing rmincgpu_fdr_pi0's fractions with
+ * smooth.spline, exactly as fast.qvalue does (R/minc_misc.R:437-451). */
+SEXP rmincgpu_fdr_method(SEXP stat, SEXP stat_type, SEXP df, SEXP mask, SEXP method, SEXP pi0)
+{
+    if (!Rf_isReal(stat) || !Rf_isReal(df)) Rf_error("stat and df must be double vectors");
+    const R_xlen_t V = XLENGTH(stat);
+    const double *m = mask_or_null(mask, V);
+    const int meth = Rf_asInteger(method);
+    if (meth == NA_INTEGER) Rf_error("method must not be NA");
+    SEXP q = PROTECT(Rf_allocVector(REALSXP, V));
+    SEXP th = PROTECT(Rf_allocVector(REALSXP, 5));
+    char err[512] = "";
+    int rc = rmg_fdr_method(REAL(stat), V, Rf_asInteger(stat_type), REAL(df)[0], LENGTH(df) > 1 ? REAL(df)[1] : 0.0, m, REAL(q),
+                            REAL(th), meth, Rf_asReal(pi0), gpu_device(), err, sizeof err);
+    if (rc != RMG_OK) {
+        UNPROTECT(2);
+        check(rc, err);
+    }
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, q);
+    SET_VECTOR_ELT(out, 1, th);
+    UNPROTECT(3);
+    return out;
+}
+
+/* mean(p >= lambda) for every lambda over the voxels with mask > 0.5 (R/minc_misc.R:439-441) */
+SEXP rmincgpu_fdr_pi0(SEXP stat, SEXP stat_type, SEXP df, SEXP mask, SEXP lambda)
+{
+    if (!Rf_isReal(stat) || !Rf_isReal(df) || !Rf_isReal(lambda)) Rf_error("stat, df and lambda must be double vectors");
+    const R_xlen_t V = XLENGTH(stat);
+    const double *m = mask_or_null(mask, V);
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, XLENGTH(lambda)));
+    char err[512] = "";
+    int rc = rmg_fdr_pi0_fractions(REAL(stat), V, Rf_asInteger(stat_type), REAL(df)[0], LENGTH(df) > 1 ? REAL(df)[1] : 0.0, m,
+                                   REAL(lambda), (int)XLENGTH(lambda), REAL(out), gpu_device(), err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
 /* Adjacency list (R list of integer vectors, 0-based as vertexTFCE documents) -> CSR in R_alloc'd memory. */
 static void adjacency_to_csr(SEXP adjacencies, int **ptr_out, int **idx_out)
 {
@@ -576,6 +617,8 @@ static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_randomize_stored", (DL_FUNC)&rmincgpu_randomize_stored, 15},
     {"rmincgpu_anova", (DL_FUNC)&rmincgpu_anova, 6},
     {"rmincgpu_fdr", (DL_FUNC)&rmincgpu_fdr, 4},
+    {"rmincgpu_fdr_method", (DL_FUNC)&rmincgpu_fdr_method, 6},
+    {"rmincgpu_fdr_pi0", (DL_FUNC)&rmincgpu_fdr_pi0, 5},
     {"rmincgpu_graph_tfce", (DL_FUNC)&rmincgpu_graph_tfce, 7},
     {"rmincgpu_randomize_tfce", (DL_FUNC)&rmincgpu_randomize_tfce, 11},
     {"rmincgpu_volume_tfce", (DL_FUNC)&rmincgpu_volume_tfce, 8},

@@ -41,9 +41,13 @@ def api(request, monkeypatch, oracle, lib):
             Y = oracle.expand_stored(U, scale, offset, voxel_min=voxel_min, slice_len=slice_len)
             return oracle.minc2_model_lm(Y, (1, 1, Y.shape[0]), X, mask=mask, lo=mask_lo, hi=mask_hi)
 
-        def fdr(stat, stat_type, df1, df2=0.0, mask=None, device=0):
-            q, th, _ = oracle.fdr(stat, "t" if stat_type == core.STAT_T else "F", df1, df2, mask=mask)
+        def fdr(stat, stat_type, df1, df2=0.0, mask=None, device=0, method="FDR", pi0=1.0):
+            q, th, _ = oracle.fdr(stat, "t" if stat_type == core.STAT_T else "F", df1, df2, mask=mask, method=method, pi0=pi0)
             return q, th
+
+        def fdr_pi0_fractions(stat, stat_type, df1, df2=0.0, mask=None, lambdas=None, device=0):
+            _, _, p = oracle.fdr(stat, "t" if stat_type == core.STAT_T else "F", df1, df2, mask=mask)
+            return oracle.pi0_fractions(p, lambdas)
 
         def graph_tfce(maps, adjacency, E=0.5, H=2.0, nsteps=100, side="both", weights=None, device=0):
             ptr, aidx = core.adjacency_csr(adjacency)
@@ -82,6 +86,7 @@ def api(request, monkeypatch, oracle, lib):
         monkeypatch.setattr(core, "graph_tfce", graph_tfce)
         monkeypatch.setattr(core, "randomize_tfce", randomize_tfce)
         monkeypatch.setattr(core, "fdr", fdr)
+        monkeypatch.setattr(core, "fdr_pi0_fractions", fdr_pi0_fractions)
         monkeypatch.setattr(core, "lm_fit_stored", lm_fit_stored)
         monkeypatch.setattr(core, "lm_fit_cov", lm_fit_cov)
         monkeypatch.setattr(core, "vertex_wlm", vertex_wlm)
@@ -424,6 +429,19 @@ def test_mincFDR(api, study):
     with pytest.raises(ValueError, match="need to specify the degrees of freedom"):
         bad = api.MincMatrix(np.asarray(vs), colnames=vs.colnames, attrs={"stat-type": vs.attrs["stat-type"]})
         api.mincFDR(bad)
+    # the other methods (R/minc_FDR.R:429-438): BY = c(m) * BH capped at 1; pFDR / qvalue estimate pi0 from the
+    # mean(p >= lambda) grid through the smoothing spline and scale by it
+    by = api.mincFDR(vs, columns=["tvalue-SexM"], mask=maskfile, method="BY")
+    c = np.sum(1.0 / np.arange(1, inside.sum() + 1))
+    assert np.asarray(by)[inside, 0] == pytest.approx(np.minimum(1.0, c * bh[np.argsort(o)]), rel=1e-9)
+    lam = np.arange(1, 20) * 0.05
+    pi0 = min(api.smooth_spline_at_last_knot(lam, np.array([np.mean(p >= l) for l in lam]) / (1 - lam), 3.0), 1.0)
+    qq = api.mincFDR(vs, columns=["tvalue-SexM"], mask=maskfile, method="qvalue")
+    assert np.asarray(qq)[inside, 0] == pytest.approx(pi0 * want, rel=1e-8)
+    pf = api.mincFDR(vs, columns=["tvalue-SexM"], mask=maskfile, method="pFDR")
+    assert pf.shape == (1000, 1) and (np.asarray(pf)[~inside] == 1).all() and (np.asarray(pf)[inside] <= 1).all()
+    with pytest.raises(ValueError, match="unknown method"):
+        api.mincFDR(vs, method="bonferroni")
 
 
 def test_vertexTFCE(api, tmp_path, oracle):

@@ -702,6 +702,60 @@ def test_fdr_matches_oracle(core, oracle, stat_type, df1, df2):
         assert th[~np.isnan(wth)] == pytest.approx(wth[~np.isnan(wth)], rel=1e-8)
 
 
+@pytest.mark.parametrize("method,pi0", [("BY", 1.0), ("pFDR", 0.83), ("fastqvalue", 1.0), ("qvalue", 0.83)])
+def test_fdr_other_methods_match_oracle(core, oracle, method, pi0):
+    """mincFDR's methods beyond Benjamini-Hochberg (R/minc_FDR.R:429-438) against the restated p.adjust(., "BY"),
+    fast.qvalue (whose qvalue_min step is pinned to the reference's object code in test_oracle.py) and qvalue forms."""
+    rng = np.random.default_rng(11)
+    V = 120_011
+    s = rng.standard_t(40, V)
+    s[: V // 15] += rng.normal(4.5, 1, V // 15)
+    s[rng.integers(0, V, 500)] = np.round(s[rng.integers(0, V, 500)], 1)        # ties
+    mask = (rng.random(V) > 0.25).astype(float)
+    for m in (None, mask):
+        q, th = core.fdr(s, core.STAT_T, 40, mask=m, method=method, pi0=pi0)
+        wq, wth, _ = oracle.fdr(s, "t", 40, mask=m, method=method, pi0=pi0)
+        assert q == pytest.approx(wq, rel=1e-9, abs=1e-300)
+        if m is not None:
+            assert (q[m < 0.5] == 1).all()
+        assert np.array_equal(np.isnan(th), np.isnan(wth))
+        assert th[~np.isnan(wth)] == pytest.approx(wth[~np.isnan(wth)], rel=1e-8)
+    sf = rng.f(3, 60, 50_000)
+    sf[:2000] *= 9
+    q, th = core.fdr(sf, core.STAT_F, 3, 60, method=method, pi0=pi0)
+    wq, wth, _ = oracle.fdr(sf, "F", 3, 60, method=method, pi0=pi0)
+    assert q == pytest.approx(wq, rel=1e-9, abs=1e-300) and th[~np.isnan(wth)] == pytest.approx(wth[~np.isnan(wth)], rel=1e-8)
+
+
+def test_fdr_storey_edge_cases_and_pi0_grid(core, oracle):
+    """The largest p as the LAST element (the reference reads past the end there: kept raw), as a middle element with a
+    successor above 1 (becomes 1); the pi0 grid; the reference's error cases."""
+    from scipy import stats as S
+    t_of_p = lambda p: S.t.isf(np.asarray(p) / 2.0, 25)
+    for p in ([0.2, 0.9, 0.01, 0.95], [0.2, 0.95, 0.9, 0.01], [0.97, 0.99, 0.98, 0.96, 0.5], [0.3]):
+        s = t_of_p(p)
+        for pi0 in (1.0, 0.6):
+            q, _ = core.fdr(s, core.STAT_T, 25, method="pFDR", pi0=pi0)
+            assert q == pytest.approx(oracle.fast_qvalue(np.asarray(p, float), pi0), rel=1e-8), (p, pi0)
+    rng = np.random.default_rng(2)
+    s = rng.standard_t(25, 30_001)
+    mask = (rng.random(30_001) > 0.5).astype(float)
+    lam = np.arange(0, 19) * 0.05
+    _, _, pv = oracle.fdr(s, "t", 25, mask=mask)
+    assert core.fdr_pi0_fractions(s, core.STAT_T, 25, mask=mask, lambdas=lam) == pytest.approx(oracle.pi0_fractions(pv, lam), abs=2.0 / pv.size)
+    with pytest.raises(core.RmincGpuError, match="pi0 <= 0"):
+        core.fdr(s, core.STAT_T, 25, method="pFDR", pi0=0.0)
+    s[3] = np.nan
+    with pytest.raises(core.RmincGpuError, match="missing value"):
+        core.fdr(s, core.STAT_T, 25, method="qvalue", pi0=0.9)
+    with pytest.raises(core.RmincGpuError, match="missing value"):
+        core.fdr_pi0_fractions(s, core.STAT_T, 25)
+    with pytest.raises(core.RmincGpuError, match=r"\[0, 1\)"):
+        core.fdr_pi0_fractions(s[4:], core.STAT_T, 25, lambdas=[0.5, 1.0])
+    q, th = core.fdr(s, core.STAT_T, 25, method="BY")                            # p.adjust drops the NA, as for "fdr"
+    assert np.isnan(q[3]) and q[np.arange(30_001) != 3] == pytest.approx(oracle.fdr(s, "t", 25, method="BY")[0][np.arange(30_001) != 3], rel=1e-9)
+
+
 def test_fdr_edge_cases_and_device_form(core, oracle):
     import torch
     # nothing significant: every threshold NA; everything masked: all ones

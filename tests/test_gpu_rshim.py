@@ -139,6 +139,13 @@ def test_randomize_fdr_and_stored_routines(R, oracle):
     wq, wth, _ = oracle.fdr(fit[:, 5], "t", n - 2, mask=mask)
     np.testing.assert_allclose(q, wq, rtol=RTOL, atol=0)
     assert np.array_equal(np.isnan(th), np.isnan(wth))
+    lam = np.arange(0, 19) * 0.05
+    _, _, pv = oracle.fdr(fit[:, 5], "t", n - 2, mask=mask)
+    frac = R.call("rmincgpu_fdr_pi0", fit[:, 5].copy(), 1, np.array([float(n - 2)]), mask, lam)
+    np.testing.assert_allclose(frac, oracle.pi0_fractions(pv, lam), atol=1.5 / pv.size)
+    for code, method in ((1, "BY"), (2, "pFDR"), (3, "qvalue")):
+        q, th = R.call("rmincgpu_fdr_method", fit[:, 5].copy(), 1, np.array([float(n - 2)]), mask, code, 0.9)
+        np.testing.assert_allclose(q, oracle.fdr(fit[:, 5], "t", n - 2, mask=mask, method=method, pi0=0.9)[0], rtol=RTOL, atol=0)
     # volumes in their stored type: a raw vector of uint16 samples + the real-range tables
     rng = np.random.default_rng(5)
     sl = 12 * 9

@@ -367,6 +367,79 @@ def test_fdr_restatement(oracle):
     assert th[1] == pytest.approx(acc.min(), rel=1e-9)       # the weakest accepted |t| is the threshold
 
 
+def test_fdr_other_methods_restatement(oracle):
+    """mincFDR's other methods (R/minc_FDR.R:429-438).  p.adjust(., "BY") against scipy's Benjamini-Yekutieli and a case
+    by hand; fast.qvalue's qvalue_min step against the REFERENCE'S OWN object code (src/modelling_functions.c:15-46),
+    including its two quirks (pairwise, not running, minimum; the last-ranked element probes its successor in the
+    vector); the qvalue package's form is pi0 times Benjamini-Hochberg."""
+    from scipy import stats as S
+    rng = np.random.default_rng(8)
+    # BY by hand: n = 4, c = 1 + 1/2 + 1/3 + 1/4 = 25/12; sorted p .005 .01 .03 .04 -> c*4/i*p = .041667 .041667 .083333 .083333
+    q = oracle.p_adjust_by([0.01, 0.04, 0.03, 0.005])
+    assert q == pytest.approx([25 / 12 * 0.02, 25 / 12 * 0.04, 25 / 12 * 0.04, 25 / 12 * 0.02], rel=1e-14)
+    p = np.r_[rng.random(500), rng.random(60) * 1e-4]
+    assert oracle.p_adjust_by(p) == pytest.approx(S.false_discovery_control(p, method="by"), rel=1e-12)
+    pn = p.copy()
+    pn[::7] = np.nan
+    qn = oracle.p_adjust_by(pn)
+    assert np.isnan(qn[::7]).all()
+    ok = ~np.isnan(pn)
+    assert qn[ok] == pytest.approx(S.false_discovery_control(pn[ok], method="by"), rel=1e-12)
+    # qvalue_min: restatement == the reference's object code, on raw q-values straddling 1, with ties, with the largest p
+    # last in the vector (the reference reads one past the end there) and not last
+    if oracle.have_ref():
+        for trial in range(20):
+            m = int(rng.integers(2, 60))
+            pp = np.round(rng.random(m), 2 if trial % 2 else 6)             # rounding makes ties
+            if trial % 3 == 0:
+                pp[-1] = 1.0                                                 # largest p is the last element
+            pi0 = float(rng.uniform(0.3, 1.0))
+            u = np.argsort(pp, kind="stable") + 1
+            v = np.searchsorted(np.sort(pp), pp, side="right")
+            raw = pi0 * m * pp / v * rng.choice([1.0, 3.0], m)               # some far above 1
+            assert np.array_equal(oracle.qvalue_min(raw, u), oracle.qvalue_min(raw, u, use_ref=True)), trial
+            assert np.array_equal(oracle.fast_qvalue(pp, pi0), oracle.fast_qvalue(pp, pi0, use_ref=True)), trial
+    # by hand: p = (.5, .01, .02), pi0 = 1, m = 3: raw q = 3 p / rank = (.5, .03, .03); u = (2, 3, 1)
+    #   rank-last (element 1): probes qvalue[u[2]] = qvalue[1] (0-based) = .03, not above 1 -> keeps .5
+    #   element 3: min(.03, .5) = .03; element 2: min(.03, .03) = .03
+    assert oracle.fast_qvalue([0.5, 0.01, 0.02], 1.0) == pytest.approx([0.5, 0.03, 0.03], rel=1e-15)
+    # NOT a running minimum: p = (.001, .5, .6, .9) * ..., raw = 4p/rank = (.004, 1, .8, .9): element 2 takes min(1, .8),
+    # element 1 takes min(.004, 1 [raw, not .8])
+    assert oracle.fast_qvalue([0.001, 0.5, 0.6, 0.9], 1.0) == pytest.approx([0.004, 0.8, 0.8, 0.9], rel=1e-15)
+    assert oracle.qvalue_package(p, 0.7) == pytest.approx(0.7 * oracle.p_adjust_bh(p), rel=1e-15)
+    assert oracle.pi0_fractions([0.1, 0.5, 0.5, 0.9], [0.0, 0.5, 0.55]) == pytest.approx([1.0, 0.75, 0.25])
+    # thresholds come from max(p[q <= level]) (a set, not a prefix: fast.qvalue's q is not monotone in p)
+    t = np.r_[rng.standard_t(30, 2000), rng.normal(5, 1, 200)]
+    for method, pi0 in (("BY", 1.0), ("pFDR", 0.85), ("qvalue", 0.85)):
+        q, th, pv = oracle.fdr(t, "t", 30, method=method, pi0=pi0)
+        for j, lev in enumerate(oracle.FDR_LEVELS):
+            acc = np.abs(t)[q <= lev]
+            assert (np.isnan(th[j]) and acc.size == 0) or th[j] == pytest.approx(acc.min(), rel=1e-9)
+
+
+def test_smoothing_spline_for_pi0():
+    """fast.qvalue's pi0 = predict(smooth.spline(lambda, pi0, df = 3), max(lambda)) (R/minc_misc.R:446-447): the host
+    smoother of the API layer against scipy's independent smoothing-spline solver at the same penalty, and its trace."""
+    from scipy.interpolate import make_smoothing_spline
+    from rminc_b200 import api
+    rng = np.random.default_rng(4)
+    lam = np.arange(0, 19) * 0.05
+    y = 0.8 + 0.1 * lam ** 2 + 0.01 * rng.standard_normal(19)
+    got = api.smooth_spline_at_last_knot(lam, y, 3.0)
+    # find the penalty whose smoother matrix has trace 3 with scipy alone (columns of the hat matrix = fits of unit vectors)
+    def trace(l):
+        return sum(make_smoothing_spline(lam, np.eye(19)[i], lam=l)(lam[i]) for i in range(19))
+    lo, hi = -30.0, 10.0
+    for _ in range(80):
+        mid = 0.5 * (lo + hi)
+        lo, hi = (mid, hi) if trace(np.exp(mid)) > 3.0 else (lo, mid)
+    want = float(make_smoothing_spline(lam, y, lam=np.exp(0.5 * (lo + hi)))(lam[-1]))
+    assert got == pytest.approx(want, rel=1e-8)
+    # a straight line is reproduced exactly (the penalty does not see it); df -> n interpolates
+    assert api.smooth_spline_at_last_knot(lam, 0.3 + 0.5 * lam, 3.0) == pytest.approx(0.3 + 0.5 * 0.9, rel=1e-12)
+    assert api.smooth_spline_at_last_knot(lam, y, 19.0) == pytest.approx(y[-1], rel=1e-6)
+
+
 def test_graph_tfce_restatement(oracle):
     """graph_tfce_wqu / graph_tfce (src/vertex_tfce.cpp:92-157): equals the reference's own object code bit for bit,
     and a case small enough to enhance by hand."""

@@ -70,6 +70,8 @@ def every_routine_call(n=12, V=40):
                                       idx, cols, True, 1),
         "rmincgpu_anova": (Y, X, np.array([0, 1, 2], dtype=np.int32), None, 1.0, 99999999.0),
         "rmincgpu_fdr": (Y[:, 0].copy(), 1, np.array([float(n - 3)]), None),
+        "rmincgpu_fdr_method": (Y[:, 0].copy(), 1, np.array([float(n - 3)]), None, 2, 0.9),
+        "rmincgpu_fdr_pi0": (Y[:, 0].copy(), 1, np.array([float(n - 3)]), None, np.arange(0, 19) * 0.05),
         "rmincgpu_graph_tfce": (Y[:, 0].copy(), adj, 0.5, 2.0, 20, np.ones(V), 0),
         "rmincgpu_randomize_tfce": (Y, X, idx, cols, True, adj, np.ones(V), 0.5, 2.0, 20, 0),
         "rmincgpu_volume_tfce": (Y[:, 0].copy(), np.array([2.0, 4.0, 5.0]), 6, 1.0, 0.25, 0.5, 2.0, 0),
