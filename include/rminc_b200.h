@@ -279,6 +279,9 @@ int rmg_randomize_stored(const void *U, int dtype, int64_t V, int64_t ldU, int n
  * batched over maps.
  *   maps      V x nmaps (column-major: one map per column), out likewise
  *   adj_ptr / adj_idx   CSR form of the 0-based adjacency list vertexTFCE takes (adj_ptr[V+1], adj_idx[adj_ptr[V]])
+ *                       The list must be symmetric (u in adj(v) <=> v in adj(u)), as an undirected surface graph is;
+ *                       a one-directional edge is RMG_ERR_INVALID (the reference would follow it from the higher-valued
+ *                       end only, src/vertex_tfce.cpp:104-118)
  *   weights   V vertex areas, NULL = ones (R/minc_vertex_statistics.R:752-758)
  *   E, H, nsteps   extent / height exponents and number of threshold steps (defaults 0.5, 2, 100); nsteps <= 253
  *   side      0 "both" (tfce(x) - tfce(-x)), 1 "positive", 2 "negative" (-tfce(-x))   (:788-796)
@@ -360,6 +363,26 @@ int rmg_lm_fit_stored_multi(const void *U, int dtype, int64_t V, int64_t ldU, in
                             const double *scale, const double *offset, double voxel_min, int64_t slice_len,
                             const double *X, int p, const double *mask, double mask_lo, double mask_hi,
                             double *out, int64_t ldOut, int n_gpus, char *err, size_t errlen);
+/*
+ * mincRandomize on a model with a voxel-wise covariate (y ~ static terms + a column of files).  The reference's loop
+ * re-evaluates the whole mincLm call with the predictor rows of the data frame re-sampled -- the covariate files move
+ * with the static columns (R/minc_voxel_statistics.R:1468-1477; src/modelling_functions.c:848-854, 1118-1144) -- so
+ * permutation r fits y_v on [Xs | z_v][idx[, r], ] at every voxel.
+ *   Y, Z     V x n, same leading dimension ldY (as rmg_lm_fit_cov); Xs n x ps static part (NULL / 0: the intercept)
+ *   cols     0-based columns of the 2 (ps + 1) + 3 column result (the covariate is the last coefficient)
+ *   dist     R x ncols column-major maxima, non-finite -> 0, abs when two_sided (as rmg_randomize)
+ * Errors: a rank-deficient permuted static part is RMG_ERR_INVALID (as rmg_lm_fit_cov); an all-zero (re-sampled)
+ * covariate at a fitted voxel is the reference's dpotri error, RMG_ERR_SINGULAR.
+ * One streaming pass over Y and Z per permutation; _multi shards the voxels over n_gpus devices (host max-merge).
+ */
+int rmg_randomize_cov(const double *Y, const double *Z, int64_t V, int64_t ldY, int n, const double *Xs, int ps,
+                      const double *mask, double mask_lo, double mask_hi,
+                      const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
+                      double *dist, int device, char *err, size_t errlen);
+int rmg_randomize_cov_multi(const double *Y, const double *Z, int64_t V, int64_t ldY, int n, const double *Xs, int ps,
+                            const double *mask, double mask_lo, double mask_hi,
+                            const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
+                            double *dist, int n_gpus, char *err, size_t errlen);
 int rmg_randomize_multi(const double *Y, int64_t V, int64_t ldY, int n, const double *X, int p,
                         const double *mask, double mask_lo, double mask_hi,
                         const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,

@@ -219,6 +219,25 @@ def randomize(Y, X, idx, cols, two_sided=True, mask=None, lo=1.0, hi=99999999.0)
     return dist
 
 
+def randomize_cov(Y, Z, Xs, idx, cols, two_sided=True, mask=None, lo=1.0, hi=99999999.0, use_ref=False):
+    """mincRandomize_core on a model with a voxel-wise covariate, literally (R/minc_voxel_statistics.R:1465-1497): per
+    permutation shuf_data[, pred_cols] <- data[sample(n), pred_cols] re-samples the static predictors AND the column of
+    covariate files together, the whole model is refitted (lm_loop_cov: the per-voxel design [Xs | z_v], restated from /
+    equal to the reference's vertex_lm_loop with data_right), non-finite -> 0, abs when two-sided, column maximum."""
+    Y = _F(Y)
+    Z = _F(Z)
+    idx = np.asarray(idx)
+    out = np.empty((idx.shape[1], len(cols)))
+    for r in range(idx.shape[1]):
+        ix = idx[:, r]
+        fit = lm_loop_cov(Y, np.asfortranarray(Z[:, ix]), None if Xs is None else np.asarray(Xs)[ix], mask=mask, lo=lo, hi=hi,
+                          use_ref=use_ref)
+        sel = fit[:, list(cols)].copy()
+        sel[~np.isfinite(sel)] = 0.0
+        out[r] = np.abs(sel).max(axis=0) if two_sided else sel.max(axis=0)
+    return out
+
+
 def design_probe(X):
     """pivot, rank, R (p x p upper), c = diag((R'R)^-1), dpotri info."""
     X = _F(X)

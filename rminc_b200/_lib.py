@@ -75,6 +75,8 @@ SIGNATURES = {
     "rmg_randomize_device": (C.c_int, _FIT_HEAD + _MASK + _PERM + [C.c_void_p, C.c_int, C.c_void_p] + _ERR),
     "rmg_lm_fit_multi": (C.c_int, _FIT_HEAD + _MASK + [C.c_void_p, C.c_int64, C.c_int] + _ERR),
     "rmg_randomize_multi": (C.c_int, _FIT_HEAD + _MASK + _PERM + [C.c_void_p, C.c_int] + _ERR),
+    "rmg_randomize_cov": (C.c_int, [C.c_void_p] + _FIT_HEAD + _MASK + _PERM + [C.c_void_p, C.c_int] + _ERR),
+    "rmg_randomize_cov_multi": (C.c_int, [C.c_void_p] + _FIT_HEAD + _MASK + _PERM + [C.c_void_p, C.c_int] + _ERR),
     "rmg_randomize_stored": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
                                        C.c_int64, C.c_void_p, C.c_int] + _MASK + _PERM + [C.c_void_p, C.c_int] + _ERR),
     "rmg_randomize_stored_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,

@@ -317,6 +317,7 @@ def mincLm(formula: str, data, subset=None, mask=None, maskval=None, parallel=No
             "likeVolume": filenames[0], "filenames": list(filenames), "model": model, "data": data,
             "call": dict(fn="mincLm", formula=formula, subset=subset, mask=mask, maskval=maskval, parallel=parallel),
             "stat-type": _stat_type(p), "df": dflist, "model-colnames": plm["rows"],
+            "_Y": Y, "_Z": Z, "_Xs": plm["mmatrix"], "_mask": m, "_mask_range": (lo, hi), "_rows": rows, "_rhs": rhs, "_lhs": lhs,
         }
         return MincMatrix(out, colnames=_colnames(plm["rows"]), attrs=attrs, r_class=("mincLm", "mincMultiDim", "matrix"))
     X, names, _ = model_matrix(rhs, data, rows)
@@ -750,7 +751,7 @@ def mincRandomize(x: MincMatrix, R: int = 500, alternative: str = "two.sided", r
     if not isinstance(x, MincMatrix) or ("_Y" not in x.attrs and "_stored" not in x.attrs):
         raise TypeError("x must be the result of mincLm / vertexLm / anatLm")
     X = x.attrs["model"]
-    n = X.shape[0]
+    n = x.attrs["_Y"].shape[1] if "_Y" in x.attrs else X.shape[0]
     if columns is None:
         columns = [i for i, c in enumerate(x.colnames) if c.startswith("tvalue-")]
     columns = [int(c) for c in columns]
@@ -761,7 +762,13 @@ def mincRandomize(x: MincMatrix, R: int = 500, alternative: str = "two.sided", r
         raise ValueError("idx must be n x R")
     lo, hi = x.attrs["_mask_range"]
     n_gpus = int(parallel[1]) if parallel is not None else None
-    if "_stored" in x.attrs:      # the fit ran on volumes in their stored type: so does the permutation test
+    if "_Z" in x.attrs:
+        # a voxel-wise covariate: its files are re-sampled with the static predictors and the per-voxel design is
+        # refitted (the loop re-evaluates the whole call, R/minc_voxel_statistics.R:1468-1477)
+        dist = core.randomize_cov(x.attrs["_Y"], x.attrs["_Z"], x.attrs["_Xs"], idx, columns,
+                                  two_sided=(alternative == "two.sided"), mask=x.attrs["_mask"], mask_lo=lo, mask_hi=hi,
+                                  device=device, n_gpus=n_gpus)
+    elif "_stored" in x.attrs:    # the fit ran on volumes in their stored type: so does the permutation test
         sv = x.attrs["_stored"]
         dist = core.randomize_stored(sv["U"], X, idx, columns, scale=sv["scale"], offset=sv["offset"],
                                      voxel_min=sv["voxel_min"], slice_len=sv["slice_len"],

@@ -540,6 +540,41 @@ def randomize(Y, X, idx, cols, two_sided=True, mask=None, mask_lo=DEFAULT_MASK_L
     return dist
 
 
+def randomize_cov(Y, Z, Xs, idx, cols, two_sided=True, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI,
+                  device=0, n_gpus=None):
+    """mincRandomize's loop for a model with a voxel-wise covariate: permutation r fits y_v on [Xs | z_v][idx[:, r], :]
+    (the covariate files are re-sampled with the static predictors, R/minc_voxel_statistics.R:1468-1477).
+    R x len(cols) maxima; cols index the 2p+3 columns of the p = ncol(Xs) + 1 column result."""
+    Y = _lib.as_f64_fortran(np.asarray(Y))
+    Z = _lib.as_f64_fortran(np.asarray(Z))
+    if Y.ndim != 2 or Z.shape != Y.shape:
+        raise ValueError("Y must be V x n and the voxel-wise covariate must have its shape")
+    V, n = Y.shape
+    Xs_ = None if Xs is None else _lib.as_f64_fortran(Xs)
+    if Xs_ is not None and (Xs_.ndim != 2 or Xs_.shape[0] != n):
+        raise ValueError(f"Xs must be n x ps with n == ncol(Y); got {Xs_.shape} vs {Y.shape}")
+    ps = 0 if Xs_ is None else Xs_.shape[1]
+    p = ps + 1 if ps else 2
+    m = None
+    if mask is not None:
+        m = np.ascontiguousarray(np.asarray(mask, dtype=np.float64).reshape(-1))
+        if m.shape[0] != V:
+            raise ValueError("mask length must equal the number of voxels")
+    idx, cols = _prep_perm(idx, n, cols)
+    if cols.size and (cols.min() < 0 or cols.max() >= 2 * p + 3):
+        raise ValueError("cols entries must be in 0..2p+2")
+    R = idx.shape[1]
+    dist = np.empty((R, len(cols)), order="F")
+    err = _lib.errbuf()
+    lib = _lib.load()
+    fn, where = (lib.rmg_randomize_cov, device) if n_gpus is None else (lib.rmg_randomize_cov_multi, int(n_gpus))
+    rc = fn(Y.ctypes.data, Z.ctypes.data, V, max(V, 1), n, Xs_.ctypes.data if ps else None, ps,
+            m.ctypes.data if m is not None else None, mask_lo, mask_hi, idx.ctypes.data, R, cols.ctypes.data, len(cols),
+            int(bool(two_sided)), dist.ctypes.data, where, err, len(err))
+    _lib.check(rc, err)
+    return dist
+
+
 def randomize_stored(U, X, idx, cols, scale=None, offset=None, voxel_min=0.0, slice_len=None, two_sided=True, mask=None,
                      mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, device=0, n_gpus=None):
     """mincRandomize's loop on volumes in their stored type (U, scale, offset, voxel_min, slice_len as lm_fit_stored):

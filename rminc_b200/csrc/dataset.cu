@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdio>
 #include <mutex>
+#include <string>
 #include <thread>
 
 #include "capi_common.hpp"
@@ -918,6 +919,170 @@ cleanup:
     }
     if (rc != RMG_OK) cudaGetLastError();
     return rc;
+}
+
+// ---- mincRandomize on a model with a voxel-wise covariate (y ~ static terms + a column of files).
+// The reference's loop re-evaluates the whole mincLm call with the PREDICTOR rows of the data frame re-sampled -- the
+// column of covariate files moves with the static columns (R/minc_voxel_statistics.R:1468-1477) -- so permutation r fits
+// y_v on P_r [Xs | z_v] at every voxel (src/modelling_functions.c:1118-1144 re-factorises that matrix per voxel).  Here:
+// the static part Xs[idx_r, ] is factored once per permutation on the host; on the device the covariate kernel pairs
+// subject j of Y with plane idx_r[j] of Z (CovArgs::zrow), result columns reduce to their maxima.  One streaming pass
+// over Y and Z per permutation (HBM-bound, 16 n bytes per voxel), voxel shards over the devices, host max.
+static int randomize_cov_transient(const double *Y, const double *Z, int64_t V, int64_t ldY, int n, const double *Xs_in, int ps_in,
+                                   const double *mask, double mask_lo, double mask_hi, const int32_t *idx, int R,
+                                   const int32_t *cols, int ncols, int two_sided, double *dist, const std::vector<int> &devices,
+                                   char *err, size_t errlen)
+{
+    if (V > 0 && (!Y || !Z)) return fail(err, errlen, RMG_ERR_INVALID, "Y or Z is NULL");
+    if (n < 1) return fail(err, errlen, RMG_ERR_INVALID, "n must be >= 1 (got %d)", n);
+    std::vector<double> ones;
+    int ps = ps_in;
+    const double *Xs = Xs_in;
+    if (!Xs || ps <= 0) {                       // the static part defaults to the intercept (src/vertex_modelling.c:36-39)
+        ones.assign((size_t)n, 1.0);
+        Xs = ones.data();
+        ps = 1;
+    }
+    const int p = ps + 1;
+    int rc = check_fit_args(Y, V, ldY, n, Xs, ps, Y, ldY, err, errlen);
+    if (rc) return rc;
+    if (ps > 16) return fail(err, errlen, RMG_ERR_INVALID, "voxel-wise covariate designs support at most 16 static columns (got %d)", ps);
+    if ((rc = check_perm_args(p, idx, R, cols, ncols, dist, err, errlen))) return rc;
+    if (R == 0 || ncols == 0) return RMG_OK;
+    PermSet pd;
+    if ((rc = factor_permutations(Xs, n, ps, idx, R, pd, err, errlen))) return rc;
+    for (int r = 0; r < R; ++r)
+        if (pd.design(r).k < ps)
+            return fail(err, errlen, RMG_ERR_INVALID,
+                        "permutation %d: rank-deficient static design (rank %d < %d columns) with a voxel-wise covariate is not supported",
+                        r + 1, pd.design(r).k, ps);
+    const int G = (int)devices.size(), nk = R * ncols, ncol_total = 2 * p + 3, KP = lm_padded_p(ps);
+    rmg_dataset *dy = nullptr, *dz = nullptr;
+    if ((rc = dataset_create(Y, nullptr, V, ldY, n, mask, mask_lo, mask_hi, devices.data(), G, &dy, err, errlen))) return rc;
+    if ((rc = dataset_create(Z, nullptr, V, ldY, n, nullptr, 0.0, 0.0, devices.data(), G, &dz, err, errlen))) {
+        dataset_destroy(dy);
+        return rc;
+    }
+    // host copies of every permuted design (shared by the shards)
+    const size_t qstride = make_qt(pd.base, KP).size();
+    std::vector<DevDesign> hdd(R);
+    std::vector<double> hqt((size_t)R * qstride);
+    parallel_for(R, [&](int r0, int r1) {
+        for (int r = r0; r < r1; ++r) {
+            const Design Dr = pd.materialise(r);
+            fill_dev_design(Dr, hdd[r]);
+            const std::vector<double> q = make_qt(Dr, KP);
+            std::copy(q.begin(), q.end(), hqt.begin() + (size_t)r * qstride);
+        }
+    });
+    ColList cl;
+    std::memset(&cl, 0, sizeof cl);
+    for (int c = 0; c < ncols; ++c) cl.c[c] = cols[c];
+    std::vector<std::vector<double>> parts(G, std::vector<double>((size_t)nk, -INFINITY));
+    std::vector<int> rcs(G, RMG_OK), status(G, 0);
+    std::vector<std::string> msgs(G, std::string(256, '\0'));
+    std::vector<int64_t> launches(G, 0);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) {
+        if (dy->sh[g].cv <= 0) continue;
+        th.emplace_back([&, g]() {
+            DsShard &sy = dy->sh[g], &sz = dz->sh[g];
+            char *e_ = &msgs[g][0];
+            const size_t el_ = msgs[g].size();
+            auto body = [&](char *err, size_t errlen) -> int {
+                int rc = RMG_OK;
+                double *scratch = nullptr, *qt = nullptr, *dD = nullptr;
+                DevDesign *dd = nullptr;
+                int32_t *didx = nullptr;
+                int *dstatus = nullptr;
+                unsigned long long *keys = nullptr;
+                cudaStream_t st = sy.st;
+                LmPlan plan;
+                plan.sm_count = sy.sm_count;
+                const int64_t ldo = (sy.cv + 1) & ~int64_t(1);
+                {
+                    RMG_CUDA(cudaSetDevice(sy.device));
+                    for (cudaEvent_t ev : sy.landed)
+                        if (ev) RMG_CUDA(cudaStreamWaitEvent(st, ev, 0));
+                    for (cudaEvent_t ev : sz.landed)
+                        if (ev) RMG_CUDA(cudaStreamWaitEvent(st, ev, 0));
+                    RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)ldo * ncol_total * sizeof(double), st));
+                    RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dd), sizeof(DevDesign) * (size_t)R, st));
+                    RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&qt), sizeof(double) * hqt.size(), st));
+                    RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&didx), sizeof(int32_t) * (size_t)R * n, st));
+                    RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dstatus), sizeof(int), st));
+                    RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&keys), sizeof(unsigned long long) * (size_t)nk, st));
+                    RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dD), sizeof(double) * (size_t)nk, st));
+                    RMG_CUDA(cudaMemsetAsync(dstatus, 0, sizeof(int), st));
+                    RMG_CUDA(cudaMemcpyAsync(dd, hdd.data(), sizeof(DevDesign) * (size_t)R, cudaMemcpyHostToDevice, st));
+                    RMG_CUDA(cudaMemcpyAsync(qt, hqt.data(), sizeof(double) * hqt.size(), cudaMemcpyHostToDevice, st));
+                    RMG_CUDA(cudaMemcpyAsync(didx, idx, sizeof(int32_t) * (size_t)R * n, cudaMemcpyHostToDevice, st));
+                    keys_init_kernel<<<(nk + 255) / 256, 256, 0, st>>>(keys, nk);
+                    ++launches[g];
+                    const int cm_grid = (int)std::min<int64_t>((sy.cv + 255) / 256, (int64_t)plan.sm_count * 8);
+                    for (int r = 0; r < R; ++r) {
+                        CovArgs ca{sy.dY, sz.dY, sy.cv, sy.ld, n, ps, qt + (size_t)r * qstride, dd + r, sy.dM, mask_lo, mask_hi,
+                                   scratch, ldo, dstatus, didx + (size_t)r * n};
+                        LmLaunchInfo info;
+                        RMG_CUDA(launch_lm_cov(ca, plan, st, &info));
+                        launches[g] += info.launches;
+                        colmax_kernel<<<cm_grid, 256, 0, st>>>(scratch, sy.cv, ldo, cl, ncols, two_sided, keys, R, r);
+                        ++launches[g];
+                    }
+                    RMG_CUDA(cudaGetLastError());
+                    keys_decode_kernel<<<(nk + 255) / 256, 256, 0, st>>>(keys, dD, nk);
+                    ++launches[g];
+                    RMG_CUDA(cudaMemcpyAsync(parts[g].data(), dD, sizeof(double) * (size_t)nk, cudaMemcpyDeviceToHost, st));
+                    RMG_CUDA(cudaMemcpyAsync(&status[g], dstatus, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    RMG_CUDA(cudaStreamSynchronize(st));
+                }
+            cleanup:
+                void *all[] = {scratch, dd, qt, didx, dstatus, keys, dD};
+                for (void *x : all)
+                    if (x) cudaFreeAsync(x, st);
+                if (rc != RMG_OK) cudaGetLastError();
+                return rc;
+            };
+            rcs[g] = body(e_, el_);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int g = 0; g < G; ++g) g_launch_count += launches[g];
+    dataset_destroy(dy);
+    dataset_destroy(dz);
+    for (int g = 0; g < G; ++g) {
+        if (rcs[g] != RMG_OK) return fail(err, errlen, rcs[g], "gpu %d: %s", g, msgs[g].c_str());
+        // an all-zero covariate at a fitted voxel: the reference's dpotri error aborts the call (src/modelling_functions.c:551-557)
+        if (status[g] > 0) return fail(err, errlen, RMG_ERR_SINGULAR, "%s", singular_message(status[g]).c_str());
+    }
+    for (int i = 0; i < nk; ++i) {
+        double m = -INFINITY;
+        for (int g = 0; g < G; ++g)
+            if (!parts[g].empty()) m = std::fmax(m, parts[g][i]);
+        dist[i] = m;
+    }
+    return RMG_OK;
+}
+
+int rmg_randomize_cov(const double *Y, const double *Z, int64_t V, int64_t ldY, int n, const double *Xs, int ps, const double *mask,
+                      double mask_lo, double mask_hi, const int32_t *idx, int R, const int32_t *cols, int ncols, int two_sided,
+                      double *dist, int device, char *err, size_t errlen)
+{
+    int rc = select_device(device, err, errlen);
+    if (rc) return rc;
+    return randomize_cov_transient(Y, Z, V, ldY, n, Xs, ps, mask, mask_lo, mask_hi, idx, R, cols, ncols, two_sided, dist,
+                                   std::vector<int>{device}, err, errlen);
+}
+
+int rmg_randomize_cov_multi(const double *Y, const double *Z, int64_t V, int64_t ldY, int n, const double *Xs, int ps,
+                            const double *mask, double mask_lo, double mask_hi, const int32_t *idx, int R, const int32_t *cols,
+                            int ncols, int two_sided, double *dist, int n_gpus, char *err, size_t errlen)
+{
+    std::vector<int> devices;
+    int rc = resolve_gpus(n_gpus, devices, err, errlen);
+    if (rc) return rc;
+    return randomize_cov_transient(Y, Z, V, ldY, n, Xs, ps, mask, mask_lo, mask_hi, idx, R, cols, ncols, two_sided, dist, devices,
+                                   err, errlen);
 }
 
 // ---- mincRandomize on host data = a transient dataset whose upload is consumed block by block as it lands

@@ -42,13 +42,13 @@ struct CovExact {
 // Explicit-residual recomputation for one voxel (rare path); scalars and pointers only, see exact_pass().
 template <int KS>
 __device__ __noinline__ CovExact exact_cov(const double *__restrict__ y, const double *__restrict__ z, int64_t ld, int n,
-                                           const double *__restrict__ Qt, double y0, double z0)
+                                           const double *__restrict__ Qt, double y0, double z0, const int32_t *__restrict__ zrow)
 {
     double e[KS], f[KS];
 #pragma unroll
     for (int k = 0; k < KS; ++k) e[k] = f[k] = 0.0;
     for (int j = 0; j < n; ++j) {
-        const double yv = y[(int64_t)j * ld] - y0, zv = z[(int64_t)j * ld] - z0;
+        const double yv = y[(int64_t)j * ld] - y0, zv = z[(int64_t)(zrow ? zrow[j] : j) * ld] - z0;
 #pragma unroll
         for (int k = 0; k < KS; ++k) {
             const double q = __ldg(Qt + (size_t)j * KS + k);
@@ -65,7 +65,7 @@ __device__ __noinline__ CovExact exact_cov(const double *__restrict__ y, const d
             fy = fma(q, e[k], fy);
             fz = fma(q, f[k], fz);
         }
-        const double r = (y[(int64_t)j * ld] - y0) - fy, zp = (z[(int64_t)j * ld] - z0) - fz;
+        const double r = (y[(int64_t)j * ld] - y0) - fy, zp = (z[(int64_t)(zrow ? zrow[j] : j) * ld] - z0) - fz;
         d2 = fma(zp, zp, d2);
         g = fma(zp, r, g);
         rr = fma(r, r, rr);
@@ -81,7 +81,7 @@ __device__ __noinline__ CovExact exact_cov(const double *__restrict__ y, const d
             fy = fma(q, e[k], fy);
             fz = fma(q, f[k], fz);
         }
-        const double zp = (z[(int64_t)j * ld] - z0) - fz;
+        const double zp = (z[(int64_t)(zrow ? zrow[j] : j) * ld] - z0) - fz;
         const double r = ((y[(int64_t)j * ld] - y0) - fy) - bz * zp;
         rss = fma(r, r, rss);
         sfull += fma(bz, zp, fy);
@@ -96,7 +96,7 @@ __device__ __noinline__ CovExact exact_cov(const double *__restrict__ y, const d
             fy = fma(q, e[k], fy);
             fz = fma(q, f[k], fz);
         }
-        const double zp = (z[(int64_t)j * ld] - z0) - fz;
+        const double zp = (z[(int64_t)(zrow ? zrow[j] : j) * ld] - z0) - fz;
         const double a = fy - ms, b = fma(bz, zp, fy) - mf;
         mss_s = fma(a, a, mss_s);
         mss = fma(b, b, mss);
@@ -108,7 +108,8 @@ __device__ __noinline__ CovExact exact_cov(const double *__restrict__ y, const d
 template <int KS>
 __device__ __forceinline__ void finish_cov(const CovSums<KS> &v, const SmemDesign<KS> &d, const double *__restrict__ y,
                                            const double *__restrict__ z, int64_t ld, const double *__restrict__ Qt,
-                                           double *__restrict__ out, int64_t ldo, int *__restrict__ status)
+                                           double *__restrict__ out, int64_t ldo, int *__restrict__ status,
+                                           const int32_t *__restrict__ zrow)
 {
     const int ps = d.p, p = ps + 1, n = d.n;
     const double nn = (double)n;
@@ -145,7 +146,7 @@ __device__ __forceinline__ void finish_cov(const CovSums<KS> &v, const SmemDesig
     bool exact = false;
     CovExact ex;
     if (v.zz > 0.0 && (d2 <= kExactThreshold * v.zz || (v.yy > 0.0 && rss <= kExactThreshold * v.yy))) {
-        ex = exact_cov<KS>(y, z, ld, n, Qt, v.y0, v.z0);
+        ex = exact_cov<KS>(y, z, ld, n, Qt, v.y0, v.z0, zrow);
         exact = true;
         d2 = ex.d2;
         g = ex.g;
@@ -250,7 +251,7 @@ lm_cov_kernel(CovArgs a, int JT)
         for (int k = 0; k < KS; ++k) sum[i].e[k] = sum[i].f[k] = 0.0;
         sum[i].yy = sum[i].zz = sum[i].zy = sum[i].sz = 0.0;
         sum[i].y0 = (sd.shift && act[i]) ? a.Y[v + i] : 0.0;
-        sum[i].z0 = (sd.shift && act[i]) ? a.Z[v + i] : 0.0;
+        sum[i].z0 = (sd.shift && act[i]) ? a.Z[(a.zrow ? (int64_t)__ldg(a.zrow) * a.ldY : 0) + v + i] : 0.0;   // first (sampled) subject
     }
     const int jb = (int)(((int64_t)s * n) / S), je = (int)(((int64_t)(s + 1) * n) / S);
     const int span = (n + S - 1) / S;
@@ -277,14 +278,15 @@ lm_cov_kernel(CovArgs a, int JT)
             double y[U][VPT], z[U][VPT];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int64_t off = (int64_t)(jb + t0 + jj + u) * a.ldY;
+                const int j = jb + t0 + jj + u;
+                const int64_t off = (int64_t)j * a.ldY, offz = a.zrow ? (int64_t)__ldg(a.zrow + j) * a.ldY : off;
                 if constexpr (VPT == 2) {
-                    const double2 ty = ldg_stream2(yp + off), tz = ldg_stream2(zp + off);
+                    const double2 ty = ldg_stream2(yp + off), tz = ldg_stream2(zp + offz);
                     y[u][0] = ty.x; y[u][1] = ty.y;
                     z[u][0] = tz.x; z[u][1] = tz.y;
                 } else {
                     y[u][0] = ldg_stream(yp + off);
-                    z[u][0] = ldg_stream(zp + off);
+                    z[u][0] = ldg_stream(zp + offz);
                 }
             }
 #pragma unroll
@@ -306,10 +308,11 @@ lm_cov_kernel(CovArgs a, int JT)
             }
         }
         for (; jj < cnt; ++jj) {
-            const int64_t off = (int64_t)(jb + t0 + jj) * a.ldY;
+            const int j = jb + t0 + jj;
+            const int64_t off = (int64_t)j * a.ldY, offz = a.zrow ? (int64_t)__ldg(a.zrow + j) * a.ldY : off;
 #pragma unroll
             for (int i = 0; i < VPT; ++i) {
-                const double yv = yp[off + i] - sum[i].y0, zv = zp[off + i] - sum[i].z0;
+                const double yv = yp[off + i] - sum[i].y0, zv = zp[offz + i] - sum[i].z0;
                 sum[i].yy = fma(yv, yv, sum[i].yy);
                 sum[i].zz = fma(zv, zv, sum[i].zz);
                 sum[i].zy = fma(zv, yv, sum[i].zy);
@@ -371,7 +374,7 @@ lm_cov_kernel(CovArgs a, int JT)
             zero_row<KS>(ncol, o, a.ldOut);
             continue;
         }
-        finish_cov<KS>(sum[i], sd, a.Y + v + i, a.Z + v + i, a.ldY, a.Qt, o, a.ldOut, a.status);
+        finish_cov<KS>(sum[i], sd, a.Y + v + i, a.Z + v + i, a.ldY, a.Qt, o, a.ldOut, a.status, a.zrow);
     }
 }
 

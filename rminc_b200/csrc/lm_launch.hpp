@@ -83,6 +83,8 @@ struct CovArgs {
     double *out;
     int64_t ldOut;
     int *status;               // device int (nullable): set to p when an unmasked voxel's covariate is all zero
+    const int32_t *zrow;       // device [n] (nullable): subject j pairs with covariate plane zrow[j] -- a permuted design
+                               // P [Xs | z_v] (mincRandomize re-samples the predictor rows, R/minc_voxel_statistics.R:1468-1474)
 };
 
 cudaError_t launch_lm_cov(const CovArgs &a, const LmPlan &plan, cudaStream_t st, LmLaunchInfo *info);

@@ -252,6 +252,38 @@ SEXP rmincgpu_randomize(SEXP Y, SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP m
     return out;
 }
 
+/* The mincRandomize loop of a model with a voxel-wise covariate: Z (V x n, the right-hand-side volumes) is re-sampled with
+ * the rows of the static model matrix (NULL: the intercept), R/minc_voxel_statistics.R:1468-1477. */
+SEXP rmincgpu_randomize_cov(SEXP Y, SEXP Z, SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP mask_upper, SEXP idx, SEXP columns,
+                            SEXP two_sided, SEXP ngpu)
+{
+    if (!Rf_isReal(Y) || !Rf_isReal(Z) || !Rf_isInteger(idx) || !Rf_isInteger(columns))
+        Rf_error("Y/Z must be double, idx/columns integer");
+    const R_xlen_t V = Rf_nrows(Y);
+    const int n = Rf_ncols(Y), R = Rf_ncols(idx), nc = LENGTH(columns);
+    if (Rf_nrows(Z) != V || Rf_ncols(Z) != n) Rf_error("the covariate volumes must match the left-hand-side volumes");
+    const int has_static = !Rf_isNull(mmatrix);
+    if (has_static && (!Rf_isReal(mmatrix) || Rf_nrows(mmatrix) != n)) Rf_error("mmatrix must be a double matrix with one row per subject");
+    const int ps = has_static ? Rf_ncols(mmatrix) : 0;
+    if (Rf_nrows(idx) != n) Rf_error("idx must have one row per subject");
+    const double *m = mask_or_null(mask, V);
+    int *idx0 = zero_based(idx, (R_xlen_t)n * R, "idx");
+    int *col0 = zero_based(columns, nc, "columns");
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, R, nc));
+    char err[512] = "";
+    const int G = count_arg(ngpu, "ngpu");
+    const double *xs = has_static ? REAL(mmatrix) : NULL;
+    int rc = G > 1 ? rmg_randomize_cov_multi(REAL(Y), REAL(Z), V, V > 0 ? V : 1, n, xs, ps, m, Rf_asReal(mask_lower),
+                                             Rf_asReal(mask_upper), idx0, R, col0, nc, flag_arg(two_sided, "two_sided"),
+                                             REAL(out), G, err, sizeof err)
+                   : rmg_randomize_cov(REAL(Y), REAL(Z), V, V > 0 ? V : 1, n, xs, ps, m, Rf_asReal(mask_lower),
+                                       Rf_asReal(mask_upper), idx0, R, col0, nc, flag_arg(two_sided, "two_sided"), REAL(out),
+                                       gpu_device(), err, sizeof err);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
 /* The mincRandomize loop on volumes in their stored type (U, dtype .. slice_len as rmincgpu_lm_stored). */
 SEXP rmincgpu_randomize_stored(SEXP U, SEXP dtype, SEXP nvoxels, SEXP scale, SEXP offset, SEXP voxel_min, SEXP slice_len,
                                SEXP mmatrix, SEXP mask, SEXP mask_lower, SEXP mask_upper, SEXP idx, SEXP columns,
@@ -614,6 +646,7 @@ static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_lm_cov", (DL_FUNC)&rmincgpu_lm_cov, 6},
     {"rmincgpu_lm_stored", (DL_FUNC)&rmincgpu_lm_stored, 11},
     {"rmincgpu_randomize", (DL_FUNC)&rmincgpu_randomize, 9},
+    {"rmincgpu_randomize_cov", (DL_FUNC)&rmincgpu_randomize_cov, 10},
     {"rmincgpu_randomize_stored", (DL_FUNC)&rmincgpu_randomize_stored, 15},
     {"rmincgpu_anova", (DL_FUNC)&rmincgpu_anova, 6},
     {"rmincgpu_fdr", (DL_FUNC)&rmincgpu_fdr, 4},

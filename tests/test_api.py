@@ -94,6 +94,11 @@ def api(request, monkeypatch, oracle, lib):
         monkeypatch.setattr(core, "lm_fit", lm_fit)
         monkeypatch.setattr(core, "vertex_lm", vertex_lm)
         monkeypatch.setattr(core, "randomize", randomize)
+
+        def randomize_cov(Y, Z, Xs, idx, cols, two_sided=True, mask=None, mask_lo=1.0, mask_hi=99999999.0, device=0,
+                          n_gpus=None):
+            return oracle.randomize_cov(Y, Z, Xs, idx, cols, two_sided=two_sided, mask=mask, lo=mask_lo, hi=mask_hi)
+        monkeypatch.setattr(core, "randomize_cov", randomize_cov)
     return A
 
 
@@ -324,6 +329,18 @@ def test_file_covariate_on_the_right_hand_side(api, study, tmp_path):
     vm = api.mincLm("jacobians ~ other + Sex", gf, mask=maskfile)
     inside = np.load(maskfile).reshape(-1) > 0.5
     assert np.allclose(np.asarray(vm)[inside], np.asarray(vs)[inside], rtol=1e-12) and (np.asarray(vm)[~inside] == 0).all()
+    # mincRandomize re-evaluates the whole call with the predictor rows re-sampled: the covariate FILES move with Sex
+    # (R/minc_voxel_statistics.R:1468-1477), so every row of the null is the column max of |t| of a refit on
+    # [1, Sex, z_v][idx, ]
+    rz = api.mincRandomize(vm, R=5, seed=7)
+    assert rz["randomization_dist"].colnames == ["tvalue-(Intercept)", "tvalue-SexM", "tvalue-other"]
+    idx = api.draw_indices(n, 5, seed=7)
+    for r in (0, 4):
+        tmax = np.zeros(3)
+        for v in np.flatnonzero(inside):
+            Xv = np.column_stack([np.ones(n), sexm, Z[v]])[idx[:, r]]
+            tmax = np.maximum(tmax, np.abs(numpy_ols(Y[v], Xv)["t"]))
+        assert np.asarray(rz["randomization_dist"])[r] == pytest.approx(tmax, rel=1e-7)
     # the file as the only term: [1 | z], coefficient names 'Intercept' and the term (:1270)
     v1 = api.mincLm("jacobians ~ other", gf)
     assert v1.shape == (1000, 7)

@@ -544,7 +544,7 @@ def test_covariate_rank_and_error_contract(core, oracle):
     mask[5] = 0
     assert_rows_match(core.lm_fit_cov(Y, Z0, Xs, mask=mask)[keep], oracle.lm_loop_cov(Y, Z0, Xs, mask=mask)[keep], RTOL, "masked zero")
     # rank-deficient static part is refused, not guessed
-    with pytest.raises(core.RmincGpuError, match="rank-deficient static design"):
+    with pytest.raises(core.RmincGpuError, match="rank-deficient static design|is zero, so the inverse"):
         core.lm_fit_cov(Y, Z, np.column_stack([Xs, Xs[:, 1]]))
 
 
@@ -670,6 +670,46 @@ def test_stored_tma_ring_variant(core, oracle, slice_len):
         assert_rows_match(got, oracle.vertex_lm_loop(F.astype(np.float64), X[:, :3]), RTOL, "tma f32")
         Fr = np.asfortranarray(F[:79999])                                     # ragged tail: TMA zero-fill, scalar stores
         assert_rows_match(core.lm_fit_stored(Fr, X), oracle.vertex_lm_loop(Fr.astype(np.float64), X), RTOL, "tma f32 ragged")
+
+
+def test_randomize_with_a_voxelwise_covariate(core, oracle):
+    """mincRandomize on y ~ static + file covariate: the reference re-samples the covariate files with the static
+    predictor rows and refits the per-voxel design (R/minc_voxel_statistics.R:1468-1477).  Against the oracle's literal
+    loop over the restated covariate fit (itself bit-equal to the reference's vertex_lm_loop object code): true
+    permutations, replace = TRUE index vectors, a mask, one-sided, the default intercept-only static part, two GPUs when
+    there are two."""
+    Y, Z, Xs = _cov_case(2501, 24, 3, seed=51)
+    n, ps = Xs.shape
+    p = ps + 1
+    rng = np.random.default_rng(52)
+    idx = np.column_stack([rng.permutation(n) for _ in range(7)] + [rng.integers(0, n, n) for _ in range(4)])
+    cols = list(range(p + 2, 2 * p + 2))                                   # every tvalue- column, the covariate's last
+    mask = (np.arange(2501) % 4 != 1).astype(float)
+    for m in (None, mask):
+        got = core.randomize_cov(Y, Z, Xs, idx, cols, mask=m)
+        np.testing.assert_allclose(got, oracle.randomize_cov(Y, Z, Xs, idx, cols, mask=m), rtol=RTOL, atol=0)
+    got = core.randomize_cov(Y, Z, Xs, idx, [0, 1, 2 * p + 1], two_sided=False)     # F, R-squared, the covariate's t, signed
+    np.testing.assert_allclose(got, oracle.randomize_cov(Y, Z, Xs, idx, [0, 1, 2 * p + 1], two_sided=False), rtol=RTOL, atol=0)
+    got = core.randomize_cov(Y, Z, None, idx[:, :5], [4, 5])                # y ~ z: static part = the intercept
+    np.testing.assert_allclose(got, oracle.randomize_cov(Y, Z, None, idx[:, :5], [4, 5]), rtol=RTOL, atol=0)
+    if oracle.have_ref():                                                   # the literal loop over the reference's object code
+        np.testing.assert_allclose(core.randomize_cov(Y[:300], Z[:300], Xs, idx[:, :6], cols),
+                                   oracle.randomize_cov(Y[:300], Z[:300], Xs, idx[:, :6], cols, use_ref=True), rtol=RTOL, atol=0)
+    G = min(2, core.device_count())
+    np.testing.assert_allclose(core.randomize_cov(Y, Z, Xs, idx, cols, mask=mask, n_gpus=G),
+                               oracle.randomize_cov(Y, Z, Xs, idx, cols, mask=mask), rtol=RTOL, atol=0)
+    # the identity permutation reproduces the column maxima of the plain covariate fit
+    fit = core.lm_fit_cov(Y, Z, Xs)
+    ident = np.arange(n)[:, None]
+    np.testing.assert_allclose(core.randomize_cov(Y, Z, Xs, ident, cols)[0], np.abs(fit[:, cols]).max(axis=0), rtol=1e-12)
+    # error contract: a re-sampled static part that loses rank; an all-zero covariate at a fitted voxel
+    bad = np.zeros((n, 1), dtype=np.int64)
+    with pytest.raises(core.RmincGpuError, match="rank-deficient static design|is zero, so the inverse"):
+        core.randomize_cov(Y, Z, Xs, bad, cols)
+    Z0 = Z.copy()
+    Z0[17] = 0.0
+    with pytest.raises(core.RmincGpuError, match="is zero, so the inverse cannot be computed"):
+        core.randomize_cov(Y, Z0, Xs, idx[:, :2], cols)
 
 
 # ------------------------------------------------------------------ mincFDR (SURVEY 8f-5)
@@ -860,6 +900,12 @@ def test_graph_tfce_matches_oracle(core, oracle):
         core.graph_tfce(M[:-1, 0], adj)
     with pytest.raises(core.RmincGpuError, match="nsteps"):
         core.graph_tfce(M[:, 0], adj, nsteps=1000)
+    # a one-directional edge (a directed igraph, a hand-built list) would give other clusters than the reference, which
+    # follows an edge from its higher-valued end only: refused
+    one_way = [list(x) for x in adj]
+    one_way[17].remove(18)
+    with pytest.raises(core.RmincGpuError, match="not symmetric: vertex 18"):
+        core.graph_tfce(M[:, 0], one_way)
 
 
 def test_randomize_tfce_matches_literal_loop(core, oracle, monkeypatch):

@@ -134,6 +134,9 @@ def test_randomize_fdr_and_stored_routines(R, oracle):
         np.testing.assert_allclose(got, want, rtol=RTOL, atol=0)
     got = R.call("rmincgpu_randomize", Y, X, None, 1.0, 99999999.0, one_based(idx), cols, False, 1)
     np.testing.assert_allclose(got, oracle.randomize(Y, X, idx, [4, 5], two_sided=False), rtol=RTOL, atol=0)
+    Zc = np.asfortranarray(50 + 3 * np.random.default_rng(6).standard_normal(Y.shape))
+    got = R.call("rmincgpu_randomize_cov", Y, Zc, X, mask, 1.0, 99999999.0, one_based(idx[:, :5]), np.array([6, 7], dtype=np.int32), True, 1)
+    np.testing.assert_allclose(got, oracle.randomize_cov(Y, Zc, X, idx[:, :5], [5, 6], mask=mask), rtol=RTOL, atol=0)
     fit = oracle.minc2_model_lm(Y, (10, 12, 9), X, mask=mask)
     q, th = R.call("rmincgpu_fdr", fit[:, 5].copy(), 1, np.array([float(n - 2)]), mask)
     wq, wth, _ = oracle.fdr(fit[:, 5], "t", n - 2, mask=mask)

@@ -66,6 +66,7 @@ def every_routine_call(n=12, V=40):
         "rmincgpu_lm_cov": (Y, Y[:, ::-1].copy(), X[:, :2], None, 1.0, 99999999.0),
         "rmincgpu_lm_stored": (rcall.Raw(U.tobytes(order="F")), 1, float(V), scale, offset, 0.0, 10.0, X, None, 1.0, 99999999.0),
         "rmincgpu_randomize": (Y, X, mask, 1.0, 99999999.0, idx, cols, True, 1),
+        "rmincgpu_randomize_cov": (Y, Y[:, ::-1].copy(), X[:, :2], mask, 1.0, 99999999.0, idx, cols, True, 1),
         "rmincgpu_randomize_stored": (rcall.Raw(U.tobytes(order="F")), 1, float(V), scale, offset, 0.0, 10.0, X, None, 1.0, 99999999.0,
                                       idx, cols, True, 1),
         "rmincgpu_anova": (Y, X, np.array([0, 1, 2], dtype=np.int32), None, 1.0, 99999999.0),
