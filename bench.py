@@ -327,6 +327,8 @@ def config5(args, torch, dist, core, dev, rank, world, local_rank, barrier, desi
     Vs = V5 // shards
     X5 = design_fn(n5, seed=5)
     stream = torch.cuda.current_stream()
+    torch.cuda.empty_cache()                      # blocks cached by the earlier legs would hide the allocations below
+    torch.cuda.reset_peak_memory_stats()
     free0, total = torch.cuda.mem_get_info()
     Ys = gen_Y(torch, Vs, n5, dev, seed=500 + rank)
     outs = torch.empty((2 * p5 + 3, Vs), dtype=torch.float64, device=dev)
@@ -350,7 +352,7 @@ def config5(args, torch, dist, core, dev, rank, world, local_rank, barrier, desi
            "whole_volume_seconds_on_8_gpus": ms * 1e-3 * max(1, shards // world),
            "achieved_gbs_per_gpu": bytes_shard / (ms * 1e-3) / 1e9, "frac": bytes_shard / (ms * 1e-3) / 1e9 / peak,
            "kernel": core.last_fit_variant(), "hbm_used_gb_per_gpu": (free0 - torch.cuda.mem_get_info()[0]) / 1e9,
-           "hbm_total_gb": total / 1e9}
+           "hbm_resident_gb_per_gpu": (Ys.numel() + outs.numel()) * 8 / 1e9, "hbm_total_gb": total / 1e9}
     # end to end from this rank's pinned host shard
     need = Vs * n5 * 8
     if psutil.virtual_memory().available > need * world * 1.2 + (8 << 30):
@@ -397,24 +399,32 @@ def config5(args, torch, dist, core, dev, rank, world, local_rank, barrier, desi
         ou = torch.empty((2 * p5 + 3, V5), dtype=torch.float64, device=dev)
         for _ in range(2):
             core.lm_fit_stored_torch(U, X5, sc, of, slice_len=slice_len, out=ou)
+        variant_u = core.last_fit_variant()
         torch.cuda.synchronize()
-        e0.record(stream)
-        for _ in range(max(1, args.steps // 2)):
+        eu0, eu1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(1, args.steps // 2)
+        tw = time.perf_counter()
+        eu0.record(stream)
+        for _ in range(reps):
             core.lm_fit_stored_torch(U, X5, sc, of, slice_len=slice_len, out=ou)
-        e1.record(stream)
+        eu1.record(stream)
         torch.cuda.synchronize()
-        msu = e0.elapsed_time(e1) / max(1, args.steps // 2)
+        ms_wall = (time.perf_counter() - tw) * 1e3 / reps
+        msu = eu0.elapsed_time(eu1) / reps
         # int64 sanity row: the last 4096 voxels start 15.2e9 samples into U; refit them alone (as a shard that keeps its
         # global slice index) and compare
         tail = core.lm_fit_stored_torch(U[:, V5 - 4096:], X5, sc, of, slice_len=slice_len, v_offset=V5 - 4096)
         torch.cuda.synchronize()
         scl = torch.maximum(tail.abs(), tail.square().mean(dim=1, keepdim=True).sqrt())
         ok = bool(((ou[:, V5 - 4096:] - tail).abs() <= 1e-9 * scl).all()) and bool(torch.isfinite(ou[0]).all())
-        res["whole_volume_uint16_one_gpu"] = {"voxels": V5, "ms": msu, "voxels_per_s": V5 / (msu * 1e-3),
-                                              "hbm_used_gb": (total - torch.cuda.mem_get_info()[0]) / 1e9,
+        bytes_u = V5 * (2 * n5 + 8 * (2 * p5 + 3))
+        res["whole_volume_uint16_one_gpu"] = {"voxels": V5, "ms": msu, "ms_wall_clock": ms_wall, "voxels_per_s": V5 / (msu * 1e-3),
+                                              "achieved_gbs": bytes_u / (msu * 1e-3) / 1e9,
+                                              "hbm_resident_gb": (U.numel() * 2 + ou.numel() * 8) / 1e9,
+                                              "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated() / 1e9,
                                               "first_sample_offset_of_the_checked_rows": int((V5 - 4096)),
                                               "samples_before_the_last_subject_row": int((n5 - 1) * V5),
-                                              "int64_offset_rows_match": ok, "kernel": core.last_fit_variant()}
+                                              "int64_offset_rows_match": ok, "kernel": variant_u}
         del U, ou, sc, of
         torch.cuda.empty_cache()
     barrier()

@@ -312,6 +312,15 @@ int rmg_randomize_tfce_multi(const double *Y, int64_t V, int64_t ldY, int n, con
  */
 int rmg_neighbour_list(int x, int y, int z, int n, int32_t *adj_ptr, int32_t *adj_idx, int64_t capacity, int64_t *nnz,
                        char *err, size_t errlen);
+/*
+ * RMINC:::mesh_area(vertices, triangles) (src/vertex_tfce.cpp:221-257; R/RcppExports.R:52): the per-vertex areas that
+ * vertexTFCE uses as weights when the surface is a bic_obj and no weights are given (R/minc_vertex_statistics.R:752-754).
+ *   vertices   3 x nvertices column-major (bic_obj$vertex_matrix), triangles 3 x ntriangles, 1-based vertex numbers as
+ *              doubles (bic_obj$triangle_matrix);  areas: nvertices doubles.
+ * A literal restatement, including the reference's first cross-product component (d1y*d2z - d1z*d2x).  Host only.
+ */
+int rmg_mesh_area(const double *vertices, int64_t nvertices, const double *triangles, int64_t ntriangles, double *areas,
+                  char *err, size_t errlen);
 
 /*
  * mincTFCE on volumes.  The reference writes the map to a file and shells out to the external `TFCE` program of

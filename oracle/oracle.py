@@ -563,6 +563,33 @@ def neighbour_list(x, y, z, n, use_ref=False):
     return nlist
 
 
+def mesh_area(vertex_matrix, triangle_matrix, use_ref=False):
+    """RMINC:::mesh_area (src/vertex_tfce.cpp:221-257), literally -- including its first cross-product component
+    d1y*d2z - d1z*d2x.  use_ref: the reference's own compiled function (oracle/_ref/librminc_ref_tfce.so)."""
+    global _ref_tfce
+    vm = np.asfortranarray(vertex_matrix, dtype=np.float64)
+    tm = np.asfortranarray(triangle_matrix, dtype=np.float64)
+    nv, nt = vm.shape[1], tm.shape[1]
+    areas = np.zeros(nv)
+    if use_ref:
+        if _ref_tfce is None:
+            _ref_tfce = _load(_REF_TFCE)
+            _ref_tfce.ref_graph_tfce.restype = C.c_int
+        _ref_tfce.ref_mesh_area(vm.ctypes.data_as(C.c_void_p), C.c_int64(nv), tm.ctypes.data_as(C.c_void_p), C.c_int64(nt),
+                                areas.ctypes.data_as(C.c_void_p))
+        return areas
+    for i in range(nt):
+        a, b, c = (int(t) - 1 for t in tm[:, i])
+        d1, d2 = vm[:, b] - vm[:, a], vm[:, c] - vm[:, a]
+        c0 = d1[1] * d2[2] - d1[2] * d2[0]
+        c1 = d1[2] * d2[0] - d1[0] * d2[2]
+        c2 = d1[0] * d2[1] - d1[1] * d2[0]
+        area = .5 * np.sqrt(c0 * c0 + c1 * c1 + c2 * c2)
+        for v in (a, b, c):
+            areas[v] += (1 / 3.0) * area
+    return areas
+
+
 def volume_tfce(x, dims, d=0.1, E=0.5, H=2.0, side="both", connectivity=6, voxel_volume=1.0):
     """mincTFCE on one volume (flat, file dimension order).  PARITY UNPINNED against the reference's mincTFCE, which
     shells out to the external `TFCE` program of minc-stuffs (R/minc_voxel_statistics.R:1225-1237; not in the reference

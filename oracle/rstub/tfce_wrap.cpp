@@ -62,3 +62,13 @@ extern "C" int ref_neighbour_list(int x, int y, int z, int n, int32_t *adj_ptr, 
     }
 }
 
+
+std::vector<double> mesh_area(std::vector<double> vertices, std::vector<double> triangles);
+
+// The reference's own mesh_area (src/vertex_tfce.cpp:221-257).
+extern "C" int ref_mesh_area(const double *vertices, int64_t nv, const double *triangles, int64_t nt, double *areas)
+{
+    const std::vector<double> a = mesh_area(std::vector<double>(vertices, vertices + 3 * nv), std::vector<double>(triangles, triangles + 3 * nt));
+    for (int64_t v = 0; v < nv; ++v) areas[v] = a[v];
+    return 0;
+}

@@ -65,6 +65,7 @@ SIGNATURES = {
                                                                 C.c_int, C.c_int, C.c_void_p, C.c_int] + _ERR),
     "rmg_neighbour_list": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.POINTER(C.c_int64)] + _ERR),
+    "rmg_mesh_area": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p] + _ERR),
     "rmg_volume_tfce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_int, C.c_void_p, C.c_int] + _ERR),
     "rmg_randomize_volume_tfce": (C.c_int, _FIT_HEAD + _MASK + _PERM + [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,

@@ -593,13 +593,57 @@ def anatFDR(buffer: MincMatrix, **kw) -> MincMatrix:
 
 
 # ----------------------------------------------------------------------------- vertexTFCE
+class BicObj:
+    """A triangle mesh as read_obj() returns it (class "bic_obj"): `vertex_matrix` 3 x nvertices coordinates and
+    `triangle_matrix` 3 x ntriangles 1-based vertex numbers.  Reading .obj files is I/O outside this package; the two
+    matrices are what the statistics need."""
+
+    def __init__(self, vertex_matrix, triangle_matrix):
+        self.vertex_matrix = np.asarray(vertex_matrix, dtype=np.float64)
+        self.triangle_matrix = np.asarray(triangle_matrix)
+        if self.vertex_matrix.ndim != 2 or self.vertex_matrix.shape[0] != 3 or self.triangle_matrix.ndim != 2 \
+                or self.triangle_matrix.shape[0] != 3:
+            raise ValueError("vertex_matrix must be 3 x nvertices and triangle_matrix 3 x ntriangles")
+
+
+def obj_to_adjacency(obj: BicObj):
+    """The adjacency list vertexTFCE derives from a bic_obj: obj_to_graph (R/minc_graphs.R:8-24) builds an undirected
+    igraph from the edge list cbind(triangle_matrix[1:2, ], triangle_matrix[2:3], triangle_matrix[c(1, 3), ]) -- as
+    written, the middle term has no comma, so it is the single pair (triangle_matrix[2], triangle_matrix[3]), the second
+    and third vertex of the FIRST triangle, and the 2-3 edges of the other triangles enter only where a neighbouring
+    triangle lists them as its 1-2 or 1-3 edge -- and vertexTFCE takes as_adj_list(graph) - 1
+    (R/minc_vertex_statistics.R:776-781).  Restated literally; neighbours are listed once (igraph repeats a neighbour per
+    parallel edge, which changes no cluster)."""
+    tm = np.asarray(obj.triangle_matrix).astype(np.int64)
+    nv = obj.vertex_matrix.shape[1]
+    edges = np.concatenate([tm[0:2, :], tm.reshape(-1, order="F")[1:3].reshape(2, 1), tm[[0, 2], :]], axis=1) - 1
+    if edges.size and (edges.min() < 0 or edges.max() >= nv):
+        raise ValueError("triangle_matrix refers to a vertex that vertex_matrix does not hold")
+    nbrs = [set() for _ in range(nv)]
+    for a, b in edges.T:
+        nbrs[int(a)].add(int(b))
+        nbrs[int(b)].add(int(a))
+    return [np.array(sorted(s), dtype=np.int32) for s in nbrs]
+
+
+def _surface_and_weights(surface, weights):
+    """vertexTFCE.numeric's preamble (R/minc_vertex_statistics.R:751-781): a bic_obj gives its mesh areas as default
+    weights and its graph as the adjacency."""
+    if isinstance(surface, BicObj):
+        if weights is None:
+            weights = core.mesh_area(surface.vertex_matrix, surface.triangle_matrix)
+        surface = obj_to_adjacency(surface)
+    return surface, weights
+
+
 def vertexTFCE(x, surface, R: int = 500, alternative: str = "two.sided", E: float = 0.5, H: float = 2.0, nsteps: int = 100,
                weights=None, side: str = "both", replace: bool = False, parallel=None, seed=None, idx=None,
                device: int = 0, column: int = 1):
     """Threshold-free cluster enhancement on a surface graph (R/minc_vertex_statistics.R:731-990).
 
-    `surface`: the 0-based adjacency list form vertexTFCE accepts (one neighbour array per vertex), or a CSR pair
-    (ptr, idx); mesh objects / igraph are outside this package.  Dispatch as in the reference:
+    `surface`: the 0-based adjacency list form vertexTFCE accepts (one neighbour array per vertex), a CSR pair
+    (ptr, idx), or a BicObj mesh (then the default weights are its vertex areas, mesh_area); igraph objects and .obj
+    files are outside this package.  Dispatch as in the reference:
       * numeric vector -> enhanced vector (vertexTFCE.numeric)
       * plain matrix   -> every column enhanced (vertexTFCE.matrix)
       * file name(s)   -> read with vertexTable(column=) then as above (vertexTFCE.character)
@@ -607,6 +651,7 @@ def vertexTFCE(x, surface, R: int = 500, alternative: str = "two.sided", E: floa
         c("vertexTFCE_randomization","vertex_randomization") (vertexTFCE.vertexLm)."""
     if side not in core.TFCE_SIDES:
         raise ValueError("'arg' should be one of 'both', 'positive', 'negative'")
+    surface, weights = _surface_and_weights(surface, weights)
     if isinstance(x, MincMatrix) and "vertexLm" in x.r_class:
         if alternative not in ("two.sided", "greater"):
             raise ValueError("'arg' should be one of 'two.sided', 'greater'")

@@ -387,6 +387,19 @@ def randomize_tfce(Y, X, idx, cols, adjacency, two_sided=True, E=0.5, H=2.0, nst
     return dist
 
 
+def mesh_area(vertex_matrix, triangle_matrix):
+    """RMINC:::mesh_area (src/vertex_tfce.cpp:221-257): per-vertex areas of a triangle mesh -- vertexTFCE's default weights
+    for a bic_obj surface.  vertex_matrix 3 x nv, triangle_matrix 3 x nt with 1-based vertex numbers.  Host only."""
+    vm = np.asfortranarray(vertex_matrix, dtype=np.float64)
+    tm = np.asfortranarray(triangle_matrix, dtype=np.float64)
+    if vm.ndim != 2 or vm.shape[0] != 3 or tm.ndim != 2 or tm.shape[0] != 3:
+        raise ValueError("vertex_matrix must be 3 x nvertices and triangle_matrix 3 x ntriangles")
+    areas = np.empty(vm.shape[1])
+    err = _lib.errbuf()
+    _lib.check(_lib.load().rmg_mesh_area(vm.ctypes.data, vm.shape[1], tm.ctypes.data, tm.shape[1], areas.ctypes.data, err, len(err)), err)
+    return areas
+
+
 def neighbour_list(x, y, z, n=6):
     """RMINC:::neighbour_list (src/vertex_tfce.cpp:178-214) as a CSR pair (ptr, idx) that vertexTFCE / graph_tfce take:
     the adjacency of an x*y*z grid, vertex = k*y*x + j*x + i.  Host only."""

@@ -427,6 +427,7 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
 {
     const size_t es = !pk ? sizeof(double) : pk->dtype == kStoredU16 ? 2 : 4;   // bytes per sample of Y
     const char *Yb = reinterpret_cast<const char *>(Y);
+    NvtxPhase nv("rmg fit (host buffers): chunked H2D -> kernel -> D2H");
     // Z != nullptr: voxel-wise covariate design [X | z_v]; X is the static part (lm_cov.cu)
     int rc = check_fit_args(Y, V, ldY, n, X, p, out, ldOut, err, errlen);
     if (rc) return rc;

@@ -1,6 +1,7 @@
 // capi_common.hpp -- helpers shared by the C-ABI translation units.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <atomic>
@@ -25,6 +26,29 @@ namespace rmg {
 extern std::atomic<int64_t> g_launch_count;
 extern thread_local double g_last_kernel_ms;
 extern thread_local int g_last_fit_variant;
+
+// NVTX ranges for a profiler timeline: one range for the call, one nested range per phase.  Header-only
+// NVTX 3: without an attached tool every call is a no-op through a null function pointer.
+struct NvtxPhase {
+    int depth = 0;
+    explicit NvtxPhase(const char *call)
+    {
+        nvtxRangePushA(call);
+        depth = 1;
+    }
+    void next(const char *phase)
+    {
+        if (depth == 2) nvtxRangePop();
+        nvtxRangePushA(phase);
+        depth = 2;
+    }
+    ~NvtxPhase()
+    {
+        while (depth-- > 0) nvtxRangePop();
+    }
+    NvtxPhase(const NvtxPhase &) = delete;
+    NvtxPhase &operator=(const NvtxPhase &) = delete;
+};
 
 inline int fail(char *err, size_t errlen, int code, const char *fmt, ...)
 {

@@ -208,7 +208,10 @@ int randomize_shards(std::vector<PermShard> &S, int n, int p, const double *X, d
     if (R == 0 || ncols == 0) return rc;
     const bool timing = std::getenv("RMG_TIMING") != nullptr;
     double t_mark = now_ms();
-    auto lap = [&](const char *what) {
+    NvtxPhase nv("rmg randomize");
+    nv.next("factor R designs");
+    auto lap = [&](const char *what, const char *next_phase) {
+        nv.next(next_phase);
         if (!timing) return;
         const double t = now_ms();
         std::fprintf(stderr, "[rmg perm] %-34s %8.3f ms\n", what, t - t_mark);
@@ -216,7 +219,7 @@ int randomize_shards(std::vector<PermShard> &S, int n, int p, const double *X, d
     };
     PermSet pd;
     if ((rc = factor_permutations(X, n, p, idx, R, pd, err, errlen))) return rc;
-    lap("factor R designs");
+    lap("factor R designs", "plan + per-device workspaces");
 
     const int G = (int)S.size();
     const int nk = R * ncols;
@@ -280,7 +283,7 @@ int randomize_shards(std::vector<PermShard> &S, int n, int p, const double *X, d
                 begun[g] = 1;
                 launches[g] += l;
             }
-            lap("plan + per-device workspaces");
+            lap("plan + per-device workspaces", "prepass; pack + upload + launch per batch");
             // per-voxel sums of block `blk` of shard g, once it has landed (skipped when the dataset already holds them)
             auto prepass = [&](int g, size_t blk) -> cudaError_t {
                 PermShard &s = S[g];
@@ -313,7 +316,7 @@ int randomize_shards(std::vector<PermShard> &S, int n, int p, const double *X, d
                     launches[g] += l;
                 }
             }
-            lap("pack + upload + block-0 launches");
+            lap("pack + upload + block-0 launches", "launches of the later voxel blocks; finalize");
             // later blocks: the whole operand is on the device, one launch per block over every permutation tile
             size_t max_blocks = 0;
             for (int g = 0; g < G; ++g) max_blocks = std::max(max_blocks, S[g].blk_v0.size());
@@ -368,7 +371,7 @@ int randomize_shards(std::vector<PermShard> &S, int n, int p, const double *X, d
             RMG_CUDA(cudaEventRecord(e1[g], s.st));
             if (s.host_part) RMG_CUDA(cudaMemcpyAsync(s.host_part, dst, (size_t)nk * sizeof(double), cudaMemcpyDeviceToHost, s.st));
         }
-        lap("remaining launches queued");
+        lap("remaining launches queued", "wait for the devices");
         if (sync_host) {
             double ms_max = 0.0;
             for (int g = 0; g < G; ++g) {
@@ -379,7 +382,7 @@ int randomize_shards(std::vector<PermShard> &S, int n, int p, const double *X, d
                 if (cudaEventElapsedTime(&ms, e0[g], e1[g]) == cudaSuccess) ms_max = std::max(ms_max, (double)ms);
             }
             g_last_kernel_ms = ms_max;
-            lap("GPU work (sync)");
+            lap("GPU work (sync)", "release");
         }
     }
 cleanup:
@@ -464,6 +467,7 @@ int dataset_create(const void *Yv, const StoredSpec *pk, int64_t V, int64_t ldY,
                    double mask_hi, const int *devices, int G, rmg_dataset **out, char *err, size_t errlen)
 {
     int rc = RMG_OK;
+    NvtxPhase nv("rmg dataset upload (queued per voxel block)");
     *out = nullptr;
     rmg_dataset *ds = new rmg_dataset();
     ds->V = V;
@@ -636,6 +640,7 @@ int dataset_fit(rmg_dataset *ds, const double *X, int p, const int32_t *asgn, do
     if (out && ldOut < ds->V) return fail(err, errlen, RMG_ERR_INVALID, "leading dimension smaller than V");
     std::lock_guard<std::mutex> lk(ds->mu);
     int rc = RMG_OK;
+    NvtxPhase nv("rmg dataset fit (resident shards)");
     int ncol = 2 * p + 3;
     double ms_max = 0.0;
     std::vector<cudaEvent_t> e0(ds->G, nullptr), e1(ds->G, nullptr);

@@ -456,11 +456,12 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
             const double2 *tabs = reinterpret_cast<const double2 *>(st + DATA_B);
             const double *q = sQ + (size_t)it * NJ * KP;
             const int nvalid = min(NJ, n - it * NJ);      // rows >= n of the last box are TMA zero-fill: skipped
-            auto run = [&](auto same_tag) {
+            auto run = [&](auto same_tag, auto full_tag) {
                 constexpr bool SAME = decltype(same_tag)::value;
+                constexpr bool FULL = decltype(full_tag)::value;     // all NJ rows real: no per-row test in the hot loop
 #pragma unroll
                 for (int jj = 0; jj < NJ; ++jj) {
-                    if (jj < nvalid) {
+                    if (FULL || jj < nvalid) {
                         double y[VPT];
                         load_convert_smem<T, VPT>(mine + jj * BOXW, y, cm);
                         double2 so0 = make_double2(1.0, 0.0), so1 = so0;
@@ -484,8 +485,12 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
                     }
                 }
             };
-            if (same) run(std::true_type{});
-            else run(std::false_type{});
+            if (same) {
+                if (nvalid == NJ) run(std::true_type{}, std::true_type{});
+                else run(std::true_type{}, std::false_type{});
+            } else {
+                run(std::false_type{}, std::false_type{});
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }

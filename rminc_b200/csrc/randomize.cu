@@ -91,10 +91,21 @@ static int randomize_tfce_impl(const double *Y, int64_t V, int64_t ldY, int n, c
     if (V > 0x7fffffffLL) return fail(err, errlen, RMG_ERR_INVALID, "bad graph arguments");
     if (side < 0 || side > 2 || nsteps < 1 || nsteps > 253) return fail(err, errlen, RMG_ERR_INVALID, "bad TFCE arguments");
     if ((rc = check_csr(hg, V, err, errlen))) return rc;
+    NvtxPhase nv("rmg randomize + TFCE");
+    nv.next("factor R designs");
+    const bool timing = std::getenv("RMG_TIMING") != nullptr;
+    auto t_mark = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        const auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[rmg tfce] %-44s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_mark).count());
+        t_mark = t;
+    };
     PermSet pd;
     if ((rc = factor_permutations(X, n, p, idx, R, pd, err, errlen))) return rc;
     if ((rc = select_device(device, err, errlen))) return rc;
     if (R == 0 || ncols == 0 || V == 0) return RMG_OK;
+    lap("argument checks + factor R designs");
 
     cudaStream_t st = nullptr;
     const int64_t ldd = std::max<int64_t>(2, (V + 1) & ~int64_t(1));
@@ -118,6 +129,7 @@ static int randomize_tfce_impl(const double *Y, int64_t V, int64_t ldY, int n, c
         const int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)R, (size_t(8) << 30) / (per_map * ncols)));
         const size_t qstride = make_qt(pd.base, KP).size();
         RMG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        nv.next("graph + workspaces + upload of Y");
         if ((rc = upload_graph(hg, V, st, g, &dptr, &didx, &dw, err, errlen))) goto cleanup;
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dY), (size_t)ldd * n * 8, st));
         RMG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)ldd * ncol_total * 8, st));
@@ -143,6 +155,11 @@ static int randomize_tfce_impl(const double *Y, int64_t V, int64_t ldY, int n, c
         }
         keys_init_kernel<<<(R * ncols + 255) / 256, 256, 0, st>>>(keys, R * ncols);
         ++launches;
+        if (timing) {
+            RMG_CUDA(cudaStreamSynchronize(st));
+            lap("graph, workspaces, Y on the device");
+        }
+        nv.next("refits + enhancement per batch of permutations");
         std::vector<DevDesign> hdd(B);
         std::vector<double> hqt((size_t)B * qstride);
         const unsigned vb = (unsigned)((V + 255) / 256);
@@ -179,6 +196,7 @@ static int randomize_tfce_impl(const double *Y, int64_t V, int64_t ldY, int n, c
         ++launches;
         RMG_CUDA(cudaMemcpyAsync(dist, dD, (size_t)R * ncols * 8, cudaMemcpyDeviceToHost, st));
         RMG_CUDA(cudaStreamSynchronize(st));
+        lap("refits + TFCE + maxima (all batches)");
     }
 cleanup:
     g_launch_count += launches;

@@ -507,6 +507,15 @@ def test_vertexTFCE(api, tmp_path, oracle):
         api.vertexRandomize(np.zeros((3, 3)))
     with pytest.raises(ValueError, match="should be one of"):
         api.vertexTFCE(t, adj, side="sideways")
+    # a bic_obj surface: default weights = mesh_area, adjacency = obj_to_graph's edge list (R/minc_vertex_statistics.R:751-781)
+    from test_oracle import _icosphere
+    vm, tm = _icosphere()
+    obj = api.BicObj(vm, tm)
+    xm = rng.standard_normal(vm.shape[1])
+    ptr_o, idx_o = oracle.adjacency_csr(api.obj_to_adjacency(obj))
+    want_o = oracle.graph_tfce(xm, ptr_o, idx_o, weights=oracle.mesh_area(vm, tm))
+    assert api.vertexTFCE(xm, obj) == pytest.approx(want_o, rel=1e-10, abs=1e-14)
+    assert api.vertexTFCE(xm, obj, weights=np.ones(vm.shape[1])) == pytest.approx(oracle.graph_tfce(xm, ptr_o, idx_o), rel=1e-10, abs=1e-14)
 
 
 def test_mincTFCE(api, study, oracle):

@@ -440,6 +440,53 @@ def test_smoothing_spline_for_pi0():
     assert api.smooth_spline_at_last_knot(lam, y, 19.0) == pytest.approx(y[-1], rel=1e-6)
 
 
+def _icosphere():
+    """A closed triangle mesh (icosahedron, each face split once): 42 vertices, 80 consistently oriented triangles."""
+    t = (1 + 5 ** 0.5) / 2
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1),
+         (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    verts = [np.array(p, float) / np.linalg.norm(p) for p in v]
+    mid, faces = {}, []
+
+    def m(a, b):
+        k = (min(a, b), max(a, b))
+        if k not in mid:
+            p = verts[a] + verts[b]
+            verts.append(p / np.linalg.norm(p))
+            mid[k] = len(verts) - 1
+        return mid[k]
+    for a, b, c in f:
+        ab, bc, ca = m(a, b), m(b, c), m(c, a)
+        faces += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+    return np.array(verts).T * [[1.0], [1.3], [0.8]], np.array(faces).T + 1
+
+
+def test_mesh_area_is_the_reference_object_code(oracle, lib):
+    """RMINC:::mesh_area (src/vertex_tfce.cpp:221-257), vertexTFCE's default weights for a bic_obj surface: the product's
+    host routine and the restatement equal the reference's compiled function bit for bit -- including its first
+    cross-product component, written d1y*d2z - d1z*d2x."""
+    from rminc_b200 import api, core
+    vm, tm = _icosphere()
+    rng = np.random.default_rng(3)
+    vm = vm + 0.01 * rng.standard_normal(vm.shape)
+    got = core.mesh_area(vm, tm)
+    assert np.array_equal(got, oracle.mesh_area(vm, tm))
+    if oracle.have_ref_tfce():
+        assert np.array_equal(got, oracle.mesh_area(vm, tm, use_ref=True))
+    # the literal formula is NOT the true area (true: |d1 x d2| / 2); the quirk is restated, not repaired
+    d1, d2 = vm[:, tm[1] - 1] - vm[:, tm[0] - 1], vm[:, tm[2] - 1] - vm[:, tm[0] - 1]
+    assert not np.allclose(got.sum(), 0.5 * np.linalg.norm(np.cross(d1.T, d2.T), axis=1).sum(), rtol=1e-3)
+    with pytest.raises(core.RmincGpuError, match="refers to vertex"):
+        core.mesh_area(vm, np.array([[1], [2], [99]]))
+    # obj_to_graph's edge list as written: every 1-2 and 1-3 edge, plus the 2-3 edge of the first triangle only
+    adj = api.obj_to_adjacency(api.BicObj(vm, tm))
+    edges = {tuple(sorted(e)) for t in (tm - 1).T for e in ((t[0], t[1]), (t[0], t[2]))} | {tuple(sorted((tm[1, 0] - 1, tm[2, 0] - 1)))}
+    assert {(a, int(b)) for a, nb in enumerate(adj) for b in nb if a < b} == edges
+    assert all(a in adj[int(b)] for a, nb in enumerate(adj) for b in nb)          # symmetric, as rmg_graph_tfce requires
+
+
 def test_graph_tfce_restatement(oracle):
     """graph_tfce_wqu / graph_tfce (src/vertex_tfce.cpp:92-157): equals the reference's own object code bit for bit,
     and a case small enough to enhance by hand."""

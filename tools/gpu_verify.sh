@@ -1,5 +1,5 @@
 #!/bin/bash
-# Short gpurun call: GPU test suite, smoke, and compute-sanitizer (memcheck) over smoke().
+# Short gpurun call: GPU test suite and smoke.  (compute-sanitizer is refused by this GPU pool, so no memcheck step.)
 set -u
 mkdir -p gpurun_out
 exec > >(tee gpurun_out/verify.log) 2>&1
@@ -8,7 +8,4 @@ echo "=== pytest -m gpu"
 timeout -k 10 900 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -15
 echo "=== smoke"
 timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke()"
-echo "=== compute-sanitizer memcheck (smoke)"
-timeout -k 10 600 compute-sanitizer --tool memcheck --log-file gpurun_out/sanitizer_memcheck.log python -c "import __graft_entry__ as g; g.smoke()"
-echo "rc=$?"; tail -5 gpurun_out/sanitizer_memcheck.log
 echo "=== done"
