@@ -557,7 +557,8 @@ cudaError_t perm_pack_plan(const PermSet &ps, int n, int p, const int32_t *hcols
     pk.n_pt = (R + pk.perms_per_cta - 1) / pk.perms_per_cta;
     pk.n_kc = (n + pk.KC - 1) / pk.KC;
     pk.tiles_per_batch = std::max(1, 256 / pk.perms_per_cta);
-    pk.nbatch = (pk.n_pt + pk.tiles_per_batch - 1) / pk.tiles_per_batch;
+    pk.first_tiles = 1;
+    pk.nbatch = pk.n_pt <= pk.first_tiles ? 1 : 1 + (pk.n_pt - pk.first_tiles + pk.tiles_per_batch - 1) / pk.tiles_per_batch;
     pk.apack_doubles = (size_t)pk.n_pt * pk.n_kc * pk.A_CHUNK;
     // pinned staging (leased from the process-wide pool: the DMA engines of every device read it directly)
     const size_t bytesA = (pk.apack_doubles * 8 + 255) & ~size_t(255);
@@ -585,7 +586,7 @@ void perm_pack_batch(const PermSet &ps, PermPack &pk, int b)
 {
     const int n = pk.n, p = pk.p, INV = pk.INV, KG = pk.KG, PG = pk.PG, WM = pk.WM, KC = pk.KC, A_CHUNK = pk.A_CHUNK;
     const int perms_per_cta = pk.perms_per_cta, n_kc = pk.n_kc;
-    const int pt0 = b * pk.tiles_per_batch, pt1 = std::min(pk.n_pt, pt0 + pk.tiles_per_batch);
+    const int pt0 = pk.batch_pt0(b), pt1 = pk.batch_pt1(b);
     const int r0 = pk.batch_r0(b), r1 = pk.batch_r1(b);
     double *Apack = pk.hA;
     PermConst *pc = pk.hpc;
@@ -695,7 +696,7 @@ cudaError_t perm_dev_prepass(PermDevice &d, const PermGemmArgs &a, int64_t v0, i
 
 cudaError_t perm_dev_upload(PermDevice &d, const PermPack &pk, int b)
 {
-    const int pt0 = b * pk.tiles_per_batch, pt1 = std::min(pk.n_pt, pt0 + pk.tiles_per_batch);
+    const int pt0 = pk.batch_pt0(b), pt1 = pk.batch_pt1(b);
     const int r0 = pk.batch_r0(b), r1 = pk.batch_r1(b);
     const size_t offA = (size_t)pt0 * pk.n_kc * pk.A_CHUNK, nA = (size_t)(pt1 - pt0) * pk.n_kc * pk.A_CHUNK;
     static_assert(sizeof(PermConst) % 16 == 0, "PermConst is fetched in 16-byte pieces");
@@ -739,7 +740,7 @@ cudaError_t perm_dev_launch(PermDevice &d, const PermPack &pk, int b0, int b1, i
     }
     for (int b = b0; b < b1; ++b)
         if ((e = cudaStreamWaitEvent(d.st, d.ev[b], 0)) != cudaSuccess) return e;
-    const int pt0 = b0 * pk.tiles_per_batch, pt1 = std::min(pk.n_pt, b1 * pk.tiles_per_batch);
+    const int pt0 = pk.batch_pt0(b0), pt1 = pk.batch_pt1(b1 - 1);
     const int r0 = pk.batch_r0(b0), r1 = pk.batch_r1(b1 - 1);
     PermKernelParams Pb = d.P;
     Pb.Y = d.P.Y + v0;

@@ -161,7 +161,7 @@ struct PermPre {
 struct PermPack {
     int R = 0, n = 0, p = 0;
     int INV = 0, KG = 0, PG = 0, WM = 0, KC = 16, WARPS_M = 4, A_CHUNK = 0, perms_per_cta = 0, n_pt = 0, n_kc = 0;
-    int tiles_per_batch = 1, nbatch = 0;
+    int tiles_per_batch = 1, first_tiles = 1, nbatch = 0;
     int shift = 0;                   // every permuted design spans the constant: voxels are centred on their first sample
     std::vector<double> c0;          // [R] constant value of Q_r[:, 0] (INV)
     size_t apack_doubles = 0;
@@ -171,8 +171,12 @@ struct PermPack {
     int ncols = 0, epi_stride = 0;
     int tcol[kPermMaxCols] = {0};    // coefficient index of each requested t-column
     void *lease = nullptr;           // pinned-pool lease behind hA / hpc (perm_pack_release)
-    int batch_r0(int b) const { return std::min(R, b * tiles_per_batch * perms_per_cta); }
-    int batch_r1(int b) const { return std::min(R, (b + 1) * tiles_per_batch * perms_per_cta); }
+    // Batch 0 is a single permutation tile, so that the first launch waits for the packing of 8 * PG * 4 permutations
+    // only (the host packs the next, full-size batch behind it); batches b >= 1 hold tiles_per_batch tiles.
+    int batch_pt0(int b) const { return b <= 0 ? 0 : std::min(n_pt, first_tiles + (b - 1) * tiles_per_batch); }
+    int batch_pt1(int b) const { return std::min(n_pt, first_tiles + b * tiles_per_batch); }
+    int batch_r0(int b) const { return std::min(R, batch_pt0(b) * perms_per_cta); }
+    int batch_r1(int b) const { return std::min(R, batch_pt1(b) * perms_per_cta); }
 };
 
 cudaError_t perm_pack_plan(const PermSet &ps, int n, int p, const int32_t *hcols, int ncols, PermPack &pk);
