@@ -660,8 +660,23 @@ def run_gpu_arm(args):
         c0 = time.perf_counter()
         O.graph_tfce(tmap, aptr, aidx)
         cpu_ms = (time.perf_counter() - c0) * 1e3
+        # the same call with Y in page-locked memory (the library's allocator): what is left is refits + enhancement
+        from rminc_b200 import _lib as _L
+        flat, hptr = pinned_numpy(_L.load(), (Vt * nv,), np.float64)
+        Yp = flat.reshape((Vt, nv), order="F")
+        Yp[...] = Yt_h
+        core.randomize_tfce(Yp, Xt, idx_t[:, :4], cols_t, (aptr, aidx))
+        t0 = time.perf_counter()
+        dp_ = core.randomize_tfce(Yp, Xt, idx_t, cols_t, (aptr, aidx))
+        sec_pinned = time.perf_counter() - t0
+        # (not bit-equal: which root a concurrent hook attaches under decides the rounding of the offset sums)
+        assert np.allclose(dp_, dt_, rtol=1e-10, atol=0), "TFCE randomisation: pinned and pageable input disagree"
+        del Yp, flat
+        _L.load().rmg_host_free(hptr)
         tfce = {"workload": f"vertexTFCE.vertexLm randomisation: {Vt} vertices x {nv} subjects, {pv} t columns, nsteps 100, both sides",
                 "R": Rt, "seconds": sec, "perms_per_s": Rt / sec, "maps_per_s": Rt * pv / sec,
+                "host_cores": os.cpu_count(), "input": f"pageable host memory, {Vt * nv * 8 / 1e6:.0f} MB (an R session's heap)",
+                "from_pinned": {"seconds": sec_pinned, "perms_per_s": Rt / sec_pinned},
                 "cpu_restatement_ms_per_map": cpu_ms, "speedup_vs_one_core": (cpu_ms * 1e-3 * Rt * pv) / sec,
                 "timing": "wall clock around the host-buffer C-ABI call (upload, refits, enhancement, maxima, download)"}
         del Yt_h
