@@ -622,8 +622,11 @@ def run_gpu_arm(args):
         stored = {"workload": "the same fit on uint16 voxels + per-slice real ranges (180 slices x 500 files)",
                   "ms_per_step": ms, "voxels_per_s": world * V / (ms * 1e-3), "achieved_gbs": sb / (ms * 1e-3) / 1e9,
                   "frac_of_hbm_peak": sb / (ms * 1e-3) / 1e9 / measured_hbm_peak()[0],
-                  "fp64_ops_per_s": V * n * (5.0 + p) / (ms * 1e-3), "kernel": core.last_fit_variant(),
-                  "bound": "FP64 pipe co-limits: (5+p) FP64 operations per 2-byte sample"}
+                  "fp64_ops_per_s": V * n * (3.0 + p) / (ms * 1e-3), "kernel": core.last_fit_variant(),
+                  # scalar FP64 issue limit measured by tools/dfma_bench.cu: one warp-wide DFMA per 2.2 cycles and scheduler
+                  "fp64_issue_floor_ms": V * n * (3.0 + p) / (148 * 4 * 32 / 2.2 * 1.965e9) * 1e3,
+                  "bound": "FP64 pipe co-limits: (3+p) FP64 operations per 2-byte sample (one FMA to expand, shift, "
+                           "square, p projections); RMG_STORED_EXACT=1 (the reader's three roundings): (5+p)"}
         # the stored-type fit equals the double fit of the expanded samples
         Ye = ((Ut[:, :4096].to(torch.float64) - 0.0) * sc_t[:, :1]) + of_t[:, :1]
         ref = core.lm_fit_torch(Ye, X)

@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(deps_time(path), os.path.getmtime(__file__)):
             continue
-        cmd = [nvcc(), *NVCC_FLAGS, "-c", path, "-o", obj]
+        cmd = [nvcc(), *NVCC_FLAGS, *os.environ.get("RMG_NVCC_EXTRA", "").split(), "-c", path, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)

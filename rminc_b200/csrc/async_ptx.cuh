@@ -20,8 +20,28 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// The wait carries a suspend-time hint: without one the hardware hands the thread back after a few dozen cycles and a
+// waiting warp -- above all a producer lane whose ring is full -- re-issues YIELD / TRYWAIT / BRA continuously, taking
+// issue slots from the consumer warps of its scheduler (a quarter of all issued warp-instructions of the stored-type fit
+// in profiles/r02m_stored_fold_source_summary.md).  A suspended thread still resumes as soon as the phase completes.
+#ifndef RMG_MBAR_HINT_NS
+#define RMG_MBAR_HINT_NS 20000
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
+#if RMG_MBAR_HINT_NS > 0
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"((uint32_t)RMG_MBAR_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -33,6 +53,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+#endif
 }
 __device__ __forceinline__ void fence_barrier_init()
 {

@@ -337,6 +337,7 @@ LmPlan plan_from_env(int device)
     if (const char *s = std::getenv("RMG_TMA_CFG")) plan.tma_cfg = std::atoi(s);
     if (const char *s = std::getenv("RMG_TMA_QSTREAM")) plan.q_stream = std::atoi(s);
     if (const char *s = std::getenv("RMG_NO_COMPACT")) plan.no_compact = std::atoi(s);
+    if (const char *s = std::getenv("RMG_STORED_EXACT")) plan.stored_exact = std::atoi(s);
     return plan;
 }
 

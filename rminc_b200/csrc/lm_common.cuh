@@ -33,8 +33,9 @@ template <int KP>
 struct SmemDesign {
     double q1[KP];
     double ct[KP];
+    double isct[KP];        // 1 / sqrt(ct): t_i = beta_i * isct_i * sqrt(rdf / rss)
     double Rinv[KP * KP];   // row-major KP x KP
-    double gap, inv_n, rdf, pm1, loglik_c, mhalf_n, loglik_add;
+    double gap, inv_n, rdf, pm1, inv_pm1, loglik_c, mhalf_n, loglik_add;
     int n, p, k, shift;
     int mode, nterms, ncol_out, pad_;
     int term[KP];
@@ -48,12 +49,13 @@ __device__ __forceinline__ void load_design_to_smem(SmemDesign<KP> &s, const Dev
     for (int i = tid; i < KP; i += nthreads) {
         s.q1[i] = d->q1[i];
         s.ct[i] = d->ct[i];
+        s.isct[i] = 1.0 / sqrt(d->ct[i]);
         s.term[i] = d->term[i];
     }
     for (int i = tid; i < KP + 1; i += nthreads) s.inv_df[i] = d->inv_df[i];
     for (int i = tid; i < KP * KP; i += nthreads) s.Rinv[i] = d->Rinv[(i / KP) * kMaxPDev + (i % KP)];
     if (tid == 0) {
-        s.gap = d->gap; s.inv_n = d->inv_n; s.rdf = d->rdf; s.pm1 = d->pm1;
+        s.gap = d->gap; s.inv_n = d->inv_n; s.rdf = d->rdf; s.pm1 = d->pm1; s.inv_pm1 = 1.0 / d->pm1;
         s.loglik_c = d->loglik_c; s.mhalf_n = d->mhalf_n; s.loglik_add = d->loglik_add;
         s.n = d->n; s.p = d->p; s.k = d->k; s.shift = d->shift;
         s.mode = d->mode; s.nterms = d->nterms; s.ncol_out = d->ncol_out;
@@ -110,8 +112,8 @@ __device__ __forceinline__ void finish_voxel(const VoxelSums<KP> &v, double rss,
                                              int64_t ld)
 {
     const int p = d.p;
-    const double resvar = rss / d.rdf;                       // :537
     if (d.mode == 1) {
+        const double resvar = rss / d.rdf;                   // :537
         // voxel_anova: F_t = (sum of effects^2 over the term's columns / df_t) / (ssr / (n-p))
         double e2[KP];
 #pragma unroll
@@ -127,7 +129,14 @@ __device__ __forceinline__ void finish_voxel(const VoxelSums<KP> &v, double rss,
         }
         return;
     }
-    out[0] = (mss / d.pm1) / resvar;                         // :542
+    // One division and one square root per voxel instead of p + 2 and p:  with r = rdf / rss = 1 / resvar,
+    //   F = (mss / (p-1)) / resvar = mss * (1/(p-1)) * r            (:542)
+    //   t_i = beta_i / sqrt(ct_i * resvar) = beta_i * (1/sqrt(ct_i)) * sqrt(r)   (:563, :568)
+    // The IEEE classes of the degenerate cases are those of the reference's expressions: rss = 0 gives r = Inf, hence
+    // F = Inf or NaN (mss = 0) and t = +-Inf or NaN (beta = 0); rdf = 0 gives r = 0, hence F = 0 and t = 0.
+    const double r = d.rdf / rss;
+    const double sr = sqrt(r);
+    out[0] = (mss * d.inv_pm1) * r;
     out[ld] = mss / (mss + rss);                             // :572
     out[(int64_t)(2 * p + 2) * ld] = d.mhalf_n * (d.loglik_c + log(rss)) + d.loglik_add;  // :527
     // un-shift: e(y) = e(y - y0) + y0 * Q'1
@@ -141,7 +150,7 @@ __device__ __forceinline__ void finish_voxel(const VoxelSums<KP> &v, double rss,
 #pragma unroll
             for (int j = i; j < KP; ++j) b = fma(d.Rinv[i * KP + j], e[j], b);
             out[(int64_t)(2 + i) * ld] = b;                            // beta, pivoted order
-            out[(int64_t)(2 + p + i) * ld] = b / sqrt(d.ct[i] * resvar);  // :563, :568
+            out[(int64_t)(2 + p + i) * ld] = (b * d.isct[i]) * sr;
         }
     }
 }
@@ -158,8 +167,8 @@ __device__ __forceinline__ void finish_pair(const VoxelSums<KP> &a, double rssa,
     auto put = [&](int c, double x, double y) {
         *reinterpret_cast<double2 *>(out + (int64_t)c * ld) = make_double2(oka ? x : 0.0, okb ? y : 0.0);
     };
-    const double rva = rssa / d.rdf, rvb = rssb / d.rdf;
     if (d.mode == 1) {
+        const double rva = rssa / d.rdf, rvb = rssb / d.rdf;
         double ea2[KP], eb2[KP];
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
@@ -178,7 +187,9 @@ __device__ __forceinline__ void finish_pair(const VoxelSums<KP> &a, double rssa,
         }
         return;
     }
-    put(0, (mssa / d.pm1) / rva, (mssb / d.pm1) / rvb);
+    const double ra = d.rdf / rssa, rb = d.rdf / rssb;       // see finish_voxel
+    const double sra = sqrt(ra), srb = sqrt(rb);
+    put(0, (mssa * d.inv_pm1) * ra, (mssb * d.inv_pm1) * rb);
     put(1, mssa / (mssa + rssa), mssb / (mssb + rssb));
     put(2 * p + 2, d.mhalf_n * (d.loglik_c + log(rssa)) + d.loglik_add, d.mhalf_n * (d.loglik_c + log(rssb)) + d.loglik_add);
     double ea[KP], eb[KP];
@@ -197,7 +208,7 @@ __device__ __forceinline__ void finish_pair(const VoxelSums<KP> &a, double rssa,
                 bb = fma(d.Rinv[i * KP + j], eb[j], bb);
             }
             put(2 + i, ba, bb);
-            put(2 + p + i, ba / sqrt(d.ct[i] * rva), bb / sqrt(d.ct[i] * rvb));
+            put(2 + p + i, (ba * d.isct[i]) * sra, (bb * d.isct[i]) * srb);
         }
     }
 }

@@ -37,6 +37,7 @@ struct LmPlan {
     int tma_cfg = -1;    // TMA path: tile-shape variant (-1 = choose by V; see lm_kernels.cu)
     int no_compact = 0;  // direct-load path: 1 = never compact masked voxels (debug / comparison)
     int q_stream = -1;   // TMA path: 1 = stream Q' with Y, 0 = keep Q' resident in smem, -1 = choose
+    int stored_exact = 0;  // stored uint16, TMA path: 1 = expand with the reader's three roundings instead of one FMA
 };
 
 struct LmLaunchInfo {

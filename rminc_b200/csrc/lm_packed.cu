@@ -110,6 +110,36 @@ __device__ __forceinline__ void load_convert_smem(const T *p, double (&y)[VPT], 
     }
 }
 
+// FOLD form of the uint16 conversion (TMA variant, default): the sample becomes w = 1 + u * 2^-16 by placing u in the
+// top 16 mantissa bits of a double -- integer work only -- and its value is ONE fused multiply-add
+//     y = A * w + C,   A = scale * 2^16 (exact),   C = fl(offset - scale * (voxel_min + 2^16)) (one rounding, host fma).
+// A * w + C is evaluated exactly and rounded once; with the rounding of C the result lies within
+// 2^-53 * |C| + ulp(y) / 2 of the real number the reader's expression denotes -- the same size as the reader's own two
+// roundings -- but it is not always the reader's double bit for bit (RMG_STORED_EXACT=1 selects the three-rounding form).
+template <int VPT>
+__device__ __forceinline__ void load_unit_smem(const uint16_t *p, double (&w)[VPT])
+{
+    uint32_t r[VPT / 2];
+    if constexpr (VPT == 8) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(p);
+        r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w;
+    } else if constexpr (VPT == 4) {
+        const uint2 q = *reinterpret_cast<const uint2 *>(p);
+        r[0] = q.x; r[1] = q.y;
+    } else {
+        r[0] = *reinterpret_cast<const uint32_t *>(p);
+    }
+#pragma unroll
+    for (int i = 0; i < VPT / 2; ++i) {
+        // (x & 0xffff0) | 0x3ff00000 as ONE three-input logic op (the compiler splits the two immediates into two)
+        uint32_t h0, h1;
+        asm("lop3.b32 %0, %1, 0x000ffff0, 0x3ff00000, 0xEA;" : "=r"(h0) : "r"(r[i] << 4));
+        asm("lop3.b32 %0, %1, 0x000ffff0, 0x3ff00000, 0xEA;" : "=r"(h1) : "r"(r[i] >> 12));
+        w[2 * i] = __hiloint2double((int)h0, 0);
+        w[2 * i + 1] = __hiloint2double((int)h1, 0);
+    }
+}
+
 // value of one sample as the reference's doubles: separate multiply and add (never an FMA)
 __device__ __forceinline__ double descale(double t, double sc, double of) { return __dadd_rn(__dmul_rn(t, sc), of); }
 
@@ -170,6 +200,52 @@ __device__ __noinline__ double2 exact_pass_packed(const T *__restrict__ u, int64
         m2 = fma(dlt, dlt, m2);
     }
     return make_double2(r2, m2);
+}
+
+// The same recomputation for the TMA variant, result row included.  A call in the middle of the epilogue makes the
+// compiler park the epilogue's live values on the stack for EVERY tile (84-104 bytes per thread and tile: ~90 MB of extra
+// DRAM writes per config-2 launch); this one is called after the regular rows are stored, takes scalars and pointers
+// only, and overwrites the voxel's row.
+template <int KP, typename T>
+__device__ __noinline__ void exact_voxel_packed(const T *__restrict__ u, int64_t ld, int n, const double *__restrict__ Qt,
+                                                double y0, double cmagic, const double *__restrict__ sc,
+                                                const double *__restrict__ of, int64_t sstride,
+                                                const SmemDesign<KP> *__restrict__ sd, double *__restrict__ out, int64_t ldOut)
+{
+    auto sample = [&](int j) {
+        double t = Stored<T>::load1(u + (int64_t)j * ld, cmagic);
+        if (Stored<T>::kScaled) t = descale(t, __ldg(sc + (int64_t)j * sstride), __ldg(of + (int64_t)j * sstride));
+        return t - y0;
+    };
+    VoxelSums<KP> s;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) s.e[k] = 0.0;
+    s.y0 = y0;
+    s.yy = 0.0;
+    for (int j = 0; j < n; ++j) {
+        const double yv = sample(j);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) s.e[k] = fma(__ldg(Qt + (size_t)j * KP + k), yv, s.e[k]);
+    }
+    double r2 = 0.0, sf = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double fit = 0.0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) fit = fma(__ldg(Qt + (size_t)j * KP + k), s.e[k], fit);
+        const double r = sample(j) - fit;
+        r2 = fma(r, r, r2);
+        sf += fit;
+    }
+    const double mean = sf / n;
+    double m2 = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double fit = 0.0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) fit = fma(__ldg(Qt + (size_t)j * KP + k), s.e[k], fit);
+        const double dlt = fit - mean;
+        m2 = fma(dlt, dlt, m2);
+    }
+    finish_voxel<KP>(s, r2, m2, *sd, out, ldOut);
 }
 
 }  // namespace
@@ -354,16 +430,22 @@ lm_fit_packed_kernel(PackedArgs a, int JT)
 // voxels per thread, expand them in registers and accumulate; Q' stays resident in shared memory.  Bytes in flight
 // are set by the ring (32 KB per CTA), not by registers, so the FP64 pipe rather than load latency limits it.
 __global__ void pack_tables_kernel(const double *__restrict__ scale, const double *__restrict__ offset, int64_t nslices,
-                                   int n, int n_pad, double2 *__restrict__ tab)
+                                   int n, int n_pad, double2 *__restrict__ tab, int fold, double voxel_min)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslices * n_pad) return;
     const int64_t s_ = i / n_pad;
     const int j = (int)(i % n_pad);
-    tab[i] = j < n ? make_double2(scale[s_ + (int64_t)j * nslices], offset[s_ + (int64_t)j * nslices]) : make_double2(0.0, 0.0);
+    double2 t = make_double2(0.0, 0.0);
+    if (j < n) {
+        const double sc = scale[s_ + (int64_t)j * nslices], of = offset[s_ + (int64_t)j * nslices];
+        // FOLD: (A, C) of load_unit_smem's form; voxel_min + 65536 is an exact integer, the fma rounds C once
+        t = fold ? make_double2(sc * 65536.0, fma(-sc, voxel_min + 65536.0, of)) : make_double2(sc, of);
+    }
+    tab[i] = t;
 }
 
-template <int KP, typename T, int CW, int NJ, int STAGES, int MINB, int VPT>
+template <int KP, typename T, int CW, int NJ, int STAGES, int MINB, int VPT, bool FOLD>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB)
 lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a, const double2 *__restrict__ tab, int n_pad)
 {
@@ -427,18 +509,22 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
     const int lane = tid & 31;
     const double cm = a.cmagic;
     const int boff = ((VPT * tid) / BOXW) * NJ * BOXW + (VPT * tid) % BOXW;     // this thread's samples inside a stage
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t v = t * TV + (int64_t)VPT * tid;
-        bool in[VPT];
-#pragma unroll
-        for (int i = 0; i < VPT; ++i) in[i] = v + i < a.V;
-        // which of the tile's two slices each voxel lies in
-        const int64_t sl_a = SC ? min((a.v_base + t * TV) / a.slice_len, a.nslices - 1) : 0;
+    // a.V < 2^31 here (the launcher's condition), so tile and voxel indices are 32-bit: nothing 64-bit stays live across
+    // the subject loop (the loop takes every register; what is live across it is spilled once per tile)
+    for (int t = blockIdx.x; t < (int)ntiles; t += gridDim.x) {
+        // Which of the tile's two slices each voxel lies in: ONE division per tile.  `bnd` = offset inside the tile of the
+        // first voxel of the tile's second slice (>= TV: the tile lies in one slice, or its first slice is the last one).
+        int bnd = TV;
+        if (SC) {
+            const int64_t g0 = a.v_base + (int64_t)t * TV;
+            const int64_t sl_a = min(g0 / a.slice_len, a.nslices - 1);
+            if (sl_a + 1 < a.nslices) bnd = (int)min((sl_a + 1) * a.slice_len - g0, (int64_t)TV);
+        }
         int sel[VPT];
         bool same = true;
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
-            sel[i] = (SC && min((a.v_base + v + i) / a.slice_len, a.nslices - 1) != sl_a) ? 1 : 0;
+            sel[i] = (VPT * tid + i >= bnd) ? 1 : 0;
             same &= sel[i] == sel[0];
         }
         VoxelSums<KP> sum[VPT];
@@ -463,7 +549,8 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
                 for (int jj = 0; jj < NJ; ++jj) {
                     if (FULL || jj < nvalid) {
                         double y[VPT];
-                        load_convert_smem<T, VPT>(mine + jj * BOXW, y, cm);
+                        if constexpr (FOLD) load_unit_smem<VPT>(mine + jj * BOXW, y);
+                        else load_convert_smem<T, VPT>(mine + jj * BOXW, y, cm);
                         double2 so0 = make_double2(1.0, 0.0), so1 = so0;
                         if (SC) {
                             so0 = tabs[(SAME ? sel[0] : 0) * NJ + jj];
@@ -474,7 +561,7 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
                             double tv = y[i];
                             if (SC) {
                                 const double2 so = (SAME || sel[i] == 0) ? so0 : so1;
-                                tv = descale(tv, so.x, so.y);
+                                tv = FOLD ? fma(so.x, tv, so.y) : descale(tv, so.x, so.y);
                             }
                             if (it == 0 && jj == 0 && sd.shift) sum[i].y0 = tv;
                             const double yv = tv - sum[i].y0;
@@ -496,18 +583,17 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         // ---- fused epilogue
+        const int64_t v = (int64_t)t * TV + VPT * tid;
+        bool in[VPT];
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) in[i] = v + i < a.V;
         double rss[VPT], mss[VPT];
+        unsigned redo = 0;       // voxels whose one-pass rss lost too many digits: redone from explicit residuals below
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
             rss[i] = sum[i].yy - sumsq_e(sum[i]);
             mss[i] = mss_from_e(sum[i], sd);
-            if (in[i] && rss[i] <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0) {
-                const int64_t sli = SC ? min((a.v_base + v + i) / a.slice_len, a.nslices - 1) : 0;
-                const double2 ex = exact_pass_packed<KP, T>(static_cast<const T *>(a.U) + v + i, a.ldU, n, a.Qt, sum[i].y0, cm,
-                                                            a.scale + sli, a.offset + sli, a.nslices);
-                rss[i] = ex.x;
-                mss[i] = ex.y;
-            }
+            if (in[i] && rss[i] <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0) redo |= 1u << i;
         }
         if (a.out_vec2 && in[VPT - 1]) {
 #pragma unroll
@@ -517,6 +603,16 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
 #pragma unroll
             for (int i = 0; i < VPT; ++i)
                 if (in[i]) finish_voxel<KP>(sum[i], rss[i], mss[i], sd, a.out + v + i, a.ldOut);
+        }
+        if (redo) {
+#pragma unroll
+            for (int i = 0; i < VPT; ++i) {
+                if (redo >> i & 1) {
+                    const int64_t sli = SC ? min((a.v_base + v + i) / a.slice_len, a.nslices - 1) : 0;
+                    exact_voxel_packed<KP, T>(static_cast<const T *>(a.U) + v + i, a.ldU, n, a.Qt, sum[i].y0, cm, a.scale + sli,
+                                              a.offset + sli, a.nslices, &sd, a.out + v + i, a.ldOut);
+                }
+            }
         }
     }
 }
@@ -541,11 +637,10 @@ EncodeTiledFn packed_encode_tiled()
 }
 
 // returns cudaErrorNotSupported when this layout / size is not for the TMA variant (caller falls back)
-template <int KP, typename T, int MINB, int CW = 4, int VPT = 4>
+template <int KP, typename T, int MINB, bool FOLD, int CW = 4, int VPT = 4, int NJ = 8, int STAGES = 4>
 cudaError_t launch_packed_tma(const PackedArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
 {
     constexpr bool SC = Stored<T>::kScaled;
-    constexpr int NJ = 8, STAGES = 4;
     constexpr int TV = CW * 32 * VPT, BOXW = TV < 256 ? TV : 256;
     constexpr int STAGE_B = (NJ * TV * (int)sizeof(T) + (SC ? 2 * NJ * 16 : 0) + 127) & ~127;
     if (a.mask || KP > 8) return cudaErrorNotSupported;
@@ -573,11 +668,12 @@ cudaError_t launch_packed_tma(const PackedArgs &a, const LmPlan &plan, LmScratch
         if (e != cudaSuccess) return e;
         const int64_t cnt = a.nslices * n_pad;
         pack_tables_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(a.scale, a.offset, a.nslices, a.n, n_pad,
-                                                                        reinterpret_cast<double2 *>(scr.flags));
+                                                                        reinterpret_cast<double2 *>(scr.flags), FOLD ? 1 : 0,
+                                                                        a.cmagic - 4503599627370496.0);
         if (info) info->launches++;
         tab = reinterpret_cast<const double2 *>(scr.flags);
     }
-    auto kern = lm_fit_packed_tma_kernel<KP, T, CW, NJ, STAGES, MINB, VPT>;
+    auto kern = lm_fit_packed_tma_kernel<KP, T, CW, NJ, STAGES, MINB, VPT, FOLD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t ntiles = (a.V + TV - 1) / TV;
@@ -592,12 +688,30 @@ cudaError_t launch_packed_t(const PackedArgs &a, const LmPlan &plan, LmScratch &
 {
     if (plan.variant != LmVariant::Ldg) {
         if constexpr (KP <= 8) {
-            // CTAs per SM: as many as the accumulators leave registers for (RMG_TMA_CFG=1 forces one more, with spills)
+            // CTAs per SM: as many as the accumulators leave registers for
             constexpr int MINB = KP <= 2 ? 4 : (KP <= 4 ? 3 : 2);
-            // Shape measured best on config 2 as uint16 (2.96 ms): 4 consumer warps x 4 voxels per thread, MINB CTAs/SM.
-            // Alternatives tried (profiles/README.md): 2 voxels/thread with 4-6 CTAs/SM 3.2-3.6 ms, 8 voxels/thread
-            // 3.2 ms, one more CTA per SM at 96 registers (spills) 3.17 ms.
-            const cudaError_t e = launch_packed_tma<KP, T, MINB>(a, plan, scr, st, info);
+            // Shape: 4 consumer warps x 4 voxels per thread, MINB CTAs/SM.  uint16 samples take one fused multiply-add
+            // each (FOLD) unless the reader's three roundings are asked for, and 16 subjects per stage in a 3-deep ring:
+            // the barrier round trip per stage is then paid half as often (config 2: 2.30 ms against 2.45 ms for 8
+            // subjects x 4 stages; the ring's bytes in flight are the same).  Measured alternatives: profiles/README.md.
+            cudaError_t e;
+            if constexpr (Stored<T>::kScaled) {
+                if (plan.stored_exact) {
+                    e = launch_packed_tma<KP, T, MINB, false>(a, plan, scr, st, info);
+                } else {
+#ifdef RMG_PACKED_EXPERIMENTS      // developer build: one more CTA per SM at 96 registers (spills in the epilogue)
+                    if constexpr (KP == 4) {
+                        if (plan.tma_cfg == 2) return launch_packed_tma<KP, T, 4, true, 4, 4, 16, 2>(a, plan, scr, st, info);
+                        if (plan.tma_cfg == 3) return launch_packed_tma<KP, T, 4, true, 4, 4, 8, 4>(a, plan, scr, st, info);
+                    }
+#endif
+                    e = plan.tma_cfg == 1 ? cudaErrorNotSupported
+                                          : launch_packed_tma<KP, T, MINB, true, 4, 4, 16, 3>(a, plan, scr, st, info);
+                    if (e == cudaErrorNotSupported) e = launch_packed_tma<KP, T, MINB, true>(a, plan, scr, st, info);
+                }
+            } else {
+                e = launch_packed_tma<KP, T, MINB, false>(a, plan, scr, st, info);
+            }
             if (e != cudaErrorNotSupported) return e;
         }
     }
@@ -658,8 +772,12 @@ cudaError_t launch_lm_packed(const PackedArgs &a_in, const LmPlan &plan, LmScrat
     a.out_vec2 = ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && a.ldOut % 2 == 0) ? 1 : 0;
     switch (lm_padded_p(a.p)) {
 #define RMG_CASE(K) case K: return launch_packed_kp<K>(a, plan, scr, st, info);
+#ifdef RMG_QUICK_KP4      // developer switch: compile the p = 4 instances only (SASS inspection in seconds)
+        RMG_CASE(4)
+#else
         RMG_CASE(1) RMG_CASE(2) RMG_CASE(3) RMG_CASE(4) RMG_CASE(5) RMG_CASE(6) RMG_CASE(7) RMG_CASE(8)
         RMG_CASE(12) RMG_CASE(16)
+#endif
 #undef RMG_CASE
     default: return cudaErrorInvalidValue;
     }

@@ -654,15 +654,27 @@ def test_stored_device_entry_point(core, oracle):
 
 
 @pytest.mark.parametrize("slice_len", [1001, 4096, 80128])
-def test_stored_tma_ring_variant(core, oracle, slice_len):
+@pytest.mark.parametrize("mode", ["fma16", "fma8", "exact"])
+def test_stored_tma_ring_variant(core, oracle, monkeypatch, slice_len, mode):
     """Large V takes the TMA-staged kernel: stored samples + the tile's (scale, offset) rows through the shared-memory
-    ring.  slice_len = 1001 puts slice boundaries inside tiles and inside a thread's four voxels."""
-    V, n = 80128, 24
+    ring.  slice_len = 1001 puts slice boundaries inside tiles and inside a thread's four voxels.  Modes: one fused
+    multiply-add per sample with 16 (default) or 8 subjects per ring stage (the fallback when the larger ring does not
+    fit), and the reader's three roundings (RMG_STORED_EXACT=1)."""
+    if mode == "fma8":
+        monkeypatch.setenv("RMG_TMA_CFG", "1")
+    if mode == "exact":
+        monkeypatch.setenv("RMG_STORED_EXACT", "1")
+    V, n = 80128, 37
     U, X, scale, offset = _stored_case(V, n, slice_len, seed=slice_len)
     Y = oracle.expand_stored(U, scale, offset, voxel_min=3.0, slice_len=slice_len)
     got = core.lm_fit_stored(U, X, scale, offset, voxel_min=3.0, slice_len=slice_len)
     assert core.last_fit_variant() == "lm_fit_packed_tma_kernel"
     assert_rows_match(got, oracle.vertex_lm_loop(Y, X), RTOL, "tma u16")
+    # the one-FMA expansion differs from the reader's doubles by at most a rounding of the real range: the fits agree
+    # far inside the tolerance
+    assert_rows_match(got, core.lm_fit(Y, X), 1e-11, "tma u16 vs the double path on the reader's doubles")
+    if mode != "fma16":
+        return
     if slice_len == 4096:
         F = np.asfortranarray(Y.astype(np.float32))
         got = core.lm_fit_stored(F, X[:, :3])
