@@ -109,6 +109,7 @@ struct PackedArgs {
     double cmagic;             // 2^52 + voxel_min (u16)
     int64_t slice_len, nslices, v_base;
     int out_vec2 = 0;
+    int zero = 0;              // always 0: a kernel parameter the compiler cannot fold (low words of built doubles)
 };
 
 cudaError_t launch_lm_packed(const PackedArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info);

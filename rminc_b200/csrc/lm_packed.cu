@@ -140,6 +140,35 @@ __device__ __forceinline__ void load_unit_smem(const uint16_t *p, double (&w)[VP
     }
 }
 
+// FOLD = 2 (default): the sample sits in the LOW 16 bits of the high word, w = 1 + u * 2^-20 -- a byte-aligned position, so
+// each high word is ONE byte permute of the packed pair and the constant 0x3ff00000 (no shift) -- with A = scale * 2^20 and
+// C = fl(offset - scale * (voxel_min + 2^20)).  |C| grows to 16 value ranges, its rounding to 2^-49 of the range: far below
+// the 2^-16 of the range one stored count stands for.
+template <int VPT>
+__device__ __forceinline__ void load_unit20_smem(const uint16_t *p, double (&w)[VPT], uint32_t kexp)
+{
+    uint32_t r[VPT / 2];
+    if constexpr (VPT == 8) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(p);
+        r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w;
+    } else if constexpr (VPT == 4) {
+        const uint2 q = *reinterpret_cast<const uint2 *>(p);
+        r[0] = q.x; r[1] = q.y;
+    } else {
+        r[0] = *reinterpret_cast<const uint32_t *>(p);
+    }
+    // Only the HIGH words of w[] are replaced: the low words (zero, but a kernel parameter the compiler cannot fold) stay
+    // where they are, so a sample costs one logic op -- no shift, no move -- before its fused multiply-add.
+#pragma unroll
+    for (int i = 0; i < VPT / 2; ++i) {
+        uint32_t h0, h1;
+        asm("lop3.b32 %0, %1, 0xffff, %2, 0xEA;" : "=r"(h0) : "r"(r[i]), "r"(kexp));       // (r & 0xffff) | 0x3ff00000
+        asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(h1) : "r"(r[i]), "r"(kexp));             // (r >> 16)    | 0x3ff00000
+        asm("{ .reg .b32 lo, hi; mov.b64 {lo, hi}, %0; mov.b64 %0, {lo, %1}; }" : "+d"(w[2 * i]) : "r"(h0));
+        asm("{ .reg .b32 lo, hi; mov.b64 {lo, hi}, %0; mov.b64 %0, {lo, %1}; }" : "+d"(w[2 * i + 1]) : "r"(h1));
+    }
+}
+
 // value of one sample as the reference's doubles: separate multiply and add (never an FMA)
 __device__ __forceinline__ double descale(double t, double sc, double of) { return __dadd_rn(__dmul_rn(t, sc), of); }
 
@@ -440,12 +469,13 @@ __global__ void pack_tables_kernel(const double *__restrict__ scale, const doubl
     if (j < n) {
         const double sc = scale[s_ + (int64_t)j * nslices], of = offset[s_ + (int64_t)j * nslices];
         // FOLD: (A, C) of load_unit_smem's form; voxel_min + 65536 is an exact integer, the fma rounds C once
-        t = fold ? make_double2(sc * 65536.0, fma(-sc, voxel_min + 65536.0, of)) : make_double2(sc, of);
+        const double one = fold == 2 ? 1048576.0 : 65536.0;        // the value of w's leading 1 in stored counts
+        t = fold ? make_double2(sc * one, fma(-sc, voxel_min + one, of)) : make_double2(sc, of);
     }
     tab[i] = t;
 }
 
-template <int KP, typename T, int CW, int NJ, int STAGES, int MINB, int VPT, bool FOLD>
+template <int KP, typename T, int CW, int NJ, int STAGES, int MINB, int VPT, int FOLD>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB)
 lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a, const double2 *__restrict__ tab, int n_pad)
 {
@@ -511,6 +541,10 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
     const int boff = ((VPT * tid) / BOXW) * NJ * BOXW + (VPT * tid) % BOXW;     // this thread's samples inside a stage
     // a.V < 2^31 here (the launcher's condition), so tile and voxel indices are 32-bit: nothing 64-bit stays live across
     // the subject loop (the loop takes every register; what is live across it is spilled once per tile)
+    const uint32_t kexp = 0x3ff00000u | (uint32_t)a.zero;
+    double wp[VPT];           // FOLD = 2: the samples of one subject as doubles; the low words are written here, once
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) wp[i] = __hiloint2double((int)kexp, a.zero);
     for (int t = blockIdx.x; t < (int)ntiles; t += gridDim.x) {
         // Which of the tile's two slices each voxel lies in: ONE division per tile.  `bnd` = offset inside the tile of the
         // first voxel of the tile's second slice (>= TV: the tile lies in one slice, or its first slice is the last one).
@@ -535,6 +569,19 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
             sum[i].yy = 0.0;
             sum[i].y0 = 0.0;
         }
+        // FOLD = 2: ONE shift per thread (the first sample of its first voxel) is folded into the offsets, C_j - shift being
+        // formed once per subject and thread instead of one subtraction per sample; adjacent voxels differ little next to
+        // their spread, and a voxel whose shifted |y|^2 still dwarfs its rss is redone from explicit residuals below.
+        double shift = 0.0;
+        if constexpr (FOLD == 2) {
+            if (sd.shift) {
+                mbar_wait(&full[stage], phase);          // the loop below waits for the same phase again: it passes at once
+                const unsigned char *st = ring + (size_t)stage * STAGE_B;
+                load_unit20_smem<VPT>(reinterpret_cast<const uint16_t *>(st) + boff, wp, kexp);
+                const double2 so = reinterpret_cast<const double2 *>(st + DATA_B)[sel[0] * NJ];
+                shift = fma(so.x, wp[0], so.y);
+            }
+        }
         for (int it = 0; it < nit; ++it) {
             mbar_wait(&full[stage], phase);
             const unsigned char *st = ring + (size_t)stage * STAGE_B;
@@ -549,22 +596,30 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
                 for (int jj = 0; jj < NJ; ++jj) {
                     if (FULL || jj < nvalid) {
                         double y[VPT];
-                        if constexpr (FOLD) load_unit_smem<VPT>(mine + jj * BOXW, y);
+                        if constexpr (FOLD == 2) load_unit20_smem<VPT>(reinterpret_cast<const uint16_t *>(mine) + jj * BOXW, wp, kexp);
+                        else if constexpr (FOLD == 1) load_unit_smem<VPT>(mine + jj * BOXW, y);
                         else load_convert_smem<T, VPT>(mine + jj * BOXW, y, cm);
                         double2 so0 = make_double2(1.0, 0.0), so1 = so0;
                         if (SC) {
                             so0 = tabs[(SAME ? sel[0] : 0) * NJ + jj];
                             if (!SAME) so1 = tabs[NJ + jj];
+                            if constexpr (FOLD == 2) {
+                                so0.y -= shift;
+                                if (!SAME) so1.y -= shift;
+                            }
                         }
 #pragma unroll
                         for (int i = 0; i < VPT; ++i) {
-                            double tv = y[i];
+                            double tv = FOLD == 2 ? wp[i] : y[i];
                             if (SC) {
                                 const double2 so = (SAME || sel[i] == 0) ? so0 : so1;
                                 tv = FOLD ? fma(so.x, tv, so.y) : descale(tv, so.x, so.y);
                             }
-                            if (it == 0 && jj == 0 && sd.shift) sum[i].y0 = tv;
-                            const double yv = tv - sum[i].y0;
+                            double yv = tv;
+                            if constexpr (FOLD != 2) {
+                                if (it == 0 && jj == 0 && sd.shift) sum[i].y0 = tv;
+                                yv = tv - sum[i].y0;
+                            }
                             sum[i].yy = fma(yv, yv, sum[i].yy);
 #pragma unroll
                             for (int k = 0; k < KP; ++k) sum[i].e[k] = fma(q[jj * KP + k], yv, sum[i].e[k]);
@@ -581,6 +636,10 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (FOLD == 2) {
+#pragma unroll
+            for (int i = 0; i < VPT; ++i) sum[i].y0 = shift;
         }
         // ---- fused epilogue
         const int64_t v = (int64_t)t * TV + VPT * tid;
@@ -637,7 +696,7 @@ EncodeTiledFn packed_encode_tiled()
 }
 
 // returns cudaErrorNotSupported when this layout / size is not for the TMA variant (caller falls back)
-template <int KP, typename T, int MINB, bool FOLD, int CW = 4, int VPT = 4, int NJ = 8, int STAGES = 4>
+template <int KP, typename T, int MINB, int FOLD, int CW = 4, int VPT = 4, int NJ = 8, int STAGES = 4>
 cudaError_t launch_packed_tma(const PackedArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info)
 {
     constexpr bool SC = Stored<T>::kScaled;
@@ -668,7 +727,7 @@ cudaError_t launch_packed_tma(const PackedArgs &a, const LmPlan &plan, LmScratch
         if (e != cudaSuccess) return e;
         const int64_t cnt = a.nslices * n_pad;
         pack_tables_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(a.scale, a.offset, a.nslices, a.n, n_pad,
-                                                                        reinterpret_cast<double2 *>(scr.flags), FOLD ? 1 : 0,
+                                                                        reinterpret_cast<double2 *>(scr.flags), FOLD,
                                                                         a.cmagic - 4503599627370496.0);
         if (info) info->launches++;
         tab = reinterpret_cast<const double2 *>(scr.flags);
@@ -697,20 +756,22 @@ cudaError_t launch_packed_t(const PackedArgs &a, const LmPlan &plan, LmScratch &
             cudaError_t e;
             if constexpr (Stored<T>::kScaled) {
                 if (plan.stored_exact) {
-                    e = launch_packed_tma<KP, T, MINB, false>(a, plan, scr, st, info);
+                    e = launch_packed_tma<KP, T, MINB, 0>(a, plan, scr, st, info);
                 } else {
-#ifdef RMG_PACKED_EXPERIMENTS      // developer build: one more CTA per SM at 96 registers (spills in the epilogue)
+                    // measured alternatives: one more CTA per SM at 96 registers
                     if constexpr (KP == 4) {
-                        if (plan.tma_cfg == 2) return launch_packed_tma<KP, T, 4, true, 4, 4, 16, 2>(a, plan, scr, st, info);
-                        if (plan.tma_cfg == 3) return launch_packed_tma<KP, T, 4, true, 4, 4, 8, 4>(a, plan, scr, st, info);
+                        if (plan.tma_cfg == 2) return launch_packed_tma<KP, T, 4, 2, 4, 4, 16, 2>(a, plan, scr, st, info);
+                        if (plan.tma_cfg == 3) return launch_packed_tma<KP, T, 4, 2, 4, 4, 8, 4>(a, plan, scr, st, info);
                     }
-#endif
-                    e = plan.tma_cfg == 1 ? cudaErrorNotSupported
-                                          : launch_packed_tma<KP, T, MINB, true, 4, 4, 16, 3>(a, plan, scr, st, info);
-                    if (e == cudaErrorNotSupported) e = launch_packed_tma<KP, T, MINB, true>(a, plan, scr, st, info);
+                    // RMG_TMA_CFG: 1 = 8 subjects x 4 stages, 4 = the round-2a form (w = 1 + u 2^-16, one shift per voxel)
+                    if (plan.tma_cfg == 4) e = launch_packed_tma<KP, T, MINB, 1, 4, 4, 16, 3>(a, plan, scr, st, info);
+                    else
+                        e = plan.tma_cfg == 1 ? cudaErrorNotSupported
+                                              : launch_packed_tma<KP, T, MINB, 2, 4, 4, 16, 3>(a, plan, scr, st, info);
+                    if (e == cudaErrorNotSupported) e = launch_packed_tma<KP, T, MINB, 2>(a, plan, scr, st, info);
                 }
             } else {
-                e = launch_packed_tma<KP, T, MINB, false>(a, plan, scr, st, info);
+                e = launch_packed_tma<KP, T, MINB, 0>(a, plan, scr, st, info);
             }
             if (e != cudaErrorNotSupported) return e;
         }
