@@ -37,6 +37,7 @@ extern "C" {
                                 (src/modelling_functions.c:551-557) */
 #define RMG_ERR_CUDA 3       /* a CUDA runtime/driver call failed */
 #define RMG_ERR_NO_DEVICE 4  /* no CUDA device / device index out of range */
+#define RMG_ERR_IO 5         /* a volume file cannot be opened or is not what it should be (rmg_minc2_*) */
 
 #define RMG_MAX_P 32         /* largest supported number of design columns */
 
@@ -452,6 +453,71 @@ void rmg_host_free(void *ptr);
  * *aggregate_gbs (nullable): all bytes / wall time.  The ceiling end-to-end numbers are reported against. */
 int rmg_h2d_probe(const void *host, size_t bytes_per_gpu, int n_gpus, int repeats, double *gbs, double *aggregate_gbs,
                   char *err, size_t errlen);
+
+/*
+ * MINC 2 volumes without libminc / libhdf5 (host only; no GPU involved).  Replaces, for the files in front of the hot
+ * path, miopen_volume + miget_volume_dimensions + miget_dimension_sizes + miget_real_value_hyperslab as minc2_model and
+ * mincGetVolume use them (src/modelling_functions.c:806-829, 1037-1055; src/minc_reader.c:294-331;
+ * R/minc_interface.R:1031-1077) -- and hands out the voxels in their STORED type with the per-slice real ranges, which is
+ * what rmg_lm_fit_stored / rmg_randomize_stored take.  The HDF5 container is parsed here (rminc_b200/csrc/minc2_reader.cpp);
+ * chunks are inflated by n_threads host threads directly into the caller's buffer.
+ *   real value = ((double)stored - valid_range[0]) * (max_s - min_s) / (valid_range[1] - valid_range[0]) + min_s
+ * with s the range entry of the voxel (entry = voxel index / slice_len); float volumes are taken as they are.
+ * Errors: RMG_ERR_IO with the reference's "Error opening input file: <path>." for a missing file, or a description of
+ * what in the file is unsupported / damaged.
+ */
+#define RMG_MINC2_MAX_DIMS 5
+#define RMG_MINC2_U8 1
+#define RMG_MINC2_I8 2
+#define RMG_MINC2_U16 3      /* == the stored-type code rmg_lm_fit_stored takes for uint16 voxels is RMG_STORED_U16 */
+#define RMG_MINC2_I16 4
+#define RMG_MINC2_U32 5
+#define RMG_MINC2_I32 6
+#define RMG_MINC2_F32 7
+#define RMG_MINC2_F64 8
+typedef struct rmg_minc2_volume rmg_minc2_volume;
+typedef struct {
+    int32_t ndims;                                  /* of /minc-2.0/image/0/image, slowest dimension first (file order) */
+    int32_t dtype;                                  /* RMG_MINC2_* */
+    int32_t elem_size;                              /* bytes per stored voxel */
+    int32_t has_real_range;                         /* image-min / image-max present */
+    int64_t sizes[RMG_MINC2_MAX_DIMS];
+    int64_t nvoxels;
+    int64_t nslices;                                /* entries of image-min / image-max (1 = one range for the volume) */
+    int64_t slice_len;                              /* voxels per range entry = nvoxels / nslices */
+    double valid_range[2];
+    double starts[RMG_MINC2_MAX_DIMS];
+    double steps[RMG_MINC2_MAX_DIMS];
+    double dircos[RMG_MINC2_MAX_DIMS][3];
+    char dimnames[RMG_MINC2_MAX_DIMS][16];          /* "zspace", "yspace", "xspace", ... from the image's dimorder */
+} rmg_minc2_info;
+int rmg_minc2_open(const char *path, rmg_minc2_volume **vol, char *err, size_t errlen);
+int rmg_minc2_get_info(const rmg_minc2_volume *vol, rmg_minc2_info *info);
+/* image_min / image_max: info.nslices doubles each */
+int rmg_minc2_read_ranges(const rmg_minc2_volume *vol, double *image_min, double *image_max, char *err, size_t errlen);
+/* the whole image in its stored type (little-endian), file order; dst_bytes >= nvoxels * elem_size */
+int rmg_minc2_read_stored(const rmg_minc2_volume *vol, void *dst, int64_t dst_bytes, int n_threads, char *err, size_t errlen);
+/* the doubles miget_real_value_hyperslab(MI_TYPE_DOUBLE) yields for the whole image; count >= nvoxels */
+int rmg_minc2_read_real(const rmg_minc2_volume *vol, double *dst, int64_t count, int n_threads, char *err, size_t errlen);
+void rmg_minc2_close(rmg_minc2_volume *vol);
+/*
+ * mincTable in one call (R/minc_interface.R:1031-1077): column j of U (leading dimension ldU >= voxels per volume) receives
+ * file paths[j], files decoded in parallel by n_threads host threads.  dtype RMG_MINC2_U16 / RMG_MINC2_F32: the stored voxels
+ * (every file must have that type) and, for uint16, image_min / image_max [nslices x n, column-major] (a file with a single
+ * range fills its column with it) -- the operands of rmg_lm_fit_stored after scale = (max - min) / (valid_range[1] -
+ * valid_range[0]), offset = min; dtype RMG_MINC2_F64: the real values, any stored type.  U may be pinned memory
+ * (rmg_host_alloc).  valid_range (nullable): the files' common valid range.
+ */
+int rmg_minc2_read_table(const char *const *paths, int n, void *U, int64_t ldU, int dtype, double *image_min, double *image_max,
+                         int64_t nslices, double *valid_range, int n_threads, char *err, size_t errlen);
+/* The container underneath, for header look-ups (mincinfo-style) and for checking the parser against files written by the
+ * HDF5 library: a dataset by its path below the root, raw elements in file order (dst nullable: shape only; dims holds up to 8
+ * entries; type_class 1 = unsigned, 2 = signed integer, 3 = float, 4 = string, 0 = other), and one attribute of an object
+ * (numbers for numeric attributes, text for fixed-length strings; *count = how many values the attribute holds). */
+int rmg_h5_read_dataset(const char *path, const char *dataset, void *dst, int64_t dst_bytes, int32_t *rank, int64_t *dims,
+                        int32_t *elem_size, int32_t *type_class, int n_threads, char *err, size_t errlen);
+int rmg_h5_read_attribute(const char *path, const char *object, const char *attribute, double *numbers, int64_t max_numbers,
+                          int64_t *count, char *text, size_t textlen, char *err, size_t errlen);
 
 /* Timing of the most recent rmg_*_device / host call on this thread, for bench.py:
  * milliseconds spent in the dominant kernel(s), measured with CUDA events on the stream the

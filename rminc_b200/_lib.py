@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librminc_b200.so")
 
-RMG_OK, RMG_ERR_INVALID, RMG_ERR_SINGULAR, RMG_ERR_CUDA, RMG_ERR_NO_DEVICE = 0, 1, 2, 3, 4
+RMG_OK, RMG_ERR_INVALID, RMG_ERR_SINGULAR, RMG_ERR_CUDA, RMG_ERR_NO_DEVICE, RMG_ERR_IO = 0, 1, 2, 3, 4, 5
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -102,6 +102,19 @@ SIGNATURES = {
     "rmg_last_kernel_ms": (C.c_double, []),
     "rmg_last_fit_variant": (C.c_int, []),
     "rmg_launch_count": (C.c_int64, []),
+    # MINC 2 / HDF5 reader (host only)
+    "rmg_minc2_open": (C.c_int, [C.c_char_p, C.c_void_p] + _ERR),
+    "rmg_minc2_get_info": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rmg_minc2_read_ranges": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + _ERR),
+    "rmg_minc2_read_stored": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + _ERR),
+    "rmg_minc2_read_real": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + _ERR),
+    "rmg_minc2_close": (None, [C.c_void_p]),
+    "rmg_minc2_read_table": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_void_p, C.c_int] + _ERR),
+    "rmg_h5_read_dataset": (C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int] + _ERR),
+    "rmg_h5_read_attribute": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_char_p,
+                                        C.c_size_t] + _ERR),
 }
 
 

@@ -91,9 +91,11 @@ def _column(data, name, rows):
 
 
 # ----------------------------------------------------------------------------- staging (I/O side)
-def default_reader(item) -> np.ndarray:
-    """Volume loader used where the reference calls mincGetVolume: in-memory arrays pass through,
-    '.npy' paths are np.load'ed.  Returns the voxels flattened in file (C) order."""
+def default_reader(item):
+    """Volume loader used where the reference calls mincGetVolume: in-memory arrays pass through, '.npy' paths are
+    np.load'ed, MINC 2 files go through the library's own reader (rminc_b200/minc2.py: uint16 / float32 volumes come back
+    as StoredVolume so that they travel in their stored type, other types as the real doubles).  Arrays are flattened in
+    file (C) order."""
     if isinstance(item, np.ndarray):
         return np.asarray(item, dtype=np.float64).reshape(-1)
     if isinstance(item, (str, os.PathLike)):
@@ -102,7 +104,10 @@ def default_reader(item) -> np.ndarray:
             raise FileNotFoundError(f"Error opening input file: {path}.")          # minc2_model :809
         if path.endswith(".npy"):
             return np.load(path).astype(np.float64, copy=False).reshape(-1)
-        raise ValueError(f"no reader for '{path}': pass reader= (MINC I/O is outside this package)")
+        from . import minc2
+        if minc2.is_minc2(path):
+            return minc2.read_volume(path)
+        raise ValueError(f"no reader for '{path}': not a MINC 2 (HDF5) file or .npy array; pass reader= (MINC 1 files: mincconvert -2)")
     raise TypeError(f"cannot stage a volume from {type(item).__name__}")
 
 
@@ -173,15 +178,41 @@ def _expand_stored(U, scale, offset, voxel_min, slice_len):
 
 def mincTable(filenames: Sequence, mask=None, reader: Callable = default_reader) -> np.ndarray:
     """V x n matrix, one column per file (R/minc_interface.R:1031-1077), Fortran order."""
-    first = reader(filenames[0])
+    def real(item):
+        v = reader(item)
+        return v.real() if isinstance(v, StoredVolume) else v
+
+    first = real(filenames[0])
     Y = np.empty((first.shape[0], len(filenames)), order="F")
     Y[:, 0] = first
     for j, f in enumerate(filenames[1:], start=1):
-        v = reader(f)
+        v = real(f)
         if v.shape[0] != first.shape[0]:
             raise ValueError("all volumes must have the same number of voxels")
         Y[:, j] = v
     return Y
+
+
+def _minc2_stage(filenames):
+    """A study of MINC 2 files decoded in parallel by the library's reader (rmg_minc2_read_table) straight into the
+    column-major matrix the entry points take: ("stored", U, scale, offset, voxel_min, slice_len) for uint16 / float32 files,
+    ("real", Y) otherwise; None when the names are not all MINC 2 files."""
+    from . import minc2
+    if not all(isinstance(f, (str, os.PathLike)) for f in filenames):
+        return None
+    for f in filenames:
+        if not os.path.exists(os.fspath(f)):
+            raise FileNotFoundError(f"Error opening input file: {os.fspath(f)}.")          # minc2_model :809
+    if not all(minc2.is_minc2(f) for f in filenames):
+        return None
+    U, lo, hi, vr, info = minc2.read_table(filenames)
+    if U.dtype == np.float64:
+        return ("real", U)
+    if U.dtype == np.float32:
+        return ("stored", U, None, None, 0.0, max(U.shape[0], 1))
+    if not vr[1] > vr[0]:
+        raise ValueError("the volumes' valid_range is empty")
+    return ("stored", U, (hi - lo) / (vr[1] - vr[0]), lo, vr[0], info.slice_len if info.nslices > 1 else max(U.shape[0], 1))
 
 
 def vertexTable(filenames: Sequence, column: int = 1) -> np.ndarray:
@@ -206,6 +237,8 @@ def _stage_mask(mask, V, reader):
     if mask is None:
         return None
     m = reader(mask) if not isinstance(mask, np.ndarray) else np.asarray(mask, dtype=np.float64).reshape(-1)
+    if isinstance(m, StoredVolume):
+        m = m.real()
     if m.shape[0] != V:
         raise ValueError("Mask Volume input volume dimension mismatch.")          # :837
     return m
@@ -275,11 +308,18 @@ def mincLm(formula: str, data, subset=None, mask=None, maskval=None, parallel=No
     plm = parseLmFormula(rhs, data, rows)                                        # :796
     filenames = _column(data, lhs, rows)
     lo, hi = core.mask_range(maskval)                                            # :781-787
-    first = reader(filenames[0])
-    if isinstance(first, StoredVolume) and not plm["matrixFound"]:
-        # the volumes travel in their stored type; the device forms the doubles (one GPU)
-        vols = [first] + [reader(f) for f in filenames[1:]]
-        U, scale, offset, vmin, slice_len = mincTableStored(vols)
+    staged = _minc2_stage(filenames) if (reader is default_reader and not plm["matrixFound"]) else None
+    Y_staged = staged[1] if staged is not None and staged[0] == "real" else None
+    if Y_staged is not None:
+        staged = None
+    first = reader(filenames[0]) if staged is None and Y_staged is None else None
+    if staged is not None or (isinstance(first, StoredVolume) and not plm["matrixFound"]):
+        # the volumes travel in their stored type; the device forms the doubles
+        if staged is not None:
+            U, scale, offset, vmin, slice_len = staged[1:]
+        else:
+            vols = [first] + [reader(f) for f in filenames[1:]]
+            U, scale, offset, vmin, slice_len = mincTableStored(vols)
         X, names, _ = model_matrix(rhs, data, rows)
         m = _stage_mask(mask, U.shape[0], reader)
         out = core.lm_fit_stored(U, X, scale, offset, voxel_min=vmin, slice_len=slice_len, mask=m, mask_lo=lo, mask_hi=hi,
@@ -301,7 +341,7 @@ def mincLm(formula: str, data, subset=None, mask=None, maskval=None, parallel=No
             v = stored_reader(item)
             return v.real() if isinstance(v, StoredVolume) else v
 
-    Y = mincTable(filenames, reader=reader)
+    Y = Y_staged if Y_staged is not None else mincTable(filenames, reader=reader)
     V, n = Y.shape
     m = _stage_mask(mask, V, reader)
     if plm["matrixFound"]:
@@ -702,7 +742,13 @@ def volume_dims(like) -> tuple:
         shp = np.load(os.fspath(like), mmap_mode="r").shape
         if len(shp) == 3:
             return tuple(int(v) for v in shp)
-    raise ValueError("like_volume must give three dimensions: a 3-tuple, a 3-D array or a .npy volume")
+    if isinstance(like, (str, os.PathLike)) and os.path.exists(os.fspath(like)):
+        from . import minc2
+        if minc2.is_minc2(like):
+            with minc2.Minc2Volume(like) as v:
+                if len(v.sizes) == 3:
+                    return v.sizes
+    raise ValueError("like_volume must give three dimensions: a 3-tuple, a 3-D array, a .npy volume or a MINC 2 file")
 
 
 def mincTFCE(x, d=0.1, E: float = 0.5, H: float = 2.0, side: str = "both", like_volume=None, R: int = 500,

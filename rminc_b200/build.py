@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librminc_b200.so")
 
-SOURCES = ["capi.cu", "lm_kernels.cu", "lm_cov.cu", "lm_packed.cu", "fdr.cu", "tfce.cu", "randomize.cu", "dataset.cu", "perm_gemm.cu", "design.cpp"]
+SOURCES = ["capi.cu", "lm_kernels.cu", "lm_cov.cu", "lm_packed.cu", "fdr.cu", "tfce.cu", "randomize.cu", "dataset.cu", "perm_gemm.cu", "design.cpp", "minc2_reader.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -80,7 +80,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out)
         if verbose and out:
             print(out, file=sys.stderr)
-    link = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lpthread", "-ldl"]
+    link = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lpthread", "-ldl", "-lz"]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout)

@@ -588,3 +588,50 @@ def test_model_selection_on_the_logLik_column(api, study):
     with pytest.raises(TypeError):
         api.AIC(np.zeros((3, 3)))
 
+
+
+def test_mincLm_on_minc2_files(api, study, tmp_path):
+    """The whole front of the path on MINC 2 files (tests/testthat/test_mincLm.R runs on .mnc files): the default reader
+    decodes the study in parallel through the library's own HDF5 / MINC 2 reader, the uint16 voxels and their per-slice
+    ranges go to the stored-type fit, the mask is a uint8 label volume, and mincTFCE takes the dimensions from the
+    likeVolume's header -- same numbers as the fit on the doubles libminc's reader would have produced."""
+    import h5mini
+    gf, maskfile, _ = study
+    files, Yq = [], []
+    for i, f in enumerate(gf.jacobians):
+        real = np.load(f)
+        lo, hi = real.min(axis=(1, 2)) - 0.01, real.max(axis=(1, 2)) + 0.01
+        vox = np.round((real - lo[:, None, None]) / (hi - lo)[:, None, None] * 65535.0).astype(np.uint16)
+        p = str(tmp_path / f"subj{i:02d}.mnc")
+        h5mini.write_minc2(p, vox, image_min=lo, image_max=hi, valid_range=(0, 65535), chunks=(1, 10, 10), compress=4,
+                           steps=(0.1, 0.1, 0.1))
+        files.append(p)
+        Yq.append(api.StoredVolume(vox, image_min=lo, image_max=hi).real())
+    Yq = np.stack(Yq, axis=1)
+    gm = gf.assign(jacobians=files)
+    mpath = str(tmp_path / "mask.mnc")
+    h5mini.write_minc2(mpath, np.load(maskfile).astype(np.uint8), valid_range=(0, 255), chunks=(10, 10, 10))
+    vs = api.mincLm("jacobians ~ Sex + Scale", gm, mask=mpath)
+    X = np.column_stack([np.ones(10), gf.Sex == "M", gf.Scale.values]).astype(float)
+    inside = np.load(maskfile).reshape(-1) > 0.5
+    for v in np.flatnonzero(inside)[[0, 17, 101]]:
+        check_row(vs, int(v), Yq[v], X, ["(Intercept)", "SexM", "Scale"])
+    assert (np.asarray(vs)[~inside] == 0).all() and vs.attrs["likeVolume"] == files[0]
+    np.testing.assert_array_equal(api._expand_stored(**vs.attrs["_stored"]), Yq)
+    # a right-hand-side volume and other stored types take the real-valued route through the same reader
+    idx = api.draw_indices(10, 3, seed=5)
+    tf = api.mincTFCE(vs, R=3, idx=idx, d=0.2)                   # dimensions from the MINC header of likeVolume
+    assert np.asarray(tf["tfce"]).shape == (1000, 3) and np.asarray(tf["randomization_dist"]).shape == (3, 3)
+    i16 = []
+    for i, f in enumerate(gf.jacobians):
+        p = str(tmp_path / f"short{i:02d}.mnc")
+        real = np.load(f)
+        vox = np.round((real - real.min()) / (real.max() - real.min()) * 65535.0 - 32768.0).astype(np.int16)
+        h5mini.write_minc2(p, vox, image_min=real.min(), image_max=real.max(), valid_range=(-32768, 32767), chunks=(2, 10, 10))
+        i16.append(p)
+    v16 = api.mincLm("jacobians ~ Sex", gf.assign(jacobians=i16))
+    Y16 = np.stack([api.default_reader(p) for p in i16], axis=1)
+    assert "_Y" in v16.attrs and np.array_equal(v16.attrs["_Y"], Y16)
+    check_row(v16, 7, Y16[7], X[:, :2], ["(Intercept)", "SexM"])
+    with pytest.raises(FileNotFoundError, match="Error opening input file"):
+        api.mincLm("jacobians ~ Sex", gm.assign(jacobians=[str(tmp_path / "gone.mnc")] * 10))
