@@ -205,6 +205,59 @@ def pinned_numpy(lib, shape, dtype):
     return np.frombuffer(buf, dtype=dtype).reshape(shape), ptr
 
 
+def files_leg(args, core):
+    """From FILES to the result: a study of MINC 2 volumes (config-2 dimensions, uint16, one deflated chunk per slice, per-slice
+    real ranges) written by the test-side writer, decoded by the library's own reader on all host cores into page-locked
+    memory and fitted in its stored type.  What the reference does here: libminc + HDF5, one thread, doubles
+    (src/modelling_functions.c:1037-1055)."""
+    import shutil
+    import tempfile
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+    import h5mini
+    from rminc_b200 import minc2
+    nf = int(os.environ.get("RMG_BENCH_FILES", 32))
+    root = tempfile.mkdtemp(prefix="rmg_files_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        rng = np.random.default_rng(11)
+        base = rng.normal(30000.0, 400.0, DIMS)
+        paths, t_w = [], time.perf_counter()
+        for j in range(nf):
+            vol = np.clip(np.rint(base + rng.normal(0.0, 150.0, DIMS)), 0, 65535).astype(np.uint16)
+            lo = rng.normal(-0.8, 0.05, DIMS[0])
+            f = os.path.join(root, f"s{j:03d}.mnc")
+            h5mini.write_minc2(f, vol, image_min=lo, image_max=lo + rng.uniform(1.5, 2.5, DIMS[0]), valid_range=(0, 65535),
+                               chunks=(1, DIMS[1], DIMS[2]), compress=1)
+            paths.append(f)
+        t_w = time.perf_counter() - t_w
+        fbytes = sum(os.path.getsize(f) for f in paths)
+        V = int(np.prod(DIMS))
+        X = design(nf) if nf > 8 else design(N_SUBJ)[:nf]
+        threads = minc2.host_threads()
+        t0 = time.perf_counter()
+        U1 = minc2.read_table(paths[:2], n_threads=1)[0]
+        t_one = (time.perf_counter() - t0) / 2
+        del U1
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            U, lo, hi, vr, info = minc2.read_table(paths, pinned=True)
+            t1 = time.perf_counter()
+            out = core.lm_fit_stored(U, X, (hi - lo) / (vr[1] - vr[0]), lo, voxel_min=vr[0], slice_len=info.slice_len)
+            t2 = time.perf_counter()
+            if best is None or t2 - t0 < best[0]:
+                best = (t2 - t0, t1 - t0, t2 - t1)
+            del U
+        assert np.isfinite(out[:, 0]).all()
+        return {"workload": f"{nf} MINC 2 files of 180x252x156 uint16 voxels (deflate, one chunk per slice, per-slice ranges) "
+                            "-> decode on the host -> stored-type fit", "files": nf, "file_bytes": fbytes, "host_threads": threads,
+                "seconds": best[0], "decode_s": best[1], "fit_s": best[2], "voxels_per_s": V / best[0],
+                "decode_stored_gbs": 2.0 * V * nf / best[1] / 1e9, "decode_file_gbs": fbytes / best[1] / 1e9,
+                "one_thread_s_per_file": t_one, "speedup_vs_one_thread": t_one * nf / best[1],
+                "writer_s": t_w, "timing": "wall clock, best of 3 (files in /dev/shm: no disk)"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def single_process_multi(args, core, Yt, X, G, d_ref, perms, idx):
     """Rank 0 alone drives G GPUs through the C ABI (what an R session does): rmg_h2d_probe (the box's concurrent
     host-link ceiling), rmg_lm_fit_multi and rmg_randomize_multi on ONE pinned config-2 matrix strong-sharded over the
@@ -622,11 +675,12 @@ def run_gpu_arm(args):
         stored = {"workload": "the same fit on uint16 voxels + per-slice real ranges (180 slices x 500 files)",
                   "ms_per_step": ms, "voxels_per_s": world * V / (ms * 1e-3), "achieved_gbs": sb / (ms * 1e-3) / 1e9,
                   "frac_of_hbm_peak": sb / (ms * 1e-3) / 1e9 / measured_hbm_peak()[0],
-                  "fp64_ops_per_s": V * n * (3.0 + p) / (ms * 1e-3), "kernel": core.last_fit_variant(),
+                  "fp64_ops_per_s": V * n * (2.25 + p) / (ms * 1e-3), "kernel": core.last_fit_variant(),
                   # scalar FP64 issue limit measured by tools/dfma_bench.cu: one warp-wide DFMA per 2.2 cycles and scheduler
-                  "fp64_issue_floor_ms": V * n * (3.0 + p) / (148 * 4 * 32 / 2.2 * 1.965e9) * 1e3,
-                  "bound": "FP64 pipe co-limits: (3+p) FP64 operations per 2-byte sample (one FMA to expand, shift, "
-                           "square, p projections); RMG_STORED_EXACT=1 (the reader's three roundings): (5+p)"}
+                  "fp64_issue_floor_ms": V * n * (2.25 + p) / (148 * 4 * 32 / 2.2 * 1.965e9) * 1e3,
+                  "bound": "FP64 pipe co-limits: (2.25+p) FP64 operations per 2-byte sample (one FMA to expand with the "
+                           "thread's shift folded in, square, p projections, one offset subtraction per 4 samples); "
+                           "RMG_STORED_EXACT=1 (the reader's three roundings): (5+p)"}
         # the stored-type fit equals the double fit of the expanded samples
         Ye = ((Ut[:, :4096].to(torch.float64) - 0.0) * sc_t[:, :1]) + of_t[:, :1]
         ref = core.lm_fit_torch(Ye, X)
@@ -984,6 +1038,10 @@ def run_gpu_arm(args):
         torch.cuda.empty_cache()
         cfg5 = config5(args, torch, dist, core, dev, rank, world, local_rank, barrier, design)
 
+    files = None
+    if rank == 0 and "files" in args.parts:
+        files = files_leg(args, core)
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and "cpu" in args.parts:
@@ -1006,6 +1064,7 @@ def run_gpu_arm(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
             "masked_variant": masked, "vertexLm": vertex, "covariate": cov, "stored_u16": stored, "vertexTFCE": tfce, "randomize": rand,
             "single_process_multi": multi, "multi_parity": (multi or {}).get("multi_parity"), "config5": cfg5,
+            "from_files": files,
         }
         if e2e is not None and multi is not None:
             e2e["single_process_multi"] = multi.get("fit_e2e")

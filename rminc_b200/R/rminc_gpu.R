@@ -47,7 +47,19 @@ rmincgpu_stage <- function(filenames) {
 }
 
 # Replacement for RMINC:::mincLm_c_wrapper.  `mask` may be a file name or NULL.
+# options(RMINC_GPU_READER = TRUE): the .Call keeps minc2_model's own eleven arguments (R/minc_voxel_statistics.R:695-712)
+# and the library reads the MINC 2 files itself -- all host cores, uint16 / float32 voxels shipped in their stored type --
+# instead of staging doubles through mincGetVolume; the GPU count comes from options(RMINC_GPU_N).
 mincLm_c_wrapper <- function(plm, mask, mask_min, mask_max, n_gpus = rmincgpu_n()) {
+  if (isTRUE(getOption("RMINC_GPU_READER", FALSE))) {
+    old <- options(RMINC_GPU_N = as.integer(n_gpus)); on.exit(options(old))
+    have_mask <- if (is.null(mask)) 0 else 1
+    mm <- if (is.logical(plm$mmatrix)) plm$mmatrix else as.matrix(plm$mmatrix)
+    right <- if (is.logical(plm$data.matrix.right)) plm$data.matrix.right else as.character(plm$data.matrix.right)
+    return(.Call("rmincgpu_minc2_model", as.character(plm$data.matrix.left), right, mm, NULL, as.double(have_mask),
+                 if (is.null(mask)) character(0) else as.character(mask), as.double(mask_min), as.double(mask_max), NULL, NULL,
+                 "lm", PACKAGE = "rmincgpu"))
+  }
   Y <- rmincgpu_stage(as.character(plm$data.matrix.left))
   m <- if (is.null(mask)) NULL else as.double(mincGetVolume(mask))
   if (!is.logical(plm$data.matrix.right)) {

@@ -10,6 +10,7 @@
  * Entry points registered exactly like the reference's (src/RMINC_init.c:57-82):
  *   rmincgpu_vertex_lm_loop  same signature as vertex_lm_loop (src/vertex_modelling.c:8), so
  *                            vertexLm / anatLm only change the routine name
+ *   rmincgpu_minc2_model     minc2_model(method = "lm") with the reference's own arguments: the files are read here
  *   rmincgpu_lm              minc2_model(method = "lm") with the volumes already staged
  *   rmincgpu_lm_cov          the same with filenames_right (a voxel-wise covariate) staged as a second matrix
  *   rmincgpu_lm_stored       the same on volumes in their stored type (uint16 + real ranges, float32)
@@ -630,6 +631,148 @@ SEXP rmincgpu_dataset_fdr(SEXP h, SEXP column, SEXP stat_type, SEXP df)
     return out;
 }
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * minc2_model itself, method "lm", with the reference's own eleven arguments (src/modelling_functions.c:743-745; R caller
+ * mincLm_c_wrapper, R/minc_voxel_statistics.R:695-712): the .Call a maintainer can swap without staging anything in R.
+ * The files are decoded by the library's MINC 2 reader on all host cores straight into page-locked memory -- uint16 /
+ * float32 studies in their stored type (rmg_lm_fit_stored), other types as the real doubles (rmg_lm_fit), a study with
+ * filenames_right as two double matrices (rmg_lm_fit_cov) -- and fitted on options(RMINC_GPU_N) GPUs (default 1).
+ * asgn, rho and nresults belong to the other methods of minc2_model, which stay on the reference's CPU path. */
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+static int gpu_count_option(void)
+{
+    SEXP o = Rf_GetOption1(Rf_install("RMINC_GPU_N"));
+    if (Rf_isNull(o)) return 1;
+    const int g = Rf_asInteger(o);
+    if (g == NA_INTEGER || g < 1) Rf_error("options(RMINC_GPU_N) must be a positive number of GPUs");
+    return g;
+}
+
+static void *staging_alloc(size_t bytes, int *pinned)
+{
+    void *p = rmg_host_alloc(bytes ? bytes : 1);
+    *pinned = p != NULL;
+    return p ? p : malloc(bytes ? bytes : 1);
+}
+
+static void staging_free(void *p, int pinned)
+{
+    if (!p) return;
+    if (pinned) rmg_host_free(p);
+    else free(p);
+}
+
+SEXP rmincgpu_minc2_model(SEXP filenames, SEXP filenames_right, SEXP mmatrix, SEXP asgn, SEXP have_mask, SEXP mask,
+                          SEXP mask_lower, SEXP mask_upper, SEXP rho, SEXP nresults, SEXP method)
+{
+    (void)asgn; (void)rho; (void)nresults;
+    if (TYPEOF(method) != STRSXP || Rf_length(method) < 1 || strcmp(CHAR(STRING_ELT(method, 0)), "lm") != 0)
+        Rf_error("rmincgpu_minc2_model runs method \"lm\"; the other methods of minc2_model stay on the CPU path");
+    if (TYPEOF(filenames) != STRSXP || Rf_length(filenames) < 1) Rf_error("filenames must be a character vector");
+    const int n = Rf_length(filenames);
+    const int cov = TYPEOF(filenames_right) == STRSXP;
+    if (cov && Rf_length(filenames_right) != n) Rf_error("filenames_right must name one volume per subject");
+    const int has_static = !Rf_isLogical(mmatrix);
+    if (has_static && (!Rf_isReal(mmatrix) || Rf_nrows(mmatrix) != n)) Rf_error("model matrix does not match the number of files");
+    if (!cov && !has_static) Rf_error("mmatrix must be a double model matrix");
+    const int ps = has_static ? Rf_ncols(mmatrix) : 0;
+    const int p = cov ? (has_static ? ps + 1 : 2) : ps;
+    const int masked = Rf_asReal(have_mask) == 1.0;
+    if (masked && (TYPEOF(mask) != STRSXP || Rf_length(mask) < 1)) Rf_error("mask must be a file name");
+    const int ngpu = gpu_count_option(), device = gpu_device();
+    const double lo = Rf_asReal(mask_lower), hi = Rf_asReal(mask_upper);
+    long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+    if (ncpu < 1) ncpu = 1;
+
+    char err[512] = "";
+    rmg_minc2_volume *first = NULL;
+    rmg_minc2_info info;
+    int rc = rmg_minc2_open(CHAR(STRING_ELT(filenames, 0)), &first, err, sizeof err);
+    check(rc, err);                                           /* "Error opening input file: <name>." like :809 */
+    rmg_minc2_get_info(first, &info);
+    rmg_minc2_close(first);
+    const int64_t V = info.nvoxels;
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, matrix_rows((R_xlen_t)V), 2 * p + 3));
+    const char **paths = (const char **)R_alloc((size_t)n, sizeof(char *));
+    const char **paths_right = (const char **)R_alloc((size_t)n, sizeof(char *));
+    for (int j = 0; j < n; ++j) {
+        paths[j] = CHAR(STRING_ELT(filenames, j));
+        paths_right[j] = cov ? CHAR(STRING_ELT(filenames_right, j)) : NULL;
+    }
+    double *m = NULL;
+    if (masked) {                                             /* the mask as doubles, whatever its stored type */
+        rmg_minc2_volume *mv = NULL;
+        rmg_minc2_info mi;
+        rc = rmg_minc2_open(CHAR(STRING_ELT(mask, 0)), &mv, err, sizeof err);
+        if (rc == RMG_OK) {
+            rmg_minc2_get_info(mv, &mi);
+            if (mi.nvoxels != V) {
+                rmg_minc2_close(mv);
+                UNPROTECT(1);
+                Rf_error("Mask Volume input volume dimension mismatch.");
+            }
+            m = (double *)R_alloc((size_t)(V > 0 ? V : 1), sizeof(double));
+            rc = rmg_minc2_read_real(mv, m, V, (int)ncpu, err, sizeof err);
+            rmg_minc2_close(mv);
+        }
+        if (rc != RMG_OK) {
+            UNPROTECT(1);
+            check(rc, err);
+        }
+    }
+    const int stored = !cov && (info.dtype == RMG_MINC2_U16 || info.dtype == RMG_MINC2_F32);
+    const int64_t ld = V > 0 ? V : 1;
+    int pin_a = 0, pin_b = 0;
+    void *A = NULL, *B = NULL;
+    double *rmin = NULL, *rmax = NULL;
+    if (stored) {
+        const int dt = info.dtype == RMG_MINC2_U16 ? RMG_STORED_U16 : RMG_STORED_F32;
+        const size_t es = dt == RMG_STORED_U16 ? 2 : 4;
+        const int64_t nsl = info.nslices > 0 ? info.nslices : 1;
+        A = staging_alloc((size_t)ld * n * es, &pin_a);
+        rmin = (double *)malloc(sizeof(double) * (size_t)nsl * n);
+        rmax = (double *)malloc(sizeof(double) * (size_t)nsl * n);
+        double vr[2] = {0.0, 1.0};
+        if (!A || !rmin || !rmax) { rc = RMG_ERR_INVALID; strcpy(err, "out of host memory while staging the volumes"); }
+        else rc = rmg_minc2_read_table(paths, n, A, ld, info.dtype, rmin, rmax, nsl, vr, (int)ncpu, err, sizeof err);
+        if (rc == RMG_OK && dt == RMG_STORED_U16) {           /* image-min / image-max -> scale / offset, in place */
+            for (int64_t i = 0; i < nsl * n; ++i) rmax[i] = (rmax[i] - rmin[i]) / (vr[1] - vr[0]);
+        }
+        if (rc == RMG_OK)
+            rc = ngpu > 1 ? rmg_lm_fit_stored_multi(A, dt, V, ld, n, rmax, rmin, vr[0], nsl > 1 ? info.slice_len : ld, REAL(mmatrix),
+                                                    p, m, lo, hi, REAL(out), ld, ngpu, err, sizeof err)
+                          : rmg_lm_fit_stored(A, dt, V, ld, n, rmax, rmin, vr[0], nsl > 1 ? info.slice_len : ld, REAL(mmatrix), p, m,
+                                              lo, hi, REAL(out), ld, device, err, sizeof err);
+    } else {
+        A = staging_alloc((size_t)ld * n * sizeof(double), &pin_a);
+        if (cov) B = staging_alloc((size_t)ld * n * sizeof(double), &pin_b);
+        if (!A || (cov && !B)) { rc = RMG_ERR_INVALID; strcpy(err, "out of host memory while staging the volumes"); }
+        else rc = rmg_minc2_read_table(paths, n, A, ld, RMG_MINC2_F64, NULL, NULL, 1, NULL, (int)ncpu, err, sizeof err);
+        if (rc == RMG_OK && cov) rc = rmg_minc2_read_table(paths_right, n, B, ld, RMG_MINC2_F64, NULL, NULL, 1, NULL, (int)ncpu, err, sizeof err);
+        if (rc == RMG_OK) {
+            if (cov)
+                rc = ngpu > 1 ? rmg_lm_fit_cov_multi((const double *)A, (const double *)B, V, ld, n, has_static ? REAL(mmatrix) : NULL,
+                                                     ps, m, lo, hi, REAL(out), ld, ngpu, err, sizeof err)
+                              : rmg_lm_fit_cov((const double *)A, (const double *)B, V, ld, n, has_static ? REAL(mmatrix) : NULL, ps, m,
+                                               lo, hi, REAL(out), ld, device, err, sizeof err);
+            else
+                rc = ngpu > 1 ? rmg_lm_fit_multi((const double *)A, V, ld, n, REAL(mmatrix), p, m, lo, hi, REAL(out), ld, ngpu, err, sizeof err)
+                              : rmg_lm_fit((const double *)A, V, ld, n, REAL(mmatrix), p, m, lo, hi, REAL(out), ld, device, err, sizeof err);
+        }
+    }
+    staging_free(A, pin_a);
+    staging_free(B, pin_b);
+    free(rmin);
+    free(rmax);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
+
 /* kernel launches issued by the library since it was loaded: lets a test assert that a call really ran on the GPU */
 SEXP rmincgpu_launch_count(void)
 {
@@ -662,6 +805,7 @@ static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_dataset_anova", (DL_FUNC)&rmincgpu_dataset_anova, 3},
     {"rmincgpu_dataset_randomize", (DL_FUNC)&rmincgpu_dataset_randomize, 5},
     {"rmincgpu_dataset_fdr", (DL_FUNC)&rmincgpu_dataset_fdr, 4},
+    {"rmincgpu_minc2_model", (DL_FUNC)&rmincgpu_minc2_model, 11},
     {"rmincgpu_launch_count", (DL_FUNC)&rmincgpu_launch_count, 0},
     {NULL, NULL, 0}};
 

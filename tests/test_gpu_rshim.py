@@ -95,6 +95,66 @@ def test_minc2_model_and_per_voxel_anova_against_the_reference_routines(R, oracl
     assert_rows_match(got, ref, RTOL, "per_voxel_anova")
 
 
+def test_minc2_model_routine_on_files_against_the_reference_routine(R, oracle, tmp_path):
+    """.Call("rmincgpu_minc2_model", <minc2_model's eleven arguments>) on MINC 2 FILES (uint16, per-slice ranges, chunked +
+    deflate; a uint8 label mask; then int16 volumes, then a covariate study) against .Call("minc2_model", ...) of the
+    reference's object code on in-memory volumes that hold the doubles libminc's reader would have produced."""
+    need_ref(R)
+    import h5mini
+    from rminc_b200 import api
+    dims = (12, 10, 9)
+    Y, X, mask = cfg1_data(dims=dims)
+    V, n = Y.shape
+    files, cols = [], []
+    for j in range(n):
+        real = Y[:, j].reshape(dims)
+        lo, hi = real.min(axis=(1, 2)) - 0.01, real.max(axis=(1, 2)) + 0.01
+        vox = np.round((real - lo[:, None, None]) / (hi - lo)[:, None, None] * 65535.0).astype(np.uint16)
+        f = str(tmp_path / f"s{j:02d}.mnc")
+        h5mini.write_minc2(f, vox, image_min=lo, image_max=hi, valid_range=(0, 65535), chunks=(1, 10, 9), compress=4)
+        files.append(f)
+        cols.append(api.StoredVolume(vox, image_min=lo, image_max=hi).real())
+    Yq = np.asfortranarray(np.stack(cols, axis=1))
+    mfile = str(tmp_path / "mask.mnc")
+    h5mini.write_minc2(mfile, (mask.reshape(dims) * 2).astype(np.uint8), valid_range=(0, 255), chunks=dims)
+    F = rcall.Strings(files)
+    for lo, hi, m in ((1.0, 99999999.0, mask * 2), (2.0, 2.0, mask * 2), (1.0, 99999999.0, None)):
+        ref = reference_minc2_model(R, Yq, dims, X, m, lo, hi)
+        got = R.call("rmincgpu_minc2_model", F, rcall.NA_MATRIX, X, None, float(m is not None),
+                     rcall.Strings([mfile] if m is not None else []), lo, hi, None, None, rcall.Strings(["lm"]))
+        inside = np.ones(V, bool) if m is None else (m > lo - 0.5) & (m < hi + 0.5)
+        assert_rows_match(got[inside], ref[inside], RTOL, f"minc2_model on files lo={lo}")
+        assert (got[~inside] == 0).all()
+    # other stored types take the real-valued route; two GPUs (when present) give the same matrix
+    f16 = []
+    for j in range(n):
+        real = Y[:, j].reshape(dims)
+        vox = np.round((real - real.min()) / (real.max() - real.min()) * 65535.0 - 32768.0).astype(np.int16)
+        f = str(tmp_path / f"i{j:02d}.mnc")
+        h5mini.write_minc2(f, vox, image_min=real.min(), image_max=real.max(), valid_range=(-32768, 32767), chunks=(3, 10, 9))
+        f16.append(f)
+    Y16 = np.asfortranarray(np.stack([api.default_reader(f) for f in f16], axis=1))
+    ref = reference_minc2_model(R, Y16, dims, X, None, 1.0, 99999999.0)
+    args = (rcall.Strings(f16), rcall.NA_MATRIX, X, None, 0.0, rcall.Strings([]), 1.0, 99999999.0, None, None, rcall.Strings(["lm"]))
+    got = R.call("rmincgpu_minc2_model", *args)
+    assert_rows_match(got, ref, RTOL, "minc2_model on int16 files")
+    from rminc_b200 import core
+    if core.device_count() >= 2:
+        R.options(RMINC_GPU_N=2)
+        try:
+            np.testing.assert_array_equal(R.call("rmincgpu_minc2_model", *args), got)
+            got2 = R.call("rmincgpu_minc2_model", F, rcall.NA_MATRIX, X, None, 0.0, rcall.Strings([]), 1.0, 99999999.0, None, None,
+                          rcall.Strings(["lm"]))
+        finally:
+            R.options(RMINC_GPU_N=None)
+        assert_rows_match(got2, reference_minc2_model(R, Yq, dims, X, None, 1.0, 99999999.0), RTOL, "2 GPUs, stored type")
+    # filenames_right: the per-voxel design [mmatrix | z_v] (src/modelling_functions.c:848-854, 1137-1143)
+    gotc = R.call("rmincgpu_minc2_model", F, rcall.Strings(f16), X[:, :1].copy(), None, 0.0, rcall.Strings([]), 1.0, 99999999.0, None, None,
+                  rcall.Strings(["lm"]))
+    wantc = R.call("rmincgpu_lm_cov", Yq, Y16, X[:, :1].copy(), None, 1.0, 99999999.0)
+    np.testing.assert_array_equal(gotc, wantc)
+
+
 def test_error_path_is_an_r_error_with_the_references_message(R):
     """dpotri info > 0: the reference calls error("element (%d, %d) is zero, so the inverse cannot be computed")
     (src/modelling_functions.c:551-557); so does the shim, through Rf_error's longjmp, leaving nothing behind."""

@@ -79,7 +79,29 @@ def every_routine_call(n=12, V=40):
         "rmincgpu_randomize_volume_tfce": (Y, X, None, 1.0, 99999999.0, idx, cols, True, np.array([2.0, 4.0, 5.0]), 6, 1.0, 0.25,
                                            0.5, 2.0, 0, 1),
         "rmincgpu_dataset_create": (Y, mask, 1.0, 99999999.0, 1),
+        "rmincgpu_minc2_model": (rcall.Strings(minc2_study(U, scale, offset)), na, X, None, 0.0, rcall.Strings([]), 1.0, 99999999.0, None,
+                                 None, rcall.Strings(["lm"])),
     }
+
+
+_study_dir = None
+
+
+def minc2_study(U, scale, offset, shape=(4, 2, 5)):
+    """One MINC 2 file per column of U (uint16, `shape` voxels, per-slice ranges from scale / offset), written once."""
+    global _study_dir
+    import tempfile
+    import h5mini
+    if _study_dir is None:
+        _study_dir = tempfile.mkdtemp(prefix="rmg_minc2_")
+    names = []
+    for j in range(U.shape[1]):
+        nm = os.path.join(_study_dir, f"s{j:03d}_{U.shape[0]}.mnc")
+        if not os.path.exists(nm):
+            h5mini.write_minc2(nm, U[:, j].reshape(shape), image_min=offset[:, j], image_max=offset[:, j] + 65535.0 * scale[:, j],
+                               valid_range=(0, 65535), chunks=(1,) + shape[1:])
+        names.append(nm)
+    return names
 
 
 @pytest.mark.skipif(have_gpu(), reason="only meaningful on a machine without a CUDA device")
@@ -102,6 +124,43 @@ def test_every_routine_runs_and_raises_the_no_device_error(R):
         args = [np.zeros(3)] + [np.zeros((2, 2))] * (registered[name] - 1)
         with pytest.raises(rcall.RError, match="not a GPU dataset handle"):
             R.call(name, *args)
+
+
+def test_minc2_model_routine_validates_and_reports_like_the_reference(R, tmp_path):
+    """rmincgpu_minc2_model takes minc2_model's own eleven arguments (src/modelling_functions.c:743-745): a missing file is
+    the reference's "Error opening input file" (:809), a mask of another size its dimension-mismatch error, methods other
+    than "lm" are refused -- all before any device is needed -- and the staging memory is released on every path."""
+    import h5mini
+    c = every_routine_call()
+    args = list(c["rmincgpu_minc2_model"])
+    files = list(args[0])
+
+    def with_(i, v):
+        a = list(args)
+        a[i] = v
+        return a
+
+    with pytest.raises(rcall.RError, match=r"Error opening input file: /nonexistent/a.mnc\."):
+        R.call("rmincgpu_minc2_model", *with_(0, rcall.Strings(["/nonexistent/a.mnc"] + files[1:])))
+    if not have_gpu():
+        with pytest.raises(rcall.RError, match="Error opening input file: .*gone.mnc"):      # not the first file: found while staging
+            R.call("rmincgpu_minc2_model", *with_(0, rcall.Strings(files[:-1] + [str(tmp_path / "gone.mnc")])))
+    with pytest.raises(rcall.RError, match='runs method "lm"'):
+        R.call("rmincgpu_minc2_model", *with_(10, rcall.Strings(["ttest"])))
+    with pytest.raises(rcall.RError, match="model matrix does not match the number of files"):
+        R.call("rmincgpu_minc2_model", *with_(0, rcall.Strings(files[:-1])))
+    small = str(tmp_path / "smallmask.mnc")
+    h5mini.write_minc2(small, np.ones((2, 2, 5), dtype=np.uint8), valid_range=(0, 255))
+    a = with_(4, 1.0)
+    a[5] = rcall.Strings([small])
+    with pytest.raises(rcall.RError, match="Mask Volume input volume dimension mismatch"):
+        R.call("rmincgpu_minc2_model", *a)
+    R.options(RMINC_GPU_N=0)
+    try:
+        with pytest.raises(rcall.RError, match="RMINC_GPU_N"):
+            R.call("rmincgpu_minc2_model", *args)
+    finally:
+        R.options(RMINC_GPU_N=None)
 
 
 def test_stored_type_arguments_are_validated_before_the_abi(R):
