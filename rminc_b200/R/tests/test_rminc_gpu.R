@@ -22,6 +22,20 @@ test_that("mincLm: every column of every voxel, masked rows zero", {
   expect_true(all(got[!inside, ] == 0))
 })
 
+test_that("minc2_model's own .Call, files read by the library's MINC 2 reader (libminc-written, chunked + deflated files)", {
+  # the one check this repository cannot run itself: real libminc / libhdf5 files through minc2_reader.cpp
+  files <- as.character(gf$jacobians_fixed_2)
+  X <- model.matrix(~ Sex + Age, gf)
+  ref <- .Call("minc2_model", files, matrix(NA), X, NULL, 1, mask, 1, 99999999, NULL, NULL, "lm", PACKAGE = "RMINC")
+  got <- .Call("rmincgpu_minc2_model", files, matrix(NA), X, NULL, 1, mask, 1, 99999999, NULL, NULL, "lm", PACKAGE = "rmincgpu")
+  inside <- mincGetVolume(mask) > 0.5
+  expect_equal(got[inside, ], ref[inside, ], tolerance = tol, check.attributes = FALSE)
+  old <- options(RMINC_GPU_READER = TRUE)
+  plm <- RMINC:::parseLmFormula(jacobians_fixed_2 ~ Sex + Age, gf, NULL)
+  expect_equal(mincLm_c_wrapper(plm, mask, 1, 99999999)[inside, ], ref[inside, ], tolerance = tol, check.attributes = FALSE)
+  options(old)
+})
+
 test_that("vertexLm / anatLm native loop keeps its signature", {
   Y <- matrix(rnorm(500 * nrow(gf)), ncol = nrow(gf))
   X <- model.matrix(~ Sex + Age, gf)
