@@ -11,6 +11,7 @@ Result columns (src/modelling_functions.c:1159-1174):
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -664,6 +665,22 @@ class Dataset:
         _lib.check(rc, err)
         self._keep = (Y, m)          # pinned sources may still be read by the queued upload until sync()
         self.n_gpus = lib.rmg_dataset_gpus(self._handle)
+
+    @classmethod
+    def from_minc2(cls, filenames, mask=None, mask_lo=DEFAULT_MASK_LO, mask_hi=DEFAULT_MASK_HI, n_gpus=None, n_threads=None):
+        """The resident dataset of a study of MINC 2 files: decoded by the library's reader on the host cores into pinned
+        memory (uint16 / float32 studies in their stored type, expanded once on the devices; other types as doubles) and
+        uploaded in voxel shards.  `mask` may be a MINC 2 file, an array or None.  What mincLm(files) followed by
+        mincRandomize / mincAnova / mincFDR re-reads from disk every time (R/minc_voxel_statistics.R:911-912, 1457-1477)."""
+        from . import minc2
+        U, lo, hi, vr, info = minc2.read_table(list(filenames), n_threads=n_threads, pinned=device_count() > 0)
+        if isinstance(mask, (str, os.PathLike)):
+            with minc2.Minc2Volume(mask) as mv:
+                mask = mv.real()
+        if U.dtype == np.uint16:
+            return cls(U, mask=mask, mask_lo=mask_lo, mask_hi=mask_hi, n_gpus=n_gpus, scale=(hi - lo) / (vr[1] - vr[0]), offset=lo,
+                       voxel_min=vr[0], slice_len=info.slice_len if info.nslices > 1 else max(U.shape[0], 1))
+        return cls(U, mask=mask, mask_lo=mask_lo, mask_hi=mask_hi, n_gpus=n_gpus)
 
     def _h(self):
         if not self._handle:

@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 
 #include "async_ptx.cuh"
@@ -369,7 +370,7 @@ lm_fit_ldg_kernel(LmArgs a, int JT)
             for (int u = 0; u < U; ++u) {
                 const double *src = yp + (int64_t)(jb + t0 + jj + u) * a.ldY;
                 if constexpr (VPT == 2) {
-                    const double2 t = ldg_stream2(src);
+                    const double2 t = ldg_stream2_hint(src, a.l2_hint);
                     y[u][0] = t.x;
                     y[u][1] = t.y;
                 } else {
@@ -602,6 +603,9 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
         if (info) info->launches += 3;
         ac.pair_list = list;
         ac.n_pairs = n_pairs;
+        // compacted runs: fetch no more than 64 bytes around what the loads touch (RMG_LDG_L2 = 0 / 64 / 128 / 256 overrides)
+        static const int env_hint = [] { const char *s_ = std::getenv("RMG_LDG_L2"); return s_ ? std::atoi(s_) : -1; }();
+        ac.l2_hint = env_hint >= 0 ? env_hint : 64;
     }
     auto go = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

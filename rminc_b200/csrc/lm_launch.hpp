@@ -26,6 +26,7 @@ struct LmArgs {
     // voxel and their count, both device-resident; null = process every pair
     const uint32_t *pair_list = nullptr;
     const unsigned int *n_pairs = nullptr;
+    int l2_hint = 0;           // direct-load kernel: L2 prefetch size of the sample loads in bytes (0 = the default policy)
 };
 
 enum class LmVariant { Auto = 0, Tma = 1, Ldg = 2 };

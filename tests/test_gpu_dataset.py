@@ -121,6 +121,40 @@ def test_dataset_from_stored_volumes(core, oracle):
         assert_rows_match(ds.lm_fit(X), oracle.vertex_lm_loop(F.astype(np.float64), X), RTOL, "float32 dataset")
 
 
+def test_dataset_from_minc2_files(core, oracle, tmp_path):
+    """Files -> resident dataset -> fit, permutation test, anova on one decode and one upload; the mask is a MINC 2 label
+    volume.  Equals the oracle on the doubles libminc's reader would have produced."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import h5mini
+    from rminc_b200 import api
+    rng = np.random.default_rng(12)
+    dims, n = (9, 14, 12), 24
+    V = int(np.prod(dims))
+    files, cols_real = [], []
+    for j in range(n):
+        vox = np.round(rng.normal(30000, 400, dims)).astype(np.uint16)
+        lo = rng.normal(-0.8, 0.05, dims[0])
+        hi = lo + rng.uniform(1.5, 2.5, dims[0])
+        f = str(tmp_path / f"s{j:02d}.mnc")
+        h5mini.write_minc2(f, vox, image_min=lo, image_max=hi, valid_range=(0, 65535), chunks=(1, 14, 12))
+        files.append(f)
+        cols_real.append(api.StoredVolume(vox, image_min=lo, image_max=hi).real())
+    Yx = np.asfortranarray(np.stack(cols_real, axis=1))
+    mask = ellipsoid_mask(dims)
+    mfile = str(tmp_path / "mask.mnc")
+    h5mini.write_minc2(mfile, mask.reshape(dims).astype(np.uint8), valid_range=(0, 255))
+    X = design_cfg2(n)
+    idx = perm_indices(n, 11)
+    for G in gpu_counts(core):
+        with core.Dataset.from_minc2(files, mask=mfile, n_gpus=G) as ds:
+            assert (ds.V, ds.n) == (V, n)
+            assert_rows_match(ds.lm_fit(X), oracle.minc2_model_lm(Yx, (1, 1, V), X, mask=mask), RTOL, f"minc2 dataset G={G}")
+            np.testing.assert_allclose(ds.randomize(X, idx, [6, 7, 8, 9]), oracle.randomize(Yx, X, idx, [6, 7, 8, 9], mask=mask),
+                                       rtol=RTOL, atol=0)
+
+
 def test_dataset_error_contract(core):
     Y, X, mask = cfg1_data(dims=(8, 8, 8))
     n = X.shape[0]
