@@ -687,6 +687,32 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         scl = torch.maximum(ref.abs(), ref.square().mean(dim=1, keepdim=True).sqrt())
         assert bool(((os_[:, :4096] - ref).abs() <= 1e-9 * scl).all()), "stored-type result differs from the double fit"
+        if rank == 0:
+            # the everyday form of the call: uint16 files AND a mask (38 % ellipsoid)
+            z, y, x = np.meshgrid(*[np.arange(d) for d in DIMS], indexing="ij")
+            c = [(d - 1) / 2 for d in DIMS]
+            inside = sum(((a - cc) / (0.45 * d)) ** 2 for a, cc, d in zip((z, y, x), c, DIMS)) <= 1
+            mt = torch.from_numpy(inside.reshape(-1).astype(np.float64)).to(dev)
+            for _ in range(2):
+                core.lm_fit_stored_torch(Ut, X, sc_t, of_t, slice_len=slice_len, mask=mt, out=os_)
+            torch.cuda.synchronize()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record(stream)
+            for _ in range(args.steps):
+                core.lm_fit_stored_torch(Ut, X, sc_t, of_t, slice_len=slice_len, mask=mt, out=os_)
+            m1.record(stream)
+            torch.cuda.synchronize()
+            stored["masked"] = {"inside_frac": float(inside.mean()), "ms_per_step": m0.elapsed_time(m1) / args.steps,
+                                "kernel": core.last_fit_variant()}
+            sel = torch.nonzero(mt[:65536] > 0.5).flatten()[:2048]
+            if sel.numel():
+                Ym = ((Ut[:, sel].to(torch.float64) - 0.0) * sc_t[:, :1]) + of_t[:, :1]
+                refm = core.lm_fit_torch(Ym, X)
+                torch.cuda.synchronize()
+                sclm = torch.maximum(refm.abs(), refm.square().mean(dim=1, keepdim=True).sqrt())
+                assert bool(((os_[:, sel] - refm).abs() <= 1e-9 * sclm).all()), "masked stored-type result differs from the double fit"
+            assert bool((os_[:, mt < 0.5] == 0).all()), "masked rows of the stored-type fit are not +0.0"
+            del mt
         del os_, Ye
 
     # ---- vertexTFCE randomisation: config-3-sized surface (grid graph stand-in for the mesh), all t columns

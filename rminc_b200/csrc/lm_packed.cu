@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <type_traits>
 
 #include "async_ptx.cuh"
@@ -451,6 +452,315 @@ lm_fit_packed_kernel(PackedArgs a, int JT)
 }
 
 
+// ------------------------------------------------------------------ masked fits on stored volumes: compacted quads
+// The everyday call -- uint16 files AND a mask -- used to cost as much as the unmasked fit: the direct-load kernel above
+// visits every voxel and only skips the loads of masked ones.  Here three small kernels turn the mask into an ascending list of
+// voxel QUADS (4 adjacent voxels = one 8-byte load of uint16 samples) that contain a selected voxel and write the +0.0 rows of all
+// other quads (the double path's pair compaction, lm_kernels.cu); the fit kernel then gives every thread one LISTED quad, so
+// all lanes of the FP64-bound loop do useful work, and its loads carry a 64-byte L2 prefetch size (runs of selected voxels are
+// ~190 bytes per subject: the default 128 bytes around each load would fetch half as much again).  Arithmetic as the TMA
+// variant: w = 1 + u 2^-20 and one fused multiply-add per sample, ONE shift per quad folded into the offsets (FOLD), or the
+// reader's three roundings (RMG_STORED_EXACT=1).
+constexpr int kQuadBlock = 1024;   // quads per compaction block
+
+__device__ __forceinline__ bool quad_selected(const double *__restrict__ mask, int64_t q, int64_t V, double lo, double hi)
+{
+    const int64_t v = q * 4;
+    bool sel = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (v + i < V) sel |= mask_selects(__ldg(mask + v + i), lo, hi);
+    return sel;
+}
+
+__global__ void __launch_bounds__(kQuadBlock)
+quad_count_kernel(const double *__restrict__ mask, int64_t V, double lo, double hi, unsigned int *__restrict__ counts)
+{
+    const int64_t q = (int64_t)blockIdx.x * kQuadBlock + threadIdx.x;
+    const int c = __syncthreads_count(quad_selected(mask, q, V, lo, hi));
+    if (threadIdx.x == 0) counts[blockIdx.x] = (unsigned int)c;
+}
+
+// exclusive scan of the per-block counts by one block; total -> *n_quads
+__global__ void __launch_bounds__(1024)
+quad_scan_kernel(unsigned int *__restrict__ counts, int nblocks, unsigned int *__restrict__ n_quads)
+{
+    __shared__ unsigned int warp_sums[32];
+    __shared__ unsigned int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned int x = i < nblocks ? counts[i] : 0u;
+        unsigned int incl = x;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned int w = warp_sums[threadIdx.x], wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int y = __shfl_up_sync(0xffffffffu, wi, o);
+                if (threadIdx.x >= o) wi += y;
+            }
+            warp_sums[threadIdx.x] = wi - w;
+        }
+        __syncthreads();
+        const unsigned int excl = carry + warp_sums[threadIdx.x >> 5] + incl - x;
+        if (i < nblocks) counts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_quads = carry;
+}
+
+__global__ void __launch_bounds__(kQuadBlock)
+quad_compact_kernel(const double *__restrict__ mask, int64_t V, double lo, double hi, const unsigned int *__restrict__ offsets,
+                    uint32_t *__restrict__ list, double *__restrict__ out, int64_t ldOut, int ncol, int vec2)
+{
+    __shared__ unsigned int warp_sums[32];
+    const int64_t q = (int64_t)blockIdx.x * kQuadBlock + threadIdx.x;
+    const bool sel = quad_selected(mask, q, V, lo, hi);
+    const unsigned int ballot = __ballot_sync(0xffffffffu, sel);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_sums[warp] = __popc(ballot);
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int w = warp_sums[lane], wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    if (sel) {
+        list[offsets[blockIdx.x] + warp_sums[warp] + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)q;
+    } else if (q * 4 < V) {
+        // V % 4 == 0 (host): the quad is whole; with out 16-byte aligned and ldOut even its rows take two 16-byte stores a column
+        if (vec2) {
+            double2 *o = reinterpret_cast<double2 *>(out + q * 4);
+            const int64_t ld2 = ldOut / 2;
+            const double2 z = make_double2(0.0, 0.0);
+#pragma unroll 4
+            for (int c = 0; c < ncol; ++c) {
+                o[(int64_t)c * ld2] = z;
+                o[(int64_t)c * ld2 + 1] = z;
+            }
+        } else {
+            for (int c = 0; c < ncol; ++c)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) out[q * 4 + i + (int64_t)c * ldOut] = 0.0;
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ typename Stored<T>::Raw load_raw_64b(const T *p);
+template <>
+__device__ __forceinline__ uint2 load_raw_64b<uint16_t>(const uint16_t *p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+template <>
+__device__ __forceinline__ float4 load_raw_64b<float>(const float *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+// the four packed uint16 samples of a quad as w = 1 + u 2^-20 (see load_unit20_smem)
+__device__ __forceinline__ void unit20_from_raw(const uint2 &r, double (&w)[4])
+{
+    w[0] = __hiloint2double((int)__byte_perm(r.x, 0x3ff00000u, 0x7610), 0);
+    w[1] = __hiloint2double((int)__byte_perm(r.x, 0x3ff00000u, 0x7632), 0);
+    w[2] = __hiloint2double((int)__byte_perm(r.y, 0x3ff00000u, 0x7610), 0);
+    w[3] = __hiloint2double((int)__byte_perm(r.y, 0x3ff00000u, 0x7632), 0);
+}
+
+template <int KP, typename T, bool FOLD>
+__global__ void __launch_bounds__(128, KP <= 4 ? 4 : (KP <= 6 ? 3 : (KP <= 8 ? 2 : 1)))
+lm_fit_packed_quads_kernel(PackedArgs a, const uint32_t *__restrict__ list, const unsigned int *__restrict__ n_quads, int JT)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SmemDesign<KP> sd;
+    constexpr bool SC = Stored<T>::kScaled;
+    constexpr bool FD = SC && FOLD;
+    constexpr int TS = (KP + 1) & ~1;
+    constexpr int QW = TS + (SC ? 4 : 0);
+    constexpr double kOne = 1048576.0;                  // the value of w's leading 1 in stored counts (2^20)
+    const unsigned int nq = *n_quads;
+    if ((int64_t)blockIdx.x * 128 >= (int64_t)nq) return;      // whole block past the list
+    double *sQ = reinterpret_cast<double *>(smem_raw);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int n = a.n;
+    const T *U = static_cast<const T *>(a.U);
+    load_design_to_smem<KP>(sd, a.design, tid, nthreads);
+    __syncthreads();
+
+    const int64_t slot = (int64_t)blockIdx.x * 128 + tid;
+    const bool have = slot < (int64_t)nq;
+    const int64_t v = have ? (int64_t)list[slot] * 4 : 0;
+    const int64_t vb = (int64_t)list[(int64_t)blockIdx.x * 128] * 4;     // first voxel of the block's first quad
+    bool act[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) act[i] = have && mask_selects(__ldg(a.mask + v + i), a.mask_lo, a.mask_hi);   // V % 4 == 0 (host)
+    const int64_t sl_a = SC ? min((a.v_base + vb) / a.slice_len, a.nslices - 1) : 0;
+    const int64_t sl_b = min(sl_a + 1, a.nslices - 1);
+    int64_t sl[4];
+    bool same = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sl[i] = SC ? min((a.v_base + v + i) / a.slice_len, a.nslices - 1) : 0;
+        same &= sl[i] == sl[0];
+    }
+    const bool fast = !SC || (same && sl[0] <= sl_b);
+    const int tsel = TS + ((SC && sl[0] != sl_a) ? 2 : 0);
+    const double cm = a.cmagic;
+    const double vmin1 = (cm - 4503599627370496.0) + kOne;      // voxel_min + 2^20, an exact integer
+    VoxelSums<KP> sum[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) sum[i].e[k] = 0.0;
+        sum[i].yy = 0.0;
+        sum[i].y0 = 0.0;
+    }
+    // ONE shift per quad: the value of its first voxel in the first subject (the exact recomputation uses the same one)
+    double shift = 0.0;
+    if (sd.shift && have) {
+        shift = Stored<T>::load1(U + v, cm);
+        if (SC) shift = descale(shift, __ldg(a.scale + sl[0]), __ldg(a.offset + sl[0]));
+    }
+    const T *up = U + v;
+    constexpr int UNR = 8;
+
+    for (int t0 = 0; t0 < n; t0 += JT) {
+        __syncthreads();
+        const int cnt = min(JT, n - t0);
+        for (int i = tid; i < cnt * QW; i += nthreads) {
+            const int j = t0 + i / QW, c = i % QW;
+            double val = 0.0;
+            if (c < KP) val = a.Qt[(size_t)j * KP + c];
+            else if (SC && c >= TS) {
+                const int64_t s_ = (c - TS) < 2 ? sl_a : sl_b;
+                const double sc = a.scale[s_ + (int64_t)j * a.nslices], of = a.offset[s_ + (int64_t)j * a.nslices];
+                if (FD) val = ((c - TS) & 1) ? fma(-sc, vmin1, of) : sc * kOne;      // (A, C) of the one-FMA form
+                else val = ((c - TS) & 1) ? of : sc;
+            }
+            sQ[i] = val;
+        }
+        __syncthreads();
+        if (!have) continue;
+
+        auto run = [&](auto fast_tag) {
+            constexpr bool FAST = decltype(fast_tag)::value;
+            auto accumulate = [&](int jj, const typename Stored<T>::Raw &raw) {
+                const double *row = sQ + jj * QW;
+                double yv[4];
+                if constexpr (FD) {
+                    double w[4];
+                    unit20_from_raw(raw, w);
+                    if (FAST) {
+                        const double2 so = *reinterpret_cast<const double2 *>(row + tsel);
+                        const double cs = so.y - shift;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) yv[i] = fma(so.x, w[i], cs);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const double sc = __ldg(a.scale + sl[i] + (int64_t)(t0 + jj) * a.nslices);
+                            const double of = __ldg(a.offset + sl[i] + (int64_t)(t0 + jj) * a.nslices);
+                            yv[i] = fma(sc * kOne, w[i], fma(-sc, vmin1, of) - shift);
+                        }
+                    }
+                } else {
+                    double y[4];
+                    Stored<T>::convert(raw, y, cm);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        double t = y[i];
+                        if (SC) {
+                            double sc, of;
+                            if (FAST) {
+                                const double2 so = *reinterpret_cast<const double2 *>(row + tsel);
+                                sc = so.x;
+                                of = so.y;
+                            } else {
+                                sc = __ldg(a.scale + sl[i] + (int64_t)(t0 + jj) * a.nslices);
+                                of = __ldg(a.offset + sl[i] + (int64_t)(t0 + jj) * a.nslices);
+                            }
+                            t = descale(t, sc, of);
+                        }
+                        yv[i] = t - shift;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    sum[i].yy = fma(yv[i], yv[i], sum[i].yy);
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) sum[i].e[k] = fma(row[k], yv[i], sum[i].e[k]);
+                }
+            };
+            int jj = 0;
+            typename Stored<T>::Raw cur[UNR], nxt[UNR];
+            if (cnt >= UNR) {
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) nxt[u] = load_raw_64b<T>(up + (int64_t)(t0 + u) * a.ldU);
+            }
+            for (; jj + UNR <= cnt; jj += UNR) {
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) cur[u] = nxt[u];
+                if (jj + 2 * UNR <= cnt) {
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) nxt[u] = load_raw_64b<T>(up + (int64_t)(t0 + jj + UNR + u) * a.ldU);
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) accumulate(jj + u, cur[u]);
+            }
+            for (; jj < cnt; ++jj) accumulate(jj, load_raw_64b<T>(up + (int64_t)(t0 + jj) * a.ldU));
+        };
+        if (fast) run(std::true_type{});
+        else run(std::false_type{});
+    }
+    if (!have) return;
+
+    // ---- fused epilogue (as lm_fit_packed_kernel)
+    double rss[4], mss[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sum[i].y0 = shift;
+        rss[i] = sum[i].yy - sumsq_e(sum[i]);
+        mss[i] = mss_from_e(sum[i], sd);
+        if (act[i] && rss[i] <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0) {
+            const double2 ex = exact_pass_packed<KP, T>(U + v + i, a.ldU, n, a.Qt, shift, cm, a.scale + sl[i], a.offset + sl[i],
+                                                        a.nslices);
+            rss[i] = ex.x;
+            mss[i] = ex.y;
+        }
+    }
+    if (a.out_vec2) {
+#pragma unroll
+        for (int i = 0; i < 4; i += 2)
+            finish_pair<KP>(sum[i], rss[i], mss[i], act[i], sum[i + 1], rss[i + 1], mss[i + 1], act[i + 1], sd, a.out + v + i,
+                            a.ldOut);
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double *o = a.out + v + i;
+        if (act[i]) finish_voxel<KP>(sum[i], rss[i], mss[i], sd, o, a.ldOut);
+        else zero_row<KP>(sd.ncol_out, o, a.ldOut);
+    }
+}
+
 // ------------------------------------------------------------------ TMA-staged variant (default when TMA can describe U)
 // Same contract, K1's structure (lm_kernels.cu): persistent CTAs, one producer lane issues 2-D TMA boxes of the
 // STORED samples (NJ subjects x up to 256 voxels, uint16 or float32 tensor map) plus, for scaled types, the NJ
@@ -782,6 +1092,32 @@ cudaError_t launch_packed_t(const PackedArgs &a, const LmPlan &plan, LmScratch &
     int JT = a.n;
     while ((size_t)JT * QW * 8 > 40 * 1024) JT = ((JT + 1) / 2 + 7) & ~7;   // multiple of the unroll depth
     const size_t smem = (size_t)JT * QW * 8;
+    // masked fits: compact the mask into a list of voxel quads and fit only those (RMG_PACKED_NOCOMPACT=1: the plain kernel)
+    static const bool env_no_compact = [] { const char *s_ = std::getenv("RMG_PACKED_NOCOMPACT"); return s_ && std::atoi(s_) != 0; }();
+    if (a.mask && vec && a.V % 4 == 0 && a.V / 4 < 0xffffffffLL && !plan.no_compact && !env_no_compact) {
+        const int64_t nquads = a.V / 4;
+        const int nb = (int)((nquads + kQuadBlock - 1) / kQuadBlock);
+        const size_t off_list = ((size_t)nb * 4 + 4 + 255) & ~size_t(255);
+        cudaError_t e = scr.ensure_bytes(off_list + (size_t)nquads * 4, st);
+        if (e != cudaSuccess) return e;
+        unsigned int *counts = reinterpret_cast<unsigned int *>(scr.flags);
+        unsigned int *n_quads = counts + nb;
+        uint32_t *list = reinterpret_cast<uint32_t *>(scr.flags + off_list);
+        const int ncol = 2 * a.p + 3;
+        quad_count_kernel<<<nb, kQuadBlock, 0, st>>>(a.mask, a.V, a.mask_lo, a.mask_hi, counts);
+        quad_scan_kernel<<<1, 1024, 0, st>>>(counts, nb, n_quads);
+        quad_compact_kernel<<<nb, kQuadBlock, 0, st>>>(a.mask, a.V, a.mask_lo, a.mask_hi, counts, list, a.out, a.ldOut, ncol, a.out_vec2);
+        const int64_t qblocks = (nquads + 127) / 128;
+        auto goq = [&](auto kern) -> cudaError_t {
+            cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e2 != cudaSuccess) return e2;
+            kern<<<(unsigned)qblocks, 128, smem, st>>>(a, list, n_quads, JT);
+            return cudaGetLastError();
+        };
+        e = plan.stored_exact ? goq(lm_fit_packed_quads_kernel<KP, T, false>) : goq(lm_fit_packed_quads_kernel<KP, T, true>);
+        if (info) { info->launches += 4; info->used_tma = 0; info->split = 1; }
+        return e;
+    }
     const int VPT = vec ? 4 : 1;
     const int64_t per_block = (int64_t)128 * VPT;
     const int64_t blocks = (a.V + per_block - 1) / per_block;

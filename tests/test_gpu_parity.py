@@ -620,6 +620,42 @@ def test_stored_variants(core, oracle, monkeypatch):
         core.lm_fit_stored(U.astype(np.int32), X, scale, offset)
 
 
+@pytest.mark.parametrize("mode", ["fold", "exact", "plain"])
+@pytest.mark.parametrize("slice_len", [1000, 333, 8000])
+def test_stored_masked_fit_on_compacted_quads(core, oracle, monkeypatch, slice_len, mode):
+    """uint16 files AND a mask: the mask is compacted into a list of voxel quads and only those are fitted.  Ragged masks (runs
+    that start and end inside quads, empty stretches, a fully selected stretch), slice boundaries inside quads (333), both
+    expansions, and the plain kernel (RMG_PACKED_NOCOMPACT=1) as the twin; masked rows are +0.0 in every column."""
+    if mode == "exact":
+        monkeypatch.setenv("RMG_STORED_EXACT", "1")
+    if mode == "plain":
+        monkeypatch.setenv("RMG_PACKED_NOCOMPACT", "1")
+    V, n = 8000, 44
+    U, X, scale, offset = _stored_case(V, n, slice_len, seed=77)
+    U = U.copy(order="F")
+    U[40:48] = 7                                                   # one stored value everywhere: the real values follow the ranges
+    U[100] = (2000 + 30000 * X[:, 1]).astype(np.uint16)           # a large group effect: little is left for the residuals
+    rng = np.random.default_rng(5)
+    mask = np.zeros(V)
+    mask[37:1203] = 1
+    mask[1500:1502] = 1
+    mask[2001] = 3
+    mask[3000:5000] = (rng.random(2000) < 0.4) * 2.0
+    mask[7996:] = 1
+    Y = oracle.expand_stored(U, scale, offset, voxel_min=10.0, slice_len=slice_len)
+    for lo, hi in ((1.0, 99999999.0), (2.0, 2.0)):
+        got = core.lm_fit_stored(U, X, scale, offset, voxel_min=10.0, slice_len=slice_len, mask=mask, mask_lo=lo, mask_hi=hi)
+        want = oracle.minc2_model_lm(Y, (1, 1, V), X, mask=mask, lo=lo, hi=hi)
+        inside = (mask > lo - 0.5) & (mask < hi + 0.5)
+        assert_rows_match(got[inside], want[inside], RTOL, f"compacted quads {mode} lo={lo}")
+        assert (got[~inside] == 0).all() and not np.signbit(got[~inside]).any()
+    F = np.asfortranarray(np.random.default_rng(4).normal(0, 0.2, (V, n)).astype(np.float32))
+    gotf = core.lm_fit_stored(F, X, mask=mask)
+    assert_rows_match(gotf, oracle.minc2_model_lm(F.astype(np.float64), (1, 1, V), X, mask=mask), RTOL, f"f32 quads {mode}")
+    # an empty mask selects nothing
+    assert (core.lm_fit_stored(U, X, scale, offset, voxel_min=10.0, slice_len=slice_len, mask=np.zeros(V)) == 0).all()
+
+
 def test_stored_degenerate_and_near_perfect_voxels(core, oracle):
     """Quantised data: constant voxels (background) and voxels the design explains almost entirely."""
     rng = np.random.default_rng(8)
