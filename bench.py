@@ -833,6 +833,10 @@ def run_gpu_arm(args):
             torch.cuda.synchronize()
             rand["dgemm_peak_tflops"] = 5 * 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
             rand["frac_of_dgemm"] = rand["algorithmic_tflops"] / world / rand["dgemm_peak_tflops"]
+            # the GEMM path skips the permutation-invariant intercept row: (p - 1) / p of the algorithmic flops are EXECUTED
+            executed = (p - 1) / p if rand["path"] == "gemm" else 1.0
+            rand["executed_tflops"] = rand["algorithmic_tflops"] * executed
+            rand["frac_of_dgemm_executed"] = rand["frac_of_dgemm"] * executed
             del A, B
 
     # ---- timed region 2: end to end through the C ABI with HOST buffers (pinned), rank-local
