@@ -36,7 +36,9 @@ class Group:
 
 
 class Writer:
-    def __init__(self, user_block: int = 0, leaf_k: int = 64, chunk_k: int = 32):
+    def __init__(self, user_block: int = 0, leaf_k: int = 64, chunk_k: int = 32, split_headers: bool = False, max_dims: bool = False):
+        self.split_headers = split_headers
+        self.max_dims = max_dims
         self.buf = bytearray(96)
         self.user_block = user_block
         self.leaf_k = leaf_k
@@ -67,9 +69,11 @@ class Writer:
             return struct.pack("<BBBBI", 0x13, 0, 0, 0, dt.itemsize)
         raise TypeError(dt)
 
-    @staticmethod
-    def dataspace(shape) -> bytes:
-        return struct.pack("<BBBBI", 1, len(shape), 0, 0, 0) + b"".join(struct.pack("<Q", s) for s in shape)
+    def dataspace(self, shape) -> bytes:
+        dims = b"".join(struct.pack("<Q", s) for s in shape)
+        if self.max_dims and len(shape):                 # flag bit 0: the maximum dimensions follow the current ones
+            return struct.pack("<BBBBI", 1, len(shape), 1, 0, 0) + dims + dims
+        return struct.pack("<BBBBI", 1, len(shape), 0, 0, 0) + dims
 
     def attribute(self, name: str, value) -> bytes:
         if isinstance(value, str):
@@ -86,11 +90,26 @@ class Writer:
         return head + _pad8(nm) + _pad8(dt) + _pad8(ds) + a.tobytes()
 
     def header(self, messages) -> int:
-        body = b""
-        for mtype, flags, data in messages:
-            d = _pad8(data)
-            body += struct.pack("<HHBBBB", mtype, len(d), flags, 0, 0, 0) + d
-        return self.put(struct.pack("<BBHII", 1, 0, len(messages), 1, len(body)) + b"\0" * 4 + body)
+        """Version-1 object header.  With self.split_headers the messages after the third go to a continuation block
+        (message 0x0010), the way libhdf5 grows the header of an object that collects attributes after its creation -- a MINC
+        image variable does -- with a NIL message padding the first block."""
+        def pack(msgs):
+            body = b""
+            for mtype, flags, data in msgs:
+                d = _pad8(data)
+                body += struct.pack("<HHBBBB", mtype, len(d), flags, 0, 0, 0) + d
+            return body
+
+        n = len(messages)
+        if self.split_headers and n > 3:
+            cont = pack(messages[3:])
+            cont_addr = self.put(cont)
+            first = messages[:3] + [(0x0000, 0, b"\0" * 8), (0x0010, 0, struct.pack("<QQ", cont_addr, len(cont)))]
+            body = pack(first)
+            n += 2
+        else:
+            body = pack(messages)
+        return self.put(struct.pack("<BBHII", 1, 0, n, 1, len(body)) + b"\0" * 4 + body)
 
     # -- datasets
     def write_dataset(self, ds: Dataset) -> int:

@@ -135,6 +135,24 @@ def test_global_range_many_chunks_and_many_group_members(tmp_path):
     assert np.array_equal(h5_attribute(path, "minc-2.0/dimensions/xspace", "length"), [24.0])
 
 
+def test_header_continuation_blocks_user_block_and_max_dims(tmp_path):
+    """What libhdf5 does to objects that grow: attributes added after creation live in an object-header continuation block
+    (message 0x0010), dataspaces carry their maximum dimensions, and a file may start with a user block."""
+    rng = np.random.default_rng(21)
+    vol = rng.integers(0, 65536, size=(5, 8, 6), dtype=np.uint16)
+    lo = rng.normal(size=5)
+    tree = h5mini.minc2_tree(vol, image_min=lo, image_max=lo + 1.25, valid_range=(0, 65535), chunks=(1, 8, 6), steps=(2.0, 1.0, 0.5))
+    path = str(tmp_path / "grown.mnc")
+    h5mini.write_h5(path, tree, split_headers=True, max_dims=True, user_block=1024)
+    assert minc2.is_minc2(path)
+    with minc2.Minc2Volume(path) as v:
+        assert v.sizes == (5, 8, 6) and v.steps == (2.0, 1.0, 0.5) and v.valid_range == (0.0, 65535.0) and v.nslices == 5
+        assert np.array_equal(v.stored(), vol)
+        assert np.array_equal(v.real(), expected_real(vol, lo, lo + 1.25, (0.0, 65535.0)))
+    assert h5_attribute(path, "minc-2.0/image/0/image", "dimorder") == "zspace,yspace,xspace"       # lives in the continuation
+    assert h5_attribute(path, "minc-2.0", "history") == "h5mini"
+
+
 def test_read_table_decodes_a_study_in_parallel(tmp_path):
     rng = np.random.default_rng(9)
     shape, n = (6, 10, 9), 7
