@@ -457,9 +457,10 @@ lm_fit_packed_kernel(PackedArgs a, int JT)
 // visits every voxel and only skips the loads of masked ones.  Here three small kernels turn the mask into an ascending list of
 // voxel QUADS (4 adjacent voxels = one 8-byte load of uint16 samples) that contain a selected voxel and write the +0.0 rows of all
 // other quads (the double path's pair compaction, lm_kernels.cu); the fit kernel then gives every thread one LISTED quad, so
-// all lanes of the FP64-bound loop do useful work; the samples arrive through a per-thread ring of asynchronous 8-byte copies
-// (32 subjects deep) with a 64-byte L2 prefetch size (runs of selected voxels are ~190 bytes per subject: the default 128 bytes
-// around each load would fetch half as much again).  Arithmetic as the TMA
+// all lanes of the FP64-bound loop do useful work, and its loads carry a 64-byte L2 prefetch size (runs of selected voxels are
+// ~190 bytes per subject: the default 128 bytes around each load would fetch half as much again).  Measured and dropped: a
+// per-thread ring of asynchronous 8-byte copies (cp.async, 32 subjects deep) instead of the register prefetch -- 1.55 ms
+// against 1.27 ms on the 38 % ellipsoid of config 2 (one LDGSTS + one LDS per quad and subject cost more than they hide).  Arithmetic as the TMA
 // variant: w = 1 + u 2^-20 and one fused multiply-add per sample, ONE shift per quad folded into the offsets (FOLD), or the
 // reader's three roundings (RMG_STORED_EXACT=1).
 constexpr int kQuadBlock = 1024;   // quads per compaction block
@@ -559,20 +560,23 @@ quad_compact_kernel(const double *__restrict__ mask, int64_t V, double lo, doubl
     }
 }
 
-// One quad of one subject, global -> this thread's slot of the shared-memory ring, asynchronously (LDGSTS) and with a
-// 64-byte L2 prefetch size: the bytes in flight are set by the ring's depth, not by registers.
-template <int BYTES>
-__device__ __forceinline__ void quad_copy_async(void *smem_dst, const void *gsrc)
+template <typename T>
+__device__ __forceinline__ typename Stored<T>::Raw load_raw_64b(const T *p);
+template <>
+__device__ __forceinline__ uint2 load_raw_64b<uint16_t>(const uint16_t *p)
 {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    if constexpr (BYTES == 8)
-        asm volatile("cp.async.ca.shared.global.L2::64B [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-    else
-        asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
 }
-__device__ __forceinline__ void quad_copy_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void quad_copy_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <>
+__device__ __forceinline__ float4 load_raw_64b<float>(const float *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
 
 // the four packed uint16 samples of a quad as w = 1 + u 2^-20 (see load_unit20_smem)
 __device__ __forceinline__ void unit20_from_raw(const uint2 &r, double (&w)[4])
@@ -638,23 +642,7 @@ lm_fit_packed_quads_kernel(PackedArgs a, const uint32_t *__restrict__ list, cons
         if (SC) shift = descale(shift, __ldg(a.scale + sl[0]), __ldg(a.offset + sl[0]));
     }
     const T *up = U + v;
-    constexpr int UNR = 8;                    // subjects per copy group
-    constexpr int DEPTH = 3;                  // groups in flight beside the one being consumed
-    constexpr int SLOTS = UNR * (DEPTH + 1);
-    using Raw = typename Stored<T>::Raw;
-    Raw *ring = reinterpret_cast<Raw *>(smem_raw + (((size_t)JT * QW * 8 + 15) & ~size_t(15)));      // [SLOTS][128]
-    auto issue = [&](int g) {                 // group g = subjects [g * UNR, g * UNR + UNR)
-        if (have) {
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int j = g * UNR + u;
-                if (j < n) quad_copy_async<(int)sizeof(Raw)>(ring + (size_t)(j % SLOTS) * 128 + tid, up + (int64_t)j * a.ldU);
-            }
-        }
-        quad_copy_commit();
-    };
-#pragma unroll
-    for (int g = 0; g < DEPTH; ++g) issue(g);
+    constexpr int UNR = 8;
 
     for (int t0 = 0; t0 < n; t0 += JT) {
         __syncthreads();
@@ -723,19 +711,23 @@ lm_fit_packed_quads_kernel(PackedArgs a, const uint32_t *__restrict__ list, cons
                     for (int k = 0; k < KP; ++k) sum[i].e[k] = fma(row[k], yv[i], sum[i].e[k]);
                 }
             };
-            // JT is a multiple of UNR: groups never straddle a tile of the staged rows
-            for (int jj = 0; jj < cnt; jj += UNR) {
-                const int g = (t0 + jj) / UNR;
-                issue(g + DEPTH);
-                quad_copy_wait<DEPTH>();       // group g has landed; every thread reads only the slots it filled itself
+            int jj = 0;
+            typename Stored<T>::Raw cur[UNR], nxt[UNR];
+            if (cnt >= UNR) {
 #pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    if (jj + u < cnt) {
-                        const Raw raw = ring[(size_t)((t0 + jj + u) % SLOTS) * 128 + tid];
-                        accumulate(jj + u, raw);
-                    }
-                }
+                for (int u = 0; u < UNR; ++u) nxt[u] = load_raw_64b<T>(up + (int64_t)(t0 + u) * a.ldU);
             }
+            for (; jj + UNR <= cnt; jj += UNR) {
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) cur[u] = nxt[u];
+                if (jj + 2 * UNR <= cnt) {
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) nxt[u] = load_raw_64b<T>(up + (int64_t)(t0 + jj + UNR + u) * a.ldU);
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) accumulate(jj + u, cur[u]);
+            }
+            for (; jj < cnt; ++jj) accumulate(jj, load_raw_64b<T>(up + (int64_t)(t0 + jj) * a.ldU));
         };
         if (fast) run(std::true_type{});
         else run(std::false_type{});
@@ -1118,14 +1110,10 @@ cudaError_t launch_packed_t(const PackedArgs &a, const LmPlan &plan, LmScratch &
         quad_scan_kernel<<<1, 1024, 0, st>>>(counts, nb, n_quads);
         quad_compact_kernel<<<nb, kQuadBlock, 0, st>>>(a.mask, a.V, a.mask_lo, a.mask_hi, counts, list, a.out, a.ldOut, ncol, a.out_vec2);
         const int64_t qblocks = (nquads + 127) / 128;
-        // staged rows (<= 16 KB a tile, a multiple of the copy-group size) + the ring of 32 subjects x 128 quads
-        int JTq = a.n;
-        while ((size_t)JTq * QW * 8 > 16 * 1024) JTq = ((JTq + 1) / 2 + 7) & ~7;
-        const size_t smem_q = (((size_t)JTq * QW * 8 + 15) & ~size_t(15)) + (size_t)32 * 128 * sizeof(typename Stored<T>::Raw);
         auto goq = [&](auto kern) -> cudaError_t {
-            cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
+            cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e2 != cudaSuccess) return e2;
-            kern<<<(unsigned)qblocks, 128, smem_q, st>>>(a, list, n_quads, JTq);
+            kern<<<(unsigned)qblocks, 128, smem, st>>>(a, list, n_quads, JT);
             return cudaGetLastError();
         };
         e = plan.stored_exact ? goq(lm_fit_packed_quads_kernel<KP, T, false>) : goq(lm_fit_packed_quads_kernel<KP, T, true>);
