@@ -527,6 +527,11 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
         // wide tiles as soon as there are two of them per SM: 2 KB row segments use DRAM pages better than 1 KB ones
         // (config 3, 320 wide tiles on 148 SMs: 0.246 ms wide vs 0.285 ms narrow)
         if (cfg < 0) cfg = (a.V >= (int64_t)plan.sm_count * 2 * 256) ? 4 : 5;
+        // ... and when all wide tiles are resident at once with 3 CTAs per SM (config 3: 321 tiles on 444 slots), every CTA
+        // streams exactly one tile: twice the ring (8 subjects a stage) instead of a fourth CTA per SM that would have nothing
+        // to do -- config 3: 0.231 ms against 0.240 ms (measured beside it: 8 x 6 stages x 2 CTAs/SM 0.276 ms -- 296 slots for
+        // 321 tiles --, 4 x 8 stages x 3 CTAs/SM 0.244 ms)
+        if (cfg == 4 && plan.tma_cfg < 0 && KP <= 8 && (a.V + 255) / 256 <= (int64_t)plan.sm_count * 3) cfg = 6;
         const int TV = cfg == 0 ? 512 : (cfg == 5 ? 128 : 256);
         const unsigned char *flags = nullptr;
         if (a.mask) {
@@ -547,6 +552,7 @@ cudaError_t launch_kp(const LmArgs &a, const LmPlan &plan, LmScratch &scr, cudaS
             case 10: e = launch_tma_cfg<KP, 2, 4, 4, 8, false>(a, flags, plan.sm_count, st); break;
             case 11: e = launch_tma_cfg<KP, 2, 4, 4, 8, true>(a, flags, plan.sm_count, st); break;
             case 8: e = launch_tma_cfg<KP, 4, 4, 4, 4, false>(a, flags, plan.sm_count, st); break;
+            case 12: case 13: e = launch_tma_cfg<KP, 4, 8, 4, 3, true>(a, flags, plan.sm_count, st); break;
             default: e = launch_tma_cfg<KP, 4, 4, 4, 4, true>(a, flags, plan.sm_count, st); break;
             }
         } else {
