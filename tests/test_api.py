@@ -635,3 +635,13 @@ def test_mincLm_on_minc2_files(api, study, tmp_path):
     check_row(v16, 7, Y16[7], X[:, :2], ["(Intercept)", "SexM"])
     with pytest.raises(FileNotFoundError, match="Error opening input file"):
         api.mincLm("jacobians ~ Sex", gm.assign(jacobians=[str(tmp_path / "gone.mnc")] * 10))
+    # the other callers of the path read the same files: mincAnova (real values of the uint16 volumes), mincRandomize and
+    # mincFDR on the fit
+    an = api.mincAnova("jacobians ~ Sex + Scale", gm, mask=mpath)
+    want_an = api.mincAnova("jacobians ~ Sex + Scale", gf.assign(jacobians=[Yq[:, j].reshape(10, 10, 10) for j in range(10)]),
+                            mask=np.load(maskfile))
+    np.testing.assert_allclose(np.asarray(an), np.asarray(want_an), rtol=1e-9, atol=0)
+    rs = api.mincRandomize(vs, R=6, idx=api.draw_indices(10, 6, seed=3))
+    assert np.asarray(rs["randomization_dist"]).shape == (6, 3)
+    fd = api.mincFDR(vs, mask=mpath)
+    assert np.asarray(fd).shape[0] == 1000
