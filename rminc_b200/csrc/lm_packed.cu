@@ -1072,8 +1072,12 @@ cudaError_t launch_packed_t(const PackedArgs &a, const LmPlan &plan, LmScratch &
                 } else {
                     // measured alternatives: one more CTA per SM at 96 registers
                     if constexpr (KP == 4) {
-                        if (plan.tma_cfg == 2) return launch_packed_tma<KP, T, 4, 2, 4, 4, 16, 2>(a, plan, scr, st, info);
-                        if (plan.tma_cfg == 3) return launch_packed_tma<KP, T, 4, 2, 4, 4, 8, 4>(a, plan, scr, st, info);
+                        cudaError_t ex = cudaErrorNotSupported;
+                        if (plan.tma_cfg == 2) ex = launch_packed_tma<KP, T, 4, 2, 4, 4, 16, 2>(a, plan, scr, st, info);
+                        if (plan.tma_cfg == 3) ex = launch_packed_tma<KP, T, 4, 2, 4, 4, 8, 4>(a, plan, scr, st, info);
+                        // (32 or 24 subjects per stage in a 2-deep ring: 2.096 / 2.065 ms against 2.10 ms -- the barrier round trips
+                        // are no longer what the kernel waits on; not kept)
+                        if (ex != cudaErrorNotSupported) return ex;
                     }
                     // RMG_TMA_CFG: 1 = 8 subjects x 4 stages, 4 = the round-2a form (w = 1 + u 2^-16, one shift per voxel)
                     if (plan.tma_cfg == 4) e = launch_packed_tma<KP, T, MINB, 1, 4, 4, 16, 3>(a, plan, scr, st, info);
