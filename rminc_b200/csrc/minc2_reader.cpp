@@ -228,7 +228,7 @@ private:
         }
         if (!found) fail(std::string(path) + ": no HDF5 signature (MINC 1 / NetCDF files are not MINC 2 volumes)");
         const uint8_t *s = p_ + pos;
-        if (pos + 96 > n_) fail("truncated superblock");
+        if (pos + 160 > n_) fail("truncated superblock");
         const int ver = s[8];
         if (ver == 0 || ver == 1) {
             so_ = s[13];
@@ -413,11 +413,13 @@ private:
         if (sz < 2) fail("short layout message");
         const int ver = d[0];
         if (ver == 1 || ver == 2) {
+            if (sz < 8) fail("short layout message");
             const int nd = d[1];
             l.cls = d[2];
             uint64_t pos = 8;
-            if (l.cls != 0) { l.addr = off_at(d + pos); pos += so_; }
             if (nd > 9) fail("layout dimensionality above 9");
+            if (pos + (l.cls != 0 ? so_ : 0) + 4ull * nd + (l.cls == 0 ? 4 : 0) > sz) fail("layout message shorter than its fields");
+            if (l.cls != 0) { l.addr = off_at(d + pos); pos += so_; }
             uint32_t dims[9] = {0};
             for (int i = 0; i < nd; ++i, pos += 4) dims[i] = (uint32_t)le(d + pos, 4);
             if (l.cls == 2) {
@@ -431,15 +433,19 @@ private:
         } else if (ver == 3) {
             l.cls = d[1];
             if (l.cls == 0) {
+                if (sz < 4) fail("short layout message");
                 l.size = le(d + 2, 2);
                 l.compact = d + 4;
                 if (4 + l.size > sz) fail("compact data runs past the layout message");
             } else if (l.cls == 1) {
+                if (2ull + so_ + sl_ > sz) fail("layout message shorter than its fields");
                 l.addr = off_at(d + 2);
                 l.size = len_at(d + 2 + so_);
             } else if (l.cls == 2) {
+                if (sz < 3) fail("short layout message");
                 const int nd = d[2];
                 if (nd < 1 || nd > 9) fail("bad chunk dimensionality");
+                if (3ull + so_ + 4ull * nd > sz) fail("layout message shorter than its fields");
                 l.addr = off_at(d + 3);
                 l.chunk_rank = nd - 1;
                 for (int i = 0; i < nd - 1; ++i) l.chunk[i] = (uint32_t)le(d + 3 + so_ + 4 * i, 4);
@@ -513,9 +519,10 @@ private:
         if (flags & 4) pos += 8;
         if (flags & 16) pos += 1;
         const int lb = 1 << (flags & 3);
+        if (pos + lb > sz) fail("link message shorter than its fields");
         const uint64_t nlen = le(d + pos, lb);
         pos += lb;
-        if (pos + nlen > sz) fail("link name runs past its message");
+        if (nlen > sz || pos + nlen > sz) fail("link name runs past its message");
         std::string name(reinterpret_cast<const char *>(d + pos), nlen);
         pos += nlen;
         if (ltype == 0 && pos + so_ <= sz) o.links.push_back({name, off_at(d + pos)});
@@ -600,9 +607,10 @@ private:
         for (int d = 0; d < rank; ++d) {
             if (o.layout.chunk[d] == 0) fail("zero chunk dimension");
             cvox *= o.layout.chunk[d];
+            if (cvox > (1ull << 30)) fail("chunk larger than 1 GiB");
         }
         const uint64_t cbytes = cvox * es;
-        if (cbytes > (1ull << 32)) fail("chunk larger than 4 GiB");
+        if (cbytes > (1ull << 30)) fail("chunk larger than 1 GiB");
         bool deflate = false, shuffle = false;
         for (const Filter &f : o.filters) {
             if (f.id == 1) deflate = true;
@@ -1061,6 +1069,7 @@ int rmg_minc2_read_table(const char *const *paths, int n, void *U, int64_t ldU, 
                 const int j = next.fetch_add(1);
                 if (j >= n || bad.load()) break;
                 try {
+                    if (!paths[j]) fail("rmg_minc2_read_table: NULL file name");
                     rmg_minc2_volume v(paths[j]);
                     open_impl(v);
                     const rmg_minc2_info &I = v.info;
