@@ -518,6 +518,10 @@ int rmg_h5_read_dataset(const char *path, const char *dataset, void *dst, int64_
                         int32_t *elem_size, int32_t *type_class, int n_threads, char *err, size_t errlen);
 int rmg_h5_read_attribute(const char *path, const char *object, const char *attribute, double *numbers, int64_t max_numbers,
                           int64_t *count, char *text, size_t textlen, char *err, size_t errlen);
+/* One zlib stream (RFC 1950: what HDF5's deflate filter stores per chunk) -> dst; returns the bytes written or -1 (malformed or
+ * truncated stream, wrong Adler-32, dst too small).  use_zlib = 0: the reader's own decoder (csrc/inflate_fast.hpp: 64-bit bit
+ * buffer, two-level tables, three literals per refill -- 1.4-1.5x zlib on volume data); 1: zlib's uncompress, its twin and back-up. */
+int64_t rmg_zlib_uncompress(const void *src, int64_t src_bytes, void *dst, int64_t dst_bytes, int use_zlib);
 
 /* Timing of the most recent rmg_*_device / host call on this thread, for bench.py:
  * milliseconds spent in the dominant kernel(s), measured with CUDA events on the stream the

@@ -111,6 +111,7 @@ SIGNATURES = {
     "rmg_minc2_close": (None, [C.c_void_p]),
     "rmg_minc2_read_table": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_void_p, C.c_int] + _ERR),
+    "rmg_zlib_uncompress": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int]),
     "rmg_h5_read_dataset": (C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int] + _ERR),
     "rmg_h5_read_attribute": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_char_p,

@@ -33,8 +33,10 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -42,6 +44,7 @@
 #include <vector>
 
 #include "../../include/rminc_b200.h"
+#include "inflate_fast.hpp"
 
 namespace {
 
@@ -643,8 +646,11 @@ private:
         std::atomic<bool> bad{false};
         std::string msg;
         std::mutex mu;
+        // RMG_INFLATE=zlib: zlib's uncompress for every chunk (the twin of the built-in decoder, which it also backs up)
+        static const bool zlib_only = [] { const char *e = std::getenv("RMG_INFLATE"); return e && std::strcmp(e, "zlib") == 0; }();
         auto work = [&]() {
             std::vector<uint8_t> buf(cbytes), tmp(shuffle ? cbytes : 0);
+            std::unique_ptr<rmg_inflate::Tables> tables(new rmg_inflate::Tables);
             for (;;) {
                 const size_t i = next.fetch_add(1);
                 if (i >= chunks.size() || bad.load()) break;
@@ -654,10 +660,19 @@ private:
                     uint64_t have = c.nbytes;
                     if (fletcher && !(c.mask & (1u << filter_index(o, 3)))) { if (have < 4) fail("chunk shorter than its checksum"); have -= 4; }
                     const uint8_t *raw = src;
+                    // A chunk that spans the dataset in every dimension but the slowest (libminc's slice chunks) and lies wholly
+                    // inside it is one contiguous piece of the destination: inflate straight into it, no staging copy.
+                    bool whole = !shuffle && c.off[0] + o.layout.chunk[0] <= o.ds.dims[0];
+                    for (int d = 1; d < rank && whole; ++d) whole = c.off[d] == 0 && o.layout.chunk[d] == o.ds.dims[d];
                     if (deflate && !(c.mask & (1u << filter_index(o, 1)))) {
-                        uLongf outlen = (uLongf)cbytes;
-                        const int rc = uncompress(buf.data(), &outlen, src, (uLong)have);
-                        if (rc != Z_OK || outlen != cbytes) fail("inflate failed on a chunk (zlib code " + std::to_string(rc) + ")");
+                        uint8_t *target = whole ? dst + c.off[0] * stride[0] * es : buf.data();
+                        const int64_t got = zlib_only ? -1 : rmg_inflate::zlib_uncompress(src, (size_t)have, target, (size_t)cbytes, *tables);
+                        if (got != (int64_t)cbytes) {               // not decoded (or not this decoder's day): zlib decides
+                            uLongf outlen = (uLongf)cbytes;
+                            const int rc = uncompress(target, &outlen, src, (uLong)have);
+                            if (rc != Z_OK || outlen != cbytes) fail("inflate failed on a chunk (zlib code " + std::to_string(rc) + ")");
+                        }
+                        if (whole) continue;
                         raw = buf.data();
                     } else if (have < cbytes) {
                         fail("stored chunk shorter than the chunk size");
@@ -1046,6 +1061,19 @@ int rmg_h5_read_attribute(const char *path, const char *object, const char *attr
             for (int64_t i = 0; numbers && i < c && i < max_numbers; ++i) numbers[i] = attr_number(*a, (size_t)i);
         }
     });
+}
+
+int64_t rmg_zlib_uncompress(const void *src, int64_t src_bytes, void *dst, int64_t dst_bytes, int use_zlib)
+{
+    if (!src || !dst || src_bytes < 0 || dst_bytes < 0) return -1;
+    if (use_zlib) {
+        uLongf outlen = (uLongf)dst_bytes;
+        const int rc = uncompress(static_cast<Bytef *>(dst), &outlen, static_cast<const Bytef *>(src), (uLong)src_bytes);
+        return rc == Z_OK ? (int64_t)outlen : -1;
+    }
+    std::unique_ptr<rmg_inflate::Tables> tables(new rmg_inflate::Tables);
+    return rmg_inflate::zlib_uncompress(static_cast<const uint8_t *>(src), (size_t)src_bytes, static_cast<uint8_t *>(dst), (size_t)dst_bytes,
+                                        *tables);
 }
 
 int rmg_minc2_read_table(const char *const *paths, int n, void *U, int64_t ldU, int dtype, double *image_min, double *image_max,
