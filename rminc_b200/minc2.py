@@ -136,13 +136,14 @@ def read_volume(path):
         return v.real()
 
 
-def read_table(paths: Sequence, dtype=None, n_threads=None, pinned: bool = False):
+def read_table(paths: Sequence, dtype=None, n_threads=None, pinned: bool = False, out=None):
     """mincTable for MINC 2 files, decoded in parallel into one Fortran-ordered V x n matrix.
 
     dtype None: the files' own stored type if it is uint16 / float32, float64 otherwise.  Returns (U, image_min, image_max,
     valid_range, info) with image_min / image_max [nslices x n] for uint16 tables and None otherwise; `info` is the first
     file's Minc2Volume (closed; its attributes stay readable).  pinned=True stages U in page-locked memory
-    (rmg_host_alloc) so the upload runs at the link rate."""
+    (rmg_host_alloc) so the upload runs at the link rate; out= reuses the matrix of an earlier call of the same shape and type
+    (page-locking half a gigabyte costs more than decoding it)."""
     paths = [os.fspath(p) for p in paths]
     with Minc2Volume(paths[0]) as first:
         pass
@@ -153,7 +154,11 @@ def read_table(paths: Sequence, dtype=None, n_threads=None, pinned: bool = False
     V, n = first.nvoxels, len(paths)
     lib = _lib.load()
     npdt = np.dtype(_NP[code])
-    if pinned:
+    if out is not None:
+        if out.shape != (V, n) or out.dtype != npdt or not out.flags.f_contiguous:
+            raise ValueError("out= must be a Fortran-ordered V x n matrix of the table's type")
+        U = out
+    elif pinned:
         nbytes = V * n * npdt.itemsize
         p = lib.rmg_host_alloc(nbytes)
         if not p:

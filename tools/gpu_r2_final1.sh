@@ -26,6 +26,10 @@ for k in ('masked_variant','vertexLm','covariate','stored_u16','randomize'):
 t=d.get('vertexTFCE') or {}
 print('tfce', t.get('perms_per_s'), (t.get('from_pinned') or {}).get('perms_per_s'), (t.get('mincTFCE') or {}).get('seconds'))
 PY
+echo "=== from files"
+timeout -k 10 900 python bench.py --steps 3 --warmup 3 --parts files --skip-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); json.dump(d['from_files'], open('gpurun_out/r2f_from_files.json','w'), indent=1); print(d['from_files'])"
 echo "=== launch list of the bench command"
 timeout -k 10 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02f_launches_bench.csv python bench.py --steps 2 --warmup 3 --parts masked,vertex,cov,stored --skip-cpu > /dev/null 2>&1
 python tools/summarize_profiles.py launches gpurun_out/r02f_launches_bench.csv "bench.py --steps 2 --warmup 3 --parts masked,vertex,cov,stored (round 2 final)" > gpurun_out/r02f_launches_bench.md 2>/dev/null || true
