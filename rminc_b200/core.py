@@ -673,7 +673,7 @@ class Dataset:
         uploaded in voxel shards.  `mask` may be a MINC 2 file, an array or None.  What mincLm(files) followed by
         mincRandomize / mincAnova / mincFDR re-reads from disk every time (R/minc_voxel_statistics.R:911-912, 1457-1477)."""
         from . import minc2
-        U, lo, hi, vr, info = minc2.read_table(list(filenames), n_threads=n_threads, pinned=device_count() > 0)
+        U, lo, hi, vr, info = minc2.read_table(list(filenames), n_threads=n_threads, pinned="auto")
         if isinstance(mask, (str, os.PathLike)):
             with minc2.Minc2Volume(mask) as mv:
                 mask = mv.real()

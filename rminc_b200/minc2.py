@@ -142,7 +142,8 @@ def read_table(paths: Sequence, dtype=None, n_threads=None, pinned: bool = False
     dtype None: the files' own stored type if it is uint16 / float32, float64 otherwise.  Returns (U, image_min, image_max,
     valid_range, info) with image_min / image_max [nslices x n] for uint16 tables and None otherwise; `info` is the first
     file's Minc2Volume (closed; its attributes stay readable).  pinned=True stages U in page-locked memory
-    (rmg_host_alloc) so the upload runs at the link rate; out= reuses the matrix of an earlier call of the same shape and type
+    (rmg_host_alloc) so the upload runs at the link rate -- "auto": only up to 2 GiB, because page-locking fresh memory (~1.4 GB/s)
+    costs a one-off study more than the library's pinned ring costs a pageable matrix; out= reuses the matrix of an earlier call of the same shape and type
     (page-locking half a gigabyte costs more than decoding it)."""
     paths = [os.fspath(p) for p in paths]
     with Minc2Volume(paths[0]) as first:
@@ -158,7 +159,7 @@ def read_table(paths: Sequence, dtype=None, n_threads=None, pinned: bool = False
         if out.shape != (V, n) or out.dtype != npdt or not out.flags.f_contiguous:
             raise ValueError("out= must be a Fortran-ordered V x n matrix of the table's type")
         U = out
-    elif pinned:
+    elif pinned is True or (pinned == "auto" and V * n * npdt.itemsize <= (2 << 30) and lib.rmg_device_count() > 0):
         nbytes = V * n * npdt.itemsize
         p = lib.rmg_host_alloc(nbytes)
         if not p:
