@@ -524,8 +524,8 @@ static int fit_host_impl(const double *Y, int64_t V, int64_t ldY, int n, const d
                         for (int i = i0; i < i1; ++i) {
                             const int r = i / 8, part = i % 8;
                             const int64_t a0 = cv * part / 8, a1 = cv * (part + 1) / 8;
-                            std::memcpy(dst + ((size_t)r * cv + a0) * es, src + ((size_t)v0 + (size_t)(r0 + r) * ldY + a0) * es,
-                                        (size_t)(a1 - a0) * es);
+                            staging_copy(dst + ((size_t)r * cv + a0) * es, src + ((size_t)v0 + (size_t)(r0 + r) * ldY + a0) * es,
+                                         (size_t)(a1 - a0) * es);
                         }
                     });
                     RMG_CUDA(cudaMemcpy2DAsync(dstdev + (size_t)r0 * ldc * es, (size_t)ldc * es, dst, (size_t)cv * es, (size_t)cv * es,
