@@ -145,6 +145,10 @@ mincRandomize_stored <- function(lmod, stored, R = 500, replace = FALSE, paralle
 # R/minc_voxel_statistics.R:557-566; .Call("vertex_anova_loop", ...), R/minc_vertex_statistics.R:314-320)
 # become one routine taking the staged matrix and model.matrix's "assign" attribute.
 per_voxel_anova_gpu <- function(filenames, mmatrix, mask = NULL, mask_min = 1, mask_max = 99999999) {
+  if (isTRUE(getOption("RMINC_GPU_READER", FALSE)))      # per_voxel_anova's own arguments; the library reads the files
+    return(.Call("rmincgpu_per_voxel_anova", as.character(filenames), mmatrix, as.integer(attr(mmatrix, "assign")),
+                 as.double(if (is.null(mask)) 0 else 1), if (is.null(mask)) character(0) else as.character(mask),
+                 as.double(mask_min), as.double(mask_max), PACKAGE = "rmincgpu"))
   Y <- rmincgpu_stage(filenames)
   m <- if (is.null(mask)) NULL else as.double(mincGetVolume(mask))
   .Call("rmincgpu_anova", Y, mmatrix, as.integer(attr(mmatrix, "assign")), m, as.double(mask_min),

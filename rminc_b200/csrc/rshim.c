@@ -11,6 +11,7 @@
  *   rmincgpu_vertex_lm_loop  same signature as vertex_lm_loop (src/vertex_modelling.c:8), so
  *                            vertexLm / anatLm only change the routine name
  *   rmincgpu_minc2_model     minc2_model(method = "lm") with the reference's own arguments: the files are read here
+ *   rmincgpu_per_voxel_anova per_voxel_anova with the reference's own arguments: the files are read here
  *   rmincgpu_lm              minc2_model(method = "lm") with the volumes already staged
  *   rmincgpu_lm_cov          the same with filenames_right (a voxel-wise covariate) staged as a second matrix
  *   rmincgpu_lm_stored       the same on volumes in their stored type (uint16 + real ranges, float32)
@@ -778,6 +779,69 @@ SEXP rmincgpu_minc2_model(SEXP filenames, SEXP filenames_right, SEXP mmatrix, SE
 }
 
 
+/* per_voxel_anova with the reference's own seven arguments (src/minc_anova.c:142-143; R caller mincAnova,
+ * R/minc_voxel_statistics.R:583-600): the files are read here, as the real doubles, and the F-statistic per term comes from
+ * rmg_anova_fit.  have_mask is 1 or 0 like minc2_model's. */
+SEXP rmincgpu_per_voxel_anova(SEXP filenames, SEXP Sx, SEXP asgn, SEXP have_mask, SEXP mask, SEXP mask_lower, SEXP mask_upper)
+{
+    if (TYPEOF(filenames) != STRSXP || Rf_length(filenames) < 1) Rf_error("filenames must be a character vector");
+    const int n = Rf_length(filenames);
+    if (!Rf_isReal(Sx) || !Rf_isInteger(asgn) || Rf_nrows(Sx) != n || LENGTH(asgn) != Rf_ncols(Sx))
+        Rf_error("model matrix / assign do not match the files");
+    const int p = Rf_ncols(Sx);
+    int nterms = 0;
+    for (int i = 0; i < p; ++i) if (INTEGER(asgn)[i] > nterms) nterms = INTEGER(asgn)[i];
+    const int masked = Rf_asReal(have_mask) == 1.0;
+    if (masked && (TYPEOF(mask) != STRSXP || Rf_length(mask) < 1)) Rf_error("mask must be a file name");
+    const int device = gpu_device();
+    long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+    if (ncpu < 1) ncpu = 1;
+    char err[512] = "";
+    rmg_minc2_volume *first = NULL;
+    rmg_minc2_info info;
+    int rc = rmg_minc2_open(CHAR(STRING_ELT(filenames, 0)), &first, err, sizeof err);
+    check(rc, err);
+    rmg_minc2_get_info(first, &info);
+    rmg_minc2_close(first);
+    const int64_t V = info.nvoxels, ld = V > 0 ? V : 1;
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, matrix_rows((R_xlen_t)V), nterms));
+    const char **paths = (const char **)R_alloc((size_t)n, sizeof(char *));
+    for (int j = 0; j < n; ++j) paths[j] = CHAR(STRING_ELT(filenames, j));
+    double *m = NULL;
+    if (masked) {
+        rmg_minc2_volume *mv = NULL;
+        rmg_minc2_info mi;
+        rc = rmg_minc2_open(CHAR(STRING_ELT(mask, 0)), &mv, err, sizeof err);
+        if (rc == RMG_OK) {
+            rmg_minc2_get_info(mv, &mi);
+            if (mi.nvoxels != V) {
+                rmg_minc2_close(mv);
+                UNPROTECT(1);
+                Rf_error("Mask Volume input volume dimension mismatch.");
+            }
+            m = (double *)R_alloc((size_t)ld, sizeof(double));
+            rc = rmg_minc2_read_real(mv, m, V, (int)ncpu, err, sizeof err);
+            rmg_minc2_close(mv);
+        }
+        if (rc != RMG_OK) {
+            UNPROTECT(1);
+            check(rc, err);
+        }
+    }
+    int pinned = 0;
+    void *A = staging_alloc((size_t)ld * n * sizeof(double), &pinned);
+    if (!A) { rc = RMG_ERR_INVALID; strcpy(err, "out of host memory while staging the volumes"); }
+    else rc = rmg_minc2_read_table(paths, n, A, ld, RMG_MINC2_F64, NULL, NULL, 1, NULL, (int)ncpu, err, sizeof err);
+    if (rc == RMG_OK && nterms > 0)
+        rc = rmg_anova_fit((const double *)A, V, ld, n, REAL(Sx), p, INTEGER(asgn), m, Rf_asReal(mask_lower), Rf_asReal(mask_upper),
+                           REAL(out), ld, device, err, sizeof err);
+    staging_free(A, pinned);
+    UNPROTECT(1);
+    check(rc, err);
+    return out;
+}
+
+
 /* kernel launches issued by the library since it was loaded: lets a test assert that a call really ran on the GPU */
 SEXP rmincgpu_launch_count(void)
 {
@@ -811,6 +875,7 @@ static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_dataset_randomize", (DL_FUNC)&rmincgpu_dataset_randomize, 5},
     {"rmincgpu_dataset_fdr", (DL_FUNC)&rmincgpu_dataset_fdr, 4},
     {"rmincgpu_minc2_model", (DL_FUNC)&rmincgpu_minc2_model, 11},
+    {"rmincgpu_per_voxel_anova", (DL_FUNC)&rmincgpu_per_voxel_anova, 7},
     {"rmincgpu_launch_count", (DL_FUNC)&rmincgpu_launch_count, 0},
     {NULL, NULL, 0}};
 

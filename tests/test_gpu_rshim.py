@@ -148,6 +148,18 @@ def test_minc2_model_routine_on_files_against_the_reference_routine(R, oracle, t
         finally:
             R.options(RMINC_GPU_N=None)
         assert_rows_match(got2, reference_minc2_model(R, Yq, dims, X, None, 1.0, 99999999.0), RTOL, "2 GPUs, stored type")
+    # per_voxel_anova with its own seven arguments on the same files, against the reference's routine on in-memory volumes
+    asg = np.array([0, 1], dtype=np.int32)
+    R.lib.rstub_clear_volumes()
+    vfiles = R.register_volumes("subject_", Yq, dims)
+    mcol = np.asfortranarray((mask * 2).reshape(-1, 1))
+    mreg = R.register_volumes("mask_", mcol, dims)
+    try:
+        ref_an = R.call("per_voxel_anova", vfiles, X, asg, 1.0, mreg, 1.0, 99999999.0)
+    finally:
+        R.lib.rstub_clear_volumes()
+    got_an = R.call("rmincgpu_per_voxel_anova", F, X, asg, 1.0, rcall.Strings([mfile]), 1.0, 99999999.0)
+    assert_rows_match(got_an, ref_an, RTOL, "per_voxel_anova on files")
     # filenames_right: the per-voxel design [mmatrix | z_v] (src/modelling_functions.c:848-854, 1137-1143)
     gotc = R.call("rmincgpu_minc2_model", F, rcall.Strings(f16), X[:, :1].copy(), None, 0.0, rcall.Strings([]), 1.0, 99999999.0, None, None,
                   rcall.Strings(["lm"]))

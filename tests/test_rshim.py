@@ -81,6 +81,8 @@ def every_routine_call(n=12, V=40):
         "rmincgpu_dataset_create": (Y, mask, 1.0, 99999999.0, 1),
         "rmincgpu_minc2_model": (rcall.Strings(minc2_study(U, scale, offset)), na, X, None, 0.0, rcall.Strings([]), 1.0, 99999999.0, None,
                                  None, rcall.Strings(["lm"])),
+        "rmincgpu_per_voxel_anova": (rcall.Strings(minc2_study(U, scale, offset)), X, np.array([0, 1, 2], dtype=np.int32), 0.0,
+                                     rcall.Strings([]), 1.0, 99999999.0),
     }
 
 
