@@ -247,3 +247,38 @@ def test_like_volume_and_mask_from_minc2_files(tmp_path):
     assert api.volume_dims(path) == (4, 5, 6)
     m = api._stage_mask(path, vol.size, api.default_reader)
     assert m.dtype == np.float64 and np.array_equal(m, vol.reshape(-1).astype(np.float64))
+
+
+def test_random_shapes_chunkings_and_filters(tmp_path):
+    """Property check over the writer's parameter space: any shape, chunking (ragged edges included), filter set, byte order
+    and B-tree fan-out reads back bit for bit, through one thread or several."""
+    rng = np.random.default_rng(2026)
+    dtypes = [np.uint8, np.int8, np.uint16, np.int16, np.uint32, np.int32, np.float32, np.float64]
+    for trial in range(60):
+        dt = np.dtype(dtypes[int(rng.integers(len(dtypes)))])
+        shape = tuple(int(rng.integers(1, 14)) for _ in range(3))
+        if dt.kind == "f":
+            vol = rng.normal(size=shape).astype(dt)
+            vr = None
+        else:
+            info = np.iinfo(dt)
+            vol = rng.integers(info.min, int(info.max) + 1, size=shape, dtype=dt)
+            vr = (float(info.min), float(info.max))
+        mode = int(rng.integers(3))
+        chunks = None if mode == 0 else tuple(int(rng.integers(1, s + 1)) for s in shape)
+        kw = dict(compress=None if mode == 1 else int(rng.integers(1, 10)), shuffle=bool(rng.integers(2)) and mode == 2,
+                  big_endian=bool(rng.integers(2)) and dt.itemsize > 1) if chunks else dict(big_endian=bool(rng.integers(2)) and dt.itemsize > 1)
+        per_slice = bool(rng.integers(2))
+        lo = rng.normal(size=shape[0]) if per_slice else np.float64(rng.normal())
+        hi = lo + rng.uniform(0.5, 2.0, size=np.shape(lo))
+        path = str(tmp_path / f"t{trial}.mnc")
+        tree = h5mini.minc2_tree(vol, image_min=lo, image_max=hi, valid_range=vr, chunks=chunks, **kw)
+        h5mini.write_h5(path, tree, leaf_k=int(rng.integers(1, 5)), chunk_k=int(rng.integers(1, 5)), split_headers=bool(rng.integers(2)),
+                        max_dims=bool(rng.integers(2)), user_block=int(rng.choice([0, 512, 2048])))
+        with minc2.Minc2Volume(path) as v:
+            assert v.sizes == shape and v.dtype == dt, (trial, shape, dt)
+            assert np.array_equal(v.stored(n_threads=int(rng.integers(1, 5))), vol), (trial, shape, dt, chunks, kw)
+            a, b = v.ranges()
+            assert np.array_equal(a, np.atleast_1d(lo)) and np.array_equal(b, np.atleast_1d(hi))
+            if dt.kind != "f":
+                assert np.array_equal(v.real(), expected_real(vol, lo, hi, vr)), (trial, shape, dt)
