@@ -440,6 +440,12 @@ int rmg_dataset_randomize(rmg_dataset *ds, const double *X, int p, const int32_t
                           int two_sided, double *dist, char *err, size_t errlen);
 int rmg_dataset_fdr(rmg_dataset *ds, int column, int stat_type, double df1, double df2, double *qvalues, double *thresholds,
                     char *err, size_t errlen);
+/* The other methods of mincFDR (R/minc_FDR.R:429-438; RMG_FDR_* and pi0 as rmg_fdr_method) and fast.qvalue's pi0 grid
+ * (mean(p >= lambda[i]), as rmg_fdr_pi0_fractions) on a column of the resident result. */
+int rmg_dataset_fdr_method(rmg_dataset *ds, int column, int stat_type, double df1, double df2, double *qvalues, double *thresholds,
+                           int method, double pi0, char *err, size_t errlen);
+int rmg_dataset_fdr_pi0_fractions(rmg_dataset *ds, int column, int stat_type, double df1, double df2, const double *lambda,
+                                  int nlambda, double *fractions, char *err, size_t errlen);
 /* Pinned host staging buffers (the ring of pageable uploads, the packed permutation operand) are kept across calls;
  * this returns every idle one to the OS. */
 void rmg_release_host_buffers(void);

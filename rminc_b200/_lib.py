@@ -95,6 +95,10 @@ SIGNATURES = {
     "rmg_dataset_anova": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64] + _ERR),
     "rmg_dataset_randomize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + _PERM + [C.c_void_p] + _ERR),
     "rmg_dataset_fdr": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p] + _ERR),
+    "rmg_dataset_fdr_method": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_double] + _ERR),
+    "rmg_dataset_fdr_pi0_fractions": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int,
+                                                C.c_void_p] + _ERR),
     "rmg_release_host_buffers": (None, []),
     "rmg_host_alloc": (C.c_void_p, [C.c_size_t]),
     "rmg_host_free": (None, [C.c_void_p]),

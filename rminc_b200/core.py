@@ -736,15 +736,26 @@ class Dataset:
         _lib.check(rc, err)
         return dist
 
-    def fdr(self, column, stat_type, df1, df2=0.0):
-        """mincFDR's native step on one column of the resident result of the last fit: (q-values [V], thresholds [5])."""
+    def fdr(self, column, stat_type, df1, df2=0.0, method="FDR", pi0=1.0):
+        """mincFDR's native step on one column of the resident result of the last fit: (q-values [V], thresholds [5]).
+        method / pi0 as core.fdr (R/minc_FDR.R:429-438)."""
         q = np.empty(self.V)
         th = np.empty(5)
         err = _lib.errbuf()
-        rc = _lib.load().rmg_dataset_fdr(self._h(), int(column), int(stat_type), float(df1), float(df2), q.ctypes.data,
-                                         th.ctypes.data, err, len(err))
+        rc = _lib.load().rmg_dataset_fdr_method(self._h(), int(column), int(stat_type), float(df1), float(df2), q.ctypes.data,
+                                                th.ctypes.data, int(FDR_METHODS[method]), float(pi0), err, len(err))
         _lib.check(rc, err)
         return q, th
+
+    def fdr_pi0_fractions(self, column, stat_type, df1, df2=0.0, lambdas=None):
+        """mean(p >= lambda) of the column's p-values (fast.qvalue's pi0 grid, R/minc_misc.R:439-441)."""
+        lam = np.ascontiguousarray(np.arange(0.0, 0.91, 0.05) if lambdas is None else lambdas, dtype=np.float64)
+        fr = np.empty(lam.size)
+        err = _lib.errbuf()
+        rc = _lib.load().rmg_dataset_fdr_pi0_fractions(self._h(), int(column), int(stat_type), float(df1), float(df2), lam.ctypes.data,
+                                                       int(lam.size), fr.ctypes.data, err, len(err))
+        _lib.check(rc, err)
+        return fr
 
     def close(self):
         if self._handle:

@@ -704,13 +704,16 @@ cleanup:
 
 // mincFDR on one column of the resident result of the last fit: the column is gathered on the first device (peer
 // copies; V doubles) and the one-GPU FDR runs there.
+// method < 0: instead of q-values, mean(p >= lambda[i]) of the column's p-values into `fractions` (the pi0 grid of fast.qvalue)
 int dataset_fdr(rmg_dataset *ds, int column, int stat_type, double df1, double df2, double *qvalues, double *thresholds,
-                char *err, size_t errlen)
+                char *err, size_t errlen, int method = RMG_FDR_BH, double pi0 = 1.0, const double *lambda = nullptr, int nlambda = 0,
+                double *fractions = nullptr)
 {
     std::lock_guard<std::mutex> lk(ds->mu);
     if (ds->out_cols == 0) return fail(err, errlen, RMG_ERR_INVALID, "no fitted result on this dataset yet: fit first");
     if (column < 0 || column >= ds->out_cols) return fail(err, errlen, RMG_ERR_INVALID, "column %d out of range (the result has %d)", column, ds->out_cols);
-    if (!qvalues) return fail(err, errlen, RMG_ERR_INVALID, "qvalues is NULL");
+    if (method >= 0 && !qvalues) return fail(err, errlen, RMG_ERR_INVALID, "qvalues is NULL");
+    if (method < 0 && (!lambda || !fractions || nlambda < 1)) return fail(err, errlen, RMG_ERR_INVALID, "lambda / fractions missing");
     if (ds->V == 0) return RMG_OK;
     int rc = RMG_OK;
     DsShard &s0 = ds->sh[0];
@@ -741,9 +744,18 @@ int dataset_fdr(rmg_dataset *ds, int column, int stat_type, double df1, double d
             stat = dcol;
             dmask = ds->dMaskFull;
         }
-        if ((rc = rmg_fdr_device(stat, ds->V, stat_type, df1, df2, dmask, dq, thresholds, s0.device, s0.st, err, errlen))) goto cleanup;
-        RMG_CUDA(cudaMemcpyAsync(qvalues, dq, (size_t)ds->V * 8, cudaMemcpyDeviceToHost, s0.st));
-        RMG_CUDA(cudaStreamSynchronize(s0.st));
+        if (method < 0) {
+            if ((rc = rmg_fdr_pi0_fractions_device(stat, ds->V, stat_type, df1, df2, dmask, lambda, nlambda, fractions, s0.device, s0.st,
+                                                   err, errlen)))
+                goto cleanup;
+            RMG_CUDA(cudaStreamSynchronize(s0.st));
+        } else {
+            if ((rc = rmg_fdr_method_device(stat, ds->V, stat_type, df1, df2, dmask, dq, thresholds, method, pi0, s0.device, s0.st, err,
+                                            errlen)))
+                goto cleanup;
+            RMG_CUDA(cudaMemcpyAsync(qvalues, dq, (size_t)ds->V * 8, cudaMemcpyDeviceToHost, s0.st));
+            RMG_CUDA(cudaStreamSynchronize(s0.st));
+        }
     }
 cleanup:
     cudaSetDevice(s0.device);
@@ -845,6 +857,21 @@ int rmg_dataset_fdr(rmg_dataset *ds, int column, int stat_type, double df1, doub
 {
     if (!ds) return fail(err, errlen, RMG_ERR_INVALID, "ds is NULL");
     return dataset_fdr(ds, column, stat_type, df1, df2, qvalues, thresholds, err, errlen);
+}
+
+int rmg_dataset_fdr_method(rmg_dataset *ds, int column, int stat_type, double df1, double df2, double *qvalues, double *thresholds,
+                           int method, double pi0, char *err, size_t errlen)
+{
+    if (!ds) return fail(err, errlen, RMG_ERR_INVALID, "ds is NULL");
+    if (method < RMG_FDR_BH || method > RMG_FDR_QVALUE) return fail(err, errlen, RMG_ERR_INVALID, "unknown FDR method %d", method);
+    return dataset_fdr(ds, column, stat_type, df1, df2, qvalues, thresholds, err, errlen, method, pi0);
+}
+
+int rmg_dataset_fdr_pi0_fractions(rmg_dataset *ds, int column, int stat_type, double df1, double df2, const double *lambda,
+                                  int nlambda, double *fractions, char *err, size_t errlen)
+{
+    if (!ds) return fail(err, errlen, RMG_ERR_INVALID, "ds is NULL");
+    return dataset_fdr(ds, column, stat_type, df1, df2, nullptr, nullptr, err, errlen, -1, 1.0, lambda, nlambda, fractions);
 }
 
 void rmg_release_host_buffers(void) { pinned_trim(); }

@@ -63,6 +63,14 @@ def test_fit_randomize_anova_fdr_on_one_upload(core, oracle):
             np.testing.assert_allclose(th[~np.isnan(wth)], wth[~np.isnan(wth)], rtol=1e-8)
             qf, _ = ds.fdr(0, core.STAT_F, 1, n - 2)
             np.testing.assert_allclose(qf, oracle.fdr(want_fit[:, 0], "F", 1, n - 2, mask=mask)[0], rtol=RTOL, atol=0)
+            # the other methods of mincFDR and fast.qvalue's pi0 grid on the resident column (R/minc_FDR.R:429-438)
+            fr = ds.fdr_pi0_fractions(5, core.STAT_T, n - 2)
+            np.testing.assert_allclose(fr, core.fdr_pi0_fractions(got[:, 5], core.STAT_T, n - 2, mask=mask), rtol=1e-12, atol=0)
+            for method, pi0 in (("BY", 1.0), ("pFDR", 0.8), ("qvalue", 0.8)):
+                qm, thm = ds.fdr(5, core.STAT_T, n - 2, method=method, pi0=pi0)
+                wm, wthm, _ = oracle.fdr(want_fit[:, 5], "t", n - 2, mask=mask, method=method, pi0=pi0)
+                np.testing.assert_allclose(qm, wm, rtol=RTOL, atol=0, err_msg=method)
+                assert np.array_equal(np.isnan(thm), np.isnan(wthm)), method
             a = ds.anova(X, [0, 1])
             assert_rows_match(a, core.anova_fit(Y, X, [0, 1], mask=mask), RTOL, f"dataset anova G={G}")
             with pytest.raises(core.RmincGpuError, match="out of range"):
