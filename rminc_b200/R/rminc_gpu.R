@@ -290,8 +290,14 @@ rmincgpu_dataset_randomize <- function(ds, lmod, R = 500, replace = FALSE, colum
 }
 
 # mincFDR's per-column step on the result of the LAST fit on the handle (column: its 1-based column number)
-rmincgpu_dataset_fdr <- function(ds, column, stat_type, df) {
-  res <- .Call("rmincgpu_dataset_fdr", ds$handle, as.integer(column), if (stat_type == "F") 2L else 1L, as.double(df),
-               PACKAGE = "rmincgpu")
+# method as mincFDR's (R/minc_FDR.R:429-438): "FDR" / "p.adjust", "BY", "pFDR" / "fastqvalue", "qvalue"; pi0 for the last two
+rmincgpu_dataset_fdr <- function(ds, column, stat_type, df, method = "FDR", pi0 = 1) {
+  st <- if (stat_type == "F") 2L else 1L
+  if (method %in% c("FDR", "p.adjust"))
+    res <- .Call("rmincgpu_dataset_fdr", ds$handle, as.integer(column), st, as.double(df), PACKAGE = "rmincgpu")
+  else
+    res <- .Call("rmincgpu_dataset_fdr_method", ds$handle, as.integer(column), st, as.double(df),
+                 switch(method, BY = 1L, pFDR = 2L, fastqvalue = 2L, qvalue = 3L, stop("unknown FDR method")), as.double(pi0),
+                 PACKAGE = "rmincgpu")
   list(qvalue = res[[1]], thresholds = res[[2]])
 }

@@ -632,6 +632,30 @@ SEXP rmincgpu_dataset_fdr(SEXP h, SEXP column, SEXP stat_type, SEXP df)
     return out;
 }
 
+/* The other methods of mincFDR on the resident column: method 0 = FDR / p.adjust, 1 = BY, 2 = pFDR / fastqvalue, 3 = qvalue
+ * (R/minc_FDR.R:429-438), pi0 for the last two. */
+SEXP rmincgpu_dataset_fdr_method(SEXP h, SEXP column, SEXP stat_type, SEXP df, SEXP method, SEXP pi0)
+{
+    rmg_dataset *ds = dataset_of(h);
+    if (!Rf_isReal(df) || LENGTH(df) < 1) Rf_error("df must be a double vector");
+    const R_xlen_t V = (R_xlen_t)rmg_dataset_voxels(ds);
+    SEXP q = PROTECT(Rf_allocVector(REALSXP, V));
+    SEXP th = PROTECT(Rf_allocVector(REALSXP, 5));
+    char err[512] = "";
+    int rc = rmg_dataset_fdr_method(ds, count_arg(column, "column") - 1, count_arg(stat_type, "stat_type"), REAL(df)[0],
+                                    LENGTH(df) > 1 ? REAL(df)[1] : 0.0, REAL(q), REAL(th), count_arg(method, "method"),
+                                    Rf_asReal(pi0), err, sizeof err);
+    if (rc != RMG_OK) {
+        UNPROTECT(2);
+        check(rc, err);
+    }
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, q);
+    SET_VECTOR_ELT(out, 1, th);
+    UNPROTECT(3);
+    return out;
+}
+
 /* ---------------------------------------------------------------------------------------------------------------------
  * minc2_model itself, method "lm", with the reference's own eleven arguments (src/modelling_functions.c:743-745; R caller
  * mincLm_c_wrapper, R/minc_voxel_statistics.R:695-712): the .Call a maintainer can swap without staging anything in R.
@@ -874,6 +898,7 @@ static const R_CallMethodDef callMethods[] = {
     {"rmincgpu_dataset_anova", (DL_FUNC)&rmincgpu_dataset_anova, 3},
     {"rmincgpu_dataset_randomize", (DL_FUNC)&rmincgpu_dataset_randomize, 5},
     {"rmincgpu_dataset_fdr", (DL_FUNC)&rmincgpu_dataset_fdr, 4},
+    {"rmincgpu_dataset_fdr_method", (DL_FUNC)&rmincgpu_dataset_fdr_method, 6},
     {"rmincgpu_minc2_model", (DL_FUNC)&rmincgpu_minc2_model, 11},
     {"rmincgpu_per_voxel_anova", (DL_FUNC)&rmincgpu_per_voxel_anova, 7},
     {"rmincgpu_launch_count", (DL_FUNC)&rmincgpu_launch_count, 0},

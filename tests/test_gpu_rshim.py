@@ -282,6 +282,8 @@ def test_dataset_routines_and_the_finalizer(R, oracle):
                                    oracle.randomize(Y, X, idx, [4, 5], mask=mask), rtol=RTOL, atol=0)
         q, th = R.call("rmincgpu_dataset_fdr", h, 6, 1, np.array([float(n - 2)]))
         np.testing.assert_allclose(q, oracle.fdr(want[:, 5], "t", n - 2, mask=mask)[0], rtol=RTOL, atol=0)
+        qb, _ = R.call("rmincgpu_dataset_fdr_method", h, 6, 1, np.array([float(n - 2)]), 1, 1.0)          # "BY"
+        np.testing.assert_allclose(qb, oracle.fdr(want[:, 5], "t", n - 2, mask=mask, method="BY")[0], rtol=RTOL, atol=0)
         a = R.call("rmincgpu_dataset_anova", h, X, np.array([0, 1], dtype=np.int32))
         assert_rows_match(a, core.anova_fit(Y, X, [0, 1], mask=mask), RTOL, "dataset_anova")
         if G == 1:

@@ -111,7 +111,7 @@ def test_every_routine_runs_and_raises_the_no_device_error(R):
     calls = every_routine_call()
     registered = dict(R.routines())
     handle_routines = {"rmincgpu_dataset_free", "rmincgpu_dataset_lm", "rmincgpu_dataset_anova", "rmincgpu_dataset_randomize",
-                       "rmincgpu_dataset_fdr"}
+                       "rmincgpu_dataset_fdr", "rmincgpu_dataset_fdr_method"}
     assert R.call("rmincgpu_launch_count")[0] == 0          # host-only: works without a device, nothing was launched
     for name in registered:
         if name.startswith("rmincgpu_") and name not in handle_routines and name != "rmincgpu_launch_count":
