@@ -111,6 +111,7 @@ struct PackedArgs {
     int64_t slice_len, nslices, v_base;
     int out_vec2 = 0;
     int zero = 0;              // always 0: a kernel parameter the compiler cannot fold (low words of built doubles)
+    int shift_mode = 0;        // FOLD kernels: 0 = tiles / warps vote for per-voxel shifts, 1 = never, 2 = always (RMG_STORED_SHIFT)
 };
 
 cudaError_t launch_lm_packed(const PackedArgs &a, const LmPlan &plan, LmScratch &scr, cudaStream_t st, LmLaunchInfo *info);

@@ -635,13 +635,46 @@ lm_fit_packed_quads_kernel(PackedArgs a, const uint32_t *__restrict__ list, cons
         sum[i].yy = 0.0;
         sum[i].y0 = 0.0;
     }
-    // ONE shift per quad: the value of its first voxel in the first subject (the exact recomputation uses the same one)
-    double shift = 0.0;
-    if (sd.shift && have) {
-        shift = Stored<T>::load1(U + v, cm);
-        if (SC) shift = descale(shift, __ldg(a.scale + sl[0]), __ldg(a.offset + sl[0]));
-    }
+    // ONE shift per quad: the value of its first voxel in the first subject -- unless a voxel of the quad lies far from it
+    // next to its spread over the first subjects (an edge inside the quad: see the TMA variant); then the WARP takes the
+    // per-voxel form of the loop (one more subtraction per sample), so that such voxels do not all end in the explicit-residual
+    // path.
     const T *up = U + v;
+    double shift = 0.0, dlt[4] = {0.0, 0.0, 0.0, 0.0};
+    bool far = false;
+    // Every value below is formed EXACTLY as the loop forms it, so that a voxel with one value in every subject gives y' = 0 bit
+    // for bit (its rss = 0 classes, without the exact path).  The three-rounding and float32 forms subtract per sample anyway:
+    // they always take per-voxel shifts (shift = 0, dlt[i] = the voxel's first sample).
+    if (sd.shift && have) {
+        const int nv0 = min(8, n);
+        double var[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int j = 0; j < nv0; ++j) {
+            const typename Stored<T>::Raw raw = load_raw_64b<T>(up + (int64_t)j * a.ldU);
+            double y[4];
+            if constexpr (FD) unit20_from_raw(raw, y);
+            else Stored<T>::convert(raw, y, cm);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double t = y[i];
+                if constexpr (FD) {
+                    const double sc = __ldg(a.scale + sl[i] + (int64_t)j * a.nslices), of = __ldg(a.offset + sl[i] + (int64_t)j * a.nslices);
+                    const double cc = fma(-sc, vmin1, of);
+                    if (j == 0 && i == 0) shift = fma(sc * kOne, t, cc);
+                    t = fma(sc * kOne, t, cc - shift);
+                } else if (SC) {
+                    t = descale(t, __ldg(a.scale + sl[i] + (int64_t)j * a.nslices), __ldg(a.offset + sl[i] + (int64_t)j * a.nslices));
+                }
+                if (j == 0) dlt[i] = t;
+                const double d = t - dlt[i];
+                var[i] = fma(d, d, var[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) far |= dlt[i] * dlt[i] * (double)nv0 > 50.0 * var[i];
+    }
+    const bool per_voxel = !FD || a.shift_mode == 2 || (a.shift_mode == 0 && __any_sync(0xffffffffu, far));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dlt[i] = per_voxel ? dlt[i] : 0.0;         // voxel i's shift is shift + dlt[i] from here on
     constexpr int UNR = 8;
 
     for (int t0 = 0; t0 < n; t0 += JT) {
@@ -662,8 +695,9 @@ lm_fit_packed_quads_kernel(PackedArgs a, const uint32_t *__restrict__ list, cons
         __syncthreads();
         if (!have) continue;
 
-        auto run = [&](auto fast_tag) {
+        auto run = [&](auto fast_tag, auto pv_tag) {
             constexpr bool FAST = decltype(fast_tag)::value;
+            constexpr bool PV = decltype(pv_tag)::value;
             auto accumulate = [&](int jj, const typename Stored<T>::Raw &raw) {
                 const double *row = sQ + jj * QW;
                 double yv[4];
@@ -674,13 +708,16 @@ lm_fit_packed_quads_kernel(PackedArgs a, const uint32_t *__restrict__ list, cons
                         const double2 so = *reinterpret_cast<const double2 *>(row + tsel);
                         const double cs = so.y - shift;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) yv[i] = fma(so.x, w[i], cs);
+                        for (int i = 0; i < 4; ++i) {
+                            yv[i] = fma(so.x, w[i], cs);
+                            if (PV) yv[i] -= dlt[i];
+                        }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const double sc = __ldg(a.scale + sl[i] + (int64_t)(t0 + jj) * a.nslices);
                             const double of = __ldg(a.offset + sl[i] + (int64_t)(t0 + jj) * a.nslices);
-                            yv[i] = fma(sc * kOne, w[i], fma(-sc, vmin1, of) - shift);
+                            yv[i] = fma(sc * kOne, w[i], fma(-sc, vmin1, of) - shift) - dlt[i];
                         }
                     }
                 } else {
@@ -701,7 +738,7 @@ lm_fit_packed_quads_kernel(PackedArgs a, const uint32_t *__restrict__ list, cons
                             }
                             t = descale(t, sc, of);
                         }
-                        yv[i] = t - shift;
+                        yv[i] = t - (shift + dlt[i]);
                     }
                 }
 #pragma unroll
@@ -729,8 +766,9 @@ lm_fit_packed_quads_kernel(PackedArgs a, const uint32_t *__restrict__ list, cons
             }
             for (; jj < cnt; ++jj) accumulate(jj, load_raw_64b<T>(up + (int64_t)(t0 + jj) * a.ldU));
         };
-        if (fast) run(std::true_type{});
-        else run(std::false_type{});
+        if (fast && !(FD && per_voxel)) run(std::true_type{}, std::false_type{});
+        else if (fast) run(std::true_type{}, std::true_type{});
+        else run(std::false_type{}, std::false_type{});
     }
     if (!have) return;
 
@@ -738,11 +776,11 @@ lm_fit_packed_quads_kernel(PackedArgs a, const uint32_t *__restrict__ list, cons
     double rss[4], mss[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        sum[i].y0 = shift;
+        sum[i].y0 = shift + dlt[i];
         rss[i] = sum[i].yy - sumsq_e(sum[i]);
         mss[i] = mss_from_e(sum[i], sd);
         if (act[i] && rss[i] <= kExactThreshold * sum[i].yy && sum[i].yy > 0.0) {
-            const double2 ex = exact_pass_packed<KP, T>(U + v + i, a.ldU, n, a.Qt, shift, cm, a.scale + sl[i], a.offset + sl[i],
+            const double2 ex = exact_pass_packed<KP, T>(U + v + i, a.ldU, n, a.Qt, sum[i].y0, cm, a.scale + sl[i], a.offset + sl[i],
                                                         a.nslices);
             rss[i] = ex.x;
             mss[i] = ex.y;
@@ -884,14 +922,55 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
         // FOLD = 2: ONE shift per thread (the first sample of its first voxel) is folded into the offsets, C_j - shift being
         // formed once per subject and thread instead of one subtraction per sample; adjacent voxels differ little next to
         // their spread, and a voxel whose shifted |y|^2 still dwarfs its rss is redone from explicit residuals below.
-        double shift = 0.0;
+        // ... WHEN adjacent voxels differ little next to their spread.  Where they do not -- a tissue / background edge
+        // inside a thread's 4 voxels of an intensity image -- the one-pass sums of the far voxels would lose their digits and
+        // those voxels would all take the explicit-residual path (measured: 26 ms instead of 2.1 ms with an edge in every 16th
+        // quad).  So the first stage of the tile is looked at before it is consumed: per voxel, the offset dlt of its first
+        // sample from the thread's shift against its spread over the stage's subjects; if any voxel of the tile is far out
+        // (dlt^2 > 100 x variance: ten times inside the 1000 x rss rule of the epilogue) the consumers of the CTA vote the
+        // tile into the per-voxel form of the loop (one more subtraction per sample: 28 instead of 25 FP64 per 4 samples).
+        double shift = 0.0, dlt[VPT];
+        bool per_voxel = false;
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) dlt[i] = 0.0;
         if constexpr (FOLD == 2) {
             if (sd.shift) {
                 mbar_wait(&full[stage], phase);          // the loop below waits for the same phase again: it passes at once
                 const unsigned char *st = ring + (size_t)stage * STAGE_B;
-                load_unit20_smem<VPT>(reinterpret_cast<const uint16_t *>(st) + boff, wp, kexp);
-                const double2 so = reinterpret_cast<const double2 *>(st + DATA_B)[sel[0] * NJ];
-                shift = fma(so.x, wp[0], so.y);
+                const uint16_t *mine0 = reinterpret_cast<const uint16_t *>(st) + boff;
+                const double2 *tabs0 = reinterpret_cast<const double2 *>(st + DATA_B);
+                const int nv0 = min(NJ, n);
+                double var[VPT];
+#pragma unroll
+                for (int i = 0; i < VPT; ++i) var[i] = 0.0;
+                // dlt[i] = voxel i's first sample EXACTLY as the loop will form it (the same fused multiply-add with the same
+                // shifted offset): a voxel with one value in every subject then gives y' = 0 bit for bit in the per-voxel form
+                // (or already here, when dlt is 0), its |y'|^2 is 0 and it keeps its rss = 0 classes without the exact path
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) {
+                    if (jj < nv0) {
+                        load_unit20_smem<VPT>(mine0 + jj * BOXW, wp, kexp);
+                        if (jj == 0) {
+                            const double2 so = tabs0[sel[0] * NJ];
+                            shift = fma(so.x, wp[0], so.y);
+                        }
+#pragma unroll
+                        for (int i = 0; i < VPT; ++i) {
+                            const double2 so = tabs0[sel[i] * NJ + jj];
+                            const double tv = fma(so.x, wp[i], so.y - shift);
+                            if (jj == 0) dlt[i] = tv;
+                            const double d = tv - dlt[i];
+                            var[i] = fma(d, d, var[i]);
+                        }
+                    }
+                }
+                bool far = false;
+#pragma unroll
+                for (int i = 0; i < VPT; ++i) far |= dlt[i] * dlt[i] * (double)nv0 > 50.0 * var[i];       // var ~ 2 nv0 sigma^2
+                int voted;
+                asm volatile("{ .reg .pred p, q; setp.ne.s32 q, %1, 0; bar.red.or.pred p, 1, %2, q; selp.s32 %0, 1, 0, p; }"
+                             : "=r"(voted) : "r"((int)far), "r"(CW * 32) : "memory");
+                per_voxel = a.shift_mode == 2 || (a.shift_mode == 0 && voted != 0);
             }
         }
         for (int it = 0; it < nit; ++it) {
@@ -901,9 +980,10 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
             const double2 *tabs = reinterpret_cast<const double2 *>(st + DATA_B);
             const double *q = sQ + (size_t)it * NJ * KP;
             const int nvalid = min(NJ, n - it * NJ);      // rows >= n of the last box are TMA zero-fill: skipped
-            auto run = [&](auto same_tag, auto full_tag) {
+            auto run = [&](auto same_tag, auto full_tag, auto pv_tag) {
                 constexpr bool SAME = decltype(same_tag)::value;
                 constexpr bool FULL = decltype(full_tag)::value;     // all NJ rows real: no per-row test in the hot loop
+                constexpr bool PV = decltype(pv_tag)::value;         // per-voxel shifts (FOLD = 2, a tile with far-out voxels)
 #pragma unroll
                 for (int jj = 0; jj < NJ; ++jj) {
                     if (FULL || jj < nvalid) {
@@ -931,6 +1011,8 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
                             if constexpr (FOLD != 2) {
                                 if (it == 0 && jj == 0 && sd.shift) sum[i].y0 = tv;
                                 yv = tv - sum[i].y0;
+                            } else if constexpr (PV) {
+                                yv = tv - dlt[i];
                             }
                             sum[i].yy = fma(yv, yv, sum[i].yy);
 #pragma unroll
@@ -939,11 +1021,14 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
                     }
                 }
             };
-            if (same) {
-                if (nvalid == NJ) run(std::true_type{}, std::true_type{});
-                else run(std::true_type{}, std::false_type{});
+            if (FOLD == 2 && per_voxel) {
+                if (same && nvalid == NJ) run(std::true_type{}, std::true_type{}, std::true_type{});
+                else run(std::false_type{}, std::false_type{}, std::true_type{});
+            } else if (same) {
+                if (nvalid == NJ) run(std::true_type{}, std::true_type{}, std::false_type{});
+                else run(std::true_type{}, std::false_type{}, std::false_type{});
             } else {
-                run(std::false_type{}, std::false_type{});
+                run(std::false_type{}, std::false_type{}, std::false_type{});
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
@@ -951,7 +1036,7 @@ lm_fit_packed_tma_kernel(const __grid_constant__ CUtensorMap umap, PackedArgs a,
         }
         if constexpr (FOLD == 2) {
 #pragma unroll
-            for (int i = 0; i < VPT; ++i) sum[i].y0 = shift;
+            for (int i = 0; i < VPT; ++i) sum[i].y0 = per_voxel ? shift + dlt[i] : shift;
         }
         // ---- fused epilogue
         const int64_t v = (int64_t)t * TV + VPT * tid;
@@ -1173,6 +1258,8 @@ cudaError_t launch_lm_packed(const PackedArgs &a_in, const LmPlan &plan, LmScrat
     if (a_in.V <= 0) return cudaSuccess;
     PackedArgs a = a_in;
     a.out_vec2 = ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && a.ldOut % 2 == 0) ? 1 : 0;
+    static const int env_shift_mode = [] { const char *s_ = std::getenv("RMG_STORED_SHIFT"); return s_ ? std::atoi(s_) : 0; }();
+    a.shift_mode = env_shift_mode;
     switch (lm_padded_p(a.p)) {
 #define RMG_CASE(K) case K: return launch_packed_kp<K>(a, plan, scr, st, info);
 #ifdef RMG_QUICK_KP4      // developer switch: compile the p = 4 instances only (SASS inspection in seconds)

@@ -676,6 +676,41 @@ def test_stored_degenerate_and_near_perfect_voxels(core, oracle):
     assert_rows_match(got[~const], want[~const], RTOL, "quantised")
 
 
+@pytest.mark.parametrize("masked", [False, True])
+def test_stored_fit_with_edges_inside_a_threads_voxels(core, oracle, masked):
+    """An intensity image with tissue / background transitions: every 7th voxel is background (about 100 +- 30 counts next to
+    30000 +- 400), every file has the same real range, so a voxel's spread is a fraction of a percent of the step to its
+    neighbour.  The one-shift-per-thread arithmetic cannot serve such quads: the tile (TMA variant) or the warp (compacted
+    quads, with a mask) votes itself into per-voxel shifts.  Either way the result equals the oracle's."""
+    rng = np.random.default_rng(31)
+    V, n = 80128, 40
+    X = design_cfg2(n)
+    U = np.clip(rng.normal(30000, 400, (V, n)) + 300.0 * np.outer(rng.random(V), X[:, 1]), 0, 65535)
+    U[::7] = rng.normal(100, 30, (len(U[::7]), n)).clip(0, 65535)
+    U[5::11] = 0                                                            # and constant voxels in between
+    U = np.asfortranarray(np.round(U).astype(np.uint16))
+    nsl, slice_len = 8, 10016
+    scale = np.full((nsl, n), 2.0 / 65535.0)
+    offset = np.full((nsl, n), -0.8)
+    Y = oracle.expand_stored(U, scale, offset, slice_len=slice_len)
+    mask = None
+    if masked:
+        mask = (rng.random(V) < 0.6).astype(float)
+        mask[1000:3000] = 0
+    got = core.lm_fit_stored(U, X, scale, offset, slice_len=slice_len, mask=mask)
+    if not masked:
+        assert core.last_fit_variant() == "lm_fit_packed_tma_kernel"
+    want = oracle.minc2_model_lm(Y, (1, 1, V), X, mask=mask) if masked else oracle.vertex_lm_loop(Y, X)
+    const = np.zeros(V, bool)
+    const[5::11] = True
+    inside = np.ones(V, bool) if mask is None else mask > 0.5
+    ok = inside & ~const
+    assert_rows_match(got[ok], want[ok], RTOL, f"edges, masked={masked}")
+    assert np.isposinf(got[inside & const, -1]).all()                       # exact rss = 0 classes (SURVEY A.4)
+    if masked:
+        assert (got[~inside] == 0).all()
+
+
 def test_stored_device_entry_point(core, oracle):
     import torch
     U, X, scale, offset = _stored_case(8192, 50, 1024, seed=21)
