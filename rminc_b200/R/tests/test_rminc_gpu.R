@@ -52,6 +52,10 @@ test_that("mincAnova F columns", {
   got <- per_voxel_anova_gpu(as.character(gf$jacobians_fixed_2), X, mask)
   inside <- mincGetVolume(mask) > 0.5
   expect_equal(got[inside, ], unclass(ref)[inside, ], tolerance = tol, check.attributes = FALSE)
+  old <- options(RMINC_GPU_READER = TRUE)             # per_voxel_anova's own arguments, files read by the library
+  got2 <- per_voxel_anova_gpu(as.character(gf$jacobians_fixed_2), X, mask)
+  options(old)
+  expect_equal(got2[inside, ], unclass(ref)[inside, ], tolerance = tol, check.attributes = FALSE)
 })
 
 test_that("mincRandomize: same null as the R loop for the same seed", {
