@@ -8,6 +8,8 @@
 // checks it against zlib's own compressor output at every level and strategy, on noise, images, runs and empty input, and against
 // truncated / damaged streams (tests/test_minc2_reader.py).  The reader falls back to zlib's uncompress if this decoder
 // reports an error, so a stream it cannot handle costs time, never correctness.
+// Measured and dropped: a 12-bit primary table whose entries carry two literals where both codes fit the index -- the per-block
+// pairing pass and the wider entries cost more than the saved look-ups (154 against 182 MB/s on noise-like uint16 samples).
 #pragma once
 #include <cstdint>
 #include <cstring>
